@@ -1,0 +1,730 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A thin driver around the UNMODIFIED reference encoder (mpeg5/xeve, Baseline profile),
+ * compiled against the reference's own headers where they lie under /root/reference and
+ * linked with oracle/_ref/libxeveb_ref.so (see oracle/Makefile.ref).  It does three things:
+ *
+ *   1. probes   -- call the reference's kernel tables (C / SSE / AVX2 variants) on caller
+ *                  buffers: SAD, SSD, DIFF, SATD, luma/chroma MC, fwd/inv transform stages;
+ *   2. tracing  -- run a real encode through the public API with logging wrappers installed on
+ *                  the reference's own operator hooks (pi->fn_me, pi->fn_mc, ctx->fn_tq; see
+ *                  reference src_base/xeve_type.h:448-453, 981-982) and record every call's
+ *                  inputs (the "work list") plus outputs / output hashes;
+ *   3. replay   -- run the reference's functions over a work list on N host threads: this is
+ *                  both the expected-output generator for the parity tests and the CPU arm
+ *                  (`bench.py --impl reference`, cpu_baseline.kind = "reference").
+ *
+ * Everything in this file is original harness code; the reference is used only through its
+ * headers, exported symbols and function-pointer hooks.
+ */
+#define _GNU_SOURCE
+#include "xeve_type.h"
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define RH_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * record layouts (mirrored as numpy dtypes in xeve_b200/refharness.py)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t  poc;           /* POC of the picture being coded */
+    int32_t  cur_pic;       /* index into the picture table (original picture) */
+    int32_t  ref_pic;       /* index into the picture table (reference picture) */
+    int32_t  ref_poc;
+    int16_t  x, y;
+    uint8_t  log2w, log2h, lidx, bi;
+    int8_t   refi;
+    uint8_t  num_refp;
+    int16_t  mvp[2];
+    int16_t  mv_in[2];
+    uint32_t lambda_mv;
+    int32_t  mot_bits_in[2];
+    int32_t  max_search_range;
+    int32_t  gop_size;
+    int32_t  org_bi_off;    /* element offset into the s16 side buffer, -1 if bi == 0 */
+    /* outputs */
+    int16_t  mv_out[2];
+    uint32_t cost;
+    int32_t  mot_bits_out[2];
+} RH_ME_REC; /* 72 bytes */
+
+typedef struct {
+    int32_t  poc;
+    int32_t  ref_pic[2];    /* picture-table index per list, -1 if refi invalid */
+    int32_t  ref_poc[2];
+    int16_t  x, y, w, h;
+    int8_t   refi[2];
+    int16_t  mv[2][2];
+    uint64_t out_hash;      /* FNV-1a over pred[0] Y,U,V as produced in situ */
+} RH_MC_REC;
+
+typedef struct {
+    int32_t  poc;
+    uint8_t  log2w, log2h, slice_type, is_intra;
+    uint8_t  run_stats, qp[3];
+    int32_t  rate_idx;      /* index into the rate-table array */
+    int64_t  in_off;        /* element offset of the 3 input planes (Y: w*h, U,V: w*h/4 each) */
+    double   lambda[3];
+    int32_t  nnz[3];
+    uint64_t out_hash;      /* FNV-1a over the three output planes */
+} RH_TQ_REC;
+
+typedef struct {
+    int32_t cbf_all[2], cbf_luma[2], cbf_cb[2], cbf_cr[2];
+    int32_t run[NUM_CTX_CC_RUN][2];
+    int32_t level[NUM_CTX_CC_LEVEL][2];
+    int32_t last[NUM_CTX_CC_LAST][2];
+} RH_RATES;
+
+typedef struct {
+    int32_t poc, kind;      /* kind 0 = original, 1 = reconstructed reference (padded) */
+    int32_t w_l, h_l, w_c, h_c, s_l, s_c, pad_l, pad_c;
+    int64_t off_y, off_u, off_v; /* element offsets of the *buffer start* (incl. padding) */
+} RH_PIC;
+
+typedef struct {            /* planes handed in by the caller for replay */
+    int16_t *y, *u, *v;     /* top-left of the active area */
+    int32_t  s_l, s_c, w_l, h_l, poc;
+} RH_PLANES;
+
+typedef struct {
+    int32_t w, h, bit_depth, me_level, hpel_cnt, qpel_cnt, me_complexity;
+    int32_t min_clip[2], max_clip[2];
+    int32_t merge_num, me_range, gop_size, rdoq, tool_iqt;
+} RH_CONST;
+
+/* ------------------------------------------------------------------------------------------
+ * growable buffers
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { void *p; size_t n, cap, esz; } vec_t;
+static void *vec_push(vec_t *v, size_t cnt)
+{
+    if(v->n + cnt > v->cap) {
+        size_t nc = v->cap ? v->cap * 2 : 1024;
+        while(nc < v->n + cnt) nc *= 2;
+        v->p   = realloc(v->p, nc * v->esz);
+        v->cap = nc;
+    }
+    void *r = (char *)v->p + v->n * v->esz;
+    v->n += cnt;
+    return r;
+}
+static void vec_reset(vec_t *v, size_t esz) { v->n = 0; v->esz = esz; }
+
+static uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
+{
+    const uint8_t *p = data;
+    for(size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+#define FNV_INIT 0xcbf29ce484222325ULL
+
+/* ------------------------------------------------------------------------------------------
+ * trace state
+ * ---------------------------------------------------------------------------------------- */
+enum { RH_T_ME = 1, RH_T_MC = 2, RH_T_TQ = 4 };
+
+static struct {
+    XEVE_CTX *ctx;
+    int       mask, pic_lo, pic_hi; /* record while pic_lo <= ctx->pic_cnt <= pic_hi */
+    u32 (*org_me)(XEVE_PINTER *, int, int, int, int, s8 *, int, s16 *, s16 *, int, int);
+    void (*org_mc)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, s8 *, s16 (*)[MV_D], XEVE_REFP (*)[REFP_NUM],
+                   pel (*)[N_C][MAX_CU_DIM], int, int, s16 (*)[REFP_NUM][MV_D]);
+    int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int);
+    vec_t    me, mc, tq, rates, pics, samp; /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
+    RH_CONST cst;
+    RH_RATES last_rates;
+    int      have_rates;
+} T;
+
+static int tracing(int kind)
+{
+    if(!(T.mask & kind) || !T.ctx) return 0;
+    int c = (int)T.ctx->pic_cnt;
+    return c >= T.pic_lo && c <= T.pic_hi;
+}
+
+static int find_or_add_pic(XEVE_PIC *pic, int poc, int kind)
+{
+    RH_PIC *tab = T.pics.p;
+    for(size_t i = 0; i < T.pics.n; i++)
+        if(tab[i].poc == poc && tab[i].kind == kind) return (int)i;
+    RH_PIC r;
+    memset(&r, 0, sizeof(r));
+    r.poc = poc; r.kind = kind;
+    r.w_l = pic->w_l; r.h_l = pic->h_l; r.w_c = pic->w_c; r.h_c = pic->h_c;
+    r.s_l = pic->s_l; r.s_c = pic->s_c; r.pad_l = pic->pad_l; r.pad_c = pic->pad_c;
+    size_t ny = (size_t)pic->s_l * (pic->h_l + 2 * pic->pad_l);
+    size_t nc = (size_t)pic->s_c * (pic->h_c + 2 * pic->pad_c);
+    r.off_y = (int64_t)T.samp.n; memcpy(vec_push(&T.samp, ny), pic->buf_y, ny * sizeof(s16));
+    r.off_u = (int64_t)T.samp.n; memcpy(vec_push(&T.samp, nc), pic->buf_u, nc * sizeof(s16));
+    r.off_v = (int64_t)T.samp.n; memcpy(vec_push(&T.samp, nc), pic->buf_v, nc * sizeof(s16));
+    *(RH_PIC *)vec_push(&T.pics, 1) = r;
+    return (int)T.pics.n - 1;
+}
+
+static u32 hook_me(XEVE_PINTER *pi, int x, int y, int log2_cuw, int log2_cuh, s8 *refi, int lidx, s16 mvp[MV_D],
+                   s16 mv[MV_D], int bi, int bit_depth_luma)
+{
+    if(!tracing(RH_T_ME)) return T.org_me(pi, x, y, log2_cuw, log2_cuh, refi, lidx, mvp, mv, bi, bit_depth_luma);
+    RH_ME_REC r;
+    memset(&r, 0, sizeof(r));
+    XEVE_PIC *rp = pi->refp[*refi][lidx].pic;
+    r.poc = pi->poc;
+    r.cur_pic = find_or_add_pic(pi->pic_o, pi->poc, 0);
+    r.ref_pic = find_or_add_pic(rp, (int)rp->poc, 1);
+    r.ref_poc = (int)pi->refp[*refi][lidx].poc;
+    r.x = x; r.y = y; r.log2w = log2_cuw; r.log2h = log2_cuh; r.lidx = lidx; r.bi = bi; r.refi = *refi;
+    r.num_refp = pi->num_refp;
+    r.mvp[0] = mvp[0]; r.mvp[1] = mvp[1]; r.mv_in[0] = mv[0]; r.mv_in[1] = mv[1];
+    r.lambda_mv = pi->lambda_mv;
+    r.mot_bits_in[0] = pi->mot_bits[0]; r.mot_bits_in[1] = pi->mot_bits[1];
+    r.max_search_range = pi->max_search_range; r.gop_size = pi->gop_size;
+    r.org_bi_off = -1;
+    if(bi) {
+        size_t n = (size_t)1 << (log2_cuw + log2_cuh);
+        r.org_bi_off = (int32_t)T.samp.n;
+        memcpy(vec_push(&T.samp, n), pi->org_bi, n * sizeof(s16));
+    }
+    u32 cost = T.org_me(pi, x, y, log2_cuw, log2_cuh, refi, lidx, mvp, mv, bi, bit_depth_luma);
+    r.mv_out[0] = mv[0]; r.mv_out[1] = mv[1]; r.cost = cost;
+    r.mot_bits_out[0] = pi->mot_bits[0]; r.mot_bits_out[1] = pi->mot_bits[1];
+    *(RH_ME_REC *)vec_push(&T.me, 1) = r;
+    return cost;
+}
+
+static void hook_mc(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int w, int h, s8 refi[REFP_NUM], s16 (*mv)[MV_D],
+                    XEVE_REFP (*refp)[REFP_NUM], pel pred[REFP_NUM][N_C][MAX_CU_DIM], int a, int b,
+                    s16 (*c)[REFP_NUM][MV_D])
+{
+    T.org_mc(ctx, core, x, y, w, h, refi, mv, refp, pred, a, b, c);
+    if(!tracing(RH_T_MC)) return;
+    RH_MC_REC r;
+    memset(&r, 0, sizeof(r));
+    r.poc = ctx->poc.poc_val; r.x = x; r.y = y; r.w = w; r.h = h;
+    for(int l = 0; l < 2; l++) {
+        r.refi[l] = refi[l]; r.mv[l][0] = mv[l][0]; r.mv[l][1] = mv[l][1];
+        r.ref_pic[l] = -1; r.ref_poc[l] = -1;
+        if(REFI_IS_VALID(refi[l])) {
+            XEVE_PIC *rp = refp[refi[l]][l].pic;
+            r.ref_pic[l] = find_or_add_pic(rp, (int)rp->poc, 1);
+            r.ref_poc[l] = (int)rp->poc;
+        }
+    }
+    uint64_t hsh = FNV_INIT;
+    hsh = fnv1a(hsh, pred[0][Y_C], (size_t)w * h * 2);
+    hsh = fnv1a(hsh, pred[0][U_C], (size_t)w * h / 2);
+    hsh = fnv1a(hsh, pred[0][V_C], (size_t)w * h / 2);
+    r.out_hash = hsh;
+    *(RH_MC_REC *)vec_push(&T.mc, 1) = r;
+}
+
+static void grab_rates(XEVE_CORE *core, RH_RATES *o)
+{
+    memcpy(o->cbf_all, core->rdoq_est_cbf_all, sizeof(o->cbf_all));
+    memcpy(o->cbf_luma, core->rdoq_est_cbf_luma, sizeof(o->cbf_luma));
+    memcpy(o->cbf_cb, core->rdoq_est_cbf_cb, sizeof(o->cbf_cb));
+    memcpy(o->cbf_cr, core->rdoq_est_cbf_cr, sizeof(o->cbf_cr));
+    memcpy(o->run, core->rdoq_est_run, sizeof(o->run));
+    memcpy(o->level, core->rdoq_est_level, sizeof(o->level));
+    memcpy(o->last, core->rdoq_est_last, sizeof(o->last));
+}
+static void put_rates(XEVE_CORE *core, const RH_RATES *o)
+{
+    memcpy(core->rdoq_est_cbf_all, o->cbf_all, sizeof(o->cbf_all));
+    memcpy(core->rdoq_est_cbf_luma, o->cbf_luma, sizeof(o->cbf_luma));
+    memcpy(core->rdoq_est_cbf_cb, o->cbf_cb, sizeof(o->cbf_cb));
+    memcpy(core->rdoq_est_cbf_cr, o->cbf_cr, sizeof(o->cbf_cr));
+    memcpy(core->rdoq_est_run, o->run, sizeof(o->run));
+    memcpy(core->rdoq_est_level, o->level, sizeof(o->level));
+    memcpy(core->rdoq_est_last, o->last, sizeof(o->last));
+}
+
+static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], int log2_cuw, int log2_cuh,
+                   int slice_type, int nnz[N_C], int is_intra, int run_stats)
+{
+    if(!tracing(RH_T_TQ)) return T.org_tq(ctx, core, coef, log2_cuw, log2_cuh, slice_type, nnz, is_intra, run_stats);
+    RH_TQ_REC r;
+    memset(&r, 0, sizeof(r));
+    size_t ny = (size_t)1 << (log2_cuw + log2_cuh), nc = ny >> 2;
+    r.poc = ctx->poc.poc_val; r.log2w = log2_cuw; r.log2h = log2_cuh; r.slice_type = slice_type;
+    r.is_intra = is_intra; r.run_stats = run_stats;
+    r.qp[0] = core->qp_y; r.qp[1] = core->qp_u; r.qp[2] = core->qp_v;
+    for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
+    RH_RATES cur;
+    grab_rates(core, &cur);
+    if(!T.have_rates || memcmp(&cur, &T.last_rates, sizeof(cur))) {
+        *(RH_RATES *)vec_push(&T.rates, 1) = cur;
+        T.last_rates = cur;
+        T.have_rates = 1;
+    }
+    r.rate_idx = (int)T.rates.n - 1;
+    r.in_off = (int64_t)T.samp.n;
+    s16 *dst = vec_push(&T.samp, ny + 2 * nc);
+    memcpy(dst, coef[Y_C], ny * 2);
+    memcpy(dst + ny, coef[U_C], nc * 2);
+    memcpy(dst + ny + nc, coef[V_C], nc * 2);
+    int ret = T.org_tq(ctx, core, coef, log2_cuw, log2_cuh, slice_type, nnz, is_intra, run_stats);
+    for(int i = 0; i < 3; i++) r.nnz[i] = nnz[i];
+    uint64_t hsh = FNV_INIT;
+    hsh = fnv1a(hsh, coef[Y_C], ny * 2);
+    hsh = fnv1a(hsh, coef[U_C], nc * 2);
+    hsh = fnv1a(hsh, coef[V_C], nc * 2);
+    r.out_hash = hsh;
+    *(RH_TQ_REC *)vec_push(&T.tq, 1) = r;
+    return ret;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * encoder session
+ * ---------------------------------------------------------------------------------------- */
+static int img_addref(XEVE_IMGB *i) { return ++i->refcnt; }
+static int img_getref(XEVE_IMGB *i) { return i->refcnt; }
+static int img_release(XEVE_IMGB *i) { return --i->refcnt; }
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static XEVE make_encoder(int w, int h, int in_depth, int preset, int qp, int threads, int bframes,
+                         const char *extra, int *err)
+{
+    XEVE_CDSC cdsc;
+    memset(&cdsc, 0, sizeof(cdsc));
+    XEVE_PARAM *p = &cdsc.param;
+    xeve_param_default(p);
+    xeve_param_ppt(p, XEVE_PROFILE_BASELINE, preset, XEVE_TUNE_NONE);
+    p->w = w; p->h = h; p->fps.num = 30; p->fps.den = 1;
+    p->threads = threads;
+    if(qp >= 0) p->qp = qp;
+    if(bframes >= 0) p->bframes = bframes;
+    p->cs = XEVE_CS_SET(XEVE_CF_YCBCR420, p->codec_bit_depth, 0);
+    /* extra "name=value;name=value" overrides through the reference's own parser */
+    if(extra && *extra) {
+        char *dup = strdup(extra), *save = NULL;
+        for(char *tok = strtok_r(dup, ";", &save); tok; tok = strtok_r(NULL, ";", &save)) {
+            char *eq = strchr(tok, '=');
+            if(!eq) continue;
+            *eq = 0;
+            if(xeve_param_parse(p, tok, eq + 1) != XEVE_OK) fprintf(stderr, "rh: bad param %s\n", tok);
+        }
+        free(dup);
+    }
+    cdsc.max_bs_buf_size = 16 * 1024 * 1024;
+    if(xeve_param_check(p) != XEVE_OK) { *err = -2; return NULL; }
+    return xeve_create(&cdsc, err);
+}
+
+/* Encode `nframes` frames of planar I420 held in memory; returns seconds spent inside
+ * xeve_encode (the quantity the reference app reports, app/xeve_app.c:1236-1246), or <0. */
+RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_depth, int preset, int qp,
+                             int threads, int bframes, const char *extra, int trace_mask, int pic_lo, int pic_hi,
+                             uint8_t *bs_out, int64_t bs_cap, int64_t *bs_len)
+{
+    int  err = 0;
+    XEVE id  = make_encoder(w, h, in_depth, preset, qp, threads, bframes, extra, &err);
+    if(!id) return -1.0;
+    XEVE_CTX *ctx = (XEVE_CTX *)id;
+
+    vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
+    vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16));
+    T.have_rates = 0;
+    T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
+    if(trace_mask) {
+        T.org_me = ctx->pinter[0].fn_me; T.org_mc = ctx->pinter[0].fn_mc; T.org_tq = ctx->fn_tq;
+        for(int i = 0; i < ctx->param.threads; i++) { ctx->pinter[i].fn_me = hook_me; ctx->pinter[i].fn_mc = hook_mc; }
+        ctx->fn_tq = hook_tq;
+    }
+    XEVE_PINTER *pi = &ctx->pinter[0];
+    T.cst.w = w; T.cst.h = h; T.cst.bit_depth = ctx->param.codec_bit_depth; T.cst.me_level = pi->me_level;
+    T.cst.hpel_cnt = pi->search_pattern_hpel_cnt; T.cst.qpel_cnt = pi->search_pattern_qpel_cnt;
+    T.cst.me_complexity = pi->me_complexity;
+    T.cst.min_clip[0] = pi->min_clip[0]; T.cst.min_clip[1] = pi->min_clip[1];
+    T.cst.max_clip[0] = pi->max_clip[0]; T.cst.max_clip[1] = pi->max_clip[1];
+    T.cst.merge_num = ctx->param.merge_num; T.cst.me_range = ctx->param.me_range; T.cst.gop_size = ctx->param.gop_size;
+    T.cst.rdoq = ctx->param.rdoq; T.cst.tool_iqt = ctx->param.tool_iqt;
+
+    int       bps = in_depth > 8 ? 2 : 1;
+    size_t    fsz = (size_t)w * h * 3 / 2 * bps;
+    XEVE_IMGB img;
+    uint8_t  *bs = malloc(16 * 1024 * 1024);
+    XEVE_BITB bitb;
+    XEVE_STAT stat;
+    memset(&bitb, 0, sizeof(bitb));
+    bitb.addr = bs; bitb.bsize = 16 * 1024 * 1024;
+    double  t_enc = 0;
+    int64_t total = 0;
+    int     pushed = 0, bumping = 0, ret;
+    while(1) {
+        if(!bumping) {
+            if(pushed < nframes) {
+                const uint8_t *f = (const uint8_t *)yuv + fsz * pushed;
+                memset(&img, 0, sizeof(img));
+                img.cs = XEVE_CS_SET(XEVE_CF_YCBCR420, in_depth, 0);
+                img.np = 3;
+                for(int c = 0; c < 3; c++) {
+                    int cw = c ? w / 2 : w, ch = c ? h / 2 : h;
+                    img.w[c] = img.aw[c] = cw; img.h[c] = img.ah[c] = ch; img.s[c] = cw * bps; img.e[c] = ch;
+                }
+                img.a[0] = (void *)f; img.a[1] = (void *)(f + (size_t)w * h * bps);
+                img.a[2] = (void *)(f + (size_t)w * h * bps * 5 / 4);
+                img.addref = img_addref; img.getref = img_getref; img.release = img_release; img.refcnt = 1;
+                img.ts[XEVE_TS_PTS] = pushed;
+                ret = xeve_push(id, &img);
+                if(XEVE_FAILED(ret)) { t_enc = -3; break; }
+                pushed++;
+            }
+            else {
+                int val = 1, size = sizeof(int);
+                xeve_config(id, XEVE_CFG_SET_FORCE_OUT, &val, &size);
+                bumping = 1;
+            }
+        }
+        double t0 = now_s();
+        ret = xeve_encode(id, &bitb, &stat);
+        t_enc += now_s() - t0;
+        if(XEVE_FAILED(ret)) { t_enc = -4; break; }
+        if(ret == XEVE_OK_NO_MORE_FRM) break;
+        if(ret == XEVE_OK && stat.write > 0) {
+            if(bs_out && total + stat.write <= bs_cap) memcpy(bs_out + total, bs, stat.write);
+            total += stat.write;
+        }
+    }
+    if(bs_len) *bs_len = total;
+    free(bs);
+    T.ctx = NULL;
+    xeve_delete(id);
+    return t_enc;
+}
+
+RH_API int64_t rh_trace_get(int what, void **ptr)
+{
+    vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
+             : what == 4 ? &T.pics : &T.samp;
+    *ptr = v->p;
+    return (int64_t)v->n;
+}
+RH_API void rh_trace_const(RH_CONST *out) { *out = T.cst; }
+RH_API int  rh_sizeof(int what)
+{
+    switch(what) {
+    case 0: return sizeof(RH_ME_REC);
+    case 1: return sizeof(RH_MC_REC);
+    case 2: return sizeof(RH_TQ_REC);
+    case 3: return sizeof(RH_RATES);
+    case 4: return sizeof(RH_PIC);
+    case 5: return sizeof(RH_PLANES);
+    case 6: return sizeof(RH_CONST);
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * utility context: a small real encoder instance whose ctx supplies the function pointers,
+ * err_scale table and parameter block the replay functions need
+ * ---------------------------------------------------------------------------------------- */
+static XEVE_CTX *g_util;
+static XEVE_CTX *util_ctx(void)
+{
+    if(!g_util) {
+        int err = 0;
+        g_util = (XEVE_CTX *)make_encoder(176, 144, 8, XEVE_PRESET_FAST, 32, 1, -1, NULL, &err);
+        /* the SPS is normally filled when the first picture is coded (src_base/xeve_enc.c:894) */
+        if(g_util) xeve_set_sps(g_util, &g_util->sps);
+    }
+    return g_util;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * kernel probes.  variant: 0 = C table, 1 = SSE, 2 = AVX2
+ * ---------------------------------------------------------------------------------------- */
+#include "xeve_sad_sse.h"
+#include "xeve_sad_avx.h"
+#include "xeve_mc_sse.h"
+#include "xeve_mc_avx.h"
+#include "xeve_itdq_sse.h"
+#include "xeve_itdq_avx.h"
+#include "xeve_tq_avx.h"
+
+RH_API int rh_sad(int variant, int log2w, int log2h, void *s1, void *s2, int st1, int st2, int bd)
+{
+    const XEVE_FN_SAD(*t)[8] = variant == 2 ? xeve_tbl_sad_16b_avx : variant == 1 ? xeve_tbl_sad_16b_sse : xeve_tbl_sad_16b;
+    XEVE_FN_SAD f = t[log2w][log2h];
+    if(!f) f = xeve_tbl_sad_16b[0][0];
+    return f(1 << log2w, 1 << log2h, s1, s2, st1, st2, bd);
+}
+RH_API int64_t rh_ssd(int variant, int log2w, int log2h, void *s1, void *s2, int st1, int st2, int bd)
+{
+    const XEVE_FN_SSD(*t)[8] = variant ? xeve_tbl_ssd_16b_sse : xeve_tbl_ssd_16b;
+    XEVE_FN_SSD f = t[log2w][log2h];
+    if(!f) f = xeve_tbl_ssd_16b[0][0];
+    return f(1 << log2w, 1 << log2h, s1, s2, st1, st2, bd);
+}
+RH_API void rh_diff(int variant, int log2w, int log2h, void *s1, void *s2, int st1, int st2, int sd, s16 *d, int bd)
+{
+    const XEVE_FN_DIFF(*t)[8] = variant ? xeve_tbl_diff_16b_sse : xeve_tbl_diff_16b;
+    XEVE_FN_DIFF f = t[log2w][log2h];
+    if(!f) f = xeve_tbl_diff_16b[0][0];
+    f(1 << log2w, 1 << log2h, s1, s2, st1, st2, sd, d, bd);
+}
+RH_API int rh_satd(int variant, int w, int h, void *s1, void *s2, int st1, int st2, int bd)
+{
+    return (variant ? xeve_tbl_satd_16b_sse : xeve_tbl_satd_16b)[0](w, h, s1, s2, st1, st2, bd);
+}
+/* gmv in 1/16 (luma) or 1/32 (chroma) pel, absolute; ref = top-left of active area */
+RH_API void rh_mc_l(int variant, s16 *ref, int gmv_x, int gmv_y, int s_ref, int s_pred, s16 *pred, int w, int h, int bd)
+{
+    const XEVE_MC_L(*t)[2] = variant == 2 ? xeve_tbl_mc_l_avx : variant == 1 ? xeve_tbl_mc_l_sse : xeve_tbl_mc_l;
+    t[(gmv_x & 15) ? 1 : 0][(gmv_y & 15) ? 1 : 0](ref, gmv_x, gmv_y, s_ref, s_pred, pred, w, h, bd, xeve_tbl_mc_l_coeff);
+}
+RH_API void rh_mc_c(int variant, s16 *ref, int gmv_x, int gmv_y, int s_ref, int s_pred, s16 *pred, int w, int h, int bd)
+{
+    const XEVE_MC_C(*t)[2] = variant == 2 ? xeve_tbl_mc_c_avx : variant == 1 ? xeve_tbl_mc_c_sse : xeve_tbl_mc_c;
+    t[(gmv_x & 31) ? 1 : 0][(gmv_y & 31) ? 1 : 0](ref, gmv_x, gmv_y, s_ref, s_pred, pred, w, h, bd, xeve_tbl_mc_c_coeff);
+}
+/* whole-block forward transform exactly as the reference sequences its two stages
+ * (src_base/xeve_tq.c:396-404), with a selectable stage table */
+RH_API void rh_fwd_transform(int variant, s16 *coef, int log2w, int log2h, int bd)
+{
+    const XEVE_TXB *t = variant == 2 ? xeve_tbl_txb_avx : xeve_tbl_txb;
+    s32 *tb = malloc(sizeof(s32) * MAX_TR_DIM);
+    int  s1 = xeve_get_transform_shift(log2w, 0, bd), s2 = xeve_get_transform_shift(log2h, 1, bd);
+    t[log2w - 1](coef, tb, 0, 1 << log2h, 0);
+    t[log2h - 1](tb, coef, s1 + s2, 1 << log2w, 1);
+    free(tb);
+}
+RH_API void rh_inv_transform(int variant, s16 *coef, int log2w, int log2h, int bd)
+{
+    const XEVE_ITXB *t = variant == 2 ? xeve_tbl_itxb_avx : variant == 1 ? xeve_tbl_itxb_sse : xeve_tbl_itxb;
+    s32 *tb = malloc(sizeof(s32) * MAX_TR_DIM);
+    t[log2h - 1](coef, tb, 0, 1 << log2w, 0);
+    t[log2w - 1](tb, coef, ITX_SHIFT1 + ITX_SHIFT2(bd), 1 << log2h, 1);
+    free(tb);
+}
+RH_API void rh_recon(s16 *coef, s16 *pred, int is_coef, int w, int h, int s_rec, s16 *rec, int bd)
+{
+    xeve_recon_blk(coef, pred, is_coef, w, h, s_rec, rec, bd);
+}
+RH_API void rh_average(s16 *a, s16 *b, s16 *d, int w, int h) { xeve_average_16b_no_clip(a, b, d, w, w, w, w, h); }
+
+/* constant tables (for checking the restatement's generated tables) */
+RH_API const void *rh_table(int which, int *bytes)
+{
+    switch(which) {
+    case 0: *bytes = sizeof(xeve_tbl_tm64); return xeve_tbl_tm64;
+    case 1: *bytes = sizeof(xeve_tbl_tm32); return xeve_tbl_tm32;
+    case 2: *bytes = sizeof(xeve_tbl_tm16); return xeve_tbl_tm16;
+    case 3: *bytes = sizeof(xeve_tbl_tm8); return xeve_tbl_tm8;
+    case 4: *bytes = sizeof(xeve_tbl_tm4); return xeve_tbl_tm4;
+    case 5: *bytes = sizeof(xeve_tbl_tm2); return xeve_tbl_tm2;
+    case 6: *bytes = 4096; return xeve_tbl_mv_bits - 2047;
+    case 7: *bytes = sizeof(xeve_tbl_refi_bits); return xeve_tbl_refi_bits;
+    case 8: *bytes = sizeof(xeve_tbl_scan); return xeve_tbl_scan;
+    case 9: *bytes = sizeof(xeve_tbl_dq_scale_b); return xeve_tbl_dq_scale_b;
+    case 10: *bytes = sizeof(xeve_quant_scale); return xeve_quant_scale;
+    case 11: *bytes = sizeof(xeve_tbl_mc_l_coeff); return xeve_tbl_mc_l_coeff;
+    case 12: *bytes = sizeof(xeve_tbl_mc_c_coeff); return xeve_tbl_mc_c_coeff;
+    case 13: *bytes = sizeof(util_ctx()->err_scale); return util_ctx()->err_scale;
+    }
+    *bytes = 0;
+    return NULL;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * replay: run the reference's own functions over a work list on `nthreads` host threads
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int              tid, nthreads, n;
+    const RH_CONST  *cst;
+    const RH_PLANES *planes;
+    const s16       *side;
+    /* ME */
+    const RH_ME_REC *me_in;
+    RH_ME_REC       *me_out;
+    /* MC */
+    const RH_MC_REC *mc_in;
+    s16             *mc_pred; /* per item: w*h*3/2 at offsets mc_off[i] */
+    const int64_t   *mc_off;
+    uint64_t        *mc_hash;
+    /* TQ */
+    const RH_TQ_REC *tq_in;
+    const RH_RATES  *rates;
+    s16             *tq_coef;  /* output, same offsets as in_off - base */
+    s16             *tq_resi;  /* optional: dequant + inverse transform output */
+    s16             *tq_rec;   /* unused */
+    int32_t         *tq_nnz;   /* n*3 */
+    int              do_itdq;
+} job_t;
+
+static void fill_pic(XEVE_PIC *p, const RH_PLANES *pl)
+{
+    memset(p, 0, sizeof(*p));
+    p->y = pl->y; p->u = pl->u; p->v = pl->v; p->s_l = pl->s_l; p->s_c = pl->s_c;
+    p->w_l = pl->w_l; p->h_l = pl->h_l; p->w_c = pl->w_l / 2; p->h_c = pl->h_l / 2; p->poc = pl->poc;
+}
+
+static void *me_worker(void *arg)
+{
+    job_t       *j   = arg;
+    XEVE_CTX    *u   = util_ctx();
+    XEVE_PINTER *pi  = calloc(1, sizeof(XEVE_PINTER));
+    XEVE_REFP (*refp)[REFP_NUM] = calloc(XEVE_MAX_NUM_REF_PICS, sizeof(XEVE_REFP[REFP_NUM]));
+    XEVE_PIC     cur, ref;
+    XEVE_PINTER *tp  = &u->pinter[0];
+    pi->fn_me = (T.org_me && tp->fn_me == hook_me) ? T.org_me : tp->fn_me;
+    pi->search_pattern_hpel = tp->search_pattern_hpel; pi->search_pattern_qpel = tp->search_pattern_qpel;
+    pi->mc_l_coeff = xeve_tbl_mc_l_coeff; pi->mc_c_coeff = xeve_tbl_mc_c_coeff;
+    pi->search_pattern_hpel_cnt = j->cst->hpel_cnt; pi->search_pattern_qpel_cnt = j->cst->qpel_cnt;
+    pi->me_level = j->cst->me_level; pi->me_complexity = j->cst->me_complexity;
+    pi->min_clip[0] = j->cst->min_clip[0]; pi->min_clip[1] = j->cst->min_clip[1];
+    pi->max_clip[0] = j->cst->max_clip[0]; pi->max_clip[1] = j->cst->max_clip[1];
+    pi->refp = refp;
+    for(int i = j->tid; i < j->n; i += j->nthreads) {
+        const RH_ME_REC *r = &j->me_in[i];
+        RH_ME_REC       *o = &j->me_out[i];
+        fill_pic(&cur, &j->planes[r->cur_pic]);
+        fill_pic(&ref, &j->planes[r->ref_pic]);
+        pi->pic_o = &cur; pi->o[0] = cur.y; pi->o[1] = cur.u; pi->o[2] = cur.v;
+        pi->s_o[0] = cur.s_l; pi->s_o[1] = pi->s_o[2] = cur.s_c;
+        refp[r->refi][r->lidx].pic = &ref; refp[r->refi][r->lidx].poc = r->ref_poc;
+        pi->poc = r->poc; pi->gop_size = r->gop_size; pi->max_search_range = r->max_search_range;
+        pi->lambda_mv = r->lambda_mv; pi->num_refp = r->num_refp;
+        pi->mot_bits[0] = r->mot_bits_in[0]; pi->mot_bits[1] = r->mot_bits_in[1];
+        if(r->bi) memcpy(pi->org_bi, j->side + r->org_bi_off, sizeof(s16) << (r->log2w + r->log2h));
+        s8  refi = r->refi;
+        s16 mvp[2] = {r->mvp[0], r->mvp[1]}, mv[2] = {r->mv_in[0], r->mv_in[1]};
+        *o = *r;
+        o->cost = pi->fn_me(pi, r->x, r->y, r->log2w, r->log2h, &refi, r->lidx, mvp, mv, r->bi, j->cst->bit_depth);
+        o->mv_out[0] = mv[0]; o->mv_out[1] = mv[1];
+        o->mot_bits_out[0] = pi->mot_bits[0]; o->mot_bits_out[1] = pi->mot_bits[1];
+    }
+    free(refp);
+    free(pi);
+    return NULL;
+}
+
+static double run_jobs(job_t *proto, void *(*fn)(void *), int nthreads)
+{
+    if(nthreads < 1) nthreads = 1;
+    util_ctx();
+    pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+    job_t     *jb = malloc(sizeof(job_t) * nthreads);
+    double     t0 = now_s();
+    for(int t = 0; t < nthreads; t++) {
+        jb[t] = *proto; jb[t].tid = t; jb[t].nthreads = nthreads;
+        pthread_create(&th[t], NULL, fn, &jb[t]);
+    }
+    for(int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    double dt = now_s() - t0;
+    free(th);
+    free(jb);
+    return dt;
+}
+
+/* returns wall seconds */
+RH_API double rh_replay_me(const RH_CONST *cst, const RH_PLANES *planes, const s16 *side, const RH_ME_REC *in,
+                           RH_ME_REC *out, int n, int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.cst = cst; j.planes = planes; j.side = side; j.me_in = in; j.me_out = out; j.n = n;
+    return run_jobs(&j, me_worker, nthreads);
+}
+
+static void *mc_worker(void *arg)
+{
+    job_t *j = arg;
+    XEVE_REFP (*refp)[REFP_NUM] = calloc(XEVE_MAX_NUM_REF_PICS, sizeof(XEVE_REFP[REFP_NUM]));
+    pel (*pred)[N_C][MAX_CU_DIM] = malloc(sizeof(pel) * 2 * N_C * MAX_CU_DIM);
+    XEVE_PIC pic[2];
+    for(int i = j->tid; i < j->n; i += j->nthreads) {
+        const RH_MC_REC *r = &j->mc_in[i];
+        s8  refi[2] = {r->refi[0], r->refi[1]};
+        s16 mv[2][2] = {{r->mv[0][0], r->mv[0][1]}, {r->mv[1][0], r->mv[1][1]}};
+        for(int l = 0; l < 2; l++)
+            if(REFI_IS_VALID(refi[l])) {
+                fill_pic(&pic[l], &j->planes[r->ref_pic[l]]);
+                refp[refi[l]][l].pic = &pic[l]; refp[refi[l]][l].poc = pic[l].poc;
+            }
+        xeve_mc(r->x, r->y, j->cst->w, j->cst->h, r->w, r->h, refi, mv, refp, pred, j->cst->bit_depth,
+                j->cst->bit_depth, 1);
+        size_t ny = (size_t)r->w * r->h, nc = ny / 4;
+        if(j->mc_pred) {
+            s16 *d = j->mc_pred + j->mc_off[i];
+            memcpy(d, pred[0][Y_C], ny * 2); memcpy(d + ny, pred[0][U_C], nc * 2); memcpy(d + ny + nc, pred[0][V_C], nc * 2);
+        }
+        if(j->mc_hash) {
+            uint64_t h = FNV_INIT;
+            h = fnv1a(h, pred[0][Y_C], ny * 2); h = fnv1a(h, pred[0][U_C], nc * 2); h = fnv1a(h, pred[0][V_C], nc * 2);
+            j->mc_hash[i] = h;
+        }
+    }
+    free(pred);
+    free(refp);
+    return NULL;
+}
+
+RH_API double rh_replay_mc(const RH_CONST *cst, const RH_PLANES *planes, const RH_MC_REC *in, int n, s16 *pred_out,
+                           const int64_t *pred_off, uint64_t *hash_out, int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.cst = cst; j.planes = planes; j.mc_in = in; j.n = n; j.mc_pred = pred_out; j.mc_off = pred_off; j.mc_hash = hash_out;
+    return run_jobs(&j, mc_worker, nthreads);
+}
+
+static void *tq_worker(void *arg)
+{
+    job_t     *j = arg;
+    XEVE_CTX  *u = util_ctx();
+    XEVE_CORE *core = calloc(1, sizeof(XEVE_CORE));
+    s16 (*coef)[MAX_CU_DIM] = malloc(sizeof(s16) * N_C * MAX_CU_DIM);
+    int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int) =
+        (u->fn_tq == hook_tq) ? T.org_tq : u->fn_tq;
+    core->ctx = u;
+    int last_rate = -1;
+    for(int i = j->tid; i < j->n; i += j->nthreads) {
+        const RH_TQ_REC *r = &j->tq_in[i];
+        size_t ny = (size_t)1 << (r->log2w + r->log2h), nc = ny >> 2;
+        const s16 *src = j->side + r->in_off;
+        memcpy(coef[Y_C], src, ny * 2); memcpy(coef[U_C], src + ny, nc * 2); memcpy(coef[V_C], src + ny + nc, nc * 2);
+        core->qp_y = r->qp[0]; core->qp_u = r->qp[1]; core->qp_v = r->qp[2];
+        for(int c = 0; c < 3; c++) core->lambda[c] = r->lambda[c];
+        core->log2_cuw = r->log2w; core->log2_cuh = r->log2h;
+        if(r->rate_idx != last_rate) { put_rates(core, &j->rates[r->rate_idx]); last_rate = r->rate_idx; }
+        int nnz[3];
+        org_tq(u, core, coef, r->log2w, r->log2h, r->slice_type, nnz, r->is_intra, r->run_stats);
+        s16 *d = j->tq_coef + r->in_off;
+        memcpy(d, coef[Y_C], ny * 2); memcpy(d + ny, coef[U_C], nc * 2); memcpy(d + ny + nc, coef[V_C], nc * 2);
+        for(int c = 0; c < 3; c++) j->tq_nnz[i * 3 + c] = nnz[c];
+        if(j->do_itdq && j->tq_resi) {
+            u->fn_itdp(u, core, coef, core->nnz_sub);
+            s16 *e = j->tq_resi + r->in_off;
+            memcpy(e, coef[Y_C], ny * 2); memcpy(e + ny, coef[U_C], nc * 2); memcpy(e + ny + nc, coef[V_C], nc * 2);
+        }
+    }
+    free(coef);
+    free(core);
+    return NULL;
+}
+
+/* side: the input planes; coef_out / resi_out use the same element offsets (in_off) */
+RH_API double rh_replay_tq(const RH_CONST *cst, const s16 *side, const RH_TQ_REC *in, const RH_RATES *rates, int n,
+                           s16 *coef_out, int32_t *nnz_out, s16 *resi_out, int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.cst = cst; j.side = side; j.tq_in = in; j.rates = rates; j.n = n; j.tq_coef = coef_out; j.tq_nnz = nnz_out;
+    j.tq_resi = resi_out; j.do_itdq = resi_out != NULL;
+    return run_jobs(&j, tq_worker, nthreads);
+}

@@ -1,0 +1,245 @@
+"""ctypes binding of oracle/_ref/libref_harness.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  It drives the UNMODIFIED reference (built by oracle/Makefile.ref from the
+sources under /root/reference, outputs only into oracle/_ref/) through oracle/ref_harness.c:
+kernel probes, call tracing of a real encode, and multi-threaded replay of work lists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libref_harness.so")
+
+NUM_CTX_CC_RUN = 24
+NUM_CTX_CC_LEVEL = 24
+NUM_CTX_CC_LAST = 2
+
+ME_REC = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("ref_pic", "<i4"), ("ref_poc", "<i4"),
+    ("x", "<i2"), ("y", "<i2"),
+    ("log2w", "u1"), ("log2h", "u1"), ("lidx", "u1"), ("bi", "u1"),
+    ("refi", "i1"), ("num_refp", "u1"),
+    ("mvp", "<i2", (2,)), ("mv_in", "<i2", (2,)),
+    ("lambda_mv", "<u4"), ("mot_bits_in", "<i4", (2,)),
+    ("max_search_range", "<i4"), ("gop_size", "<i4"), ("org_bi_off", "<i4"),
+    ("mv_out", "<i2", (2,)), ("cost", "<u4"), ("mot_bits_out", "<i4", (2,)),
+], align=True)
+
+MC_REC = np.dtype([
+    ("poc", "<i4"), ("ref_pic", "<i4", (2,)), ("ref_poc", "<i4", (2,)),
+    ("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"),
+    ("refi", "i1", (2,)), ("mv", "<i2", (2, 2)),
+    ("out_hash", "<u8"),
+], align=True)
+
+TQ_REC = np.dtype([
+    ("poc", "<i4"),
+    ("log2w", "u1"), ("log2h", "u1"), ("slice_type", "u1"), ("is_intra", "u1"),
+    ("run_stats", "u1"), ("qp", "u1", (3,)),
+    ("rate_idx", "<i4"), ("in_off", "<i8"),
+    ("lambda", "<f8", (3,)), ("nnz", "<i4", (3,)),
+    ("out_hash", "<u8"),
+], align=True)
+
+RATES = np.dtype([
+    ("cbf_all", "<i4", (2,)), ("cbf_luma", "<i4", (2,)), ("cbf_cb", "<i4", (2,)), ("cbf_cr", "<i4", (2,)),
+    ("run", "<i4", (NUM_CTX_CC_RUN, 2)), ("level", "<i4", (NUM_CTX_CC_LEVEL, 2)), ("last", "<i4", (NUM_CTX_CC_LAST, 2)),
+], align=True)
+
+PIC = np.dtype([
+    ("poc", "<i4"), ("kind", "<i4"),
+    ("w_l", "<i4"), ("h_l", "<i4"), ("w_c", "<i4"), ("h_c", "<i4"),
+    ("s_l", "<i4"), ("s_c", "<i4"), ("pad_l", "<i4"), ("pad_c", "<i4"),
+    ("off_y", "<i8"), ("off_u", "<i8"), ("off_v", "<i8"),
+], align=True)
+
+CONST = np.dtype([
+    ("w", "<i4"), ("h", "<i4"), ("bit_depth", "<i4"), ("me_level", "<i4"), ("hpel_cnt", "<i4"), ("qpel_cnt", "<i4"),
+    ("me_complexity", "<i4"), ("min_clip", "<i4", (2,)), ("max_clip", "<i4", (2,)),
+    ("merge_num", "<i4"), ("me_range", "<i4"), ("gop_size", "<i4"), ("rdoq", "<i4"), ("tool_iqt", "<i4"),
+], align=True)
+
+
+class PLANES(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("s_l", C.c_int32), ("s_c", C.c_int32), ("w_l", C.c_int32), ("h_l", C.c_int32), ("poc", C.c_int32)]
+
+
+def available() -> bool:
+    return os.path.exists(_LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref is not built (run: make -C oracle -f Makefile.ref; needs /root/reference)")
+        L = C.CDLL(_LIB_PATH)
+        L.rh_encode_clip.restype = C.c_double
+        L.rh_encode_clip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.rh_trace_get.restype = C.c_int64
+        L.rh_trace_get.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.rh_trace_const.argtypes = [C.c_void_p]
+        L.rh_sizeof.restype = C.c_int
+        L.rh_sad.restype = C.c_int
+        L.rh_sad.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rh_ssd.restype = C.c_int64
+        L.rh_ssd.argtypes = L.rh_sad.argtypes
+        L.rh_diff.restype = None
+        L.rh_diff.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.rh_satd.restype = C.c_int
+        L.rh_satd.argtypes = L.rh_sad.argtypes
+        for f in (L.rh_mc_l, L.rh_mc_c):
+            f.restype = None
+            f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        for f in (L.rh_fwd_transform, L.rh_inv_transform):
+            f.restype = None
+            f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rh_recon.restype = None
+        L.rh_recon.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.rh_average.restype = None
+        L.rh_average.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.rh_table.restype = C.c_void_p
+        L.rh_table.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.rh_replay_me.restype = C.c_double
+        L.rh_replay_me.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.rh_replay_mc.restype = C.c_double
+        L.rh_replay_mc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.rh_replay_tq.restype = C.c_double
+        L.rh_replay_tq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int]
+        for i, dt in enumerate((ME_REC, MC_REC, TQ_REC, RATES, PIC)):
+            assert L.rh_sizeof(i) == dt.itemsize, (i, L.rh_sizeof(i), dt.itemsize)
+        assert L.rh_sizeof(5) == C.sizeof(PLANES)
+        assert L.rh_sizeof(6) == CONST.itemsize
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
+PRESET = {"default": 0, "fast": 1, "medium": 2, "slow": 3, "placebo": 4}
+
+
+class Trace:
+    """Work lists recorded from one real reference encode (copied out of the harness)."""
+
+    def __init__(self, me, mc, tq, rates, pics, samp, const, enc_seconds, bitstream):
+        self.me, self.mc, self.tq, self.rates, self.pics, self.samp = me, mc, tq, rates, pics, samp
+        self.const, self.enc_seconds, self.bitstream = const, enc_seconds, bitstream
+
+    # -- picture helpers -------------------------------------------------------------
+    def plane_views(self, idx):
+        """(Y, U, V) full-buffer 2-D views (including padding) of picture-table entry idx."""
+        p = self.pics[idx]
+        out = []
+        for off, s, hh, pad in ((p["off_y"], p["s_l"], p["h_l"], p["pad_l"]),
+                                (p["off_u"], p["s_c"], p["h_c"], p["pad_c"]),
+                                (p["off_v"], p["s_c"], p["h_c"], p["pad_c"])):
+            rows = int(hh + 2 * pad)
+            out.append(self.samp[int(off):int(off) + rows * int(s)].reshape(rows, int(s)))
+        return out
+
+    def planes_struct(self):
+        """ctypes PLANES array addressing the active areas inside self.samp (keep self alive)."""
+        arr = (PLANES * len(self.pics))()
+        base = self.samp.ctypes.data
+        for i, p in enumerate(self.pics):
+            pl, pc = int(p["pad_l"]), int(p["pad_c"])
+            arr[i].y = base + 2 * (int(p["off_y"]) + pl * int(p["s_l"]) + pl)
+            arr[i].u = base + 2 * (int(p["off_u"]) + pc * int(p["s_c"]) + pc)
+            arr[i].v = base + 2 * (int(p["off_v"]) + pc * int(p["s_c"]) + pc)
+            arr[i].s_l, arr[i].s_c = int(p["s_l"]), int(p["s_c"])
+            arr[i].w_l, arr[i].h_l, arr[i].poc = int(p["w_l"]), int(p["h_l"]), int(p["poc"])
+        return arr
+
+
+def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1, threads=1, bframes=-1,
+                extra="", trace_mask=0, pic_lo=0, pic_hi=1 << 30, want_bitstream=True) -> Trace:
+    """Run the reference encoder over an in-memory I420 clip, optionally tracing hot-path calls."""
+    L = lib()
+    yuv = np.ascontiguousarray(yuv)
+    cap = 32 << 20
+    bs = np.empty(cap, np.uint8) if want_bitstream else None
+    n = C.c_int64(0)
+    sec = L.rh_encode_clip(_p(yuv), nframes, w, h, in_depth, PRESET[preset], qp, threads, bframes,
+                           extra.encode(), trace_mask, pic_lo, pic_hi, _p(bs), cap, C.byref(n))
+    if sec < 0:
+        raise RuntimeError(f"reference encode failed ({sec})")
+
+    def grab(what, dt):
+        ptr = C.c_void_p()
+        cnt = L.rh_trace_get(what, C.byref(ptr))
+        if cnt == 0:
+            return np.empty(0, dt)
+        buf = (C.c_char * (cnt * dt.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt, count=cnt).copy()
+
+    me, mc, tq = grab(0, ME_REC), grab(1, MC_REC), grab(2, TQ_REC)
+    rates, pics, samp = grab(3, RATES), grab(4, PIC), grab(5, np.dtype("<i2"))
+    cst = np.zeros(1, CONST)
+    L.rh_trace_const(_p(cst))
+    return Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
+
+
+def replay_me(tr: Trace, recs: np.ndarray | None = None, nthreads=1):
+    """Reference pinter_me_epzs over a work list; returns (records with outputs filled, seconds)."""
+    L = lib()
+    recs = tr.me if recs is None else np.ascontiguousarray(recs)
+    out = np.empty_like(recs)
+    planes = tr.planes_struct()
+    sec = L.rh_replay_me(_p(tr.const), C.addressof(planes), _p(tr.samp), _p(recs), _p(out), len(recs), nthreads)
+    return out, sec
+
+
+def mc_offsets(recs):
+    sz = recs["w"].astype(np.int64) * recs["h"].astype(np.int64) * 3 // 2
+    off = np.zeros(len(recs), np.int64)
+    np.cumsum(sz[:-1], out=off[1:])
+    return off, int(sz.sum())
+
+
+def replay_mc(tr: Trace, recs=None, nthreads=1, want_pred=True):
+    L = lib()
+    recs = tr.mc if recs is None else np.ascontiguousarray(recs)
+    off, total = mc_offsets(recs)
+    pred = np.empty(total, np.int16) if want_pred else None
+    hsh = np.empty(len(recs), np.uint64)
+    planes = tr.planes_struct()
+    sec = L.rh_replay_mc(_p(tr.const), C.addressof(planes), _p(recs), len(recs), _p(pred), _p(off), _p(hsh), nthreads)
+    return pred, off, hsh, sec
+
+
+def replay_tq(tr: Trace, recs=None, nthreads=1, want_itdq=True):
+    """Reference xeve_sub_block_tq (+ xeve_itdq) over a work list.
+
+    Returns (coef, nnz[n,3], resi or None, seconds); coef/resi share tr.samp's element offsets.
+    """
+    L = lib()
+    recs = tr.tq if recs is None else np.ascontiguousarray(recs)
+    coef = np.zeros_like(tr.samp)
+    resi = np.zeros_like(tr.samp) if want_itdq else None
+    nnz = np.zeros((len(recs), 3), np.int32)
+    sec = L.rh_replay_tq(_p(tr.const), _p(tr.samp), _p(recs), _p(tr.rates), len(recs), _p(coef), _p(nnz), _p(resi),
+                         nthreads)
+    return coef, nnz, resi, sec
+
+
+def table(which: int, dtype) -> np.ndarray:
+    L = lib()
+    n = C.c_int(0)
+    ptr = L.rh_table(which, C.byref(n))
+    buf = (C.c_char * n.value).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
