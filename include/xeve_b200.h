@@ -1,0 +1,211 @@
+/*
+ * xeve_b200.h -- C ABI of the B200-native XEVE inter-search + transform hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no torch or
+ * CUDA types.  Each entry point replaces one of the reference's internal operator hooks for the
+ * path xeve_pinter -> xeve_sad / xeve_mc -> xeve_tq / xeve_itdq, in *batched* form: instead of one
+ * synchronous call per block, the caller hands over a work list (one record per call the
+ * reference would have made) and gets every result back.  Record fields carry exactly the
+ * arguments and the XEVE_PINTER / XEVE_CORE fields the reference hook reads.
+ *
+ *   entry point              replaces (reference file:line)
+ *   -----------------------  ---------------------------------------------------------------
+ *   xb200_pic_upload         xeve_imgb_cpy bit-depth convert (src_base/xeve_util.c:1552-1704)
+ *                            + xeve_picbuf_expand padding     (src_base/xeve_util.c:190-248)
+ *   xb200_sad / ssd / diff   xeve_func_sad/ssd/diff[log2w][log2h] (src_base/xeve_sad.h:40-68)
+ *   xb200_satd               xeve_func_satd[0] = xeve_had     (src_base/xeve_sad.c:1043-1140)
+ *   xb200_me                 pi->fn_me = pinter_me_epzs        (src_base/xeve_pinter.c:699-869,
+ *                            hook declared src_base/xeve_type.h:448)
+ *   xb200_mc                 pi->fn_mc -> xeve_mc              (src_base/xeve_mc.c:465-610,
+ *                            hook declared src_base/xeve_type.h:452)
+ *   xb200_tq                 ctx->fn_tq = xeve_sub_block_tq    (src_base/xeve_tq.c:750-864,
+ *                            hook declared src_base/xeve_type.h:982)
+ *   xb200_itdq               ctx->fn_itdp = xeve_itdq          (src_base/xeve_itdq.c:499-580)
+ *   xb200_recon              ctx->fn_recon -> xeve_recon_blk   (src_base/xeve_recon.c:35-57)
+ *   xb200_residue            the distortion/transform body of pinter_residue_rdo
+ *                            (src_base/xeve_pinter.c:961-1056): fn_mc -> xeve_diff_pred -> SSD ->
+ *                            fn_tq -> fn_itdp -> fn_recon -> SSD, fused on the device
+ *
+ * Status codes are the reference's own (inc/xeve.h:50-74): XB200_OK == XEVE_OK == 0, errors
+ * negative.  All functions are synchronous on return (results are in the caller's buffers).
+ * `mem` selects where the caller's *bulk* buffers live: XB200_MEM_HOST (the FFI case: staged
+ * through pinned memory, copies included in the call) or XB200_MEM_DEVICE (already in HBM).
+ * The library never falls back to a CPU implementation: without a usable sm_100 device
+ * xb200_create fails with XB200_ERR_UNSUPPORTED.
+ */
+#ifndef XEVE_B200_H_
+#define XEVE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB200_API __attribute__((visibility("default")))
+
+/* status codes (values of inc/xeve.h:50-74) */
+#define XB200_OK                   (0)
+#define XB200_ERR                  (-1)
+#define XB200_ERR_INVALID_ARGUMENT (-101)
+#define XB200_ERR_OUT_OF_MEMORY    (-102)
+#define XB200_ERR_UNSUPPORTED      (-104)
+#define XB200_ERR_UNEXPECTED       (-105)
+
+#define XB200_MEM_HOST   0
+#define XB200_MEM_DEVICE 1
+
+#define XB200_PAD_L 144 /* PIC_PAD_SIZE_L, src_base/xeve_def.h:380 */
+#define XB200_PAD_C 72  /* PIC_PAD_SIZE_C, src_base/xeve_def.h:381 */
+
+#define XB200_NUM_CTX_CC_RUN   24 /* src_base/xeve_def.h:722-724 */
+#define XB200_NUM_CTX_CC_LEVEL 24
+#define XB200_NUM_CTX_CC_LAST  2
+
+typedef struct xb200_ctx xb200_ctx; /* opaque */
+
+/* Sequence-level constants of the search: the XEVE_PINTER / XEVE_PARAM fields that stay fixed
+ * for an encoder instance (src_base/xeve_pinter.c:2087-2133). */
+typedef struct {
+    int32_t w, h;            /* picture size in luma samples (param.w/h aligned up to 8) */
+    int32_t bit_depth;       /* internal bit depth (10; src_base/xeve_enc.c:2298) */
+    int32_t me_level;        /* param.me_sub: 1 int-pel, 2 half-pel, 3 quarter-pel */
+    int32_t hpel_cnt;        /* param.me_sub_pos */
+    int32_t qpel_cnt;        /* param.me_sub_pos */
+    int32_t me_complexity;   /* param.me_algo */
+    int32_t min_clip[2];     /* -MAX_CU_SIZE + 1 */
+    int32_t max_clip[2];     /* param.w - 1, param.h - 1 */
+    int32_t merge_num, me_range, gop_size, rdoq, tool_iqt;
+} xb200_seq;
+
+/* One pi->fn_me call (in/out record). */
+typedef struct {
+    int32_t  poc;            /* pi->poc */
+    int32_t  cur_pic;        /* picture handle of the original (pi->o) */
+    int32_t  ref_pic;        /* picture handle of pi->refp[refi][lidx].pic */
+    int32_t  ref_poc;        /* pi->refp[refi][lidx].poc */
+    int16_t  x, y;
+    uint8_t  log2_cuw, log2_cuh, lidx, bi;
+    int8_t   refi;
+    uint8_t  num_refp;       /* pi->num_refp */
+    int16_t  mvp[2];
+    int16_t  mv_in[2];       /* mv[] on entry (start MV when bi != 0) */
+    uint32_t lambda_mv;      /* pi->lambda_mv */
+    int32_t  mot_bits_in[2]; /* pi->mot_bits[] on entry */
+    int32_t  max_search_range; /* pi->max_search_range */
+    int32_t  gop_size;       /* pi->gop_size */
+    int32_t  org_bi_off;     /* bi != 0: element offset of pi->org_bi (cuw*cuh s16) in `side`; else -1 */
+    /* results */
+    int16_t  mv_out[2];      /* mv[] on return (quarter-pel, relative to the CU) */
+    uint32_t cost;           /* return value */
+    int32_t  mot_bits_out[2];/* pi->mot_bits[] on return */
+} xb200_me_item;
+
+/* One pi->fn_mc call.  The prediction of item i (Y: w*h, then U, V: w*h/4 each, s16, stride = block
+ * width, exactly pred[0][Y_C..V_C]) is written at element offset pred_off[i] of the output. */
+typedef struct {
+    int32_t  poc;
+    int32_t  ref_pic[2];     /* picture handle per list, -1 when refi[l] is invalid */
+    int32_t  ref_poc[2];
+    int16_t  x, y, w, h;
+    int8_t   refi[2];
+    int16_t  mv[2][2];
+    uint64_t out_hash;       /* unused by the library (test bookkeeping) */
+} xb200_mc_item;
+
+/* CABAC-derived rate tables RDOQ reads (XEVE_CORE::rdoq_est_*, src_base/xeve_type.h:737-747). */
+typedef struct {
+    int32_t cbf_all[2], cbf_luma[2], cbf_cb[2], cbf_cr[2];
+    int32_t run[XB200_NUM_CTX_CC_RUN][2];
+    int32_t level[XB200_NUM_CTX_CC_LEVEL][2];
+    int32_t last[XB200_NUM_CTX_CC_LAST][2];
+} xb200_rates;
+
+/* One ctx->fn_tq call.  Input/output planes of item i live at element offset in_off of the
+ * coefficient buffer: Y (cuw*cuh) then U, V ((cuw/2)*(cuh/2) each), s16, in place. */
+typedef struct {
+    int32_t  poc;
+    uint8_t  log2_cuw, log2_cuh, slice_type, is_intra;
+    uint8_t  run_stats, qp[3];     /* core->qp_y/u/v (already + 6*(bd-8)) */
+    int32_t  rate_idx;             /* index into the xb200_rates array */
+    int64_t  in_off;
+    double   lambda[3];            /* core->lambda[] */
+    int32_t  nnz[3];               /* result */
+    uint64_t out_hash;             /* unused by the library */
+} xb200_tq_item;
+
+/* Fused residue work item = the distortion/transform body of pinter_residue_rdo for one
+ * candidate mode of one CU.  Outputs are written to per-item slots of size 3/2*cuw*cuh at
+ * element offset out_off in each of the coef / rec buffers. */
+typedef struct {
+    xb200_mc_item mc;              /* prediction to build (x, y, w, h, refi, mv, refs) */
+    int32_t  cur_pic;              /* picture handle of the original picture */
+    uint8_t  slice_type, run_stats, qp[3], pad_[3];
+    int32_t  rate_idx;
+    double   lambda[3];
+    int64_t  out_off;
+    /* results */
+    int32_t  nnz[3];
+    int64_t  dist_pred[3];         /* SSD(pred, org)  -- dist[0][] / dist_no_resi[] */
+    int64_t  dist_rec[3];          /* SSD(rec, org) where nnz != 0, else = dist_pred -- dist[1][] */
+} xb200_residue_item;
+
+/* Element-wise kernel probe (XEVE_FN_SAD / SSD / DIFF / SATD argument lists). Buffers are the
+ * picture planes; a block is addressed by picture handle, plane and (x, y) which may reach
+ * into the padding. */
+typedef struct {
+    int32_t pic1, pic2;
+    int16_t x1, y1, x2, y2;
+    uint8_t plane1, plane2, log2w, log2h;
+} xb200_blk_item;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+XB200_API int  xb200_create(xb200_ctx **out, int device, const xb200_seq *seq);
+XB200_API void xb200_destroy(xb200_ctx *c);
+XB200_API const char *xb200_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+XB200_API int64_t xb200_launch_count(const xb200_ctx *c);
+
+/* ---- pictures (device-resident, s16, 4:2:0) ------------------------------------------------ */
+/* padded != 0: planes carry PIC_PAD_SIZE_L/C of edge-replicated border like xeve_picbuf_alloc +
+ * xeve_picbuf_expand; padded == 0: original-picture layout, stride = w (src_base/xeve_enc.c:1942). */
+XB200_API int xb200_pic_create(xb200_ctx *c, int padded, int32_t *handle);
+XB200_API int xb200_pic_destroy(xb200_ctx *c, int32_t handle);
+/* planes[3]: caller's Y, U, V; stride_bytes[3]; in_bit_depth 8 (u8 samples) or 10..16 (u16 LE).
+ * Converts to the internal depth (left shift) and, for padded pictures, replicates the borders. */
+XB200_API int xb200_pic_upload(xb200_ctx *c, int32_t handle, const void *const planes[3], const int32_t stride_bytes[3],
+                               int in_bit_depth, int mem);
+/* raw s16 upload/download of the active area (internal samples) */
+XB200_API int xb200_pic_upload_s16(xb200_ctx *c, int32_t handle, const int16_t *const planes[3],
+                                   const int32_t stride_elems[3], int mem);
+XB200_API int xb200_pic_download(xb200_ctx *c, int32_t handle, int with_padding, int16_t *const planes[3],
+                                 const int32_t stride_elems[3]);
+
+/* ---- kernel probes ---------------------------------------------------------------------------- */
+XB200_API int xb200_sad(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem);
+XB200_API int xb200_ssd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int64_t *out, int mem);
+XB200_API int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem);
+
+/* ---- hot-path operators ----------------------------------------------------------------------- */
+/* side: s16 buffer holding the org_bi blocks referenced by org_bi_off (may be NULL if none). */
+XB200_API int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem);
+XB200_API int xb200_mc(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int64_t *pred_off, int16_t *pred,
+                       int64_t pred_elems, int mem);
+XB200_API int xb200_tq(xb200_ctx *c, xb200_tq_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates,
+                       int16_t *coef, int64_t coef_elems, int mem);
+/* dequantise + inverse transform the planes whose nnz[] is non-zero, in place (fn_itdp) */
+XB200_API int xb200_itdq(xb200_ctx *c, const xb200_tq_item *items, int64_t n, int16_t *coef, int64_t coef_elems, int mem);
+/* rec = clip(pred + resi) per plane where nnz != 0, else clip(pred) (fn_recon) */
+XB200_API int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16_t *resi, const int16_t *pred,
+                          int16_t *rec, int64_t elems, int mem);
+XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates,
+                            int64_t n_rates, int16_t *coef, int16_t *rec, int64_t elems, int mem);
+
+/* ---- timing aid for bench.py: device time (ms) of the kernels of the last call, measured with
+ *      CUDA events on the library's own stream ------------------------------------------------- */
+XB200_API double xb200_last_kernel_ms(const xb200_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEVE_B200_H_ */

@@ -1,0 +1,96 @@
+"""ctypes binding of oracle/liboracle.so (the scalar C restatement) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+
+class PLANES(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("s_l", C.c_int32), ("s_c", C.c_int32), ("w_l", C.c_int32), ("h_l", C.c_int32), ("poc", C.c_int32)]
+
+
+_lib = None
+VP = C.c_void_p
+I = C.c_int
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "liboracle.so")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.xo_sad.restype = I
+        L.xo_sad.argtypes = [I, I, VP, I, VP, I, I]
+        L.xo_ssd.restype = C.c_int64
+        L.xo_ssd.argtypes = [I, I, VP, I, VP, I, I]
+        L.xo_diff.restype = None
+        L.xo_diff.argtypes = [I, I, VP, I, VP, I, VP, I]
+        L.xo_satd.restype = I
+        L.xo_satd.argtypes = [I, I, VP, I, VP, I, I]
+        for f in (L.xo_mc_luma, L.xo_mc_chroma):
+            f.restype = None
+            f.argtypes = [VP, I, I, I, I, I, VP, I, I, I, I]
+        for f in (L.xo_fwd_transform, L.xo_inv_transform):
+            f.restype = None
+            f.argtypes = [VP, I, I, I]
+        L.xo_recon.restype = None
+        L.xo_recon.argtypes = [VP, VP, I, I, VP, I]
+        L.xo_pad_plane.restype = None
+        L.xo_pad_plane.argtypes = [VP, I, I, I, I]
+        L.xo_me_batch.restype = None
+        L.xo_me_batch.argtypes = [VP, VP, VP, VP, C.c_int64]
+        L.xo_mc_batch.restype = None
+        L.xo_mc_batch.argtypes = [VP, VP, VP, C.c_int64, VP, VP]
+        L.xo_tq_batch.restype = None
+        L.xo_tq_batch.argtypes = [VP, VP, C.c_int64, VP, VP, VP]
+        L.xo_residue_batch.restype = None
+        L.xo_residue_batch.argtypes = [VP, VP, VP, VP, C.c_int64, VP, VP]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(VP) if a is not None else None
+
+
+def me_batch(seq, planes, side, items):
+    out = items.copy()
+    lib().xo_me_batch(_p(seq), C.addressof(planes), _p(side), _p(out), len(out))
+    return out
+
+
+def mc_batch(seq, planes, items, off, total):
+    pred = np.zeros(total, np.int16)
+    lib().xo_mc_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(items)), len(items), _p(off), _p(pred))
+    return pred
+
+
+def tq_batch(seq, items, rates, coef_in, want_itdq=True):
+    items = items.copy()
+    coef = coef_in.copy()
+    resi = np.zeros_like(coef) if want_itdq else None
+    lib().xo_tq_batch(_p(seq), _p(items), len(items), _p(rates), _p(coef), _p(resi))
+    return items, coef, resi
+
+
+def residue_batch(seq, planes, rates, items, elems):
+    items = items.copy()
+    coef = np.zeros(elems, np.int16)
+    rec = np.zeros(elems, np.int16)
+    lib().xo_residue_batch(_p(seq), C.addressof(planes), _p(rates), _p(items), len(items), _p(coef), _p(rec))
+    return items, coef, rec

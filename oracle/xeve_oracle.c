@@ -1,0 +1,695 @@
+/*
+ * xeve_oracle.c -- TEST INFRASTRUCTURE ONLY: a plain scalar C restatement of the reference's
+ * inter-search + transform path, used as the checker in tests/, __graft_entry__.smoke() and the
+ * cpu_baseline leg of bench.py.  The shipped library never links or calls this file.
+ *
+ * Parity of this restatement is PINNED: tests/test_oracle_vs_ref.py checks every function here
+ * against the compiled reference itself (oracle/_ref, built by oracle/Makefile.ref from the
+ * sources under /root/reference) on random blocks and on work lists traced from real encodes,
+ * and tests/golden/ holds fixtures generated the same way for machines without /root/reference.
+ * (The reference ships no tests or golden vectors of its own)
+ *
+ * Each function cites the reference file:line it follows.  The code is written from the
+ * arithmetic, not transcribed: transforms are direct matrix products instead of butterflies,
+ * the motion search is expressed as "build the candidate list of this round, then take the
+ * first strict minimum", RDOQ as a two-pass scan.
+ */
+#include "xeve_oracle.h"
+#include "../xeve_b200/csrc/xb200_tables.h"
+#include <stdlib.h>
+#include <string.h>
+
+static int8_t   g_tm64[64 * 64];
+static uint16_t g_scan[7][4096]; /* square blocks, index log2 size */
+static int      g_init;
+
+static void oracle_init(void)
+{
+    if(g_init) return;
+    xb200_gen_tm64(g_tm64);
+    for(int l = 1; l <= 6; l++) xb200_gen_scan(g_scan[l], l, l);
+    g_init = 1;
+}
+static inline int tm(int log2n, int k, int n) { return g_tm64[(k << (6 - log2n)) * 64 + n]; }
+static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+
+/* ---------------------------------------------------------------------------------------------
+ * distortion kernels
+ * ------------------------------------------------------------------------------------------- */
+/* src_base/xeve_sad.c:40-61: sum |a-b| then >> (bd-8).  XEVE_ABS16 (src_base/xeve_util.h:55) is a
+ * 16-bit sign-fold applied to the int difference; identical to abs() while |d| < 32768. */
+int xo_sad(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd)
+{
+    int sum = 0;
+    for(int y = 0; y < h; y++, a += sa, b += sb)
+        for(int x = 0; x < w; x++) {
+            int d = (int)a[x] - (int)b[x];
+            sum += (d ^ (d >> 15)) - (d >> 15);
+        }
+    return sum >> (bd - 8);
+}
+
+/* src_base/xeve_sad.c:275-297: each squared difference is shifted before summing */
+int64_t xo_ssd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd)
+{
+    const int sh  = (bd - 8) << 1;
+    int64_t   sum = 0;
+    for(int y = 0; y < h; y++, a += sa, b += sb)
+        for(int x = 0; x < w; x++) {
+            int d = a[x] - b[x];
+            sum += (d * d) >> sh;
+        }
+    return sum;
+}
+
+/* src_base/xeve_sad.c:160-178 */
+void xo_diff(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int16_t *d, int sd)
+{
+    for(int y = 0; y < h; y++, a += sa, b += sb, d += sd)
+        for(int x = 0; x < w; x++) d[x] = (int16_t)(a[x] - b[x]);
+}
+
+/* Hadamard SATD for square blocks (what Baseline reaches): 8x8 tiles when both sides are
+ * multiples of 8, else 4x4 tiles.  src_base/xeve_sad.c:417-607 (tiles), 1043-1140 (dispatch).
+ * Per tile: sum of |H d H^T| with the DC term >> 2, then (s+2)>>2 (8x8) or (s+1)>>1 (4x4). */
+static int had_tile(const int16_t *a, int sa, const int16_t *b, int sb, int n)
+{
+    int m[8][8], t[8][8];
+    for(int y = 0; y < n; y++)
+        for(int x = 0; x < n; x++) m[y][x] = a[y * sa + x] - b[y * sb + x];
+    /* unnormalised Walsh-Hadamard along rows then columns (order of outputs is irrelevant for
+     * the sum of magnitudes; only the all-plus (DC) output is treated specially) */
+    for(int pass = 0; pass < 2; pass++) {
+        for(int r = 0; r < n; r++) {
+            int v[8];
+            for(int i = 0; i < n; i++) v[i] = pass ? m[i][r] : m[r][i];
+            for(int len = 1; len < n; len <<= 1)
+                for(int i = 0; i < n; i += len << 1)
+                    for(int j = i; j < i + len; j++) {
+                        int p = v[j], q = v[j + len];
+                        v[j] = p + q; v[j + len] = p - q;
+                    }
+            for(int i = 0; i < n; i++) if(pass) t[i][r] = v[i]; else t[r][i] = v[i];
+        }
+        memcpy(m, t, sizeof(m));
+    }
+    int s = abs(m[0][0]) >> 2;
+    for(int y = 0; y < n; y++)
+        for(int x = 0; x < n; x++) if(x | y) s += abs(m[y][x]);
+    return n == 8 ? (s + 2) >> 2 : (s + 1) >> 1;
+}
+
+int xo_satd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd)
+{
+    int n = (w % 8 == 0 && h % 8 == 0) ? 8 : 4, sum = 0;
+    for(int y = 0; y < h; y += n)
+        for(int x = 0; x < w; x += n) sum += had_tile(a + y * sa + x, sa, b + y * sb + x, sb, n);
+    return sum >> (bd - 8);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * motion compensation
+ * ------------------------------------------------------------------------------------------- */
+static const int16_t k_luma[4][8]   = XB200_MC_L_TAPS;
+static const int16_t k_chroma[8][4] = XB200_MC_C_TAPS;
+
+/* Generic separable interpolation, `taps` taps (8 luma / 4 chroma).
+ * 1-D cases: sum >> 6 with no rounding offset (src_base/xeve_mc.h:36-48, xeve_mc.c:122-182);
+ * 2-D: horizontal pass >> min(4, bd-8) into s16, vertical pass (sum + 2^(s2-1)) >> s2 with
+ * s2 = max(8, 20-bd) (src_base/xeve_mc.c:184-254, 337-381); result clipped to [0, 2^bd-1].
+ * fx/fy: filter phase selected from the sub-sample bits of the (already clipped) position;
+ * want_h/want_v: which passes run -- chosen by the caller from the UNCLIPPED mv (quirk q9). */
+static void interp(const int16_t *ref, int sr, int ix, int iy, const int16_t *ch, const int16_t *cv, int taps,
+                   int want_h, int want_v, int16_t *pred, int sp, int w, int h, int bd)
+{
+    const int maxv = (1 << bd) - 1, half = taps / 2 - 1;
+    if(!want_h && !want_v) {
+        for(int y = 0; y < h; y++) memcpy(pred + y * sp, ref + (iy + y) * sr + ix, sizeof(int16_t) * w);
+        return;
+    }
+    if(want_h && !want_v) {
+        for(int y = 0; y < h; y++)
+            for(int x = 0; x < w; x++) {
+                const int16_t *p = ref + (iy + y) * sr + ix + x - half;
+                int acc = 0;
+                for(int t = 0; t < taps; t++) acc += ch[t] * p[t];
+                pred[y * sp + x] = (int16_t)clip3(0, maxv, acc >> 6);
+            }
+        return;
+    }
+    if(!want_h && want_v) {
+        for(int y = 0; y < h; y++)
+            for(int x = 0; x < w; x++) {
+                const int16_t *p = ref + (iy + y - half) * sr + ix + x;
+                int acc = 0;
+                for(int t = 0; t < taps; t++) acc += cv[t] * p[t * sr];
+                pred[y * sp + x] = (int16_t)clip3(0, maxv, acc >> 6);
+            }
+        return;
+    }
+    const int s1 = bd - 8 < 4 ? bd - 8 : 4, s2 = 20 - bd > 8 ? 20 - bd : 8;
+    int16_t  *tmp = malloc(sizeof(int16_t) * w * (h + taps - 1));
+    for(int y = 0; y < h + taps - 1; y++)
+        for(int x = 0; x < w; x++) {
+            const int16_t *p = ref + (iy + y - half) * sr + ix + x - half;
+            int acc = 0;
+            for(int t = 0; t < taps; t++) acc += ch[t] * p[t];
+            tmp[y * w + x] = (int16_t)(acc >> s1);
+        }
+    for(int y = 0; y < h; y++)
+        for(int x = 0; x < w; x++) {
+            int acc = 0;
+            for(int t = 0; t < taps; t++) acc += cv[t] * tmp[(y + t) * w + x];
+            pred[y * sp + x] = (int16_t)clip3(0, maxv, (acc + (1 << (s2 - 1))) >> s2);
+        }
+    free(tmp);
+}
+
+/* luma block at absolute position (gx, gy) in quarter-pel; sel_x/sel_y = the mv the filter
+ * choice is made from (xeve_mc_l macro, src_base/xeve_mc.h:94-97) */
+void xo_mc_luma(const int16_t *ref, int sr, int gx, int gy, int sel_x, int sel_y, int16_t *pred, int sp, int w, int h,
+                int bd)
+{
+    interp(ref, sr, gx >> 2, gy >> 2, k_luma[gx & 3], k_luma[gy & 3], 8, (sel_x & 3) != 0, (sel_y & 3) != 0, pred, sp,
+           w, h, bd);
+}
+/* chroma (4:2:0): position in eighth-pel of the chroma grid = the luma quarter-pel value */
+void xo_mc_chroma(const int16_t *ref, int sr, int gx, int gy, int sel_x, int sel_y, int16_t *pred, int sp, int w,
+                  int h, int bd)
+{
+    interp(ref, sr, gx >> 3, gy >> 3, k_chroma[gx & 7], k_chroma[gy & 7], 4, (sel_x & 7) != 0, (sel_y & 7) != 0, pred,
+           sp, w, h, bd);
+}
+
+/* src_base/xeve_mc.c:401-447 (xeve_mv_clip) + 465-610 (xeve_mc): uni/bi prediction of Y,U,V.
+ * pred: Y (w*h) | U (w/2*h/2) | V, stride = block width. */
+void xo_mc(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int16_t *pred)
+{
+    const int w = it->w, h = it->h, x = it->x, y = it->y, bd = sq->bit_depth;
+    const int ny = w * h, nc = ny / 4;
+    int16_t  *buf[2] = {pred, NULL};
+    int       mvt[2][2], n = 0;
+    for(int l = 0; l < 2; l++) {
+        mvt[l][0] = it->mv[l][0]; mvt[l][1] = it->mv[l][1];
+        if(it->refi[l] < 0) continue;
+        const int lo = -(128 << 2), hx = (sq->w - 1 + 128) << 2, hy = (sq->h - 1 + 128) << 2;
+        if((x << 2) + it->mv[l][0] < lo) mvt[l][0] = lo - (x << 2);
+        if((y << 2) + it->mv[l][1] < lo) mvt[l][1] = lo - (y << 2);
+        if((x << 2) + it->mv[l][0] + (w << 2) - 4 > hx) mvt[l][0] = hx - (x << 2) - (w << 2) + 4;
+        if((y << 2) + it->mv[l][1] + (h << 2) - 4 > hy) mvt[l][1] = hy - (y << 2) - (h << 2) + 4;
+        mvt[l][0] = (int16_t)mvt[l][0]; mvt[l][1] = (int16_t)mvt[l][1];
+    }
+    for(int l = 0; l < 2; l++) {
+        if(it->refi[l] < 0) continue;
+        if(l == 1 && it->refi[0] >= 0) {
+            /* identical-motion shortcut, src_base/xeve_mc.c:545-551 */
+            if(it->ref_poc[0] == it->ref_poc[1] && mvt[0][0] == mvt[1][0] && mvt[0][1] == mvt[1][1]) return;
+        }
+        const xo_planes *r = &pl[it->ref_pic[l]];
+        int16_t *dst = n == 0 ? pred : (buf[1] = malloc(sizeof(int16_t) * (ny + 2 * nc)));
+        int gx = (x << 2) + mvt[l][0], gy = (y << 2) + mvt[l][1];
+        xo_mc_luma(r->y, r->s_l, gx, gy, it->mv[l][0], it->mv[l][1], dst, w, w, h, bd);
+        xo_mc_chroma(r->u, r->s_c, gx, gy, it->mv[l][0], it->mv[l][1], dst + ny, w / 2, w / 2, h / 2, bd);
+        xo_mc_chroma(r->v, r->s_c, gx, gy, it->mv[l][0], it->mv[l][1], dst + ny + nc, w / 2, w / 2, h / 2, bd);
+        n++;
+    }
+    if(n == 2) { /* src_base/xeve_mc.c:449-463: (a + b + 1) >> 1, no clip */
+        for(int i = 0; i < ny + 2 * nc; i++) pred[i] = (int16_t)((pred[i] + buf[1][i] + 1) >> 1);
+        free(buf[1]);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * transforms
+ * ------------------------------------------------------------------------------------------- */
+/* src_base/xeve_tq.c:396-404 + tx_pb*b: stage 0 exact (rows, shift 0), stage 1 (columns) rounded by
+ * shift = (log2w - 1 + bd - 8) + (log2h + 6) (src_base/xeve_util.c:34-35), result truncated to s16.
+ * The 64-point transform only produces outputs 0..31 (src_base/xeve_tq.c:318-381). */
+void xo_fwd_transform(int16_t *blk, int log2w, int log2h, int bd)
+{
+    oracle_init();
+    const int w = 1 << log2w, h = 1 << log2h;
+    const int shift = (log2w - 1 + bd - 8) + (log2h + 6);
+    const int kw = w == 64 ? 32 : w, kh = h == 64 ? 32 : h;
+    int32_t  *t = calloc((size_t)w * h, sizeof(int32_t)); /* t[u][y] */
+    for(int y = 0; y < h; y++)
+        for(int u = 0; u < kw; u++) {
+            int64_t acc = 0;
+            for(int x = 0; x < w; x++) acc += (int64_t)tm(log2w, u, x) * blk[y * w + x];
+            t[u * h + y] = (int32_t)acc;
+        }
+    for(int u = 0; u < w; u++)
+        for(int v = 0; v < h; v++) {
+            int64_t acc = 0;
+            if(v < kh) {
+                for(int y = 0; y < h; y++) acc += (int64_t)tm(log2h, v, y) * t[u * h + y];
+                acc = (acc + ((int64_t)1 << (shift - 1))) >> shift;
+            }
+            blk[v * w + u] = (int16_t)acc;
+        }
+    free(t);
+}
+
+/* src_base/xeve_itdq.c:435-440 + xeve_itx_pb*b: columns first (shift 0, clip to s32), then rows
+ * with shift 7 + 12 - (bd - 8), clip to s16. */
+void xo_inv_transform(int16_t *blk, int log2w, int log2h, int bd)
+{
+    oracle_init();
+    const int w = 1 << log2w, h = 1 << log2h, shift = 7 + 12 - (bd - 8);
+    int32_t  *t = malloc(sizeof(int32_t) * w * h); /* t[u][y] */
+    for(int u = 0; u < w; u++)
+        for(int y = 0; y < h; y++) {
+            int64_t acc = 0;
+            for(int v = 0; v < h; v++) acc += (int64_t)tm(log2h, v, y) * blk[v * w + u];
+            t[u * h + y] = acc <= INT32_MIN ? INT32_MIN : acc >= INT32_MAX ? INT32_MAX : (int32_t)acc;
+        }
+    for(int y = 0; y < h; y++)
+        for(int x = 0; x < w; x++) {
+            int64_t acc = 0;
+            for(int u = 0; u < w; u++) acc += (int64_t)tm(log2w, u, x) * t[u * h + y];
+            acc = (acc + ((int64_t)1 << (shift - 1))) >> shift;
+            blk[y * w + x] = (int16_t)(acc < -32768 ? -32768 : acc > 32767 ? 32767 : acc);
+        }
+    free(t);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * quantisation with RDOQ (square blocks), src_base/xeve_tq.c:425-730
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const xb200_rates *r; int ctx; int64_t lambda; } rate_env;
+
+/* get_ic_rate_cost_rl, src_base/xeve_tq.c:425-457 */
+static int64_t level_rate(const rate_env *e, uint32_t lev, int run_is_zero)
+{
+    int32_t        rate;
+    const int32_t *rr = e->r->run[e->ctx + (run_is_zero ? 0 : 1)];
+    if(lev == 0) rate = rr[1];
+    else {
+        rate = 32768 + rr[0];
+        if(lev == 1) rate += e->r->level[e->ctx][0];
+        else rate += e->r->level[e->ctx][1] + e->r->level[e->ctx + 1][1] * (int32_t)(lev - 2) + e->r->level[e->ctx + 1][0];
+    }
+    return (int64_t)rate * e->lambda;
+}
+
+int xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intra, int ch, int slice_type,
+                  const xb200_rates *rt, int bd)
+{
+    oracle_init();
+    static const int qs[6] = XB200_QUANT_SCALE;
+    const int        n = 1 << (2 * log2n), q = qs[qp % 6];
+    const int        qbits = 14 + (15 - bd - log2n) + qp / 6;
+    /* zero-block pre-test, src_base/xeve_tq.c:666-700 (slice_type: 2 == SLICE_I in the reference) */
+    {
+        int64_t off = (int64_t)(slice_type == 2 ? 201 : 153) << (qbits - 9), thr = ((int64_t)1 << qbits) - off;
+        int     coded = 0;
+        for(int i = 0; i < n && !coded; i++) coded = (int64_t)abs(coef[i]) * q >= thr;
+        if(!coded) { memset(coef, 0, sizeof(int16_t) * n); return 0; }
+    }
+    const uint16_t *scan = g_scan[log2n];
+    const int64_t   es = xb200_err_scale(qp % 6, log2n, bd);
+    rate_env        e  = {rt, ch == 0 ? 0 : 2, (int64_t)(d_lambda * 32768.0 + 0.5)};
+    int64_t *ld   = malloc(sizeof(int64_t) * n);
+    int32_t *maxl = malloc(sizeof(int32_t) * n);
+    int16_t *out  = calloc(n, sizeof(int16_t));
+    int64_t  uncoded_blk = 0;
+    long     sum_all = 0;
+    for(int i = 0; i < n; i++) { /* position order is irrelevant for this pass */
+        int64_t t = (int64_t)abs(coef[i]) * q, cap = (int64_t)INT32_MAX - ((int64_t)1 << (qbits - 1));
+        int64_t v = (int32_t)(t < cap ? t : cap);
+        ld[i]     = v;
+        uint32_t m = (uint32_t)(v >> qbits);
+        if(v - ((int64_t)m << qbits) >= ((int64_t)1 << (qbits - 1))) m++;
+        maxl[i]  = (int32_t)m;
+        int64_t err = (v * es) >> 20;
+        uncoded_blk += err * err;
+        sum_all += m;
+    }
+    int nnz = 0;
+    if(sum_all) {
+        const int32_t *cbf = (!is_intra && ch == 0) ? rt->cbf_all : ch == 0 ? rt->cbf_luma : ch == 1 ? rt->cbf_cb : rt->cbf_cr;
+        int64_t best = uncoded_blk + (int64_t)cbf[0] * e.lambda, base = uncoded_blk + (int64_t)cbf[1] * e.lambda;
+        const int32_t *last = rt->last[ch == 0 ? 0 : 1];
+        int run = 0, best_last = 0;
+        for(int sp = 0; sp < n; sp++) {
+            int      p = scan[sp];
+            /* get_coded_level_rl, src_base/xeve_tq.c:459-489: candidates max, max-1 (>= 1), else 0 */
+            int64_t  err0 = (ld[p] * es) >> 20, unc = err0 * err0;
+            int64_t  cod = unc + level_rate(&e, 0, run == 0);
+            uint32_t lev = 0, mx = (uint32_t)maxl[p], mn = mx > 1 ? mx - 1 : 1;
+            for(uint32_t a = mx; a >= mn; a--) {
+                int64_t d = ld[p] - ((int64_t)a << qbits), er = (d * es) >> 20;
+                int64_t c = er * er + level_rate(&e, a, run == 0);
+                if(c < cod) { lev = a; cod = c; }
+            }
+            out[p] = (int16_t)((coef[p] > 0 ? maxl[p] : -maxl[p]) < 0 ? -(int32_t)lev : (int32_t)lev);
+            base += cod - unc;
+            if(lev) {
+                int64_t as_last = base + (int64_t)last[1] * e.lambda;
+                base += (int64_t)last[0] * e.lambda;
+                if(as_last < best) { best = as_last; best_last = sp + 1; }
+                run = 0;
+            }
+            else run++;
+        }
+        for(int sp = 0; sp < n; sp++) {
+            int p = scan[sp];
+            if(sp < best_last) nnz += out[p] != 0; else out[p] = 0;
+        }
+    }
+    memcpy(coef, out, sizeof(int16_t) * n);
+    free(ld); free(maxl); free(out);
+    return nnz;
+}
+
+/* plain quantiser (rdoq == 0), src_base/xeve_tq.c:704-727 */
+int xo_quant_plain(int16_t *coef, int log2n, int qp, int slice_type, int bd)
+{
+    static const int qs[6] = XB200_QUANT_SCALE;
+    const int n = 1 << (2 * log2n), shift = 14 + (15 - bd - log2n) + qp / 6;
+    const int32_t off = (int32_t)(slice_type == 2 ? 171 : 85) << (shift - 9);
+    int       nnz = 0;
+    for(int i = 0; i < n; i++) {
+        int32_t lev = (int16_t)(((int32_t)abs(coef[i]) * qs[qp % 6] + off) >> shift);
+        coef[i]     = (int16_t)(coef[i] < 0 ? -lev : lev);
+        nnz += coef[i] != 0;
+    }
+    return nnz;
+}
+
+/* xeve_sub_block_tq for CU <= 64 (one transform block per plane), src_base/xeve_tq.c:750-864.
+ * planes: Y | U | V contiguous; returns nnz per plane. */
+void xo_tq(const xb200_seq *sq, const xb200_tq_item *it, const xb200_rates *rates, int16_t *planes, int nnz[3])
+{
+    const int ny = 1 << (it->log2_cuw + it->log2_cuh), nc = ny >> 2;
+    int16_t  *p[3] = {planes, planes + ny, planes + ny + nc};
+    for(int c = 0; c < 3; c++) {
+        nnz[c] = 0;
+        if(!((it->run_stats >> c) & 1)) continue;
+        int l2 = c ? it->log2_cuw - 1 : it->log2_cuw;
+        xo_fwd_transform(p[c], l2, l2, sq->bit_depth);
+        nnz[c] = sq->rdoq ? xo_quant_rdoq(p[c], l2, it->qp[c], it->lambda[c], it->is_intra, c, it->slice_type,
+                                          &rates[it->rate_idx], sq->bit_depth)
+                          : xo_quant_plain(p[c], l2, it->qp[c], it->slice_type, sq->bit_depth);
+    }
+}
+
+/* xeve_itdq for CU <= 64, src_base/xeve_itdq.c:442-580: dequantise (scale << qp/6, rounded shift,
+ * clip s16) then inverse transform, for the planes with nnz != 0 */
+void xo_itdq(const xb200_seq *sq, const xb200_tq_item *it, int16_t *planes, const int nnz[3])
+{
+    static const int dq[6] = XB200_DEQUANT_SCALE;
+    const int ny = 1 << (it->log2_cuw + it->log2_cuh), nc = ny >> 2;
+    int16_t  *p[3] = {planes, planes + ny, planes + ny + nc};
+    for(int c = 0; c < 3; c++) {
+        if(!nnz[c]) continue;
+        int     l2 = c ? it->log2_cuw - 1 : it->log2_cuw, n = 1 << (2 * l2);
+        int     shift = 20 - 14 - (15 - sq->bit_depth - l2);
+        int64_t scale = (int64_t)dq[it->qp[c] % 6] << (it->qp[c] / 6), off = shift ? 1 << (shift - 1) : 0;
+        for(int i = 0; i < n; i++) {
+            int64_t v = (p[c][i] * scale + off) >> shift;
+            p[c][i]   = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+        }
+        xo_inv_transform(p[c], l2, l2, sq->bit_depth);
+    }
+}
+
+/* src_base/xeve_recon.c:35-57; the sum is formed in s16 */
+void xo_recon(const int16_t *resi, const int16_t *pred, int is_coef, int n, int16_t *rec, int bd)
+{
+    const int maxv = (1 << bd) - 1;
+    for(int i = 0; i < n; i++) {
+        int16_t t = is_coef ? (int16_t)(resi[i] + pred[i]) : pred[i];
+        rec[i]    = (int16_t)clip3(0, maxv, t);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * integer + sub-pel motion search, src_base/xeve_pinter.c:122-140, 363-869
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const xb200_seq *sq;
+    const int16_t   *org;  int so;   /* original block or the 2*org - pred block of bi search */
+    const int16_t   *ref;  int sr;   /* reference luma, active-area origin */
+    int      x, y, w, h, bi, other_bits, num_refp, refi;
+    uint32_t lambda_mv;
+    int      gmvp[2], lo[2], hi[2];  /* predictor in frame coordinates; current search window */
+    int      dyn_range;              /* distance-scaled search range */
+    int      static_range;           /* pi->max_search_range */
+} search_t;
+
+typedef struct { int x, y; } pt;
+
+static void set_window(search_t *s, int cx, int cy, int bi_mode)
+{
+    int r = bi_mode ? 5 : s->dyn_range;
+    s->lo[0] = clip3(s->sq->min_clip[0], s->sq->max_clip[0], cx - r);
+    s->hi[0] = clip3(s->sq->min_clip[0], s->sq->max_clip[0], cx + r);
+    s->lo[1] = clip3(s->sq->min_clip[1], s->sq->max_clip[1], cy - r);
+    s->hi[1] = clip3(s->sq->min_clip[1], s->sq->max_clip[1], cy + r);
+}
+
+static uint32_t mv_cost(const search_t *s, int qx, int qy, int *bits_out)
+{
+    int bits = xb200_mv_bits(qx - s->gmvp[0], qy - s->gmvp[1], s->num_refp, s->refi);
+    if(s->bi) bits += s->other_bits;
+    *bits_out = bits;
+    return (uint32_t)((s->lambda_mv * (uint32_t)bits + (1u << 15)) >> 16);
+}
+
+static uint32_t int_cost(const search_t *s, int px, int py, int *bits)
+{
+    if(px < s->lo[0] || px > s->hi[0] || py < s->lo[1] || py > s->hi[1]) return UINT32_MAX;
+    uint32_t c   = mv_cost(s, px << 2, py << 2, bits);
+    int      sad = xo_sad(s->w, s->h, s->org, s->so, s->ref + py * s->sr + px, s->sr, s->sq->bit_depth);
+    return c + (uint32_t)(s->bi ? sad >> 1 : sad);
+}
+
+/* one me_ipel_diamond run; returns best cost, writes best integer position, the step at which
+ * the best was found (only when something was found) and the bit count of the winner */
+static uint32_t diamond(search_t *s, int sx, int sy, int patience, pt *best_out, int *found_step, int *best_bits)
+{
+    static const int8_t d8[9][2]   = {{-2, 0}, {-1, 1}, {0, 2}, {1, 1}, {2, 0}, {1, -1}, {0, -2}, {-1, -1}, {0, 0}};
+    static const int8_t d16[16][2] = {{-4, 0}, {-3, 1}, {-2, 2}, {-1, 3}, {0, 4}, {1, 3}, {2, 2}, {3, 1},
+                                      {4, 0}, {3, -1}, {2, -2}, {1, -3}, {0, -4}, {-1, -3}, {-2, -2}, {-3, -1}};
+    pt       c0 = {clip3(s->sq->min_clip[0], s->sq->max_clip[0], sx), clip3(s->sq->min_clip[1], s->sq->max_clip[1], sy)};
+    pt       best = c0;
+    uint32_t best_cost = UINT32_MAX;
+    int      misses = 0, step = 0;
+    *best_bits = 0;
+    for(;;) {
+        pt  cand[128];
+        int n = 0, this_step;
+        misses++;
+        if(step <= 2) { /* dense window around the running best */
+            int r  = s->bi == 1 ? 5 : 2;
+            int x0 = best.x <= s->lo[0] ? best.x : best.x - r, x1 = best.x >= s->hi[0] ? best.x : best.x + r;
+            int y0 = best.y <= s->lo[1] ? best.y : best.y - r, y1 = best.y >= s->hi[1] ? best.y : best.y + r;
+            for(int yy = y0; yy <= y1; yy++)
+                for(int xx = x0; xx <= x1; xx++) cand[n++] = (pt){xx, yy};
+            this_step = 2;
+        }
+        else if(step <= 8) { /* 4 axis points at step 4, 8-point diamond at step 8, plus the centre */
+            for(int i = 0; i < 9; i++) {
+                if(step == 4 && (i & 1)) continue;
+                cand[n++] = (pt){c0.x + (step >> 1) * d8[i][0], c0.y + (step >> 1) * d8[i][1]};
+            }
+            this_step = step;
+        }
+        else {
+            for(int i = 0; i < 16; i++) cand[n++] = (pt){c0.x + (step >> 2) * d16[i][0], c0.y + (step >> 2) * d16[i][1]};
+            this_step = step;
+        }
+        for(int i = 0; i < n; i++) {
+            int      bits;
+            uint32_t c = int_cost(s, (int16_t)cand[i].x, (int16_t)cand[i].y, &bits);
+            if(c < best_cost) {
+                best_cost = c; best = (pt){(int16_t)cand[i].x, (int16_t)cand[i].y};
+                *found_step = this_step; *best_bits = bits; misses = 0;
+            }
+        }
+        if(step <= 2) { /* the window is re-centred on the new best (quirk q6) */
+            set_window(s, best.x, best.y, s->bi == 1);
+            step += 2;
+        }
+        if(misses == patience || s->bi == 1) break;
+        step <<= 1;
+        if(step > s->static_range) break;
+    }
+    *best_out = best;
+    return best_cost;
+}
+
+static uint32_t subpel(const search_t *s, const int16_t mvi[2], int16_t mv[2], int *win_bits)
+{
+    static const int8_t hp[8][2] = {{-2, 0}, {-2, 2}, {0, 2}, {2, 2}, {2, 0}, {2, -2}, {0, -2}, {-2, -2}};
+    static const int8_t qp[8][2] = {{-1, 0}, {0, 1}, {1, 0}, {0, -1}, {-1, 1}, {1, 1}, {-1, -1}, {1, -1}};
+    int16_t *pred = malloc(sizeof(int16_t) * s->w * s->h);
+    uint32_t best = UINT32_MAX;
+    *win_bits = 0;
+    mv[0] = mvi[0]; mv[1] = mvi[1];
+    for(int stage = 0; stage < 2; stage++) {
+        if(stage == 1 && s->sq->me_level <= 2) break;
+        int cx = (int16_t)(mv[0] + (s->x << 2)), cy = (int16_t)(mv[1] + (s->y << 2));
+        int cnt = stage ? s->sq->qpel_cnt : s->sq->hpel_cnt;
+        for(int i = 0; i < cnt; i++) {
+            int qx = (int16_t)(cx + (stage ? qp[i][0] : hp[i][0])), qy = (int16_t)(cy + (stage ? qp[i][1] : hp[i][1]));
+            int      bits;
+            uint32_t c = mv_cost(s, qx, qy, &bits);
+            xo_mc_luma(s->ref, s->sr, qx, qy, qx, qy, pred, s->w, s->w, s->h, s->sq->bit_depth);
+            int sad = xo_sad(s->w, s->h, s->org, s->so, pred, s->w, s->sq->bit_depth);
+            c += (uint32_t)(s->bi ? sad >> 1 : sad);
+            if(c < best) {
+                best = c; mv[0] = (int16_t)(qx - (s->x << 2)); mv[1] = (int16_t)(qy - (s->y << 2));
+                if(stage) *win_bits = bits; /* the half-pel loop does not record its bits (quirk q3) */
+            }
+        }
+    }
+    free(pred);
+    return best;
+}
+
+void xo_me(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *it)
+{
+    search_t s;
+    memset(&s, 0, sizeof(s));
+    const xo_planes *cur = &pl[it->cur_pic], *ref = &pl[it->ref_pic];
+    s.sq = sq; s.x = it->x; s.y = it->y; s.w = 1 << it->log2_cuw; s.h = 1 << it->log2_cuh; s.bi = it->bi;
+    if(it->bi) { s.org = side + it->org_bi_off; s.so = s.w; }
+    else { s.org = cur->y + it->y * cur->s_l + it->x; s.so = cur->s_l; }
+    s.ref = ref->y; s.sr = ref->s_l;
+    s.lambda_mv = it->lambda_mv; s.num_refp = it->num_refp; s.refi = it->refi;
+    s.other_bits = it->mot_bits_in[it->lidx ? 0 : 1];
+    s.static_range = it->max_search_range;
+    {   /* get_range_ipel, src_base/xeve_pinter.c:122-140 */
+        int d = it->poc - it->ref_poc; if(d < 0) d = -d;
+        s.dyn_range = clip3(it->max_search_range >> 2, it->max_search_range,
+                            (it->max_search_range * d + (it->gop_size >> 1)) / it->gop_size);
+    }
+    s.gmvp[0] = (int16_t)(it->mvp[0] + (it->x << 2)); s.gmvp[1] = (int16_t)(it->mvp[1] + (it->y << 2));
+    int mot_bits[2] = {it->mot_bits_in[0], it->mot_bits_in[1]};
+    int16_t mv[2] = {it->mv_in[0], it->mv_in[1]};
+    const int16_t *start = it->bi == 1 ? mv : it->mvp;
+    int cx = clip3(sq->min_clip[0], sq->max_clip[0], it->x + (start[0] >> 2));
+    int cy = clip3(sq->min_clip[1], sq->max_clip[1], it->y + (start[1] >> 2));
+    set_window(&s, cx, cy, it->bi == 1);
+
+    uint32_t best = UINT32_MAX, c;
+    int      found = 0, beststep = 0, bits;
+    pt       b;
+    c = diamond(&s, (int16_t)(start[0] + (it->x << 2)) >> 2, (int16_t)(start[1] + (it->y << 2)) >> 2, 3, &b, &found, &bits);
+    if(it->bi != 1 && bits > 0) mot_bits[it->lidx] = bits;
+    if(c < best) {
+        best = c; mv[0] = (int16_t)((b.x - it->x) << 2); mv[1] = (int16_t)((b.y - it->y) << 2);
+        beststep = (abs(it->mvp[0] - mv[0]) < 2 && abs(it->mvp[1] - mv[1]) < 2) ? 0 : found;
+    }
+    /* me_raster (me_algo > 1, placebo only) is not part of the fast/medium presets: not restated */
+    while(it->bi != 1 && beststep > 0 && sq->me_complexity > 0) {
+        set_window(&s, it->x + (mv[0] >> 2), it->y + (mv[1] >> 2), 0);
+        beststep = 0;
+        c = diamond(&s, (int16_t)(mv[0] + (it->x << 2)) >> 2, (int16_t)(mv[1] + (it->y << 2)) >> 2, 2, &b, &found, &bits);
+        if(bits > 0) mot_bits[it->lidx] = bits;
+        if(c < best) {
+            best = c; mv[0] = (int16_t)((b.x - it->x) << 2); mv[1] = (int16_t)((b.y - it->y) << 2);
+            beststep = (abs(it->mvp[0] - mv[0]) < 2 && abs(it->mvp[1] - mv[1]) < 2) ? 0 : found;
+        }
+    }
+    if(sq->me_level > 1) {
+        int16_t t[2];
+        c = subpel(&s, mv, t, &bits);
+        if(!it->bi && bits > 0) mot_bits[it->lidx] = bits;
+        if(c < best) { best = c; mv[0] = t[0]; mv[1] = t[1]; }
+    }
+    else { /* me_ipel_refinement, src_base/xeve_pinter.c:272-361: 3x3 around the best */
+        static const int8_t o9[9][2] = {{0, 0}, {-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+        set_window(&s, it->x + (mv[0] >> 2), it->y + (mv[1] >> 2), it->bi == 1);
+        int ix = clip3(sq->min_clip[0], sq->max_clip[0], (int16_t)(mv[0] + (it->x << 2)) >> 2);
+        int iy = clip3(sq->min_clip[1], sq->max_clip[1], (int16_t)(mv[1] + (it->y << 2)) >> 2);
+        uint32_t rb = UINT32_MAX; pt rbp = {ix, iy}; int rbits = 0;
+        for(int i = 0; i < 9; i++) {
+            c = int_cost(&s, ix + o9[i][0], iy + o9[i][1], &bits);
+            if(c < rb) { rb = c; rbp = (pt){ix + o9[i][0], iy + o9[i][1]}; rbits = bits; }
+        }
+        if(it->bi != 1 && rbits > 0) mot_bits[it->lidx] = rbits;
+        if(rb < best) { best = rb; mv[0] = (int16_t)((rbp.x - it->x) << 2); mv[1] = (int16_t)((rbp.y - it->y) << 2); }
+    }
+    it->mv_out[0] = mv[0]; it->mv_out[1] = mv[1]; it->cost = best;
+    it->mot_bits_out[0] = mot_bits[0]; it->mot_bits_out[1] = mot_bits[1];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * fused residue item (the distortion/transform body of pinter_residue_rdo,
+ * src_base/xeve_pinter.c:961-1056)
+ * ------------------------------------------------------------------------------------------- */
+void xo_residue(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_residue_item *it,
+                int16_t *coef, int16_t *rec)
+{
+    const int w = it->mc.w, h = it->mc.h, ny = w * h, nc = ny / 4, bd = sq->bit_depth;
+    int       l2 = 0; while((1 << l2) < w) l2++;
+    int16_t  *pred = malloc(sizeof(int16_t) * (ny + 2 * nc)), *resi = malloc(sizeof(int16_t) * (ny + 2 * nc));
+    xo_mc(sq, pl, &it->mc, pred);
+    const xo_planes *o = &pl[it->cur_pic];
+    const int16_t   *org[3] = {o->y + it->mc.y * o->s_l + it->mc.x, o->u + (it->mc.y / 2) * o->s_c + it->mc.x / 2,
+                               o->v + (it->mc.y / 2) * o->s_c + it->mc.x / 2};
+    const int so[3] = {o->s_l, o->s_c, o->s_c}, off[3] = {0, ny, ny + nc}, bw[3] = {w, w / 2, w / 2}, bh[3] = {h, h / 2, h / 2};
+    for(int c = 0; c < 3; c++) {
+        xo_diff(bw[c], bh[c], org[c], so[c], pred + off[c], bw[c], coef + off[c], bw[c]);
+        it->dist_pred[c] = xo_ssd(bw[c], bh[c], pred + off[c], bw[c], org[c], so[c], bd);
+    }
+    xb200_tq_item tq;
+    memset(&tq, 0, sizeof(tq));
+    tq.log2_cuw = tq.log2_cuh = (uint8_t)l2; tq.slice_type = it->slice_type; tq.is_intra = 0; tq.run_stats = it->run_stats;
+    memcpy(tq.qp, it->qp, 3); tq.rate_idx = it->rate_idx; memcpy(tq.lambda, it->lambda, sizeof(tq.lambda));
+    xo_tq(sq, &tq, rates, coef, it->nnz);
+    memcpy(resi, coef, sizeof(int16_t) * (ny + 2 * nc));
+    xo_itdq(sq, &tq, resi, it->nnz);
+    for(int c = 0; c < 3; c++) {
+        xo_recon(resi + off[c], pred + off[c], it->nnz[c] != 0, bw[c] * bh[c], rec + off[c], bd);
+        it->dist_rec[c] = it->nnz[c] ? xo_ssd(bw[c], bh[c], rec + off[c], bw[c], org[c], so[c], bd) : it->dist_pred[c];
+    }
+    free(pred); free(resi);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * picture preparation: input-depth -> internal depth (src_base/xeve_util.c:1552-1571) and edge
+ * replication of the PIC_PAD border (src_base/xeve_util.c:190-248)
+ * ------------------------------------------------------------------------------------------- */
+void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad)
+{
+    int16_t *a = buf + pad * stride + pad;
+    for(int y = 0; y < h; y++) {
+        for(int x = 1; x <= pad; x++) { a[y * stride - x] = a[y * stride]; a[y * stride + w - 1 + x] = a[y * stride + w - 1]; }
+    }
+    for(int y = 1; y <= pad; y++) {
+        memcpy(a - y * stride - pad, a - pad, sizeof(int16_t) * (w + 2 * pad));
+        memcpy(a + (h - 1 + y) * stride - pad, a + (h - 1) * stride - pad, sizeof(int16_t) * (w + 2 * pad));
+    }
+}
+
+/* batch drivers --------------------------------------------------------------------------------- */
+void xo_me_batch(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *items, int64_t n)
+{
+    for(int64_t i = 0; i < n; i++) xo_me(sq, pl, side, &items[i]);
+}
+void xo_mc_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n, const int64_t *off,
+                 int16_t *pred)
+{
+    for(int64_t i = 0; i < n; i++) xo_mc(sq, pl, &items[i], pred + off[i]);
+}
+void xo_tq_batch(const xb200_seq *sq, xb200_tq_item *items, int64_t n, const xb200_rates *rates, int16_t *coef,
+                 int16_t *resi)
+{
+    for(int64_t i = 0; i < n; i++) {
+        xo_tq(sq, &items[i], rates, coef + items[i].in_off, items[i].nnz);
+        if(resi) {
+            int sz = (3 << (items[i].log2_cuw + items[i].log2_cuh)) >> 1;
+            memcpy(resi + items[i].in_off, coef + items[i].in_off, sizeof(int16_t) * sz);
+            xo_itdq(sq, &items[i], resi + items[i].in_off, items[i].nnz);
+        }
+    }
+}
+void xo_residue_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_residue_item *items,
+                      int64_t n, int16_t *coef, int16_t *rec)
+{
+    for(int64_t i = 0; i < n; i++) xo_residue(sq, pl, rates, &items[i], coef + items[i].out_off, rec + items[i].out_off);
+}

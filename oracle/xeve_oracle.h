@@ -1,0 +1,41 @@
+/* xeve_oracle.h -- TEST INFRASTRUCTURE ONLY: prototypes of the scalar CPU restatement
+ * (oracle/xeve_oracle.c).  Work-list records are the C-ABI's own (include/xeve_b200.h). */
+#ifndef XEVE_ORACLE_H_
+#define XEVE_ORACLE_H_
+#include "../include/xeve_b200.h"
+
+typedef struct {          /* one picture: pointers to the top-left sample of the active area */
+    int16_t *y, *u, *v;
+    int32_t  s_l, s_c, w_l, h_l, poc;
+} xo_planes;
+
+#define XO_API __attribute__((visibility("default")))
+XO_API int     xo_sad(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd);
+XO_API int64_t xo_ssd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd);
+XO_API void    xo_diff(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int16_t *d, int sd);
+XO_API int     xo_satd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd);
+XO_API void xo_mc_luma(const int16_t *ref, int sr, int gx, int gy, int sel_x, int sel_y, int16_t *pred, int sp, int w,
+                       int h, int bd);
+XO_API void xo_mc_chroma(const int16_t *ref, int sr, int gx, int gy, int sel_x, int sel_y, int16_t *pred, int sp, int w,
+                         int h, int bd);
+XO_API void xo_mc(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int16_t *pred);
+XO_API void xo_fwd_transform(int16_t *blk, int log2w, int log2h, int bd);
+XO_API void xo_inv_transform(int16_t *blk, int log2w, int log2h, int bd);
+XO_API int  xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intra, int ch, int slice_type,
+                          const xb200_rates *rt, int bd);
+XO_API int  xo_quant_plain(int16_t *coef, int log2n, int qp, int slice_type, int bd);
+XO_API void xo_tq(const xb200_seq *sq, const xb200_tq_item *it, const xb200_rates *rates, int16_t *planes, int nnz[3]);
+XO_API void xo_itdq(const xb200_seq *sq, const xb200_tq_item *it, int16_t *planes, const int nnz[3]);
+XO_API void xo_recon(const int16_t *resi, const int16_t *pred, int is_coef, int n, int16_t *rec, int bd);
+XO_API void xo_me(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *it);
+XO_API void xo_residue(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_residue_item *it,
+                       int16_t *coef, int16_t *rec);
+XO_API void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad);
+XO_API void xo_me_batch(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *items, int64_t n);
+XO_API void xo_mc_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n,
+                        const int64_t *off, int16_t *pred);
+XO_API void xo_tq_batch(const xb200_seq *sq, xb200_tq_item *items, int64_t n, const xb200_rates *rates, int16_t *coef,
+                        int16_t *resi);
+XO_API void xo_residue_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates,
+                             xb200_residue_item *items, int64_t n, int16_t *coef, int16_t *rec);
+#endif
