@@ -22,7 +22,7 @@ NUM_CTX_CC_LAST = 2
 ME_REC = np.dtype([
     ("poc", "<i4"), ("cur_pic", "<i4"), ("ref_pic", "<i4"), ("ref_poc", "<i4"),
     ("x", "<i2"), ("y", "<i2"),
-    ("log2w", "u1"), ("log2h", "u1"), ("lidx", "u1"), ("bi", "u1"),
+    ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("lidx", "u1"), ("bi", "u1"),
     ("refi", "i1"), ("num_refp", "u1"),
     ("mvp", "<i2", (2,)), ("mv_in", "<i2", (2,)),
     ("lambda_mv", "<u4"), ("mot_bits_in", "<i4", (2,)),
@@ -39,7 +39,7 @@ MC_REC = np.dtype([
 
 TQ_REC = np.dtype([
     ("poc", "<i4"),
-    ("log2w", "u1"), ("log2h", "u1"), ("slice_type", "u1"), ("is_intra", "u1"),
+    ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"), ("is_intra", "u1"),
     ("run_stats", "u1"), ("qp", "u1", (3,)),
     ("rate_idx", "<i4"), ("in_off", "<i8"),
     ("lambda", "<f8", (3,)), ("nnz", "<i4", (3,)),

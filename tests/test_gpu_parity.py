@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the results the
+UNMODIFIED reference produced in situ for the very same calls (traced work lists) and (b) the
+oracle restatement.  Bit-exact: everything here is integer work."""
+import numpy as np
+import pytest
+
+import tracedata
+from oracle import oracle as xo
+from oracle import refharness as rh
+from xeve_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def _remap(arr, field, handles):
+    out = arr.copy()
+    v = out[field]
+    out[field] = np.where(v >= 0, handles[np.clip(v, 0, len(handles) - 1)], -1)
+    return out
+
+
+def test_padding_matches_reference(trace, gpu_ctx):
+    """device border replication == xeve_picbuf_expand (reference src_base/xeve_util.c:190-248)"""
+    for i, p in enumerate(trace.pics):
+        if int(p["kind"]) != 1:
+            continue
+        got = gpu_ctx.pic_download(int(gpu_ctx.handles[i]), with_padding=True)
+        exp = trace.padded_planes(i)
+        for g, e in zip(got, exp):
+            assert np.array_equal(g, e)
+        if trace.source == "live":  # the reference's own padded buffer
+            full = trace.live.plane_views(i)
+            assert np.array_equal(got[0], full[0][:, : got[0].shape[1]])
+            assert np.array_equal(got[1], full[1][:, : got[1].shape[1]])
+
+
+def test_upload_8bit_converts_and_pads(gpu_ctx):
+    """xb200_pic_upload: 8-bit input -> internal 10-bit (<< 2) + padding"""
+    from xeve_b200.clips import Clip, to_internal10
+    w, h = gpu_ctx.w, gpu_ctx.hgt
+    c = Clip("cif", w=w, h=h)
+    y, u, v = c.frame(3)
+    hd = gpu_ctx.pic_create(padded=True)
+    gpu_ctx.pic_upload(hd, y, u, v, 8)
+    gy, gu, gv = gpu_ctx.pic_download(hd, with_padding=False)
+    assert np.array_equal(gy, to_internal10(y, 8)) and np.array_equal(gu, to_internal10(u, 8)) and np.array_equal(gv, to_internal10(v, 8))
+    py = gpu_ctx.pic_download(hd, with_padding=True)[0]
+    assert np.array_equal(py[144:-144, 144:-144], gy)
+    assert (py[:144, :144] == gy[0, 0]).all() and (py[-144:, -144:] == gy[-1, -1]).all()
+    assert np.array_equal(py[10, 144:-144], gy[0]) and np.array_equal(py[144:-144, 3], gy[:, 0])
+    gpu_ctx.pic_destroy(hd)
+
+
+def test_distortion_probes(trace, gpu_ctx):
+    """SAD / SSD / SATD kernels vs the oracle on random blocks reaching into the padding"""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    refs = [i for i, p in enumerate(trace.pics) if int(p["kind"]) == 1]
+    orgs = [i for i, p in enumerate(trace.pics) if int(p["kind"]) == 0]
+    n = 600
+    items = np.zeros(n, api.BLK_ITEM)
+    w, h = gpu_ctx.w, gpu_ctx.hgt
+    exp_sad, exp_ssd, exp_satd = np.zeros(n, np.int32), np.zeros(n, np.int64), np.zeros(n, np.int32)
+    L = xo.lib()
+    for k in range(n):
+        l2 = int(rng.integers(2, 7))
+        pl = int(rng.integers(0, 3))
+        sc = 1 if pl == 0 else 2
+        bs = 1 << l2
+        o, r = int(rng.choice(orgs)), int(rng.choice(refs))
+        x1 = int(rng.integers(0, (w // sc - bs) // 4 + 1)) * 4
+        y1 = int(rng.integers(0, (h // sc - bs) // 4 + 1)) * 4
+        x2 = int(rng.integers(-127 // sc, w // sc - 1))
+        y2 = int(rng.integers(-127 // sc, h // sc - 1))
+        items[k] = (gpu_ctx.handles[o], gpu_ctx.handles[r], x1, y1, x2, y2, pl, pl, l2, l2)
+        a = trace.planes[o][pl]
+        b = trace.padded_planes(r)[pl]
+        pad = 144 // sc
+        ap = a.ctypes.data + 2 * (y1 * a.shape[1] + x1)
+        bp = b.ctypes.data + 2 * ((y2 + pad) * b.shape[1] + x2 + pad)
+        exp_sad[k] = L.xo_sad(bs, bs, ap, a.shape[1], bp, b.shape[1], 10)
+        exp_ssd[k] = L.xo_ssd(bs, bs, ap, a.shape[1], bp, b.shape[1], 10)
+        exp_satd[k] = L.xo_satd(bs, bs, ap, a.shape[1], bp, b.shape[1], 10)
+    assert np.array_equal(gpu_ctx.sad(items), exp_sad)
+    assert np.array_equal(gpu_ctx.ssd(items), exp_ssd)
+    assert np.array_equal(gpu_ctx.satd(items), exp_satd)
+
+
+def _me_items(trace, gpu_ctx):
+    it = np.ascontiguousarray(trace.me).astype(api.ME_ITEM)
+    it = _remap(it, "cur_pic", gpu_ctx.handles)
+    it = _remap(it, "ref_pic", gpu_ctx.handles)
+    return it
+
+
+def test_me_matches_reference_in_situ(trace, gpu_ctx):
+    """xb200_me vs what pinter_me_epzs returned inside the real encode (mv, cost, mot_bits)"""
+    items = _me_items(trace, gpu_ctx)
+    items["mv_out"] = 0
+    items["cost"] = 0
+    items["mot_bits_out"] = 0
+    got = gpu_ctx.me(items, trace.side)
+    exp = trace.me
+    bad = np.where((got["mv_out"] != exp["mv_out"]).any(1) | (got["cost"] != exp["cost"]) |
+                   (got["mot_bits_out"] != exp["mot_bits_out"]).any(1))[0]
+    assert len(bad) == 0, (len(bad), len(exp), exp[bad[:3]], got[bad[:3]])
+    assert len(exp) > 1000 and (exp["bi"] == 1).sum() > 100 and set(np.unique(exp["log2_cuw"])) == {3, 4, 5, 6}
+
+
+def test_me_matches_oracle(trace, gpu_ctx):
+    items = _me_items(trace, gpu_ctx)
+    got = gpu_ctx.me(items, trace.side)
+    opl = trace.oracle_planes()
+    exp = xo.me_batch(trace.seq, opl, trace.side, np.ascontiguousarray(trace.me))
+    for f in ("mv_out", "cost", "mot_bits_out"):
+        assert np.array_equal(got[f], exp[f]), f
+
+
+def test_mc_matches_reference(trace, gpu_ctx):
+    """xb200_mc vs xeve_mc (replayed through the reference) and the oracle: Y, U, V, uni + bi"""
+    recs = np.ascontiguousarray(trace.mc)
+    off, total = rh.mc_offsets(recs)
+    items = _remap(recs.astype(api.MC_ITEM), "ref_pic", gpu_ctx.handles)
+    got = gpu_ctx.mc(items, off, total)
+    exp = xo.mc_batch(trace.seq, trace.oracle_planes(), recs, off, total)
+    assert np.array_equal(got, exp)
+    if trace.source == "live":
+        pred_ref, _, hsh, _ = rh.replay_mc(trace.live, nthreads=4)
+        assert np.array_equal(hsh, recs["out_hash"])  # replay == in situ
+        assert np.array_equal(got, pred_ref)
+    else:
+        n = len(trace.expect["mc_off"])
+        end = int(trace.expect["mc_off"][-1] + recs[n - 1]["w"] * recs[n - 1]["h"] * 3 // 2)
+        assert np.array_equal(got[:end], trace.expect["mc_pred"][:end])
+    assert ((recs["refi"] >= 0).all(1)).sum() > 100  # bi-prediction is exercised
+
+
+def _tq_expected(trace):
+    if trace.source == "live":
+        coef, nnz, resi, _ = rh.replay_tq(trace.live, nthreads=4)
+        return coef, nnz, resi
+    items, coef, resi = xo.tq_batch(trace.seq, np.ascontiguousarray(trace.tq), trace.rates, trace.tq_coef)
+    return coef, items["nnz"], resi
+
+
+def _item_mask(tq, n):
+    m = np.zeros(n, bool)
+    for r in tq:
+        o = int(r["in_off"])
+        m[o:o + ((3 << (2 * int(r["log2_cuw"]))) >> 1)] = True
+    return m
+
+
+def test_tq_itdq_recon_match_reference(trace, gpu_ctx):
+    """xb200_tq (DCT + RDOQ), xb200_itdq, xb200_recon vs xeve_sub_block_tq / xeve_itdq / xeve_recon_blk"""
+    tq = np.ascontiguousarray(trace.tq).astype(api.TQ_ITEM)
+    exp_coef, exp_nnz, exp_resi = _tq_expected(trace)
+    if trace.source == "live":
+        assert np.array_equal(exp_nnz, trace.tq["nnz"])  # replay == in situ
+    tq["nnz"] = 0
+    items, coef = gpu_ctx.tq(tq, trace.rates, trace.tq_coef)
+    m = _item_mask(tq, len(coef))
+    assert np.array_equal(items["nnz"], exp_nnz)
+    assert np.array_equal(coef[m], exp_coef[m])
+    resi = gpu_ctx.itdq(items, coef)
+    # planes with nnz == 0 are left untouched by fn_itdp: compare only where the reference wrote
+    for r, nz in zip(items, exp_nnz):
+        o, ny = int(r["in_off"]), 1 << (2 * int(r["log2_cuw"]))
+        for c, (a, b) in enumerate(((0, ny), (ny, ny + ny // 4), (ny + ny // 4, ny + ny // 2))):
+            if nz[c]:
+                assert np.array_equal(resi[o + a:o + b], exp_resi[o + a:o + b])
+    # recon against the oracle on a synthetic prediction
+    rng = np.random.default_rng(3)
+    pred = rng.integers(0, 1024, len(coef)).astype(np.int16)
+    rec = gpu_ctx.recon(items, resi, pred)
+    L = xo.lib()
+    import ctypes as C
+    for r in items[:: max(1, len(items) // 300)]:
+        o, ny = int(r["in_off"]), 1 << (2 * int(r["log2_cuw"]))
+        for c, (a, b) in enumerate(((0, ny), (ny, ny + ny // 4), (ny + ny // 4, ny + ny // 2))):
+            e = np.zeros(b - a, np.int16)
+            rs, pr = np.ascontiguousarray(resi[o + a:o + b]), np.ascontiguousarray(pred[o + a:o + b])
+            L.xo_recon(rs.ctypes.data_as(C.c_void_p), pr.ctypes.data_as(C.c_void_p), int(r["nnz"][c] != 0), b - a,
+                       e.ctypes.data_as(C.c_void_p), 10)
+            assert np.array_equal(rec[o + a:o + b], e)
+    assert (exp_nnz.sum(1) > 0).sum() > 100 and set(np.unique(tq["log2_cuw"])) == {3, 4, 5, 6}
+
+
+def test_fused_residue_matches_oracle(trace, gpu_ctx):
+    """xb200_residue = MC -> diff -> SSD -> DCT+RDOQ -> dequant+IDCT -> recon -> SSD in one kernel"""
+    rng = np.random.default_rng(11)
+    mc = np.ascontiguousarray(trace.mc)
+    pocs = {int(p["poc"]): i for i, p in enumerate(trace.pics) if int(p["kind"]) == 0}
+    sel = [i for i in range(len(mc)) if int(mc[i]["w"]) >= 8 and int(mc[i]["poc"]) in pocs]
+    sel = np.array(sel)[rng.permutation(len(sel))[:1500]]
+    items = np.zeros(len(sel), api.RESIDUE_ITEM)
+    off = 0
+    tq = trace.tq
+    for k, i in enumerate(sel):
+        t = tq[int(rng.integers(0, len(tq)))]
+        items[k]["mc"] = mc[i]
+        items[k]["cur_pic"] = pocs[int(mc[i]["poc"])]
+        items[k]["slice_type"], items[k]["run_stats"], items[k]["qp"] = 0, 7, t["qp"]
+        items[k]["rate_idx"], items[k]["lambda"], items[k]["out_off"] = t["rate_idx"], t["lambda"], off
+        off += int(mc[i]["w"]) * int(mc[i]["h"]) * 3 // 2
+    exp_items, exp_coef, exp_rec = xo.residue_batch(trace.seq, trace.oracle_planes(), trace.rates, items, off)
+    dev = items.copy()
+    dev["cur_pic"] = gpu_ctx.handles[items["cur_pic"]]
+    dmc = dev["mc"].copy()
+    dmc = _remap(dmc, "ref_pic", gpu_ctx.handles)
+    dev["mc"] = dmc
+    got_items, got_coef, got_rec = gpu_ctx.residue(dev, trace.rates, off)
+    for f in ("nnz", "dist_pred", "dist_rec"):
+        assert np.array_equal(got_items[f], exp_items[f]), f
+    assert np.array_equal(got_coef, exp_coef)
+    assert np.array_equal(got_rec, exp_rec)
+    assert (exp_items["nnz"].sum(1) > 0).sum() > 50
+
+
+def test_bad_arguments_are_rejected(gpu_ctx):
+    """error convention of the boundary: reference codes (inc/xeve.h:50-74)"""
+    it = np.zeros(1, api.ME_ITEM)
+    it["cur_pic"], it["ref_pic"] = 9999, 9999
+    it["log2_cuw"] = it["log2_cuh"] = 4
+    it["gop_size"] = 16
+    with pytest.raises(api.Xb200Error) as e:
+        gpu_ctx.me(it)
+    assert e.value.code == api.ERR_INVALID_ARGUMENT
+    it["cur_pic"] = it["ref_pic"] = int(gpu_ctx.handles[0])
+    it["log2_cuw"], it["log2_cuh"] = 4, 3  # non-square CUs do not exist in Baseline
+    with pytest.raises(api.Xb200Error) as e:
+        gpu_ctx.me(it)
+    assert e.value.code in (api.ERR_UNSUPPORTED, api.ERR_INVALID_ARGUMENT)
+    assert len(gpu_ctx.me(np.zeros(0, api.ME_ITEM))) == 0

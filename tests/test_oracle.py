@@ -1,0 +1,130 @@
+"""CPU tests (no GPU): the oracle restatement against (a) the golden fixture traced from the
+reference and (b) the compiled reference itself when oracle/_ref is present."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import tracedata
+from oracle import oracle as xo
+from oracle import refharness as rh
+
+needs_ref = pytest.mark.skipif(not rh.available(), reason="oracle/_ref (compiled reference) not built here")
+p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+def test_oracle_me_matches_golden(golden):
+    out = xo.me_batch(golden.seq, golden.oracle_planes(), golden.side, np.ascontiguousarray(golden.me))
+    for f in ("mv_out", "cost", "mot_bits_out"):
+        assert np.array_equal(out[f], golden.me[f]), f
+    assert (golden.me["bi"] == 1).sum() > 100
+
+
+def test_oracle_mc_matches_golden(golden):
+    mc = np.ascontiguousarray(golden.mc)
+    off, total = rh.mc_offsets(mc)
+    assert np.array_equal(off, golden.expect["mc_off"])
+    pred = xo.mc_batch(golden.seq, golden.oracle_planes(), mc, off, total)
+    assert np.array_equal(pred, golden.expect["mc_pred"])
+
+
+def test_oracle_tq_itdq_match_golden(golden):
+    items, coef, resi = xo.tq_batch(golden.seq, np.ascontiguousarray(golden.tq), golden.rates, golden.tq_coef)
+    assert np.array_equal(items["nnz"], golden.expect["tq_nnz"])
+    assert np.array_equal(coef, golden.expect["tq_coef_out"])
+    for r, nz in zip(items, items["nnz"]):  # the reference leaves nnz == 0 planes untouched
+        o, ny = int(r["in_off"]), 1 << (2 * int(r["log2_cuw"]))
+        for c, (a, b) in enumerate(((0, ny), (ny, ny + ny // 4), (ny + ny // 4, ny + ny // 2))):
+            if nz[c]:
+                assert np.array_equal(resi[o + a:o + b], golden.expect["tq_resi_out"][o + a:o + b])
+
+
+@needs_ref
+def test_kernels_match_compiled_reference():
+    """SAD / SSD / SATD / transforms / MC vs the reference's C, SSE and AVX2 tables"""
+    L, R = xo.lib(), rh.lib()
+    rng = np.random.default_rng(1)
+    for l2 in (2, 3, 4, 5, 6):
+        n = 1 << l2
+        for trial in range(12):
+            a = rng.integers(0, 1024, (n + 8, n + 40)).astype(np.int16)
+            b = rng.integers(-1023, 2047, (n + 8, n + 40)).astype(np.int16)
+            if trial == 0:
+                a[:], b[:] = 1023, 0
+            sa, sb = a.shape[1], b.shape[1]
+            assert L.xo_sad(n, n, p(a), sa, p(b), sb, 10) == R.rh_sad(0, l2, l2, p(a), p(b), sa, sb, 10) == R.rh_sad(2, l2, l2, p(a), p(b), sa, sb, 10)
+            assert L.xo_ssd(n, n, p(a), sa, p(b), sb, 10) == R.rh_ssd(1, l2, l2, p(a), p(b), sa, sb, 10) == R.rh_ssd(0, l2, l2, p(a), p(b), sa, sb, 10)
+            assert L.xo_satd(n, n, p(a), sa, p(b), sb, 10) == R.rh_satd(0, n, n, p(a), p(b), sa, sb, 10) == R.rh_satd(1, n, n, p(a), p(b), sa, sb, 10)
+            blk = rng.integers(-1023, 1024, (n, n)).astype(np.int16)
+            if trial == 1:
+                blk[:] = 1023
+            if trial == 2:
+                blk[:] = -1023
+            x1, x2, x3 = blk.copy(), blk.copy(), blk.copy()
+            L.xo_fwd_transform(p(x1), l2, l2, 10)
+            R.rh_fwd_transform(0, p(x2), l2, l2, 10)
+            R.rh_fwd_transform(2, p(x3), l2, l2, 10)
+            assert np.array_equal(x1, x2) and np.array_equal(x1, x3)
+            # inverse: encoder-plausible coefficient ranges (the reference's C butterflies form partial
+            # sums in 32-bit int and its AVX2 path multiplies in 32 bits; all three agree here)
+            cf = (rng.integers(-2000, 2000, (n, n)) * (rng.random((n, n)) < 0.15)).astype(np.int16)
+            y1, y2, y3 = cf.copy(), cf.copy(), cf.copy()
+            L.xo_inv_transform(p(y1), l2, l2, 10)
+            R.rh_inv_transform(0, p(y2), l2, l2, 10)
+            R.rh_inv_transform(2, p(y3), l2, l2, 10)
+            assert np.array_equal(y1, y2) and np.array_equal(y1, y3)
+    ref = rng.integers(0, 1024, (200, 200)).astype(np.int16)
+    for trial in range(200):
+        w = int(rng.choice([4, 8, 16, 32, 64]))
+        gx, gy = int(rng.integers(160, 400)), int(rng.integers(160, 400))
+        if trial % 3 == 0:
+            gx &= ~3
+        if trial % 5 == 0:
+            gy &= ~3
+        o1, o2, o3 = (np.zeros((w, w), np.int16) for _ in range(3))
+        L.xo_mc_luma(p(ref), 200, gx, gy, gx, gy, p(o1), w, w, w, 10)
+        R.rh_mc_l(0, p(ref), gx << 2, gy << 2, 200, w, p(o2), w, w, 10)
+        R.rh_mc_l(2, p(ref), gx << 2, gy << 2, 200, w, p(o3), w, w, 10)
+        assert np.array_equal(o1, o2) and np.array_equal(o1, o3)
+        L.xo_mc_chroma(p(ref), 200, gx, gy, gx, gy, p(o1), w, w, w, 10)
+        R.rh_mc_c(0, p(ref), gx << 2, gy << 2, 200, w, p(o2), w, w, 10)
+        assert np.array_equal(o1, o2)
+
+
+@needs_ref
+def test_oracle_matches_reference_in_situ_cif(trace):
+    """every pi->fn_me / pi->fn_mc / ctx->fn_tq call of 3 CIF pictures, as the reference ran them"""
+    assert trace.source == "live"
+    opl = trace.oracle_planes()
+    out = xo.me_batch(trace.seq, opl, trace.side, np.ascontiguousarray(trace.me))
+    for f in ("mv_out", "cost", "mot_bits_out"):
+        assert np.array_equal(out[f], trace.me[f]), f
+    mc = np.ascontiguousarray(trace.mc)
+    off, total = rh.mc_offsets(mc)
+    pred_ref, _, hsh, _ = rh.replay_mc(trace.live, nthreads=4)
+    assert np.array_equal(hsh, mc["out_hash"])
+    assert np.array_equal(xo.mc_batch(trace.seq, opl, mc, off, total), pred_ref)
+    coef_ref, nnz_ref, resi_ref, _ = rh.replay_tq(trace.live, nthreads=4)
+    items, coef, resi = xo.tq_batch(trace.seq, np.ascontiguousarray(trace.tq), trace.rates, trace.tq_coef)
+    assert np.array_equal(nnz_ref, trace.tq["nnz"]) and np.array_equal(items["nnz"], nnz_ref)
+    m = np.zeros(len(coef), bool)
+    for r in trace.tq:
+        o = int(r["in_off"])
+        m[o:o + ((3 << (2 * int(r["log2_cuw"]))) >> 1)] = True
+    assert np.array_equal(coef[m], coef_ref[m])
+    for r, nz in zip(items, nnz_ref):
+        o, ny = int(r["in_off"]), 1 << (2 * int(r["log2_cuw"]))
+        for c, (a, b) in enumerate(((0, ny), (ny, ny + ny // 4), (ny + ny // 4, ny + ny // 2))):
+            if nz[c]:
+                assert np.array_equal(resi[o + a:o + b], resi_ref[o + a:o + b])
+
+
+@needs_ref
+def test_padding_matches_reference(trace):
+    for i, pc in enumerate(trace.pics):
+        if int(pc["kind"]) != 1:
+            continue
+        full = trace.live.plane_views(i)
+        mine = trace.padded_planes(i)
+        for a, b in zip(mine, full):
+            assert np.array_equal(a, b[:, : a.shape[1]])

@@ -1,0 +1,107 @@
+"""CPU tests: generated constant tables vs the reference's, struct layouts, exported symbols."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import refharness as rh
+from xeve_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built here")
+
+PROBE = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "include/xeve_b200.h"
+#include "xeve_b200/csrc/xb200_tables.h"
+int main(void){
+  printf("seq %zu\nme %zu\nmc %zu\nrates %zu\ntq %zu\nres %zu\nblk %zu\n", sizeof(xb200_seq), sizeof(xb200_me_item),
+         sizeof(xb200_mc_item), sizeof(xb200_rates), sizeof(xb200_tq_item), sizeof(xb200_residue_item), sizeof(xb200_blk_item));
+  printf("off %zu %zu %zu %zu\n", offsetof(xb200_me_item, lambda_mv), offsetof(xb200_tq_item, lambda),
+         offsetof(xb200_residue_item, out_off), offsetof(xb200_residue_item, dist_rec));
+  static int8_t tm[4096]; xb200_gen_tm64(tm);
+  FILE* f = fopen("tm64.bin","wb"); fwrite(tm,1,4096,f); fclose(f);
+  static uint16_t sc[4096];
+  f = fopen("scan.bin","wb");
+  for(int l=1;l<=6;l++){ xb200_gen_scan(sc,l,l); fwrite(sc,2,1<<(2*l),f);} fclose(f);
+  f = fopen("mvbits.bin","wb"); for(int v=-2047; v<=2048; v++){ unsigned char b=(unsigned char)xb200_mvd_bits(v); fwrite(&b,1,1,f);} fclose(f);
+  f = fopen("refi.bin","wb"); for(int n=0;n<17;n++) for(int r=0;r<16;r++){ unsigned char b = r<n||n==0 ? (unsigned char)xb200_refi_bits(n,r):0; fwrite(&b,1,1,f);} fclose(f);
+  f = fopen("es.bin","wb"); for(int q=0;q<6;q++) for(int l=1;l<=7;l++){ long long e = xb200_err_scale(q,l,10); fwrite(&e,8,1,f);} fclose(f);
+  return 0; }
+'''
+
+
+@pytest.fixture(scope="module")
+def probe_dir():
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "probe.c")
+    open(src, "w").write(PROBE)
+    subprocess.check_call(["gcc", "-O1", "-I", ROOT, "-o", os.path.join(d, "probe"), src, "-lm"])
+    out = subprocess.check_output([os.path.join(d, "probe")], cwd=d).decode()
+    return d, out
+
+
+def test_struct_layouts_match_numpy(probe_dir):
+    _, out = probe_dir
+    sizes = dict(re.findall(r"(\w+) (\d+)\n", out))
+    assert int(sizes["seq"]) == api.SEQ.itemsize
+    assert int(sizes["me"]) == api.ME_ITEM.itemsize
+    assert int(sizes["mc"]) == api.MC_ITEM.itemsize
+    assert int(sizes["rates"]) == api.RATES.itemsize
+    assert int(sizes["tq"]) == api.TQ_ITEM.itemsize
+    assert int(sizes["res"]) == api.RESIDUE_ITEM.itemsize
+    assert int(sizes["blk"]) == api.BLK_ITEM.itemsize
+    offs = [int(v) for v in re.search(r"off (\d+) (\d+) (\d+) (\d+)", out).groups()]
+    assert offs == [api.ME_ITEM.fields["lambda_mv"][1], api.TQ_ITEM.fields["lambda"][1],
+                    api.RESIDUE_ITEM.fields["out_off"][1], api.RESIDUE_ITEM.fields["dist_rec"][1]]
+    # the harness records and the ABI records are the same bytes
+    assert rh.ME_REC.itemsize == api.ME_ITEM.itemsize and rh.MC_REC.itemsize == api.MC_ITEM.itemsize
+    assert rh.TQ_REC.itemsize == api.TQ_ITEM.itemsize and rh.RATES.itemsize == api.RATES.itemsize
+
+
+@needs_ref
+def test_generated_tables_match_reference(probe_dir):
+    d, _ = probe_dir
+    rd = lambda n, dt: np.fromfile(os.path.join(d, n), dt)
+    assert np.array_equal(rd("tm64.bin", np.int8), rh.table(0, np.int8))
+    tm64 = rh.table(0, np.int8).reshape(64, 64)
+    for i, n in enumerate((32, 16, 8, 4, 2)):  # N-point matrices are sub-sampled rows of tm64
+        assert np.array_equal(rh.table(1 + i, np.int8).reshape(n, n), tm64[:: 64 // n, :n])
+    scan_ref = rh.table(8, np.uint16).reshape(6, 6, 4096)
+    mine = rd("scan.bin", np.uint16)
+    pos = 0
+    for l in range(1, 7):
+        n = 1 << (2 * l)
+        assert np.array_equal(mine[pos:pos + n], scan_ref[l - 1, l - 1, :n]), l
+        pos += n
+    assert np.array_equal(rd("mvbits.bin", np.uint8), rh.table(6, np.uint8))
+    assert np.array_equal(rd("refi.bin", np.uint8).reshape(17, 16), rh.table(7, np.uint8).reshape(17, 16))
+    assert np.array_equal(rd("es.bin", np.int64).reshape(6, 7), rh.table(13, np.int64).reshape(6, 7))
+    assert list(rh.table(9, np.int32)) == [40, 45, 51, 57, 64, 71]
+    assert list(rh.table(10, np.int32)[:6]) == [26214, 23302, 20560, 18396, 16384, 14764]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """the C-ABI .so exists in-tree, dlopens without a GPU and exports what include/xeve_b200.h declares"""
+    hdr = open(os.path.join(ROOT, "include", "xeve_b200.h")).read()
+    declared = set(re.findall(r"XB200_API\s+[\w\s\*]+?\b(xb200_\w+)\s*\(", hdr))
+    assert len(declared) >= 19
+    L = api.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert set(api.EXPORTS) == declared
+    assert b"sm_100a" in L.xb200_version()
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.Xb200Error) as e:
+        api.Hotpath(api.make_seq(352, 288))
+    assert e.value.code == api.ERR_UNSUPPORTED

@@ -1,0 +1,113 @@
+"""Work lists for the parity tests.
+
+Two sources, same shape:
+  * live  -- oracle/_ref is built (this container, and the GPU box where the prebuilt binary
+             travels): run the UNMODIFIED reference encoder on a seeded clip with logging hooks
+             on pi->fn_me / pi->fn_mc / ctx->fn_tq and take the recorded calls + in-situ results;
+  * golden -- tests/golden/qcif_trace.npz, produced by tests/golden/make_golden.py from the
+             same harness in this container, for machines without oracle/_ref.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import oracle as xo  # noqa: E402
+from oracle import refharness as rh  # noqa: E402
+from xeve_b200.clips import Clip  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "qcif_trace.npz")
+QCIF = dict(w=176, h=144, n=20, squares=[(32, 20, 30, 3, 2)])
+
+
+def clip_yuv(name, frames, **override):
+    c = Clip(name, **override)
+    dt = np.uint8 if c.depth == 8 else np.dtype("<u2")
+    return c, np.frombuffer(b"".join(c.frame_bytes(i) for i in range(frames)), dt)
+
+
+class TraceData:
+    """Uniform view over a live rh.Trace or the golden fixture."""
+
+    def __init__(self, seq, pics, planes, me, mc, tq, rates, side, tq_coef, source, expect=None):
+        self.seq, self.pics, self.planes = seq, pics, planes  # planes[i] = (Y, U, V) ACTIVE areas (s16 2-D)
+        self.me, self.mc, self.tq, self.rates = me, mc, tq, rates
+        self.side = side          # s16 buffer addressed by me.org_bi_off
+        self.tq_coef = tq_coef    # s16 buffer addressed by tq.in_off (inputs)
+        self.source = source
+        self.expect = expect or {}
+        self._padded = {}
+
+    def padded_planes(self, i):
+        """(Y, U, V) with the 144/72 border replicated by the ORACLE (reference src_base/xeve_util.c:190-248)."""
+        if i not in self._padded:
+            out = []
+            for k, a in enumerate(self.planes[i]):
+                pad = 144 if k == 0 else 72
+                h, w = a.shape
+                buf = np.zeros((h + 2 * pad, w + 2 * pad), np.int16)
+                buf[pad:pad + h, pad:pad + w] = a
+                xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], w, h, pad)
+                out.append(buf)
+            self._padded[i] = out
+        return self._padded[i]
+
+    def oracle_planes(self):
+        """ctypes xo_planes array (active origins inside oracle-padded copies); keep self alive."""
+        arr = (xo.PLANES * len(self.pics))()
+        for i, p in enumerate(self.pics):
+            if int(p["kind"]) == 1:
+                bufs = self.padded_planes(i)
+                pads = (144, 72, 72)
+            else:
+                bufs = [np.ascontiguousarray(a) for a in self.planes[i]]
+                self._padded[i] = bufs
+                pads = (0, 0, 0)
+            ptrs = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(bufs, pads)]
+            arr[i].y, arr[i].u, arr[i].v = ptrs
+            arr[i].s_l, arr[i].s_c = bufs[0].shape[1], bufs[1].shape[1]
+            arr[i].w_l, arr[i].h_l, arr[i].poc = int(p["w_l"]), int(p["h_l"]), int(p["poc"])
+        return arr
+
+
+def from_live(tr: "rh.Trace") -> TraceData:
+    planes = []
+    for i, p in enumerate(tr.pics):
+        full = tr.plane_views(i)
+        pl, pc = int(p["pad_l"]), int(p["pad_c"])
+        w, h = int(p["w_l"]), int(p["h_l"])
+        planes.append((full[0][pl:pl + h, pl:pl + w].copy(), full[1][pc:pc + h // 2, pc:pc + w // 2].copy(),
+                       full[2][pc:pc + h // 2, pc:pc + w // 2].copy()))
+    td = TraceData(tr.const.copy(), tr.pics.copy(), planes, tr.me.copy(), tr.mc.copy(), tr.tq.copy(), tr.rates.copy(), tr.samp,
+                   tr.samp, "live")
+    td.live = tr
+    return td
+
+
+def live_trace(name="cif", frames=30, pic_lo=1, pic_hi=3, preset="fast", mask=7, **override) -> TraceData:
+    c, yuv = clip_yuv(name, frames, **override)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, trace_mask=mask, pic_lo=pic_lo, pic_hi=pic_hi)
+    return from_live(tr)
+
+
+def golden_trace() -> TraceData:
+    z = np.load(GOLDEN)
+    pics = z["pics"]
+    planes = [(z[f"p{i}_y"], z[f"p{i}_u"], z[f"p{i}_v"]) for i in range(len(pics))]
+    expect = dict(mc_pred=z["mc_pred"], mc_off=z["mc_off"], tq_coef_out=z["tq_coef_out"], tq_resi_out=z["tq_resi_out"],
+                  tq_nnz=z["tq_nnz"])
+    return TraceData(z["seq"], pics, planes, z["me"], z["mc"], z["tq"], z["rates"], z["side"], z["tq_in"], "golden", expect)
+
+
+def get_trace() -> TraceData:
+    if rh.available():
+        return live_trace()
+    return golden_trace()

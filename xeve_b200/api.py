@@ -1,0 +1,265 @@
+"""Python binding of the C ABI in include/xeve_b200.h (libxeve_b200.so, hand-written sm_100a CUDA).
+
+This module is plumbing only: numpy record dtypes that mirror the C structs byte for byte, and a
+thin ``Hotpath`` object around the opaque context.  There is no CPU implementation behind it --
+if the shared library or a B200 is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxeve_b200.so")
+
+OK, ERR, ERR_INVALID_ARGUMENT, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_UNEXPECTED = 0, -1, -101, -102, -104, -105
+MEM_HOST, MEM_DEVICE = 0, 1
+PAD_L, PAD_C = 144, 72
+
+SEQ = np.dtype([
+    ("w", "<i4"), ("h", "<i4"), ("bit_depth", "<i4"), ("me_level", "<i4"), ("hpel_cnt", "<i4"), ("qpel_cnt", "<i4"),
+    ("me_complexity", "<i4"), ("min_clip", "<i4", (2,)), ("max_clip", "<i4", (2,)),
+    ("merge_num", "<i4"), ("me_range", "<i4"), ("gop_size", "<i4"), ("rdoq", "<i4"), ("tool_iqt", "<i4"),
+], align=True)
+
+ME_ITEM = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("ref_pic", "<i4"), ("ref_poc", "<i4"),
+    ("x", "<i2"), ("y", "<i2"),
+    ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("lidx", "u1"), ("bi", "u1"),
+    ("refi", "i1"), ("num_refp", "u1"),
+    ("mvp", "<i2", (2,)), ("mv_in", "<i2", (2,)),
+    ("lambda_mv", "<u4"), ("mot_bits_in", "<i4", (2,)),
+    ("max_search_range", "<i4"), ("gop_size", "<i4"), ("org_bi_off", "<i4"),
+    ("mv_out", "<i2", (2,)), ("cost", "<u4"), ("mot_bits_out", "<i4", (2,)),
+], align=True)
+
+MC_ITEM = np.dtype([
+    ("poc", "<i4"), ("ref_pic", "<i4", (2,)), ("ref_poc", "<i4", (2,)),
+    ("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"),
+    ("refi", "i1", (2,)), ("mv", "<i2", (2, 2)),
+    ("out_hash", "<u8"),
+], align=True)
+
+RATES = np.dtype([
+    ("cbf_all", "<i4", (2,)), ("cbf_luma", "<i4", (2,)), ("cbf_cb", "<i4", (2,)), ("cbf_cr", "<i4", (2,)),
+    ("run", "<i4", (24, 2)), ("level", "<i4", (24, 2)), ("last", "<i4", (2, 2)),
+], align=True)
+
+TQ_ITEM = np.dtype([
+    ("poc", "<i4"),
+    ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"), ("is_intra", "u1"),
+    ("run_stats", "u1"), ("qp", "u1", (3,)),
+    ("rate_idx", "<i4"), ("in_off", "<i8"),
+    ("lambda", "<f8", (3,)), ("nnz", "<i4", (3,)),
+    ("out_hash", "<u8"),
+], align=True)
+
+RESIDUE_ITEM = np.dtype([
+    ("mc", MC_ITEM),
+    ("cur_pic", "<i4"),
+    ("slice_type", "u1"), ("run_stats", "u1"), ("qp", "u1", (3,)), ("pad_", "u1", (3,)),
+    ("rate_idx", "<i4"),
+    ("lambda", "<f8", (3,)),
+    ("out_off", "<i8"),
+    ("nnz", "<i4", (3,)),
+    ("dist_pred", "<i8", (3,)), ("dist_rec", "<i8", (3,)),
+], align=True)
+
+BLK_ITEM = np.dtype([
+    ("pic1", "<i4"), ("pic2", "<i4"),
+    ("x1", "<i2"), ("y1", "<i2"), ("x2", "<i2"), ("y2", "<i2"),
+    ("plane1", "u1"), ("plane2", "u1"), ("log2w", "u1"), ("log2h", "u1"),
+], align=True)
+
+VP = C.c_void_p
+_lib = None
+
+
+class Xb200Error(RuntimeError):
+    def __init__(self, code, what):
+        super().__init__(f"{what} failed with status {code}")
+        self.code = code
+
+
+def load():
+    """dlopen the in-tree library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.xb200_version.restype = C.c_char_p
+        L.xb200_create.argtypes = [C.POINTER(VP), C.c_int, VP]
+        L.xb200_destroy.argtypes = [VP]
+        L.xb200_destroy.restype = None
+        L.xb200_launch_count.argtypes = [VP]
+        L.xb200_launch_count.restype = C.c_int64
+        L.xb200_last_kernel_ms.argtypes = [VP]
+        L.xb200_last_kernel_ms.restype = C.c_double
+        L.xb200_pic_create.argtypes = [VP, C.c_int, C.POINTER(C.c_int32)]
+        L.xb200_pic_destroy.argtypes = [VP, C.c_int32]
+        L.xb200_pic_upload.argtypes = [VP, C.c_int32, VP, VP, C.c_int, C.c_int]
+        L.xb200_pic_upload_s16.argtypes = [VP, C.c_int32, VP, VP, C.c_int]
+        L.xb200_pic_download.argtypes = [VP, C.c_int32, C.c_int, VP, VP]
+        for f in (L.xb200_sad, L.xb200_ssd, L.xb200_satd):
+            f.argtypes = [VP, VP, C.c_int64, VP, C.c_int]
+        L.xb200_me.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
+        L.xb200_mc.argtypes = [VP, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
+        L.xb200_tq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, C.c_int]
+        L.xb200_itdq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
+        L.xb200_recon.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
+        L.xb200_residue.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
+           "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
+           "xb200_me", "xb200_mc", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return VP(a)
+    return a.ctypes.data_as(VP)
+
+
+def make_seq(w, h, preset="fast", bit_depth=10, **kw):
+    """Sequence constants of a Baseline encode (reference presets, src_base/xeve_enc.c:2431-2531)."""
+    s = np.zeros(1, SEQ)
+    pre = {"fast": dict(me_range=32, hpel_cnt=2, merge_num=2), "medium": dict(me_range=64, hpel_cnt=4, merge_num=3)}[preset]
+    s["w"], s["h"], s["bit_depth"] = w, h, bit_depth
+    s["me_level"], s["hpel_cnt"], s["qpel_cnt"], s["me_complexity"] = 2, pre["hpel_cnt"], pre["hpel_cnt"], 1
+    s["min_clip"], s["max_clip"] = [-127, -127], [w - 1, h - 1]
+    s["merge_num"], s["me_range"], s["gop_size"], s["rdoq"], s["tool_iqt"] = pre["merge_num"], pre["me_range"], 16, 1, 0
+    for k, v in kw.items():
+        s[k] = v
+    return s
+
+
+class Hotpath:
+    """One encoder instance's device context (xb200_ctx)."""
+
+    def __init__(self, seq: np.ndarray, device: int = 0):
+        self.L = load()
+        self.seq = np.ascontiguousarray(seq).copy()
+        h = VP()
+        r = self.L.xb200_create(C.byref(h), device, _p(self.seq))
+        if r != OK:
+            raise Xb200Error(r, "xb200_create")
+        self.h = h
+        self.w, self.hgt = int(self.seq["w"][0]), int(self.seq["h"][0])
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, what):
+        if r != OK:
+            raise Xb200Error(r, what)
+
+    @property
+    def launches(self):
+        return int(self.L.xb200_launch_count(self.h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.L.xb200_last_kernel_ms(self.h))
+
+    # ---- pictures ----------------------------------------------------------------------------
+    def pic_create(self, padded: bool) -> int:
+        hd = C.c_int32(-1)
+        self._ck(self.L.xb200_pic_create(self.h, int(padded), C.byref(hd)), "xb200_pic_create")
+        return hd.value
+
+    def pic_destroy(self, handle):
+        self._ck(self.L.xb200_pic_destroy(self.h, handle), "xb200_pic_destroy")
+
+    def pic_upload(self, handle, y, u, v, in_bit_depth):
+        planes = (VP * 3)(_p(y), _p(u), _p(v))
+        strides = (C.c_int32 * 3)(y.strides[0], u.strides[0], v.strides[0])
+        self._ck(self.L.xb200_pic_upload(self.h, handle, planes, strides, in_bit_depth, MEM_HOST), "xb200_pic_upload")
+
+    def pic_upload_s16(self, handle, y, u, v):
+        planes = (VP * 3)(_p(y), _p(u), _p(v))
+        strides = (C.c_int32 * 3)(y.strides[0] // 2, u.strides[0] // 2, v.strides[0] // 2)
+        self._ck(self.L.xb200_pic_upload_s16(self.h, handle, planes, strides, MEM_HOST), "xb200_pic_upload_s16")
+
+    def pic_download(self, handle, with_padding: bool):
+        pl, pc = (PAD_L, PAD_C) if with_padding else (0, 0)
+        y = np.empty((self.hgt + 2 * pl, self.w + 2 * pl), np.int16)
+        u = np.empty((self.hgt // 2 + 2 * pc, self.w // 2 + 2 * pc), np.int16)
+        v = np.empty_like(u)
+        planes = (VP * 3)(_p(y), _p(u), _p(v))
+        strides = (C.c_int32 * 3)(y.shape[1], u.shape[1], v.shape[1])
+        self._ck(self.L.xb200_pic_download(self.h, handle, int(with_padding), planes, strides), "xb200_pic_download")
+        return y, u, v
+
+    # ---- probes ------------------------------------------------------------------------------
+    def _probe(self, fn, items, dtype, what):
+        items = np.ascontiguousarray(items, BLK_ITEM)
+        out = np.zeros(len(items), dtype)
+        self._ck(fn(self.h, _p(items), len(items), _p(out), MEM_HOST), what)
+        return out
+
+    def sad(self, items):
+        return self._probe(self.L.xb200_sad, items, np.int32, "xb200_sad")
+
+    def ssd(self, items):
+        return self._probe(self.L.xb200_ssd, items, np.int64, "xb200_ssd")
+
+    def satd(self, items):
+        return self._probe(self.L.xb200_satd, items, np.int32, "xb200_satd")
+
+    # ---- operators (host buffers) -----------------------------------------------------------
+    def me(self, items, side=None):
+        items = np.ascontiguousarray(items, ME_ITEM).copy()
+        n_side = 0 if side is None else len(side)
+        self._ck(self.L.xb200_me(self.h, _p(items), len(items), _p(side), n_side, MEM_HOST), "xb200_me")
+        return items
+
+    def mc(self, items, pred_off, total):
+        items = np.ascontiguousarray(items, MC_ITEM)
+        pred_off = np.ascontiguousarray(pred_off, np.int64)
+        pred = np.zeros(total, np.int16)
+        self._ck(self.L.xb200_mc(self.h, _p(items), len(items), _p(pred_off), _p(pred), total, MEM_HOST), "xb200_mc")
+        return pred
+
+    def tq(self, items, rates, coef):
+        items = np.ascontiguousarray(items, TQ_ITEM).copy()
+        rates = np.ascontiguousarray(rates, RATES)
+        coef = np.ascontiguousarray(coef, np.int16).copy()
+        self._ck(self.L.xb200_tq(self.h, _p(items), len(items), _p(rates), len(rates), _p(coef), len(coef), MEM_HOST), "xb200_tq")
+        return items, coef
+
+    def itdq(self, items, coef):
+        items = np.ascontiguousarray(items, TQ_ITEM)
+        coef = np.ascontiguousarray(coef, np.int16).copy()
+        self._ck(self.L.xb200_itdq(self.h, _p(items), len(items), _p(coef), len(coef), MEM_HOST), "xb200_itdq")
+        return coef
+
+    def recon(self, items, resi, pred):
+        items = np.ascontiguousarray(items, TQ_ITEM)
+        rec = np.zeros(len(resi), np.int16)
+        self._ck(self.L.xb200_recon(self.h, _p(items), len(items), _p(resi), _p(pred), _p(rec), len(resi), MEM_HOST), "xb200_recon")
+        return rec
+
+    def residue(self, items, rates, elems):
+        items = np.ascontiguousarray(items, RESIDUE_ITEM).copy()
+        rates = np.ascontiguousarray(rates, RATES)
+        coef = np.zeros(elems, np.int16)
+        rec = np.zeros(elems, np.int16)
+        self._ck(self.L.xb200_residue(self.h, _p(items), len(items), _p(rates), len(rates), _p(coef), _p(rec), elems, MEM_HOST),
+                 "xb200_residue")
+        return items, coef, rec

@@ -1,0 +1,655 @@
+// xb200_api.cu -- host side of the C ABI declared in include/xeve_b200.h: context, device
+// picture pool, staging, kernel launches.  Single translation unit (the kernels share
+// __constant__ tables).  There is deliberately no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "xb200_common.cuh"
+#include "xb200_me.cuh"
+#include "xb200_mc.cuh"
+#include "xb200_tq.cuh"
+#include "xb200_misc.cuh"
+
+namespace {
+
+struct DevBuf {
+    void  *p   = nullptr;
+    size_t cap = 0;
+};
+
+struct Pic {
+    bool     used = false, padded = false;
+    int      pad[3] = {0, 0, 0}, s[3] = {0, 0, 0}, w[3] = {0, 0, 0}, h[3] = {0, 0, 0};
+    int16_t *buf[3] = {nullptr, nullptr, nullptr};
+};
+
+} // namespace
+
+struct xb200_ctx {
+    int              device = 0;
+    cudaStream_t     stream = nullptr;
+    xb200_seq        seq{};
+    SeqDev           sq{};
+    std::vector<Pic> pics;
+    PicDev          *d_pics = nullptr;
+    int              d_pics_cap = 0;
+    bool             pics_dirty = true;
+    int8_t          *d_tm64 = nullptr;
+    int             *d_err = nullptr;
+    int             *d_bins = nullptr; // 8 counters + 8 max-range
+    DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
+    cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
+    double           last_ms = 0.0;
+    int64_t          launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if(e_ != cudaSuccess) {                                                                          \
+            fprintf(stderr, "xeve_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_ == cudaErrorMemoryAllocation ? XB200_ERR_OUT_OF_MEMORY : XB200_ERR_UNEXPECTED;    \
+        }                                                                                                \
+    } while(0)
+
+int ensure(DevBuf &b, size_t bytes)
+{
+    if(bytes <= b.cap) return XB200_OK;
+    if(b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return XB200_OK;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+int sync_pics(xb200_ctx *c)
+{
+    if(!c->pics_dirty) return XB200_OK;
+    const int n = (int)c->pics.size();
+    if(n > c->d_pics_cap) {
+        if(c->d_pics) cudaFree(c->d_pics);
+        c->d_pics_cap = n + 16;
+        CK(cudaMalloc(&c->d_pics, sizeof(PicDev) * c->d_pics_cap));
+    }
+    std::vector<PicDev> h(n);
+    for(int i = 0; i < n; i++) {
+        const Pic &p = c->pics[i];
+        memset(&h[i], 0, sizeof(PicDev));
+        if(!p.used) continue;
+        for(int k = 0; k < 3; k++) {
+            h[i].p[k] = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
+            h[i].s[k] = p.s[k];
+        }
+        h[i].w = p.w[0]; h[i].h = p.h[0]; h[i].pad_l = p.pad[0]; h[i].pad_c = p.pad[1]; h[i].valid = 1;
+    }
+    if(n) CK(cudaMemcpyAsync(c->d_pics, h.data(), sizeof(PicDev) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); // h goes out of scope
+    c->pics_dirty = false;
+    return XB200_OK;
+}
+
+bool pic_ok(const xb200_ctx *c, int h) { return h >= 0 && h < (int)c->pics.size() && c->pics[h].used; }
+
+// bring a caller buffer to the device (or use it in place)
+template <typename T> int to_dev(xb200_ctx *c, DevBuf &b, const T *src, size_t count, int mem, T **out)
+{
+    if(mem == XB200_MEM_DEVICE || src == nullptr) { *out = const_cast<T *>(src); return XB200_OK; }
+    int r = ensure(b, count * sizeof(T) + 64);
+    if(r) return r;
+    if(count) CK(cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = static_cast<T *>(b.p);
+    return XB200_OK;
+}
+template <typename T> int to_host(xb200_ctx *c, T *dst, const T *dev, size_t count, int mem)
+{
+    if(mem == XB200_MEM_DEVICE || (const void *)dst == (const void *)dev) return XB200_OK;
+    if(count) CK(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return XB200_OK;
+}
+
+int finish(xb200_ctx *c)
+{
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+__global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const xb200_me_item &it = items[i];
+    const int            l2 = it.log2_cuw;
+    int                  key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : 4; // bin 4 = unsupported shape
+    const int            slot = atomicAdd(&bins[key], 1);
+    if(key < 4) {
+        order[(size_t)key * n + slot] = i;
+        int d = it.poc - it.ref_poc;
+        d     = d < 0 ? -d : d;
+        int dyn = (it.max_search_range * d + (it.gop_size >> 1)) / max(1, it.gop_size);
+        dyn     = max(it.max_search_range >> 2, min(it.max_search_range, dyn));
+        atomicMax(&bins[8 + key], it.bi ? 5 : dyn + 2);
+    }
+}
+
+template <int L2>
+int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cnt, const int16_t *d_side, int margin)
+{
+    if(cnt == 0) return XB200_OK;
+    const int W = 1 << L2, ext = W + 2 * margin + 7;
+    const int cap = (align_up(ext, 8) + 8) * ext + 16;
+    const size_t smem = me_smem_bytes(L2, cap);
+    if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(k_me<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_me<L2><<<cnt, ME_THREADS, smem, c->stream>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *xb200_version(void) { return "xeve_b200 0.1 (sm_100a)"; }
+
+int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
+{
+    if(!out || !seq) return XB200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if(seq->w <= 0 || seq->h <= 0 || (seq->w & 7) || (seq->h & 7) || seq->bit_depth < 8 || seq->bit_depth > 14)
+        return XB200_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "xeve_b200: no usable CUDA device (this library has no CPU path)\n");
+        return XB200_ERR_UNSUPPORTED;
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if(prop.major != 10) {
+        fprintf(stderr, "xeve_b200: device %d is sm_%d%d; this build targets sm_100a only\n", device, prop.major, prop.minor);
+        return XB200_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(device));
+    xb200_ctx *c = new xb200_ctx();
+    c->device = device;
+    c->seq    = *seq;
+    c->sq.w = seq->w; c->sq.h = seq->h; c->sq.bd = seq->bit_depth;
+    c->sq.me_level = seq->me_level; c->sq.hpel_cnt = seq->hpel_cnt; c->sq.qpel_cnt = seq->qpel_cnt;
+    c->sq.me_complexity = seq->me_complexity;
+    for(int i = 0; i < 2; i++) { c->sq.min_clip[i] = seq->min_clip[i]; c->sq.max_clip[i] = seq->max_clip[i]; }
+    c->sq.rdoq = seq->rdoq;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    // constant tables
+    {
+        static int8_t tm[64 * 64];
+        xb200_gen_tm64(tm);
+        CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
+        CK(cudaMalloc(&c->d_tm64, sizeof(tm)));
+        CK(cudaMemcpy(c->d_tm64, tm, sizeof(tm), cudaMemcpyHostToDevice));
+        const int16_t l[4][8] = XB200_MC_L_TAPS;
+        const int16_t ch[8][4] = XB200_MC_C_TAPS;
+        const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
+        int64_t       es[6][7];
+        for(int q = 0; q < 6; q++)
+            for(int l2 = 0; l2 < 7; l2++) es[q][l2] = xb200_err_scale(q, l2, seq->bit_depth);
+        CK(cudaMemcpyToSymbol(c_mc_l, l, sizeof(l)));
+        CK(cudaMemcpyToSymbol(c_mc_c, ch, sizeof(ch)));
+        CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
+        CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
+        CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+    }
+    CK(cudaMalloc(&c->d_err, sizeof(int)));
+    CK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CK(cudaMalloc(&c->d_bins, sizeof(int) * 16));
+    CK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResSmem)));
+    CK(cudaFuncSetAttribute(k_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
+    CK(cudaFuncSetAttribute(k_itdq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
+    *out = c;
+    return XB200_OK;
+}
+
+void xb200_destroy(xb200_ctx *c)
+{
+    if(!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for(auto &p : c->pics)
+        for(int k = 0; k < 3; k++)
+            if(p.buf[k]) cudaFree(p.buf[k]);
+    for(DevBuf *b : {&c->b_items, &c->b_side, &c->b_aux0, &c->b_aux1, &c->b_aux2, &c->b_order, &c->b_stage})
+        if(b->p) cudaFree(b->p);
+    if(c->d_pics) cudaFree(c->d_pics);
+    if(c->d_tm64) cudaFree(c->d_tm64);
+    if(c->d_err) cudaFree(c->d_err);
+    if(c->d_bins) cudaFree(c->d_bins);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int64_t xb200_launch_count(const xb200_ctx *c) { return c ? c->launches : 0; }
+double  xb200_last_kernel_ms(const xb200_ctx *c) { return c ? c->last_ms : 0.0; }
+
+// ---- pictures ---------------------------------------------------------------------------------------------
+int xb200_pic_create(xb200_ctx *c, int padded, int32_t *handle)
+{
+    if(!c || !handle) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    int idx = -1;
+    for(size_t i = 0; i < c->pics.size(); i++)
+        if(!c->pics[i].used) { idx = (int)i; break; }
+    if(idx < 0) { c->pics.emplace_back(); idx = (int)c->pics.size() - 1; }
+    Pic &p = c->pics[idx];
+    p = Pic();
+    p.padded = padded != 0;
+    for(int k = 0; k < 3; k++) {
+        p.w[k]   = k ? c->seq.w / 2 : c->seq.w;
+        p.h[k]   = k ? c->seq.h / 2 : c->seq.h;
+        p.pad[k] = padded ? (k ? XB200_PAD_C : XB200_PAD_L) : 0;
+        p.s[k]   = align_up(p.w[k] + 2 * p.pad[k], 64);
+        const size_t elems = (size_t)p.s[k] * (p.h[k] + 2 * p.pad[k] + 1) + 64;
+        CK(cudaMalloc(&p.buf[k], elems * sizeof(int16_t)));
+        CK(cudaMemsetAsync(p.buf[k], 0, elems * sizeof(int16_t), c->stream));
+    }
+    p.used = true;
+    c->pics_dirty = true;
+    *handle = idx;
+    return XB200_OK;
+}
+
+int xb200_pic_destroy(xb200_ctx *c, int32_t handle)
+{
+    if(!c || !pic_ok(c, handle)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    Pic &p = c->pics[handle];
+    for(int k = 0; k < 3; k++) { cudaFree(p.buf[k]); p.buf[k] = nullptr; }
+    p.used = false;
+    c->pics_dirty = true;
+    return XB200_OK;
+}
+
+static int pad_planes(xb200_ctx *c, Pic &p)
+{
+    if(!p.padded) return XB200_OK;
+    for(int k = 0; k < 3; k++) {
+        int16_t *act = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
+        dim3     grid((p.w[k] + 2 * p.pad[k] + 127) / 128, p.h[k] + 2 * p.pad[k]);
+        k_pad<<<grid, 128, 0, c->stream>>>(act, p.s[k], p.w[k], p.h[k], p.pad[k]);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_pic_upload(xb200_ctx *c, int32_t handle, const void *const planes[3], const int32_t stride_bytes[3], int in_bit_depth,
+                     int mem)
+{
+    if(!c || !pic_ok(c, handle) || !planes || !stride_bytes || in_bit_depth < 8 || in_bit_depth > c->seq.bit_depth)
+        return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    Pic      &p = c->pics[handle];
+    const int bps = in_bit_depth > 8 ? 2 : 1, shift = c->seq.bit_depth - in_bit_depth;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    size_t off[3], total = 0;
+    for(int k = 0; k < 3; k++) { off[k] = total; total += (size_t)align_up(p.w[k] * bps, 256) * p.h[k]; }
+    if(mem == XB200_MEM_HOST) {
+        int r = ensure(c->b_stage, total);
+        if(r) return r;
+    }
+    for(int k = 0; k < 3; k++) {
+        const uint8_t *src;
+        int            sstride;
+        if(mem == XB200_MEM_HOST) {
+            sstride = align_up(p.w[k] * bps, 256);
+            uint8_t *d = static_cast<uint8_t *>(c->b_stage.p) + off[k];
+            CK(cudaMemcpy2DAsync(d, sstride, planes[k], stride_bytes[k], (size_t)p.w[k] * bps, p.h[k], cudaMemcpyHostToDevice,
+                                 c->stream));
+            src = d;
+        }
+        else { src = static_cast<const uint8_t *>(planes[k]); sstride = stride_bytes[k]; }
+        int16_t *act = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
+        dim3     grid((p.w[k] + 255) / 256, p.h[k]);
+        if(bps == 1) k_convert<uint8_t><<<grid, 256, 0, c->stream>>>(src, sstride, act, p.s[k], p.w[k], p.h[k], shift);
+        else k_convert<uint16_t><<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint16_t *>(src), sstride / 2, act, p.s[k], p.w[k], p.h[k], shift);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    int r = pad_planes(c, p);
+    if(r) return r;
+    return finish(c);
+}
+
+int xb200_pic_upload_s16(xb200_ctx *c, int32_t handle, const int16_t *const planes[3], const int32_t stride_elems[3], int mem)
+{
+    if(!c || !pic_ok(c, handle) || !planes || !stride_elems) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    Pic &p = c->pics[handle];
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for(int k = 0; k < 3; k++) {
+        int16_t *act = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
+        CK(cudaMemcpy2DAsync(act, (size_t)p.s[k] * 2, planes[k], (size_t)stride_elems[k] * 2, (size_t)p.w[k] * 2, p.h[k],
+                             mem == XB200_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int r = pad_planes(c, p);
+    if(r) return r;
+    return finish(c);
+}
+
+int xb200_pic_download(xb200_ctx *c, int32_t handle, int with_padding, int16_t *const planes[3], const int32_t stride_elems[3])
+{
+    if(!c || !pic_ok(c, handle) || !planes || !stride_elems) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    Pic &p = c->pics[handle];
+    for(int k = 0; k < 3; k++) {
+        const int      pad = with_padding ? p.pad[k] : 0;
+        const int16_t *src = p.buf[k] + (size_t)(p.pad[k] - pad) * p.s[k] + (p.pad[k] - pad);
+        CK(cudaMemcpy2DAsync(planes[k], (size_t)stride_elems[k] * 2, src, (size_t)p.s[k] * 2, (size_t)(p.w[k] + 2 * pad) * 2,
+                             p.h[k] + 2 * pad, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
+// ---- probes -----------------------------------------------------------------------------------------------
+} // extern "C"
+template <typename OutT, typename K>
+static int run_probe(xb200_ctx *c, const xb200_blk_item *items, int64_t n, OutT *out, int mem, K kernel)
+{
+    if(!c || (n && (!items || !out)) || n < 0) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++)
+            if(!pic_ok(c, items[i].pic1) || !pic_ok(c, items[i].pic2) || items[i].plane1 > 2 || items[i].plane2 > 2)
+                return XB200_ERR_INVALID_ARGUMENT;
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_blk_item *d_items;
+    OutT           *d_out = out;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if(mem == XB200_MEM_HOST) {
+        if((r = ensure(c->b_aux0, (size_t)n * sizeof(OutT) + 64))) return r;
+        d_out = static_cast<OutT *>(c->b_aux0.p);
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if(n) {
+        kernel<<<(unsigned)((n + 3) / 4), 128, 0, c->stream>>>(c->d_pics, d_items, n, d_out, c->sq.bd);
+        c->launches++;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, out, d_out, (size_t)n, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+extern "C" {
+int xb200_sad(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem) { return run_probe(c, items, n, out, mem, k_sad); }
+int xb200_ssd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int64_t *out, int mem) { return run_probe(c, items, n, out, mem, k_ssd); }
+int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem) { return run_probe(c, items, n, out, mem, k_satd); }
+
+// ---- motion search ------------------------------------------------------------------------------------------
+int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem)
+{
+    if(!c || n < 0 || (n && !items) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            const xb200_me_item &it = items[i];
+            if(!pic_ok(c, it.cur_pic) || !pic_ok(c, it.ref_pic) || !c->pics[it.ref_pic].padded || it.gop_size <= 0 ||
+               (it.bi && (it.org_bi_off < 0 || (it.org_bi_off & 3) || !side ||
+                          it.org_bi_off + (1 << (it.log2_cuw + it.log2_cuh)) > side_elems)))
+                return XB200_ERR_INVALID_ARGUMENT;
+            if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 3 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
+        }
+    if(c->sq.me_complexity > 1) return XB200_ERR_UNSUPPORTED; // me_raster (placebo) is not offloaded
+    if(n == 0) return XB200_OK;
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_me_item *d_items;
+    int16_t       *d_side;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_side, side, (size_t)side_elems, mem, &d_side))) return r;
+    if((r = ensure(c->b_order, sizeof(int32_t) * 4 * (size_t)n))) return r;
+    int32_t *order = static_cast<int32_t *>(c->b_order.p);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int) * 16, c->stream));
+    k_me_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins);
+    c->launches++;
+    int bins[16];
+    CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if(bins[4]) return XB200_ERR_UNSUPPORTED;
+    // largest blocks first: they are the long poles of the launch sequence
+    if((r = launch_me<6>(c, d_items, order + 3 * n, bins[3], d_side, bins[8 + 3]))) return r;
+    if((r = launch_me<5>(c, d_items, order + 2 * n, bins[2], d_side, bins[8 + 2]))) return r;
+    if((r = launch_me<4>(c, d_items, order + 1 * n, bins[1], d_side, bins[8 + 1]))) return r;
+    if((r = launch_me<3>(c, d_items, order + 0 * n, bins[0], d_side, bins[8 + 0]))) return r;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    if(err) { cudaMemset(c->d_err, 0, sizeof(int)); return XB200_ERR_UNEXPECTED; }
+    return XB200_OK;
+}
+
+// ---- motion compensation ------------------------------------------------------------------------------------
+static int check_mc(const xb200_ctx *c, const xb200_mc_item &it)
+{
+    if(it.w < 4 || it.h < 4 || it.w > 64 || it.h > 64 || (it.w & 3) || (it.h & 3)) return XB200_ERR_UNSUPPORTED;
+    if(it.refi[0] < 0 && it.refi[1] < 0) return XB200_ERR_INVALID_ARGUMENT;
+    for(int l = 0; l < 2; l++)
+        if(it.refi[l] >= 0 && (!pic_ok(c, it.ref_pic[l]) || !c->pics[it.ref_pic[l]].padded)) return XB200_ERR_INVALID_ARGUMENT;
+    return XB200_OK;
+}
+
+int xb200_mc(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int64_t *pred_off, int16_t *pred, int64_t pred_elems,
+             int mem)
+{
+    if(!c || n < 0 || (n && (!items || !pred_off || !pred)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            int r = check_mc(c, items[i]);
+            if(r) return r;
+            if(pred_off[i] < 0 || pred_off[i] + items[i].w * items[i].h * 3 / 2 > pred_elems) return XB200_ERR_INVALID_ARGUMENT;
+        }
+    if(n == 0) return XB200_OK;
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_mc_item *d_items;
+    int64_t       *d_off;
+    int16_t       *d_pred = pred;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, pred_off, (size_t)n, mem, &d_off))) return r;
+    if(mem == XB200_MEM_HOST) {
+        if((r = ensure(c->b_aux1, (size_t)pred_elems * 2 + 64))) return r;
+        d_pred = static_cast<int16_t *>(c->b_aux1.p);
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_mc<<<(unsigned)n, MC_THREADS, MC_SMEM_BYTES, c->stream>>>(c->d_pics, d_items, (int)n, d_off, d_pred, c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, pred, d_pred, (size_t)pred_elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+// ---- transform / quantisation ---------------------------------------------------------------------------------
+static int check_tq(const xb200_tq_item &it, int64_t n_rates, int64_t elems)
+{
+    if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 3 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
+    if(it.rate_idx < 0 || it.rate_idx >= n_rates) return XB200_ERR_INVALID_ARGUMENT;
+    if(it.in_off < 0 || it.in_off + ((int64_t)3 << (2 * it.log2_cuw)) / 2 > elems) return XB200_ERR_INVALID_ARGUMENT;
+    return XB200_OK;
+}
+
+int xb200_tq(xb200_ctx *c, xb200_tq_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
+             int64_t coef_elems, int mem)
+{
+    if(!c || n < 0 || (n && (!items || !coef || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            int r = check_tq(items[i], n_rates, coef_elems);
+            if(r) return r;
+        }
+    if(n == 0) return XB200_OK;
+    int            r;
+    xb200_tq_item *d_items;
+    xb200_rates   *d_rates;
+    int16_t       *d_coef;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, rates, (size_t)n_rates, mem, &d_rates))) return r;
+    if((r = to_dev(c, c->b_aux1, coef, (size_t)coef_elems, mem, &d_coef))) return r;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_tq<<<(unsigned)n, TQ_THREADS, sizeof(TqSmem), c->stream>>>(d_items, (int)n, d_rates, d_coef, c->d_tm64, c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
+    if((r = to_host(c, coef, d_coef, (size_t)coef_elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_itdq(xb200_ctx *c, const xb200_tq_item *items, int64_t n, int16_t *coef, int64_t coef_elems, int mem)
+{
+    if(!c || n < 0 || (n && (!items || !coef)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            int r = check_tq(items[i], INT64_MAX, coef_elems);
+            if(r) return r;
+        }
+    if(n == 0) return XB200_OK;
+    int            r;
+    xb200_tq_item *d_items;
+    int16_t       *d_coef;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux1, coef, (size_t)coef_elems, mem, &d_coef))) return r;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_itdq<<<(unsigned)n, TQ_THREADS, sizeof(TqSmem), c->stream>>>(d_items, (int)n, d_coef, c->d_tm64, c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, coef, d_coef, (size_t)coef_elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16_t *resi, const int16_t *pred, int16_t *rec,
+                int64_t elems, int mem)
+{
+    if(!c || n < 0 || (n && (!items || !resi || !pred || !rec)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            int r = check_tq(items[i], INT64_MAX, elems);
+            if(r) return r;
+        }
+    if(n == 0) return XB200_OK;
+    int            r;
+    xb200_tq_item *d_items;
+    int16_t       *d_resi, *d_pred, *d_rec = rec;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, resi, (size_t)elems, mem, &d_resi))) return r;
+    if((r = to_dev(c, c->b_aux1, pred, (size_t)elems, mem, &d_pred))) return r;
+    if(mem == XB200_MEM_HOST) {
+        if((r = ensure(c->b_aux2, (size_t)elems * 2 + 64))) return r;
+        d_rec = static_cast<int16_t *>(c->b_aux2.p);
+        CK(cudaMemsetAsync(d_rec, 0, (size_t)elems * 2, c->stream));
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_recon<<<(unsigned)n, 128, 0, c->stream>>>(d_items, (int)n, d_resi, d_pred, d_rec, c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, rec, d_rec, (size_t)elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
+                  int16_t *rec, int64_t elems, int mem)
+{
+    if(!c || n < 0 || (n && (!items || !coef || !rec || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            const xb200_residue_item &it = items[i];
+            int r = check_mc(c, it.mc);
+            if(r) return r;
+            if(it.mc.w != it.mc.h || it.mc.w < 8 || (it.mc.w & (it.mc.w - 1))) return XB200_ERR_UNSUPPORTED;
+            if(!pic_ok(c, it.cur_pic) || it.rate_idx < 0 || it.rate_idx >= n_rates || it.out_off < 0 ||
+               it.out_off + it.mc.w * it.mc.h * 3 / 2 > elems)
+                return XB200_ERR_INVALID_ARGUMENT;
+        }
+    if(n == 0) return XB200_OK;
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_residue_item *d_items;
+    xb200_rates        *d_rates;
+    int16_t            *d_coef = coef, *d_rec = rec;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, rates, (size_t)n_rates, mem, &d_rates))) return r;
+    if(mem == XB200_MEM_HOST) {
+        if((r = ensure(c->b_aux1, (size_t)elems * 2 + 64))) return r;
+        if((r = ensure(c->b_aux2, (size_t)elems * 2 + 64))) return r;
+        d_coef = static_cast<int16_t *>(c->b_aux1.p);
+        d_rec  = static_cast<int16_t *>(c->b_aux2.p);
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_residue<<<(unsigned)n, TQ_THREADS, sizeof(ResSmem), c->stream>>>(c->d_pics, d_items, (int)n, d_rates, d_coef, d_rec, c->d_tm64,
+                                                                          c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
+    if((r = to_host(c, coef, d_coef, (size_t)elems, mem))) return r;
+    if((r = to_host(c, rec, d_rec, (size_t)elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+} // extern "C"

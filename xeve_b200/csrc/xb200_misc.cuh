@@ -1,0 +1,200 @@
+// xb200_misc.cuh -- picture preparation, distortion probes and the fused residue kernel.
+#pragma once
+#include "xb200_common.cuh"
+#include "xb200_mc.cuh"
+#include "xb200_tq.cuh"
+
+// ---- picture upload: input depth -> internal depth (reference src_base/xeve_util.c:1552-1571, 1670-1704)
+//      and border replication (reference src_base/xeve_util.c:190-248) ----------------------------------
+template <typename T>
+__global__ void k_convert(const T *__restrict__ src, int src_stride_elems, int16_t *__restrict__ dst, int dst_stride, int w, int h,
+                          int shift)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if(x < w && y < h) dst[(size_t)y * dst_stride + x] = (int16_t)((int)src[(size_t)y * src_stride_elems + x] << shift);
+}
+
+// one thread per sample of the padded plane; interior samples are left alone
+__global__ void k_pad(int16_t *__restrict__ act, int stride, int w, int h, int pad)
+{
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x) - pad, y = (int)blockIdx.y - pad;
+    if(x >= w + pad) return;
+    if(x >= 0 && x < w && y >= 0 && y < h) return;
+    const int sx = min(max(x, 0), w - 1), sy = min(max(y, 0), h - 1);
+    act[(ptrdiff_t)y * stride + x] = act[(ptrdiff_t)sy * stride + sx];
+}
+
+// ---- distortion probes: one warp per item, blocks addressed inside device pictures -------------------------
+XB_DEV const int16_t *blk_ptr(const PicDev *pics, int pic, int plane, int x, int y, int &stride)
+{
+    const PicDev p = pics[pic];
+    stride         = p.s[plane];
+    return p.p[plane] + (ptrdiff_t)y * stride + x;
+}
+
+// XEVE_FN_SAD (src_base/xeve_sad.c:40-61); the shift is applied to the sum
+__global__ void k_sad(const PicDev *__restrict__ pics, const xb200_blk_item *__restrict__ items, int64_t n, int32_t *__restrict__ out, int bd)
+{
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(i >= n) return;
+    const xb200_blk_item it = items[i];
+    int            s1, s2;
+    const int16_t *a = blk_ptr(pics, it.pic1, it.plane1, it.x1, it.y1, s1), *b = blk_ptr(pics, it.pic2, it.plane2, it.x2, it.y2, s2);
+    const int      w = 1 << it.log2w, h = 1 << it.log2h, lane = threadIdx.x & 31;
+    int            sum = 0;
+    for(int e = lane; e < w * h; e += 32) {
+        const int d = (int)a[(ptrdiff_t)(e / w) * s1 + e % w] - (int)b[(ptrdiff_t)(e / w) * s2 + e % w];
+        sum += (d ^ (d >> 15)) - (d >> 15); // XEVE_ABS16 applied to the int difference
+    }
+#pragma unroll
+    for(int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if(lane == 0) out[i] = sum >> (bd - 8);
+}
+
+// XEVE_FN_SSD (src_base/xeve_sad.c:275-297); the shift is applied to every squared difference
+__global__ void k_ssd(const PicDev *__restrict__ pics, const xb200_blk_item *__restrict__ items, int64_t n, int64_t *__restrict__ out, int bd)
+{
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(i >= n) return;
+    const xb200_blk_item it = items[i];
+    int            s1, s2;
+    const int16_t *a = blk_ptr(pics, it.pic1, it.plane1, it.x1, it.y1, s1), *b = blk_ptr(pics, it.pic2, it.plane2, it.x2, it.y2, s2);
+    const int      w = 1 << it.log2w, h = 1 << it.log2h, lane = threadIdx.x & 31, sh = (bd - 8) << 1;
+    int64_t        sum = 0;
+    for(int e = lane; e < w * h; e += 32) {
+        const int d = (int)a[(ptrdiff_t)(e / w) * s1 + e % w] - (int)b[(ptrdiff_t)(e / w) * s2 + e % w];
+        sum += (d * d) >> sh;
+    }
+#pragma unroll
+    for(int m = 16; m > 0; m >>= 1) sum += (int64_t)shfl_xor_u64((uint64_t)sum, m);
+    if(lane == 0) out[i] = sum;
+}
+
+// Hadamard SATD of one TN x TN tile held by one thread (src_base/xeve_sad.c:417-607)
+template <int TN> XB_DEV int had_tile_dev(const int16_t *a, int sa, const int16_t *b, int sb)
+{
+    int m[TN][TN];
+#pragma unroll
+    for(int y = 0; y < TN; y++)
+#pragma unroll
+        for(int x = 0; x < TN; x++) m[y][x] = (int)a[(ptrdiff_t)y * sa + x] - (int)b[(ptrdiff_t)y * sb + x];
+#pragma unroll
+    for(int pass = 0; pass < 2; pass++)
+#pragma unroll
+        for(int r = 0; r < TN; r++)
+#pragma unroll
+            for(int len = 1; len < TN; len <<= 1)
+#pragma unroll
+                for(int i = 0; i < TN; i += len << 1)
+#pragma unroll
+                    for(int jj = i; jj < i + len; jj++) {
+                        int &p = pass ? m[jj][r] : m[r][jj], &q = pass ? m[jj + len][r] : m[r][jj + len];
+                        const int u = p + q, v = p - q;
+                        p = u; q = v;
+                    }
+    int s = abs(m[0][0]) >> 2;
+#pragma unroll
+    for(int y = 0; y < TN; y++)
+#pragma unroll
+        for(int x = 0; x < TN; x++)
+            if(x | y) s += abs(m[y][x]);
+    return TN == 8 ? (s + 2) >> 2 : (s + 1) >> 1;
+}
+
+// XEVE_FN_SATD = xeve_had for square blocks (src_base/xeve_sad.c:1043-1140)
+__global__ void k_satd(const PicDev *__restrict__ pics, const xb200_blk_item *__restrict__ items, int64_t n, int32_t *__restrict__ out, int bd)
+{
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(i >= n) return;
+    const xb200_blk_item it = items[i];
+    int            s1, s2;
+    const int16_t *a = blk_ptr(pics, it.pic1, it.plane1, it.x1, it.y1, s1), *b = blk_ptr(pics, it.pic2, it.plane2, it.x2, it.y2, s2);
+    const int      w = 1 << it.log2w, h = 1 << it.log2h, lane = threadIdx.x & 31;
+    int            sum = 0;
+    if((w & 7) == 0 && (h & 7) == 0) {
+        const int tw = w >> 3, nt = tw * (h >> 3);
+        for(int t = lane; t < nt; t += 32) {
+            const int tx = (t % tw) * 8, ty = (t / tw) * 8;
+            sum += had_tile_dev<8>(a + (ptrdiff_t)ty * s1 + tx, s1, b + (ptrdiff_t)ty * s2 + tx, s2);
+        }
+    }
+    else {
+        const int tw = w >> 2, nt = tw * (h >> 2);
+        for(int t = lane; t < nt; t += 32) {
+            const int tx = (t % tw) * 4, ty = (t / tw) * 4;
+            sum += had_tile_dev<4>(a + (ptrdiff_t)ty * s1 + tx, s1, b + (ptrdiff_t)ty * s2 + tx, s2);
+        }
+    }
+#pragma unroll
+    for(int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if(lane == 0) out[i] = sum >> (bd - 8);
+}
+
+// ---- fused residue kernel: prediction -> residual -> SSD -> DCT + RDOQ -> dequant + IDCT -> recon -> SSD
+//      (the distortion/transform body of pinter_residue_rdo, reference src_base/xeve_pinter.c:961-1056)
+struct ResSmem {
+    TqSmem  tq;
+    int16_t pred[6144];
+    int16_t aux[6144];
+};
+
+__global__ void __launch_bounds__(TQ_THREADS) k_residue(const PicDev *__restrict__ pics, xb200_residue_item *__restrict__ items, int n,
+                                                         const xb200_rates *__restrict__ rates, int16_t *__restrict__ coef,
+                                                         int16_t *__restrict__ rec, const int8_t *__restrict__ g_tm64, SeqDev sq)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ResSmem &R = *reinterpret_cast<ResSmem *>(smem_raw);
+    TqSmem  &S = R.tq;
+    const int tid = threadIdx.x;
+    if(blockIdx.x >= n) return;
+    xb200_residue_item *it = &items[blockIdx.x];
+    const xb200_mc_item mc = it->mc;
+    tq_load_tm(S, g_tm64, tid, TQ_THREADS);
+    mc_item(pics, mc, sq, R.pred, R.aux, reinterpret_cast<int16_t *>(S.T), tid, TQ_THREADS);
+
+    const PicDev o = pics[it->cur_pic];
+    const int    w = mc.w, ny = w * mc.h, nc = ny >> 2, maxv = (1 << sq.bd) - 1, sh = (sq.bd - 8) << 1;
+    int          l2y = 0;
+    while((1 << l2y) < w) l2y++;
+    for(int c = 0; c < 3; c++) {
+        const int      l2 = c ? l2y - 1 : l2y, bw = 1 << l2, nn = bw * bw, poff = c == 0 ? 0 : (c == 1 ? ny : ny + nc);
+        const int16_t *org = o.p[c] + (ptrdiff_t)(c ? mc.y >> 1 : mc.y) * o.s[c] + (c ? mc.x >> 1 : mc.x);
+        const int      so = o.s[c];
+        const int16_t *pr = R.pred + poff;
+        int64_t        dpart = 0;
+        for(int e = tid; e < nn; e += TQ_THREADS) {
+            const int d = (int)org[(ptrdiff_t)(e >> l2) * so + (e & (bw - 1))] - (int)pr[e];
+            S.blk[e] = (int16_t)d;
+            dpart += (d * d) >> sh;
+        }
+        const int64_t dist_pred = block_sum_s64(S, dpart, tid, TQ_THREADS);
+        int           nnz = 0;
+        int16_t      *gco = coef + it->out_off + poff, *grec = rec + it->out_off + poff;
+        if((it->run_stats >> c) & 1) {
+            fwd_dct(S, l2, sq.bd, tid, TQ_THREADS);
+            nnz = quant_block(S, l2, it->qp[c], it->lambda[c], 0, c, it->slice_type, &rates[it->rate_idx], sq.bd, sq.rdoq, tid,
+                              TQ_THREADS);
+        }
+        for(int e = tid; e < nn; e += TQ_THREADS) gco[e] = S.blk[e];
+        __syncthreads();
+        int64_t dist_rec = dist_pred;
+        if(nnz) {
+            dequant_block(S, l2, it->qp[c], sq.bd, tid, TQ_THREADS);
+            inv_dct(S, l2, sq.bd, tid, TQ_THREADS);
+            int64_t rpart = 0;
+            for(int e = tid; e < nn; e += TQ_THREADS) {
+                const int16_t t = (int16_t)(S.blk[e] + pr[e]);
+                const int     v = clip3i(0, maxv, t);
+                grec[e]         = (int16_t)v;
+                const int d     = v - (int)org[(ptrdiff_t)(e >> l2) * so + (e & (bw - 1))];
+                rpart += (d * d) >> sh;
+            }
+            dist_rec = block_sum_s64(S, rpart, tid, TQ_THREADS);
+        }
+        else {
+            for(int e = tid; e < nn; e += TQ_THREADS) grec[e] = (int16_t)clip3i(0, maxv, pr[e]);
+        }
+        if(tid == 0) { it->nnz[c] = nnz; it->dist_pred[c] = dist_pred; it->dist_rec[c] = dist_rec; }
+        __syncthreads();
+    }
+}
