@@ -72,12 +72,14 @@ XB_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 }
 
 // ---- packed 16-bit SAD primitives (VIMNMX.S16x2 on sm_100a) -------------------------------------
-XB_DEV uint32_t absdiff_s16x2(uint32_t a, uint32_t b)
+// |a - b| per 16-bit half for operands whose halves compare correctly as UNSIGNED numbers
+// (non-negative samples, or signed samples biased by ^0x8000): max - min never borrows.
+XB_DEV uint32_t absdiff_u16x2(uint32_t a, uint32_t b)
 {
     uint32_t mx, mn;
-    asm("max.s16x2 %0, %1, %2;" : "=r"(mx) : "r"(a), "r"(b));
-    asm("min.s16x2 %0, %1, %2;" : "=r"(mn) : "r"(a), "r"(b));
-    return mx - mn; // each half: max - min >= 0, no borrow across halves
+    asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(a), "r"(b));
+    asm("min.u16x2 %0, %1, %2;" : "=r"(mn) : "r"(a), "r"(b));
+    return mx - mn;
 }
 XB_DEV uint32_t sum_halves(uint32_t v) { return (v & 0xffffu) + (v >> 16); }
 

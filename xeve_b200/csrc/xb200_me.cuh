@@ -36,7 +36,7 @@ struct MeWin {
 
 template <int L2>
 XB_DEV uint32_t me_group_sad(const int16_t *__restrict__ win, const MeWin &wn, const int16_t *__restrict__ org, int px, int py,
-                             int j /* lane in group */)
+                             int j /* lane in group */, uint32_t bias)
 {
     using Gm = MeGeom<L2>;
     const int      col_lane = j % Gm::LPR, row_lane = j / Gm::LPR;
@@ -53,8 +53,8 @@ XB_DEV uint32_t me_group_sad(const int16_t *__restrict__ win, const MeWin &wn, c
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(rowp + qc);
             const uint32_t  w0 = rp[0], w1 = rp[1], w2 = rp[2];
             const uint2     o  = *reinterpret_cast<const uint2 *>(org + r * Gm::W + qc);
-            acc += absdiff_s16x2(o.x, __funnelshift_r(w0, w1, sh));
-            acc += absdiff_s16x2(o.y, __funnelshift_r(w1, w2, sh));
+            acc += absdiff_u16x2(o.x, __funnelshift_r(w0, w1, sh) ^ bias);
+            acc += absdiff_u16x2(o.y, __funnelshift_r(w1, w2, sh) ^ bias);
             if(++cnt == 8) { total += sum_halves(acc); acc = 0; cnt = 0; } // halves hold <= 16 * 4093
         }
     }
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int grp = tid / Gm::G, j = tid % Gm::G;
-    const int it_idx = order[blockIdx.x];
     if(blockIdx.x >= n) return;
+    const int it_idx = order[blockIdx.x];
     xb200_me_item *it = &items[it_idx];
 
     if(tid == 0) mbar_init(bar, 1);
@@ -94,13 +94,18 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     const int16_t *refy = ref.p[0];
     const int      sref = ref.s[0];
 
-    // original block -> shared (picture rows, or the contiguous 2*org - pred block of bi search)
+    // original block -> shared (picture rows, or the contiguous 2*org - pred block of bi search).
+    // The bi block holds signed values: both operands are biased by ^0x8000 so that the packed
+    // unsigned max/min of the SAD sees them in the right order.
+    const uint32_t bias = bi ? 0x80008000u : 0u;
     {
         const int16_t *src = bi ? side + it->org_bi_off : cur.p[0] + (size_t)y * cur.s[0] + x;
         const int      so  = bi ? W : cur.s[0];
         for(int e = tid; e < W * W / 4; e += ME_THREADS) {
             const int r = e / (W / 4), c = (e % (W / 4)) * 4;
-            *reinterpret_cast<uint2 *>(org + r * W + c) = *reinterpret_cast<const uint2 *>(src + (size_t)r * so + c);
+            uint2 v = *reinterpret_cast<const uint2 *>(src + (size_t)r * so + c);
+            v.x ^= bias; v.y ^= bias;
+            *reinterpret_cast<uint2 *>(org + r * W + c) = v;
         }
     }
     __syncthreads();
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
             if(live) pos(c, px, py);
             px = (int16_t)px; py = (int16_t)py;
             const bool inr = live && px >= st.lo[0] && px <= st.hi[0] && py >= st.lo[1] && py <= st.hi[1];
-            uint32_t   sad = me_group_sad<L2>(win, wn, org, inr ? px : safe_x, inr ? py : safe_y, j);
+            uint32_t   sad = me_group_sad<L2>(win, wn, org, inr ? px : safe_x, inr ? py : safe_y, j, bias);
             if(live && j == 0) {
                 uint32_t cost = 0xffffffffu;
                 if(inr) {
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     if(sq.me_level > 1) {
         // ---- me_spel_pattern: every candidate = 8-tap interpolation of the whole CU + SAD -----------
         int       smv_x = mv_x, smv_y = mv_y, sbits = 0;
+        const int16_t obias = bi ? (int16_t)0x8000 : (int16_t)0;
         uint32_t  sbest = 0xffffffffu;
         ensure_window(x + (mv_x >> 2), y + (mv_y >> 2), 2);
         for(int stage = 0; stage < 2; stage++) {
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
 #pragma unroll
                         for(int t = 0; t < 8; t++) acc += c_mc_l[dy][t] * tmp[e + t * W];
                         const int v = clip3i(0, maxv, (acc + (1 << (s2 - 1))) >> s2);
-                        part += (uint32_t)abs((int)org[e] - v);
+                        part += (uint32_t)abs((int)(int16_t)(org[e] ^ obias) - v);
                     }
                 }
                 else {
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                             for(int t = 0; t < 8; t++) acc += c_mc_l[ph][t] * p[t * stp];
                             v = clip3i(0, maxv, acc >> 6);
                         }
-                        part += (uint32_t)abs((int)org[e] - v);
+                        part += (uint32_t)abs((int)(int16_t)(org[e] ^ obias) - v);
                     }
                 }
 #pragma unroll
