@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path throughput of the B200 library on the BASELINE.json workload.
+
+A "step" = one pass of the inter-search + transform hot path over ONE 1080p B picture
+(Baseline profile, preset fast): the frame-wide work lists of xeve_b200/worklist.py
+(2 uni-directional searches, the bi-prediction search, and the L0/L1/BI residue candidates of
+every CU of the 64/32/16/8 quad-tree) run as frame-wide grids.  Metric: frames per second.
+
+  value : whole-job fps with all inputs resident in HBM (C ABI called with XB200_MEM_DEVICE)
+  e2e   : same calls with HOST (pinned) buffers -- picture upload, work lists in, every result out
+  --impl reference : the reference's own CPU functions (oracle/_ref, all host threads) over a
+                     bounded sample of the same work lists
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP, W, H = "1080p", 1920, 1080
+POC, REF_POCS = 8, (0, 16)
+PAN = (3, 1)
+SAMPLE_ROWS = 4  # CTU rows of the bounded CPU sample (of 17)
+
+
+def frames_for_bench():
+    from xeve_b200.clips import Clip
+    c = Clip(CLIP)
+    return c, {n: c.frame(n) for n in (REF_POCS[0], POC, REF_POCS[1])}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                              timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def algorithmic_bytes(fw):
+    """SURVEY.md 8(d) compulsory HBM traffic of each stage for the units it processes (bytes).
+    ME: original luma once + each searched padded reference luma once + one result record per item.
+    residue: per item 3/2*N^2 samples x (org read + R reference reads + coef write + rec write)."""
+    w, h = fw.w, fw.h
+    ref_luma = 2 * (w + 288) * (h + 288)
+    n_me = 2 * fw.n_cu
+    me_uni = 2 * w * h + 2 * ref_luma + n_me * 16
+    me_bi = 2 * fw.side_elems + 2 * ref_luma + fw.n_cu * 16
+    bi_org = 2 * w * h + ref_luma + 2 * fw.side_elems
+    area = (1 << (2 * fw.l2.astype(np.int64))) * 3 // 2 * 2  # bytes of one Y+U+V block
+    residue = int((area * (1 + 1 + 2)).sum() * 2 + (area * (1 + 2 + 2)).sum())  # L0, L1 (R=1) + BI (R=2)
+    return dict(me_uni=me_uni, bi_org=bi_org, me_bi=me_bi, residue=residue)
+
+
+def run_b200(args, rank, world, dist):
+    import torch
+    from xeve_b200 import api
+    from xeve_b200.worklist import FrameWork
+
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    seq = api.make_seq(W, H, "fast")
+    if world > 1:  # the only exchange the path has: rank 0 broadcasts the sequence header
+        t = torch.from_numpy(seq.view(np.uint8).copy()).cuda()
+        dist.broadcast(t, src=0)
+        seq = t.cpu().numpy().view(api.SEQ)
+    hp = api.Hotpath(seq, device=dev)
+    L, ctx = hp.L, hp.h
+    clip, fr = frames_for_bench()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    refs = []
+    for poc in REF_POCS:
+        hd = hp.pic_create(padded=True)
+        hp.pic_upload(hd, *fr[poc], 8)
+        refs.append(hd)
+    cur = hp.pic_create(padded=False)
+    cur_planes = [pin(p) for p in fr[POC]]
+    cur_np = [p.numpy() for p in cur_planes]
+    hp.pic_upload(cur, *cur_np, 8)
+
+    fw = FrameWork(W, H, POC, REF_POCS, PAN, cur, refs, seed=rank)
+    cnt = fw.counts()
+    # ---- warm-up pass through the host-buffer API; also builds the dependent work lists ----------------
+    me_uni = hp.me(fw.me_uni)
+    bi_mc, me_bi_in = fw.build_bi(me_uni)
+    side = hp.bi_org(bi_mc, fw.bi_cur, fw.side_off, fw.side_elems)
+    me_bi = hp.me(me_bi_in, side)
+    res_in = fw.build_residue(me_bi)
+    res_out, coef, rec = hp.residue(res_in, fw.rates, fw.res_elems)
+    checksum = int(res_out["dist_rec"].sum() % (1 << 31))
+
+    # ---- device-resident buffers -----------------------------------------------------------------------------
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    d_me_uni, d_bi_mc, d_bi_cur, d_side_off = dv(fw.me_uni), dv(bi_mc), dv(fw.bi_cur), dv(fw.side_off)
+    d_me_bi, d_res, d_rates = dv(me_bi_in), dv(res_in), dv(fw.rates)
+    d_side = torch.zeros(fw.side_elems, dtype=torch.int16, device="cuda")
+    d_coef = torch.zeros(fw.res_elems, dtype=torch.int16, device="cuda")
+    d_rec = torch.zeros(fw.res_elems, dtype=torch.int16, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    stage_ms = {k: 0.0 for k in ("me_uni", "bi_org", "me_bi", "residue")}
+
+    def step_device(accumulate):
+        for name, call in (
+            ("me_uni", lambda: L.xb200_me(ctx, P(d_me_uni), cnt["me_uni"], None, 0, api.MEM_DEVICE)),
+            ("bi_org", lambda: L.xb200_bi_org(ctx, P(d_bi_mc), cnt["bi_org"], P(d_bi_cur), P(d_side_off), P(d_side), fw.side_elems, api.MEM_DEVICE)),
+            ("me_bi", lambda: L.xb200_me(ctx, P(d_me_bi), cnt["me_bi"], P(d_side), fw.side_elems, api.MEM_DEVICE)),
+            ("residue", lambda: L.xb200_residue(ctx, P(d_res), cnt["residue"], P(d_rates), 1, P(d_coef), P(d_rec), fw.res_elems, api.MEM_DEVICE)),
+        ):
+            r = call()
+            if r != 0:
+                raise RuntimeError(f"{name} failed: {r}")
+            if accumulate:
+                stage_ms[name] += hp.last_kernel_ms
+
+    for _ in range(args.warmup):
+        step_device(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    launches0 = hp.launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device(True)
+    torch.cuda.synchronize()
+    t_dev = time.perf_counter() - t0
+    launches = hp.launches - launches0
+    sampler.stop_flag = True
+    # results of the device-resident run equal the host-buffer run
+    got = np.frombuffer(d_res.cpu().numpy().tobytes(), api.RESIDUE_ITEM)
+    assert int(got["dist_rec"].sum() % (1 << 31)) == checksum, "device-resident run disagrees with host-buffer run"
+
+    # ---- e2e: the same calls with host (pinned) buffers, picture upload included ----------------------------
+    h_me_uni, h_me_bi, h_res = pin(fw.me_uni.view(np.uint8)), pin(me_bi_in.view(np.uint8)), pin(res_in.view(np.uint8))
+    h_side = pin(np.zeros(fw.side_elems, np.int16))
+    h_coef, h_rec = pin(np.zeros(fw.res_elems, np.int16)), pin(np.zeros(fw.res_elems, np.int16))
+    HP = lambda t: C.c_void_p(t.data_ptr())
+    planes = (C.c_void_p * 3)(*[p.data_ptr() for p in cur_planes])
+    strides = (C.c_int32 * 3)(W, W // 2, W // 2)
+
+    def step_host():
+        rr = [L.xb200_pic_upload(ctx, cur, planes, strides, 8, api.MEM_HOST),
+              L.xb200_me(ctx, HP(h_me_uni), cnt["me_uni"], None, 0, api.MEM_HOST),
+              L.xb200_bi_org(ctx, bi_mc.ctypes.data_as(C.c_void_p), cnt["bi_org"], fw.bi_cur.ctypes.data_as(C.c_void_p),
+                             fw.side_off.ctypes.data_as(C.c_void_p), HP(h_side), fw.side_elems, api.MEM_HOST),
+              L.xb200_me(ctx, HP(h_me_bi), cnt["me_bi"], HP(h_side), fw.side_elems, api.MEM_HOST),
+              L.xb200_residue(ctx, HP(h_res), cnt["residue"], fw.rates.ctypes.data_as(C.c_void_p), 1, HP(h_coef), HP(h_rec),
+                              fw.res_elems, api.MEM_HOST)]
+        if any(rr):
+            raise RuntimeError(f"e2e step failed: {rr}")
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(2, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    frame_bytes = W * H * 3 // 2
+    h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
+        + res_in.nbytes + fw.rates.nbytes
+    d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + 2 * 2 * fw.res_elems
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        hp.close()
+        return None
+    ms_step = t_dev / args.steps * 1e3
+    value = world * args.steps / t_dev
+    e2e_val = world * e2e_steps / t_e2e
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = algorithmic_bytes(fw)
+    per_stage = {k: v / args.steps for k, v in stage_ms.items()}
+    dom = max(per_stage, key=per_stage.get)
+    achieved = alg[dom] / (per_stage[dom] * 1e-3) / 1e9
+    out = {
+        "metric": "encoded fps (1080p, preset fast): inter-search + transform hot path of one B picture", "value": round(value, 3),
+        "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16 samples, s32/s64 arithmetic", "data": "synthetic",
+        "config": {"workload": "1080p B picture (POC 8 <- POC 0/16), Baseline preset fast, full 64/32/16/8 quad-tree: "
+                               f"{cnt['me_uni']} uni ME + {cnt['me_bi']} bi ME + {cnt['bi_org']} bi_org + {cnt['residue']} residue items per frame",
+                   "clip": "seeded synthetic 1920x1080 8-bit (xeve_b200/clips.py)", "mvp": "synthetic (true motion + jitter)",
+                   "parallelism": f"{world} independent picture streams (one per GPU), header broadcast only",
+                   "l2": "no explicit flush: each step writes 2 x %.0f MB of coef/rec, more than the 126 MB L2" % (2 * fw.res_elems / 1e6)},
+        "e2e": {"value": round(e2e_val, 3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": {k: round(v, 3) for k, v in per_stage.items()},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_bytes_per_launch": int(alg[dom]),
+                     "note": "integer ALU / shared-memory bound, not HBM bound: see DESIGN.md section 5"},
+        "clocks": sampler.summary(),
+    }
+    hp.close()
+    return out
+
+
+def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
+    """The reference's own CPU implementation of the path (oracle/_ref replay, all host threads) on a
+    bounded sample: the CUs of the first `sample_rows` CTU rows of the same picture."""
+    from oracle import refharness as rh
+    from xeve_b200 import api
+    from xeve_b200.clips import to_internal10
+    from xeve_b200.worklist import FrameWork
+    from tests_support import padded_planes_struct  # noqa: F401  (defined below, registered in sys.modules)
+
+    if not rh.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present on this machine"}
+    clip, fr = frames_for_bench()
+    seq = api.make_seq(W, H, "fast")
+    keep, planes = padded_planes_struct(fr, [REF_POCS[0], REF_POCS[1], POC])
+    fw = FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], rows=sample_rows)
+    cores = os.cpu_count() or 1
+    frac = fw.n_cu / FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1]).n_cu
+    steps = steps or args.steps
+    times = []
+    for it in range(args.warmup and 1 or 0, steps + 1):
+        t0 = time.perf_counter()
+        me_uni, s1 = rh.replay_me_raw(seq, planes, None, fw.me_uni.astype(rh.ME_REC), cores)
+        bi_mc, me_bi_in = fw.build_bi(me_uni.astype(api.ME_ITEM))
+        pred, off, s2 = rh.replay_mc_raw(seq, planes, bi_mc.astype(rh.MC_REC), cores)
+        side = np.zeros(fw.side_elems, np.int16)  # get_org_bi (untimed bookkeeping, trivial next to the search)
+        cy = to_internal10(fr[POC][0], 8)
+        for i in range(fw.n_cu):
+            s = 1 << int(fw.l2[i])
+            blk = cy[fw.y[i]:fw.y[i] + s, fw.x[i]:fw.x[i] + s].astype(np.int32) * 2 - pred[off[i]:off[i] + s * s].reshape(s, s)
+            side[fw.side_off[i]:fw.side_off[i] + s * s] = blk.reshape(-1)
+        me_bi, s3 = rh.replay_me_raw(seq, planes, side, me_bi_in.astype(rh.ME_REC), cores)
+        res_in = fw.build_residue(me_bi.astype(api.ME_ITEM))
+        _, _, _, s4 = rh.replay_residue(seq, planes, fw.rates, res_in.astype(rh.RES_REC), fw.res_elems, cores)
+        if it > 0:
+            times.append(s1 + s2 + s3 + s4)
+        _ = time.perf_counter() - t0
+    sec = float(np.mean(times)) / frac  # scaled to a whole picture
+    value = 1.0 / sec
+    out = {"impl": "reference", "metric": "encoded fps (1080p, preset fast): inter-search + transform hot path of one B picture",
+           "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+           "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "s16 samples, s32/s64 arithmetic", "data": "synthetic",
+           "config": {"workload": "same 1080p B-picture work lists as the b200 arm", "sample": f"first {sample_rows} of 17 CTU rows "
+                      f"({fw.n_cu} CUs = {frac:.3f} of the picture), time scaled to the whole picture"},
+           "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
+                            "sample": f"{sample_rows}/17 CTU rows, reference AVX2 functions replayed on {cores} host threads"},
+           "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return out
+
+
+# ---- helper module (kept here so bench.py is self-contained) -----------------------------------------------------
+import types  # noqa: E402
+
+_ts = types.ModuleType("tests_support")
+
+
+def _padded_planes_struct(fr, pocs):
+    """Internal-depth, edge-padded copies of frames + a ctypes PLANES array for the reference harness."""
+    from oracle import refharness as rh
+    from xeve_b200.clips import to_internal10
+    keep, arr = [], (rh.PLANES * len(pocs))()
+    for i, poc in enumerate(pocs):
+        bufs = []
+        for k, p in enumerate(fr[poc]):
+            pad = 144 if k == 0 else 72
+            bufs.append(np.ascontiguousarray(np.pad(to_internal10(p, 8), pad, mode="edge")))
+        keep.append(bufs)
+        arr[i].y = bufs[0].ctypes.data + 2 * (144 * bufs[0].shape[1] + 144)
+        arr[i].u = bufs[1].ctypes.data + 2 * (72 * bufs[1].shape[1] + 72)
+        arr[i].v = bufs[2].ctypes.data + 2 * (72 * bufs[2].shape[1] + 72)
+        arr[i].s_l, arr[i].s_c, arr[i].w_l, arr[i].h_l, arr[i].poc = bufs[0].shape[1], bufs[1].shape[1], W, H, poc
+    return keep, arr
+
+
+_ts.padded_planes_struct = _padded_planes_struct
+sys.modules["tests_support"] = _ts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    if args.impl == "reference":
+        if rank == 0:
+            a = argparse.Namespace(**vars(args))
+            a.steps = min(args.steps, 3)
+            print(json.dumps(run_reference(a)))
+        return
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    out = run_b200(args, rank, world, dist)
+    if rank == 0:
+        if world == 1:
+            a = argparse.Namespace(**vars(args))
+            a.steps, a.warmup = 1, 1
+            ref = run_reference(a)
+            out["cpu_baseline"] = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

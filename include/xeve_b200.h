@@ -18,6 +18,7 @@
  *                            hook declared src_base/xeve_type.h:448)
  *   xb200_mc                 pi->fn_mc -> xeve_mc              (src_base/xeve_mc.c:465-610,
  *                            hook declared src_base/xeve_type.h:452)
+ *   xb200_bi_org             get_org_bi after fn_mc            (src_base/xeve_pinter.c:143-156, 1620-1622)
  *   xb200_tq                 ctx->fn_tq = xeve_sub_block_tq    (src_base/xeve_tq.c:750-864,
  *                            hook declared src_base/xeve_type.h:982)
  *   xb200_itdq               ctx->fn_itdp = xeve_itdq          (src_base/xeve_itdq.c:499-580)
@@ -191,6 +192,11 @@ XB200_API int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, i
 XB200_API int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem);
 XB200_API int xb200_mc(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int64_t *pred_off, int16_t *pred,
                        int64_t pred_elems, int mem);
+/* bi-search target of analyze_bi (src_base/xeve_pinter.c:143-156, 1620-1622): luma prediction of
+ * items[i] (fn_mc) folded into org_bi = 2*org - pred, written as a contiguous w*h block at element
+ * offset off[i] of `side` -- the buffer xb200_me reads through org_bi_off. */
+XB200_API int xb200_bi_org(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int32_t *cur_pic, const int64_t *off,
+                           int16_t *side, int64_t side_elems, int mem);
 XB200_API int xb200_tq(xb200_ctx *c, xb200_tq_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates,
                        int16_t *coef, int64_t coef_elems, int mem);
 /* dequantise + inverse transform the planes whose nnz[] is non-zero, in place (fn_itdp) */

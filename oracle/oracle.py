@@ -56,6 +56,8 @@ def lib():
         L.xo_me_batch.argtypes = [VP, VP, VP, VP, C.c_int64]
         L.xo_mc_batch.restype = None
         L.xo_mc_batch.argtypes = [VP, VP, VP, C.c_int64, VP, VP]
+        L.xo_bi_org_batch.restype = None
+        L.xo_bi_org_batch.argtypes = [VP, VP, VP, C.c_int64, VP, VP, VP]
         L.xo_tq_batch.restype = None
         L.xo_tq_batch.argtypes = [VP, VP, C.c_int64, VP, VP, VP]
         L.xo_residue_batch.restype = None
@@ -78,6 +80,13 @@ def mc_batch(seq, planes, items, off, total):
     pred = np.zeros(total, np.int16)
     lib().xo_mc_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(items)), len(items), _p(off), _p(pred))
     return pred
+
+
+def bi_org_batch(seq, planes, items, cur_pic, off, total):
+    side = np.zeros(total, np.int16)
+    lib().xo_bi_org_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(items)), len(items),
+                          _p(np.ascontiguousarray(cur_pic, np.int32)), _p(np.ascontiguousarray(off, np.int64)), _p(side))
+    return side
 
 
 def tq_batch(seq, items, rates, coef_in, want_itdq=True):

@@ -728,3 +728,105 @@ RH_API double rh_replay_tq(const RH_CONST *cst, const s16 *side, const RH_TQ_REC
     j.tq_resi = resi_out; j.do_itdq = resi_out != NULL;
     return run_jobs(&j, tq_worker, nthreads);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * replay of the distortion/transform body of pinter_residue_rdo (src_base/xeve_pinter.c:961-1056)
+ * with the reference's own functions: xeve_mc -> xeve_func_diff -> xeve_func_ssd -> ctx->fn_tq ->
+ * ctx->fn_itdp -> xeve_recon_blk -> xeve_func_ssd.  Record layout = xb200_residue_item.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    RH_MC_REC mc;
+    int32_t   cur_pic;
+    uint8_t   slice_type, run_stats, qp[3], pad_[3];
+    int32_t   rate_idx;
+    double    lambda[3];
+    int64_t   out_off;
+    int32_t   nnz[3];
+    int64_t   dist_pred[3];
+    int64_t   dist_rec[3];
+} RH_RES_REC;
+
+typedef struct {
+    int              tid, nthreads, n;
+    const RH_CONST  *cst;
+    const RH_PLANES *planes;
+    const RH_RATES  *rates;
+    RH_RES_REC      *items;
+    s16             *coef, *rec;
+} resjob_t;
+
+static void *res_worker(void *arg)
+{
+    resjob_t  *j = arg;
+    XEVE_CTX  *u = util_ctx();
+    XEVE_CORE *core = calloc(1, sizeof(XEVE_CORE));
+    XEVE_REFP (*refp)[REFP_NUM] = calloc(XEVE_MAX_NUM_REF_PICS, sizeof(XEVE_REFP[REFP_NUM]));
+    pel (*pred)[N_C][MAX_CU_DIM] = malloc(sizeof(pel) * 2 * N_C * MAX_CU_DIM);
+    s16 (*coef)[MAX_CU_DIM] = malloc(sizeof(s16) * N_C * MAX_CU_DIM);
+    s16 (*resi)[MAX_CU_DIM] = malloc(sizeof(s16) * N_C * MAX_CU_DIM);
+    XEVE_PIC pic[2];
+    int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int) =
+        (u->fn_tq == hook_tq) ? T.org_tq : u->fn_tq;
+    core->ctx = u;
+    int last_rate = -1, bd = j->cst->bit_depth;
+    for(int i = j->tid; i < j->n; i += j->nthreads) {
+        RH_RES_REC *r = &j->items[i];
+        s8  refi[2] = {r->mc.refi[0], r->mc.refi[1]};
+        s16 mv[2][2] = {{r->mc.mv[0][0], r->mc.mv[0][1]}, {r->mc.mv[1][0], r->mc.mv[1][1]}};
+        for(int l = 0; l < 2; l++)
+            if(REFI_IS_VALID(refi[l])) {
+                fill_pic(&pic[l], &j->planes[r->mc.ref_pic[l]]);
+                refp[refi[l]][l].pic = &pic[l]; refp[refi[l]][l].poc = pic[l].poc;
+            }
+        const int w = r->mc.w, h = r->mc.h, x = r->mc.x, y = r->mc.y;
+        int l2 = 0; while((1 << l2) < w) l2++;
+        xeve_mc(x, y, j->cst->w, j->cst->h, w, h, refi, mv, refp, pred, bd, bd, 1);
+        const RH_PLANES *o = &j->planes[r->cur_pic];
+        s16 *org[3] = {o->y + y * o->s_l + x, o->u + (y >> 1) * o->s_c + (x >> 1), o->v + (y >> 1) * o->s_c + (x >> 1)};
+        int  so[3] = {o->s_l, o->s_c, o->s_c}, lw[3] = {l2, l2 - 1, l2 - 1};
+        for(int c = 0; c < 3; c++) {
+            xeve_diff_16b(lw[c], lw[c], org[c], pred[0][c], so[c], 1 << lw[c], 1 << lw[c], coef[c], bd);
+            r->dist_pred[c] = xeve_ssd_16b(lw[c], lw[c], pred[0][c], org[c], 1 << lw[c], so[c], bd);
+        }
+        core->qp_y = r->qp[0]; core->qp_u = r->qp[1]; core->qp_v = r->qp[2];
+        for(int c = 0; c < 3; c++) core->lambda[c] = r->lambda[c];
+        core->log2_cuw = l2; core->log2_cuh = l2;
+        if(r->rate_idx != last_rate) { put_rates(core, &j->rates[r->rate_idx]); last_rate = r->rate_idx; }
+        int nnz[3];
+        org_tq(u, core, coef, l2, l2, r->slice_type, nnz, 0, r->run_stats);
+        size_t ny = (size_t)w * h, nc = ny >> 2, off[3] = {0, ny, ny + nc};
+        for(int c = 0; c < 3; c++) {
+            memcpy(j->coef + r->out_off + off[c], coef[c], (c ? nc : ny) * 2);
+            memcpy(resi[c], coef[c], (c ? nc : ny) * 2);
+        }
+        u->fn_itdp(u, core, resi, core->nnz_sub);
+        for(int c = 0; c < 3; c++) {
+            s16 *rc = j->rec + r->out_off + off[c];
+            xeve_recon_blk(resi[c], pred[0][c], nnz[c], 1 << lw[c], 1 << lw[c], 1 << lw[c], rc, bd);
+            r->nnz[c] = nnz[c];
+            r->dist_rec[c] = nnz[c] ? xeve_ssd_16b(lw[c], lw[c], rc, org[c], 1 << lw[c], so[c], bd) : r->dist_pred[c];
+        }
+    }
+    free(resi); free(coef); free(pred); free(refp); free(core);
+    return NULL;
+}
+
+RH_API double rh_replay_residue(const RH_CONST *cst, const RH_PLANES *planes, const RH_RATES *rates, RH_RES_REC *items, int n,
+                                s16 *coef, s16 *rec, int nthreads)
+{
+    if(nthreads < 1) nthreads = 1;
+    util_ctx();
+    /* the global kernel tables are normally selected when a picture is first encoded */
+    pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
+    resjob_t  *jb = malloc(sizeof(resjob_t) * nthreads);
+    double     t0 = now_s();
+    for(int t = 0; t < nthreads; t++) {
+        jb[t] = (resjob_t){t, nthreads, n, cst, planes, rates, items, coef, rec};
+        pthread_create(&th[t], NULL, res_worker, &jb[t]);
+    }
+    for(int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    double dt = now_s() - t0;
+    free(th); free(jb);
+    return dt;
+}
+RH_API int rh_sizeof_res(void) { return sizeof(RH_RES_REC); }

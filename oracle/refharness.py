@@ -237,6 +237,49 @@ def replay_tq(tr: Trace, recs=None, nthreads=1, want_itdq=True):
     return coef, nnz, resi, sec
 
 
+RES_REC = np.dtype([
+    ("mc", MC_REC), ("cur_pic", "<i4"),
+    ("slice_type", "u1"), ("run_stats", "u1"), ("qp", "u1", (3,)), ("pad_", "u1", (3,)),
+    ("rate_idx", "<i4"), ("lambda", "<f8", (3,)), ("out_off", "<i8"),
+    ("nnz", "<i4", (3,)), ("dist_pred", "<i8", (3,)), ("dist_rec", "<i8", (3,)),
+], align=True)
+
+
+def replay_residue(const, planes_struct, rates, items, elems, nthreads=1):
+    """Reference xeve_mc -> diff -> SSD -> fn_tq -> fn_itdp -> recon -> SSD over residue items.
+
+    planes_struct: ctypes PLANES array (picture-table order); returns (items, coef, rec, seconds).
+    """
+    L = lib()
+    L.rh_replay_residue.restype = C.c_double
+    L.rh_replay_residue.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    assert L.rh_sizeof_res() == RES_REC.itemsize
+    items = np.ascontiguousarray(items).copy()
+    coef = np.zeros(elems, np.int16)
+    rec = np.zeros(elems, np.int16)
+    sec = L.rh_replay_residue(_p(const), C.addressof(planes_struct), _p(np.ascontiguousarray(rates)), _p(items), len(items),
+                              _p(coef), _p(rec), nthreads)
+    return items, coef, rec, sec
+
+
+def replay_me_raw(const, planes_struct, side, recs, nthreads=1):
+    """rh_replay_me on caller-provided pictures (ctypes PLANES array) instead of a Trace."""
+    L = lib()
+    recs = np.ascontiguousarray(recs)
+    out = np.empty_like(recs)
+    sec = L.rh_replay_me(_p(const), C.addressof(planes_struct), _p(side), _p(recs), _p(out), len(recs), nthreads)
+    return out, sec
+
+
+def replay_mc_raw(const, planes_struct, recs, nthreads=1):
+    L = lib()
+    recs = np.ascontiguousarray(recs)
+    off, total = mc_offsets(recs)
+    pred = np.empty(total, np.int16)
+    sec = L.rh_replay_mc(_p(const), C.addressof(planes_struct), _p(recs), len(recs), _p(pred), _p(off), None, nthreads)
+    return pred, off, sec
+
+
 def table(which: int, dtype) -> np.ndarray:
     L = lib()
     n = C.c_int(0)

@@ -666,6 +666,24 @@ void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad)
     }
 }
 
+/* get_org_bi, src_base/xeve_pinter.c:143-156, applied to the luma prediction of one fn_mc call */
+void xo_bi_org(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int cur_pic, int16_t *org_bi)
+{
+    const int w = it->w, h = it->h;
+    int16_t  *pred = malloc(sizeof(int16_t) * w * h * 3 / 2);
+    xo_mc(sq, pl, it, pred);
+    const xo_planes *o = &pl[cur_pic];
+    for(int y = 0; y < h; y++)
+        for(int x = 0; x < w; x++)
+            org_bi[y * w + x] = (int16_t)(((int16_t)o->y[(it->y + y) * o->s_l + it->x + x] << 1) - pred[y * w + x]);
+    free(pred);
+}
+void xo_bi_org_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n, const int32_t *cur_pic,
+                     const int64_t *off, int16_t *side)
+{
+    for(int64_t i = 0; i < n; i++) xo_bi_org(sq, pl, &items[i], cur_pic[i], side + off[i]);
+}
+
 /* batch drivers --------------------------------------------------------------------------------- */
 void xo_me_batch(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *items, int64_t n)
 {

@@ -107,6 +107,7 @@ def load():
             f.argtypes = [VP, VP, C.c_int64, VP, C.c_int]
         L.xb200_me.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_mc.argtypes = [VP, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
+        L.xb200_bi_org.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
         L.xb200_tq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_itdq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_recon.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
@@ -117,7 +118,7 @@ def load():
 
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
-           "xb200_me", "xb200_mc", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
+           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
 
 
 def _p(a):
@@ -235,6 +236,14 @@ class Hotpath:
         pred = np.zeros(total, np.int16)
         self._ck(self.L.xb200_mc(self.h, _p(items), len(items), _p(pred_off), _p(pred), total, MEM_HOST), "xb200_mc")
         return pred
+
+    def bi_org(self, items, cur_pic, off, total):
+        items = np.ascontiguousarray(items, MC_ITEM)
+        cur_pic = np.ascontiguousarray(cur_pic, np.int32)
+        off = np.ascontiguousarray(off, np.int64)
+        side = np.zeros(total, np.int16)
+        self._ck(self.L.xb200_bi_org(self.h, _p(items), len(items), _p(cur_pic), _p(off), _p(side), total, MEM_HOST), "xb200_bi_org")
+        return side
 
     def tq(self, items, rates, coef):
         items = np.ascontiguousarray(items, TQ_ITEM).copy()

@@ -217,6 +217,7 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     CK(cudaMemset(c->d_err, 0, sizeof(int)));
     CK(cudaMalloc(&c->d_bins, sizeof(int) * 16));
     CK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_bi_org, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResSmem)));
     CK(cudaFuncSetAttribute(k_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
     CK(cudaFuncSetAttribute(k_itdq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
@@ -495,6 +496,46 @@ int xb200_mc(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int64_t 
     c->launches++;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, pred, d_pred, (size_t)pred_elems, mem))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_bi_org(xb200_ctx *c, const xb200_mc_item *items, int64_t n, const int32_t *cur_pic, const int64_t *off, int16_t *side,
+                 int64_t side_elems, int mem)
+{
+    if(!c || n < 0 || (n && (!items || !cur_pic || !off || !side)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(mem == XB200_MEM_HOST)
+        for(int64_t i = 0; i < n; i++) {
+            int r = check_mc(c, items[i]);
+            if(r) return r;
+            if(!pic_ok(c, cur_pic[i]) || off[i] < 0 || (off[i] & 3) || off[i] + items[i].w * items[i].h > side_elems)
+                return XB200_ERR_INVALID_ARGUMENT;
+        }
+    if(n == 0) return XB200_OK;
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_mc_item *d_items;
+    int32_t       *d_cur;
+    int64_t       *d_off;
+    int16_t       *d_side = side;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, mem, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, off, (size_t)n, mem, &d_off))) return r;
+    if((r = to_dev(c, c->b_aux2, cur_pic, (size_t)n, mem, &d_cur))) return r;
+    if(mem == XB200_MEM_HOST) {
+        if((r = ensure(c->b_aux1, (size_t)side_elems * 2 + 64))) return r;
+        d_side = static_cast<int16_t *>(c->b_aux1.p);
+        CK(cudaMemsetAsync(d_side, 0, (size_t)side_elems * 2, c->stream));
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_bi_org<<<(unsigned)n, MC_THREADS, MC_SMEM_BYTES, c->stream>>>(c->d_pics, d_items, (int)n, d_cur, d_off, d_side, c->sq);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, side, d_side, (size_t)side_elems, mem))) return r;
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);

@@ -58,7 +58,7 @@ XB_DEV void mc_plane(const int16_t *__restrict__ ref, int sr, int gx, int gy, bo
 // Full xeve_mc for one item into `pred` (Y | U | V, stride = block width).  `aux` = second
 // prediction buffer of the same size (bi), `tmp` = interpolation scratch (71*64 samples).
 XB_DEV void mc_item(const PicDev *__restrict__ pics, const xb200_mc_item &it, const SeqDev &sq, int16_t *pred, int16_t *aux,
-                    int16_t *tmp, int tid, int nthr)
+                    int16_t *tmp, int tid, int nthr, bool luma_only = false)
 {
     const int w = it.w, h = it.h, x = it.x, y = it.y, ny = w * h, nc = ny >> 2;
     int       mvt[2][2];
@@ -85,12 +85,14 @@ XB_DEV void mc_item(const PicDev *__restrict__ pics, const xb200_mc_item &it, co
         const bool   hl = (it.mv[l][0] & 3) != 0, vl = (it.mv[l][1] & 3) != 0;
         const bool   hc = (it.mv[l][0] & 7) != 0, vc = (it.mv[l][1] & 7) != 0;
         mc_plane<8, 4>(rp.p[0], rp.s[0], gx, gy, hl, vl, dst, w, h, sq.bd, tmp, tid, nthr);
-        mc_plane<4, 8>(rp.p[1], rp.s[1], gx, gy, hc, vc, dst + ny, w >> 1, h >> 1, sq.bd, tmp, tid, nthr);
-        mc_plane<4, 8>(rp.p[2], rp.s[2], gx, gy, hc, vc, dst + ny + nc, w >> 1, h >> 1, sq.bd, tmp, tid, nthr);
+        if(!luma_only) {
+            mc_plane<4, 8>(rp.p[1], rp.s[1], gx, gy, hc, vc, dst + ny, w >> 1, h >> 1, sq.bd, tmp, tid, nthr);
+            mc_plane<4, 8>(rp.p[2], rp.s[2], gx, gy, hc, vc, dst + ny + nc, w >> 1, h >> 1, sq.bd, tmp, tid, nthr);
+        }
         n++;
     }
     if(n == 2) {
-        for(int e = tid; e < ny + 2 * nc; e += nthr) pred[e] = (int16_t)((pred[e] + aux[e] + 1) >> 1);
+        for(int e = tid; e < (luma_only ? ny : ny + 2 * nc); e += nthr) pred[e] = (int16_t)((pred[e] + aux[e] + 1) >> 1);
         __syncthreads();
     }
 }
@@ -109,5 +111,24 @@ __global__ void __launch_bounds__(MC_THREADS) k_mc(const PicDev *__restrict__ pi
     const int total = it.w * it.h * 3 / 2;
     int16_t  *o     = out + pred_off[i];
     for(int e = threadIdx.x; e < total; e += MC_THREADS) o[e] = pred[e];
+}
+// get_org_bi after fn_mc: org_bi = 2*org - pred (luma), contiguous w*h block per item
+__global__ void __launch_bounds__(MC_THREADS) k_bi_org(const PicDev *__restrict__ pics, const xb200_mc_item *__restrict__ items,
+                                                        int n, const int32_t *__restrict__ cur_pic, const int64_t *__restrict__ off,
+                                                        int16_t *__restrict__ side, SeqDev sq)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int16_t *pred = reinterpret_cast<int16_t *>(smem_raw);
+    int16_t *aux  = pred + 6144;
+    int16_t *tmp  = aux + 6144;
+    const int i = blockIdx.x;
+    if(i >= n) return;
+    const xb200_mc_item it = items[i];
+    mc_item(pics, it, sq, pred, aux, tmp, threadIdx.x, MC_THREADS, true);
+    const PicDev   o   = pics[cur_pic[i]];
+    const int16_t *org = o.p[0] + (ptrdiff_t)it.y * o.s[0] + it.x;
+    int16_t       *dst = side + off[i];
+    for(int e = threadIdx.x; e < it.w * it.h; e += MC_THREADS)
+        dst[e] = (int16_t)(((int16_t)org[(ptrdiff_t)(e / it.w) * o.s[0] + e % it.w] << 1) - pred[e]);
 }
 #define MC_SMEM_BYTES ((6144 * 2 + 71 * 64) * 2)
