@@ -12,6 +12,7 @@
 #include "xb200_mc.cuh"
 #include "xb200_tq.cuh"
 #include "xb200_misc.cuh"
+#include "xb200_residue2.cuh"
 
 namespace {
 
@@ -128,19 +129,33 @@ int finish(xb200_ctx *c)
 
 __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) return;
-    const xb200_me_item &it = items[i];
-    const int            l2 = it.log2_cuw;
-    int                  key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : 4; // bin 4 = unsupported shape
-    const int            slot = atomicAdd(&bins[key], 1);
-    if(key < 4) {
-        order[(size_t)key * n + slot] = i;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int       key = 5, margin = 0; // key 4 = unsupported shape, 5 = out of range
+    if(i < n) {
+        const xb200_me_item &it = items[i];
+        const int            l2 = it.log2_cuw;
+        key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : 4;
         int d = it.poc - it.ref_poc;
         d     = d < 0 ? -d : d;
         int dyn = (it.max_search_range * d + (it.gop_size >> 1)) / max(1, it.gop_size);
         dyn     = max(it.max_search_range >> 2, min(it.max_search_range, dyn));
-        atomicMax(&bins[8 + key], it.bi ? 5 : dyn + 2);
+        margin  = it.bi ? 5 : dyn + 2;
+    }
+#pragma unroll
+    for(int k = 0; k < 5; k++) { // warp-aggregated: one atomic per warp and bin
+        const unsigned m = __ballot_sync(0xffffffffu, key == k);
+        if(m == 0) continue;
+        const int leader = __ffs(m) - 1;
+        int       mx = key == k ? margin : 0;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int base = 0;
+        if(lane == leader) {
+            base = atomicAdd(&bins[k], __popc(m));
+            if(k < 4) atomicMax(&bins[8 + k], mx);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if(key == k && k < 4) order[(size_t)k * n + base + __popc(m & ((1u << lane) - 1))] = i;
     }
 }
 
@@ -154,6 +169,26 @@ int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cn
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
     CK(cudaFuncSetAttribute(k_me<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_me<L2><<<cnt, ME_THREADS, smem, c->stream>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+template <int L2>
+int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates,
+                    int16_t *d_coef, int16_t *d_rec)
+{
+    if(cnt == 0) return XB200_OK;
+    using Cf = Res2Cfg<L2>;
+    static int blocks_per_sm = 0, sms = 0;
+    if(!blocks_per_sm) {
+        CK(cudaFuncSetAttribute(k_residue2<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_residue2<L2>, Cf::CTA, Cf::SMEM));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if(blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
+    k_residue2<L2><<<grid, Cf::CTA, Cf::SMEM, c->stream>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
@@ -677,10 +712,20 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
         d_coef = static_cast<int16_t *>(c->b_aux1.p);
         d_rec  = static_cast<int16_t *>(c->b_aux2.p);
     }
+    if((r = ensure(c->b_order, sizeof(int32_t) * 4 * (size_t)n))) return r;
+    int32_t *order = static_cast<int32_t *>(c->b_order.p);
     CK(cudaEventRecord(c->ev0, c->stream));
-    k_residue<<<(unsigned)n, TQ_THREADS, sizeof(ResSmem), c->stream>>>(c->d_pics, d_items, (int)n, d_rates, d_coef, d_rec, c->d_tm64,
-                                                                          c->sq);
+    CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int) * 16, c->stream));
+    k_res_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins);
     c->launches++;
+    int bins[16];
+    CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if(bins[4]) return XB200_ERR_UNSUPPORTED;
+    if((r = launch_residue2<6>(c, d_items, order + 3 * n, bins[3], d_rates, d_coef, d_rec))) return r;
+    if((r = launch_residue2<5>(c, d_items, order + 2 * n, bins[2], d_rates, d_coef, d_rec))) return r;
+    if((r = launch_residue2<4>(c, d_items, order + 1 * n, bins[1], d_rates, d_coef, d_rec))) return r;
+    if((r = launch_residue2<3>(c, d_items, order + 0 * n, bins[0], d_rates, d_coef, d_rec))) return r;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
     if((r = to_host(c, coef, d_coef, (size_t)elems, mem))) return r;
