@@ -168,7 +168,7 @@ int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cn
     const size_t smem = me_smem_bytes(L2, cap);
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
     CK(cudaFuncSetAttribute(k_me<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_me<L2><<<cnt, ME_THREADS, smem, c->stream>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
+    k_me<L2><<<(cnt + MeGeom<L2>::TEAMS - 1) / MeGeom<L2>::TEAMS, ME_THREADS, smem, c->stream>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;

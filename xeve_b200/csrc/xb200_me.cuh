@@ -15,6 +15,15 @@
 
 #define ME_THREADS 128
 
+// shared memory of one team: mbarrier, round keys, reduction slots, original block, interpolation
+// scratch, staged window (multiple of 16 bytes)
+__host__ __device__ inline size_t me_team_bytes(int l2, int win_cap_elems)
+{
+    const int W = 1 << l2;
+    return (16 + 2 * 128 * 8 + 32 + (size_t)(W * W + (W + 8) * W + win_cap_elems + 16) * 2 + 15) & ~(size_t)15;
+}
+static inline size_t me_smem_bytes(int l2, int win_cap_elems) { return me_team_bytes(l2, win_cap_elems) * (l2 <= 4 ? 4 : 1); }
+
 struct MeState { // uniform per CTA (kept in registers by every thread)
     int lo[2], hi[2];
 };
@@ -26,8 +35,16 @@ template <int L2> struct MeGeom {
     static constexpr int LPR  = QPR < G ? QPR : G;                      // lanes along a row
     static constexpr int RG   = G / LPR;                                // row groups inside the lane group
     static constexpr int QPL  = QPR / LPR;                              // quads per lane per row
-    static constexpr int NG   = ME_THREADS / G;                         // candidates in flight per CTA
+    static constexpr int T    = L2 <= 4 ? 32 : ME_THREADS;              // threads per item (team)
+    static constexpr int CTA   = ME_THREADS;
+    static constexpr int TEAMS = CTA / T;
+    static constexpr int NG   = T / G;                                  // candidates in flight per team
 };
+template <int T> XB_DEV void me_team_sync()
+{
+    if(T == 32) __syncwarp();
+    else __syncthreads();
+}
 
 // window bookkeeping: staged region [x0, x0+pitch) x [y0, y0+rows) in reference-plane coordinates
 struct MeWin {
@@ -71,7 +88,10 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
 {
     using Gm = MeGeom<L2>;
     constexpr int W = Gm::W;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = Gm::T;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int team = threadIdx.x / T;
+    unsigned char *smem_raw = smem_all + (size_t)team * me_team_bytes(L2, win_cap_elems);
     uint64_t *bar   = reinterpret_cast<uint64_t *>(smem_raw);                 // 8 B (padded to 16)
     uint64_t *keys  = reinterpret_cast<uint64_t *>(smem_raw + 16);            // 2 x 128 keys
     int32_t  *red   = reinterpret_cast<int32_t *>(smem_raw + 16 + 2 * 128 * 8); // 8 ints
@@ -79,10 +99,11 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     int16_t  *tmp   = org + W * W;                  // (W + 7) * W, horizontal pass of 2-D interpolation
     int16_t  *win   = tmp + (W + 8) * W;            // staged reference window (+ slack)
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x % T, lane = tid & 31; // tid = thread index inside the team
     const int grp = tid / Gm::G, j = tid % Gm::G;
-    if(blockIdx.x >= n) return;
-    const int it_idx = order[blockIdx.x];
+    const int item_no = blockIdx.x * Gm::TEAMS + team;
+    if(item_no >= n) return; // whole team leaves (teams never meet at a block barrier when TEAMS > 1)
+    const int it_idx = order[item_no];
     xb200_me_item *it = &items[it_idx];
 
     if(tid == 0) mbar_init(bar, 1);
@@ -101,14 +122,14 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     {
         const int16_t *src = bi ? side + it->org_bi_off : cur.p[0] + (size_t)y * cur.s[0] + x;
         const int      so  = bi ? W : cur.s[0];
-        for(int e = tid; e < W * W / 4; e += ME_THREADS) {
+        for(int e = tid; e < W * W / 4; e += T) {
             const int r = e / (W / 4), c = (e % (W / 4)) * 4;
             uint2 v = *reinterpret_cast<const uint2 *>(src + (size_t)r * so + c);
             v.x ^= bias; v.y ^= bias;
             *reinterpret_cast<uint2 *>(org + r * W + c) = v;
         }
     }
-    __syncthreads();
+    me_team_sync<T>();
 
     // ---- search parameters (uniform) -----------------------------------------------------------
     const uint32_t lambda_mv = it->lambda_mv;
@@ -154,7 +175,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
             if(tid == 0) atomicExch(err_flag, 1);
             rows = (win_cap_elems - 8) / pitch;
         }
-        __syncthreads(); // every reader of the previous window is done
+        me_team_sync<T>(); // every reader of the previous window is done
         if(tid < 32) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if(tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(pitch * rows * 2));
@@ -174,6 +195,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     auto eval_round = [&](int ncand, int safe_x, int safe_y, auto pos) -> uint64_t {
         uint64_t *kb = keys + key_buf * 128;
         key_buf ^= 1;
+        uint64_t kmine = ~0ull;
         for(int c = grp; c < ((ncand + Gm::NG - 1) / Gm::NG) * Gm::NG; c += Gm::NG) {
             int  px = 0, py = 0;
             bool live = c < ncand;
@@ -189,12 +211,15 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                     sad >>= (bd - 8);
                     cost += bi ? (sad >> 1) : sad;
                 }
-                kb[c] = ((uint64_t)cost << 32) | (uint32_t)c;
+                if(T == 32) kmine = min(kmine, ((uint64_t)cost << 32) | (uint32_t)c);
+                else kb[c] = ((uint64_t)cost << 32) | (uint32_t)c;
             }
         }
-        __syncthreads();
-        uint64_t k = ~0ull;
-        for(int c = lane; c < ncand; c += 32) k = min(k, kb[c]);
+        uint64_t k = kmine;
+        if(T > 32) {
+            __syncthreads();
+            for(int c = lane; c < ncand; c += 32) k = min(k, kb[c]);
+        }
 #pragma unroll
         for(int m = 16; m > 0; m >>= 1) k = min(k, shfl_xor_u64(k, m));
         return k;
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                 uint32_t  part = 0;
                 if(dx && dy) {
                     const int s1 = min(4, bd - 8);
-                    for(int e = tid; e < (W + 7) * W; e += ME_THREADS) {
+                    for(int e = tid; e < (W + 7) * W; e += T) {
                         const int r = e / W, cc = e % W;
                         const int16_t *p = win + (iy + r - 3) * wn.pitch + ix + cc - 3;
                         int acc = 0;
@@ -342,9 +367,9 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                         for(int t = 0; t < 8; t++) acc += c_mc_l[dx][t] * p[t];
                         tmp[e] = (int16_t)(acc >> s1);
                     }
-                    __syncthreads();
+                    me_team_sync<T>();
                     const int s2 = max(8, 20 - bd);
-                    for(int e = tid; e < W * W; e += ME_THREADS) {
+                    for(int e = tid; e < W * W; e += T) {
                         int acc = 0;
 #pragma unroll
                         for(int t = 0; t < 8; t++) acc += c_mc_l[dy][t] * tmp[e + t * W];
@@ -354,7 +379,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                 }
                 else {
                     const int stp = dx ? 1 : wn.pitch, ph = dx ? dx : dy;
-                    for(int e = tid; e < W * W; e += ME_THREADS) {
+                    for(int e = tid; e < W * W; e += T) {
                         const int r = e / W, cc = e % W;
                         int       v;
                         if(!dx && !dy) v = win[(iy + r) * wn.pitch + ix + cc];
@@ -370,12 +395,16 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                 }
 #pragma unroll
                 for(int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-                __syncthreads(); // red[] free, tmp[] reads done
-                if(lane == 0) red[tid >> 5] = (int32_t)part;
-                __syncthreads();
-                uint32_t sad = 0;
+                uint32_t sad = part;
+                if(T > 32) {
+                    __syncthreads(); // red[] free, tmp[] reads done
+                    if(lane == 0) red[tid >> 5] = (int32_t)part;
+                    __syncthreads();
+                    sad = 0;
 #pragma unroll
-                for(int wi = 0; wi < ME_THREADS / 32; wi++) sad += (uint32_t)red[wi];
+                    for(int wi = 0; wi < T / 32; wi++) sad += (uint32_t)red[wi];
+                }
+                else __syncwarp();
                 sad >>= (bd - 8);
                 int      cb;
                 uint32_t cost = mv_cost(qx, qy, cb) + (bi ? (sad >> 1) : sad);
@@ -420,8 +449,4 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
     }
 }
 
-static inline size_t me_smem_bytes(int l2, int win_cap_elems)
-{
-    const int W = 1 << l2;
-    return 16 + 2 * 128 * 8 + 32 + (size_t)(W * W + (W + 8) * W + win_cap_elems + 16) * 2;
-}
+
