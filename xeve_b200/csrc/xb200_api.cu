@@ -43,6 +43,8 @@ struct xb200_ctx {
     int             *d_bins = nullptr; // 8 counters + 8 max-range
     DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
     cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t     side[4] = {nullptr, nullptr, nullptr, nullptr}; // one per CU size: the four size-binned grids overlap
+    cudaEvent_t      ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     double           last_ms = 0.0;
     int64_t          launches = 0;
 };
@@ -159,6 +161,22 @@ __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t
     }
 }
 
+// the four size-binned grids of one operator call run concurrently on side streams
+int fork_streams(xb200_ctx *c)
+{
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for(int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    return XB200_OK;
+}
+int join_streams(xb200_ctx *c)
+{
+    for(int i = 0; i < 4; i++) {
+        CK(cudaEventRecord(c->ev_join[i], c->side[i]));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+    }
+    return XB200_OK;
+}
+
 template <int L2>
 int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cnt, const int16_t *d_side, int margin)
 {
@@ -168,7 +186,7 @@ int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cn
     const size_t smem = me_smem_bytes(L2, cap);
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
     CK(cudaFuncSetAttribute(k_me<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_me<L2><<<(cnt + MeGeom<L2>::TEAMS - 1) / MeGeom<L2>::TEAMS, ME_THREADS, smem, c->stream>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
+    k_me<L2><<<(cnt + MeGeom<L2>::TEAMS - 1) / MeGeom<L2>::TEAMS, MeGeom<L2>::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_side, c->sq, cap, c->d_err);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
@@ -188,7 +206,7 @@ int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *or
         if(blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
-    k_residue2<L2><<<grid, Cf::CTA, Cf::SMEM, c->stream>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
+    k_residue2<L2><<<grid, Cf::CTA, Cf::SMEM, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
@@ -229,6 +247,11 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for(int i = 0; i < 4; i++) {
+        CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
     // constant tables
     {
         static int8_t tm[64 * 64];
@@ -276,6 +299,8 @@ void xb200_destroy(xb200_ctx *c)
     if(c->d_bins) cudaFree(c->d_bins);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev_fork);
+    for(int i = 0; i < 4; i++) { cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -476,10 +501,12 @@ int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side,
     CK(cudaStreamSynchronize(c->stream));
     if(bins[4]) return XB200_ERR_UNSUPPORTED;
     // largest blocks first: they are the long poles of the launch sequence
+    if((r = fork_streams(c))) return r;
     if((r = launch_me<6>(c, d_items, order + 3 * n, bins[3], d_side, bins[8 + 3]))) return r;
     if((r = launch_me<5>(c, d_items, order + 2 * n, bins[2], d_side, bins[8 + 2]))) return r;
     if((r = launch_me<4>(c, d_items, order + 1 * n, bins[1], d_side, bins[8 + 1]))) return r;
     if((r = launch_me<3>(c, d_items, order + 0 * n, bins[0], d_side, bins[8 + 0]))) return r;
+    if((r = join_streams(c))) return r;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
     int err = 0;
@@ -722,10 +749,12 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
     CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if(bins[4]) return XB200_ERR_UNSUPPORTED;
+    if((r = fork_streams(c))) return r;
     if((r = launch_residue2<6>(c, d_items, order + 3 * n, bins[3], d_rates, d_coef, d_rec))) return r;
     if((r = launch_residue2<5>(c, d_items, order + 2 * n, bins[2], d_rates, d_coef, d_rec))) return r;
     if((r = launch_residue2<4>(c, d_items, order + 1 * n, bins[1], d_rates, d_coef, d_rec))) return r;
     if((r = launch_residue2<3>(c, d_items, order + 0 * n, bins[0], d_rates, d_coef, d_rec))) return r;
+    if((r = join_streams(c))) return r;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
     if((r = to_host(c, coef, d_coef, (size_t)elems, mem))) return r;

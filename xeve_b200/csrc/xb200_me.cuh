@@ -35,8 +35,8 @@ template <int L2> struct MeGeom {
     static constexpr int LPR  = QPR < G ? QPR : G;                      // lanes along a row
     static constexpr int RG   = G / LPR;                                // row groups inside the lane group
     static constexpr int QPL  = QPR / LPR;                              // quads per lane per row
-    static constexpr int T    = L2 <= 4 ? 32 : ME_THREADS;              // threads per item (team)
-    static constexpr int CTA   = ME_THREADS;
+    static constexpr int T    = L2 <= 4 ? 32 : (L2 == 5 ? 128 : 256);   // threads per item (team)
+    static constexpr int CTA   = L2 <= 4 ? ME_THREADS : T;
     static constexpr int TEAMS = CTA / T;
     static constexpr int NG   = T / G;                                  // candidates in flight per team
 };
@@ -48,41 +48,53 @@ template <int T> XB_DEV void me_team_sync()
 
 // window bookkeeping: staged region [x0, x0+pitch) x [y0, y0+rows) in reference-plane coordinates
 struct MeWin {
-    int x0, y0, pitch, rows, staged;
+    int x0, y0, pitch, rows, staged, biased;
 };
 
-template <int L2>
-XB_DEV uint32_t me_group_sad(const int16_t *__restrict__ win, const MeWin &wn, const int16_t *__restrict__ org, int px, int py,
-                             int j /* lane in group */, uint32_t bias)
+template <int L2, bool ODD>
+XB_DEV uint32_t me_group_sad_impl(const int16_t *__restrict__ win, int pitch, const int16_t *__restrict__ org, int ox, int oy, int j)
 {
     using Gm = MeGeom<L2>;
-    const int      col_lane = j % Gm::LPR, row_lane = j / Gm::LPR;
-    const int      ox = px - wn.x0, oy = py - wn.y0;
-    const uint32_t sh = (ox & 1) ? 16u : 0u;
-    uint32_t       acc = 0, total = 0;
-    int            cnt = 0;
-#pragma unroll 4
-    for(int r = row_lane; r < Gm::W; r += Gm::RG) {
-        const int16_t *rowp = win + (oy + r) * wn.pitch + (ox & ~1);
+    constexpr int ROWS = Gm::W / Gm::RG;          // rows handled by one lane
+    constexpr int QUADS = ROWS * Gm::QPL;         // 4-sample quads per lane: 4 / 4 / 8 / 32
+    constexpr int FLUSH = QUADS < 8 ? QUADS : 8;  // packed halves hold <= 16 differences of <= 3069
+    const int     col_lane = j % Gm::LPR, row_lane = j / Gm::LPR;
+    const int16_t *base = win + (oy + row_lane) * pitch + (ox & ~1) + col_lane * 4;
+    const int16_t *ob   = org + row_lane * Gm::W + col_lane * 4;
+    uint32_t       total = 0;
+#pragma unroll 1
+    for(int q0 = 0; q0 < QUADS; q0 += FLUSH) {
+        uint32_t acc = 0;
 #pragma unroll
-        for(int q = 0; q < Gm::QPL; q++) {
-            const int       qc = (col_lane + q * Gm::LPR) * 4;
-            const uint32_t *rp = reinterpret_cast<const uint32_t *>(rowp + qc);
-            const uint32_t  w0 = rp[0], w1 = rp[1], w2 = rp[2];
-            const uint2     o  = *reinterpret_cast<const uint2 *>(org + r * Gm::W + qc);
-            acc += absdiff_u16x2(o.x, __funnelshift_r(w0, w1, sh) ^ bias);
-            acc += absdiff_u16x2(o.y, __funnelshift_r(w1, w2, sh) ^ bias);
-            if(++cnt == 8) { total += sum_halves(acc); acc = 0; cnt = 0; } // halves hold <= 16 * 4093
+        for(int qq = 0; qq < FLUSH; qq++) {
+            const int       q = q0 + qq, rr = (q / Gm::QPL) * Gm::RG, qc = (q % Gm::QPL) * Gm::LPR * 4;
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(base + rr * pitch + qc);
+            const uint2     o  = *reinterpret_cast<const uint2 *>(ob + rr * Gm::W + qc);
+            if(ODD) {
+                const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+                acc += absdiff_u16x2(o.x, __funnelshift_r(w0, w1, 16));
+                acc += absdiff_u16x2(o.y, __funnelshift_r(w1, w2, 16));
+            }
+            else {
+                acc += absdiff_u16x2(o.x, rp[0]);
+                acc += absdiff_u16x2(o.y, rp[1]);
+            }
         }
+        total += sum_halves(acc);
     }
-    total += sum_halves(acc);
 #pragma unroll
     for(int m = Gm::G >> 1; m > 0; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
     return total;
 }
+template <int L2>
+XB_DEV uint32_t me_group_sad(const int16_t *__restrict__ win, const MeWin &wn, const int16_t *__restrict__ org, int px, int py, int j)
+{
+    const int ox = px - wn.x0, oy = py - wn.y0;
+    return (ox & 1) ? me_group_sad_impl<L2, true>(win, wn.pitch, org, ox, oy, j) : me_group_sad_impl<L2, false>(win, wn.pitch, org, ox, oy, j);
+}
 
 template <int L2>
-__global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pics, xb200_me_item *__restrict__ items,
+__global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict__ pics, xb200_me_item *__restrict__ items,
                                                     const int32_t *__restrict__ order, int n, const int16_t *__restrict__ side,
                                                     SeqDev sq, int win_cap_elems, int *__restrict__ err_flag)
 {
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
 
     MeState st;
     MeWin   wn;
-    wn.staged = 0; wn.x0 = wn.y0 = wn.pitch = wn.rows = 0;
+    wn.staged = 0; wn.x0 = wn.y0 = wn.pitch = wn.rows = 0; wn.biased = 0;
     int key_buf = 0;
 
     auto set_window = [&](int cx, int cy, int bi_mode) {
@@ -185,7 +197,16 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
         }
         mbar_wait(bar, phase);
         phase ^= 1;
-        wn.x0 = ax0; wn.y0 = ny0; wn.pitch = pitch; wn.rows = rows; wn.staged = 1;
+        wn.x0 = ax0; wn.y0 = ny0; wn.pitch = pitch; wn.rows = rows; wn.staged = 1; wn.biased = 0;
+    };
+    // bi search: the signed 2*org - pred block is compared through unsigned packed min/max, so both
+    // operands carry a ^0x8000 bias during the integer rounds; the window is un-biased for sub-pel
+    auto set_bias = [&](int want) {
+        if(!bi || wn.biased == want) return;
+        uint32_t *w32 = reinterpret_cast<uint32_t *>(win);
+        for(int e = tid; e < (wn.pitch * wn.rows) >> 1; e += T) w32[e] ^= 0x80008000u;
+        wn.biased = want;
+        me_team_sync<T>();
     };
 
     // Evaluate `ncand` integer candidates (positions produced by `pos(c, px, py)`), then reduce.
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
             if(live) pos(c, px, py);
             px = (int16_t)px; py = (int16_t)py;
             const bool inr = live && px >= st.lo[0] && px <= st.hi[0] && py >= st.lo[1] && py <= st.hi[1];
-            uint32_t   sad = me_group_sad<L2>(win, wn, org, inr ? px : safe_x, inr ? py : safe_y, j, bias);
+            uint32_t   sad = me_group_sad<L2>(win, wn, org, inr ? px : safe_x, inr ? py : safe_y, j);
             if(live && j == 0) {
                 uint32_t cost = 0xffffffffu;
                 if(inr) {
@@ -243,7 +264,8 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
                 const int wx1 = bx >= st.hi[0] ? bx : bx + r, wy1 = by >= st.hi[1] ? by : by + r;
                 wnx = wx1 - wx0 + 1;
                 const int ncand = wnx * (wy1 - wy0 + 1);
-                k = eval_round(ncand, c0x, c0y, [&](int c, int &px, int &py) { px = wx0 + c % wnx; py = wy0 + c / wnx; });
+                const int rcp = (65536 + wnx - 1) / wnx; // exact c / wnx for c < 128, wnx <= 11
+                k = eval_round(ncand, c0x, c0y, [&](int c, int &px, int &py) { const int qy = (c * rcp) >> 16; px = wx0 + c - qy * wnx; py = wy0 + qy; });
                 this_step = 2;
             }
             else if(step <= 8) {
@@ -313,6 +335,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
         const int sx = ((int16_t)(start_x + (x << 2))) >> 2, sy = ((int16_t)(start_y + (y << 2))) >> 2;
         ensure_window(clip3i(sq.min_clip[0], sq.max_clip[0], sx), clip3i(sq.min_clip[1], sq.max_clip[1], sy),
                       bi == 1 ? 5 : dyn_range + 2);
+        set_bias(1);
         c = diamond(sx, sy, 3, bx, by, found, bits);
     }
     if(bi != 1 && bits > 0) mot_bits_l = bits;
@@ -339,6 +362,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
         const int16_t obias = bi ? (int16_t)0x8000 : (int16_t)0;
         uint32_t  sbest = 0xffffffffu;
         ensure_window(x + (mv_x >> 2), y + (mv_y >> 2), 2);
+        set_bias(0);
         for(int stage = 0; stage < 2; stage++) {
             if(stage == 1 && sq.me_level <= 2) break;
             const int cx = (int16_t)(smv_x + (x << 2)), cy = (int16_t)(smv_y + (y << 2));
@@ -423,6 +447,7 @@ __global__ void __launch_bounds__(ME_THREADS) k_me(const PicDev *__restrict__ pi
         const int ix = clip3i(sq.min_clip[0], sq.max_clip[0], ((int16_t)(mv_x + (x << 2))) >> 2);
         const int iy = clip3i(sq.min_clip[1], sq.max_clip[1], ((int16_t)(mv_y + (y << 2))) >> 2);
         ensure_window(ix, iy, 2);
+        set_bias(1);
         const uint64_t k = eval_round(9, ix, iy, [&](int cc, int &px, int &py) {
             // (0,0) (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
             const int dx9 = cc == 0 ? 0 : (cc <= 3 ? -1 : (cc <= 5 ? 0 : 1));

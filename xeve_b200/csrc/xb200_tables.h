@@ -60,8 +60,12 @@ XB_HD int xb200_mvd_bits(int v)
     }
     if(v == -2047) return 22;
     unsigned a = (unsigned)(v < 0 ? -v : v) + 1u;
-    int      l = 0;
-    while(a >> (l + 1)) l++; // floor(log2(|v|+1))
+#if defined(__CUDA_ARCH__)
+    const int l = 31 - __clz(a); // floor(log2(|v|+1))
+#else
+    int l = 0;
+    while(a >> (l + 1)) l++;
+#endif
     return 2 * l + 1 + (v != 0);
 }
 
