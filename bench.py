@@ -92,9 +92,8 @@ def run_b200(args, rank, world, dist):
     torch.cuda.set_device(dev)
     seq = api.make_seq(W, H, "fast")
     if world > 1:  # the only exchange the path has: rank 0 broadcasts the sequence header
-        t = torch.from_numpy(seq.view(np.uint8).copy()).cuda()
-        dist.broadcast(t, src=0)
-        seq = t.cpu().numpy().view(api.SEQ)
+        from xeve_b200 import dist as xd
+        seq = xd.broadcast_seq(seq, dist, device="cuda")
     hp = api.Hotpath(seq, device=dev)
     L, ctx = hp.L, hp.h
     clip, fr = frames_for_bench()
@@ -197,9 +196,7 @@ def run_b200(args, rank, world, dist):
     d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + 2 * 2 * fw.res_elems
 
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+        t_dev, t_e2e = xd.max_over_ranks([t_dev, t_e2e], dist, device="cuda")
     if rank != 0:
         hp.close()
         return None
