@@ -232,3 +232,93 @@ def test_bad_arguments_are_rejected(gpu_ctx):
         gpu_ctx.me(it)
     assert e.value.code in (api.ERR_UNSUPPORTED, api.ERR_INVALID_ARGUMENT)
     assert len(gpu_ctx.me(np.zeros(0, api.ME_ITEM))) == 0
+
+
+# ---- other BASELINE.json configurations: preset medium (range 64, 4 half-pel points), 10-bit input --------------
+def _upload_trace(tr):
+    hp = api.Hotpath(tr.seq)
+    handles = []
+    for i, p in enumerate(tr.pics):
+        h = hp.pic_create(padded=int(p["kind"]) == 1)
+        hp.pic_upload_s16(h, *(np.ascontiguousarray(a) for a in tr.planes[i]))
+        handles.append(h)
+    hp.handles = np.array(handles, np.int32)
+    return hp
+
+
+@pytest.mark.skipif(not rh.available(), reason="needs oracle/_ref to trace a live encode")
+@pytest.mark.parametrize("name,preset,frames,override", [
+    ("cif", "medium", 20, dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),           # configs 3/4 search settings
+    ("2160p10", "fast", 18, dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),  # 10-bit input, faster motion
+])
+def test_me_mc_tq_other_configs(name, preset, frames, override):
+    tr = tracedata.live_trace(name, frames=frames, pic_lo=1, pic_hi=2, preset=preset, **override)
+    hp = _upload_trace(tr)
+    try:
+        items = np.ascontiguousarray(tr.me).astype(api.ME_ITEM)
+        items = _remap(_remap(items, "cur_pic", hp.handles), "ref_pic", hp.handles)
+        got = hp.me(items, tr.side)
+        for f in ("mv_out", "cost", "mot_bits_out"):
+            assert np.array_equal(got[f], tr.me[f]), (name, preset, f)
+        recs = np.ascontiguousarray(tr.mc)
+        off, total = rh.mc_offsets(recs)
+        pred_ref, _, hsh, _ = rh.replay_mc(tr.live, nthreads=4)
+        assert np.array_equal(hp.mc(_remap(recs.astype(api.MC_ITEM), "ref_pic", hp.handles), off, total), pred_ref)
+        coef_ref, nnz_ref, _, _ = rh.replay_tq(tr.live, nthreads=4)
+        tq = np.ascontiguousarray(tr.tq).astype(api.TQ_ITEM)
+        it2, coef = hp.tq(tq, tr.rates, tr.tq_coef)
+        m = _item_mask(tq, len(coef))
+        assert np.array_equal(it2["nnz"], nnz_ref) and np.array_equal(coef[m], coef_ref[m])
+        assert int(tr.seq["hpel_cnt"][0]) == (4 if preset == "medium" else 2) and len(tr.me) > 500
+    finally:
+        hp.close()
+
+
+def test_full_size_1080p_properties():
+    """BASELINE config 2 size (1920x1080), properties that need no oracle run at this size:
+    (1) a CU whose content is an exact integer translation of the reference is found with SAD 0 when the
+        true vector lies inside the first search window; (2) residue of a perfect prediction is all zero:
+        nnz = 0, dist_pred = dist_rec = 0, rec == org; (3) ME cost is invariant to which picture slot holds
+        the reference; (4) bi_org of a perfect prediction equals org."""
+    from xeve_b200.worklist import FrameWork, cu_grid
+    w, h = 1920, 1080
+    rng = np.random.default_rng(5)
+    ref = [rng.integers(0, 1024, (h, w)).astype(np.int16), rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16),
+           rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16)]
+    dx, dy = 2, -1  # integer-pel shift (chroma shifts by 1, -0.5 -> not exact; only luma properties are asserted for ME)
+    cur = [np.roll(ref[0], (-dy, -dx), (0, 1)), ref[1].copy(), ref[2].copy()]
+    hp = api.Hotpath(api.make_seq(w, h, "fast"))
+    try:
+        r0, r1 = hp.pic_create(True), hp.pic_create(True)
+        hp.pic_upload_s16(r0, *ref)
+        hp.pic_upload_s16(r1, *ref)
+        c = hp.pic_create(False)
+        hp.pic_upload_s16(c, *cur)
+        fw = FrameWork(w, h, 8, (0, 16), (0, 0), c, [r0, r1], seed=1)
+        inner = (fw.x >= 64) & (fw.y >= 64) & (fw.x + (1 << fw.l2.astype(int)) <= w - 64) & (fw.y + (1 << fw.l2.astype(int)) <= h - 64)
+        me = fw.me_uni.copy()
+        me["mvp"] = 0
+        out = hp.me(me)
+        sel = np.repeat(inner, 2)
+        assert (out["mv_out"][sel] == [dx * 4, dy * 4]).all()      # cur(x) = ref(x + d)
+        lam = int(me["lambda_mv"][0])
+        from xeve_b200 import worklist  # noqa: F401
+        assert np.array_equal(out["cost"][0::2], out["cost"][1::2])  # same content in both reference slots
+        # residue with the found vectors: luma residual is exactly zero inside
+        bi_mc, me_bi_in = fw.build_bi(out)
+        side = hp.bi_org(bi_mc, fw.bi_cur, fw.side_off, fw.side_elems)
+        k = int(np.where(inner & (fw.l2 == 6))[0][0])
+        s = 64
+        blk = cur[0][fw.y[k]:fw.y[k] + s, fw.x[k]:fw.x[k] + s]
+        assert np.array_equal(side[fw.side_off[k]:fw.side_off[k] + s * s].reshape(s, s), blk)  # 2*org - org
+        me_bi = hp.me(me_bi_in, side)
+        res = fw.build_residue(me_bi)
+        res["run_stats"] = 1  # luma only (chroma is not translation-exact for odd shifts)
+        ro, coef, rec = hp.residue(res, fw.rates, fw.res_elems)
+        sel3 = np.repeat(inner, 3)
+        assert (ro["nnz"][sel3, 0] == 0).all() and (ro["dist_pred"][sel3, 0] == 0).all() and (ro["dist_rec"][sel3, 0] == 0).all()
+        o = int(ro["out_off"][3 * k])
+        assert np.array_equal(rec[o:o + s * s].reshape(s, s), blk)
+        assert len(out) == 2 * len(cu_grid(w, h)[0]) == 85800
+    finally:
+        hp.close()
