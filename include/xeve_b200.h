@@ -187,6 +187,11 @@ XB200_API int xb200_sad(xb200_ctx *c, const xb200_blk_item *items, int64_t n, in
 XB200_API int xb200_ssd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int64_t *out, int mem);
 XB200_API int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem);
 
+/* forward DCT-II of n contiguous N x N s16 blocks (N = 1 << log2n, 32 or 64; |x| <= 2048) on the tcgen05
+ * tensor cores -- the transform stage of xb200_residue exposed for parity checks against
+ * xeve_trans (src_base/xeve_tq.c:396-404).  Host buffers. */
+XB200_API int xb200_fwd_dct_tc(xb200_ctx *c, const int16_t *in, int16_t *out, int64_t n, int log2n);
+
 /* ---- hot-path operators ----------------------------------------------------------------------- */
 /* side: s16 buffer holding the org_bi blocks referenced by org_bi_off (may be NULL if none). */
 XB200_API int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem);

@@ -322,3 +322,26 @@ def test_full_size_1080p_properties():
         assert len(out) == 2 * len(cu_grid(w, h)[0]) == 85800
     finally:
         hp.close()
+
+
+@pytest.mark.parametrize("log2n", [5, 6])
+def test_tensor_core_dct_is_bit_exact(gpu_ctx, log2n):
+    """tcgen05 (fp16 operands, fp32 TMEM accumulators, hi/lo split) forward DCT == the integer transform of
+    the reference (xeve_trans, src_base/xeve_tq.c:396-404), incl. saturated +-1023 residuals"""
+    import ctypes as C
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    blocks = rng.integers(-1023, 1024, (300, n, n)).astype(np.int16)
+    blocks[0] = 1023
+    blocks[1] = -1023
+    blocks[2] = np.where((np.add.outer(np.arange(n), np.arange(n)) & 1) == 0, 1023, -1023)
+    blocks[3] = np.where(rng.random((n, n)) < 0.5, 1023, -1023)
+    blocks[4] = 0
+    blocks[5, :, :] = (np.sign(np.cos(np.pi * (2 * np.arange(n) + 1) / (2 * n)))[None, :] * 1023).astype(np.int16)
+    blocks[6:40] = rng.integers(-8, 9, (34, n, n)).astype(np.int16)
+    got = gpu_ctx.fwd_dct_tc(blocks, log2n)
+    L = xo.lib()
+    exp = blocks.copy()
+    for b in exp:
+        L.xo_fwd_transform(b.ctypes.data_as(C.c_void_p), log2n, log2n, 10)
+    assert np.array_equal(got, exp)

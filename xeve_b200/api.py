@@ -108,6 +108,7 @@ def load():
         L.xb200_me.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_mc.argtypes = [VP, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
         L.xb200_bi_org.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
+        L.xb200_fwd_dct_tc.argtypes = [VP, VP, VP, C.c_int64, C.c_int]
         L.xb200_tq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_itdq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_recon.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
@@ -118,7 +119,7 @@ def load():
 
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
-           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
+           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
 
 
 def _p(a):
@@ -244,6 +245,13 @@ class Hotpath:
         side = np.zeros(total, np.int16)
         self._ck(self.L.xb200_bi_org(self.h, _p(items), len(items), _p(cur_pic), _p(off), _p(side), total, MEM_HOST), "xb200_bi_org")
         return side
+
+    def fwd_dct_tc(self, blocks, log2n):
+        blocks = np.ascontiguousarray(blocks, np.int16)
+        out = np.zeros_like(blocks)
+        n = blocks.size >> (2 * log2n)
+        self._ck(self.L.xb200_fwd_dct_tc(self.h, _p(blocks), _p(out), n, log2n), "xb200_fwd_dct_tc")
+        return out
 
     def tq(self, items, rates, coef):
         items = np.ascontiguousarray(items, TQ_ITEM).copy()

@@ -13,6 +13,7 @@
 #include "xb200_tq.cuh"
 #include "xb200_misc.cuh"
 #include "xb200_residue2.cuh"
+#include "xb200_dct_tc.cuh"
 
 namespace {
 
@@ -467,6 +468,45 @@ extern "C" {
 int xb200_sad(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem) { return run_probe(c, items, n, out, mem, k_sad); }
 int xb200_ssd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int64_t *out, int mem) { return run_probe(c, items, n, out, mem, k_ssd); }
 int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *out, int mem) { return run_probe(c, items, n, out, mem, k_satd); }
+
+} // extern "C"
+template <int LN> static int run_dct_tc(xb200_ctx *c, const int16_t *d_in, int16_t *d_out, int n)
+{
+    constexpr int N = 1 << LN;
+    const size_t  smem = sizeof(TcDctSmem<LN>) + (size_t)N * N * 2 + 128;
+    CK(cudaFuncSetAttribute(k_dct_tc<LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = n < 296 ? n : 296;
+    k_dct_tc<LN><<<grid, 128, smem, c->stream>>>(d_in, d_out, n, c->d_tm64, c->sq.bd);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+extern "C" {
+int xb200_fwd_dct_tc(xb200_ctx *c, const int16_t *in, int16_t *out, int64_t n, int log2n)
+{
+    if(!c || n < 0 || (n && (!in || !out)) || n > (1 << 24)) return XB200_ERR_INVALID_ARGUMENT;
+    if(log2n != 5 && log2n != 6) return XB200_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    const size_t elems = (size_t)n << (2 * log2n);
+    int r;
+    int16_t *d_in;
+    if((r = to_dev(c, c->b_aux0, in, elems, XB200_MEM_HOST, &d_in))) return r;
+    if((r = ensure(c->b_aux1, elems * 2 + 64))) return r;
+    int16_t *d_out = static_cast<int16_t *>(c->b_aux1.p);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    r = log2n == 6 ? run_dct_tc<6>(c, d_in, d_out, (int)n) : run_dct_tc<5>(c, d_in, d_out, (int)n);
+    if(r) return r;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, out, d_out, elems, XB200_MEM_HOST))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
 
 // ---- motion search ------------------------------------------------------------------------------------------
 int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem)

@@ -1,0 +1,217 @@
+// xb200_dct_tc.cuh -- forward 32- and 64-point DCT-II on the 5th-generation tensor cores
+// (tcgen05.mma kind::f16, accumulators in TMEM), bit-identical to the integer path
+// (fwd_dct / reference src_base/xeve_tq.c:396-404, tx_pb32b / tx_pb64b :208-392).
+//
+// Why fp16 operands are exact here
+//   stage 0:  T[y][u] = sum_x X[y][x] * tm[u][x].  X is a residual of 10-bit samples (|X| <= 1023) and
+//             |tm| <= 90: both are integers below 2^11, i.e. exactly representable in fp16; every
+//             partial sum is an integer below 64*1023*90 < 2^23, exactly representable in the fp32
+//             accumulator, so the tensor core result is the exact integer.
+//   stage 1:  C[v][u] = (sum_y tm[v][y] * T[y][u] + rnd) >> shift.  T needs 24 bits, so it is split
+//             T = hi * 4096 + lo with lo in [-2048, 2047], |hi| <= 1440: both fp16-exact.  Two MMAs give
+//             the exact integers sum tm*hi (< 2^23.1) and sum tm*lo (< 2^23.5); the epilogue recombines
+//             them in 64-bit integer arithmetic and applies the reference's rounding shift.
+//
+// GEMM shapes (cta_group::1, M = 128, N = 32, K = 16 per instruction, operands in shared memory in the
+// canonical no-swizzle K-major core-matrix layout: 8 rows x 16 bytes contiguous, SBO between 8-row
+// groups, LBO between the two 8-element K chunks):
+//   stage 0:  D0[y][u]  (rows y: the N block rows, zero-padded to 128)  A = X, B = tm rows u < 32
+//   stage 1:  D1[v][u]  (rows v: matrix rows, zero-padded to 128)       A = tm, B = hi^T / lo^T
+// The 64-point transform only keeps the 32 low-frequency outputs per dimension (zero-out,
+// src_base/xeve_tq.c:318-381), so N = 32 output columns suffice for both sizes.
+#pragma once
+#include <cuda_fp16.h>
+#include "xb200_common.cuh"
+
+#define TC_LBO_A 2048 // bytes between K chunks of a 128-row operand: 16 row groups * 128 B
+#define TC_LBO_B 512  // bytes between K chunks of a 32-row operand:   4 row groups * 128 B
+#define TC_SBO   128
+
+XB_DEV uint64_t tc_smem_desc(const void *p, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(p) >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46; // descriptor version (Blackwell)
+    return d;               // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N = 32, M = 128
+XB_DEV uint32_t tc_idesc_f16_m128_n32() { return (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24); }
+
+XB_DEV void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+XB_DEV void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+XB_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+XB_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+XB_DEV void tc_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+XB_DEV void tc_alloc(uint32_t *slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+XB_DEV void tc_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// one warp: its 32 TMEM lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane = row)
+XB_DEV void tc_ld_row32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of element (row, k) inside a canonical K-major operand with `lbo` bytes between K chunks
+XB_DEV int tc_off(int row, int k, int lbo) { return (k >> 3) * lbo + (row >> 3) * TC_SBO + (row & 7) * 16 + (k & 7) * 2; }
+
+// shared-memory working set of the tensor-core DCT (per CTA)
+template <int LN> struct TcDctSmem {
+    static constexpr int N = 1 << LN;
+    __half   tmh[128 * N]; // DCT matrix rows (zero-padded to 128), canonical layout, K = N
+    __half   xa[128 * N];  // block rows (zero-padded to 128)
+    __half   bh[32 * N];   // hi^T: rows u < 32, K = y
+    __half   bl[32 * N];   // lo^T
+    uint64_t bar;
+    uint32_t tmem_base;
+    uint32_t phase;
+};
+
+// fill the constant operand once per CTA (all threads)
+template <int LN, int NT> XB_DEV void tc_dct_setup(TcDctSmem<LN> &S, const int8_t *__restrict__ g_tm64, int tid)
+{
+    constexpr int N = 1 << LN, ks = 6 - LN;
+    char *tm = reinterpret_cast<char *>(S.tmh), *xa = reinterpret_cast<char *>(S.xa);
+    for(int e = tid; e < 128 * N; e += NT) {
+        const int m = e / N, k = e % N;
+        const int v = m < N ? (int)g_tm64[(m << ks) * 64 + k] : 0;
+        *reinterpret_cast<__half *>(tm + tc_off(m, k, TC_LBO_A)) = __int2half_rn(v);
+        *reinterpret_cast<__half *>(xa + tc_off(m, k, TC_LBO_A)) = __int2half_rn(0);
+    }
+    if(tid == 0) { mbar_init(&S.bar, 1); S.phase = 0; }
+    if(tid < 32) tc_alloc(&S.tmem_base, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
+template <int LN> XB_DEV void tc_dct_teardown(TcDctSmem<LN> &S, int tid)
+{
+    __syncthreads();
+    if(tid < 32) tc_dealloc(S.tmem_base, 128);
+}
+
+// Forward transform of blk (N x N s16, |x| <= 2048, stride N) in place; NT threads (>= 128), all call.
+template <int LN, int NT> XB_DEV void tc_fwd_dct(TcDctSmem<LN> &S, int16_t *blk, int bd, int tid)
+{
+    constexpr int N = 1 << LN;
+    const int      shift = (LN - 1 + bd - 8) + (LN + 6), warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem = S.tmem_base, idesc = tc_idesc_f16_m128_n32();
+    char *xa = reinterpret_cast<char *>(S.xa), *bh = reinterpret_cast<char *>(S.bh), *bl = reinterpret_cast<char *>(S.bl);
+    uint32_t phase = S.phase;
+    // ---- A operand of stage 0: the block rows as fp16 -------------------------------------------------------
+    for(int e = tid; e < N * N; e += NT) {
+        const int y = e >> LN, x = e & (N - 1);
+        *reinterpret_cast<__half *>(xa + tc_off(y, x, TC_LBO_A)) = __int2half_rn((int)blk[e]);
+    }
+    tc_proxy_fence();
+    __syncthreads();
+    if(tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for(int s = 0; s < N / 16; s++)
+            tc_mma_f16(tmem, tc_smem_desc(xa + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO),
+                       tc_smem_desc(reinterpret_cast<char *>(S.tmh) + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO), idesc, s > 0);
+        tc_commit(&S.bar);
+    }
+    mbar_wait(&S.bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- stage-0 result rows y < N -> hi / lo halves, transposed into the B operands of stage 1 -----------------
+    if(warp < N / 32) {
+        uint32_t r[32];
+        tc_ld_row32(tmem + ((uint32_t)(warp * 32) << 16), r);
+        const int y = warp * 32 + lane;
+#pragma unroll
+        for(int u = 0; u < 32; u++) {
+            const int t  = __float2int_rn(__uint_as_float(r[u]));
+            const int lo = ((t + 2048) & 4095) - 2048, hi = (t - lo) >> 12;
+            *reinterpret_cast<__half *>(bh + tc_off(u, y, TC_LBO_B)) = __int2half_rn(hi);
+            *reinterpret_cast<__half *>(bl + tc_off(u, y, TC_LBO_B)) = __int2half_rn(lo);
+        }
+    }
+    tc_fence_before();
+    tc_proxy_fence();
+    __syncthreads();
+    if(tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for(int s = 0; s < N / 16; s++) {
+            const uint64_t da = tc_smem_desc(reinterpret_cast<char *>(S.tmh) + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+            tc_mma_f16(tmem + 32, da, tc_smem_desc(bh + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
+            tc_mma_f16(tmem + 64, da, tc_smem_desc(bl + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
+        }
+        tc_commit(&S.bar);
+    }
+    mbar_wait(&S.bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: rows v < 32 recombine, round, store; everything else of the block is zero ----------------------
+    if(warp == 0) {
+        uint32_t rh[32], rl[32];
+        tc_ld_row32(tmem + 32, rh);
+        tc_ld_row32(tmem + 64, rl);
+#pragma unroll
+        for(int u = 0; u < 32; u++) {
+            const int64_t acc = (int64_t)__float2int_rn(__uint_as_float(rh[u])) * 4096 + (int64_t)__float2int_rn(__uint_as_float(rl[u]));
+            blk[lane * N + u] = (int16_t)((acc + ((int64_t)1 << (shift - 1))) >> shift);
+        }
+        if(N == 64)
+            for(int u = 32; u < 64; u++) blk[lane * N + u] = 0;
+    }
+    else if(N == 64) {
+        for(int e = tid - 32; e < 32 * 64; e += NT - 32) blk[32 * 64 + e] = 0;
+    }
+    tc_fence_before();
+    if(tid == 0) S.phase = phase;
+    __syncthreads();
+}
+
+// standalone probe: one CTA per block (used by the parity test of the tensor-core path)
+template <int LN>
+__global__ void __launch_bounds__(128) k_dct_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, int n,
+                                                 const int8_t *__restrict__ g_tm64, int bd)
+{
+    constexpr int N = 1 << LN;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcDctSmem<LN> &S   = *reinterpret_cast<TcDctSmem<LN> *>(smem_raw);
+    int16_t       *blk = reinterpret_cast<int16_t *>(smem_raw + sizeof(TcDctSmem<LN>));
+    const int      tid = threadIdx.x;
+    tc_dct_setup<LN, 128>(S, g_tm64, tid);
+    for(int b = blockIdx.x; b < n; b += gridDim.x) {
+        for(int e = tid; e < N * N; e += 128) blk[e] = in[(size_t)b * N * N + e];
+        __syncthreads();
+        tc_fwd_dct<LN, 128>(S, blk, bd, tid);
+        for(int e = tid; e < N * N; e += 128) out[(size_t)b * N * N + e] = blk[e];
+        __syncthreads();
+    }
+    tc_dct_teardown<LN>(S, tid);
+}
