@@ -472,8 +472,7 @@ int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, int32_t *ou
 } // extern "C"
 template <int LN> static int run_dct_tc(xb200_ctx *c, const int16_t *d_in, int16_t *d_out, int n)
 {
-    constexpr int N = 1 << LN;
-    const size_t  smem = sizeof(TcDctSmem<LN>) + (size_t)N * N * 2 + 128;
+    const size_t  smem = tc_probe_smem<LN>();
     CK(cudaFuncSetAttribute(k_dct_tc<LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = n < 296 ? n : 296;
     k_dct_tc<LN><<<grid, 128, smem, c->stream>>>(d_in, d_out, n, c->d_tm64, c->sq.bd);

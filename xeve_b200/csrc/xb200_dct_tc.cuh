@@ -84,49 +84,58 @@ XB_DEV void tc_ld_row32(uint32_t taddr, uint32_t (&r)[32])
 // byte offset of element (row, k) inside a canonical K-major operand with `lbo` bytes between K chunks
 XB_DEV int tc_off(int row, int k, int lbo) { return (k >> 3) * lbo + (row >> 3) * TC_SBO + (row & 7) * 16 + (k & 7) * 2; }
 
-// shared-memory working set of the tensor-core DCT (per CTA)
-template <int LN> struct TcDctSmem {
-    static constexpr int N = 1 << LN;
-    __half   tmh[128 * N]; // DCT matrix rows (zero-padded to 128), canonical layout, K = N
-    __half   xa[128 * N];  // block rows (zero-padded to 128)
-    __half   bh[32 * N];   // hi^T: rows u < 32, K = y
-    __half   bl[32 * N];   // lo^T
+// shared-memory working set of the tensor-core DCT (per CTA), sized for transforms up to 1 << LNMAX
+template <int LNMAX> struct alignas(128) TcWork { // sizeof is a multiple of 128: operands placed after it stay 128-byte aligned
+    static constexpr int NMAX = 1 << LNMAX;
+    __half   xa[128 * NMAX]; // block rows (zero-padded to 128), canonical layout
+    __half   bh[32 * NMAX];  // hi^T: rows u < 32, K = y
+    __half   bl[32 * NMAX];  // lo^T
     uint64_t bar;
     uint32_t tmem_base;
     uint32_t phase;
+    uint32_t pad_;
 };
 
-// fill the constant operand once per CTA (all threads)
-template <int LN, int NT> XB_DEV void tc_dct_setup(TcDctSmem<LN> &S, const int8_t *__restrict__ g_tm64, int tid)
+// DCT matrix rows (zero-padded to 128) as fp16 in the canonical layout, K = N: 128 * N halves
+template <int LN, int NT> XB_DEV void tc_fill_tm(__half *tmh, const int8_t *__restrict__ g_tm64, int tid)
 {
     constexpr int N = 1 << LN, ks = 6 - LN;
-    char *tm = reinterpret_cast<char *>(S.tmh), *xa = reinterpret_cast<char *>(S.xa);
+    char *tm = reinterpret_cast<char *>(tmh);
     for(int e = tid; e < 128 * N; e += NT) {
-        const int m = e / N, k = e % N;
+        const int m = e >> LN, k = e & (N - 1);
         const int v = m < N ? (int)g_tm64[(m << ks) * 64 + k] : 0;
         *reinterpret_cast<__half *>(tm + tc_off(m, k, TC_LBO_A)) = __int2half_rn(v);
-        *reinterpret_cast<__half *>(xa + tc_off(m, k, TC_LBO_A)) = __int2half_rn(0);
     }
-    if(tid == 0) { mbar_init(&S.bar, 1); S.phase = 0; }
-    if(tid < 32) tc_alloc(&S.tmem_base, 128);
+}
+// once per CTA (all threads): zero the A operand, init the mbarrier, allocate 64 TMEM columns
+template <int LNMAX, int NT> XB_DEV void tc_setup(TcWork<LNMAX> &W, int tid)
+{
+    uint32_t *z = reinterpret_cast<uint32_t *>(W.xa);
+    for(int e = tid; e < 128 * TcWork<LNMAX>::NMAX / 2; e += NT) z[e] = 0;
+    if(tid == 0) { mbar_init(&W.bar, 1); W.phase = 0; }
+    if(tid < 32) tc_alloc(&W.tmem_base, 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 }
-template <int LN> XB_DEV void tc_dct_teardown(TcDctSmem<LN> &S, int tid)
+template <int LNMAX> XB_DEV void tc_teardown(TcWork<LNMAX> &W, int tid)
 {
     __syncthreads();
-    if(tid < 32) tc_dealloc(S.tmem_base, 128);
+    if(tid < 32) tc_dealloc(W.tmem_base, 64);
 }
 
 // Forward transform of blk (N x N s16, |x| <= 2048, stride N) in place; NT threads (>= 128), all call.
-template <int LN, int NT> XB_DEV void tc_fwd_dct(TcDctSmem<LN> &S, int16_t *blk, int bd, int tid)
+// tmh: canonical fp16 copy of the N-point matrix (tc_fill_tm<LN>).  TMEM columns: stage-0 accumulator
+// 0..31; stage 1 reuses 0..31 (hi) and 32..63 (lo) once the stage-0 rows have been read back.
+template <int LN, int NT, int LNMAX> XB_DEV void tc_fwd_dct(TcWork<LNMAX> &W, const __half *tmh, int16_t *blk, int bd, int tid)
 {
     constexpr int N = 1 << LN;
+    static_assert(LN <= LNMAX && NT >= 128 && N >= 32, "tensor-core DCT: 32- or 64-point, at least 4 warps");
     const int      shift = (LN - 1 + bd - 8) + (LN + 6), warp = tid >> 5, lane = tid & 31;
-    const uint32_t tmem = S.tmem_base, idesc = tc_idesc_f16_m128_n32();
-    char *xa = reinterpret_cast<char *>(S.xa), *bh = reinterpret_cast<char *>(S.bh), *bl = reinterpret_cast<char *>(S.bl);
-    uint32_t phase = S.phase;
+    const uint32_t tmem = W.tmem_base, idesc = tc_idesc_f16_m128_n32();
+    char       *xa = reinterpret_cast<char *>(W.xa), *bh = reinterpret_cast<char *>(W.bh), *bl = reinterpret_cast<char *>(W.bl);
+    const char *tm = reinterpret_cast<const char *>(tmh);
+    uint32_t    phase = W.phase;
     // ---- A operand of stage 0: the block rows as fp16 -------------------------------------------------------
     for(int e = tid; e < N * N; e += NT) {
         const int y = e >> LN, x = e & (N - 1);
@@ -138,11 +147,11 @@ template <int LN, int NT> XB_DEV void tc_fwd_dct(TcDctSmem<LN> &S, int16_t *blk,
         tc_fence_after();
 #pragma unroll
         for(int s = 0; s < N / 16; s++)
-            tc_mma_f16(tmem, tc_smem_desc(xa + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO),
-                       tc_smem_desc(reinterpret_cast<char *>(S.tmh) + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO), idesc, s > 0);
-        tc_commit(&S.bar);
+            tc_mma_f16(tmem, tc_smem_desc(xa + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO), tc_smem_desc(tm + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO),
+                       idesc, s > 0);
+        tc_commit(&W.bar);
     }
-    mbar_wait(&S.bar, phase);
+    mbar_wait(&W.bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- stage-0 result rows y < N -> hi / lo halves, transposed into the B operands of stage 1 -----------------
@@ -165,20 +174,20 @@ template <int LN, int NT> XB_DEV void tc_fwd_dct(TcDctSmem<LN> &S, int16_t *blk,
         tc_fence_after();
 #pragma unroll
         for(int s = 0; s < N / 16; s++) {
-            const uint64_t da = tc_smem_desc(reinterpret_cast<char *>(S.tmh) + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-            tc_mma_f16(tmem + 32, da, tc_smem_desc(bh + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
-            tc_mma_f16(tmem + 64, da, tc_smem_desc(bl + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
+            const uint64_t da = tc_smem_desc(tm + s * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+            tc_mma_f16(tmem, da, tc_smem_desc(bh + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
+            tc_mma_f16(tmem + 32, da, tc_smem_desc(bl + s * 2 * TC_LBO_B, TC_LBO_B, TC_SBO), idesc, s > 0);
         }
-        tc_commit(&S.bar);
+        tc_commit(&W.bar);
     }
-    mbar_wait(&S.bar, phase);
+    mbar_wait(&W.bar, phase);
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue: rows v < 32 recombine, round, store; everything else of the block is zero ----------------------
     if(warp == 0) {
         uint32_t rh[32], rl[32];
-        tc_ld_row32(tmem + 32, rh);
-        tc_ld_row32(tmem + 64, rl);
+        tc_ld_row32(tmem, rh);
+        tc_ld_row32(tmem + 32, rl);
 #pragma unroll
         for(int u = 0; u < 32; u++) {
             const int64_t acc = (int64_t)__float2int_rn(__uint_as_float(rh[u])) * 4096 + (int64_t)__float2int_rn(__uint_as_float(rl[u]));
@@ -191,27 +200,30 @@ template <int LN, int NT> XB_DEV void tc_fwd_dct(TcDctSmem<LN> &S, int16_t *blk,
         for(int e = tid - 32; e < 32 * 64; e += NT - 32) blk[32 * 64 + e] = 0;
     }
     tc_fence_before();
-    if(tid == 0) S.phase = phase;
+    if(tid == 0) W.phase = phase;
     __syncthreads();
 }
 
-// standalone probe: one CTA per block (used by the parity test of the tensor-core path)
+// standalone probe: persistent CTAs over contiguous blocks (parity test of the tensor-core path)
 template <int LN>
 __global__ void __launch_bounds__(128) k_dct_tc(const int16_t *__restrict__ in, int16_t *__restrict__ out, int n,
                                                  const int8_t *__restrict__ g_tm64, int bd)
 {
     constexpr int N = 1 << LN;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TcDctSmem<LN> &S   = *reinterpret_cast<TcDctSmem<LN> *>(smem_raw);
-    int16_t       *blk = reinterpret_cast<int16_t *>(smem_raw + sizeof(TcDctSmem<LN>));
-    const int      tid = threadIdx.x;
-    tc_dct_setup<LN, 128>(S, g_tm64, tid);
+    TcWork<LN> &W   = *reinterpret_cast<TcWork<LN> *>(smem_raw);
+    __half     *tmh = reinterpret_cast<__half *>(smem_raw + sizeof(TcWork<LN>));
+    int16_t    *blk = reinterpret_cast<int16_t *>(tmh + 128 * N);
+    const int   tid = threadIdx.x;
+    tc_fill_tm<LN, 128>(tmh, g_tm64, tid);
+    tc_setup<LN, 128>(W, tid);
     for(int b = blockIdx.x; b < n; b += gridDim.x) {
         for(int e = tid; e < N * N; e += 128) blk[e] = in[(size_t)b * N * N + e];
         __syncthreads();
-        tc_fwd_dct<LN, 128>(S, blk, bd, tid);
+        tc_fwd_dct<LN, 128, LN>(W, tmh, blk, bd, tid);
         for(int e = tid; e < N * N; e += 128) out[(size_t)b * N * N + e] = blk[e];
         __syncthreads();
     }
-    tc_dct_teardown<LN>(S, tid);
+    tc_teardown<LN>(W, tid);
 }
+template <int LN> constexpr size_t tc_probe_smem() { return sizeof(TcWork<LN>) + (size_t)128 * (1 << LN) * 2 + (size_t)(1 << (2 * LN)) * 2 + 128; }

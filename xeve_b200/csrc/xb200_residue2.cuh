@@ -10,6 +10,7 @@
 #pragma once
 #include "xb200_common.cuh"
 #include "xb200_tq.cuh"
+#include "xb200_dct_tc.cuh"
 
 template <int T> XB_DEV void team_sync()
 {
@@ -369,11 +370,12 @@ template <int LN, int T> XB_DEV void dequant_team(int16_t *blk, int qp, int bd, 
 }
 
 // ---- one plane of one item: residual, SSD, TQ, ITDQ, recon, SSD ------------------------------------------------------------
-template <int LN, int T>
+// TCW / tmh: tensor-core work area and fp16 matrix of this plane's size, or null -> integer transform
+template <int LN, int T, int LNMAX>
 XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t *pr, int16_t *blk, int32_t *TB, const int8_t *tm,
                           const int8_t *tmT, int16_t *__restrict__ gco, int16_t *__restrict__ grec, int run, int qp, double lambda,
                           int ch, int slice_type, const xb200_rates *__restrict__ rt, const SeqDev &sq, int tt, TeamScratch &X,
-                          int &nnz_out, int64_t &dist_pred, int64_t &dist_rec)
+                          int &nnz_out, int64_t &dist_pred, int64_t &dist_rec, TcWork<LNMAX> *TCW, const __half *tmh)
 {
     constexpr int N = 1 << LN, nn = N * N;
     const int     maxv = (1 << sq.bd) - 1, sh = (sq.bd - 8) << 1;
@@ -387,7 +389,12 @@ XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t
     dist_pred = team_sum_s64<T>(dpart, tt, X);
     int nnz = 0;
     if(run) {
-        fwd_dct_t<LN, T>(blk, TB, tm, tmT, sq.bd, tt);
+        if constexpr(LN >= 5 && T >= 128 && LN <= LNMAX) {
+            // residuals of <= 10-bit samples are fp16-exact: 32/64-point stages go to the tensor cores
+            if(TCW != nullptr && sq.bd <= 10) tc_fwd_dct<LN, T, LNMAX>(*TCW, tmh, blk, sq.bd, tt);
+            else fwd_dct_t<LN, T>(blk, TB, tm, tmT, sq.bd, tt);
+        }
+        else fwd_dct_t<LN, T>(blk, TB, tm, tmT, sq.bd, tt);
         nnz = quant_team<LN, T>(blk, TB, qp, lambda, ch, slice_type, rt, sq.bd, sq.rdoq, tt, X);
     }
     for(int e = tt; e < nn; e += T) gco[e] = blk[e];
@@ -421,7 +428,9 @@ template <int L2> struct Res2Cfg {
     static constexpr int PRED  = N * N * 3 / 2;                               // samples
     static constexpr int TBW   = L2 == 6 ? 4096 : N * N;                      // int32 words: DCT stage / MC tmp / RDOQ scratch
     static constexpr int TEAM_BYTES = (2 * PRED + N * N) * 2 + TBW * 4 + (int)sizeof(TeamScratch);
-    static constexpr int SMEM  = 8192 + TEAMS * TEAM_BYTES;
+    static constexpr bool TC   = L2 >= 5;                                     // 32/64-point luma (and 32-point chroma) on tcgen05
+    static constexpr int TC_BYTES = TC ? (int)sizeof(TcWork<(L2 >= 5 ? L2 : 5)>) + 128 * N * 2 + (L2 == 6 ? 128 * 32 * 2 : 0) : 0;
+    static constexpr int SMEM  = 8192 + TEAMS * TEAM_BYTES + TC_BYTES + (TC ? 128 : 0);
 };
 
 template <int L2>
@@ -446,6 +455,21 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
         tm[e] = v;
         tmT[(e & 63) * 64 + (e >> 6)] = v;
     }
+    constexpr int LNMAX = L2 >= 5 ? L2 : 5;
+    TcWork<LNMAX> *TCW = nullptr;
+    __half        *tmh_y = nullptr, *tmh_c = nullptr;
+    if constexpr(Cf::TC) {
+        unsigned char *tcb = smem_raw + 8192 + Cf::TEAMS * Cf::TEAM_BYTES;
+        tcb += (128 - (smem_u32(tcb) & 127)) & 127;
+        TCW   = reinterpret_cast<TcWork<LNMAX> *>(tcb);
+        tmh_y = reinterpret_cast<__half *>(tcb + sizeof(TcWork<LNMAX>));
+        tc_fill_tm<L2, Cf::CTA>(tmh_y, g_tm64, threadIdx.x);
+        if constexpr(L2 == 6) {
+            tmh_c = tmh_y + 128 * N;
+            tc_fill_tm<5, Cf::CTA>(tmh_c, g_tm64, threadIdx.x);
+        }
+        tc_setup<LNMAX, Cf::CTA>(*TCW, threadIdx.x);
+    }
     __syncthreads();
     for(int i = blockIdx.x * Cf::TEAMS + team; i < n; i += gridDim.x * Cf::TEAMS) {
         xb200_residue_item *it = &items[order[i]];
@@ -457,19 +481,20 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
         const int rs = it->run_stats, st = it->slice_type;
         int     nnz[3];
         int64_t dp[3], dr[3];
-        residue_plane<L2, T>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec + oo, rs & 1,
-                             it->qp[0], it->lambda[0], 0, st, rt, sq, tt, X, nnz[0], dp[0], dr[0]);
-        residue_plane<L2 - 1, T>(o.p[1] + (ptrdiff_t)(mc.y >> 1) * o.s[1] + (mc.x >> 1), o.s[1], pred + NY, blk, TB, tm, tmT,
-                                 coef + oo + NY, rec + oo + NY, (rs >> 1) & 1, it->qp[1], it->lambda[1], 1, st, rt, sq, tt, X, nnz[1],
-                                 dp[1], dr[1]);
-        residue_plane<L2 - 1, T>(o.p[2] + (ptrdiff_t)(mc.y >> 1) * o.s[2] + (mc.x >> 1), o.s[2], pred + NY + NCH, blk, TB, tm, tmT,
-                                 coef + oo + NY + NCH, rec + oo + NY + NCH, (rs >> 2) & 1, it->qp[2], it->lambda[2], 2, st, rt, sq, tt, X,
-                                 nnz[2], dp[2], dr[2]);
+        residue_plane<L2, T, LNMAX>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec + oo, rs & 1,
+                                    it->qp[0], it->lambda[0], 0, st, rt, sq, tt, X, nnz[0], dp[0], dr[0], TCW, tmh_y);
+        residue_plane<L2 - 1, T, LNMAX>(o.p[1] + (ptrdiff_t)(mc.y >> 1) * o.s[1] + (mc.x >> 1), o.s[1], pred + NY, blk, TB, tm, tmT,
+                                        coef + oo + NY, rec + oo + NY, (rs >> 1) & 1, it->qp[1], it->lambda[1], 1, st, rt, sq, tt, X,
+                                        nnz[1], dp[1], dr[1], tmh_c ? TCW : nullptr, tmh_c);
+        residue_plane<L2 - 1, T, LNMAX>(o.p[2] + (ptrdiff_t)(mc.y >> 1) * o.s[2] + (mc.x >> 1), o.s[2], pred + NY + NCH, blk, TB, tm,
+                                        tmT, coef + oo + NY + NCH, rec + oo + NY + NCH, (rs >> 2) & 1, it->qp[2], it->lambda[2], 2, st,
+                                        rt, sq, tt, X, nnz[2], dp[2], dr[2], tmh_c ? TCW : nullptr, tmh_c);
         if(tt == 0) {
 #pragma unroll
             for(int c = 0; c < 3; c++) { it->nnz[c] = nnz[c]; it->dist_pred[c] = dp[c]; it->dist_rec[c] = dr[c]; }
         }
     }
+    if constexpr(Cf::TC) tc_teardown<LNMAX>(*TCW, threadIdx.x);
 }
 
 __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
