@@ -345,3 +345,36 @@ def test_tensor_core_dct_is_bit_exact(gpu_ctx, log2n):
     for b in exp:
         L.xo_fwd_transform(b.ctypes.data_as(C.c_void_p), log2n, log2n, 10)
     assert np.array_equal(got, exp)
+
+
+def test_fused_residue_with_tensor_core_dct(trace, monkeypatch):
+    """xb200_residue with XB200_TC_DCT=1: the 32/64-point forward stages run on tcgen05 inside the fused
+    kernel and every output (coefficients, nnz, distortions, reconstruction) stays bit-identical"""
+    monkeypatch.setenv("XB200_TC_DCT", "1")
+    hp = _upload_trace(trace)
+    try:
+        rng = np.random.default_rng(21)
+        mc = np.ascontiguousarray(trace.mc)
+        pocs = {int(p["poc"]): i for i, p in enumerate(trace.pics) if int(p["kind"]) == 0}
+        sel = np.array([i for i in range(len(mc)) if int(mc[i]["w"]) >= 32 and int(mc[i]["poc"]) in pocs])
+        sel = sel[rng.permutation(len(sel))[:600]]
+        items = np.zeros(len(sel), api.RESIDUE_ITEM)
+        off = 0
+        for k, i in enumerate(sel):
+            t = trace.tq[int(rng.integers(0, len(trace.tq)))]
+            items[k]["mc"] = mc[i]
+            items[k]["cur_pic"] = pocs[int(mc[i]["poc"])]
+            items[k]["slice_type"], items[k]["run_stats"], items[k]["qp"] = 0, 7, [34, 34, 34]  # low QP: many non-zero blocks
+            items[k]["rate_idx"], items[k]["lambda"], items[k]["out_off"] = t["rate_idx"], t["lambda"], off
+            off += int(mc[i]["w"]) * int(mc[i]["h"]) * 3 // 2
+        exp_items, exp_coef, exp_rec = xo.residue_batch(trace.seq, trace.oracle_planes(), trace.rates, items, off)
+        dev = items.copy()
+        dev["cur_pic"] = hp.handles[items["cur_pic"]]
+        dev["mc"] = _remap(dev["mc"].copy(), "ref_pic", hp.handles)
+        got_items, got_coef, got_rec = hp.residue(dev, trace.rates, off)
+        for f in ("nnz", "dist_pred", "dist_rec"):
+            assert np.array_equal(got_items[f], exp_items[f]), f
+        assert np.array_equal(got_coef, exp_coef) and np.array_equal(got_rec, exp_rec)
+        assert (exp_items["nnz"][:, 0] > 0).sum() > 100
+    finally:
+        hp.close()

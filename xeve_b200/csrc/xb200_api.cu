@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -193,24 +194,32 @@ int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cn
     return XB200_OK;
 }
 
+template <int L2, bool USE_TC>
+int launch_residue2_v(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates,
+                      int16_t *d_coef, int16_t *d_rec)
+{
+    using Cf = Res2Cfg<L2>;
+    static int blocks_per_sm = 0, sms = 0;
+    constexpr int smem = USE_TC ? Cf::SMEM : Cf::SMEM_INT;
+    if(!blocks_per_sm) {
+        CK(cudaFuncSetAttribute(k_residue2<L2, USE_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_residue2<L2, USE_TC>, Cf::CTA, smem));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if(blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
+    k_residue2<L2, USE_TC><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
 template <int L2>
 int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates,
                     int16_t *d_coef, int16_t *d_rec)
 {
     if(cnt == 0) return XB200_OK;
-    using Cf = Res2Cfg<L2>;
-    static int blocks_per_sm = 0, sms = 0;
-    if(!blocks_per_sm) {
-        CK(cudaFuncSetAttribute(k_residue2<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_residue2<L2>, Cf::CTA, Cf::SMEM));
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        if(blocks_per_sm < 1) blocks_per_sm = 1;
-    }
-    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
-    k_residue2<L2><<<grid, Cf::CTA, Cf::SMEM, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
-    c->launches++;
-    CK(cudaGetLastError());
-    return XB200_OK;
+    if(Res2Cfg<L2>::TC && c->sq.tc_dct && c->sq.bd <= 10) return launch_residue2_v<L2, true>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
+    return launch_residue2_v<L2, false>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
 }
 
 } // namespace
@@ -245,6 +254,10 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     c->sq.me_complexity = seq->me_complexity;
     for(int i = 0; i < 2; i++) { c->sq.min_clip[i] = seq->min_clip[i]; c->sq.max_clip[i] = seq->max_clip[i]; }
     c->sq.rdoq = seq->rdoq;
+    {   // opt-in: tensor-core transform stages inside xb200_residue (bit-identical to the integer stages)
+        const char *e = getenv("XB200_TC_DCT");
+        c->sq.tc_dct = (e && e[0] == '1') ? 1 : 0;
+    }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));

@@ -22,6 +22,7 @@ struct SeqDev {
     int32_t me_level, hpel_cnt, qpel_cnt, me_complexity;
     int32_t min_clip[2], max_clip[2];
     int32_t rdoq;
+    int32_t tc_dct; // 32/64-point forward DCT on tcgen05 (bit-identical; off by default)
 };
 
 __constant__ int8_t  c_tm64[64 * 64];           // DCT-II matrix, N-point rows at stride 64/N

@@ -371,7 +371,7 @@ template <int LN, int T> XB_DEV void dequant_team(int16_t *blk, int qp, int bd, 
 
 // ---- one plane of one item: residual, SSD, TQ, ITDQ, recon, SSD ------------------------------------------------------------
 // TCW / tmh: tensor-core work area and fp16 matrix of this plane's size, or null -> integer transform
-template <int LN, int T, int LNMAX>
+template <int LN, int T, int LNMAX, bool USE_TC>
 XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t *pr, int16_t *blk, int32_t *TB, const int8_t *tm,
                           const int8_t *tmT, int16_t *__restrict__ gco, int16_t *__restrict__ grec, int run, int qp, double lambda,
                           int ch, int slice_type, const xb200_rates *__restrict__ rt, const SeqDev &sq, int tt, TeamScratch &X,
@@ -389,7 +389,7 @@ XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t
     dist_pred = team_sum_s64<T>(dpart, tt, X);
     int nnz = 0;
     if(run) {
-        if constexpr(LN >= 5 && T >= 128 && LN <= LNMAX) {
+        if constexpr(USE_TC && LN >= 5 && T >= 128 && LN <= LNMAX) {
             // residuals of <= 10-bit samples are fp16-exact: 32/64-point stages go to the tensor cores
             if(TCW != nullptr && sq.bd <= 10) tc_fwd_dct<LN, T, LNMAX>(*TCW, tmh, blk, sq.bd, tt);
             else fwd_dct_t<LN, T>(blk, TB, tm, tmT, sq.bd, tt);
@@ -430,10 +430,11 @@ template <int L2> struct Res2Cfg {
     static constexpr int TEAM_BYTES = (2 * PRED + N * N) * 2 + TBW * 4 + (int)sizeof(TeamScratch);
     static constexpr bool TC   = L2 >= 5;                                     // 32/64-point luma (and 32-point chroma) on tcgen05
     static constexpr int TC_BYTES = TC ? (int)sizeof(TcWork<(L2 >= 5 ? L2 : 5)>) + 128 * N * 2 + (L2 == 6 ? 128 * 32 * 2 : 0) : 0;
-    static constexpr int SMEM  = 8192 + TEAMS * TEAM_BYTES + TC_BYTES + (TC ? 128 : 0);
+    static constexpr int SMEM_INT = 8192 + TEAMS * TEAM_BYTES;                  // integer transform only
+    static constexpr int SMEM  = SMEM_INT + TC_BYTES + (TC ? 128 : 0);           // with the tensor-core work area
 };
 
-template <int L2>
+template <int L2, bool USE_TC>
 __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__restrict__ pics, xb200_residue_item *__restrict__ items,
                                                                const int32_t *__restrict__ order, int n,
                                                                const xb200_rates *__restrict__ rates, int16_t *__restrict__ coef,
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
     constexpr int LNMAX = L2 >= 5 ? L2 : 5;
     TcWork<LNMAX> *TCW = nullptr;
     __half        *tmh_y = nullptr, *tmh_c = nullptr;
-    if constexpr(Cf::TC) {
+    if constexpr(Cf::TC && USE_TC) {
         unsigned char *tcb = smem_raw + 8192 + Cf::TEAMS * Cf::TEAM_BYTES;
         tcb += (128 - (smem_u32(tcb) & 127)) & 127;
         TCW   = reinterpret_cast<TcWork<LNMAX> *>(tcb);
@@ -481,12 +482,12 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
         const int rs = it->run_stats, st = it->slice_type;
         int     nnz[3];
         int64_t dp[3], dr[3];
-        residue_plane<L2, T, LNMAX>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec + oo, rs & 1,
+        residue_plane<L2, T, LNMAX, USE_TC>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec + oo, rs & 1,
                                     it->qp[0], it->lambda[0], 0, st, rt, sq, tt, X, nnz[0], dp[0], dr[0], TCW, tmh_y);
-        residue_plane<L2 - 1, T, LNMAX>(o.p[1] + (ptrdiff_t)(mc.y >> 1) * o.s[1] + (mc.x >> 1), o.s[1], pred + NY, blk, TB, tm, tmT,
+        residue_plane<L2 - 1, T, LNMAX, USE_TC>(o.p[1] + (ptrdiff_t)(mc.y >> 1) * o.s[1] + (mc.x >> 1), o.s[1], pred + NY, blk, TB, tm, tmT,
                                         coef + oo + NY, rec + oo + NY, (rs >> 1) & 1, it->qp[1], it->lambda[1], 1, st, rt, sq, tt, X,
                                         nnz[1], dp[1], dr[1], tmh_c ? TCW : nullptr, tmh_c);
-        residue_plane<L2 - 1, T, LNMAX>(o.p[2] + (ptrdiff_t)(mc.y >> 1) * o.s[2] + (mc.x >> 1), o.s[2], pred + NY + NCH, blk, TB, tm,
+        residue_plane<L2 - 1, T, LNMAX, USE_TC>(o.p[2] + (ptrdiff_t)(mc.y >> 1) * o.s[2] + (mc.x >> 1), o.s[2], pred + NY + NCH, blk, TB, tm,
                                         tmT, coef + oo + NY + NCH, rec + oo + NY + NCH, (rs >> 2) & 1, it->qp[2], it->lambda[2], 2, st,
                                         rt, sq, tt, X, nnz[2], dp[2], dr[2], tmh_c ? TCW : nullptr, tmh_c);
         if(tt == 0) {
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
             for(int c = 0; c < 3; c++) { it->nnz[c] = nnz[c]; it->dist_pred[c] = dp[c]; it->dist_rec[c] = dr[c]; }
         }
     }
-    if constexpr(Cf::TC) tc_teardown<LNMAX>(*TCW, threadIdx.x);
+    if constexpr(Cf::TC && USE_TC) tc_teardown<LNMAX>(*TCW, threadIdx.x);
 }
 
 __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
