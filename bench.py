@@ -30,7 +30,15 @@ sys.path.insert(0, ROOT)
 CLIP, W, H = "1080p", 1920, 1080
 POC, REF_POCS = 8, (0, 16)
 PAN = (3, 1)
-SAMPLE_ROWS = 4  # CTU rows of the bounded CPU sample (of 17)
+SAMPLE_ROWS = 4  # CTU rows of the bounded CPU sample
+PRESET = "fast"
+
+
+def select_workload(name):
+    """1080p fast (BASELINE.json configs[1], the default) or 2160p 10-bit medium (configs[2])."""
+    global CLIP, W, H, PRESET
+    if name == "2160p":
+        CLIP, W, H, PRESET = "2160p10", 3840, 2160, "medium"
 
 
 def frames_for_bench():
@@ -71,7 +79,8 @@ class ClockSampler(threading.Thread):
 def algorithmic_bytes(fw):
     """SURVEY.md 8(d) compulsory HBM traffic of each stage for the units it processes (bytes).
     ME: original luma once + each searched padded reference luma once + one result record per item.
-    residue: per item 3/2*N^2 samples x (org read + R reference reads + coef write + rec write)."""
+    residue: per item 3/2*N^2 samples x (org read + R reference reads + coef write); the per-candidate
+    reconstruction is consumed on chip (SSD) and not stored, as in the reference (xeve_pinter.c:2006-2038)."""
     w, h = fw.w, fw.h
     ref_luma = 2 * (w + 288) * (h + 288)
     n_me = 2 * fw.n_cu
@@ -79,7 +88,7 @@ def algorithmic_bytes(fw):
     me_bi = 2 * fw.side_elems + 2 * ref_luma + fw.n_cu * 16
     bi_org = 2 * w * h + ref_luma + 2 * fw.side_elems
     area = (1 << (2 * fw.l2.astype(np.int64))) * 3 // 2 * 2  # bytes of one Y+U+V block
-    residue = int((area * (1 + 1 + 2)).sum() * 2 + (area * (1 + 2 + 2)).sum())  # L0, L1 (R=1) + BI (R=2)
+    residue = int((area * (1 + 1 + 1)).sum() * 2 + (area * (1 + 2 + 1)).sum())  # L0, L1 (R=1) + BI (R=2); coef out, rec not stored
     return dict(me_uni=me_uni, bi_org=bi_org, me_bi=me_bi, residue=residue)
 
 
@@ -90,25 +99,29 @@ def run_b200(args, rank, world, dist):
 
     dev = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(dev)
-    seq = api.make_seq(W, H, "fast")
+    seq = api.make_seq(W, H, PRESET)
     if world > 1:  # the only exchange the path has: rank 0 broadcasts the sequence header
         from xeve_b200 import dist as xd
         seq = xd.broadcast_seq(seq, dist, device="cuda")
     hp = api.Hotpath(seq, device=dev)
     L, ctx = hp.L, hp.h
     clip, fr = frames_for_bench()
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint16:
+            a = a.view(np.int16)  # torch has no pinned uint16; the bytes are what matters
+        return torch.from_numpy(a).pin_memory()
     refs = []
     for poc in REF_POCS:
         hd = hp.pic_create(padded=True)
-        hp.pic_upload(hd, *fr[poc], 8)
+        hp.pic_upload(hd, *fr[poc], clip.depth)
         refs.append(hd)
     cur = hp.pic_create(padded=False)
     cur_planes = [pin(p) for p in fr[POC]]
     cur_np = [p.numpy() for p in cur_planes]
-    hp.pic_upload(cur, *cur_np, 8)
+    hp.pic_upload(cur, *cur_np, clip.depth)
 
-    fw = FrameWork(W, H, POC, REF_POCS, PAN, cur, refs, seed=rank)
+    fw = FrameWork(W, H, POC, REF_POCS, PAN, cur, refs, seed=rank, me_range=int(seq["me_range"][0]))
     cnt = fw.counts()
     # ---- warm-up pass through the host-buffer API; also builds the dependent work lists ----------------
     me_uni = hp.me(fw.me_uni)
@@ -116,7 +129,7 @@ def run_b200(args, rank, world, dist):
     side = hp.bi_org(bi_mc, fw.bi_cur, fw.side_off, fw.side_elems)
     me_bi = hp.me(me_bi_in, side)
     res_in = fw.build_residue(me_bi)
-    res_out, coef, rec = hp.residue(res_in, fw.rates, fw.res_elems)
+    res_out, coef, _ = hp.residue(res_in, fw.rates, fw.res_elems, want_rec=False)
     checksum = int(res_out["dist_rec"].sum() % (1 << 31))
 
     # ---- device-resident buffers -----------------------------------------------------------------------------
@@ -125,7 +138,6 @@ def run_b200(args, rank, world, dist):
     d_me_bi, d_res, d_rates = dv(me_bi_in), dv(res_in), dv(fw.rates)
     d_side = torch.zeros(fw.side_elems, dtype=torch.int16, device="cuda")
     d_coef = torch.zeros(fw.res_elems, dtype=torch.int16, device="cuda")
-    d_rec = torch.zeros(fw.res_elems, dtype=torch.int16, device="cuda")
     P = lambda t: C.c_void_p(t.data_ptr())
     stage_ms = {k: 0.0 for k in ("me_uni", "bi_org", "me_bi", "residue")}
 
@@ -134,7 +146,7 @@ def run_b200(args, rank, world, dist):
             ("me_uni", lambda: L.xb200_me(ctx, P(d_me_uni), cnt["me_uni"], None, 0, api.MEM_DEVICE)),
             ("bi_org", lambda: L.xb200_bi_org(ctx, P(d_bi_mc), cnt["bi_org"], P(d_bi_cur), P(d_side_off), P(d_side), fw.side_elems, api.MEM_DEVICE)),
             ("me_bi", lambda: L.xb200_me(ctx, P(d_me_bi), cnt["me_bi"], P(d_side), fw.side_elems, api.MEM_DEVICE)),
-            ("residue", lambda: L.xb200_residue(ctx, P(d_res), cnt["residue"], P(d_rates), 1, P(d_coef), P(d_rec), fw.res_elems, api.MEM_DEVICE)),
+            ("residue", lambda: L.xb200_residue(ctx, P(d_res), cnt["residue"], P(d_rates), 1, P(d_coef), None, fw.res_elems, api.MEM_DEVICE)),
         ):
             r = call()
             if r != 0:
@@ -150,11 +162,15 @@ def run_b200(args, rank, world, dist):
     sampler = ClockSampler(dev)
     sampler.start()
     launches0 = hp.launches
-    t0 = time.perf_counter()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    t_dev = 0.0
     for _ in range(args.steps):
+        flush.fill_(1)  # evict the 126 MB L2 between timed steps (outside the timed region)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         step_device(True)
-    torch.cuda.synchronize()
-    t_dev = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        t_dev += time.perf_counter() - t0
     launches = hp.launches - launches0
     sampler.stop_flag = True
     # results of the device-resident run equal the host-buffer run
@@ -164,18 +180,19 @@ def run_b200(args, rank, world, dist):
     # ---- e2e: the same calls with host (pinned) buffers, picture upload included ----------------------------
     h_me_uni, h_me_bi, h_res = pin(fw.me_uni.view(np.uint8)), pin(me_bi_in.view(np.uint8)), pin(res_in.view(np.uint8))
     h_side = pin(np.zeros(fw.side_elems, np.int16))
-    h_coef, h_rec = pin(np.zeros(fw.res_elems, np.int16)), pin(np.zeros(fw.res_elems, np.int16))
+    h_coef = pin(np.zeros(fw.res_elems, np.int16))
     HP = lambda t: C.c_void_p(t.data_ptr())
     planes = (C.c_void_p * 3)(*[p.data_ptr() for p in cur_planes])
-    strides = (C.c_int32 * 3)(W, W // 2, W // 2)
+    bps = 2 if clip.depth > 8 else 1
+    strides = (C.c_int32 * 3)(W * bps, W // 2 * bps, W // 2 * bps)
 
     def step_host():
-        rr = [L.xb200_pic_upload(ctx, cur, planes, strides, 8, api.MEM_HOST),
+        rr = [L.xb200_pic_upload(ctx, cur, planes, strides, clip.depth, api.MEM_HOST),
               L.xb200_me(ctx, HP(h_me_uni), cnt["me_uni"], None, 0, api.MEM_HOST),
               L.xb200_bi_org(ctx, bi_mc.ctypes.data_as(C.c_void_p), cnt["bi_org"], fw.bi_cur.ctypes.data_as(C.c_void_p),
                              fw.side_off.ctypes.data_as(C.c_void_p), HP(h_side), fw.side_elems, api.MEM_HOST),
               L.xb200_me(ctx, HP(h_me_bi), cnt["me_bi"], HP(h_side), fw.side_elems, api.MEM_HOST),
-              L.xb200_residue(ctx, HP(h_res), cnt["residue"], fw.rates.ctypes.data_as(C.c_void_p), 1, HP(h_coef), HP(h_rec),
+              L.xb200_residue(ctx, HP(h_res), cnt["residue"], fw.rates.ctypes.data_as(C.c_void_p), 1, HP(h_coef), None,
                               fw.res_elems, api.MEM_HOST)]
         if any(rr):
             raise RuntimeError(f"e2e step failed: {rr}")
@@ -190,10 +207,10 @@ def run_b200(args, rank, world, dist):
         step_host()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    frame_bytes = W * H * 3 // 2
+    frame_bytes = W * H * 3 // 2 * bps
     h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
         + res_in.nbytes + fw.rates.nbytes
-    d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + 2 * 2 * fw.res_elems
+    d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + 2 * fw.res_elems
 
     if world > 1:
         t_dev, t_e2e = xd.max_over_ranks([t_dev, t_e2e], dist, device="cuda")
@@ -206,24 +223,28 @@ def run_b200(args, rank, world, dist):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg = algorithmic_bytes(fw)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic = json.load(open(tpath)).get(f"{CLIP}", {})
     per_stage = {k: v / args.steps for k, v in stage_ms.items()}
     dom = max(per_stage, key=per_stage.get)
     achieved = alg[dom] / (per_stage[dom] * 1e-3) / 1e9
     out = {
-        "metric": "encoded fps (1080p, preset fast): inter-search + transform hot path of one B picture", "value": round(value, 3),
+        "metric": f"encoded fps ({CLIP}, preset {PRESET}): inter-search + transform hot path of one B picture", "value": round(value, 3),
         "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16 samples, s32/s64 arithmetic", "data": "synthetic",
-        "config": {"workload": "1080p B picture (POC 8 <- POC 0/16), Baseline preset fast, full 64/32/16/8 quad-tree: "
+        "config": {"workload": f"{W}x{H} B picture (POC 8 <- POC 0/16), Baseline preset {PRESET}, full 64/32/16/8 quad-tree: "
                                f"{cnt['me_uni']} uni ME + {cnt['me_bi']} bi ME + {cnt['bi_org']} bi_org + {cnt['residue']} residue items per frame",
-                   "clip": "seeded synthetic 1920x1080 8-bit (xeve_b200/clips.py)", "mvp": "synthetic (true motion + jitter)",
+                   "clip": f"seeded synthetic {W}x{H} {clip.depth}-bit (xeve_b200/clips.py)", "mvp": "synthetic (true motion + jitter)",
                    "parallelism": f"{world} independent picture streams (one per GPU), header broadcast only",
-                   "l2": "no explicit flush: each step writes 2 x %.0f MB of coef/rec, more than the 126 MB L2" % (2 * fw.res_elems / 1e6)},
+                   "l2": "L2 flushed (256 MB write) before every timed step" },
         "e2e": {"value": round(e2e_val, 3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: round(v, 3) for k, v in per_stage.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 5), "traffic": None,
+                     "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get(dom),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": int(alg[dom]),
                      "note": "integer ALU / shared-memory bound, not HBM bound: see DESIGN.md section 5"},
@@ -245,11 +266,13 @@ def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
     if not rh.available():
         return {"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present on this machine"}
     clip, fr = frames_for_bench()
-    seq = api.make_seq(W, H, "fast")
-    keep, planes = padded_planes_struct(fr, [REF_POCS[0], REF_POCS[1], POC])
-    fw = FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], rows=sample_rows)
+    seq = api.make_seq(W, H, PRESET)
+    keep, planes = padded_planes_struct(fr, [REF_POCS[0], REF_POCS[1], POC], clip.depth)
+    mr = int(seq["me_range"][0])
+    fw = FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], rows=sample_rows, me_range=mr)
     cores = os.cpu_count() or 1
-    frac = fw.n_cu / FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1]).n_cu
+    frac = fw.n_cu / FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], me_range=mr).n_cu
+    rows_total = (H + 63) // 64
     steps = steps or args.steps
     times = []
     for it in range(args.warmup and 1 or 0, steps + 1):
@@ -258,7 +281,7 @@ def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
         bi_mc, me_bi_in = fw.build_bi(me_uni.astype(api.ME_ITEM))
         pred, off, s2 = rh.replay_mc_raw(seq, planes, bi_mc.astype(rh.MC_REC), cores)
         side = np.zeros(fw.side_elems, np.int16)  # get_org_bi (untimed bookkeeping, trivial next to the search)
-        cy = to_internal10(fr[POC][0], 8)
+        cy = to_internal10(fr[POC][0], clip.depth)
         for i in range(fw.n_cu):
             s = 1 << int(fw.l2[i])
             blk = cy[fw.y[i]:fw.y[i] + s, fw.x[i]:fw.x[i] + s].astype(np.int32) * 2 - pred[off[i]:off[i] + s * s].reshape(s, s)
@@ -271,14 +294,14 @@ def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
         _ = time.perf_counter() - t0
     sec = float(np.mean(times)) / frac  # scaled to a whole picture
     value = 1.0 / sec
-    out = {"impl": "reference", "metric": "encoded fps (1080p, preset fast): inter-search + transform hot path of one B picture",
+    out = {"impl": "reference", "metric": f"encoded fps ({CLIP}, preset {PRESET}): inter-search + transform hot path of one B picture",
            "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
            "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "s16 samples, s32/s64 arithmetic", "data": "synthetic",
-           "config": {"workload": "same 1080p B-picture work lists as the b200 arm", "sample": f"first {sample_rows} of 17 CTU rows "
+           "config": {"workload": f"same {W}x{H} B-picture work lists as the b200 arm", "sample": f"first {sample_rows} of {rows_total} CTU rows "
                       f"({fw.n_cu} CUs = {frac:.3f} of the picture), time scaled to the whole picture"},
            "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
-                            "sample": f"{sample_rows}/17 CTU rows, reference AVX2 functions replayed on {cores} host threads"},
+                            "sample": f"{sample_rows}/{rows_total} CTU rows, reference AVX2 functions replayed on {cores} host threads"},
            "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return out
 
@@ -289,7 +312,7 @@ import types  # noqa: E402
 _ts = types.ModuleType("tests_support")
 
 
-def _padded_planes_struct(fr, pocs):
+def _padded_planes_struct(fr, pocs, depth=8):
     """Internal-depth, edge-padded copies of frames + a ctypes PLANES array for the reference harness."""
     from oracle import refharness as rh
     from xeve_b200.clips import to_internal10
@@ -298,7 +321,7 @@ def _padded_planes_struct(fr, pocs):
         bufs = []
         for k, p in enumerate(fr[poc]):
             pad = 144 if k == 0 else 72
-            bufs.append(np.ascontiguousarray(np.pad(to_internal10(p, 8), pad, mode="edge")))
+            bufs.append(np.ascontiguousarray(np.pad(to_internal10(p, depth), pad, mode="edge")))
         keep.append(bufs)
         arr[i].y = bufs[0].ctypes.data + 2 * (144 * bufs[0].shape[1] + 144)
         arr[i].u = bufs[1].ctypes.data + 2 * (72 * bufs[1].shape[1] + 72)
@@ -317,7 +340,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p fast (default, BASELINE configs[1]) or 2160p 10-bit medium")
     args = ap.parse_args()
+    select_workload(args.workload)
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     if args.impl == "reference":

@@ -12,7 +12,8 @@
  *   -----------------------  ---------------------------------------------------------------
  *   xb200_pic_upload         xeve_imgb_cpy bit-depth convert (src_base/xeve_util.c:1552-1704)
  *                            + xeve_picbuf_expand padding     (src_base/xeve_util.c:190-248)
- *   xb200_sad / ssd / diff   xeve_func_sad/ssd/diff[log2w][log2h] (src_base/xeve_sad.h:40-68)
+ *   xb200_sad / xb200_ssd    xeve_func_sad/ssd[log2w][log2h] (src_base/xeve_sad.h:40-68); xeve_func_diff
+ *                            is fused into xb200_residue
  *   xb200_satd               xeve_func_satd[0] = xeve_had     (src_base/xeve_sad.c:1043-1140)
  *   xb200_me                 pi->fn_me = pinter_me_epzs        (src_base/xeve_pinter.c:699-869,
  *                            hook declared src_base/xeve_type.h:448)
@@ -209,6 +210,8 @@ XB200_API int xb200_itdq(xb200_ctx *c, const xb200_tq_item *items, int64_t n, in
 /* rec = clip(pred + resi) per plane where nnz != 0, else clip(pred) (fn_recon) */
 XB200_API int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16_t *resi, const int16_t *pred,
                           int16_t *rec, int64_t elems, int mem);
+/* rec may be NULL: the per-candidate reconstruction is then only used for dist_rec and not stored -- the
+ * reference itself recomputes the reconstruction of the winning mode (src_base/xeve_pinter.c:2006-2038). */
 XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates,
                             int64_t n_rates, int16_t *coef, int16_t *rec, int64_t elems, int mem);
 

@@ -272,11 +272,11 @@ class Hotpath:
         self._ck(self.L.xb200_recon(self.h, _p(items), len(items), _p(resi), _p(pred), _p(rec), len(resi), MEM_HOST), "xb200_recon")
         return rec
 
-    def residue(self, items, rates, elems):
+    def residue(self, items, rates, elems, want_rec=True):
         items = np.ascontiguousarray(items, RESIDUE_ITEM).copy()
         rates = np.ascontiguousarray(rates, RATES)
         coef = np.zeros(elems, np.int16)
-        rec = np.zeros(elems, np.int16)
+        rec = np.zeros(elems, np.int16) if want_rec else None
         self._ck(self.L.xb200_residue(self.h, _p(items), len(items), _p(rates), len(rates), _p(coef), _p(rec), elems, MEM_HOST),
                  "xb200_residue")
         return items, coef, rec

@@ -765,7 +765,7 @@ int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16
 int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
                   int16_t *rec, int64_t elems, int mem)
 {
-    if(!c || n < 0 || (n && (!items || !coef || !rec || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    if(!c || n < 0 || (n && (!items || !coef || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     if(mem == XB200_MEM_HOST)
         for(int64_t i = 0; i < n; i++) {
@@ -787,9 +787,11 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
     if((r = to_dev(c, c->b_aux0, rates, (size_t)n_rates, mem, &d_rates))) return r;
     if(mem == XB200_MEM_HOST) {
         if((r = ensure(c->b_aux1, (size_t)elems * 2 + 64))) return r;
-        if((r = ensure(c->b_aux2, (size_t)elems * 2 + 64))) return r;
         d_coef = static_cast<int16_t *>(c->b_aux1.p);
-        d_rec  = static_cast<int16_t *>(c->b_aux2.p);
+        if(rec) {
+            if((r = ensure(c->b_aux2, (size_t)elems * 2 + 64))) return r;
+            d_rec = static_cast<int16_t *>(c->b_aux2.p);
+        }
     }
     if((r = ensure(c->b_order, sizeof(int32_t) * 4 * (size_t)n))) return r;
     int32_t *order = static_cast<int32_t *>(c->b_order.p);
@@ -810,7 +812,7 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
     if((r = to_host(c, coef, d_coef, (size_t)elems, mem))) return r;
-    if((r = to_host(c, rec, d_rec, (size_t)elems, mem))) return r;
+    if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, mem))) return r;
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);

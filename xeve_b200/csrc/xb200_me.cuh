@@ -27,6 +27,12 @@
 
 #define ME_THREADS 128
 #define ME_MAX_CAND 160
+#ifndef ME_ISSUE_SINGLE
+#define ME_ISSUE_SINGLE 0
+#endif
+#ifndef ME_LAZY
+#define ME_LAZY 1
+#endif
 
 template <int L2> struct MeGeom {
     static constexpr int W     = 1 << L2;
@@ -199,6 +205,16 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
             rows = (win_cap_elems - 8) / pitch;
         }
         me_team_sync<T>(); // every reader of the previous window is done
+#if ME_ISSUE_SINGLE
+        if(tid == 0) { // one elected thread drives the copy engine: the row loop stays in uniform registers
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(bar, (uint32_t)(pitch * rows * 2));
+            const int16_t *src = refy + (ptrdiff_t)ny0 * sref + ax0;
+            int16_t       *dst = win;
+#pragma unroll 4
+            for(int r = 0; r < rows; r++, src += sref, dst += pitch) bulk_g2s(dst, src, (uint32_t)(pitch * 2), bar);
+        }
+#else
         if(tid < 32) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if(tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(pitch * rows * 2));
@@ -206,6 +222,7 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
             for(int r = lane; r < rows; r += 32)
                 bulk_g2s(win + r * pitch, refy + (ptrdiff_t)(ny0 + r) * sref + ax0, (uint32_t)(pitch * 2), bar);
         }
+#endif
         mbar_wait(bar, phase);
         phase ^= 1;
         wn.x0 = ax0; wn.y0 = ny0; wn.pitch = pitch; wn.rows = rows; wn.staged = 1; wn.biased = 0;
@@ -242,8 +259,8 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
     };
     // batch evaluation: costs[i] = MV cost + SAD for every table entry that lies inside the clip range and the
     // staged window (anything else can never be in range and stays UINT32_MAX)
-    auto eval_table = [&](int c0x, int c0y, int ntab) {
-        for(int c = grp; c < ntab; c += Gm::NG) {
+    auto eval_table = [&](int c0x, int c0y, int from, int ntab) {
+        for(int c = from + grp; c < ntab; c += Gm::NG) {
             int dx, dy;
             cand_off(c, dx, dy);
             const int  px = c0x + dx, py = c0y + dy, ox = px - wn.x0, oy = py - wn.y0;
@@ -283,7 +300,10 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
     // one me_ipel_diamond run (start position already clipped by the caller's ensure_window)
     auto diamond = [&](int sx, int sy, int patience, int &bx, int &by, int &found_step, int &best_bits) -> uint32_t {
         const int c0x = clip3i(sq.min_clip[0], sq.max_clip[0], sx), c0y = clip3i(sq.min_clip[1], sq.max_clip[1], sy);
-        eval_table(c0x, c0y, n_tab);
+        // the table is evaluated lazily in three batches (window + step 4 | steps 8, 16 | the rest): most runs end
+        // after the first or second batch (not_found_best early exit)
+        int done = ME_LAZY ? min(n_tab, NW + 5) : n_tab;
+        eval_table(c0x, c0y, 0, done);
         bx = c0x; by = c0y;
         uint32_t best_cost = 0xffffffffu;
         int      misses = 0, step = 0, tab = 0;
@@ -303,6 +323,11 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
             else {
                 const int cnt = step == 4 ? 5 : (step == 8 ? 9 : 16);
                 a = tab;
+                if(a + cnt > done && a + cnt <= n_tab) {
+                    const int upto = (done < NW + 30) ? min(n_tab, NW + 30) : n_tab;
+                    eval_table(c0x, c0y, done, upto);
+                    done = upto;
+                }
                 k = (a + cnt <= n_tab) ? round_min(a, a + cnt, c0x, c0y, -32768, 32767, -32768, 32767) : ~0ull;
                 this_step = step;
                 tab += cnt;
@@ -453,7 +478,7 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
         const int iy = clip3i(sq.min_clip[1], sq.max_clip[1], ((int16_t)(mv_y + (y << 2))) >> 2);
         ensure_window(ix, iy, WR + 1);
         set_bias(1);
-        eval_table(ix, iy, NW);
+        eval_table(ix, iy, 0, NW);
         // reference order: (0,0) (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)  [dx first]
         uint32_t rb = 0xffffffffu;
         int      rx = ix, ry = iy, rbits = 0;

@@ -407,13 +407,13 @@ XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t
         for(int e = tt; e < nn; e += T) {
             const int16_t t = (int16_t)(blk[e] + pr[e]);
             const int     v = clip3i(0, maxv, t);
-            grec[e]         = (int16_t)v;
+            if(grec) grec[e] = (int16_t)v;
             const int d     = v - (int)org[(ptrdiff_t)(e >> LN) * so + (e & (N - 1))];
             rpart += (d * d) >> sh;
         }
         dist_rec = team_sum_s64<T>(rpart, tt, X);
     }
-    else {
+    else if(grec) {
         for(int e = tt; e < nn; e += T) grec[e] = (int16_t)clip3i(0, maxv, pr[e]);
     }
     team_sync<T>();
@@ -482,13 +482,13 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
         const int rs = it->run_stats, st = it->slice_type;
         int     nnz[3];
         int64_t dp[3], dr[3];
-        residue_plane<L2, T, LNMAX, USE_TC>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec + oo, rs & 1,
+        residue_plane<L2, T, LNMAX, USE_TC>(o.p[0] + (ptrdiff_t)mc.y * o.s[0] + mc.x, o.s[0], pred, blk, TB, tm, tmT, coef + oo, rec ? rec + oo : nullptr, rs & 1,
                                     it->qp[0], it->lambda[0], 0, st, rt, sq, tt, X, nnz[0], dp[0], dr[0], TCW, tmh_y);
         residue_plane<L2 - 1, T, LNMAX, USE_TC>(o.p[1] + (ptrdiff_t)(mc.y >> 1) * o.s[1] + (mc.x >> 1), o.s[1], pred + NY, blk, TB, tm, tmT,
-                                        coef + oo + NY, rec + oo + NY, (rs >> 1) & 1, it->qp[1], it->lambda[1], 1, st, rt, sq, tt, X,
+                                        coef + oo + NY, rec ? rec + oo + NY : nullptr, (rs >> 1) & 1, it->qp[1], it->lambda[1], 1, st, rt, sq, tt, X,
                                         nnz[1], dp[1], dr[1], tmh_c ? TCW : nullptr, tmh_c);
         residue_plane<L2 - 1, T, LNMAX, USE_TC>(o.p[2] + (ptrdiff_t)(mc.y >> 1) * o.s[2] + (mc.x >> 1), o.s[2], pred + NY + NCH, blk, TB, tm,
-                                        tmT, coef + oo + NY + NCH, rec + oo + NY + NCH, (rs >> 2) & 1, it->qp[2], it->lambda[2], 2, st,
+                                        tmT, coef + oo + NY + NCH, rec ? rec + oo + NY + NCH : nullptr, (rs >> 2) & 1, it->qp[2], it->lambda[2], 2, st,
                                         rt, sq, tt, X, nnz[2], dp[2], dr[2], tmh_c ? TCW : nullptr, tmh_c);
         if(tt == 0) {
 #pragma unroll
