@@ -154,13 +154,13 @@ def run_b200(args, rank, world, dist):
             if accumulate:
                 stage_ms[name] += hp.last_kernel_ms
 
+    sampler = ClockSampler(dev)
+    sampler.start()  # samples clocks / throttle reasons from the warm-up through the timed regions
     for _ in range(args.warmup):
         step_device(False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(dev)
-    sampler.start()
     launches0 = hp.launches
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     t_dev = 0.0
@@ -172,7 +172,6 @@ def run_b200(args, rank, world, dist):
         torch.cuda.synchronize()
         t_dev += time.perf_counter() - t0
     launches = hp.launches - launches0
-    sampler.stop_flag = True
     # results of the device-resident run equal the host-buffer run
     got = np.frombuffer(d_res.cpu().numpy().tobytes(), api.RESIDUE_ITEM)
     assert int(got["dist_rec"].sum() % (1 << 31)) == checksum, "device-resident run disagrees with host-buffer run"
@@ -207,6 +206,7 @@ def run_b200(args, rank, world, dist):
         step_host()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    sampler.stop_flag = True
     frame_bytes = W * H * 3 // 2 * bps
     h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
         + res_in.nbytes + fw.rates.nbytes
