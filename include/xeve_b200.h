@@ -161,6 +161,27 @@ typedef struct {
     uint8_t plane1, plane2, log2w, log2h;
 } xb200_blk_item;
 
+/* MV-predictor inputs of one CU: xeve_get_avail_inter (src_base/xeve_util.c:652-715,
+ * single tile), xeve_get_motion (:526-573) for one list, and the temporal-direct MVs of xeve_get_mv_dir
+ * (:619-650).  Maps are SCU-granular (4x4) frame maps as the reference keeps them (ctx->map_scu u32 flags,
+ * ctx->map_mv [f_scu][2][2] s16, the colocated refp[0][lidx].map_mv). */
+typedef struct {
+    int16_t  x_scu, y_scu;
+    uint8_t  log2_cuw, log2_cuh, lidx, pad_;
+    /* results */
+    uint16_t avail;          /* AVAIL_* bit mask (src_base/xeve_def.h:402-425) */
+    int8_t   refi[4];
+    int16_t  mvp[4][2];      /* left, up, up-right (or (1,1)), colocated */
+    int16_t  mv_dir[2][2];   /* xeve_get_mv_dir for the SCU at the CU's bottom-right corner */
+} xb200_mvp_item;
+
+typedef struct {             /* picture-level inputs of xb200_mvp */
+    int32_t w_scu, h_scu;
+    int32_t poc;             /* current picture */
+    int32_t ref_poc[2];      /* refp[0][REFP_0].poc, refp[0][REFP_1].poc */
+    int32_t col_list_poc0;   /* refp[0][REFP_1].list_poc[0] */
+} xb200_mvp_pic;
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 XB200_API int  xb200_create(xb200_ctx **out, int device, const xb200_seq *seq);
 XB200_API void xb200_destroy(xb200_ctx *c);
@@ -192,6 +213,10 @@ XB200_API int xb200_satd(xb200_ctx *c, const xb200_blk_item *items, int64_t n, i
  * tensor cores -- the transform stage of xb200_residue exposed for parity checks against
  * xeve_trans (src_base/xeve_tq.c:396-404).  Host buffers. */
 XB200_API int xb200_fwd_dct_tc(xb200_ctx *c, const int16_t *in, int16_t *out, int64_t n, int log2n);
+
+/* map_scu: u32[f_scu]; map_mv: s16[f_scu][2][2]; col_mv[l]: s16[f_scu][2][2] = refp[0][l].map_mv.  Host buffers. */
+XB200_API int xb200_mvp(xb200_ctx *c, xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pic, const uint32_t *map_scu,
+                        const int16_t *map_mv, const int16_t *col_mv0, const int16_t *col_mv1);
 
 /* ---- hot-path operators ----------------------------------------------------------------------- */
 /* side: s16 buffer holding the org_bi blocks referenced by org_bi_off (may be NULL if none). */

@@ -830,3 +830,40 @@ RH_API double rh_replay_residue(const RH_CONST *cst, const RH_PLANES *planes, co
     return dt;
 }
 RH_API int rh_sizeof_res(void) { return sizeof(RH_RES_REC); }
+
+/* ------------------------------------------------------------------------------------------
+ * MV-predictor probe: the reference's xeve_get_avail_inter / xeve_get_motion / xeve_get_mv_dir on
+ * caller-provided SCU maps (record layout = xb200_mvp_item / xb200_mvp_pic)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int16_t  x_scu, y_scu;
+    uint8_t  log2_cuw, log2_cuh, lidx, pad_;
+    uint16_t avail;
+    int8_t   refi[4];
+    int16_t  mvp[4][2];
+    int16_t  mv_dir[2][2];
+} RH_MVP_REC;
+typedef struct { int32_t w_scu, h_scu, poc, ref_poc[2], col_list_poc0; } RH_MVP_PIC;
+
+RH_API void rh_mvp(RH_MVP_REC *items, int n, const RH_MVP_PIC *pp, u32 *map_scu, s16 (*map_mv)[REFP_NUM][MV_D],
+                   s16 (*col0)[REFP_NUM][MV_D], s16 (*col1)[REFP_NUM][MV_D])
+{
+    XEVE_REFP refp[XEVE_MAX_NUM_REF_PICS][REFP_NUM];
+    memset(refp, 0, sizeof(refp));
+    u32 list_poc[XEVE_MAX_NUM_REF_PICS] = {0};
+    list_poc[0] = pp->col_list_poc0;
+    refp[0][REFP_0].map_mv = col0; refp[0][REFP_0].poc = pp->ref_poc[0];
+    refp[0][REFP_1].map_mv = col1; refp[0][REFP_1].poc = pp->ref_poc[1]; refp[0][REFP_1].list_poc = list_poc;
+    refp[0][REFP_0].list_poc = list_poc;
+    u8 *tidx = calloc((size_t)pp->w_scu * pp->h_scu, 1);
+    for(int i = 0; i < n; i++) {
+        RH_MVP_REC *r = &items[i];
+        int cuw = 1 << r->log2_cuw, cuh = 1 << r->log2_cuh, scup = r->x_scu + r->y_scu * pp->w_scu;
+        r->avail = xeve_get_avail_inter(r->x_scu, r->y_scu, pp->w_scu, pp->h_scu, scup, cuw, cuh, map_scu, tidx);
+        xeve_get_motion(scup, r->lidx, NULL, map_mv, refp, cuw, cuh, pp->w_scu, r->avail, r->refi, r->mvp);
+        xeve_get_mv_dir(refp[0], pp->poc, scup + ((cuw >> 2) - 1) + ((cuh >> 2) - 1) * pp->w_scu, scup, pp->w_scu, pp->h_scu,
+                        r->mv_dir, 0);
+    }
+    free(tidx);
+}
+RH_API int rh_sizeof_mvp(void) { return sizeof(RH_MVP_REC); }

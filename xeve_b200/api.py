@@ -73,6 +73,12 @@ BLK_ITEM = np.dtype([
     ("plane1", "u1"), ("plane2", "u1"), ("log2w", "u1"), ("log2h", "u1"),
 ], align=True)
 
+MVP_ITEM = np.dtype([
+    ("x_scu", "<i2"), ("y_scu", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("lidx", "u1"), ("pad_", "u1"),
+    ("avail", "<u2"), ("refi", "i1", (4,)), ("mvp", "<i2", (4, 2)), ("mv_dir", "<i2", (2, 2)),
+], align=True)
+MVP_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("poc", "<i4"), ("ref_poc", "<i4", (2,)), ("col_list_poc0", "<i4")], align=True)
+
 VP = C.c_void_p
 _lib = None
 
@@ -109,6 +115,7 @@ def load():
         L.xb200_mc.argtypes = [VP, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
         L.xb200_bi_org.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
         L.xb200_fwd_dct_tc.argtypes = [VP, VP, VP, C.c_int64, C.c_int]
+        L.xb200_mvp.argtypes = [VP, VP, C.c_int64, VP, VP, VP, VP, VP]
         L.xb200_tq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_itdq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_recon.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
@@ -119,7 +126,7 @@ def load():
 
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
-           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
+           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
 
 
 def _p(a):
@@ -252,6 +259,13 @@ class Hotpath:
         n = blocks.size >> (2 * log2n)
         self._ck(self.L.xb200_fwd_dct_tc(self.h, _p(blocks), _p(out), n, log2n), "xb200_fwd_dct_tc")
         return out
+
+    def mvp(self, items, pic, map_scu, map_mv, col0, col1):
+        items = np.ascontiguousarray(items, MVP_ITEM).copy()
+        self._ck(self.L.xb200_mvp(self.h, _p(items), len(items), _p(np.ascontiguousarray(pic, MVP_PIC)),
+                                  _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_mv, np.int16)),
+                                  _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16))), "xb200_mvp")
+        return items
 
     def tq(self, items, rates, coef):
         items = np.ascontiguousarray(items, TQ_ITEM).copy()

@@ -520,6 +520,43 @@ int xb200_fwd_dct_tc(xb200_ctx *c, const int16_t *in, int16_t *out, int64_t n, i
     return XB200_OK;
 }
 
+int xb200_mvp(xb200_ctx *c, xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pic, const uint32_t *map_scu, const int16_t *map_mv,
+              const int16_t *col_mv0, const int16_t *col_mv1)
+{
+    if(!c || n < 0 || (n && (!items || !pic || !map_scu || !map_mv || !col_mv0 || !col_mv1)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    if(pic->w_scu <= 0 || pic->h_scu <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    const size_t f = (size_t)pic->w_scu * pic->h_scu;
+    for(int64_t i = 0; i < n; i++) {
+        const xb200_mvp_item &it = items[i];
+        const int sw = (1 << it.log2_cuw) >> 2, sh = (1 << it.log2_cuh) >> 2;
+        if(it.x_scu < 0 || it.y_scu < 0 || it.log2_cuw < 2 || it.log2_cuh < 2 || it.log2_cuw > 7 || it.log2_cuh > 7 || it.lidx > 1 ||
+           it.x_scu + sw > pic->w_scu || it.y_scu + sh > pic->h_scu)
+            return XB200_ERR_INVALID_ARGUMENT;
+    }
+    int r;
+    xb200_mvp_item *d_items;
+    uint32_t       *d_scu;
+    int16_t        *d_mv, *d_c0, *d_c1;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, map_scu, f, XB200_MEM_HOST, &d_scu))) return r;
+    if((r = to_dev(c, c->b_aux1, map_mv, f * 4, XB200_MEM_HOST, &d_mv))) return r;
+    if((r = to_dev(c, c->b_aux2, col_mv0, f * 4, XB200_MEM_HOST, &d_c0))) return r;
+    if((r = to_dev(c, c->b_side, col_mv1, f * 4, XB200_MEM_HOST, &d_c1))) return r;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_mvp<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_items, n, *pic, d_scu, d_mv, d_c0, d_c1);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
 // ---- motion search ------------------------------------------------------------------------------------------
 int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem)
 {

@@ -130,6 +130,63 @@ __global__ void k_satd(const PicDev *__restrict__ pics, const xb200_blk_item *__
     if(lane == 0) out[i] = sum >> (bd - 8);
 }
 
+// ---- MV-predictor inputs ---------------------------------------------------------------------
+// xeve_get_avail_inter (src_base/xeve_util.c:652-715, one tile), xeve_get_motion (:526-573), xeve_get_mv_dir (:619-650)
+__global__ void k_mvp(xb200_mvp_item *__restrict__ items, int64_t n, xb200_mvp_pic pp, const uint32_t *__restrict__ map_scu,
+                      const int16_t *__restrict__ map_mv, const int16_t *__restrict__ col0, const int16_t *__restrict__ col1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    xb200_mvp_item it = items[i];
+    const int x = it.x_scu, y = it.y_scu, w = pp.w_scu, h = pp.h_scu, scuw = (1 << it.log2_cuw) >> 2, scuh = (1 << it.log2_cuh) >> 2;
+    const int scup = x + y * w, l = it.lidx;
+    auto COD = [&](int p) { return (int)((map_scu[p] >> 31) & 1); };
+    auto IF  = [&](int p) { return (int)((map_scu[p] >> 15) & 1); };
+    auto IBC = [&](int p) { return (int)((map_scu[p] >> 26) & 1); };
+    unsigned av = 0;
+    if(x > 0 && !IF(scup - 1) && COD(scup - 1) && !IBC(scup - 1)) {
+        av |= 1u << 1; // AVAIL_LE
+        if(y + scuh < h && COD(scup + scuh * w - 1) && !IF(scup + scuh * w - 1) && !IBC(scup + scuh * w - 1)) av |= 1u << 7; // LO_LE
+    }
+    if(y > 0) {
+        if(!IF(scup - w) && !IBC(scup - w)) av |= 1u << 0;                                   // AVAIL_UP
+        if(!IF(scup - w + scuw - 1) && !IBC(scup - w + scuw - 1)) av |= 1u << 9;             // AVAIL_RI_UP
+        if(x > 0 && !IF(scup - w - 1) && COD(scup - w - 1) && !IBC(scup - w - 1)) av |= 1u << 5; // AVAIL_UP_LE
+        if(x + scuw < w && ((map_scu[scup - w + scuw] >> 15) & 0x10001) == 0x10000 && COD(scup - w + scuw)) av |= 1u << 6; // UP_RI
+    }
+    if(x + scuw < w && !IF(scup + scuw) && COD(scup + scuw) && !IBC(scup + scuw)) {
+        av |= 1u << 3; // AVAIL_RI
+        if(y + scuh < h && COD(scup + scuh * w + scuw) && !IF(scup + scuh * w + scuw) && !IBC(scup + scuh * w + scuw)) av |= 1u << 8;
+    }
+    it.avail = (uint16_t)av;
+    auto mvat = [&](const int16_t *m, int p, int list, int c) { return m[((size_t)p * 2 + list) * 2 + c]; };
+    const int nb[3] = {scup - 1, scup - w, scup - w + scuw};
+    const unsigned need[3] = {1u << 1, 1u << 0, 1u << 6};
+#pragma unroll
+    for(int k = 0; k < 3; k++) {
+        it.refi[k] = 0;
+        const bool ok = (av & need[k]) != 0;
+        it.mvp[k][0] = ok ? mvat(map_mv, nb[k], l, 0) : (int16_t)1;
+        it.mvp[k][1] = ok ? mvat(map_mv, nb[k], l, 1) : (int16_t)1;
+    }
+    const int16_t *col = l ? col1 : col0;
+    it.refi[3] = 0;
+    it.mvp[3][0] = mvat(col, scup, 0, 0);
+    it.mvp[3][1] = mvat(col, scup, 0, 1);
+    // temporal direct: colocated MV of the list-1 reference at the CU's bottom-right SCU, scaled by POC distances
+    {
+        const int br = scup + (scuw - 1) + (scuh - 1) * w;
+        const int mx = mvat(col1, br, 0, 0), my = mvat(col1, br, 0, 1);
+        const int dco = pp.ref_poc[1] - pp.col_list_poc0, d0 = pp.poc - pp.ref_poc[0], d1 = pp.ref_poc[1] - pp.poc;
+        if(dco == 0) { it.mv_dir[0][0] = it.mv_dir[0][1] = it.mv_dir[1][0] = it.mv_dir[1][1] = 0; }
+        else {
+            it.mv_dir[0][0] = (int16_t)(d0 * mx / dco); it.mv_dir[0][1] = (int16_t)(d0 * my / dco);
+            it.mv_dir[1][0] = (int16_t)(-d1 * mx / dco); it.mv_dir[1][1] = (int16_t)(-d1 * my / dco);
+        }
+    }
+    items[i] = it;
+}
+
 // ---- fused residue kernel: prediction -> residual -> SSD -> DCT + RDOQ -> dequant + IDCT -> recon -> SSD
 //      (the distortion/transform body of pinter_residue_rdo, reference src_base/xeve_pinter.c:961-1056)
 struct ResSmem {
