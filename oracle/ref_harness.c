@@ -726,6 +726,7 @@ RH_API double rh_replay_tq(const RH_CONST *cst, const s16 *side, const RH_TQ_REC
     memset(&j, 0, sizeof(j));
     j.cst = cst; j.side = side; j.tq_in = in; j.rates = rates; j.n = n; j.tq_coef = coef_out; j.tq_nnz = nnz_out;
     j.tq_resi = resi_out; j.do_itdq = resi_out != NULL;
+    util_ctx()->param.rdoq = cst->rdoq; /* the utility context follows the traced encode's quantiser choice */
     return run_jobs(&j, tq_worker, nthreads);
 }
 
@@ -815,8 +816,7 @@ RH_API double rh_replay_residue(const RH_CONST *cst, const RH_PLANES *planes, co
                                 s16 *coef, s16 *rec, int nthreads)
 {
     if(nthreads < 1) nthreads = 1;
-    util_ctx();
-    /* the global kernel tables are normally selected when a picture is first encoded */
+    util_ctx()->param.rdoq = cst->rdoq;
     pthread_t *th = malloc(sizeof(pthread_t) * nthreads);
     resjob_t  *jb = malloc(sizeof(resjob_t) * nthreads);
     double     t0 = now_s();

@@ -247,12 +247,15 @@ def _upload_trace(tr):
 
 
 @pytest.mark.skipif(not rh.available(), reason="needs oracle/_ref to trace a live encode")
-@pytest.mark.parametrize("name,preset,frames,override", [
-    ("cif", "medium", 20, dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),           # configs 3/4 search settings
-    ("2160p10", "fast", 18, dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),  # 10-bit input, faster motion
+@pytest.mark.parametrize("name,preset,frames,extra,override", [
+    ("cif", "medium", 20, "", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),           # configs 3/4 search settings
+    ("2160p10", "fast", 18, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),  # 10-bit input, faster motion
+    ("cif", "fast", 20, "me_sub=3;me_sub_pos=8", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # quarter-pel stage (slow preset)
+    ("cif", "fast", 20, "me_sub=1", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),      # integer-pel only: me_ipel_refinement
+    ("cif", "fast", 20, "rdoq=0;qp=27", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # plain quantiser, lower QP
 ])
-def test_me_mc_tq_other_configs(name, preset, frames, override):
-    tr = tracedata.live_trace(name, frames=frames, pic_lo=1, pic_hi=2, preset=preset, **override)
+def test_me_mc_tq_other_configs(name, preset, frames, extra, override):
+    tr = tracedata.live_trace(name, frames=frames, pic_lo=1, pic_hi=2, preset=preset, extra=extra, **override)
     hp = _upload_trace(tr)
     try:
         items = np.ascontiguousarray(tr.me).astype(api.ME_ITEM)
@@ -268,8 +271,9 @@ def test_me_mc_tq_other_configs(name, preset, frames, override):
         tq = np.ascontiguousarray(tr.tq).astype(api.TQ_ITEM)
         it2, coef = hp.tq(tq, tr.rates, tr.tq_coef)
         m = _item_mask(tq, len(coef))
+        assert np.array_equal(nnz_ref, tr.tq["nnz"])  # replay == in situ
         assert np.array_equal(it2["nnz"], nnz_ref) and np.array_equal(coef[m], coef_ref[m])
-        assert int(tr.seq["hpel_cnt"][0]) == (4 if preset == "medium" else 2) and len(tr.me) > 500
+        assert len(tr.me) > 500
     finally:
         hp.close()
 

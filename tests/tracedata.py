@@ -92,9 +92,9 @@ def from_live(tr: "rh.Trace") -> TraceData:
     return td
 
 
-def live_trace(name="cif", frames=30, pic_lo=1, pic_hi=3, preset="fast", mask=7, **override) -> TraceData:
+def live_trace(name="cif", frames=30, pic_lo=1, pic_hi=3, preset="fast", mask=7, extra="", **override) -> TraceData:
     c, yuv = clip_yuv(name, frames, **override)
-    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, trace_mask=mask, pic_lo=pic_lo, pic_hi=pic_hi)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=mask, pic_lo=pic_lo, pic_hi=pic_hi)
     return from_live(tr)
 
 

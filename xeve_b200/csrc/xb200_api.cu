@@ -290,7 +290,6 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     CK(cudaMalloc(&c->d_bins, sizeof(int) * 16));
     CK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_bi_org, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResSmem)));
     CK(cudaFuncSetAttribute(k_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
     CK(cudaFuncSetAttribute(k_itdq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
     *out = c;

@@ -1,4 +1,5 @@
-// xb200_misc.cuh -- picture preparation, distortion probes and the fused residue kernel.
+// xb200_misc.cuh -- picture preparation, distortion probes, MV-predictor inputs.
+// (The fused candidate-evaluation kernel lives in xb200_residue2.cuh.)
 #pragma once
 #include "xb200_common.cuh"
 #include "xb200_mc.cuh"
@@ -185,73 +186,4 @@ __global__ void k_mvp(xb200_mvp_item *__restrict__ items, int64_t n, xb200_mvp_p
         }
     }
     items[i] = it;
-}
-
-// ---- fused residue kernel: prediction -> residual -> SSD -> DCT + RDOQ -> dequant + IDCT -> recon -> SSD
-//      (the distortion/transform body of pinter_residue_rdo, reference src_base/xeve_pinter.c:961-1056)
-struct ResSmem {
-    TqSmem  tq;
-    int16_t pred[6144];
-    int16_t aux[6144];
-};
-
-__global__ void __launch_bounds__(TQ_THREADS) k_residue(const PicDev *__restrict__ pics, xb200_residue_item *__restrict__ items, int n,
-                                                         const xb200_rates *__restrict__ rates, int16_t *__restrict__ coef,
-                                                         int16_t *__restrict__ rec, const int8_t *__restrict__ g_tm64, SeqDev sq)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ResSmem &R = *reinterpret_cast<ResSmem *>(smem_raw);
-    TqSmem  &S = R.tq;
-    const int tid = threadIdx.x;
-    if(blockIdx.x >= n) return;
-    xb200_residue_item *it = &items[blockIdx.x];
-    const xb200_mc_item mc = it->mc;
-    tq_load_tm(S, g_tm64, tid, TQ_THREADS);
-    mc_item(pics, mc, sq, R.pred, R.aux, reinterpret_cast<int16_t *>(S.T), tid, TQ_THREADS);
-
-    const PicDev o = pics[it->cur_pic];
-    const int    w = mc.w, ny = w * mc.h, nc = ny >> 2, maxv = (1 << sq.bd) - 1, sh = (sq.bd - 8) << 1;
-    int          l2y = 0;
-    while((1 << l2y) < w) l2y++;
-    for(int c = 0; c < 3; c++) {
-        const int      l2 = c ? l2y - 1 : l2y, bw = 1 << l2, nn = bw * bw, poff = c == 0 ? 0 : (c == 1 ? ny : ny + nc);
-        const int16_t *org = o.p[c] + (ptrdiff_t)(c ? mc.y >> 1 : mc.y) * o.s[c] + (c ? mc.x >> 1 : mc.x);
-        const int      so = o.s[c];
-        const int16_t *pr = R.pred + poff;
-        int64_t        dpart = 0;
-        for(int e = tid; e < nn; e += TQ_THREADS) {
-            const int d = (int)org[(ptrdiff_t)(e >> l2) * so + (e & (bw - 1))] - (int)pr[e];
-            S.blk[e] = (int16_t)d;
-            dpart += (d * d) >> sh;
-        }
-        const int64_t dist_pred = block_sum_s64(S, dpart, tid, TQ_THREADS);
-        int           nnz = 0;
-        int16_t      *gco = coef + it->out_off + poff, *grec = rec + it->out_off + poff;
-        if((it->run_stats >> c) & 1) {
-            fwd_dct(S, l2, sq.bd, tid, TQ_THREADS);
-            nnz = quant_block(S, l2, it->qp[c], it->lambda[c], 0, c, it->slice_type, &rates[it->rate_idx], sq.bd, sq.rdoq, tid,
-                              TQ_THREADS);
-        }
-        for(int e = tid; e < nn; e += TQ_THREADS) gco[e] = S.blk[e];
-        __syncthreads();
-        int64_t dist_rec = dist_pred;
-        if(nnz) {
-            dequant_block(S, l2, it->qp[c], sq.bd, tid, TQ_THREADS);
-            inv_dct(S, l2, sq.bd, tid, TQ_THREADS);
-            int64_t rpart = 0;
-            for(int e = tid; e < nn; e += TQ_THREADS) {
-                const int16_t t = (int16_t)(S.blk[e] + pr[e]);
-                const int     v = clip3i(0, maxv, t);
-                grec[e]         = (int16_t)v;
-                const int d     = v - (int)org[(ptrdiff_t)(e >> l2) * so + (e & (bw - 1))];
-                rpart += (d * d) >> sh;
-            }
-            dist_rec = block_sum_s64(S, rpart, tid, TQ_THREADS);
-        }
-        else {
-            for(int e = tid; e < nn; e += TQ_THREADS) grec[e] = (int16_t)clip3i(0, maxv, pr[e]);
-        }
-        if(tid == 0) { it->nnz[c] = nnz; it->dist_pred[c] = dist_pred; it->dist_rec[c] = dist_rec; }
-        __syncthreads();
-    }
 }
