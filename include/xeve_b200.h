@@ -182,6 +182,42 @@ typedef struct {             /* picture-level inputs of xb200_mvp */
     int32_t col_list_poc0;   /* refp[0][REFP_1].list_poc[0] */
 } xb200_mvp_pic;
 
+/* ---- device-side rate estimation: CABAC bit counting for inter RDO ------------------------------
+ * The RDO bit count of the reference is the arithmetic coder run in "bitcount" mode after xeve_sbac_bit_reset
+ * (src_base/xeve_mode.c:39-55); it equals the number of renormalisation shifts, so only the coder's range and
+ * the context models matter.  xb200_sbac carries exactly those (models of the Baseline inter syntax, 2-byte
+ * SBAC_CTX_MODEL = state << 1 | mps, src_base/xeve_def.h:727-790). */
+enum {
+    XB200_CM_SKIP_FLAG = 0, XB200_CM_PRED_MODE = 2, XB200_CM_DIRECT = 5, XB200_CM_INTER_DIR = 6, XB200_CM_REFI = 8,
+    XB200_CM_MVP_IDX = 10, XB200_CM_MVD = 13, XB200_CM_CBF_ALL = 14, XB200_CM_CBF_LUMA = 15, XB200_CM_CBF_CB = 16,
+    XB200_CM_CBF_CR = 17, XB200_CM_RUN = 18, XB200_CM_LAST = 42, XB200_CM_LEVEL = 44, XB200_CM_COUNT = 68
+};
+typedef struct {
+    uint32_t range;                  /* XEVE_SBAC::range */
+    uint16_t m[XB200_CM_COUNT];      /* context models, laid out by the XB200_CM_* offsets */
+} xb200_sbac;
+
+/* One RDO bit-count call: SBAC_LOAD(state) -> xeve_sbac_bit_reset -> syntax -> xeve_get_bit_number.
+ * kind 0: xeve_rdo_bit_cnt_cu_skip (src_base/xeve_mode.c:283-302)      kind 1: xeve_rdo_bit_cnt_cu_inter (:185-281)
+ * kind 2: xeve_rdo_bit_cnt_mvp (:57-77, mvp_idx[0] used for both lists)  kind 3: xeve_rdo_bit_cnt_cu_inter_comp (:160-183) */
+typedef struct {
+    uint8_t  kind, slice_type, log2_cuw, log2_cuh;
+    uint8_t  pidx;                   /* PRED_L0 0, PRED_L1 1, PRED_BI 2, PRED_SKIP 3, PRED_DIR 4 */
+    uint8_t  ch;                     /* kind 3: component */
+    uint8_t  ctx_skip, ctx_pred_mode;/* core->ctx_flags[CNID_SKIP_FLAG], [CNID_PRED_MODE] */
+    int8_t   refi[2];
+    uint8_t  mvp_idx[2];
+    uint8_t  num_refp[2];
+    uint8_t  all_preds, pad_;        /* xeve_check_all_preds(core->tree_cons) */
+    int16_t  mvd[2][2];
+    int32_t  nnz[3];                 /* core->nnz_sub[c][0] */
+    int32_t  state_in;               /* index of the input coder state */
+    int32_t  state_out;              /* index where the coder state after the call is stored, -1: discard */
+    int64_t  coef_off;               /* element offset of the coefficient planes (Y | U | V), kinds 1 and 3 */
+    uint32_t bits;                   /* result: xeve_get_bit_number */
+    uint32_t pad2_;
+} xb200_bits_item;
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 XB200_API int  xb200_create(xb200_ctx **out, int device, const xb200_seq *seq);
 XB200_API void xb200_destroy(xb200_ctx *c);
@@ -217,6 +253,13 @@ XB200_API int xb200_fwd_dct_tc(xb200_ctx *c, const int16_t *in, int16_t *out, in
 /* map_scu: u32[f_scu]; map_mv: s16[f_scu][2][2]; col_mv[l]: s16[f_scu][2][2] = refp[0][l].map_mv.  Host buffers. */
 XB200_API int xb200_mvp(xb200_ctx *c, xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pic, const uint32_t *map_scu,
                         const int16_t *map_mv, const int16_t *col_mv0, const int16_t *col_mv1);
+
+/* states: in/out array of coder states (entries named by state_out are written); coef: s16 buffer.  Host buffers. */
+XB200_API int xb200_rdo_bits(xb200_ctx *c, xb200_bits_item *items, int64_t n, xb200_sbac *states, int64_t n_states,
+                             const int16_t *coef, int64_t coef_elems);
+/* xeve_rdoq_bit_est (src_base/xeve_mode.c:304-373): RDOQ rate tables of n coder states (fields not used by the
+ * Baseline RDOQ -- sig_coeff, gtx, last_sig_coeff -- are not produced) */
+XB200_API int xb200_rdoq_rates(xb200_ctx *c, const xb200_sbac *states, int64_t n, xb200_rates *rates);
 
 /* ---- hot-path operators ----------------------------------------------------------------------- */
 /* side: s16 buffer holding the org_bi blocks referenced by org_bi_off (may be NULL if none). */

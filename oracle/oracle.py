@@ -103,3 +103,17 @@ def residue_batch(seq, planes, rates, items, elems):
     rec = np.zeros(elems, np.int16)
     lib().xo_residue_batch(_p(seq), C.addressof(planes), _p(rates), _p(items), len(items), _p(coef), _p(rec))
     return items, coef, rec
+
+
+def rdo_bits_batch(items, states, coef):
+    items, states = items.copy(), states.copy()
+    coef = np.ascontiguousarray(coef, np.int16)
+    lib().xo_rdo_bits_batch(_p(items), len(items), _p(states), _p(coef))
+    return items, states
+
+
+def rdoq_rates(states, rates_dtype):
+    states = np.ascontiguousarray(states)
+    out = np.zeros(len(states), rates_dtype)
+    lib().xo_rdoq_rates(_p(states), len(states), _p(out))
+    return out

@@ -103,6 +103,9 @@ typedef struct {
 /* ------------------------------------------------------------------------------------------
  * growable buffers
  * ---------------------------------------------------------------------------------------- */
+typedef struct { uint32_t range; uint16_t m[68]; } RH_SBAC;
+static void sbac_pack(const XEVE_SBAC *d, RH_SBAC *s);
+static void sbac_unpack(const RH_SBAC *s, XEVE_SBAC *d);
 typedef struct { void *p; size_t n, cap, esz; } vec_t;
 static void *vec_push(vec_t *v, size_t cnt)
 {
@@ -138,7 +141,8 @@ static struct {
     void (*org_mc)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, s8 *, s16 (*)[MV_D], XEVE_REFP (*)[REFP_NUM],
                    pel (*)[N_C][MAX_CU_DIM], int, int, s16 (*)[REFP_NUM][MV_D]);
     int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int);
-    vec_t    me, mc, tq, rates, pics, samp; /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
+    vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
+    /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
     RH_CONST cst;
     RH_RATES last_rates;
     int      have_rates;
@@ -262,6 +266,7 @@ static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], in
     grab_rates(core, &cur);
     if(!T.have_rates || memcmp(&cur, &T.last_rates, sizeof(cur))) {
         *(RH_RATES *)vec_push(&T.rates, 1) = cur;
+        sbac_pack(&core->s_curr_best[log2_cuw - 2][log2_cuh - 2], (RH_SBAC *)vec_push(&T.sbac, 1));
         T.last_rates = cur;
         T.have_rates = 1;
     }
@@ -337,7 +342,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     XEVE_CTX *ctx = (XEVE_CTX *)id;
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
-    vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16));
+    vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC));
     T.have_rates = 0;
     T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
     if(trace_mask) {
@@ -410,7 +415,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 RH_API int64_t rh_trace_get(int what, void **ptr)
 {
     vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
-             : what == 4 ? &T.pics : &T.samp;
+             : what == 4 ? &T.pics : what == 5 ? &T.samp : &T.sbac;
     *ptr = v->p;
     return (int64_t)v->n;
 }
@@ -867,3 +872,86 @@ RH_API void rh_mvp(RH_MVP_REC *items, int n, const RH_MVP_PIC *pp, u32 *map_scu,
     free(tidx);
 }
 RH_API int rh_sizeof_mvp(void) { return sizeof(RH_MVP_REC); }
+
+/* ------------------------------------------------------------------------------------------
+ * RDO bit counting probes: the reference's xeve_rdo_bit_cnt_* on a scratch core, exactly the
+ * SBAC_LOAD -> xeve_sbac_bit_reset -> count -> xeve_get_bit_number sequence of xeve_pinter.c
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint8_t  kind, slice_type, log2_cuw, log2_cuh, pidx, ch, ctx_skip, ctx_pred_mode;
+    int8_t   refi[2];
+    uint8_t  mvp_idx[2], num_refp[2], all_preds, pad_;
+    int16_t  mvd[2][2];
+    int32_t  nnz[3], state_in, state_out;
+    int64_t  coef_off;
+    uint32_t bits, pad2_;
+} RH_BITS_REC;
+
+static void sbac_unpack(const RH_SBAC *s, XEVE_SBAC *d)
+{
+    XEVE_SBAC_CTX *c = &d->ctx;
+    d->range = s->range;
+    memcpy(c->skip_flag, s->m + 0, 4); memcpy(c->pred_mode, s->m + 2, 6); memcpy(c->direct_mode_flag, s->m + 5, 2);
+    memcpy(c->inter_dir, s->m + 6, 4); memcpy(c->refi, s->m + 8, 4); memcpy(c->mvp_idx, s->m + 10, 6);
+    memcpy(c->mvd, s->m + 13, 2); memcpy(c->cbf_all, s->m + 14, 2); memcpy(c->cbf_luma, s->m + 15, 2);
+    memcpy(c->cbf_cb, s->m + 16, 2); memcpy(c->cbf_cr, s->m + 17, 2); memcpy(c->run, s->m + 18, 48);
+    memcpy(c->last, s->m + 42, 4); memcpy(c->level, s->m + 44, 48);
+}
+static void sbac_pack(const XEVE_SBAC *d, RH_SBAC *s)
+{
+    const XEVE_SBAC_CTX *c = &d->ctx;
+    s->range = d->range;
+    memcpy(s->m + 0, c->skip_flag, 4); memcpy(s->m + 2, c->pred_mode, 6); memcpy(s->m + 5, c->direct_mode_flag, 2);
+    memcpy(s->m + 6, c->inter_dir, 4); memcpy(s->m + 8, c->refi, 4); memcpy(s->m + 10, c->mvp_idx, 6);
+    memcpy(s->m + 13, c->mvd, 2); memcpy(s->m + 14, c->cbf_all, 2); memcpy(s->m + 15, c->cbf_luma, 2);
+    memcpy(s->m + 16, c->cbf_cb, 2); memcpy(s->m + 17, c->cbf_cr, 2); memcpy(s->m + 18, c->run, 48);
+    memcpy(s->m + 42, c->last, 4); memcpy(s->m + 44, c->level, 48);
+}
+
+RH_API int rh_rdo_bits(RH_BITS_REC *items, int n, RH_SBAC *states, const s16 *coef_buf)
+{
+    XEVE_CTX  *ctx = util_ctx();
+    XEVE_CORE *core = calloc(1, sizeof(XEVE_CORE));
+    s16(*coef)[MAX_CU_DIM] = calloc(N_C, sizeof(*coef));
+    if(!ctx || !core || !coef) return -1;
+    ctx->pps.cu_qp_delta_enabled_flag = 0;
+    ctx->sps.tool_admvp = 0;
+    ctx->sps.chroma_format_idc = 1;
+    core->bs_temp.pdata[1] = &core->s_temp_run;
+    for(int i = 0; i < n; i++) {
+        RH_BITS_REC *it = &items[i];
+        memset(&core->s_temp_run, 0, sizeof(core->s_temp_run));
+        /* an arbitrary legal low/pending state: the count must not depend on it */
+        core->s_temp_run.code = 0x12345u + 977u * (u32)i;
+        core->s_temp_run.code_bits = 1 + i % 11;
+        sbac_unpack(&states[it->state_in], &core->s_temp_run);
+        core->s_temp_run.is_bitcount = 1;
+        xeve_sbac_bit_reset(&core->s_temp_run);
+        core->log2_cuw = it->log2_cuw; core->log2_cuh = it->log2_cuh;
+        core->cuw = 1 << it->log2_cuw; core->cuh = 1 << it->log2_cuh;
+        core->ctx_flags[CNID_SKIP_FLAG] = it->ctx_skip; core->ctx_flags[CNID_PRED_MODE] = it->ctx_pred_mode;
+        core->tree_cons = xeve_get_default_tree_cons();
+        if(!it->all_preds) core->tree_cons.mode_cons = eOnlyInter;
+        memset(core->nnz_sub, 0, sizeof(core->nnz_sub));
+        for(int c = 0; c < 3; c++) core->nnz[c] = core->nnz_sub[c][0] = it->nnz[c];
+        ctx->rpm.num_refp[0] = it->num_refp[0]; ctx->rpm.num_refp[1] = it->num_refp[1];
+        if(it->kind == 1 || it->kind == 3) {
+            int ny = 1 << (it->log2_cuw + it->log2_cuh), nc = ny >> 2;
+            memcpy(coef[0], coef_buf + it->coef_off, ny * 2);
+            memcpy(coef[1], coef_buf + it->coef_off + ny, nc * 2);
+            memcpy(coef[2], coef_buf + it->coef_off + ny + nc, nc * 2);
+        }
+        switch(it->kind) {
+        case 0: xeve_rdo_bit_cnt_cu_skip(ctx, core, it->slice_type, 0, it->mvp_idx[0], it->mvp_idx[1], 0, 0); break;
+        case 1: xeve_rdo_bit_cnt_cu_inter(ctx, core, it->slice_type, 0, it->refi, it->mvd, coef, it->pidx, it->mvp_idx, 0, 0, NULL); break;
+        case 2: xeve_rdo_bit_cnt_mvp(ctx, core, it->slice_type, it->refi, it->mvd, it->pidx, it->mvp_idx[0]); break;
+        default: xeve_rdo_bit_cnt_cu_inter_comp(core, coef, it->ch, it->pidx, ctx, core->tree_cons); break;
+        }
+        it->bits = xeve_get_bit_number(&core->s_temp_run);
+        if(it->state_out >= 0) sbac_pack(&core->s_temp_run, &states[it->state_out]);
+    }
+    free(coef);
+    free(core);
+    return 0;
+}
+RH_API int rh_sizeof_bits(void) { return sizeof(RH_BITS_REC); }

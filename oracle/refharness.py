@@ -125,6 +125,27 @@ def lib():
     return _lib
 
 
+SBAC = np.dtype([("range", "<u4"), ("m", "<u2", (68,))], align=True)
+BITS_REC = np.dtype([
+    ("kind", "u1"), ("slice_type", "u1"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pidx", "u1"), ("ch", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("num_refp", "u1", (2,)),
+    ("all_preds", "u1"), ("pad_", "u1"), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,)), ("state_in", "<i4"),
+    ("state_out", "<i4"), ("coef_off", "<i8"), ("bits", "<u4"), ("pad2_", "<u4"),
+], align=True)
+
+
+def rdo_bits(items, states, coef):
+    """The reference's xeve_rdo_bit_cnt_* (src_base/xeve_mode.c:57-302) on a scratch core."""
+    L = lib()
+    assert L.rh_sizeof_bits() == BITS_REC.itemsize
+    items = np.ascontiguousarray(items, BITS_REC).copy()
+    states = np.ascontiguousarray(states, SBAC).copy()
+    coef = np.ascontiguousarray(coef, np.int16)
+    L.rh_rdo_bits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.rh_rdo_bits(_p(items), len(items), _p(states), _p(coef)) == 0
+    return items, states
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -189,9 +210,12 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
 
     me, mc, tq = grab(0, ME_REC), grab(1, MC_REC), grab(2, TQ_REC)
     rates, pics, samp = grab(3, RATES), grab(4, PIC), grab(5, np.dtype("<i2"))
+    sbac = grab(6, SBAC)
     cst = np.zeros(1, CONST)
     L.rh_trace_const(_p(cst))
-    return Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
+    tr = Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
+    tr.sbac = sbac
+    return tr
 
 
 def replay_me(tr: Trace, recs: np.ndarray | None = None, nthreads=1):

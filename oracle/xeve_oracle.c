@@ -16,6 +16,7 @@
  */
 #include "xeve_oracle.h"
 #include "../xeve_b200/csrc/xb200_tables.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -682,6 +683,179 @@ void xo_bi_org_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_it
                      const int64_t *off, int16_t *side)
 {
     for(int64_t i = 0; i < n; i++) xo_bi_org(sq, pl, &items[i], cur_pic[i], side + off[i]);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * CABAC bit counting for inter RDO (src_base/xeve_eco.c:455-620 engine, :674-1260 syntax;
+ * src_base/xeve_mode.c:39-302 counters).  After xeve_sbac_bit_reset the value of xeve_get_bit_number
+ * is the number of renormalisation shifts: every carry_propagate moves exactly one byte into
+ * {bitcounter, stacked_zero, stacked_ff, pending}, so 8*bytes + 11 - code_bits == shifts.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { xb200_sbac s; uint32_t bits; } cabac_t;
+
+static void cb_bin(cabac_t *c, int m, int bin) /* xeve_sbac_encode_bin */
+{
+    uint16_t model = c->s.m[m], mps = model & 1, state = model >> 1;
+    uint32_t lps = (state * c->s.range) >> 9;
+    if(lps < 437) lps = 437;
+    c->s.range -= lps;
+    if((uint16_t)(bin != 0) != mps) {
+        if(c->s.range >= lps) c->s.range = lps;
+        state = state + ((512 - state + 16) >> 5);
+        if(state > 256) { mps = 1 - mps; state = 512 - state; }
+    }
+    else state = state - ((state + 16) >> 5);
+    c->s.m[m] = (uint16_t)((state << 1) + mps);
+    while(c->s.range < 8192) { c->s.range <<= 1; c->bits++; }
+}
+static void cb_ep(cabac_t *c) { c->s.range &= ~1u; c->bits++; } /* sbac_encode_bin_ep: range >>= 1, <<= 1 drops the LSB */
+static void cb_unary(cabac_t *c, uint32_t sym, int m) /* sbac_write_unary_sym with num_ctx == 2 */
+{
+    cb_bin(c, m, sym ? 1 : 0);
+    if(sym == 0) return;
+    while(sym--) cb_bin(c, m + 1, sym ? 1 : 0);
+}
+static void cb_mvp_idx(cabac_t *c, int idx) /* sbac_write_truncate_unary_sym(idx, 3, 4) */
+{
+    for(int i = 0; i < 3; i++) {
+        int symbol = (i == idx) ? 0 : 1;
+        cb_bin(c, XB200_CM_MVP_IDX + i, symbol);
+        if(!symbol) break;
+    }
+}
+static void cb_abs_mvd(cabac_t *c, uint32_t val) /* xeve_eco_abs_mvd: exp-golomb, first two bins context coded */
+{
+    int len_i = 0, nn = (int)((val + 1) >> 1);
+    while(len_i < 16 && nn != 0) { nn >>= 1; len_i++; }
+    uint32_t info = val + 1 - (1u << len_i), code = (1u << len_i) | (info & ((1u << len_i) - 1));
+    int      len_c = (len_i << 1) + 1;
+    for(int i = 0; i < len_c; i++) {
+        int bin = (code >> (len_c - 1 - i)) & 1;
+        if(i <= 1) cb_bin(c, XB200_CM_MVD, bin); else cb_ep(c);
+    }
+}
+static void cb_mvd(cabac_t *c, const int16_t mvd[2])
+{
+    for(int k = 0; k < 2; k++) {
+        int mv = mvd[k] < 0 ? -mvd[k] : mvd[k];
+        cb_abs_mvd(c, (uint32_t)mv);
+        if(mv) cb_ep(c);
+    }
+}
+static void cb_refi(cabac_t *c, int num_refp, int refi) /* xeve_eco_refi */
+{
+    if(num_refp <= 1) return;
+    if(refi == 0) { cb_bin(c, XB200_CM_REFI, 0); return; }
+    cb_bin(c, XB200_CM_REFI, 1);
+    for(int i = 2; i < num_refp; i++) {
+        int bin = (i == refi + 1) ? 0 : 1;
+        if(i == 2) cb_bin(c, XB200_CM_REFI + 1, bin); else cb_ep(c);
+        if(!bin) break;
+    }
+}
+static void cb_run_length(cabac_t *c, const int16_t *coef, int log2n, int num_sig, int ch) /* xeve_eco_run_length_cc */
+{
+    oracle_init();
+    const uint16_t *scan = g_scan[log2n];
+    const int       n = 1 << (2 * log2n), t0 = ch == 0 ? 0 : 2;
+    uint32_t        run = 0;
+    for(int sp = 0; sp < n; sp++) {
+        int v = coef[scan[sp]];
+        if(!v) { run++; continue; }
+        uint32_t level = (uint32_t)(v < 0 ? -v : v);
+        cb_unary(c, run, XB200_CM_RUN + t0);
+        cb_unary(c, level - 1, XB200_CM_LEVEL + t0);
+        cb_ep(c); /* sign */
+        if(sp == n - 1) break;
+        run = 0;
+        num_sig--;
+        cb_bin(c, XB200_CM_LAST + (ch == 0 ? 0 : 1), num_sig == 0);
+        if(num_sig == 0) break;
+    }
+}
+/* xeve_eco_coef for an inter CU <= 64 (one transform block per plane), b_no_cbf = 0 */
+static void cb_coef(cabac_t *c, const xb200_bits_item *it, const int16_t *coef, int run_stats)
+{
+    const int run[3] = {run_stats & 1, (run_stats >> 1) & 1, (run_stats >> 2) & 1};
+    const int cbf[3] = {it->nnz[0] != 0, it->nnz[1] != 0, it->nnz[2] != 0};
+    int       cbf_all = 0;
+    for(int k = 0; k < 3; k++) if(run[k]) cbf_all += cbf[k];
+    if(run[0] + run[1] + run[2] == 3) {
+        cb_bin(c, XB200_CM_CBF_ALL, cbf_all != 0);
+        if(!cbf_all) return;
+    }
+    if(run[1]) cb_bin(c, XB200_CM_CBF_CB, cbf[1]);
+    if(run[2]) cb_bin(c, XB200_CM_CBF_CR, cbf[2]);
+    if(run[0] && (cbf[1] + cbf[2] != 0)) cb_bin(c, XB200_CM_CBF_LUMA, cbf[0]);
+    const int ny = 1 << (it->log2_cuw + it->log2_cuh), off[3] = {0, ny, ny + (ny >> 2)};
+    for(int k = 0; k < 3; k++)
+        if(it->nnz[k] && run[k]) cb_run_length(c, coef + off[k], k ? it->log2_cuw - 1 : it->log2_cuw, it->nnz[k], k);
+}
+void xo_rdo_bits(xb200_bits_item *it, xb200_sbac *states, const int16_t *coef)
+{
+    cabac_t c;
+    c.s = states[it->state_in];
+    c.bits = 0;
+    const int B = it->slice_type == 0, inter = it->slice_type != 2; /* SLICE_B 0, SLICE_P 1, SLICE_I 2 */
+    if(it->kind == 0) {
+        if(inter) {
+            cb_bin(&c, XB200_CM_SKIP_FLAG + it->ctx_skip, 1);
+            cb_mvp_idx(&c, it->mvp_idx[0]);
+            if(B) cb_mvp_idx(&c, it->mvp_idx[1]);
+        }
+    }
+    else if(it->kind == 1) {
+        if(inter) {
+            cb_bin(&c, XB200_CM_SKIP_FLAG + it->ctx_skip, 0);
+            if(it->all_preds) cb_bin(&c, XB200_CM_PRED_MODE + it->ctx_pred_mode, 0);
+            cb_bin(&c, XB200_CM_DIRECT, it->pidx == 4);
+            if(it->pidx != 4) {
+                if(it->refi[0] >= 0 && it->refi[1] >= 0) cb_bin(&c, XB200_CM_INTER_DIR, 0);
+                else {
+                    if(B) cb_bin(&c, XB200_CM_INTER_DIR, 1);
+                    cb_bin(&c, XB200_CM_INTER_DIR + 1, it->refi[0] >= 0 ? 0 : 1);
+                }
+                if(it->refi[0] >= 0) { cb_refi(&c, it->num_refp[0], it->refi[0]); cb_mvp_idx(&c, it->mvp_idx[0]); cb_mvd(&c, it->mvd[0]); }
+                if(B && it->refi[1] >= 0) { cb_refi(&c, it->num_refp[1], it->refi[1]); cb_mvp_idx(&c, it->mvp_idx[1]); cb_mvd(&c, it->mvd[1]); }
+            }
+        }
+        cb_coef(&c, it, coef + it->coef_off, 7);
+    }
+    else if(it->kind == 2) {
+        if(it->pidx != 4) {
+            if(inter && it->refi[0] >= 0) { cb_mvp_idx(&c, it->mvp_idx[0]); cb_mvd(&c, it->mvd[0]); }
+            if(B && it->refi[1] >= 0) { cb_mvp_idx(&c, it->mvp_idx[0]); cb_mvd(&c, it->mvd[1]); }
+        }
+    }
+    else cb_coef(&c, it, coef + it->coef_off, 1 << it->ch);
+    it->bits = c.bits;
+    if(it->state_out >= 0) states[it->state_out] = c.s;
+}
+void xo_rdo_bits_batch(xb200_bits_item *items, int64_t n, xb200_sbac *states, const int16_t *coef)
+{
+    for(int64_t i = 0; i < n; i++) xo_rdo_bits(&items[i], states, coef);
+}
+/* xeve_rdoq_bit_est + biari_no_bits + xeve_init_bits_est, src_base/xeve_mode.c:304-373 */
+void xo_rdoq_rates(const xb200_sbac *st, int64_t n, xb200_rates *out)
+{
+    static int32_t ebits[1024];
+    static int     init;
+    if(!init) {
+        for(int i = 0; i < 1024; i++) { double p = (512 * (i + 0.5)) / 1024; ebits[i] = (int32_t)(-32768 * (log(p) / log(2.0) - 9)); }
+        init = 1;
+    }
+#define NB(sym, model) ebits[(((uint16_t)((sym) != 0) != ((model) & 1)) ? ((model) >> 1) : (512 - ((model) >> 1))) << 1]
+    for(int64_t i = 0; i < n; i++) {
+        const uint16_t *m = st[i].m;
+        memset(&out[i], 0, sizeof(out[i]));
+        for(int b = 0; b < 2; b++) {
+            out[i].cbf_all[b] = NB(b, m[XB200_CM_CBF_ALL]); out[i].cbf_luma[b] = NB(b, m[XB200_CM_CBF_LUMA]);
+            out[i].cbf_cb[b] = NB(b, m[XB200_CM_CBF_CB]); out[i].cbf_cr[b] = NB(b, m[XB200_CM_CBF_CR]);
+            for(int k = 0; k < 24; k++) { out[i].run[k][b] = NB(b, m[XB200_CM_RUN + k]); out[i].level[k][b] = NB(b, m[XB200_CM_LEVEL + k]); }
+            for(int k = 0; k < 2; k++) out[i].last[k][b] = NB(b, m[XB200_CM_LAST + k]);
+        }
+    }
+#undef NB
 }
 
 /* batch drivers --------------------------------------------------------------------------------- */

@@ -33,6 +33,9 @@ XO_API void xo_residue(const xb200_seq *sq, const xo_planes *pl, const xb200_rat
 XO_API void xo_bi_org(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int cur_pic, int16_t *org_bi);
 XO_API void xo_bi_org_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n,
                             const int32_t *cur_pic, const int64_t *off, int16_t *side);
+XO_API void xo_rdo_bits(xb200_bits_item *it, xb200_sbac *states, const int16_t *coef);
+XO_API void xo_rdo_bits_batch(xb200_bits_item *items, int64_t n, xb200_sbac *states, const int16_t *coef);
+XO_API void xo_rdoq_rates(const xb200_sbac *st, int64_t n, xb200_rates *out);
 XO_API void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad);
 XO_API void xo_me_batch(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *items, int64_t n);
 XO_API void xo_mc_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n,

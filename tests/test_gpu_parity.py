@@ -417,3 +417,33 @@ def test_mvp_inputs_match_reference(gpu_ctx):
         for fld in ("avail", "refi", "mvp", "mv_dir"):
             assert np.array_equal(got[fld], exp[fld]), (fld, poc)
     assert len(np.unique(exp["avail"])) > 10 and (exp["mvp"][:, :3] == 1).all(-1).any()
+
+
+def test_rdo_bit_counter_matches_oracle_and_reference(gpu_ctx):
+    """xb200_rdo_bits: bits and output coder states identical to the oracle (and to the reference's counters when built)."""
+    import ratedata
+    it, st, coef = ratedata.work(seed=11, n=4000)
+    g, sg = gpu_ctx.rdo_bits(it, st, coef)
+    o, so = xo.rdo_bits_batch(it, st, coef)
+    assert np.array_equal(g["bits"], o["bits"])
+    assert sg.tobytes() == so.tobytes()
+    if rh.available():
+        r, sr = rh.rdo_bits(it, st, coef)
+        assert np.array_equal(g["bits"], r["bits"]) and sg.tobytes() == sr.tobytes()
+    bad = it[:1].copy()
+    bad["state_in"] = len(st)
+    with pytest.raises(api.Xb200Error):
+        gpu_ctx.rdo_bits(bad, st, coef)
+
+
+def test_rdoq_rate_tables_match_reference(trace, gpu_ctx):
+    """xb200_rdoq_rates on traced coder states == the rate tables the reference derived from them."""
+    if trace.source != "live":
+        rng = np.random.default_rng(3)
+        import ratedata
+        st = ratedata.rand_states(rng, 500)
+        assert gpu_ctx.rdoq_rates(st).tobytes() == xo.rdoq_rates(st, api.RATES).tobytes()
+        return
+    tr = trace.live
+    assert gpu_ctx.rdoq_rates(tr.sbac).tobytes() == tr.rates.tobytes()
+    assert xo.rdoq_rates(tr.sbac, api.RATES).tobytes() == tr.rates.tobytes()

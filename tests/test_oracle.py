@@ -128,3 +128,39 @@ def test_padding_matches_reference(trace):
         mine = trace.padded_planes(i)
         for a, b in zip(mine, full):
             assert np.array_equal(a, b[:, : a.shape[1]])
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+def test_rdo_bit_counter_matches_reference():
+    """xo_rdo_bits == the reference's xeve_rdo_bit_cnt_* + xeve_get_bit_number, bits and resulting coder states."""
+    import ratedata
+    it, st, coef = ratedata.work()
+    a, sa = rh.rdo_bits(it, st, coef)
+    b, sb = xo.rdo_bits_batch(it, st, coef)
+    assert a["bits"].max() > 1000 and len(np.unique(it["kind"])) == 4
+    assert np.array_equal(a["bits"], b["bits"])
+    assert sa.tobytes() == sb.tobytes()
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+def test_rdoq_rate_tables_match_reference():
+    """xo_rdoq_rates(state) == the rdoq_est_* tables the reference derived from the same state (xeve_rdoq_bit_est)."""
+    import tracedata
+    td = tracedata.live_trace(name="cif", frames=12, pic_lo=1, pic_hi=2, mask=4)
+    tr = td.live
+    assert len(tr.sbac) == len(tr.rates) > 100
+    o = xo.rdoq_rates(tr.sbac, rh.RATES)
+    assert o.tobytes() == tr.rates.tobytes()
+
+
+def test_rate_estimation_matches_golden():
+    """The oracle's bit counter and RDOQ rate tables against reference outputs committed in tests/golden/rate_golden.npz."""
+    import os
+    import ratedata
+    from xeve_b200 import api
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rate_golden.npz"))
+    it, st, coef = ratedata.work()
+    b, sb = xo.rdo_bits_batch(it, st, coef)
+    assert np.array_equal(b["bits"], z["bits"])
+    assert sb.tobytes() == z["states"].tobytes()
+    assert xo.rdoq_rates(z["sbac"], api.RATES).tobytes() == z["rates"].tobytes()

@@ -79,6 +79,16 @@ MVP_ITEM = np.dtype([
 ], align=True)
 MVP_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("poc", "<i4"), ("ref_poc", "<i4", (2,)), ("col_list_poc0", "<i4")], align=True)
 
+SBAC = np.dtype([("range", "<u4"), ("m", "<u2", (68,))], align=True)
+BITS_ITEM = np.dtype([
+    ("kind", "u1"), ("slice_type", "u1"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pidx", "u1"), ("ch", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("num_refp", "u1", (2,)),
+    ("all_preds", "u1"), ("pad_", "u1"), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,)), ("state_in", "<i4"),
+    ("state_out", "<i4"), ("coef_off", "<i8"), ("bits", "<u4"), ("pad2_", "<u4"),
+], align=True)
+(CM_SKIP_FLAG, CM_PRED_MODE, CM_DIRECT, CM_INTER_DIR, CM_REFI, CM_MVP_IDX, CM_MVD, CM_CBF_ALL, CM_CBF_LUMA, CM_CBF_CB,
+ CM_CBF_CR, CM_RUN, CM_LAST, CM_LEVEL, CM_COUNT) = (0, 2, 5, 6, 8, 10, 13, 14, 15, 16, 17, 18, 42, 44, 68)
+
 VP = C.c_void_p
 _lib = None
 
@@ -120,13 +130,16 @@ def load():
         L.xb200_itdq.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         L.xb200_recon.argtypes = [VP, VP, C.c_int64, VP, VP, VP, C.c_int64, C.c_int]
         L.xb200_residue.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
+        L.xb200_rdo_bits.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]
+        L.xb200_rdoq_rates.argtypes = [VP, VP, C.c_int64, VP]
         _lib = L
     return _lib
 
 
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
-           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms"]
+           "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
+           "xb200_rdo_bits", "xb200_rdoq_rates"]
 
 
 def _p(a):
@@ -266,6 +279,20 @@ class Hotpath:
                                   _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_mv, np.int16)),
                                   _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16))), "xb200_mvp")
         return items
+
+    def rdo_bits(self, items, states, coef=None):
+        """-> (items with .bits, states with the state_out slots written)"""
+        items = np.ascontiguousarray(items, BITS_ITEM).copy()
+        states = np.ascontiguousarray(states, SBAC).copy()
+        coef = np.zeros(1, np.int16) if coef is None else np.ascontiguousarray(coef, np.int16)
+        self._ck(self.L.xb200_rdo_bits(self.h, _p(items), len(items), _p(states), len(states), _p(coef), len(coef)), "xb200_rdo_bits")
+        return items, states
+
+    def rdoq_rates(self, states):
+        states = np.ascontiguousarray(states, SBAC)
+        out = np.zeros(len(states), RATES)
+        self._ck(self.L.xb200_rdoq_rates(self.h, _p(states), len(states), _p(out)), "xb200_rdoq_rates")
+        return out
 
     def tq(self, items, rates, coef):
         items = np.ascontiguousarray(items, TQ_ITEM).copy()

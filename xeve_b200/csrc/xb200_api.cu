@@ -15,6 +15,8 @@
 #include "xb200_misc.cuh"
 #include "xb200_residue2.cuh"
 #include "xb200_dct_tc.cuh"
+#include "xb200_rate.cuh"
+#include <math.h>
 
 namespace {
 
@@ -285,6 +287,18 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
         CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
         CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
     }
+    {   // rate estimation tables: zig-zag scans (closed form) and xeve_init_bits_est (src_base/xeve_mode.c:304-313, host libm)
+        static uint16_t scan[16 + 64 + 256 + 1024 + 4096];
+        static int32_t  eb[1024];
+        int             off = 0;
+        for(int l2 = 2; l2 <= 6; l2++) { xb200_gen_scan(scan + off, l2, l2); off += 1 << (2 * l2); }
+        for(int i = 0; i < 1024; i++) {
+            const double p = (512 * (i + 0.5)) / 1024;
+            eb[i] = (int32_t)(-32768 * (log(p) / log(2.0) - 9));
+        }
+        CK(cudaMemcpyToSymbol(g_scan, scan, sizeof(scan)));
+        CK(cudaMemcpyToSymbol(g_entropy_bits, eb, sizeof(eb)));
+    }
     CK(cudaMalloc(&c->d_err, sizeof(int)));
     CK(cudaMemset(c->d_err, 0, sizeof(int)));
     CK(cudaMalloc(&c->d_bins, sizeof(int) * 16));
@@ -554,6 +568,60 @@ int xb200_mvp(xb200_ctx *c, xb200_mvp_item *items, int64_t n, const xb200_mvp_pi
     c->last_ms = ms;
     CK(cudaGetLastError());
     return XB200_OK;
+}
+
+// ---- rate estimation ----------------------------------------------------------------------------------------
+int xb200_rdo_bits(xb200_ctx *c, xb200_bits_item *items, int64_t n, xb200_sbac *states, int64_t n_states, const int16_t *coef,
+                   int64_t coef_elems)
+{
+    if(!c || n < 0 || n_states < 0 || coef_elems < 0 || (n && (!items || !states)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    for(int64_t i = 0; i < n; i++) {
+        const xb200_bits_item &it = items[i];
+        if(it.kind > 3 || it.slice_type > 2 || it.state_in < 0 || it.state_in >= n_states || it.state_out >= n_states || it.ch > 2 ||
+           it.mvp_idx[0] > 3 || it.mvp_idx[1] > 3)
+            return XB200_ERR_INVALID_ARGUMENT;
+        if(it.kind == 1 || it.kind == 3) {
+            const int64_t ny = (int64_t)1 << (it.log2_cuw + it.log2_cuh);
+            if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 3 || it.log2_cuw > 6 || !coef || it.coef_off < 0 ||
+               it.coef_off + ny + (ny >> 1) > coef_elems)
+                return XB200_ERR_INVALID_ARGUMENT;
+        }
+    }
+    int r;
+    xb200_bits_item *d_items;
+    xb200_sbac      *d_in, *d_out;
+    int16_t         *d_coef;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, states, (size_t)n_states, XB200_MEM_HOST, &d_in))) return r;
+    if((r = to_dev(c, c->b_aux1, states, (size_t)n_states, XB200_MEM_HOST, &d_out))) return r;
+    if((r = to_dev(c, c->b_side, coef, (size_t)coef_elems, XB200_MEM_HOST, &d_coef))) return r;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    const long long blocks = (n + RATE_WARPS - 1) / RATE_WARPS;
+    k_rdo_bits<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), RATE_WARPS * 32, 0, c->stream>>>(d_items, n, d_in, d_out, d_coef);
+    c->launches++;
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, states, d_out, (size_t)n_states, XB200_MEM_HOST))) return r;
+    return finish(c);
+}
+
+int xb200_rdoq_rates(xb200_ctx *c, const xb200_sbac *states, int64_t n, xb200_rates *rates)
+{
+    if(!c || n < 0 || (n && (!states || !rates)) || n > (1 << 24)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    int r;
+    xb200_sbac *d_st;
+    if((r = to_dev(c, c->b_aux0, states, (size_t)n, XB200_MEM_HOST, &d_st))) return r;
+    if((r = ensure(c->b_aux1, (size_t)n * sizeof(xb200_rates)))) return r;
+    xb200_rates *d_rt = static_cast<xb200_rates *>(c->b_aux1.p);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(d_rt, 0, (size_t)n * sizeof(xb200_rates), c->stream));
+    k_rdoq_rates<<<(unsigned)((n * 64 + 127) / 128), 128, 0, c->stream>>>(d_st, n, d_rt);
+    c->launches++;
+    if((r = to_host(c, rates, d_rt, (size_t)n, XB200_MEM_HOST))) return r;
+    return finish(c);
 }
 
 // ---- motion search ------------------------------------------------------------------------------------------
