@@ -218,6 +218,37 @@ typedef struct {
     uint32_t pad2_;
 } xb200_bits_item;
 
+/* One ctx->fn_pinter_analyze_cu call (src_base/xeve_pinter.c:1839-2056): best inter mode of one CU among SKIP, DIRECT (B),
+ * L0, L1 and BI by RD cost.  The neighbourhood enters through the xeve_get_motion candidates (xb200_mvp) and the input
+ * coder state; costs are IEEE doubles evaluated in the reference's operation order (no fused multiply-add). */
+#define XB200_MAX_REFP 4
+typedef struct {
+    int32_t  poc, cur_pic;          /* POC and original-picture handle of the picture being coded */
+    int16_t  x, y;
+    uint8_t  log2_cuw, log2_cuh, slice_type, ctx_skip, ctx_pred_mode, all_preds;
+    uint8_t  num_refp[2];           /* ctx->rpm.num_refp[] */
+    uint8_t  qp[3], pad0_;          /* core->qp_y/u/v */
+    int32_t  max_search_range;      /* pi->max_search_range (src_base/xeve_pinter.c:2093) */
+    int32_t  ref_pic[2][XB200_MAX_REFP], ref_poc[2][XB200_MAX_REFP]; /* pi->refp[refi][lidx] as [lidx][refi] */
+    uint32_t lambda_mv;             /* pi->lambda_mv */
+    int32_t  rate_idx;              /* RDOQ rate tables of the input coder state (xb200_rdoq_rates) */
+    int32_t  state_in, state_out;   /* coder state slots: core->s_curr_best[..] in, core->s_next_best[..] out */
+    double   lambda[3], dist_chroma_weight[2];
+    int16_t  mvp[2][4][2];          /* pi->mvp[lidx][] (== pi->mvp_scale[lidx][refi][]) */
+    int8_t   refi_pred[2][4];       /* pi->refi_pred[lidx][] */
+    int16_t  mv_dir[2][2];          /* xeve_get_mv_dir result (B slices) */
+    int64_t  out_off;               /* element offset of this CU's coef / rec slots (3/2 * cuw * cuh each) */
+    /* results */
+    double   cost;                  /* return value */
+    uint8_t  best_idx, pad1_;       /* PRED_L0 0, PRED_L1 1, PRED_BI 2, PRED_SKIP 3, PRED_DIR 4 */
+    int8_t   refi[2];               /* XEVE_MODE::refi, mvp_idx, mv, mvd */
+    uint8_t  mvp_idx[2];
+    int16_t  mv[2][2], mvd[2][2];
+    int32_t  nnz[3];                /* core->nnz */
+    uint64_t coef_hash, rec_hash;   /* unused by the library (test bookkeeping) */
+    int32_t  me_first, me_cnt;      /* unused by the library (test bookkeeping) */
+} xb200_cu_item;
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 XB200_API int  xb200_create(xb200_ctx **out, int device, const xb200_seq *seq);
 XB200_API void xb200_destroy(xb200_ctx *c);

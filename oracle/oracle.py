@@ -56,6 +56,12 @@ def lib():
         L.xo_me_batch.argtypes = [VP, VP, VP, VP, C.c_int64]
         L.xo_mc_batch.restype = None
         L.xo_mc_batch.argtypes = [VP, VP, VP, C.c_int64, VP, VP]
+        L.xo_analyze_cu_batch.restype = None
+        L.xo_analyze_cu_batch.argtypes = [VP, VP, VP, VP, C.c_int64, VP, VP, VP]
+        L.xo_rdo_bits_batch.restype = None
+        L.xo_rdo_bits_batch.argtypes = [VP, C.c_int64, VP, VP]
+        L.xo_rdoq_rates.restype = None
+        L.xo_rdoq_rates.argtypes = [VP, C.c_int64, VP]
         L.xo_bi_org_batch.restype = None
         L.xo_bi_org_batch.argtypes = [VP, VP, VP, C.c_int64, VP, VP, VP]
         L.xo_tq_batch.restype = None
@@ -116,4 +122,25 @@ def rdoq_rates(states, rates_dtype):
     states = np.ascontiguousarray(states)
     out = np.zeros(len(states), rates_dtype)
     lib().xo_rdoq_rates(_p(states), len(states), _p(out))
+    return out
+
+
+def analyze_cu_batch(seq, planes, rates, items, states, elems):
+    items, states = items.copy(), states.copy()
+    coef = np.zeros(elems, np.int16)
+    rec = np.zeros(elems, np.int16)
+    lib().xo_analyze_cu_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(rates)), _p(items), len(items), _p(states),
+                              _p(coef), _p(rec))
+    return items, states, coef, rec
+
+
+def hash_slots(buf, off, elems):
+    """FNV-1a of buf[off[i] : off[i] + elems[i]] (s16) per item -- the hash the harness stores for in-situ outputs."""
+    off = np.ascontiguousarray(off, np.int64)
+    elems = np.ascontiguousarray(elems, np.int64)
+    out = np.zeros(len(off), np.uint64)
+    L = lib()
+    L.xo_hash_slots.restype = None
+    L.xo_hash_slots.argtypes = [VP, VP, VP, C.c_int64, VP]
+    L.xo_hash_slots(_p(np.ascontiguousarray(buf, np.int16)), _p(off), _p(elems), len(off), _p(out))
     return out

@@ -100,6 +100,34 @@ typedef struct {
     int32_t merge_num, me_range, gop_size, rdoq, tool_iqt;
 } RH_CONST;
 
+/* One ctx->fn_pinter_analyze_cu call (layout == xb200_cu_item of include/xeve_b200.h). */
+#define RH_MAXR 4
+typedef struct {
+    int32_t  poc, cur_pic;
+    int16_t  x, y;
+    uint8_t  log2_cuw, log2_cuh, slice_type, ctx_skip, ctx_pred_mode, all_preds;
+    uint8_t  num_refp[2];
+    uint8_t  qp[3], pad0_;
+    int32_t  max_search_range;   /* pi->max_search_range */
+    int32_t  ref_pic[2][RH_MAXR], ref_poc[2][RH_MAXR];   /* [lidx][refi] */
+    uint32_t lambda_mv;
+    int32_t  rate_idx, state_in, state_out;
+    double   lambda[3], dist_chroma_weight[2];
+    int16_t  mvp[2][4][2];       /* xeve_get_motion candidates per list */
+    int8_t   refi_pred[2][4];
+    int16_t  mv_dir[2][2];       /* xeve_get_mv_dir (B slices) */
+    int64_t  out_off;            /* element offset of the coef / rec output slots */
+    /* results */
+    double   cost;
+    uint8_t  best_idx, pad1_;    /* PRED_L0 0, L1 1, BI 2, SKIP 3, DIR 4 */
+    int8_t   refi[2];
+    uint8_t  mvp_idx[2];
+    int16_t  mv[2][2], mvd[2][2];
+    int32_t  nnz[3];
+    uint64_t coef_hash, rec_hash;  /* FNV-1a over coef / rec Y,U,V (test bookkeeping) */
+    int32_t  me_first, me_cnt;     /* this CU's slice of the ME trace (test bookkeeping) */
+} RH_CU_REC;
+
 /* ------------------------------------------------------------------------------------------
  * growable buffers
  * ---------------------------------------------------------------------------------------- */
@@ -141,6 +169,8 @@ static struct {
     void (*org_mc)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, s8 *, s16 (*)[MV_D], XEVE_REFP (*)[REFP_NUM],
                    pel (*)[N_C][MAX_CU_DIM], int, int, s16 (*)[REFP_NUM][MV_D]);
     int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int);
+    double (*org_cu)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, XEVE_MODE *, s16 (*)[MAX_CU_DIM], pel **, int *);
+    vec_t    cu, cu_sbac; /* cu_sbac: coder states named by RH_CU_REC::state_in / state_out */
     vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
     /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
     RH_CONST cst;
@@ -251,6 +281,19 @@ static void put_rates(XEVE_CORE *core, const RH_RATES *o)
     memcpy(core->rdoq_est_last, o->last, sizeof(o->last));
 }
 
+static int rate_index(XEVE_CORE *core, int log2_cuw, int log2_cuh)
+{
+    RH_RATES cur;
+    grab_rates(core, &cur);
+    if(!T.have_rates || memcmp(&cur, &T.last_rates, sizeof(cur))) {
+        *(RH_RATES *)vec_push(&T.rates, 1) = cur;
+        sbac_pack(&core->s_curr_best[log2_cuw - 2][log2_cuh - 2], (RH_SBAC *)vec_push(&T.sbac, 1));
+        T.last_rates = cur;
+        T.have_rates = 1;
+    }
+    return (int)T.rates.n - 1;
+}
+
 static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], int log2_cuw, int log2_cuh,
                    int slice_type, int nnz[N_C], int is_intra, int run_stats)
 {
@@ -262,15 +305,7 @@ static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], in
     r.is_intra = is_intra; r.run_stats = run_stats;
     r.qp[0] = core->qp_y; r.qp[1] = core->qp_u; r.qp[2] = core->qp_v;
     for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
-    RH_RATES cur;
-    grab_rates(core, &cur);
-    if(!T.have_rates || memcmp(&cur, &T.last_rates, sizeof(cur))) {
-        *(RH_RATES *)vec_push(&T.rates, 1) = cur;
-        sbac_pack(&core->s_curr_best[log2_cuw - 2][log2_cuh - 2], (RH_SBAC *)vec_push(&T.sbac, 1));
-        T.last_rates = cur;
-        T.have_rates = 1;
-    }
-    r.rate_idx = (int)T.rates.n - 1;
+    r.rate_idx = rate_index(core, log2_cuw, log2_cuh);
     r.in_off = (int64_t)T.samp.n;
     s16 *dst = vec_push(&T.samp, ny + 2 * nc);
     memcpy(dst, coef[Y_C], ny * 2);
@@ -285,6 +320,74 @@ static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], in
     r.out_hash = hsh;
     *(RH_TQ_REC *)vec_push(&T.tq, 1) = r;
     return ret;
+}
+
+#define RH_T_CU 8
+static double hook_cu(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw, int log2_cuh, XEVE_MODE *mi,
+                      s16 coef[N_C][MAX_CU_DIM], pel *rec[N_C], int s_rec[N_C])
+{
+    if(!tracing(RH_T_CU)) return T.org_cu(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+    XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];
+    RH_CU_REC    r;
+    memset(&r, 0, sizeof(r));
+    r.poc = ctx->poc.poc_val;
+    r.cur_pic = find_or_add_pic(pi->pic_o, r.poc, 0);
+    r.x = x; r.y = y; r.log2_cuw = log2_cuw; r.log2_cuh = log2_cuh; r.slice_type = pi->slice_type;
+    r.ctx_skip = core->ctx_flags[CNID_SKIP_FLAG]; r.ctx_pred_mode = core->ctx_flags[CNID_PRED_MODE];
+    r.all_preds = xeve_check_all_preds(core->tree_cons);
+    r.qp[0] = core->qp_y; r.qp[1] = core->qp_u; r.qp[2] = core->qp_v;
+    for(int l = 0; l < 2; l++) {
+        r.num_refp[l] = ctx->rpm.num_refp[l];
+        for(int k = 0; k < RH_MAXR; k++) {
+            r.ref_pic[l][k] = -1; r.ref_poc[l][k] = -1;
+            if(k < r.num_refp[l] && (l == 0 || pi->slice_type == SLICE_B)) {
+                XEVE_PIC *rp = pi->refp[k][l].pic;
+                r.ref_pic[l][k] = find_or_add_pic(rp, (int)rp->poc, 1);
+                r.ref_poc[l][k] = (int)pi->refp[k][l].poc;
+            }
+        }
+    }
+    r.lambda_mv = pi->lambda_mv; r.max_search_range = pi->max_search_range;
+    r.rate_idx = rate_index(core, log2_cuw, log2_cuh);
+    r.state_in = (int)T.cu_sbac.n;
+    sbac_pack(&core->s_curr_best[log2_cuw - 2][log2_cuh - 2], (RH_SBAC *)vec_push(&T.cu_sbac, 1));
+    for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
+    r.dist_chroma_weight[0] = core->dist_chroma_weight[0]; r.dist_chroma_weight[1] = core->dist_chroma_weight[1];
+    if(pi->slice_type == SLICE_B)
+        xeve_get_mv_dir(pi->refp[0], ctx->poc.poc_val,
+                        core->scup + ((1 << (log2_cuw - MIN_CU_LOG2)) - 1) + ((1 << (log2_cuh - MIN_CU_LOG2)) - 1) * ctx->w_scu,
+                        core->scup, ctx->w_scu, ctx->h_scu, r.mv_dir, 0);
+    r.me_first = (int)T.me.n;
+    size_t ny = (size_t)1 << (log2_cuw + log2_cuh), nc = ny >> 2;
+    r.out_off = -1;
+
+    double cost = T.org_cu(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+
+    r.me_cnt = (int)T.me.n - r.me_first;
+    for(int l = 0; l < 2; l++)
+        for(int k = 0; k < 4; k++) {
+            r.mvp[l][k][0] = pi->mvp[l][k][0]; r.mvp[l][k][1] = pi->mvp[l][k][1];
+            r.refi_pred[l][k] = pi->refi_pred[l][k];
+        }
+    r.cost = cost;
+    int both = REFI_IS_VALID(mi->refi[0]) && REFI_IS_VALID(mi->refi[1]);
+    r.best_idx = core->cu_mode == MODE_SKIP ? PRED_SKIP : core->cu_mode == MODE_DIR ? PRED_DIR
+               : both ? PRED_BI : REFI_IS_VALID(mi->refi[0]) ? PRED_L0 : PRED_L1;
+    for(int l = 0; l < 2; l++) {
+        r.refi[l] = mi->refi[l]; r.mvp_idx[l] = mi->mvp_idx[l];
+        r.mv[l][0] = mi->mv[l][0]; r.mv[l][1] = mi->mv[l][1]; r.mvd[l][0] = mi->mvd[l][0]; r.mvd[l][1] = mi->mvd[l][1];
+    }
+    for(int i = 0; i < 3; i++) r.nnz[i] = core->nnz[i];
+    uint64_t hsh = FNV_INIT;
+    hsh = fnv1a(hsh, coef[Y_C], ny * 2); hsh = fnv1a(hsh, coef[U_C], nc * 2); hsh = fnv1a(hsh, coef[V_C], nc * 2);
+    r.coef_hash = hsh;
+    hsh = FNV_INIT;
+    hsh = fnv1a(hsh, rec[Y_C], ny * 2); hsh = fnv1a(hsh, rec[U_C], nc * 2); hsh = fnv1a(hsh, rec[V_C], nc * 2);
+    r.rec_hash = hsh;
+    r.state_out = (int)T.cu_sbac.n;
+    sbac_pack(&core->s_next_best[log2_cuw - 2][log2_cuh - 2], (RH_SBAC *)vec_push(&T.cu_sbac, 1));
+    *(RH_CU_REC *)vec_push(&T.cu, 1) = r;
+    return cost;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -342,13 +445,15 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     XEVE_CTX *ctx = (XEVE_CTX *)id;
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
-    vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC));
+    vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
     T.have_rates = 0;
     T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
     if(trace_mask) {
         T.org_me = ctx->pinter[0].fn_me; T.org_mc = ctx->pinter[0].fn_mc; T.org_tq = ctx->fn_tq;
         for(int i = 0; i < ctx->param.threads; i++) { ctx->pinter[i].fn_me = hook_me; ctx->pinter[i].fn_mc = hook_mc; }
         ctx->fn_tq = hook_tq;
+        T.org_cu = ctx->fn_pinter_analyze_cu;
+        ctx->fn_pinter_analyze_cu = hook_cu;
     }
     XEVE_PINTER *pi = &ctx->pinter[0];
     T.cst.w = w; T.cst.h = h; T.cst.bit_depth = ctx->param.codec_bit_depth; T.cst.me_level = pi->me_level;
@@ -415,7 +520,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 RH_API int64_t rh_trace_get(int what, void **ptr)
 {
     vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
-             : what == 4 ? &T.pics : what == 5 ? &T.samp : &T.sbac;
+             : what == 4 ? &T.pics : what == 5 ? &T.samp : what == 6 ? &T.sbac : what == 7 ? &T.cu : &T.cu_sbac;
     *ptr = v->p;
     return (int64_t)v->n;
 }
@@ -430,6 +535,7 @@ RH_API int  rh_sizeof(int what)
     case 4: return sizeof(RH_PIC);
     case 5: return sizeof(RH_PLANES);
     case 6: return sizeof(RH_CONST);
+    case 7: return sizeof(RH_CU_REC);
     }
     return -1;
 }

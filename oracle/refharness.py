@@ -125,6 +125,16 @@ def lib():
     return _lib
 
 
+CU_REC = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("all_preds", "u1"), ("num_refp", "u1", (2,)), ("qp", "u1", (3,)), ("pad0_", "u1"),
+    ("max_search_range", "<i4"), ("ref_pic", "<i4", (2, 4)), ("ref_poc", "<i4", (2, 4)), ("lambda_mv", "<u4"), ("rate_idx", "<i4"), ("state_in", "<i4"),
+    ("state_out", "<i4"), ("lambda", "<f8", (3,)), ("dist_chroma_weight", "<f8", (2,)), ("mvp", "<i2", (2, 4, 2)),
+    ("refi_pred", "i1", (2, 4)), ("mv_dir", "<i2", (2, 2)), ("out_off", "<i8"), ("cost", "<f8"), ("best_idx", "u1"), ("pad1_", "u1"),
+    ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,)),
+    ("coef_hash", "<u8"), ("rec_hash", "<u8"), ("me_first", "<i4"), ("me_cnt", "<i4"),
+], align=True)
+TRACE_CU = 8
 SBAC = np.dtype([("range", "<u4"), ("m", "<u2", (68,))], align=True)
 BITS_REC = np.dtype([
     ("kind", "u1"), ("slice_type", "u1"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pidx", "u1"), ("ch", "u1"),
@@ -211,10 +221,12 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
     me, mc, tq = grab(0, ME_REC), grab(1, MC_REC), grab(2, TQ_REC)
     rates, pics, samp = grab(3, RATES), grab(4, PIC), grab(5, np.dtype("<i2"))
     sbac = grab(6, SBAC)
+    assert L.rh_sizeof(7) == CU_REC.itemsize, (L.rh_sizeof(7), CU_REC.itemsize)
+    cu, cu_sbac = grab(7, CU_REC), grab(8, SBAC)
     cst = np.zeros(1, CONST)
     L.rh_trace_const(_p(cst))
     tr = Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
-    tr.sbac = sbac
+    tr.sbac, tr.cu, tr.cu_sbac = sbac, cu, cu_sbac
     return tr
 
 

@@ -36,6 +36,11 @@ XO_API void xo_bi_org_batch(const xb200_seq *sq, const xo_planes *pl, const xb20
 XO_API void xo_rdo_bits(xb200_bits_item *it, xb200_sbac *states, const int16_t *coef);
 XO_API void xo_rdo_bits_batch(xb200_bits_item *items, int64_t n, xb200_sbac *states, const int16_t *coef);
 XO_API void xo_rdoq_rates(const xb200_sbac *st, int64_t n, xb200_rates *out);
+XO_API void xo_analyze_cu(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_cu_item *cu, xb200_sbac *states,
+                          int16_t *coef_out, int16_t *rec_out);
+XO_API void xo_analyze_cu_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_cu_item *items, int64_t n,
+                                xb200_sbac *states, int16_t *coef, int16_t *rec);
+XO_API void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out);
 XO_API void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad);
 XO_API void xo_me_batch(const xb200_seq *sq, const xo_planes *pl, const int16_t *side, xb200_me_item *items, int64_t n);
 XO_API void xo_mc_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *items, int64_t n,

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import tracedata  # noqa: E402
 from oracle import refharness as rh  # noqa: E402
 
-td = tracedata.live_trace("cif", frames=20, pic_lo=1, pic_hi=2, **tracedata.QCIF)
+td = tracedata.live_trace("cif", frames=20, pic_lo=1, pic_hi=2, mask=15, **tracedata.QCIF)
 tr = td.live
 rng = np.random.default_rng(5)
 
@@ -55,10 +55,21 @@ for r in tq:
     pos += n
 assert np.array_equal(nnz_ref[idx], tq["nnz"])
 
-out = dict(seq=tr.const, pics=tr.pics, me=me, side=side, mc=mc, mc_pred=pred, mc_off=off, tq=tq, rates=tr.rates[used_rates],
+# CU decisions: 500 xeve_pinter_analyze_cu calls with the reference's results, coder states and rate tables compacted
+cidx = np.sort(rng.permutation(len(tr.cu))[:500])
+cu = tr.cu[cidx].copy()
+cu_rates_used = np.unique(cu["rate_idx"])
+rmap = {int(r): i for i, r in enumerate(cu_rates_used)}
+cu_sbac = np.zeros(2 * len(cu), tr.cu_sbac.dtype)
+for i, r in enumerate(cu):
+    cu_sbac[2 * i], cu_sbac[2 * i + 1] = tr.cu_sbac[int(r["state_in"])], tr.cu_sbac[int(r["state_out"])]
+    r["state_in"], r["state_out"], r["rate_idx"] = 2 * i, 2 * i + 1, rmap[int(r["rate_idx"])]
+    r["me_first"] = r["me_cnt"] = 0
+
+out = dict(cu=cu, cu_sbac=cu_sbac, cu_rates=tr.rates[cu_rates_used], seq=tr.const, pics=tr.pics, me=me, side=side, mc=mc, mc_pred=pred, mc_off=off, tq=tq, rates=tr.rates[used_rates],
            tq_in=np.concatenate(tq_in), tq_coef_out=np.concatenate(tq_out), tq_resi_out=np.concatenate(tq_resi), tq_nnz=nnz_ref[idx])
 for i in range(len(tr.pics)):
     out[f"p{i}_y"], out[f"p{i}_u"], out[f"p{i}_v"] = td.planes[i]
 path = os.path.join(ROOT, "tests", "golden", "qcif_trace.npz")
 np.savez_compressed(path, **out)
-print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(me), "ME,", len(mc), "MC,", len(tq), "TQ items")
+print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(me), "ME,", len(mc), "MC,", len(tq), "TQ,", len(cu), "CU items")

@@ -164,3 +164,22 @@ def test_rate_estimation_matches_golden():
     assert np.array_equal(b["bits"], z["bits"])
     assert sb.tobytes() == z["states"].tobytes()
     assert xo.rdoq_rates(z["sbac"], api.RATES).tobytes() == z["rates"].tobytes()
+
+
+def test_oracle_analyze_cu_matches_golden(golden):
+    """xo_analyze_cu (SKIP / DIRECT / L0 / L1 / BI decision with cbf RDO) == xeve_pinter_analyze_cu in situ: mode, double
+    cost, motion, nnz, coefficient and reconstruction hashes and the output coder state."""
+    td = golden
+    cu, sz, elems = tracedata.cu_slots(td.cu)
+    o, st, coef, rec = xo.analyze_cu_batch(td.seq, td.oracle_planes(), td.cu_rates, cu, td.cu_sbac, elems)
+    assert len(np.unique(td.cu["best_idx"])) == 5
+    tracedata.check_cu_results(o, td.cu, coef, rec, sz, st, td.cu_sbac)
+
+
+@needs_ref
+def test_oracle_analyze_cu_matches_reference_in_situ_cif(trace):
+    td = trace
+    cu, sz, elems = tracedata.cu_slots(td.cu)
+    o, st, coef, rec = xo.analyze_cu_batch(td.seq, td.oracle_planes(), td.cu_rates, cu, td.cu_sbac, elems)
+    assert len(cu) > 5000
+    tracedata.check_cu_results(o, td.cu, coef, rec, sz, st, td.cu_sbac)

@@ -89,10 +89,11 @@ def from_live(tr: "rh.Trace") -> TraceData:
     td = TraceData(tr.const.copy(), tr.pics.copy(), planes, tr.me.copy(), tr.mc.copy(), tr.tq.copy(), tr.rates.copy(), tr.samp,
                    tr.samp, "live")
     td.live = tr
+    td.cu, td.cu_sbac, td.cu_rates = tr.cu.copy(), tr.cu_sbac.copy(), tr.rates.copy()
     return td
 
 
-def live_trace(name="cif", frames=30, pic_lo=1, pic_hi=3, preset="fast", mask=7, extra="", **override) -> TraceData:
+def live_trace(name="cif", frames=30, pic_lo=1, pic_hi=3, preset="fast", mask=15, extra="", **override) -> TraceData:
     c, yuv = clip_yuv(name, frames, **override)
     tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=mask, pic_lo=pic_lo, pic_hi=pic_hi)
     return from_live(tr)
@@ -104,7 +105,33 @@ def golden_trace() -> TraceData:
     planes = [(z[f"p{i}_y"], z[f"p{i}_u"], z[f"p{i}_v"]) for i in range(len(pics))]
     expect = dict(mc_pred=z["mc_pred"], mc_off=z["mc_off"], tq_coef_out=z["tq_coef_out"], tq_resi_out=z["tq_resi_out"],
                   tq_nnz=z["tq_nnz"])
-    return TraceData(z["seq"], pics, planes, z["me"], z["mc"], z["tq"], z["rates"], z["side"], z["tq_in"], "golden", expect)
+    td = TraceData(z["seq"], pics, planes, z["me"], z["mc"], z["tq"], z["rates"], z["side"], z["tq_in"], "golden", expect)
+    td.cu, td.cu_sbac, td.cu_rates = z["cu"], z["cu_sbac"], z["cu_rates"]
+    return td
+
+
+def cu_slots(cu):
+    """(items with out_off assigned, per-item slot sizes, total elements) for the coef / rec outputs of a CU list."""
+    cu = cu.copy()
+    sz = (3 << (2 * cu["log2_cuw"].astype(np.int64))) >> 1
+    cu["out_off"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+    return cu, sz, int(sz.sum())
+
+
+def check_cu_results(got, ref, coef, rec, sz, st_got, st_ref):
+    """Decision-level comparison of analyze_cu outputs with the reference's in-situ results (fields the reference leaves
+    stale -- MVs of unused lists, mvp_idx of SKIP/DIRECT, coefficients of all-zero CUs -- are not compared)."""
+    assert np.array_equal(got["best_idx"], ref["best_idx"])
+    assert np.array_equal(got["cost"], ref["cost"])          # IEEE doubles, bit for bit
+    assert np.array_equal(got["nnz"], ref["nnz"]) and np.array_equal(got["refi"], ref["refi"])
+    used = ref["refi"] >= 0
+    for f in ("mv", "mvd"):
+        assert not ((got[f] != ref[f]).any(2) & used & (ref["best_idx"] != 4)[:, None]).any(), f
+    assert not ((got["mvp_idx"] != ref["mvp_idx"]) & used & (ref["best_idx"] < 3)[:, None]).any()
+    assert st_got[ref["state_out"]].tobytes() == st_ref[ref["state_out"]].tobytes()
+    hc, hr = xo.hash_slots(coef, got["out_off"], sz), xo.hash_slots(rec, got["out_off"], sz)
+    nz = ref["nnz"].any(1)
+    assert np.array_equal(hc[nz], ref["coef_hash"][nz]) and np.array_equal(hr, ref["rec_hash"])
 
 
 def get_trace() -> TraceData:
