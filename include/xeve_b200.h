@@ -292,6 +292,13 @@ XB200_API int xb200_rdo_bits(xb200_ctx *c, xb200_bits_item *items, int64_t n, xb
  * Baseline RDOQ -- sig_coeff, gtx, last_sig_coeff -- are not produced) */
 XB200_API int xb200_rdoq_rates(xb200_ctx *c, const xb200_sbac *states, int64_t n, xb200_rates *rates);
 
+/* xeve_pinter_analyze_cu over a list of CUs (host buffers).  Every item is decided independently from its own inputs
+ * (MVP candidates, input coder state, rate tables): CUs whose inputs do not depend on each other -- different pictures of
+ * a temporal layer, or a wavefront inside a picture -- go into one call.  coef / rec receive the winner's coefficient
+ * planes and reconstruction at items[i].out_off (rec may be NULL); states[items[i].state_out] receives s_next_best. */
+XB200_API int xb200_analyze_cu(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates,
+                               xb200_sbac *states, int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems);
+
 /* ---- hot-path operators ----------------------------------------------------------------------- */
 /* side: s16 buffer holding the org_bi blocks referenced by org_bi_off (may be NULL if none). */
 XB200_API int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side, int64_t side_elems, int mem);

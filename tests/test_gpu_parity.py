@@ -447,3 +447,25 @@ def test_rdoq_rate_tables_match_reference(trace, gpu_ctx):
     tr = trace.live
     assert gpu_ctx.rdoq_rates(tr.sbac).tobytes() == tr.rates.tobytes()
     assert xo.rdoq_rates(tr.sbac, api.RATES).tobytes() == tr.rates.tobytes()
+
+
+def _cu_to_device(cu, handles):
+    dev = cu.copy()
+    dev["cur_pic"] = handles[cu["cur_pic"]]
+    rp = cu["ref_pic"]
+    dev["ref_pic"] = np.where(rp >= 0, handles[np.clip(rp, 0, len(handles) - 1)], -1)
+    return dev
+
+
+def test_analyze_cu_matches_reference_in_situ(trace, gpu_ctx):
+    """xb200_analyze_cu == xeve_pinter_analyze_cu as it ran inside the reference encoder: best mode, IEEE-double RD cost,
+    refi / mv / mvd / mvp_idx, nnz, coefficient and reconstruction hashes, output coder state -- every traced CU."""
+    cu, sz, elems = tracedata.cu_slots(trace.cu)
+    got, st, coef, rec = gpu_ctx.analyze_cu(_cu_to_device(cu, gpu_ctx.handles), trace.cu_rates, trace.cu_sbac, elems)
+    assert len(np.unique(trace.cu["best_idx"])) == 5 and len(np.unique(trace.cu["log2_cuw"])) == 4
+    tracedata.check_cu_results(got, trace.cu, coef, rec, sz, st, trace.cu_sbac)
+    # and the oracle, element for element (covers the coefficients of CUs the hash check skips)
+    o, so, ocoef, orec = xo.analyze_cu_batch(trace.seq, trace.oracle_planes(), trace.cu_rates, cu, trace.cu_sbac, elems)
+    assert np.array_equal(coef, ocoef) and np.array_equal(rec, orec)
+    assert np.array_equal(got["cost"], o["cost"]) and np.array_equal(got["mvp_idx"], o["mvp_idx"])
+    assert st[cu["state_out"]].tobytes() == so[cu["state_out"]].tobytes()

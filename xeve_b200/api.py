@@ -89,6 +89,16 @@ BITS_ITEM = np.dtype([
 (CM_SKIP_FLAG, CM_PRED_MODE, CM_DIRECT, CM_INTER_DIR, CM_REFI, CM_MVP_IDX, CM_MVD, CM_CBF_ALL, CM_CBF_LUMA, CM_CBF_CB,
  CM_CBF_CR, CM_RUN, CM_LAST, CM_LEVEL, CM_COUNT) = (0, 2, 5, 6, 8, 10, 13, 14, 15, 16, 17, 18, 42, 44, 68)
 
+CU_ITEM = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("all_preds", "u1"), ("num_refp", "u1", (2,)), ("qp", "u1", (3,)), ("pad0_", "u1"),
+    ("max_search_range", "<i4"), ("ref_pic", "<i4", (2, 4)), ("ref_poc", "<i4", (2, 4)), ("lambda_mv", "<u4"), ("rate_idx", "<i4"),
+    ("state_in", "<i4"), ("state_out", "<i4"), ("lambda", "<f8", (3,)), ("dist_chroma_weight", "<f8", (2,)),
+    ("mvp", "<i2", (2, 4, 2)), ("refi_pred", "i1", (2, 4)), ("mv_dir", "<i2", (2, 2)), ("out_off", "<i8"), ("cost", "<f8"),
+    ("best_idx", "u1"), ("pad1_", "u1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)),
+    ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"), ("me_first", "<i4"), ("me_cnt", "<i4"),
+], align=True)
+
 VP = C.c_void_p
 _lib = None
 
@@ -132,6 +142,7 @@ def load():
         L.xb200_residue.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64, C.c_int]
         L.xb200_rdo_bits.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]
         L.xb200_rdoq_rates.argtypes = [VP, VP, C.c_int64, VP]
+        L.xb200_analyze_cu.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
         _lib = L
     return _lib
 
@@ -139,7 +150,7 @@ def load():
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
-           "xb200_rdo_bits", "xb200_rdoq_rates"]
+           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu"]
 
 
 def _p(a):
@@ -293,6 +304,17 @@ class Hotpath:
         out = np.zeros(len(states), RATES)
         self._ck(self.L.xb200_rdoq_rates(self.h, _p(states), len(states), _p(out)), "xb200_rdoq_rates")
         return out
+
+    def analyze_cu(self, items, rates, states, elems, want_rec=True):
+        """xeve_pinter_analyze_cu over a CU list -> (items with results, states with s_next_best slots, coef, rec)"""
+        items = np.ascontiguousarray(items, CU_ITEM).copy()
+        rates = np.ascontiguousarray(rates, RATES)
+        states = np.ascontiguousarray(states, SBAC).copy()
+        coef = np.zeros(elems, np.int16)
+        rec = np.zeros(elems, np.int16) if want_rec else None
+        self._ck(self.L.xb200_analyze_cu(self.h, _p(items), len(items), _p(rates), len(rates), _p(states), len(states), _p(coef),
+                                         _p(rec), elems), "xb200_analyze_cu")
+        return items, states, coef, rec
 
     def tq(self, items, rates, coef):
         items = np.ascontiguousarray(items, TQ_ITEM).copy()

@@ -16,6 +16,7 @@
 #include "xb200_residue2.cuh"
 #include "xb200_dct_tc.cuh"
 #include "xb200_rate.cuh"
+#include "xb200_analyze.cuh"
 #include <math.h>
 
 namespace {
@@ -46,6 +47,7 @@ struct xb200_ctx {
     int             *d_err = nullptr;
     int             *d_bins = nullptr; // 8 counters + 8 max-range
     DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
+    DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
     cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
     cudaStream_t     side[4] = {nullptr, nullptr, nullptr, nullptr}; // one per CU size: the four size-binned grids overlap
     cudaEvent_t      ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -224,6 +226,31 @@ int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *or
     return launch_residue2_v<L2, false>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
 }
 
+template <int L2>
+int launch_analyze(xb200_ctx *c, xb200_cu_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates, const xb200_sbac *d_st_in,
+                   xb200_sbac *d_st_out, int16_t *d_coef, int16_t *d_rec, int margin)
+{
+    if(cnt == 0) return XB200_OK;
+    using Cf = CuCfg<L2>;
+    const int W = 1 << L2, ext = W + 2 * margin + 7;
+    const int cap = (align_up(ext, 8) + 8) * ext + 16;
+    const size_t smem = Cf::smem_bytes(cap);
+    if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
+    int blocks_per_sm = 0, sms = 0;
+    CK(cudaFuncSetAttribute(k_analyze_cu<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_analyze_cu<L2>, Cf::CTA, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if(blocks_per_sm < 1) blocks_per_sm = 1;
+    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
+    int r = ensure(c->b_scr[L2 - 3], (size_t)grid * Cf::TEAMS * Cf::SCRATCH * sizeof(int16_t));
+    if(r) return r;
+    k_analyze_cu<L2><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec,
+                                                              static_cast<int16_t *>(c->b_scr[L2 - 3].p), c->d_tm64, c->sq, cap, c->d_err);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -255,7 +282,7 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     c->sq.me_level = seq->me_level; c->sq.hpel_cnt = seq->hpel_cnt; c->sq.qpel_cnt = seq->qpel_cnt;
     c->sq.me_complexity = seq->me_complexity;
     for(int i = 0; i < 2; i++) { c->sq.min_clip[i] = seq->min_clip[i]; c->sq.max_clip[i] = seq->max_clip[i]; }
-    c->sq.rdoq = seq->rdoq;
+    c->sq.rdoq = seq->rdoq; c->sq.merge_num = seq->merge_num; c->sq.gop_size = seq->gop_size;
     {   // opt-in: tensor-core transform stages inside xb200_residue (bit-identical to the integer stages)
         const char *e = getenv("XB200_TC_DCT");
         c->sq.tc_dct = (e && e[0] == '1') ? 1 : 0;
@@ -457,6 +484,81 @@ int xb200_pic_download(xb200_ctx *c, int32_t handle, int with_padding, int16_t *
 }
 
 // ---- probes -----------------------------------------------------------------------------------------------
+// ---- whole inter mode decision of a list of CUs ---------------------------------------------------------------------
+int xb200_analyze_cu(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
+                     int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems)
+{
+    if(!c || n < 0 || n_rates < 0 || n_states < 0 || elems < 0 || (n && (!items || !rates || !states || !coef)) || n > (1 << 26))
+        return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    if(c->seq.merge_num < 1 || c->seq.merge_num > 4 || c->seq.gop_size < 1) return XB200_ERR_INVALID_ARGUMENT;
+    std::vector<int32_t> order((size_t)4 * n);
+    int                  cnt[4] = {0, 0, 0, 0}, margin[4] = {0, 0, 0, 0};
+    for(int64_t i = 0; i < n; i++) {
+        const xb200_cu_item &it = items[i];
+        if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 3 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
+        const int w = 1 << it.log2_cuw, k = it.log2_cuw - 3;
+        if(!pic_ok(c, it.cur_pic) || it.slice_type > 1 || it.x < 0 || it.y < 0 || it.x + w > c->seq.w || it.y + w > c->seq.h ||
+           it.rate_idx < 0 || it.rate_idx >= n_rates || it.state_in < 0 || it.state_in >= n_states || it.state_out >= n_states ||
+           it.out_off < 0 || it.out_off + w * w * 3 / 2 > elems || it.max_search_range < 1 || it.max_search_range > 256)
+            return XB200_ERR_INVALID_ARGUMENT;
+        for(int l = 0; l < (it.slice_type == 0 ? 2 : 1); l++) {
+            if(it.num_refp[l] < 1 || it.num_refp[l] > XB200_MAX_REFP) return XB200_ERR_UNSUPPORTED;
+            for(int q = 0; q < it.num_refp[l]; q++) {
+                if(!pic_ok(c, it.ref_pic[l][q]) || !c->pics[it.ref_pic[l][q]].padded) return XB200_ERR_INVALID_ARGUMENT;
+                int d = it.poc - it.ref_poc[l][q];
+                d = d < 0 ? -d : d;
+                int dyn = (it.max_search_range * d + (c->seq.gop_size >> 1)) / c->seq.gop_size;
+                dyn = dyn < (it.max_search_range >> 2) ? (it.max_search_range >> 2) : (dyn > it.max_search_range ? it.max_search_range : dyn);
+                if(dyn + 2 > margin[k]) margin[k] = dyn + 2;
+            }
+            for(int q = 0; q < 4; q++)
+                if(it.refi_pred[l][q] >= (int)it.num_refp[l]) return XB200_ERR_INVALID_ARGUMENT;
+        }
+        order[(size_t)k * n + cnt[k]++] = (int32_t)i;
+    }
+    int r = sync_pics(c);
+    if(r) return r;
+    xb200_cu_item *d_items;
+    xb200_rates   *d_rates;
+    xb200_sbac    *d_in, *d_out;
+    int32_t       *d_order;
+    if((r = to_dev(c, c->b_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_aux0, rates, (size_t)n_rates, XB200_MEM_HOST, &d_rates))) return r;
+    if((r = to_dev(c, c->b_st0, states, (size_t)n_states, XB200_MEM_HOST, &d_in))) return r;
+    if((r = to_dev(c, c->b_st1, states, (size_t)n_states, XB200_MEM_HOST, &d_out))) return r;
+    if((r = to_dev(c, c->b_order, order.data(), order.size(), XB200_MEM_HOST, &d_order))) return r;
+    if((r = ensure(c->b_aux1, (size_t)elems * 2 + 64))) return r;
+    int16_t *d_coef = static_cast<int16_t *>(c->b_aux1.p), *d_rec = nullptr;
+    if(rec) {
+        if((r = ensure(c->b_aux2, (size_t)elems * 2 + 64))) return r;
+        d_rec = static_cast<int16_t *>(c->b_aux2.p);
+    }
+    CK(cudaStreamSynchronize(c->stream)); // `order` is pageable host memory
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if((r = fork_streams(c))) return r;
+    if((r = launch_analyze<6>(c, d_items, d_order + 3 * n, cnt[3], d_rates, d_in, d_out, d_coef, d_rec, margin[3]))) return r;
+    if((r = launch_analyze<5>(c, d_items, d_order + 2 * n, cnt[2], d_rates, d_in, d_out, d_coef, d_rec, margin[2]))) return r;
+    if((r = launch_analyze<4>(c, d_items, d_order + 1 * n, cnt[1], d_rates, d_in, d_out, d_coef, d_rec, margin[1]))) return r;
+    if((r = launch_analyze<3>(c, d_items, d_order + 0 * n, cnt[0], d_rates, d_in, d_out, d_coef, d_rec, margin[0]))) return r;
+    if((r = join_streams(c))) return r;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, states, d_out, (size_t)n_states, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, coef, d_coef, (size_t)elems, XB200_MEM_HOST))) return r;
+    if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, XB200_MEM_HOST))) return r;
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    if(err) { cudaMemset(c->d_err, 0, sizeof(int)); return XB200_ERR_UNEXPECTED; }
+    return XB200_OK;
+}
+
 } // extern "C"
 template <typename OutT, typename K>
 static int run_probe(xb200_ctx *c, const xb200_blk_item *items, int64_t n, OutT *out, int mem, K kernel)

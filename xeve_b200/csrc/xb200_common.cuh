@@ -22,6 +22,7 @@ struct SeqDev {
     int32_t me_level, hpel_cnt, qpel_cnt, me_complexity;
     int32_t min_clip[2], max_clip[2];
     int32_t rdoq;
+    int32_t merge_num, gop_size; // analyze_cu: skip candidates per list, pi->gop_size
     int32_t tc_dct; // 32/64-point forward DCT on tcgen05 (bit-identical; off by default)
 };
 

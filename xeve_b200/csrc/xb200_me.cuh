@@ -115,32 +115,25 @@ XB_DEV void me_d16(int c, int &dx, int &dy) // (-4,0) (-3,1) .. (0,4) .. (4,0) .
     dy = c <= 4 ? c : (c <= 12 ? 8 - c : c - 16);
 }
 
+// One pi->fn_me call by one team.  smem_raw: the team's me_team_bytes() area with the mbarrier at offset 0 already
+// initialised (count 1); `phase` is the barrier's parity and persists across calls of the same team.  Results are
+// uniform across the team's threads.
 template <int L2>
-__global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict__ pics, xb200_me_item *__restrict__ items,
-                                                        const int32_t *__restrict__ order, int n, const int16_t *__restrict__ side,
-                                                        SeqDev sq, int win_cap_elems, int *__restrict__ err_flag)
+XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, const xb200_me_item *__restrict__ it,
+                      const int16_t *__restrict__ side, const SeqDev &sq, int win_cap_elems, int *__restrict__ err_flag, int tid,
+                      uint32_t &phase, int &o_mv_x, int &o_mv_y, uint32_t &o_cost, int &o_mot_bits)
 {
     using Gm = MeGeom<L2>;
     constexpr int W = Gm::W, T = Gm::T, G = Gm::G;
-    extern __shared__ __align__(16) unsigned char smem_all[];
-    const int      team = threadIdx.x / T;
-    unsigned char *smem_raw = smem_all + (size_t)team * me_team_bytes(L2, win_cap_elems);
     uint64_t *bar   = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *costs = reinterpret_cast<uint32_t *>(smem_raw + 16);                       // cost table of the current run
     int32_t  *red   = reinterpret_cast<int32_t *>(smem_raw + 16 + ME_MAX_CAND * 4);      // 8 ints
     int16_t  *org   = reinterpret_cast<int16_t *>(smem_raw + 16 + ME_MAX_CAND * 4 + 32);
     int16_t  *tmp   = org + W * W;         // (W + 7) * W, horizontal pass of 2-D interpolation
     int16_t  *win   = tmp + (W + 8) * W;   // staged reference window (+ slack)
-
-    const int      tid = threadIdx.x % T, lane = tid & 31; // tid = thread index inside the team
+    const int      lane = tid & 31;
     const int      grp = tid / G, j = tid % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    const int      item_no = blockIdx.x * Gm::TEAMS + team;
-    if(item_no >= n) return; // whole team leaves (teams never meet at a block barrier when TEAMS > 1)
-    xb200_me_item *it = &items[order[item_no]];
-
-    if(tid == 0) mbar_init(bar, 1);
-    uint32_t phase = 0;
 
     const PicDev &cur = pics[it->cur_pic], &ref = pics[it->ref_pic];
     const int      x = it->x, y = it->y, bi = it->bi, lidx = it->lidx, bd = sq.bd;
@@ -494,6 +487,28 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
         if(rb < best) { best = rb; mv_x = (int16_t)((rx - x) << 2); mv_y = (int16_t)((ry - y) << 2); }
     }
 
+    o_mv_x = mv_x; o_mv_y = mv_y; o_cost = best; o_mot_bits = mot_bits_l;
+    me_team_sync<T>(); // the team's shared area is free again
+}
+
+template <int L2>
+__global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict__ pics, xb200_me_item *__restrict__ items,
+                                                        const int32_t *__restrict__ order, int n, const int16_t *__restrict__ side,
+                                                        SeqDev sq, int win_cap_elems, int *__restrict__ err_flag)
+{
+    using Gm = MeGeom<L2>;
+    constexpr int T = Gm::T;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int      team = threadIdx.x / T, tid = threadIdx.x % T; // tid = thread index inside the team
+    unsigned char *smem_raw = smem_all + (size_t)team * me_team_bytes(L2, win_cap_elems);
+    const int      item_no = blockIdx.x * Gm::TEAMS + team;
+    if(item_no >= n) return; // whole team leaves (teams never meet at a block barrier when TEAMS > 1)
+    xb200_me_item *it = &items[order[item_no]];
+    if(tid == 0) mbar_init(reinterpret_cast<uint64_t *>(smem_raw), 1);
+    uint32_t phase = 0, best;
+    int      mv_x, mv_y, mot_bits_l;
+    const int lidx = it->lidx, other_bits = it->mot_bits_in[lidx ? 0 : 1];
+    me_search<L2>(smem_raw, pics, it, side, sq, win_cap_elems, err_flag, tid, phase, mv_x, mv_y, best, mot_bits_l);
     if(tid == 0) {
         it->mv_out[0] = (int16_t)mv_x; it->mv_out[1] = (int16_t)mv_y; it->cost = best;
         it->mot_bits_out[lidx] = mot_bits_l;

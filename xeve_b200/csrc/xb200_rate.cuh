@@ -76,7 +76,7 @@ __device__ __forceinline__ void cb_refi(Cabac &c, int num_refp, int refi)
     }
 }
 // xeve_eco_run_length_cc of one transform block; warp-cooperative, engine state valid on lane 0 only
-__device__ __forceinline__ void cb_run_length(Cabac &c, const int16_t *__restrict__ coef, int l2, int num_sig, int ch, int lane)
+__device__ __forceinline__ void cb_run_length(Cabac &c, const int16_t *coef, int l2, int num_sig, int ch, int lane)
 {
     const uint16_t *scan = g_scan + scan_base(l2);
     const int       n = 1 << (2 * l2), t0 = ch == 0 ? 0 : 2;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void cb_run_length(Cabac &c, const int16_t *__restric
     bool            done = false;
     for(int base = 0; base < n && !done; base += 32) {
         const int sp = base + lane;
-        const int v = sp < n ? coef[scan[sp]] : 0;
+        const int v = sp < n ? __ldcg(coef + scan[sp]) : 0;   // L2 read: the planes may have been written by this CTA
         uint32_t  nzm = __ballot_sync(0xffffffffu, v != 0);
         int       prev = -1;
         while(nzm && !done) {
