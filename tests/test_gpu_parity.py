@@ -253,6 +253,9 @@ def _upload_trace(tr):
     ("cif", "fast", 20, "me_sub=3;me_sub_pos=8", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # quarter-pel stage (slow preset)
     ("cif", "fast", 20, "me_sub=1", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),      # integer-pel only: me_ipel_refinement
     ("cif", "fast", 20, "rdoq=0;qp=27", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # plain quantiser, lower QP
+    ("cif", "fast", 20, "ref=2;me_ref_num=2;qp=24", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # two references per list
+    ("cif", "fast", 12, "bframes=0", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),     # low delay: static range 64
+    ("cif", "fast", 12, "bframes=0;inter_slice_type=1", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)])),  # P slices
 ])
 def test_me_mc_tq_other_configs(name, preset, frames, extra, override):
     tr = tracedata.live_trace(name, frames=frames, pic_lo=1, pic_hi=2, preset=preset, extra=extra, **override)
@@ -273,7 +276,12 @@ def test_me_mc_tq_other_configs(name, preset, frames, extra, override):
         m = _item_mask(tq, len(coef))
         assert np.array_equal(nnz_ref, tr.tq["nnz"])  # replay == in situ
         assert np.array_equal(it2["nnz"], nnz_ref) and np.array_equal(coef[m], coef_ref[m])
-        assert len(tr.me) > 500
+        assert len(tr.me) > 300
+        # the whole CU decision under this configuration
+        cu, sz, elems = tracedata.cu_slots(tr.cu)
+        got, st, coef, rec = hp.analyze_cu(_cu_to_device(cu, hp.handles), tr.cu_rates, tr.cu_sbac, elems)
+        tracedata.check_cu_results(got, tr.cu, coef, rec, sz, st, tr.cu_sbac)
+        assert len(cu) > 300
     finally:
         hp.close()
 

@@ -36,9 +36,9 @@ struct CuHdr {
 };
 #define CU_MAX_COST (1.7e+308)
 
-template <int L2> struct CuCfg {
+template <int L2, int TEAMS_ = Res2Cfg<L2>::TEAMS> struct CuCfg { // TEAMS_: CUs in flight per CTA (fewer when the search window is large)
     using R = Res2Cfg<L2>;
-    static constexpr int T = R::T, CTA = R::CTA, TEAMS = R::TEAMS, N = R::N, NY = N * N, NCH = NY >> 2, NP = R::PRED;
+    static constexpr int T = R::T, TEAMS = TEAMS_, CTA = T * TEAMS, N = R::N, NY = N * N, NCH = NY >> 2, NP = R::PRED;
     static constexpr int HDR = ((int)sizeof(CuHdr) + 15) & ~15;
     static constexpr int ORGBI = NY * 2;                       // 2*org - pred block of the bi search (shared)
     static constexpr int SCRATCH = 5 * 3 * NP;                 // s16 elements of global scratch per team
@@ -234,15 +234,15 @@ __device__ __noinline__ uint32_t cu_me(const CuTeam<L2> &Tm, const PicDev *__res
     return cost;
 }
 
-template <int L2>
-__global__ void __launch_bounds__(CuCfg<L2>::CTA) k_analyze_cu(const PicDev *__restrict__ pics, xb200_cu_item *__restrict__ items,
+template <int L2, int TEAMS>
+__global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicDev *__restrict__ pics, xb200_cu_item *__restrict__ items,
                                                                const int32_t *__restrict__ order, int n, const xb200_rates *__restrict__ rates,
                                                                const xb200_sbac *__restrict__ st_in, xb200_sbac *__restrict__ st_out,
                                                                int16_t *__restrict__ coef_out, int16_t *__restrict__ rec_out,
                                                                int16_t *__restrict__ scratch, const int8_t *__restrict__ g_tm64, SeqDev sq,
                                                                int win_cap, int *__restrict__ err_flag)
 {
-    using Cf = CuCfg<L2>;
+    using Cf = CuCfg<L2, TEAMS>;
     constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NCH = Cf::NCH, NP = Cf::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int8_t *tm = reinterpret_cast<int8_t *>(smem_raw), *tmT = tm + 4096;

@@ -226,29 +226,40 @@ int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *or
     return launch_residue2_v<L2, false>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
 }
 
+template <int L2, int TEAMS>
+int launch_analyze_v(xb200_ctx *c, xb200_cu_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates, const xb200_sbac *d_st_in,
+                     xb200_sbac *d_st_out, int16_t *d_coef, int16_t *d_rec, int cap)
+{
+    using Cf = CuCfg<L2, TEAMS>;
+    const size_t smem = Cf::smem_bytes(cap);
+    int blocks_per_sm = 0, sms = 0;
+    CK(cudaFuncSetAttribute(k_analyze_cu<L2, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_analyze_cu<L2, TEAMS>, Cf::CTA, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if(blocks_per_sm < 1) blocks_per_sm = 1;
+    const int want = (cnt + TEAMS - 1) / TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
+    int r = ensure(c->b_scr[L2 - 3], (size_t)grid * TEAMS * Cf::SCRATCH * sizeof(int16_t));
+    if(r) return r;
+    k_analyze_cu<L2, TEAMS><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec,
+                                                                     static_cast<int16_t *>(c->b_scr[L2 - 3].p), c->d_tm64, c->sq, cap, c->d_err);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
 template <int L2>
 int launch_analyze(xb200_ctx *c, xb200_cu_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates, const xb200_sbac *d_st_in,
                    xb200_sbac *d_st_out, int16_t *d_coef, int16_t *d_rec, int margin)
 {
     if(cnt == 0) return XB200_OK;
-    using Cf = CuCfg<L2>;
-    const int W = 1 << L2, ext = W + 2 * margin + 7;
-    const int cap = (align_up(ext, 8) + 8) * ext + 16;
-    const size_t smem = Cf::smem_bytes(cap);
-    if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
-    int blocks_per_sm = 0, sms = 0;
-    CK(cudaFuncSetAttribute(k_analyze_cu<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_analyze_cu<L2>, Cf::CTA, smem));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    if(blocks_per_sm < 1) blocks_per_sm = 1;
-    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
-    int r = ensure(c->b_scr[L2 - 3], (size_t)grid * Cf::TEAMS * Cf::SCRATCH * sizeof(int16_t));
-    if(r) return r;
-    k_analyze_cu<L2><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec,
-                                                              static_cast<int16_t *>(c->b_scr[L2 - 3].p), c->d_tm64, c->sq, cap, c->d_err);
-    c->launches++;
-    CK(cudaGetLastError());
-    return XB200_OK;
+    const int    W = 1 << L2, ext = W + 2 * margin + 7;
+    const int    cap = (align_up(ext, 8) + 8) * ext + 16;
+    const size_t lim = 227 * 1024;
+    if constexpr(L2 <= 4) { // a warp per CU: as many CUs per CTA as the staged search windows leave room for
+        if(CuCfg<L2, 4>::smem_bytes(cap) <= lim) return launch_analyze_v<L2, 4>(c, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec, cap);
+        if(CuCfg<L2, 2>::smem_bytes(cap) <= lim) return launch_analyze_v<L2, 2>(c, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec, cap);
+    }
+    if(CuCfg<L2, 1>::smem_bytes(cap) <= lim) return launch_analyze_v<L2, 1>(c, d_items, order, cnt, d_rates, d_st_in, d_st_out, d_coef, d_rec, cap);
+    return XB200_ERR_UNSUPPORTED;
 }
 
 } // namespace
