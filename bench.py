@@ -206,6 +206,19 @@ def run_b200(args, rank, world, dist):
         step_host()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    # ---- the fused per-CU decision over the same picture (xb200_analyze_cu, host-buffer API) ------------------------
+    cu_items = fw.build_cu(hp.rdoq_rates, max_search_range=int(seq["me_range"][0]), seed=rank)
+    cu_out, _, cu_coef, _ = hp.analyze_cu(cu_items, fw.cu_rates, fw.cu_states, fw.cu_elems, want_rec=True)  # warm-up
+    t_cu_k, t0 = 0.0, time.perf_counter()
+    cu_steps = max(2, args.steps // 4)
+    for _ in range(cu_steps):
+        hp.analyze_cu(cu_items, fw.cu_rates, fw.cu_states, fw.cu_elems, want_rec=True)
+        t_cu_k += hp.last_kernel_ms
+    t_cu = (time.perf_counter() - t0) / cu_steps
+    analyze = {"cus_per_frame": int(len(cu_items)), "kernel_ms_per_frame": round(t_cu_k / cu_steps, 3),
+               "host_api_ms_per_frame": round(t_cu * 1e3, 3), "frames_per_s_kernel": round(1e3 / (t_cu_k / cu_steps), 2),
+               "best_mode_hist": np.bincount(cu_out["best_idx"], minlength=5).tolist(),
+               "note": "whole xeve_pinter_analyze_cu per CU on the device (skip/direct/L0/L1/BI + cbf RDO + CABAC bit counts)"}
     sampler.stop_flag = True
     frame_bytes = W * H * 3 // 2 * bps
     h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
@@ -243,6 +256,7 @@ def run_b200(args, rank, world, dist):
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: round(v, 3) for k, v in per_stage.items()},
+        "analyze_cu": analyze,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get(dom),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

@@ -57,13 +57,13 @@ XB_DEV void cu_st_copy(CuHdr &H, int dst, int src, int lane)
     if(lane == 0) H.rg[dst] = H.rg[src];
     __syncwarp();
 }
-template <int T> XB_DEV void cu_st_save(CuHdr &H, int dst, int src, int tt)
+template <int T> __device__ __noinline__ void cu_st_save(CuHdr &H, int dst, int src, int tt)
 {
     if(tt < 32) cu_st_copy(H, dst, src, tt);
     team_sync<T>();
 }
 // SBAC_LOAD(s_temp_run, slot src) -> xeve_sbac_bit_reset -> syntax of `it` -> xeve_get_bit_number; the coded state stays in ST_RUN
-template <int T> XB_DEV uint32_t cu_count(CuHdr &H, const xb200_bits_item &it, const int16_t *coef, int src, int tt)
+template <int T> __device__ __noinline__ uint32_t cu_count(CuHdr &H, const xb200_bits_item &it, const int16_t *coef, int src, int tt)
 {
     if(tt < 32) {
         cu_st_copy(H, ST_RUN, src, tt);
@@ -111,6 +111,18 @@ template <int LN, int T> XB_DEV int64_t ssd_plane_t(const int16_t *__restrict__ 
     return team_sum_s64<T>(part, tt, X);
 }
 
+// prediction of the CU for (refi, mv) into the team's pred buffer: one out-of-line copy of the interpolation code per size
+template <int L2>
+__device__ __noinline__ void cu_predict(const PicDev *__restrict__ pics, const xb200_cu_item &cu, const SeqDev &sq, int refi0, int refi1, int mv00,
+                                        int mv01, int mv10, int mv11, int16_t *pred, int16_t *aux, int16_t *tmp, int tt)
+{
+    const int8_t  refi[2] = {(int8_t)refi0, (int8_t)refi1};
+    const int16_t mv[2][2] = {{(int16_t)mv00, (int16_t)mv01}, {(int16_t)mv10, (int16_t)mv11}};
+    xb200_mc_item mc;
+    cu_mc_item(cu, 1 << L2, refi, mv, mc);
+    mc_item_t<L2, Res2Cfg<L2>::T>(pics, mc, sq, pred, aux, tmp, tt);
+}
+
 // per-team working set handed to the helpers
 template <int L2> struct CuTeam {
     CuHdr         *H;
@@ -123,31 +135,14 @@ template <int L2> struct CuTeam {
     int            so[3];
 };
 
-// pinter_residue_rdo for mode pidx (H.md[pidx].refi/mv/mvd set and visible): fills md[pidx].nnz/cbf, leaves s_temp_best in ST_MODE
-template <int L2>
-__device__ __noinline__ double cu_residue_rdo(const CuTeam<L2> &Tm, const PicDev *__restrict__ pics, const xb200_rates *__restrict__ rt,
-                                              const SeqDev &sq, int pidx, uint8_t mi0, uint8_t mi1, int tt)
+// The cbf decisions of pinter_residue_rdo (src_base/xeve_pinter.c:1087-1335) for one candidate mode whose transform results are
+// known: store[] = nnz of the coded planes, d0 / d1 = SSD of prediction / reconstruction, gco = the coefficient planes.
+// Returns the RD cost, the chosen plane mask in cbf, and leaves s_temp_best in ST_MODE.
+template <int T>
+__device__ __noinline__ double cu_cbf_decide(CuHdr &H, int pidx, const CuMode &M, uint8_t mi0, uint8_t mi1, const int *store, const int64_t *d0,
+                                             const int64_t *d1, const int16_t *gco, int &cbf_out, int tt)
 {
-    using Cf = CuCfg<L2>;
-    constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NCH = Cf::NCH, NP = Cf::NP;
-    constexpr int LNMAX = L2 >= 5 ? L2 : 5;
-    CuHdr               &H = *Tm.H;
     const xb200_cu_item &cu = H.cu;
-    CuMode              &M = H.md[pidx];
-    int16_t *gco = Tm.scratch + (size_t)(3 * pidx) * NP, *grec = gco + NP, *gpred = grec + NP;
-    xb200_mc_item mc;
-    cu_mc_item(cu, N, M.refi, M.mv, mc);
-    mc_item_t<L2, T>(pics, mc, sq, Tm.pred, Tm.aux, reinterpret_cast<int16_t *>(Tm.TB), tt);
-    for(int e = tt; e < NP; e += T) gpred[e] = Tm.pred[e];
-    int     store[3];
-    int64_t d0[3], d1[3];
-    residue_plane<L2, T, LNMAX, false>(Tm.org[0], Tm.so[0], Tm.pred, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco, grec, 1, cu.qp[0], cu.lambda[0], 0,
-                                       cu.slice_type, rt, sq, tt, H.X, store[0], d0[0], d1[0], nullptr, nullptr);
-    residue_plane<L2 - 1, T, LNMAX, false>(Tm.org[1], Tm.so[1], Tm.pred + NY, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco + NY, grec + NY, 1, cu.qp[1],
-                                           cu.lambda[1], 1, cu.slice_type, rt, sq, tt, H.X, store[1], d0[1], d1[1], nullptr, nullptr);
-    residue_plane<L2 - 1, T, LNMAX, false>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco + NY + NCH, grec + NY + NCH,
-                                           1, cu.qp[2], cu.lambda[2], 2, cu.slice_type, rt, sq, tt, H.X, store[2], d0[2], d1[2], nullptr, nullptr);
-    team_sync<T>(); // coefficient planes visible to the coder warp
     const double   w0 = cu.dist_chroma_weight[0], w1 = cu.dist_chroma_weight[1];
     xb200_bits_item bi = cu_bits_item(cu, 1, pidx, 0);
     bi.refi[0] = M.refi[0]; bi.refi[1] = M.refi[1]; bi.mvp_idx[0] = mi0; bi.mvp_idx[1] = mi1;
@@ -200,6 +195,36 @@ __device__ __noinline__ double cu_residue_rdo(const CuTeam<L2> &Tm, const PicDev
         best = __dadd_rn(best, __dmul_rn((double)bits, cu.lambda[0]));
         cu_st_save<T>(H, ST_MODE, ST_RUN, tt);
     }
+    cbf_out = cbf;
+    return best;
+}
+
+// pinter_residue_rdo for mode pidx (H.md[pidx].refi/mv/mvd set and visible): fills md[pidx].nnz/cbf, leaves s_temp_best in ST_MODE
+template <int L2>
+__device__ __noinline__ double cu_residue_rdo(const CuTeam<L2> &Tm, const PicDev *__restrict__ pics, const xb200_rates *__restrict__ rt,
+                                              const SeqDev &sq, int pidx, uint8_t mi0, uint8_t mi1, int tt)
+{
+    using Cf = CuCfg<L2>;
+    constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NCH = Cf::NCH, NP = Cf::NP;
+    constexpr int LNMAX = L2 >= 5 ? L2 : 5;
+    CuHdr               &H = *Tm.H;
+    const xb200_cu_item &cu = H.cu;
+    CuMode              &M = H.md[pidx];
+    int16_t *gco = Tm.scratch + (size_t)(3 * pidx) * NP, *grec = gco + NP, *gpred = grec + NP;
+    cu_predict<L2>(pics, cu, sq, M.refi[0], M.refi[1], M.mv[0][0], M.mv[0][1], M.mv[1][0], M.mv[1][1], Tm.pred, Tm.aux,
+                   reinterpret_cast<int16_t *>(Tm.TB), tt);
+    for(int e = tt; e < NP; e += T) gpred[e] = Tm.pred[e];
+    int     store[3];
+    int64_t d0[3], d1[3];
+    residue_plane<L2, T, LNMAX, false>(Tm.org[0], Tm.so[0], Tm.pred, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco, grec, 1, cu.qp[0], cu.lambda[0], 0,
+                                       cu.slice_type, rt, sq, tt, H.X, store[0], d0[0], d1[0], nullptr, nullptr);
+    residue_plane<L2 - 1, T, LNMAX, false>(Tm.org[1], Tm.so[1], Tm.pred + NY, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco + NY, grec + NY, 1, cu.qp[1],
+                                           cu.lambda[1], 1, cu.slice_type, rt, sq, tt, H.X, store[1], d0[1], d1[1], nullptr, nullptr);
+    residue_plane<L2 - 1, T, LNMAX, false>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco + NY + NCH, grec + NY + NCH,
+                                           1, cu.qp[2], cu.lambda[2], 2, cu.slice_type, rt, sq, tt, H.X, store[2], d0[2], d1[2], nullptr, nullptr);
+    team_sync<T>(); // coefficient planes visible to the coder warp
+    int          cbf;
+    const double best = cu_cbf_decide<T>(H, pidx, M, mi0, mi1, store, d0, d1, gco, cbf, tt);
     if(tt == 0) {
         M.cbf = cbf;
         M.nnz[0] = (cbf & 1) ? store[0] : 0; M.nnz[1] = (cbf & 2) ? store[1] : 0; M.nnz[2] = (cbf & 4) ? store[2] : 0;
@@ -308,9 +333,8 @@ __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicD
                     const int8_t  refi[2] = {cu.refi_pred[0][idx0], (int8_t)(B ? cu.refi_pred[1][idx1] : -1)};
                     const int16_t mv[2][2] = {{cu.mvp[0][idx0][0], cu.mvp[0][idx0][1]}, {cu.mvp[1][idx1][0], cu.mvp[1][idx1][1]}};
                     if(refi[0] < 0 && refi[1] < 0) continue;
-                    xb200_mc_item mc;
-                    cu_mc_item(cu, N, refi, mv, mc);
-                    mc_item_t<L2, T>(pics, mc, sq, Tm.pred, Tm.aux, reinterpret_cast<int16_t *>(Tm.TB), tt);
+                    cu_predict<L2>(pics, cu, sq, refi[0], refi[1], mv[0][0], mv[0][1], mv[1][0], mv[1][1], Tm.pred, Tm.aux,
+                                   reinterpret_cast<int16_t *>(Tm.TB), tt);
                     const int64_t cy = ssd_plane_t<L2, T>(Tm.org[0], Tm.so[0], Tm.pred, sh, tt, H.X);
                     const int64_t cb = ssd_plane_t<L2 - 1, T>(Tm.org[1], Tm.so[1], Tm.pred + NY, sh, tt, H.X);
                     const int64_t cr = ssd_plane_t<L2 - 1, T>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, sh, tt, H.X);
@@ -411,9 +435,8 @@ __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicD
                 int      refi_best = 0;
                 refi[lidx_ref] = m_refi[lidx_ref];
                 for(int iter = 0; iter < 4; iter++) {
-                    xb200_mc_item mc;
-                    cu_mc_item(cu, N, refi, m_mv, mc);
-                    mc_item_t<L2, T>(pics, mc, sq, Tm.pred, Tm.aux, reinterpret_cast<int16_t *>(Tm.TB), tt);
+                    cu_predict<L2>(pics, cu, sq, refi[0], refi[1], m_mv[0][0], m_mv[0][1], m_mv[1][0], m_mv[1][1], Tm.pred, Tm.aux,
+                                   reinterpret_cast<int16_t *>(Tm.TB), tt);
                     for(int e = tt; e < NY; e += T)   // get_org_bi
                         Tm.org_bi[e] = (int16_t)(((int)Tm.org[0][(ptrdiff_t)(e >> L2) * Tm.so[0] + (e & (N - 1))] << 1) - (int)Tm.pred[e]);
                     team_sync<T>();
@@ -454,9 +477,8 @@ __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicD
         const CuMode &M = H.md[best_idx];
         int16_t      *gc = coef_out + cu.out_off, *gr = rec_out ? rec_out + cu.out_off : nullptr;
         if(best_idx == 3) {
-            xb200_mc_item mc;
-            cu_mc_item(cu, N, M.refi, M.mv, mc);
-            mc_item_t<L2, T>(pics, mc, sq, Tm.pred, Tm.aux, reinterpret_cast<int16_t *>(Tm.TB), tt);
+            cu_predict<L2>(pics, cu, sq, M.refi[0], M.refi[1], M.mv[0][0], M.mv[0][1], M.mv[1][0], M.mv[1][1], Tm.pred, Tm.aux,
+                           reinterpret_cast<int16_t *>(Tm.TB), tt);
             for(int e = tt; e < NP; e += T) {
                 gc[e] = 0;
                 if(gr) gr[e] = Tm.pred[e];

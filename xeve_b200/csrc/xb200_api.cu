@@ -17,6 +17,7 @@
 #include "xb200_dct_tc.cuh"
 #include "xb200_rate.cuh"
 #include "xb200_analyze.cuh"
+#include "xb200_pipeline.cuh"
 #include <math.h>
 
 namespace {
@@ -48,6 +49,8 @@ struct xb200_ctx {
     int             *d_bins = nullptr; // 8 counters + 8 max-range
     DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
     DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
+    DevBuf           b_cu_items, b_cu_rates, b_cu_state, b_cu_me, b_cu_res, b_cu_mc, b_cu_cur, b_cu_off, b_cu_side, b_cu_order,
+                     b_cu_coef, b_cu_rec; // CU pipeline
     cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
     cudaStream_t     side[4] = {nullptr, nullptr, nullptr, nullptr}; // one per CU size: the four size-binned grids overlap
     cudaEvent_t      ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -142,12 +145,12 @@ __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t
     if(i < n) {
         const xb200_me_item &it = items[i];
         const int            l2 = it.log2_cuw;
-        key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : 4;
+        key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : (l2 == 0 ? 5 : 4); // log2 0: slot left empty by the CU pipeline
         int d = it.poc - it.ref_poc;
         d     = d < 0 ? -d : d;
         int dyn = (it.max_search_range * d + (it.gop_size >> 1)) / max(1, it.gop_size);
         dyn     = max(it.max_search_range >> 2, min(it.max_search_range, dyn));
-        margin  = it.bi ? 5 : dyn + 2;
+        margin  = it.bi ? 6 : dyn + 2; // bi: window radius 5, +1 for the integer refinement pass (me_level 1)
     }
 #pragma unroll
     for(int k = 0; k < 5; k++) { // warp-aggregated: one atomic per warp and bin
@@ -200,7 +203,7 @@ int launch_me(xb200_ctx *c, xb200_me_item *d_items, const int32_t *order, int cn
 
 template <int L2, bool USE_TC>
 int launch_residue2_v(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates,
-                      int16_t *d_coef, int16_t *d_rec)
+                      int16_t *d_coef, int16_t *d_rec, int16_t *d_pred)
 {
     using Cf = Res2Cfg<L2>;
     static int blocks_per_sm = 0, sms = 0;
@@ -212,18 +215,18 @@ int launch_residue2_v(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *
         if(blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
-    k_residue2<L2, USE_TC><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq);
+    k_residue2<L2, USE_TC><<<grid, Cf::CTA, smem, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_rates, d_coef, d_rec, c->d_tm64, c->sq, d_pred);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
 }
 template <int L2>
 int launch_residue2(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *order, int cnt, const xb200_rates *d_rates,
-                    int16_t *d_coef, int16_t *d_rec)
+                    int16_t *d_coef, int16_t *d_rec, int16_t *d_pred = nullptr)
 {
     if(cnt == 0) return XB200_OK;
-    if(Res2Cfg<L2>::TC && c->sq.tc_dct && c->sq.bd <= 10) return launch_residue2_v<L2, true>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
-    return launch_residue2_v<L2, false>(c, d_items, order, cnt, d_rates, d_coef, d_rec);
+    if(Res2Cfg<L2>::TC && c->sq.tc_dct && c->sq.bd <= 10) return launch_residue2_v<L2, true>(c, d_items, order, cnt, d_rates, d_coef, d_rec, d_pred);
+    return launch_residue2_v<L2, false>(c, d_items, order, cnt, d_rates, d_coef, d_rec, d_pred);
 }
 
 template <int L2, int TEAMS>
@@ -496,6 +499,9 @@ int xb200_pic_download(xb200_ctx *c, int32_t handle, int with_padding, int16_t *
 
 // ---- probes -----------------------------------------------------------------------------------------------
 // ---- whole inter mode decision of a list of CUs ---------------------------------------------------------------------
+static int analyze_pipeline(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
+                            int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems, const int32_t *order, const int *cnt);
+
 int xb200_analyze_cu(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
                      int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems)
 {
@@ -531,6 +537,10 @@ int xb200_analyze_cu(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_
     }
     int r = sync_pics(c);
     if(r) return r;
+    {   // default: the pipeline of frame-wide grids; XB200_ANALYZE=fused selects the one-team-per-CU kernel (same results)
+        const char *e = getenv("XB200_ANALYZE");
+        if(!(e && e[0] == 'f')) return analyze_pipeline(c, items, n, rates, n_rates, states, n_states, coef, rec, elems, order.data(), cnt);
+    }
     xb200_cu_item *d_items;
     xb200_rates   *d_rates;
     xb200_sbac    *d_in, *d_out;
@@ -979,8 +989,16 @@ int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16
     return XB200_OK;
 }
 
+static int residue_impl(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
+                        int16_t *rec, int64_t elems, int mem, int16_t *pred_dev);
 int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
                   int16_t *rec, int64_t elems, int mem)
+{
+    return residue_impl(c, items, n, rates, n_rates, coef, rec, elems, mem, nullptr);
+}
+// pred_dev (device pointer or null): the prediction of every item is stored next to its coefficients (CU pipeline)
+static int residue_impl(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, int16_t *coef,
+                        int16_t *rec, int64_t elems, int mem, int16_t *pred_dev)
 {
     if(!c || n < 0 || (n && (!items || !coef || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
@@ -1021,10 +1039,10 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
     CK(cudaStreamSynchronize(c->stream));
     if(bins[4]) return XB200_ERR_UNSUPPORTED;
     if((r = fork_streams(c))) return r;
-    if((r = launch_residue2<6>(c, d_items, order + 3 * n, bins[3], d_rates, d_coef, d_rec))) return r;
-    if((r = launch_residue2<5>(c, d_items, order + 2 * n, bins[2], d_rates, d_coef, d_rec))) return r;
-    if((r = launch_residue2<4>(c, d_items, order + 1 * n, bins[1], d_rates, d_coef, d_rec))) return r;
-    if((r = launch_residue2<3>(c, d_items, order + 0 * n, bins[0], d_rates, d_coef, d_rec))) return r;
+    if((r = launch_residue2<6>(c, d_items, order + 3 * n, bins[3], d_rates, d_coef, d_rec, pred_dev))) return r;
+    if((r = launch_residue2<5>(c, d_items, order + 2 * n, bins[2], d_rates, d_coef, d_rec, pred_dev))) return r;
+    if((r = launch_residue2<4>(c, d_items, order + 1 * n, bins[1], d_rates, d_coef, d_rec, pred_dev))) return r;
+    if((r = launch_residue2<3>(c, d_items, order + 0 * n, bins[0], d_rates, d_coef, d_rec, pred_dev))) return r;
     if((r = join_streams(c))) return r;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
@@ -1034,6 +1052,122 @@ int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb20
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+} // extern "C"
+
+namespace {
+template <int L2> int launch_skip(xb200_ctx *c, const xb200_cu_item *d_items, const int32_t *order, int cnt, const xb200_sbac *d_in,
+                                         CuState *d_state, int16_t *d_scr, int64_t elems)
+{
+    if(cnt == 0) return XB200_OK;
+    using Cf = SkipCfg<L2>;
+    CK(cudaFuncSetAttribute(k_cu_skip<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM));
+    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < 148 * 8 ? want : 148 * 8;
+    k_cu_skip<L2><<<grid, Cf::CTA, Cf::SMEM, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_in, d_state, d_scr, elems, c->sq);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+static int analyze_pipeline(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
+                            int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems, const int32_t *order, const int *cnt)
+{
+    int r;
+    xb200_cu_item *d_items;
+    xb200_rates   *d_rates;
+    xb200_sbac    *d_in, *d_out;
+    int32_t       *d_order;
+    const int64_t  side_elems = elems / 3 * 2 + 64;
+    if((r = to_dev(c, c->b_cu_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_cu_rates, rates, (size_t)n_rates, XB200_MEM_HOST, &d_rates))) return r;
+    if((r = to_dev(c, c->b_st0, states, (size_t)n_states, XB200_MEM_HOST, &d_in))) return r;
+    if((r = to_dev(c, c->b_st1, states, (size_t)n_states, XB200_MEM_HOST, &d_out))) return r;
+    if((r = to_dev(c, c->b_cu_order, order, (size_t)4 * n, XB200_MEM_HOST, &d_order))) return r;
+    if((r = ensure(c->b_cu_state, (size_t)n * sizeof(CuState)))) return r;
+    if((r = ensure(c->b_cu_me, (size_t)n * 8 * sizeof(xb200_me_item)))) return r;
+    if((r = ensure(c->b_cu_res, (size_t)n * 3 * sizeof(xb200_residue_item)))) return r;
+    if((r = ensure(c->b_cu_mc, (size_t)n * sizeof(xb200_mc_item)))) return r;
+    if((r = ensure(c->b_cu_cur, (size_t)n * sizeof(int32_t)))) return r;
+    if((r = ensure(c->b_cu_off, (size_t)n * sizeof(int64_t)))) return r;
+    if((r = ensure(c->b_cu_side, (size_t)side_elems * 2))) return r;
+    if((r = ensure(c->b_scr[0], (size_t)15 * elems * 2 + 64))) return r;
+    if((r = ensure(c->b_cu_coef, (size_t)elems * 2 + 64))) return r;
+    if(rec && (r = ensure(c->b_cu_rec, (size_t)elems * 2 + 64))) return r;
+    CuState            *d_state = static_cast<CuState *>(c->b_cu_state.p);
+    xb200_me_item      *d_me = static_cast<xb200_me_item *>(c->b_cu_me.p);
+    xb200_residue_item *d_res = static_cast<xb200_residue_item *>(c->b_cu_res.p);
+    xb200_mc_item      *d_mc = static_cast<xb200_mc_item *>(c->b_cu_mc.p);
+    int32_t            *d_cur = static_cast<int32_t *>(c->b_cu_cur.p);
+    int64_t            *d_off = static_cast<int64_t *>(c->b_cu_off.p);
+    int16_t            *d_side = static_cast<int16_t *>(c->b_cu_side.p), *d_scr = static_cast<int16_t *>(c->b_scr[0].p);
+    int16_t            *d_coef = static_cast<int16_t *>(c->b_cu_coef.p), *d_rec = rec ? static_cast<int16_t *>(c->b_cu_rec.p) : nullptr;
+    const int           ni = (int)n;
+    bool                any_b = false;
+    for(int64_t i = 0; i < n && !any_b; i++) any_b = items[i].slice_type == 0;
+    CK(cudaStreamSynchronize(c->stream)); // pageable `order`
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, c->stream));
+    // 1. skip candidates
+    if((r = fork_streams(c))) return r;
+    if((r = launch_skip<6>(c, d_items, d_order + 3 * n, cnt[3], d_in, d_state, d_scr, elems))) return r;
+    if((r = launch_skip<5>(c, d_items, d_order + 2 * n, cnt[2], d_in, d_state, d_scr, elems))) return r;
+    if((r = launch_skip<4>(c, d_items, d_order + 1 * n, cnt[1], d_in, d_state, d_scr, elems))) return r;
+    if((r = launch_skip<3>(c, d_items, d_order + 0 * n, cnt[0], d_in, d_state, d_scr, elems))) return r;
+    if((r = join_streams(c))) return r;
+    // 2. uni-directional searches
+    k_cu_make_me_uni<<<(ni * 8 + 255) / 256, 256, 0, c->stream>>>(d_items, ni, d_state, d_me, c->sq);
+    c->launches++;
+    if((r = xb200_me(c, d_me, (int64_t)ni * 8, nullptr, 0, XB200_MEM_DEVICE))) return r;
+    // 3. best reference / MVP index, DIR | L0 | L1 candidates through the residue operator, cbf decisions
+    k_cu_after_uni<<<(ni + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni, d_in, d_state, d_me, d_res, elems);
+    c->launches++;
+    if((r = residue_impl(c, d_res, (int64_t)ni * 3, d_rates, n_rates, d_scr, d_scr + elems, 15 * elems, XB200_MEM_DEVICE, d_scr + 2 * elems))) return r;
+    k_cu_decide<<<(ni * 3 + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni * 3, 3, d_in, d_state, d_res, d_scr);
+    c->launches++;
+    // 4. analyze_bi
+    if(any_b) {
+        for(int iter = 0; iter < 4; iter++) {
+            k_cu_bi_prep<<<(ni + 127) / 128, 128, 0, c->stream>>>(d_items, ni, d_state, iter, d_mc, d_cur, d_off, d_me, c->sq);
+            c->launches++;
+            if((r = xb200_bi_org(c, d_mc, n, d_cur, d_off, d_side, side_elems, XB200_MEM_DEVICE))) return r;
+            if((r = xb200_me(c, d_me, (int64_t)ni * XB200_MAX_REFP, d_side, side_elems, XB200_MEM_DEVICE))) return r;
+            CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int), c->stream));
+            k_cu_bi_update<<<(ni + 127) / 128, 128, 0, c->stream>>>(ni, d_state, d_me, c->d_bins);
+            c->launches++;
+            int active = 0;
+            CK(cudaMemcpyAsync(&active, c->d_bins, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if(!active) break;
+        }
+        k_cu_bi_emit<<<(ni + 127) / 128, 128, 0, c->stream>>>(d_items, ni, d_state, d_res, elems);
+        c->launches++;
+        if((r = residue_impl(c, d_res, n, d_rates, n_rates, d_scr, d_scr + elems, 15 * elems, XB200_MEM_DEVICE, d_scr + 2 * elems))) return r;
+        k_cu_decide<<<(ni + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni, 1, d_in, d_state, d_res, d_scr);
+        c->launches++;
+    }
+    // 5. winners
+    k_cu_final<<<ni, 128, 0, c->stream>>>(d_items, ni, d_state, d_scr, elems, d_out, d_coef, d_rec);
+    c->launches++;
+    CK(cudaEventRecord(e1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, states, d_out, (size_t)n_states, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, coef, d_coef, (size_t)elems, XB200_MEM_HOST))) return r;
+    if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, XB200_MEM_HOST))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->last_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     CK(cudaGetLastError());
     return XB200_OK;
 }

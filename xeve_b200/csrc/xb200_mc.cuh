@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(MC_THREADS) k_bi_org(const PicDev *__restrict_
     const int i = blockIdx.x;
     if(i >= n) return;
     const xb200_mc_item it = items[i];
+    if(it.w == 0) return; // slot left empty by the CU pipeline
     mc_item(pics, it, sq, pred, aux, tmp, threadIdx.x, MC_THREADS, true);
     const PicDev   o   = pics[cur_pic[i]];
     const int16_t *org = o.p[0] + (ptrdiff_t)it.y * o.s[0] + it.x;

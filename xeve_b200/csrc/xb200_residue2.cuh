@@ -438,7 +438,8 @@ template <int L2, bool USE_TC>
 __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__restrict__ pics, xb200_residue_item *__restrict__ items,
                                                                const int32_t *__restrict__ order, int n,
                                                                const xb200_rates *__restrict__ rates, int16_t *__restrict__ coef,
-                                                               int16_t *__restrict__ rec, const int8_t *__restrict__ g_tm64, SeqDev sq)
+                                                               int16_t *__restrict__ rec, const int8_t *__restrict__ g_tm64, SeqDev sq,
+                                                               int16_t *__restrict__ pred_out)
 {
     using Cf = Res2Cfg<L2>;
     constexpr int T = Cf::T, N = Cf::N, NY = N * N, NCH = NY >> 2;
@@ -478,6 +479,8 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
         mc_item_t<L2, T>(pics, mc, sq, pred, aux, reinterpret_cast<int16_t *>(TB), tt);
         const PicDev &o = pics[it->cur_pic];
         const int64_t oo = it->out_off;
+        if(pred_out) // the CU pipeline keeps the prediction of every candidate mode (planes dropped by the cbf decision)
+            for(int e = tt; e < Cf::PRED; e += T) pred_out[oo + e] = pred[e];
         const xb200_rates *rt = &rates[it->rate_idx];
         const int rs = it->run_stats, st = it->slice_type;
         int     nnz[3];
@@ -504,7 +507,7 @@ __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, i
     int       key = 5;
     if(i < n) {
         const int w = items[i].mc.w;
-        key = (items[i].mc.h == w) ? (w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : w == 64 ? 3 : 4) : 4;
+        key = (items[i].mc.h == w) ? (w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : w == 64 ? 3 : (w == 0 ? 5 : 4)) : 4; // w 0: empty slot
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll

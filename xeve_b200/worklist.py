@@ -144,6 +144,37 @@ class FrameWork:
         self.residue = res
         return res
 
+    # ---- the fused per-CU decision (xb200_analyze_cu): one item per CU of the quad-tree ---------------------------
+    def build_cu(self, rates_of_state, max_search_range=32, seed=0):
+        """xeve_pinter_analyze_cu inputs of every CU: MVP candidates per list = {stage-1 MVP, a jittered copy, (1,1) for
+        an unavailable neighbour, the colocated (true-motion) vector} as xeve_get_motion orders them; fresh coder state
+        (xeve_sbac_reset: range 16384, every model PROB_INIT) and the RDOQ tables derived from it by xb200_rdoq_rates."""
+        rng = np.random.default_rng(seed + 77)
+        n = self.n_cu
+        cu = np.zeros(n, api.CU_ITEM)
+        cu["poc"], cu["cur_pic"], cu["x"], cu["y"], cu["log2_cuw"], cu["log2_cuh"] = self.poc, self.cur_pic, self.x, self.y, self.l2, self.l2
+        cu["slice_type"], cu["all_preds"], cu["num_refp"], cu["qp"], cu["max_search_range"] = 0, 1, 1, self.qp, max_search_range
+        cu["ref_pic"], cu["ref_poc"] = -1, -1
+        for l in (0, 1):
+            cu["ref_pic"][:, l, 0], cu["ref_poc"][:, l, 0] = self.ref_pics[l], self.ref_pocs[l]
+            m0 = self.me_uni["mvp"][l::2]
+            cu["mvp"][:, l, 0] = m0
+            cu["mvp"][:, l, 1] = m0 + rng.integers(-3, 4, (n, 2))
+            cu["mvp"][:, l, 2] = 1
+            cu["mvp"][:, l, 3] = m0 + rng.integers(-2, 3, (n, 2))
+            cu["mv_dir"][:, l] = m0
+        cu["ctx_skip"], cu["ctx_pred_mode"] = rng.integers(0, 2, n), rng.integers(0, 3, n)
+        cu["lambda_mv"], cu["lambda"] = self.lambda_mv, self.lam
+        cu["dist_chroma_weight"] = 1.0 / 0.63
+        cu["rate_idx"], cu["state_in"], cu["state_out"] = 0, 0, 1 + np.arange(n)
+        sz = (3 << (2 * self.l2.astype(np.int64))) >> 1
+        cu["out_off"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+        states = np.zeros(n + 1, api.SBAC)
+        states["range"], states["m"] = 16384, 512
+        self.cu, self.cu_states, self.cu_elems = cu, states, int(sz.sum())
+        self.cu_rates = rates_of_state(states[:1])
+        return cu
+
     # ---- bookkeeping for bench.py ------------------------------------------------------------------------
     def counts(self):
         return dict(cus=self.n_cu, me_uni=2 * self.n_cu, bi_org=self.n_cu, me_bi=self.n_cu, residue=3 * self.n_cu)
