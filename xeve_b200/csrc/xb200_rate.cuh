@@ -39,10 +39,34 @@ __device__ __forceinline__ void cb_ep(Cabac &c, int nbins = 1)   // sbac_encode_
 {
     if(nbins > 0) { c.range &= ~1u; c.bits += nbins; }
 }
+// the engine step on a model held in registers (state / mps unpacked)
+__device__ __forceinline__ void cb_step(uint32_t &range, uint32_t &bits, uint32_t &state, uint32_t &mps, uint32_t bin)
+{
+    uint32_t lps = (state * range) >> 9;
+    lps = max(lps, 437u);
+    range -= lps;
+    if(bin != mps) {
+        if(range >= lps) range = lps;
+        state += (512 - state + 16) >> 5;
+        if(state > 256) { mps ^= 1; state = 512 - state; }
+    }
+    else state -= (state + 16) >> 5;
+    const int sh = max(0, __clz(range) - 18);
+    range <<= sh;
+    bits += sh;
+}
+// sbac_write_unary_sym with two contexts: bin 0 on model idx, the remaining `sym` bins (sym - 1 ones and a zero) on model
+// idx + 1, which stays in registers for the whole run
 __device__ __forceinline__ void cb_unary(Cabac &c, uint32_t sym, int idx)
 {
     cb_bin(c, idx, sym != 0);
-    for(; sym; sym--) cb_bin(c, idx + 1, sym != 1);
+    if(sym == 0) return;
+    const uint32_t model = c.m[idx + 1];
+    uint32_t       mps = model & 1, state = model >> 1, range = c.range, bits = c.bits;
+    for(; sym > 1; sym--) cb_step(range, bits, state, mps, 1);
+    cb_step(range, bits, state, mps, 0);
+    c.m[idx + 1] = (uint16_t)((state << 1) | mps);
+    c.range = range; c.bits = bits;
 }
 __device__ __forceinline__ void cb_mvp_idx(Cabac &c, int v)
 {
