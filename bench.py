@@ -34,6 +34,25 @@ SAMPLE_ROWS = 4  # CTU rows of the bounded CPU sample
 PRESET = "fast"
 
 
+def usable_cores():
+    """Host threads the reference arm can really run on: the affinity mask capped by the cgroup CPU quota (the GPU boxes expose
+    128 logical CPUs under a 16-CPU quota; oversubscribing the quota makes the reference slower, not faster)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p) + 0.5)))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, (q + p // 2) // p))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def select_workload(name):
     """1080p fast (BASELINE.json configs[1], the default) or 2160p 10-bit medium (configs[2])."""
     global CLIP, W, H, PRESET
@@ -208,15 +227,28 @@ def run_b200(args, rank, world, dist):
     t_e2e = time.perf_counter() - t0
     # ---- the fused per-CU decision over the same picture (xb200_analyze_cu, host-buffer API) ------------------------
     cu_items = fw.build_cu(hp.rdoq_rates, max_search_range=int(seq["me_range"][0]), seed=rank)
-    cu_out, _, cu_coef, _ = hp.analyze_cu(cu_items, fw.cu_rates, fw.cu_states, fw.cu_elems, want_rec=True)  # warm-up
+    h_cu, h_st = pin(cu_items.view(np.uint8)), pin(fw.cu_states.view(np.uint8))
+    h_cu_coef, h_cu_rec = pin(np.zeros(fw.cu_elems, np.int16)), pin(np.zeros(fw.cu_elems, np.int16))
+    cu_rates_p = fw.cu_rates.ctypes.data_as(C.c_void_p)
+
+    def step_cu():
+        r = L.xb200_analyze_cu(ctx, HP(h_cu), len(cu_items), cu_rates_p, len(fw.cu_rates), HP(h_st), len(fw.cu_states), HP(h_cu_coef),
+                               HP(h_cu_rec), fw.cu_elems)
+        if r:
+            raise RuntimeError(f"analyze_cu failed: {r}")
+    step_cu()  # warm-up
+    cu_out = np.frombuffer(h_cu.numpy().tobytes(), api.CU_ITEM)
     t_cu_k, t0 = 0.0, time.perf_counter()
     cu_steps = max(2, args.steps // 4)
     for _ in range(cu_steps):
-        hp.analyze_cu(cu_items, fw.cu_rates, fw.cu_states, fw.cu_elems, want_rec=True)
+        step_cu()
         t_cu_k += hp.last_kernel_ms
     t_cu = (time.perf_counter() - t0) / cu_steps
     analyze = {"cus_per_frame": int(len(cu_items)), "kernel_ms_per_frame": round(t_cu_k / cu_steps, 3),
                "host_api_ms_per_frame": round(t_cu * 1e3, 3), "frames_per_s_kernel": round(1e3 / (t_cu_k / cu_steps), 2),
+               "frames_per_s_host_api": round(1.0 / t_cu, 2),
+               "h2d_bytes": int(cu_items.nbytes + fw.cu_states.nbytes + fw.cu_rates.nbytes),
+               "d2h_bytes": int(cu_items.nbytes + fw.cu_states.nbytes + 4 * fw.cu_elems),
                "best_mode_hist": np.bincount(cu_out["best_idx"], minlength=5).tolist(),
                "note": "whole xeve_pinter_analyze_cu per CU on the device (skip/direct/L0/L1/BI + cbf RDO + CABAC bit counts)"}
     sampler.stop_flag = True
@@ -284,7 +316,7 @@ def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
     keep, planes = padded_planes_struct(fr, [REF_POCS[0], REF_POCS[1], POC], clip.depth)
     mr = int(seq["me_range"][0])
     fw = FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], rows=sample_rows, me_range=mr)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     frac = fw.n_cu / FrameWork(W, H, POC, REF_POCS, PAN, 2, [0, 1], me_range=mr).n_cu
     rows_total = (H + 63) // 64
     steps = steps or args.steps
@@ -315,9 +347,31 @@ def run_reference(args, sample_rows=SAMPLE_ROWS, steps=None, quiet=False):
            "config": {"workload": f"same {W}x{H} B-picture work lists as the b200 arm", "sample": f"first {sample_rows} of {rows_total} CTU rows "
                       f"({fw.n_cu} CUs = {frac:.3f} of the picture), time scaled to the whole picture"},
            "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
-                            "sample": f"{sample_rows}/{rows_total} CTU rows, reference AVX2 functions replayed on {cores} host threads"},
+                            "sample": f"{sample_rows}/{rows_total} CTU rows, reference AVX2 functions replayed on {cores} host threads "
+                                      f"(usable CPUs: affinity {len(os.sched_getaffinity(0))}, cgroup quota applied)"},
            "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return out
+
+
+def reference_cu_rate(frames=3):
+    """Reference side of the analyze_cu line: a real (single-thread, parity-configuration) encode of the first pictures of
+    the same clip by the compiled reference with a stop-watch around its own xeve_pinter_analyze_cu (oracle/ref_harness.c,
+    trace mask TRACE_CU_TIME) -> CUs per second per host core."""
+    from oracle import refharness as rh
+    from xeve_b200.clips import Clip
+    if not rh.available():
+        return {"unavailable": "oracle/_ref not present"}
+    c = Clip(CLIP)
+    dt = np.uint8 if c.depth == 8 else np.dtype("<u2")
+    yuv = np.frombuffer(b"".join(c.frame_bytes(i) for i in range(frames)), dt)
+    rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=PRESET, trace_mask=rh.TRACE_CU_TIME, pic_lo=1, pic_hi=1 << 30,
+                   want_bitstream=False)
+    sec, calls = rh.cu_time()
+    cores = usable_cores()
+    rate = calls / sec if sec > 0 else 0.0
+    return {"cus_per_s_per_core": round(rate, 1), "calls": int(calls), "seconds": round(sec, 3), "cores": cores,
+            "cus_per_s_all_cores_ideal": round(rate * cores, 1), "kind": "reference",
+            "sample": f"xeve_pinter_analyze_cu inside a real 1-thread encode of {frames} {c.w}x{c.h} pictures (inter pictures only)"}
 
 
 # ---- helper module (kept here so bench.py is self-contained) -----------------------------------------------------
@@ -377,6 +431,12 @@ def main():
             a.steps, a.warmup = 1, 1
             ref = run_reference(a)
             out["cpu_baseline"] = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+            cur = reference_cu_rate()
+            out["analyze_cu"]["cpu_reference"] = cur
+            if cur.get("cus_per_s_per_core"):
+                gpu_rate = out["analyze_cu"]["cus_per_frame"] * out["analyze_cu"]["frames_per_s_kernel"]
+                out["analyze_cu"]["cus_per_s_kernel"] = round(gpu_rate, 1)
+                out["analyze_cu"]["host_cores_equivalent"] = round(gpu_rate / cur["cus_per_s_per_core"], 1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -323,9 +323,21 @@ static int hook_tq(XEVE_CTX *ctx, XEVE_CORE *core, s16 coef[N_C][MAX_CU_DIM], in
 }
 
 #define RH_T_CU 8
+#define RH_T_CU_TIME 16 /* no records: only the time spent inside the reference's xeve_pinter_analyze_cu and the call count */
+static double g_cu_secs;
+static int64_t g_cu_calls;
+RH_API double rh_cu_time(int64_t *calls) { if(calls) *calls = g_cu_calls; return g_cu_secs; }
+static double now_s(void);
 static double hook_cu(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw, int log2_cuh, XEVE_MODE *mi,
                       s16 coef[N_C][MAX_CU_DIM], pel *rec[N_C], int s_rec[N_C])
 {
+    if(tracing(RH_T_CU_TIME) && !tracing(RH_T_CU)) {
+        const double t0 = now_s();
+        const double c = T.org_cu(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+        g_cu_secs += now_s() - t0;
+        g_cu_calls++;
+        return c;
+    }
     if(!tracing(RH_T_CU)) return T.org_cu(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
     XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];
     RH_CU_REC    r;
@@ -447,6 +459,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
     vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
     T.have_rates = 0;
+    g_cu_secs = 0; g_cu_calls = 0;
     T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
     if(trace_mask) {
         T.org_me = ctx->pinter[0].fn_me; T.org_mc = ctx->pinter[0].fn_mc; T.org_tq = ctx->fn_tq;

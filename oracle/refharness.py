@@ -134,7 +134,16 @@ CU_REC = np.dtype([
     ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,)),
     ("coef_hash", "<u8"), ("rec_hash", "<u8"), ("me_first", "<i4"), ("me_cnt", "<i4"),
 ], align=True)
-TRACE_CU = 8
+TRACE_CU, TRACE_CU_TIME = 8, 16
+
+
+def cu_time():
+    """(seconds inside the reference's xeve_pinter_analyze_cu, calls) of the last encode_clip(trace_mask=TRACE_CU_TIME)"""
+    L = lib()
+    L.rh_cu_time.restype = C.c_double
+    n = C.c_int64(0)
+    sec = L.rh_cu_time(C.byref(n))
+    return sec, n.value
 SBAC = np.dtype([("range", "<u4"), ("m", "<u2", (68,))], align=True)
 BITS_REC = np.dtype([
     ("kind", "u1"), ("slice_type", "u1"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pidx", "u1"), ("ch", "u1"),
