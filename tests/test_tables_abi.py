@@ -22,6 +22,8 @@ PROBE = r'''
 int main(void){
   printf("seq %zu\nme %zu\nmc %zu\nrates %zu\ntq %zu\nres %zu\nblk %zu\n", sizeof(xb200_seq), sizeof(xb200_me_item),
          sizeof(xb200_mc_item), sizeof(xb200_rates), sizeof(xb200_tq_item), sizeof(xb200_residue_item), sizeof(xb200_blk_item));
+  printf("sbac %zu\nbits %zu\ncu %zu\nmvpi %zu\n", sizeof(xb200_sbac), sizeof(xb200_bits_item), sizeof(xb200_cu_item), sizeof(xb200_mvp_item));
+  printf("cuoff %zu %zu %zu %zu\n", offsetof(xb200_cu_item, lambda), offsetof(xb200_cu_item, mvp), offsetof(xb200_cu_item, cost), offsetof(xb200_bits_item, coef_off));
   printf("off %zu %zu %zu %zu\n", offsetof(xb200_me_item, lambda_mv), offsetof(xb200_tq_item, lambda),
          offsetof(xb200_residue_item, out_off), offsetof(xb200_residue_item, dist_rec));
   static int8_t tm[4096]; xb200_gen_tm64(tm);
@@ -56,7 +58,13 @@ def test_struct_layouts_match_numpy(probe_dir):
     assert int(sizes["tq"]) == api.TQ_ITEM.itemsize
     assert int(sizes["res"]) == api.RESIDUE_ITEM.itemsize
     assert int(sizes["blk"]) == api.BLK_ITEM.itemsize
-    offs = [int(v) for v in re.search(r"off (\d+) (\d+) (\d+) (\d+)", out).groups()]
+    assert int(sizes["sbac"]) == api.SBAC.itemsize and int(sizes["bits"]) == api.BITS_ITEM.itemsize
+    assert int(sizes["cu"]) == api.CU_ITEM.itemsize == rh.CU_REC.itemsize and int(sizes["mvpi"]) == api.MVP_ITEM.itemsize
+    cuoffs = [int(v) for v in re.search(r"cuoff (\d+) (\d+) (\d+) (\d+)", out).groups()]
+    assert cuoffs == [api.CU_ITEM.fields["lambda"][1], api.CU_ITEM.fields["mvp"][1], api.CU_ITEM.fields["cost"][1],
+                      api.BITS_ITEM.fields["coef_off"][1]]
+    assert api.CU_ITEM.fields == rh.CU_REC.fields and api.BITS_ITEM.fields == rh.BITS_REC.fields
+    offs = [int(v) for v in re.search(r"\noff (\d+) (\d+) (\d+) (\d+)", out).groups()]
     assert offs == [api.ME_ITEM.fields["lambda_mv"][1], api.TQ_ITEM.fields["lambda"][1],
                     api.RESIDUE_ITEM.fields["out_off"][1], api.RESIDUE_ITEM.fields["dist_rec"][1]]
     # the harness records and the ABI records are the same bytes

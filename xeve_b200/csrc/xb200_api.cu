@@ -18,6 +18,7 @@
 #include "xb200_rate.cuh"
 #include "xb200_analyze.cuh"
 #include "xb200_pipeline.cuh"
+#include "xb200_lanecoder.cuh"
 #include <math.h>
 
 namespace {
@@ -50,7 +51,7 @@ struct xb200_ctx {
     DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
     DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
     DevBuf           b_cu_items, b_cu_rates, b_cu_state, b_cu_me, b_cu_res, b_cu_mc, b_cu_cur, b_cu_off, b_cu_side, b_cu_order,
-                     b_cu_coef, b_cu_rec; // CU pipeline
+                     b_cu_coef, b_cu_rec, b_cu_nzr, b_cu_nzl, b_cu_meta; // CU pipeline
     cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
     cudaStream_t     side[4] = {nullptr, nullptr, nullptr, nullptr}; // one per CU size: the four size-binned grids overlap
     cudaEvent_t      ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1076,6 +1077,40 @@ template <int L2> int launch_skip(xb200_ctx *c, const xb200_cu_item *d_items, co
 
 extern "C" {
 
+// cbf decisions of all residue slots.  Small CUs (short bin streams, 92 % of the slots): one coder per LANE; large CUs (long
+// streams: the serial critical path matters, not throughput): one coder per warp with ballot-parallel coefficient fetch and
+// register-resident unary runs.  The two grids run concurrently.  XB200_DECIDE=warp / lanes forces one kernel for all sizes.
+static int run_decide(xb200_ctx *c, const xb200_cu_item *d_items, int n_slots, int per_cu, const xb200_sbac *d_in, CuState *d_state,
+                      const xb200_residue_item *d_res, const int16_t *d_scr, int64_t elems)
+{
+    const char *e = getenv("XB200_DECIDE");
+    int         split = (e && e[0] == 'w') ? 0 : ((e && e[0] == 'l') ? 64 : 16);   // widths <= split go to the lane coder
+    if(e && e[0] >= '0' && e[0] <= '9') split = atoi(e);
+    int r;
+    if((r = fork_streams(c))) return r;
+    if(split < 64) {
+        k_cu_decide<<<(n_slots + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->side[0]>>>(d_items, n_slots, per_cu, d_in, d_state, d_res, d_scr,
+                                                                                         split + 1, 64);
+        c->launches++;
+    }
+    if(split > 0) {
+        if((r = ensure(c->b_cu_nzr, (size_t)5 * elems * 2 + 64))) return r;
+        if((r = ensure(c->b_cu_nzl, (size_t)5 * elems * 2 + 64))) return r;
+        if((r = ensure(c->b_cu_meta, (size_t)n_slots + 64))) return r;
+        uint16_t *nzr = static_cast<uint16_t *>(c->b_cu_nzr.p);
+        int16_t  *nzl = static_cast<int16_t *>(c->b_cu_nzl.p);
+        uint8_t  *meta = static_cast<uint8_t *>(c->b_cu_meta.p);
+        k_cu_nzlist<<<(n_slots + 3) / 4, 128, 0, c->side[1]>>>(d_res, n_slots, d_scr, nzr, nzl, meta, elems, 1, split);
+        const int smem = 4 * (int)sizeof(LcShared);
+        CK(cudaFuncSetAttribute(k_cu_decide_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_cu_decide_lanes<<<(n_slots + 127) / 128, 128, smem, c->side[1]>>>(d_items, n_slots, per_cu, d_in, d_state, d_res, nzr, nzl, meta, elems, 1,
+                                                                           split);
+        c->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return join_streams(c);
+}
+
 static int analyze_pipeline(xb200_ctx *c, xb200_cu_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
                             int64_t n_states, int16_t *coef, int16_t *rec, int64_t elems, const int32_t *order, const int *cnt)
 {
@@ -1131,8 +1166,7 @@ static int analyze_pipeline(xb200_ctx *c, xb200_cu_item *items, int64_t n, const
     k_cu_after_uni<<<(ni + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni, d_in, d_state, d_me, d_res, elems);
     c->launches++;
     if((r = residue_impl(c, d_res, (int64_t)ni * 3, d_rates, n_rates, d_scr, d_scr + elems, 15 * elems, XB200_MEM_DEVICE, d_scr + 2 * elems))) return r;
-    k_cu_decide<<<(ni * 3 + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni * 3, 3, d_in, d_state, d_res, d_scr);
-    c->launches++;
+    if((r = run_decide(c, d_items, ni * 3, 3, d_in, d_state, d_res, d_scr, elems))) return r;
     // 4. analyze_bi
     if(any_b) {
         for(int iter = 0; iter < 4; iter++) {
@@ -1151,8 +1185,7 @@ static int analyze_pipeline(xb200_ctx *c, xb200_cu_item *items, int64_t n, const
         k_cu_bi_emit<<<(ni + 127) / 128, 128, 0, c->stream>>>(d_items, ni, d_state, d_res, elems);
         c->launches++;
         if((r = residue_impl(c, d_res, n, d_rates, n_rates, d_scr, d_scr + elems, 15 * elems, XB200_MEM_DEVICE, d_scr + 2 * elems))) return r;
-        k_cu_decide<<<(ni + PIPE_WARPS - 1) / PIPE_WARPS, PIPE_WARPS * 32, 0, c->stream>>>(d_items, ni, 1, d_in, d_state, d_res, d_scr);
-        c->launches++;
+        if((r = run_decide(c, d_items, ni, 1, d_in, d_state, d_res, d_scr, elems))) return r;
     }
     // 5. winners
     k_cu_final<<<ni, 128, 0, c->stream>>>(d_items, ni, d_state, d_scr, elems, d_out, d_coef, d_rec);

@@ -247,14 +247,15 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32) k_cu_after_uni(const xb200_cu
 // per_cu = 1: the BI candidate
 __global__ void __launch_bounds__(PIPE_WARPS * 32) k_cu_decide(const xb200_cu_item *__restrict__ items, int n_slots, int per_cu,
                                                                const xb200_sbac *__restrict__ st_in, CuState *__restrict__ states,
-                                                               const xb200_residue_item *__restrict__ res, const int16_t *__restrict__ scratch)
+                                                               const xb200_residue_item *__restrict__ res, const int16_t *__restrict__ scratch,
+                                                               int w_lo, int w_hi)
 {
     __shared__ CuHdr hdr[PIPE_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sl = blockIdx.x * PIPE_WARPS + w;
     if(sl >= n_slots) return;
     const xb200_residue_item &it = res[sl];
-    if(it.mc.w == 0) return;
+    if(it.mc.w < w_lo || it.mc.w > w_hi) return;   // empty slot (w = 0) or a size class handled by the lane coder
     const int ci = sl / per_cu, k = sl - ci * per_cu;
     const int pidx = per_cu == 1 ? 2 : (k == 0 ? 4 : k - 1);
     CuHdr    &H = hdr[w];
