@@ -27,6 +27,9 @@
  *   xb200_residue            the distortion/transform body of pinter_residue_rdo
  *                            (src_base/xeve_pinter.c:961-1056): fn_mc -> xeve_diff_pred -> SSD ->
  *                            fn_tq -> fn_itdp -> fn_recon -> SSD, fused on the device
+ *   xb200_deblock            ctx->fn_loop_filter = xeve_loop_filter (src_base/xeve_enc.c:2355-2414) ->
+ *                            xeve_deblock / _cu_ver / _cu_hor   (src_base/xeve_df.c:34-573)
+ *                            + ctx->fn_picbuf_expand            (src_base/xeve_enc.c:1274)
  *
  * Status codes are the reference's own (inc/xeve.h:50-74): XB200_OK == XEVE_OK == 0, errors
  * negative.  All functions are synchronous on return (results are in the caller's buffers).
@@ -249,6 +252,19 @@ typedef struct {
     int32_t  me_first, me_cnt;      /* unused by the library (test bookkeeping) */
 } xb200_cu_item;
 
+/* ---- in-loop deblocking of a reconstructed picture --------------------------------------------------
+ * One leaf CU of the coding tree, as xeve_deblock_tree hands it to ctx->fn_deblock_unit (src_base/xeve_df.c:575-639). */
+typedef struct {
+    int16_t x, y;                   /* luma position */
+    uint8_t log2_cuw, log2_cuh, pad_[2];
+} xb200_df_cu;
+
+typedef struct {                    /* picture-level inputs of xb200_deblock */
+    int32_t w_scu, h_scu;           /* ctx->w_scu / h_scu (4x4 units) */
+    int32_t qp_u_offset, qp_v_offset; /* sh->qp_u_offset / qp_v_offset (-> pic->pic_qp_u/v_offset, src_base/xeve_df.c:594-595) */
+    int32_t chroma_qp[2][70];       /* ctx->qp_chroma_dynamic[c][q] stored at [q + 6 * (bit_depth - 8)], q <= 57 */
+} xb200_df_pic;
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 XB200_API int  xb200_create(xb200_ctx **out, int device, const xb200_seq *seq);
 XB200_API void xb200_destroy(xb200_ctx *c);
@@ -320,6 +336,16 @@ XB200_API int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, c
  * reference itself recomputes the reconstruction of the winning mode (src_base/xeve_pinter.c:2006-2038). */
 XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates,
                             int64_t n_rates, int16_t *coef, int16_t *rec, int64_t elems, int mem);
+
+/* In-loop deblocking of picture `pic` (a padded picture holding the unfiltered reconstruction), in place: every CU's left
+ * edge (x > 0), then every CU's top edge (y > 0), 4-sample segments with the filter strength derived from the two
+ * SCUs' intra / cbf / motion data, exactly as xeve_loop_filter does with one tile and one slice.  `cus` lists the leaf
+ * CUs in coding order (left and upper neighbours of a CU precede it), covering the picture.  map_scu: u32[f_scu]
+ * (MCU_* bit layout, src_base/xeve_def.h:585-640; only IF, QP, CBFL, IBC are read), map_refi: s8[f_scu][2], map_mv:
+ * s16[f_scu][2][2].  expand != 0 replicates the borders afterwards (xeve_picbuf_expand), which makes the picture a
+ * usable reference.  `mem` applies to cus and the three maps. */
+XB200_API int xb200_deblock(xb200_ctx *c, int32_t pic, const xb200_df_cu *cus, int64_t n, const xb200_df_pic *pp,
+                            const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int expand, int mem);
 
 /* ---- timing aid for bench.py: device time (ms) of the kernels of the last call, measured with
  *      CUDA events on the library's own stream ------------------------------------------------- */

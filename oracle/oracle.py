@@ -144,3 +144,16 @@ def hash_slots(buf, off, elems):
     L.xo_hash_slots.argtypes = [VP, VP, VP, C.c_int64, VP]
     L.xo_hash_slots(_p(np.ascontiguousarray(buf, np.int16)), _p(off), _p(elems), len(off), _p(out))
     return out
+
+
+def deblock(planes, cus, pp, map_scu, map_refi, map_mv, bit_depth=10):
+    """xo_deblock on copies of the (Y, U, V) active-area arrays; returns the filtered planes."""
+    L = lib()
+    L.xo_deblock.restype = None
+    L.xo_deblock.argtypes = [VP, VP, VP, I, I, I, I, VP, C.c_int64, VP, VP, VP, VP, I]
+    out = [np.ascontiguousarray(a, np.int16).copy() for a in planes]
+    cus, pp = np.ascontiguousarray(cus), np.ascontiguousarray(pp).reshape(1)
+    L.xo_deblock(_p(out[0]), _p(out[1]), _p(out[2]), out[0].shape[1], out[1].shape[1], out[0].shape[1], out[0].shape[0], _p(cus),
+                 len(cus), _p(pp), _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_refi, np.int8)),
+                 _p(np.ascontiguousarray(map_mv, np.int16)), bit_depth)
+    return out

@@ -171,6 +171,10 @@ static struct {
     int (*org_tq)(XEVE_CTX *, XEVE_CORE *, s16 (*)[MAX_CU_DIM], int, int, int, int *, int, int);
     double (*org_cu)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, XEVE_MODE *, s16 (*)[MAX_CU_DIM], pel **, int *);
     vec_t    cu, cu_sbac; /* cu_sbac: coder states named by RH_CU_REC::state_in / state_out */
+    int (*org_lf)(XEVE_CTX *, XEVE_CORE *);
+    void (*org_df_unit)(XEVE_CTX *, XEVE_PIC *, int, int, int, int, int, XEVE_CORE *, int);
+    vec_t    df, df_cu, df_maps; /* deblocking: one record per picture, CU rectangles, frame maps (bytes) */
+    int      df_collect;
     vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
     /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
     RH_CONST cst;
@@ -403,6 +407,103 @@ static double hook_cu(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw
 }
 
 /* ------------------------------------------------------------------------------------------
+ * deblocking trace: ctx->fn_loop_filter with the picture before / after, the frame
+ * maps it reads and the CU rectangles xeve_deblock_tree enumerates (ctx->fn_deblock_unit)
+ * ---------------------------------------------------------------------------------------- */
+#define RH_T_DF 32
+typedef struct { int16_t x, y; uint8_t log2_cuw, log2_cuh, pad_[2]; } RH_DF_CU;
+typedef struct {                /* == xb200_df_pic */
+    int32_t w_scu, h_scu, qp_u_offset, qp_v_offset;
+    int32_t chroma_qp[2][70];   /* ctx->qp_chroma_dynamic[c][q] at [q + 6 * (bit_depth - 8)] */
+} RH_DF_PIC;
+typedef struct {
+    int32_t   poc, pre_pic, post_pic, on;
+    int64_t   cu_first, cu_cnt;
+    int64_t   maps_off;         /* byte offset: map_scu u32[f] | map_refi s8[f][2] | map_mv s16[f][2][2] */
+    RH_DF_PIC pp;
+} RH_DF_REC;
+
+static int ilog2(int v) { int l = 0; while((1 << l) < v) l++; return l; }
+
+static void hook_df_unit(XEVE_CTX *ctx, XEVE_PIC *pic, int x, int y, int cuw, int cuh, int is_hor_edge, XEVE_CORE *core, int bf)
+{
+    if(T.df_collect && !is_hor_edge) {
+        RH_DF_CU c = {(int16_t)x, (int16_t)y, (uint8_t)ilog2(cuw), (uint8_t)ilog2(cuh), {0, 0}};
+        *(RH_DF_CU *)vec_push(&T.df_cu, 1) = c;
+    }
+    T.org_df_unit(ctx, pic, x, y, cuw, cuh, is_hor_edge, core, bf);
+}
+
+static void df_fill_pic(XEVE_CTX *ctx, RH_DF_PIC *pp)
+{
+    const int bdo = 6 * (ctx->param.codec_bit_depth - 8);
+    memset(pp, 0, sizeof(*pp));
+    pp->w_scu = ctx->w_scu; pp->h_scu = ctx->h_scu;
+    pp->qp_u_offset = ctx->sh->qp_u_offset; pp->qp_v_offset = ctx->sh->qp_v_offset;
+    for(int c = 0; c < 2; c++)
+        for(int q = -bdo; q <= 57; q++) pp->chroma_qp[c][q + bdo] = ctx->qp_chroma_dynamic[c][q];
+}
+
+static int hook_loop_filter(XEVE_CTX *ctx, XEVE_CORE *core)
+{
+    if(!tracing(RH_T_DF)) return T.org_lf(ctx, core);
+    RH_DF_REC r;
+    memset(&r, 0, sizeof(r));
+    r.poc = ctx->poc.poc_val;
+    r.on  = ctx->sh->deblocking_filter_on;
+    r.pre_pic = find_or_add_pic(PIC_CURR(ctx), r.poc, 2);
+    df_fill_pic(ctx, &r.pp);
+    const size_t f = ctx->f_scu;
+    r.maps_off = (int64_t)T.df_maps.n;
+    uint8_t *m = vec_push(&T.df_maps, f * 14);
+    memcpy(m, ctx->map_scu, f * 4); memcpy(m + f * 4, ctx->map_refi, f * 2); memcpy(m + f * 6, ctx->map_mv, f * 8);
+    r.cu_first = (int64_t)T.df_cu.n;
+    T.df_collect = 1;
+    int ret = T.org_lf(ctx, core);
+    T.df_collect = 0;
+    r.cu_cnt = (int64_t)T.df_cu.n - r.cu_first;
+    r.post_pic = find_or_add_pic(PIC_CURR(ctx), r.poc, 3);
+    *(RH_DF_REC *)vec_push(&T.df, 1) = r;
+    return ret;
+}
+
+/* The reference's own edge filters (exported xeve_deblock_cu_ver / _hor, src_base/xeve_df.c:253-471) driven like
+ * xeve_loop_filter + xeve_deblock (src_base/xeve_enc.c:2355-2414, xeve_df.c:522-573): all vertical edges, then all
+ * horizontal ones, CUs in the order given.  Planes are filtered in place. */
+RH_API int rh_sizeof_df(int what) { return what == 0 ? sizeof(RH_DF_REC) : what == 1 ? sizeof(RH_DF_CU) : sizeof(RH_DF_PIC); }
+RH_API double rh_deblock(const RH_PLANES *pl, const RH_DF_CU *cus, int64_t n, const RH_DF_PIC *pp, const u32 *map_scu_in,
+                         s8 (*map_refi)[REFP_NUM], s16 (*map_mv)[REFP_NUM][MV_D], int bit_depth)
+{
+    XEVE_PIC pic;
+    memset(&pic, 0, sizeof(pic));
+    pic.y = pl->y; pic.u = pl->u; pic.v = pl->v; pic.s_l = pl->s_l; pic.s_c = pl->s_c; pic.w_l = pl->w_l; pic.h_l = pl->h_l;
+    pic.w_c = pl->w_l / 2; pic.h_c = pl->h_l / 2;
+    pic.pic_qp_u_offset = pp->qp_u_offset; pic.pic_qp_v_offset = pp->qp_v_offset;
+    const size_t f = (size_t)pp->w_scu * pp->h_scu;
+    u32 *map_scu = malloc(f * 4);
+    u8  *tidx = calloc(f, 1);
+    memcpy(map_scu, map_scu_in, f * 4);
+    const int bdo = 6 * (bit_depth - 8);
+    int *tbl[2] = {(int *)pp->chroma_qp[0] + bdo, (int *)pp->chroma_qp[1] + bdo};
+    double t0 = now_s();
+    for(int is_hor = 0; is_hor <= 1; is_hor++) {
+        for(size_t i = 0; i < f; i++) MCU_CLR_COD(map_scu[i]);
+        for(int64_t i = 0; i < n; i++) {
+            const RH_DF_CU *c = &cus[i];
+            if(is_hor)
+                xeve_deblock_cu_hor(&pic, c->x, c->y, 1 << c->log2_cuw, 1 << c->log2_cuh, map_scu, map_refi, map_mv, pp->w_scu,
+                                    xeve_get_default_tree_cons(), tidx, 0, bit_depth, bit_depth, 1, tbl);
+            else
+                xeve_deblock_cu_ver(&pic, c->x, c->y, 1 << c->log2_cuw, 1 << c->log2_cuh, map_scu, map_refi, map_mv, pp->w_scu,
+                                    NULL, xeve_get_default_tree_cons(), tidx, 0, bit_depth, bit_depth, 1, tbl);
+        }
+    }
+    double t = now_s() - t0;
+    free(map_scu); free(tidx);
+    return t;
+}
+
+/* ------------------------------------------------------------------------------------------
  * encoder session
  * ---------------------------------------------------------------------------------------- */
 static int img_addref(XEVE_IMGB *i) { return ++i->refcnt; }
@@ -458,6 +559,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
     vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
+    vec_reset(&T.df, sizeof(RH_DF_REC)); vec_reset(&T.df_cu, sizeof(RH_DF_CU)); vec_reset(&T.df_maps, 1); T.df_collect = 0;
     T.have_rates = 0;
     g_cu_secs = 0; g_cu_calls = 0;
     T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
@@ -467,6 +569,8 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
         ctx->fn_tq = hook_tq;
         T.org_cu = ctx->fn_pinter_analyze_cu;
         ctx->fn_pinter_analyze_cu = hook_cu;
+        T.org_lf = ctx->fn_loop_filter; T.org_df_unit = ctx->fn_deblock_unit;
+        ctx->fn_loop_filter = hook_loop_filter; ctx->fn_deblock_unit = hook_df_unit;
     }
     XEVE_PINTER *pi = &ctx->pinter[0];
     T.cst.w = w; T.cst.h = h; T.cst.bit_depth = ctx->param.codec_bit_depth; T.cst.me_level = pi->me_level;
@@ -533,7 +637,8 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 RH_API int64_t rh_trace_get(int what, void **ptr)
 {
     vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
-             : what == 4 ? &T.pics : what == 5 ? &T.samp : what == 6 ? &T.sbac : what == 7 ? &T.cu : &T.cu_sbac;
+             : what == 4 ? &T.pics : what == 5 ? &T.samp : what == 6 ? &T.sbac : what == 7 ? &T.cu : what == 8 ? &T.cu_sbac
+             : what == 9 ? &T.df : what == 10 ? &T.df_cu : &T.df_maps;
     *ptr = v->p;
     return (int64_t)v->n;
 }
@@ -659,6 +764,7 @@ RH_API const void *rh_table(int which, int *bytes)
     case 11: *bytes = sizeof(xeve_tbl_mc_l_coeff); return xeve_tbl_mc_l_coeff;
     case 12: *bytes = sizeof(xeve_tbl_mc_c_coeff); return xeve_tbl_mc_c_coeff;
     case 13: *bytes = sizeof(util_ctx()->err_scale); return util_ctx()->err_scale;
+    case 14: *bytes = sizeof(xeve_tbl_df_st); return xeve_tbl_df_st;
     }
     *bytes = 0;
     return NULL;

@@ -170,6 +170,39 @@ def _p(a):
 
 
 TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
+TRACE_DF = 32
+
+# deblocking: layouts == xb200_df_cu / xb200_df_pic of include/xeve_b200.h
+DF_CU = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pad_", "u1", (2,))], align=True)
+DF_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("qp_u_offset", "<i4"), ("qp_v_offset", "<i4"),
+                   ("chroma_qp", "<i4", (2, 70))], align=True)
+DF_REC = np.dtype([("poc", "<i4"), ("pre_pic", "<i4"), ("post_pic", "<i4"), ("on", "<i4"), ("cu_first", "<i8"), ("cu_cnt", "<i8"),
+                   ("maps_off", "<i8"), ("pp", DF_PIC)], align=True)
+
+
+def df_maps(maps, off, f):
+    """(map_scu u32[f], map_refi s8[f,2], map_mv s16[f,2,2]) of one traced picture (copies)."""
+    b = maps[off:off + 14 * f]
+    return (np.frombuffer(b[:4 * f].tobytes(), "<u4").copy(), np.frombuffer(b[4 * f:6 * f].tobytes(), "i1").reshape(f, 2).copy(),
+            np.frombuffer(b[6 * f:14 * f].tobytes(), "<i2").reshape(f, 2, 2).copy())
+
+
+def deblock(planes, cus, pp, map_scu, map_refi, map_mv, bit_depth=10):
+    """The reference's xeve_deblock_cu_ver / _hor over a CU list (vertical edges of the whole picture, then horizontal),
+    on copies of the (Y, U, V) active-area arrays; returns (filtered planes, seconds)."""
+    L = lib()
+    L.rh_deblock.restype = C.c_double
+    L.rh_deblock.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    assert L.rh_sizeof_df(1) == DF_CU.itemsize and L.rh_sizeof_df(2) == DF_PIC.itemsize
+    out = [np.ascontiguousarray(a, np.int16).copy() for a in planes]
+    pl = PLANES()
+    pl.y, pl.u, pl.v = (a.ctypes.data for a in out)
+    pl.s_l, pl.s_c, pl.w_l, pl.h_l, pl.poc = out[0].shape[1], out[1].shape[1], out[0].shape[1], out[0].shape[0], 0
+    cus = np.ascontiguousarray(cus, DF_CU)
+    pp = np.ascontiguousarray(pp, DF_PIC).reshape(1)
+    sec = L.rh_deblock(C.addressof(pl), _p(cus), len(cus), _p(pp), _p(np.ascontiguousarray(map_scu, np.uint32)),
+                       _p(np.ascontiguousarray(map_refi, np.int8)), _p(np.ascontiguousarray(map_mv, np.int16)), bit_depth)
+    return out, sec
 PRESET = {"default": 0, "fast": 1, "medium": 2, "slow": 3, "placebo": 4}
 
 
@@ -236,6 +269,8 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
     L.rh_trace_const(_p(cst))
     tr = Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
     tr.sbac, tr.cu, tr.cu_sbac = sbac, cu, cu_sbac
+    assert L.rh_sizeof_df(0) == DF_REC.itemsize, (L.rh_sizeof_df(0), DF_REC.itemsize)
+    tr.df, tr.df_cu, tr.df_maps = grab(9, DF_REC), grab(10, DF_CU), grab(11, np.dtype("u1"))
     return tr
 
 

@@ -667,6 +667,120 @@ void xo_pad_plane(int16_t *buf, int stride, int w, int h, int pad)
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * in-loop deblocking.  Follows src_base/xeve_df.c: boundary-strength class of an edge
+ * segment (:34-87), the 4-sample luma / chroma filters (:89-251), the per-CU edge walks with their
+ * "already coded in this pass" bookkeeping (:253-471) and the two whole-picture passes of
+ * xeve_loop_filter (src_base/xeve_enc.c:2355-2414): vertical edges first, then horizontal edges.
+ * ------------------------------------------------------------------------------------------- */
+#define XO_MCU_IF(m)   (((m) >> 15) & 1)  /* src_base/xeve_def.h:591 */
+#define XO_MCU_QP(m)   (((m) >> 16) & 0x7F)
+#define XO_MCU_CBFL(m) (((m) >> 24) & 1)
+#define XO_MCU_IBC(m)  (((m) >> 26) & 1)
+
+/* boundary class 0..3 of the edge between SCU p (the one whose QP is used) and SCU q, src_base/xeve_df.c:34-87 */
+static int df_class(const uint32_t *scu, const int8_t *refi, const int16_t *mv, int64_t p, int64_t q)
+{
+    if(XO_MCU_IF(scu[p]) || XO_MCU_IF(scu[q])) return 0;
+    if(XO_MCU_CBFL(scu[p]) || XO_MCU_CBFL(scu[q])) return 1;
+    if(XO_MCU_IBC(scu[p]) || XO_MCU_IBC(scu[q])) return 2;
+    int        m[2][2][2]; /* [scu][list][xy], invalid lists count as zero motion */
+    const int8_t *rp = refi + 2 * p, *rq = refi + 2 * q;
+    for(int l = 0; l < 2; l++)
+        for(int k = 0; k < 2; k++) {
+            m[0][l][k] = rp[l] >= 0 ? mv[4 * p + 2 * l + k] : 0;
+            m[1][l][k] = rq[l] >= 0 ? mv[4 * q + 2 * l + k] : 0;
+        }
+    int cross; /* compare list l of p against list l (0) or list 1-l (1) of q */
+    if(rp[0] == rq[0] && rp[1] == rq[1]) cross = 0;
+    else if(rp[0] == rq[1] && rp[1] == rq[0]) cross = 1;
+    else return 2;
+    for(int l = 0; l < 2; l++)
+        for(int k = 0; k < 2; k++)
+            if(abs(m[0][l][k] - m[1][l ^ cross][k]) >= 4) return 2;
+    return 3;
+}
+
+/* one 4-tap line across an edge: p[-2*step] p[-step] | p[0] p[step]; luma moves all four, chroma the inner two
+ * (src_base/xeve_df.c:89-251; s16 intermediates as there, C division truncating toward zero) */
+static void df_line(int16_t *p, int step, int st, int luma, int maxv)
+{
+    int16_t A = p[-2 * step], B = p[-step], Cc = p[0], D = p[step];
+    int16_t d    = (int16_t)((A - (B << 2) + (Cc << 2) - D) / 8);
+    int16_t ad   = (int16_t)(d < 0 ? -d : d);
+    int16_t t16  = (int16_t)((ad - st) << 1); if(t16 < 0) t16 = 0;
+    int16_t clip = (int16_t)(ad - t16);       if(clip < 0) clip = 0;
+    int16_t d1   = (int16_t)(d < 0 ? -clip : clip);
+    B = (int16_t)(B + d1); Cc = (int16_t)(Cc - d1);
+    if(luma) {
+        clip >>= 1;
+        int16_t d2 = (int16_t)((A - D) / 4);
+        d2 = d2 < -clip ? (int16_t)-clip : (d2 > clip ? clip : d2);
+        A = (int16_t)(A - d2); D = (int16_t)(D + d2);
+        p[-2 * step] = (int16_t)(A < 0 ? 0 : (A > maxv ? maxv : A));
+        p[step]      = (int16_t)(D < 0 ? 0 : (D > maxv ? maxv : D));
+    }
+    p[-step] = (int16_t)(B < 0 ? 0 : (B > maxv ? maxv : B));
+    p[0]     = (int16_t)(Cc < 0 ? 0 : (Cc > maxv ? maxv : Cc));
+}
+
+typedef struct {
+    int16_t *pl[3];
+    int      s[3], w, h, bd;
+    const xb200_df_pic *pp;
+    const uint32_t *scu; const int8_t *refi; const int16_t *mv;
+    uint8_t *done;      /* MCU_GET_COD of the current pass */
+} df_ctx;
+
+/* filter the 4-sample (2 for chroma) segment between SCU p (current side) and q; `hor` = horizontal edge */
+static void df_segment(const df_ctx *d, int x_scu, int y_scu, int64_t p, int64_t q, int hor)
+{
+    const int cls = df_class(d->scu, d->refi, d->mv, p, q), qp = XO_MCU_QP(d->scu[p]);
+    const int maxv = (1 << d->bd) - 1, bdo = 6 * (d->bd - 8);
+    int st = xb200_df_strength(cls, qp) << (d->bd - 8);
+    if(st) {
+        int16_t *b = d->pl[0] + (int64_t)(y_scu * 4) * d->s[0] + x_scu * 4;
+        for(int i = 0; i < 4; i++) df_line(hor ? b + i : b + (int64_t)i * d->s[0], hor ? d->s[0] : 1, st, 1, maxv);
+    }
+    for(int c = 1; c < 3; c++) {
+        int qc = qp + (c == 1 ? d->pp->qp_u_offset : d->pp->qp_v_offset);
+        qc = qc < -bdo ? -bdo : (qc > 57 ? 57 : qc);
+        st = xb200_df_strength(cls, d->pp->chroma_qp[c - 1][qc + bdo]) << (d->bd - 8);
+        if(!st) continue;
+        int16_t *b = d->pl[c] + (int64_t)(y_scu * 2) * d->s[c] + x_scu * 2;
+        for(int i = 0; i < 2; i++) df_line(hor ? b + i : b + (int64_t)i * d->s[c], hor ? d->s[c] : 1, st, 0, maxv);
+    }
+}
+
+void xo_deblock(int16_t *y, int16_t *u, int16_t *v, int s_l, int s_c, int w, int h, const xb200_df_cu *cus, int64_t n,
+                const xb200_df_pic *pp, const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int bit_depth)
+{
+    const int ws = pp->w_scu;
+    df_ctx d = {{y, u, v}, {s_l, s_c, s_c}, w, h, bit_depth, pp, map_scu, map_refi, map_mv, NULL};
+    d.done = malloc((size_t)ws * pp->h_scu);
+    for(int hor = 0; hor <= 1; hor++) {
+        memset(d.done, 0, (size_t)ws * pp->h_scu);
+        for(int64_t i = 0; i < n; i++) {
+            const int xs = cus[i].x >> 2, ys = cus[i].y >> 2, cw = (1 << cus[i].log2_cuw) >> 2, ch = (1 << cus[i].log2_cuh) >> 2;
+            const int64_t t = xs + (int64_t)ys * ws;
+            if(hor) { /* top edge, src_base/xeve_df.c:296-324 */
+                if(cus[i].y > 0)
+                    for(int k = 0; k < cw; k++) df_segment(&d, xs + k, ys, t + k, t + k - ws, 1);
+            }
+            else {    /* left edge if the left neighbour was visited in this pass (:386-417), then the right edge if the
+                         right neighbour already was (:419-462; cannot happen in z-scan order, kept for fidelity) */
+                if(cus[i].x > 0 && d.done[t - 1])
+                    for(int k = 0; k < ch; k++) df_segment(&d, xs, ys + k, t + (int64_t)k * ws, t + (int64_t)k * ws - 1, 0);
+                if(cus[i].x + (cw << 2) < w && d.done[t + cw])
+                    for(int k = 0; k < ch; k++)
+                        df_segment(&d, xs + cw, ys + k, t + (int64_t)k * ws + cw, t + (int64_t)k * ws + cw - 1, 0);
+            }
+            for(int r = 0; r < ch; r++) memset(d.done + t + (int64_t)r * ws, 1, cw);
+        }
+    }
+    free(d.done);
+}
+
 /* get_org_bi, src_base/xeve_pinter.c:143-156, applied to the luma prediction of one fn_mc call */
 void xo_bi_org(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int cur_pic, int16_t *org_bi)
 {

@@ -477,3 +477,54 @@ def test_analyze_cu_matches_reference_in_situ(trace, gpu_ctx):
     assert np.array_equal(coef, ocoef) and np.array_equal(rec, orec)
     assert np.array_equal(got["cost"], o["cost"]) and np.array_equal(got["mvp_idx"], o["mvp_idx"])
     assert st[cu["state_out"]].tobytes() == so[cu["state_out"]].tobytes()
+
+
+# ---- deblocking ---------------------------------------------------------------------------------------
+def _gpu_deblock(hp, d, expand=True):
+    h = hp.pic_create(padded=True)
+    hp.pic_upload_s16(h, *(np.ascontiguousarray(a) for a in d["pre"]))
+    hp.deblock(h, d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"], expand=expand)
+    act, full = hp.pic_download(h, with_padding=False), hp.pic_download(h, with_padding=True)
+    hp.pic_destroy(h)
+    return act, full
+
+
+def test_deblock_matches_reference_in_situ():
+    """xb200_deblock == the picture xeve_loop_filter left behind (golden fixture always; live pictures incl. another preset
+    and QP when oracle/_ref is here), and the expanded borders == xeve_picbuf_expand of that picture"""
+    pics = tracedata.golden_df()
+    if rh.available():
+        pics += tracedata.live_df(pic_hi=5) + tracedata.live_df(pic_hi=2, preset="medium", extra="qp=22")
+    h, w = pics[0]["pre"][0].shape
+    hp = api.Hotpath(api.make_seq(w, h))
+    for d in pics:
+        act, full = _gpu_deblock(hp, d)
+        for k, (g, e) in enumerate(zip(act, d["post"])):
+            assert np.array_equal(g, e), k
+        for k, (g, e) in enumerate(zip(full, d["post"])):
+            pad = 144 if k == 0 else 72
+            assert np.array_equal(g, np.pad(e, pad, mode="edge")), k
+    hp.close()
+
+
+@pytest.mark.parametrize("w,h,seed", [(64, 64, 0), (200, 136, 1), (1920, 1080, 2)])
+def test_deblock_matches_oracle_synthetic(w, h, seed):
+    """random quad-trees down to 4x4 with 30 % intra CUs (long chroma runs), random strengths, up to full 1080p"""
+    d = tracedata.synth_df(w, h, seed, intra_frac=0.3)
+    exp = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+    hp = api.Hotpath(api.make_seq(w, h))
+    act, _ = _gpu_deblock(hp, d, expand=False)
+    for k, (g, e) in enumerate(zip(act, exp)):
+        assert np.array_equal(g, e), k
+    # idempotence-style property at full size: a picture whose maps say "no edge is active" (class 3) comes back untouched
+    quiet = dict(d, map_scu=(d["map_scu"] & ~np.uint32((1 << 15) | (1 << 24))), map_refi=np.zeros_like(d["map_refi"]),
+                 map_mv=np.zeros_like(d["map_mv"]))
+    act, _ = _gpu_deblock(hp, quiet, expand=False)
+    assert all(np.array_equal(g, e) for g, e in zip(act, d["pre"]))
+    # argument checks
+    bad = d["cus"].copy()
+    bad["x"][0] = w
+    hb = hp.pic_create(padded=True)
+    with pytest.raises(api.Xb200Error):
+        hp.deblock(hb, bad, d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+    hp.close()

@@ -183,3 +183,34 @@ def test_oracle_analyze_cu_matches_reference_in_situ_cif(trace):
     o, st, coef, rec = xo.analyze_cu_batch(td.seq, td.oracle_planes(), td.cu_rates, cu, td.cu_sbac, elems)
     assert len(cu) > 5000
     tracedata.check_cu_results(o, td.cu, coef, rec, sz, st, td.cu_sbac)
+
+
+# ---- deblocking ---------------------------------------------------------------------------------------
+def test_oracle_deblock_matches_golden():
+    """xo_deblock == the picture the reference's xeve_loop_filter left behind, on the committed fixture (incl. the intra
+    picture whose 4x4 CUs make chroma edges 2 samples apart)"""
+    pics = tracedata.golden_df()
+    assert len(pics) == 3 and (pics[0]["cus"]["log2_cuw"] == 2).sum() >= 8
+    for d in pics:
+        got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+        assert any(not np.array_equal(a, b) for a, b in zip(d["pre"], d["post"]))  # the filter did something
+        for g, e in zip(got, d["post"]):
+            assert np.array_equal(g, e)
+
+
+@needs_ref
+def test_oracle_deblock_matches_reference_live_and_synthetic():
+    """in-situ results of a live encode (two presets), then the reference's exported edge filters replayed over random
+    well-formed inputs, in coding order and in shuffled order (exercises the right-edge / COD branches)"""
+    for kw in (dict(pic_hi=4), dict(pic_hi=2, preset="medium", extra="qp=22")):
+        for d in tracedata.live_df(**kw):
+            got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+            assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
+    rng = np.random.default_rng(3)
+    for seed, (w, h) in enumerate(((64, 64), (200, 136), (352, 288))):
+        d = tracedata.synth_df(w, h, seed, intra_frac=0.3)
+        for order in (np.arange(len(d["cus"])), rng.permutation(len(d["cus"]))):
+            exp, _ = rh.deblock(d["pre"], d["cus"][order], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+            got = xo.deblock(d["pre"], d["cus"][order], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+            assert all(np.array_equal(g, e) for g, e in zip(got, exp))
+            assert not np.array_equal(exp[1], d["pre"][1])

@@ -23,6 +23,7 @@ int main(void){
   printf("seq %zu\nme %zu\nmc %zu\nrates %zu\ntq %zu\nres %zu\nblk %zu\n", sizeof(xb200_seq), sizeof(xb200_me_item),
          sizeof(xb200_mc_item), sizeof(xb200_rates), sizeof(xb200_tq_item), sizeof(xb200_residue_item), sizeof(xb200_blk_item));
   printf("sbac %zu\nbits %zu\ncu %zu\nmvpi %zu\n", sizeof(xb200_sbac), sizeof(xb200_bits_item), sizeof(xb200_cu_item), sizeof(xb200_mvp_item));
+  printf("dfcu %zu\ndfpic %zu\n", sizeof(xb200_df_cu), sizeof(xb200_df_pic));
   printf("cuoff %zu %zu %zu %zu\n", offsetof(xb200_cu_item, lambda), offsetof(xb200_cu_item, mvp), offsetof(xb200_cu_item, cost), offsetof(xb200_bits_item, coef_off));
   printf("off %zu %zu %zu %zu\n", offsetof(xb200_me_item, lambda_mv), offsetof(xb200_tq_item, lambda),
          offsetof(xb200_residue_item, out_off), offsetof(xb200_residue_item, dist_rec));
@@ -34,6 +35,7 @@ int main(void){
   f = fopen("mvbits.bin","wb"); for(int v=-2047; v<=2048; v++){ unsigned char b=(unsigned char)xb200_mvd_bits(v); fwrite(&b,1,1,f);} fclose(f);
   f = fopen("refi.bin","wb"); for(int n=0;n<17;n++) for(int r=0;r<16;r++){ unsigned char b = r<n||n==0 ? (unsigned char)xb200_refi_bits(n,r):0; fwrite(&b,1,1,f);} fclose(f);
   f = fopen("es.bin","wb"); for(int q=0;q<6;q++) for(int l=1;l<=7;l++){ long long e = xb200_err_scale(q,l,10); fwrite(&e,8,1,f);} fclose(f);
+  f = fopen("dfst.bin","wb"); for(int i=0;i<4;i++) for(int q=0;q<52;q++){ unsigned char b=(unsigned char)xb200_df_strength(i,q); fwrite(&b,1,1,f);} fclose(f);
   return 0; }
 '''
 
@@ -60,6 +62,7 @@ def test_struct_layouts_match_numpy(probe_dir):
     assert int(sizes["blk"]) == api.BLK_ITEM.itemsize
     assert int(sizes["sbac"]) == api.SBAC.itemsize and int(sizes["bits"]) == api.BITS_ITEM.itemsize
     assert int(sizes["cu"]) == api.CU_ITEM.itemsize == rh.CU_REC.itemsize and int(sizes["mvpi"]) == api.MVP_ITEM.itemsize
+    assert int(sizes["dfcu"]) == api.DF_CU.itemsize == rh.DF_CU.itemsize and int(sizes["dfpic"]) == api.DF_PIC.itemsize == rh.DF_PIC.itemsize
     cuoffs = [int(v) for v in re.search(r"cuoff (\d+) (\d+) (\d+) (\d+)", out).groups()]
     assert cuoffs == [api.CU_ITEM.fields["lambda"][1], api.CU_ITEM.fields["mvp"][1], api.CU_ITEM.fields["cost"][1],
                       api.BITS_ITEM.fields["coef_off"][1]]
@@ -90,6 +93,7 @@ def test_generated_tables_match_reference(probe_dir):
     assert np.array_equal(rd("mvbits.bin", np.uint8), rh.table(6, np.uint8))
     assert np.array_equal(rd("refi.bin", np.uint8).reshape(17, 16), rh.table(7, np.uint8).reshape(17, 16))
     assert np.array_equal(rd("es.bin", np.int64).reshape(6, 7), rh.table(13, np.int64).reshape(6, 7))
+    assert np.array_equal(rd("dfst.bin", np.uint8), rh.table(14, np.uint8))
     assert list(rh.table(9, np.int32)) == [40, 45, 51, 57, 64, 71]
     assert list(rh.table(10, np.int32)[:6]) == [26214, 23302, 20560, 18396, 16384, 14764]
 

@@ -110,6 +110,89 @@ def golden_trace() -> TraceData:
     return td
 
 
+DF_GOLDEN = os.path.join(ROOT, "tests", "golden", "df_golden.npz")
+
+
+def live_df(name="cif", frames=20, pic_lo=0, pic_hi=2, preset="fast", extra="", **override):
+    """Deblocking inputs / in-situ results of the traced pictures: list of dicts {pre, post: (Y, U, V) active areas,
+    cus, pp, map_scu, map_refi, map_mv}."""
+    override = override or QCIF
+    c, yuv = clip_yuv(name, frames, **override)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_DF, pic_lo=pic_lo,
+                        pic_hi=pic_hi)
+
+    def act(i):
+        p, full = tr.pics[i], tr.plane_views(i)
+        pl, pc, w, h = int(p["pad_l"]), int(p["pad_c"]), int(p["w_l"]), int(p["h_l"])
+        return [full[0][pl:pl + h, pl:pl + w].copy(), full[1][pc:pc + h // 2, pc:pc + w // 2].copy(),
+                full[2][pc:pc + h // 2, pc:pc + w // 2].copy()]
+    out = []
+    for r in tr.df:
+        assert int(r["on"]) == 1
+        f = int(r["pp"]["w_scu"]) * int(r["pp"]["h_scu"])
+        ms, mr, mm = rh.df_maps(tr.df_maps, int(r["maps_off"]), f)
+        out.append(dict(pre=act(int(r["pre_pic"])), post=act(int(r["post_pic"])), pp=r["pp"].copy(), map_scu=ms, map_refi=mr,
+                        map_mv=mm, cus=tr.df_cu[int(r["cu_first"]):int(r["cu_first"] + r["cu_cnt"])].copy(), poc=int(r["poc"])))
+    return out
+
+
+def golden_df():
+    z = np.load(DF_GOLDEN)
+    return [dict(pre=[z[f"pre{i}_{k}"] for k in "yuv"], post=[z[f"post{i}_{k}"] for k in "yuv"], cus=z[f"cus{i}"], pp=z[f"pp{i}"],
+                 map_scu=z[f"map_scu{i}"], map_refi=z[f"map_refi{i}"], map_mv=z[f"map_mv{i}"]) for i in range(int(z["n"]))]
+
+
+def synth_df(w, h, seed, intra_frac=0.1):
+    """Random but well-formed deblocking input at any size: a random quad-tree per 64x64 CTU down to 4x4 (z-scan order, CUs
+    clipped to the picture like the reference's implicit boundary splits), random per-CU intra / cbf / QP / motion, random
+    samples.  Returns the dict layout of live_df() without `post`."""
+    rng = np.random.default_rng(seed)
+    ws, hs = w // 4, h // 4
+    cus = []
+
+    def tree(x, y, l2):
+        if x >= w or y >= h:
+            return
+        size = 1 << l2
+        if x + size > w or y + size > h or (l2 > 2 and rng.random() < (0.9 if l2 > 4 else 0.45)):
+            for dy in (0, size // 2):
+                for dx in (0, size // 2):
+                    tree(x + dx, y + dy, l2 - 1)
+        else:
+            cus.append((x, y, l2, l2, (0, 0)))
+    for y in range(0, h, 64):
+        for x in range(0, w, 64):
+            tree(x, y, 6)
+    from xeve_b200 import api
+    cus = np.array(cus, api.DF_CU)
+    map_scu = np.zeros((hs, ws), np.uint32)
+    map_refi = np.zeros((hs, ws, 2), np.int8)
+    map_mv = np.zeros((hs, ws, 2, 2), np.int16)
+    n = len(cus)
+    intra = rng.random(n) < intra_frac
+    cbf = rng.random(n) < 0.4
+    qp = rng.integers(22, 52, n)
+    refi = rng.integers(-1, 2, (n, 2)).astype(np.int8)
+    refi[(refi < 0).all(1), 0] = 0
+    mv = rng.integers(-6, 7, (n, 2, 2)).astype(np.int16)
+    for i, c in enumerate(cus):
+        xs, ys, cw = int(c["x"]) >> 2, int(c["y"]) >> 2, (1 << int(c["log2_cuw"])) >> 2
+        v = (int(qp[i]) << 16) | (int(intra[i]) << 15) | (int(cbf[i] and not intra[i]) << 24) | (1 << 31)
+        map_scu[ys:ys + cw, xs:xs + cw] = v
+        map_refi[ys:ys + cw, xs:xs + cw] = -1 if intra[i] else refi[i]
+        map_mv[ys:ys + cw, xs:xs + cw] = 0 if intra[i] else mv[i]
+    pp = np.zeros(1, api.DF_PIC)
+    pp["w_scu"], pp["h_scu"], pp["qp_u_offset"], pp["qp_v_offset"] = ws, hs, int(rng.integers(-2, 3)), int(rng.integers(-2, 3))
+    tab = np.arange(-12, 58)
+    pp["chroma_qp"][0, 0] = np.where(tab < 30, tab, 30 + (tab - 30) * 3 // 4)   # a plausible monotone mapping
+    pp["chroma_qp"][0, 1] = np.where(tab < 33, tab, 33 + (tab - 33) * 2 // 3)
+    base = rng.integers(0, 1024, (h // 8 + 1, w // 8 + 1))
+    yy = np.kron(base, np.ones((8, 8), np.int64))[:h, :w] + rng.integers(-20, 21, (h, w))
+    pre = [np.clip(yy, 0, 1023).astype(np.int16), np.clip(yy[::2, ::2] + rng.integers(-9, 10, (h // 2, w // 2)), 0, 1023).astype(np.int16),
+           rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16)]
+    return dict(pre=pre, cus=cus, pp=pp[0], map_scu=map_scu.reshape(-1), map_refi=map_refi.reshape(-1, 2), map_mv=map_mv.reshape(-1, 2, 2))
+
+
 def cu_slots(cu):
     """(items with out_off assigned, per-item slot sizes, total elements) for the coef / rec outputs of a CU list."""
     cu = cu.copy()

@@ -79,6 +79,10 @@ MVP_ITEM = np.dtype([
 ], align=True)
 MVP_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("poc", "<i4"), ("ref_poc", "<i4", (2,)), ("col_list_poc0", "<i4")], align=True)
 
+DF_CU = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pad_", "u1", (2,))], align=True)
+DF_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("qp_u_offset", "<i4"), ("qp_v_offset", "<i4"),
+                   ("chroma_qp", "<i4", (2, 70))], align=True)
+
 SBAC = np.dtype([("range", "<u4"), ("m", "<u2", (68,))], align=True)
 BITS_ITEM = np.dtype([
     ("kind", "u1"), ("slice_type", "u1"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pidx", "u1"), ("ch", "u1"),
@@ -143,6 +147,7 @@ def load():
         L.xb200_rdo_bits.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]
         L.xb200_rdoq_rates.argtypes = [VP, VP, C.c_int64, VP]
         L.xb200_analyze_cu.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
+        L.xb200_deblock.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -150,7 +155,7 @@ def load():
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
-           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu"]
+           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock"]
 
 
 def _p(a):
@@ -290,6 +295,14 @@ class Hotpath:
                                   _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_mv, np.int16)),
                                   _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16))), "xb200_mvp")
         return items
+
+    def deblock(self, handle, cus, pp, map_scu, map_refi, map_mv, expand=True):
+        """xeve_loop_filter (+ xeve_picbuf_expand) on the device picture `handle`, in place"""
+        cus = np.ascontiguousarray(cus, DF_CU)
+        pp = np.ascontiguousarray(pp, DF_PIC).reshape(1)
+        self._ck(self.L.xb200_deblock(self.h, handle, _p(cus), len(cus), _p(pp), _p(np.ascontiguousarray(map_scu, np.uint32)),
+                                      _p(np.ascontiguousarray(map_refi, np.int8)), _p(np.ascontiguousarray(map_mv, np.int16)),
+                                      int(expand), MEM_HOST), "xb200_deblock")
 
     def rdo_bits(self, items, states, coef=None):
         """-> (items with .bits, states with the state_out slots written)"""

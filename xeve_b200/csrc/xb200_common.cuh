@@ -26,17 +26,21 @@ struct SeqDev {
     int32_t tc_dct; // 32/64-point forward DCT on tcgen05 (bit-identical; off by default)
 };
 
+#ifndef XB200_NO_CONSTANTS // the tables are defined once, in the translation unit that uploads them (xb200_api.cu)
 __constant__ int8_t  c_tm64[64 * 64];           // DCT-II matrix, N-point rows at stride 64/N
 __constant__ int16_t c_mc_l[4][8];              // luma taps by quarter-pel phase
 __constant__ int16_t c_mc_c[8][4];              // chroma taps by eighth-pel phase
 __constant__ int32_t c_quant_scale[6];
 __constant__ int32_t c_dequant_scale[6];
 __constant__ int64_t c_err_scale[6][7];         // [qp % 6][log2 size] (host-computed doubles -> s64)
+#endif
 
 #define XB_DEV __device__ __forceinline__
 
 XB_DEV int clip3i(int lo, int hi, int v) { return max(lo, min(hi, v)); }
+#ifndef XB200_NO_CONSTANTS
 XB_DEV int tmN(int log2n, int k, int n) { return c_tm64[(k << (6 - log2n)) * 64 + n]; }
+#endif
 
 XB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

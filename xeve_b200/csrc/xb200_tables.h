@@ -100,3 +100,18 @@ static inline int64_t xb200_err_scale(int qp_rem, int log2_size, int bit_depth)
     e               = e / q[qp_rem] / (1 << (bit_depth - 8));
     return (int64_t)(e * (double)(1 << 20));
 }
+
+// Deblocking filter strength (EVC Baseline table, src_base/xeve_tbl.c:239-257): the intra row is a step function of qp
+// with steps at the qps below; the "luma cbf" and "motion differs" rows are the same curve lowered by 1 and 2 (floored
+// at 0), the fourth row is all zero.  qp outside 0..51 never occurs for the values the encoder stores (clamped here).
+XB_HD int xb200_df_strength(int idx, int qp)
+{
+    if(idx > 2) return 0;
+    qp = qp < 0 ? 0 : (qp > 51 ? 51 : qp);
+    //                        st:  1   2   3   4   5   6   7   8   9  10  11  12
+    const unsigned char step[12] = {18, 27, 32, 35, 38, 40, 42, 43, 44, 45, 46, 47};
+    int st = 0;
+    for(int i = 0; i < 12; i++) st += qp >= step[i];
+    st -= idx;
+    return st < 0 ? 0 : st;
+}
