@@ -251,6 +251,41 @@ def run_b200(args, rank, world, dist):
                "d2h_bytes": int(cu_items.nbytes + fw.cu_states.nbytes + 4 * fw.cu_elems),
                "best_mode_hist": np.bincount(cu_out["best_idx"], minlength=5).tolist(),
                "note": "whole xeve_pinter_analyze_cu per CU on the device (skip/direct/L0/L1/BI + cbf RDO + CABAC bit counts)"}
+    # ---- in-loop deblocking + border expansion of one reconstructed picture (xb200_deblock) ------------
+    from xeve_b200.worklist import synth_deblock
+    df = synth_deblock(W, H, seed=rank)
+    df_pic = hp.pic_create(padded=True)
+    df_pre = [np.ascontiguousarray(a) for a in df["pre"]]
+    df_args = [np.ascontiguousarray(df["cus"], api.DF_CU), np.ascontiguousarray(df["pp"], api.DF_PIC).reshape(1),
+               np.ascontiguousarray(df["map_scu"], np.uint32), np.ascontiguousarray(df["map_refi"], np.int8),
+               np.ascontiguousarray(df["map_mv"], np.int16)]
+    df_dev = [dv(a) for a in (df_args[0], df_args[2], df_args[3], df_args[4])]
+    t_df_k = t_df_h = 0.0
+    df_steps = max(3, args.steps // 2)
+    for it in range(df_steps + 1):
+        hp.pic_upload_s16(df_pic, *df_pre)     # the unfiltered reconstruction (untimed: it is produced on the device)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        r = L.xb200_deblock(ctx, df_pic, P(df_dev[0]), len(df_args[0]), df_args[1].ctypes.data_as(C.c_void_p), P(df_dev[1]), P(df_dev[2]),
+                            P(df_dev[3]), 1, api.MEM_DEVICE)
+        if r:
+            raise RuntimeError(f"deblock failed: {r}")
+        if it:
+            t_df_k += hp.last_kernel_ms
+        hp.pic_upload_s16(df_pic, *df_pre)
+        t0 = time.perf_counter()
+        hp.deblock(df_pic, *df_args)           # host-buffer API: CU list + frame maps go in with the call
+        if it:
+            t_df_h += time.perf_counter() - t0
+    f_scu = (W // 4) * (H // 4)
+    df_alg = 2 * (W * H * 3 // 2 * 2) + 14 * f_scu + df_args[0].nbytes + 2 * f_scu \
+        + 2 * ((W + 288) * (H + 288) - W * H) + 4 * ((W // 2 + 144) * (H // 2 + 144) - W * H // 4)
+    deblock = {"cus_per_frame": int(len(df_args[0])), "kernel_ms_per_frame": round(t_df_k / df_steps, 4),
+               "host_api_ms_per_frame": round(t_df_h / df_steps * 1e3, 3), "launches_per_frame": 6,
+               "algorithmic_bytes": int(df_alg), "achieved_gbs": round(df_alg / (t_df_k / df_steps * 1e-3) / 1e9, 1),
+               "note": "mark edges + vertical-edge pass + horizontal-edge pass + 3 border-expansion grids, L2 flushed before the call; "
+                       "random quad-tree down to 4x4, 10 % intra CUs"}
+    hp.pic_destroy(df_pic)
     sampler.stop_flag = True
     frame_bytes = W * H * 3 // 2 * bps
     h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
@@ -289,6 +324,7 @@ def run_b200(args, rank, world, dist):
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: round(v, 3) for k, v in per_stage.items()},
         "analyze_cu": analyze,
+        "deblock": deblock,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get(dom),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -374,6 +410,19 @@ def reference_cu_rate(frames=3):
             "sample": f"xeve_pinter_analyze_cu inside a real 1-thread encode of {frames} {c.w}x{c.h} pictures (inter pictures only)"}
 
 
+def reference_deblock():
+    """The reference's own edge filters (xeve_deblock_cu_ver / _hor, one thread -- xeve_loop_filter is single-threaded with one
+    tile) over the same synthetic picture as the b200 arm's deblock line."""
+    from oracle import refharness as rh
+    from xeve_b200.worklist import synth_deblock
+    if not rh.available():
+        return {"unavailable": "oracle/_ref not present"}
+    df = synth_deblock(W, H, seed=0)
+    secs = [rh.deblock(df["pre"], df["cus"].astype(rh.DF_CU), df["pp"], df["map_scu"], df["map_refi"], df["map_mv"])[1] for _ in range(3)]
+    return {"ms_per_frame": round(min(secs) * 1e3, 3), "cores": 1, "kind": "reference",
+            "sample": "whole picture, best of 3 (filter only; the reference's border expansion is not included)"}
+
+
 # ---- helper module (kept here so bench.py is self-contained) -----------------------------------------------------
 import types  # noqa: E402
 
@@ -432,6 +481,7 @@ def main():
             a.steps, a.warmup = 1, 1
             ref = run_reference(a)
             out["cpu_baseline"] = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+            out["deblock"]["cpu_reference"] = reference_deblock()
             cur = reference_cu_rate()
             out["analyze_cu"]["cpu_reference"] = cur
             if cur.get("cus_per_s_per_core"):

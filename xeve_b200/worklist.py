@@ -178,3 +178,53 @@ class FrameWork:
     # ---- bookkeeping for bench.py ------------------------------------------------------------------------
     def counts(self):
         return dict(cus=self.n_cu, me_uni=2 * self.n_cu, bi_org=self.n_cu, me_bi=self.n_cu, residue=3 * self.n_cu)
+
+
+def synth_deblock(w, h, seed, intra_frac=0.1):
+    """Random but well-formed deblocking input at any size: a random quad-tree per 64x64 CTU down to 4x4 (z-scan order, CUs
+    clipped to the picture like the reference's implicit boundary splits), random per-CU intra / cbf / QP / motion, random
+    samples.  Returns dict(pre=(Y, U, V), cus, pp, map_scu, map_refi, map_mv)."""
+    rng = np.random.default_rng(seed)
+    ws, hs = w // 4, h // 4
+    cus = []
+
+    def tree(x, y, l2):
+        if x >= w or y >= h:
+            return
+        size = 1 << l2
+        if x + size > w or y + size > h or (l2 > 2 and rng.random() < (0.9 if l2 > 4 else 0.45)):
+            for dy in (0, size // 2):
+                for dx in (0, size // 2):
+                    tree(x + dx, y + dy, l2 - 1)
+        else:
+            cus.append((x, y, l2, l2, (0, 0)))
+    for y in range(0, h, 64):
+        for x in range(0, w, 64):
+            tree(x, y, 6)
+    cus = np.array(cus, api.DF_CU)
+    map_scu = np.zeros((hs, ws), np.uint32)
+    map_refi = np.zeros((hs, ws, 2), np.int8)
+    map_mv = np.zeros((hs, ws, 2, 2), np.int16)
+    n = len(cus)
+    intra = rng.random(n) < intra_frac
+    cbf = rng.random(n) < 0.4
+    qp = rng.integers(22, 52, n)
+    refi = rng.integers(-1, 2, (n, 2)).astype(np.int8)
+    refi[(refi < 0).all(1), 0] = 0
+    mv = rng.integers(-6, 7, (n, 2, 2)).astype(np.int16)
+    for i, c in enumerate(cus):
+        xs, ys, cw = int(c["x"]) >> 2, int(c["y"]) >> 2, (1 << int(c["log2_cuw"])) >> 2
+        v = (int(qp[i]) << 16) | (int(intra[i]) << 15) | (int(cbf[i] and not intra[i]) << 24) | (1 << 31)
+        map_scu[ys:ys + cw, xs:xs + cw] = v
+        map_refi[ys:ys + cw, xs:xs + cw] = -1 if intra[i] else refi[i]
+        map_mv[ys:ys + cw, xs:xs + cw] = 0 if intra[i] else mv[i]
+    pp = np.zeros(1, api.DF_PIC)
+    pp["w_scu"], pp["h_scu"], pp["qp_u_offset"], pp["qp_v_offset"] = ws, hs, int(rng.integers(-2, 3)), int(rng.integers(-2, 3))
+    tab = np.arange(-12, 58)
+    pp["chroma_qp"][0, 0] = np.where(tab < 30, tab, 30 + (tab - 30) * 3 // 4)   # a plausible monotone mapping
+    pp["chroma_qp"][0, 1] = np.where(tab < 33, tab, 33 + (tab - 33) * 2 // 3)
+    base = rng.integers(0, 1024, (h // 8 + 1, w // 8 + 1))
+    yy = np.kron(base, np.ones((8, 8), np.int64))[:h, :w] + rng.integers(-20, 21, (h, w))
+    pre = [np.clip(yy, 0, 1023).astype(np.int16), np.clip(yy[::2, ::2] + rng.integers(-9, 10, (h // 2, w // 2)), 0, 1023).astype(np.int16),
+           rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16)]
+    return dict(pre=pre, cus=cus, pp=pp[0], map_scu=map_scu.reshape(-1), map_refi=map_refi.reshape(-1, 2), map_mv=map_mv.reshape(-1, 2, 2))
