@@ -27,6 +27,8 @@
  *   xb200_residue            the distortion/transform body of pinter_residue_rdo
  *                            (src_base/xeve_pinter.c:961-1056): fn_mc -> xeve_diff_pred -> SSD ->
  *                            fn_tq -> fn_itdp -> fn_recon -> SSD, fused on the device
+ *   xb200_analyze_intra      ctx->fn_pintra_analyze_cu = pintra_analyze_cu (src_base/xeve_pintra.c:544-698,
+ *                            hook declared src_base/xeve_type.h:966) over xeve_ipred (src_base/xeve_ipred.c:99-228)
  *   xb200_deblock            ctx->fn_loop_filter = xeve_loop_filter (src_base/xeve_enc.c:2355-2414) ->
  *                            xeve_deblock / _cu_ver / _cu_hor   (src_base/xeve_df.c:34-573)
  *                            + ctx->fn_picbuf_expand            (src_base/xeve_enc.c:1274)
@@ -252,6 +254,39 @@ typedef struct {
     int32_t  me_first, me_cnt;      /* unused by the library (test bookkeeping) */
 } xb200_cu_item;
 
+/* ---- intra analysis of one CU -----------------------------------------------------------------------
+ * One ctx->fn_pintra_analyze_cu call (src_base/xeve_pintra.c:544-698), Baseline profile: the five intra modes (DC, HOR,
+ * VER, UL, UR; xeve_ipred, src_base/xeve_ipred.c:99-228) ranked by SATD + mode bits (make_ipred_list, :308-374, pruned
+ * against core->inter_satd), a luma RDO per surviving mode (transform, RDOQ, CABAC bit count, reconstruction, SSD;
+ * pintra_residue_rdo :69-272), chroma with the winning mode, and the final CU bit count.  The neighbourhood enters as
+ * the reference samples xeve_get_nbr (src_base/xeve_ipred.c:33-97) assembled from the picture being reconstructed: at
+ * element offset nb_off of `side`, per plane c (size n = cuw, cuw/2, cuw/2): left[-1 .. 2n-1] then up[-1 .. 2n-1]
+ * (2n+1 samples each, unavailable ones already replaced by 1 << (bit_depth-1)); 8*cuw + 6 samples per CU.
+ * The two ctx.intra_dir context models of the coder states travel in the item (xb200_sbac holds the inter syntax). */
+typedef struct {
+    int32_t  poc, cur_pic;          /* POC and original-picture handle of the picture being coded */
+    int16_t  x, y;
+    uint8_t  log2_cuw, log2_cuh, slice_type, ctx_skip, ctx_pred_mode, all_preds;
+    uint8_t  qp[3];                 /* core->qp_y/u/v */
+    uint8_t  mpm[5];                /* core->mpm_b_list[ipm] = xeve_tbl_mpm[ipm_l][ipm_u][ipm] (xeve_get_mpm, src_base/xeve_ipred.c:230-252) */
+    uint8_t  pad0_[2];
+    uint32_t inter_satd;            /* core->inter_satd (src_base/xeve_mode.c:1247-1258), UINT32_MAX when there is no inter mode */
+    int32_t  rate_idx;              /* RDOQ rate tables of the input coder state */
+    int32_t  state_in, state_out;   /* coder state slots: core->s_curr_best[..] in, core->s_temp_best out */
+    uint16_t cm_ipm_in[2];          /* ctx.intra_dir models of the input state */
+    uint16_t cm_ipm_out[2];         /* result: the same models after the CU */
+    double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
+    int64_t  nb_off;                /* neighbour samples in `side` */
+    int64_t  out_off;               /* element offset of this CU's coef / rec slots (3/2 * cuw * cuh each) */
+    /* results */
+    double   cost;                  /* return value (MAX_COST 1.7e308 when every mode was pruned) */
+    int32_t  dist_cu;               /* core->dist_cu */
+    int8_t   ipm[2];                /* core->ipm[] */
+    uint8_t  pad1_[2];
+    int32_t  nnz[3];
+    uint64_t coef_hash, rec_hash;   /* unused by the library (test bookkeeping) */
+} xb200_intra_item;
+
 /* ---- in-loop deblocking of a reconstructed picture --------------------------------------------------
  * One leaf CU of the coding tree, as xeve_deblock_tree hands it to ctx->fn_deblock_unit (src_base/xeve_df.c:575-639). */
 typedef struct {
@@ -336,6 +371,12 @@ XB200_API int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, c
  * reference itself recomputes the reconstruction of the winning mode (src_base/xeve_pinter.c:2006-2038). */
 XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates,
                             int64_t n_rates, int16_t *coef, int16_t *rec, int64_t elems, int mem);
+
+/* pintra_analyze_cu over a list of CUs (host buffers); items are independent of each other, like xb200_analyze_cu.
+ * CU sizes 4x4 .. 32x32 (param.min_cu_intra .. max_cu_intra of every preset but placebo). */
+XB200_API int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates,
+                                  xb200_sbac *states, int64_t n_states, const int16_t *side, int64_t side_elems, int16_t *coef,
+                                  int16_t *rec, int64_t elems);
 
 /* In-loop deblocking of picture `pic` (a padded picture holding the unfiltered reconstruction), in place: every CU's left
  * edge (x > 0), then every CU's top edge (y > 0), 4-sample segments with the filter strength derived from the two

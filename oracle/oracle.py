@@ -157,3 +157,15 @@ def deblock(planes, cus, pp, map_scu, map_refi, map_mv, bit_depth=10):
                  len(cus), _p(pp), _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_refi, np.int8)),
                  _p(np.ascontiguousarray(map_mv, np.int16)), bit_depth)
     return out
+
+
+def analyze_intra_batch(seq, planes, rates, items, states, side, elems):
+    items, states = items.copy(), states.copy()
+    coef = np.zeros(elems, np.int16)
+    rec = np.zeros(elems, np.int16)
+    L = lib()
+    L.xo_analyze_intra_batch.restype = None
+    L.xo_analyze_intra_batch.argtypes = [VP, VP, VP, VP, C.c_int64, VP, VP, VP, VP]
+    L.xo_analyze_intra_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(rates)), _p(items), len(items), _p(states),
+                             _p(np.ascontiguousarray(side, np.int16)), _p(coef), _p(rec))
+    return items, states, coef, rec

@@ -173,6 +173,8 @@ static struct {
     vec_t    cu, cu_sbac; /* cu_sbac: coder states named by RH_CU_REC::state_in / state_out */
     int (*org_lf)(XEVE_CTX *, XEVE_CORE *);
     void (*org_df_unit)(XEVE_CTX *, XEVE_PIC *, int, int, int, int, int, XEVE_CORE *, int);
+    double (*org_intra)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, XEVE_MODE *, s16 (*)[MAX_CU_DIM], pel **, int *);
+    vec_t    intra;    /* RH_INTRA_REC; coder states go to cu_sbac, neighbour samples to samp */
     vec_t    df, df_cu, df_maps; /* deblocking: one record per picture, CU rectangles, frame maps (bytes) */
     int      df_collect;
     vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
@@ -407,6 +409,91 @@ static double hook_cu(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw
 }
 
 /* ------------------------------------------------------------------------------------------
+ * intra analysis trace: ctx->fn_pintra_analyze_cu (src_base/xeve_pintra.c:544-698)
+ * ---------------------------------------------------------------------------------------- */
+#define RH_T_INTRA 64
+typedef struct {                /* == xb200_intra_item */
+    int32_t  poc, cur_pic;
+    int16_t  x, y;
+    uint8_t  log2_cuw, log2_cuh, slice_type, ctx_skip, ctx_pred_mode, all_preds;
+    uint8_t  qp[3];
+    uint8_t  mpm[5];
+    uint8_t  pad0_[2];
+    uint32_t inter_satd;
+    int32_t  rate_idx, state_in, state_out;
+    uint16_t cm_ipm_in[2], cm_ipm_out[2];
+    double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
+    int64_t  nb_off, out_off;
+    double   cost;
+    int32_t  dist_cu;
+    int8_t   ipm[2];
+    uint8_t  pad1_[2];
+    int32_t  nnz[3];
+    uint64_t coef_hash, rec_hash;
+} RH_INTRA_REC;
+RH_API int rh_sizeof_intra(void) { return sizeof(RH_INTRA_REC); }
+
+/* neighbour samples as xeve_get_nbr left them in core->nb: per plane left[-1 .. 2n-1] then up[-1 .. 2n-1] */
+static int64_t push_nbr(XEVE_CORE *core, int cuw, int cuh)
+{
+    int64_t off = (int64_t)T.samp.n;
+    for(int c = 0; c < 3; c++) {
+        int w = c ? cuw >> 1 : cuw, h = c ? cuh >> 1 : cuh, n = w + h + 1;
+        memcpy(vec_push(&T.samp, n), core->nb[c][0] + 2 - 1, n * sizeof(s16));
+        memcpy(vec_push(&T.samp, n), core->nb[c][1] + h - 1, n * sizeof(s16));
+    }
+    return off;
+}
+
+static double hook_intra(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw, int log2_cuh, XEVE_MODE *mi,
+                         s16 coef[N_C][MAX_CU_DIM], pel *rec[N_C], int s_rec[N_C])
+{
+    if(!tracing(RH_T_INTRA)) return T.org_intra(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+    XEVE_PINTRA *pi = &ctx->pintra[core->thread_cnt];
+    RH_INTRA_REC r;
+    memset(&r, 0, sizeof(r));
+    r.poc = ctx->poc.poc_val;
+    r.cur_pic = find_or_add_pic(pi->pic_o, r.poc, 0);
+    r.x = x; r.y = y; r.log2_cuw = log2_cuw; r.log2_cuh = log2_cuh; r.slice_type = pi->slice_type;
+    r.ctx_skip = core->ctx_flags[CNID_SKIP_FLAG]; r.ctx_pred_mode = core->ctx_flags[CNID_PRED_MODE];
+    r.all_preds = xeve_check_all_preds(core->tree_cons);
+    r.qp[0] = core->qp_y; r.qp[1] = core->qp_u; r.qp[2] = core->qp_v;
+    r.inter_satd = core->inter_satd;
+    r.rate_idx = rate_index(core, log2_cuw, log2_cuh);
+    XEVE_SBAC *sin = &core->s_curr_best[log2_cuw - 2][log2_cuh - 2];
+    r.state_in = (int)T.cu_sbac.n;
+    sbac_pack(sin, (RH_SBAC *)vec_push(&T.cu_sbac, 1));
+    memcpy(r.cm_ipm_in, sin->ctx.intra_dir, 4);
+    for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
+    r.sqrt_lambda0 = core->sqrt_lambda[0];
+    r.dist_chroma_weight[0] = core->dist_chroma_weight[0]; r.dist_chroma_weight[1] = core->dist_chroma_weight[1];
+    r.out_off = -1;
+
+    double cost = T.org_intra(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+
+    r.nb_off = push_nbr(core, 1 << log2_cuw, 1 << log2_cuh);
+    memcpy(r.mpm, core->mpm_b_list, 5);
+    r.cost = cost;
+    if(cost < MAX_COST) {
+        size_t ny = (size_t)1 << (log2_cuw + log2_cuh), nc = ny >> 2;
+        r.dist_cu = core->dist_cu;
+        r.ipm[0] = core->ipm[0]; r.ipm[1] = core->ipm[1];
+        for(int i = 0; i < 3; i++) r.nnz[i] = core->nnz[i];
+        uint64_t hsh = FNV_INIT;
+        hsh = fnv1a(hsh, coef[Y_C], ny * 2); hsh = fnv1a(hsh, coef[U_C], nc * 2); hsh = fnv1a(hsh, coef[V_C], nc * 2);
+        r.coef_hash = hsh;
+        hsh = FNV_INIT;
+        hsh = fnv1a(hsh, rec[Y_C], ny * 2); hsh = fnv1a(hsh, rec[U_C], nc * 2); hsh = fnv1a(hsh, rec[V_C], nc * 2);
+        r.rec_hash = hsh;
+        memcpy(r.cm_ipm_out, core->s_temp_best.ctx.intra_dir, 4);
+    }
+    r.state_out = (int)T.cu_sbac.n;
+    sbac_pack(&core->s_temp_best, (RH_SBAC *)vec_push(&T.cu_sbac, 1));
+    *(RH_INTRA_REC *)vec_push(&T.intra, 1) = r;
+    return cost;
+}
+
+/* ------------------------------------------------------------------------------------------
  * deblocking trace: ctx->fn_loop_filter with the picture before / after, the frame
  * maps it reads and the CU rectangles xeve_deblock_tree enumerates (ctx->fn_deblock_unit)
  * ---------------------------------------------------------------------------------------- */
@@ -559,6 +646,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
     vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
+    vec_reset(&T.intra, sizeof(RH_INTRA_REC));
     vec_reset(&T.df, sizeof(RH_DF_REC)); vec_reset(&T.df_cu, sizeof(RH_DF_CU)); vec_reset(&T.df_maps, 1); T.df_collect = 0;
     T.have_rates = 0;
     g_cu_secs = 0; g_cu_calls = 0;
@@ -569,6 +657,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
         ctx->fn_tq = hook_tq;
         T.org_cu = ctx->fn_pinter_analyze_cu;
         ctx->fn_pinter_analyze_cu = hook_cu;
+        T.org_intra = ctx->fn_pintra_analyze_cu; ctx->fn_pintra_analyze_cu = hook_intra;
         T.org_lf = ctx->fn_loop_filter; T.org_df_unit = ctx->fn_deblock_unit;
         ctx->fn_loop_filter = hook_loop_filter; ctx->fn_deblock_unit = hook_df_unit;
     }
@@ -638,7 +727,7 @@ RH_API int64_t rh_trace_get(int what, void **ptr)
 {
     vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
              : what == 4 ? &T.pics : what == 5 ? &T.samp : what == 6 ? &T.sbac : what == 7 ? &T.cu : what == 8 ? &T.cu_sbac
-             : what == 9 ? &T.df : what == 10 ? &T.df_cu : &T.df_maps;
+             : what == 9 ? &T.df : what == 10 ? &T.df_cu : what == 11 ? &T.df_maps : &T.intra;
     *ptr = v->p;
     return (int64_t)v->n;
 }

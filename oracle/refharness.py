@@ -171,6 +171,15 @@ def _p(a):
 
 TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
 TRACE_DF = 32
+TRACE_INTRA = 64
+INTRA_REC = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("all_preds", "u1"), ("qp", "u1", (3,)), ("mpm", "u1", (5,)), ("pad0_", "u1", (2,)),
+    ("inter_satd", "<u4"), ("rate_idx", "<i4"), ("state_in", "<i4"), ("state_out", "<i4"), ("cm_ipm_in", "<u2", (2,)),
+    ("cm_ipm_out", "<u2", (2,)), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
+    ("nb_off", "<i8"), ("out_off", "<i8"), ("cost", "<f8"), ("dist_cu", "<i4"), ("ipm", "i1", (2,)), ("pad1_", "u1", (2,)),
+    ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"),
+], align=True)
 
 # deblocking: layouts == xb200_df_cu / xb200_df_pic of include/xeve_b200.h
 DF_CU = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pad_", "u1", (2,))], align=True)
@@ -270,6 +279,8 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
     tr = Trace(me, mc, tq, rates, pics, samp, cst, sec, bs[: n.value].copy() if want_bitstream else None)
     tr.sbac, tr.cu, tr.cu_sbac = sbac, cu, cu_sbac
     assert L.rh_sizeof_df(0) == DF_REC.itemsize, (L.rh_sizeof_df(0), DF_REC.itemsize)
+    assert L.rh_sizeof_intra() == INTRA_REC.itemsize, (L.rh_sizeof_intra(), INTRA_REC.itemsize)
+    tr.intra = grab(12, INTRA_REC)
     tr.df, tr.df_cu, tr.df_maps = grab(9, DF_REC), grab(10, DF_CU), grab(11, np.dtype("u1"))
     return tr
 

@@ -805,11 +805,13 @@ void xo_bi_org_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_it
  * is the number of renormalisation shifts: every carry_propagate moves exactly one byte into
  * {bitcounter, stacked_zero, stacked_ff, pending}, so 8*bytes + 11 - code_bits == shifts.
  * ------------------------------------------------------------------------------------------- */
-typedef struct { xb200_sbac s; uint32_t bits; } cabac_t;
+typedef struct { xb200_sbac s; uint32_t bits; uint16_t ipm[2]; /* ctx.intra_dir: model indices XO_CM_IPM, +1 */ } cabac_t;
+#define XO_CM_IPM XB200_CM_COUNT
 
 static void cb_bin(cabac_t *c, int m, int bin) /* xeve_sbac_encode_bin */
 {
-    uint16_t model = c->s.m[m], mps = model & 1, state = model >> 1;
+    uint16_t *pm = m < XB200_CM_COUNT ? &c->s.m[m] : &c->ipm[m - XB200_CM_COUNT];
+    uint16_t model = *pm, mps = model & 1, state = model >> 1;
     uint32_t lps = (state * c->s.range) >> 9;
     if(lps < 437) lps = 437;
     c->s.range -= lps;
@@ -819,7 +821,7 @@ static void cb_bin(cabac_t *c, int m, int bin) /* xeve_sbac_encode_bin */
         if(state > 256) { mps = 1 - mps; state = 512 - state; }
     }
     else state = state - ((state + 16) >> 5);
-    c->s.m[m] = (uint16_t)((state << 1) + mps);
+    *pm = (uint16_t)((state << 1) + mps);
     while(c->s.range < 8192) { c->s.range <<= 1; c->bits++; }
 }
 static void cb_ep(cabac_t *c) { c->s.range &= ~1u; c->bits++; } /* sbac_encode_bin_ep: range >>= 1, <<= 1 drops the LSB */
@@ -1285,6 +1287,185 @@ void xo_analyze_cu_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_r
 {
     for(int64_t i = 0; i < n; i++) xo_analyze_cu(sq, pl, rates, &items[i], states, coef + items[i].out_off, rec + items[i].out_off);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * intra analysis: pintra_analyze_cu, make_ipred_list, pintra_residue_rdo
+ * (src_base/xeve_pintra.c:69-374, 544-698), the Baseline predictors (src_base/xeve_ipred.c:99-228) and the intra bit
+ * counters (src_base/xeve_mode.c:81-171, src_base/xeve_eco.c:793-905, 1104-1121).
+ * ------------------------------------------------------------------------------------------- */
+/* src_base/xeve_ipred.c:99-228; le / up point at sample 0 of the left column / upper row (index -1 = corner) */
+static void ipred_b(const int16_t *le, const int16_t *up, int16_t *dst, int ipm, int w, int h)
+{
+    int l2 = 0, dc = 0;
+    while((1 << l2) < w) l2++;
+    if(ipm == 0) {
+        for(int i = 0; i < h; i++) dc += le[i];
+        for(int j = 0; j < w; j++) dc += up[j];
+        dc = (dc + w) >> (l2 + 1);
+    }
+    for(int i = 0; i < h; i++)
+        for(int j = 0; j < w; j++) {
+            int v;
+            switch(ipm) {
+            case 0: v = dc; break;
+            case 1: v = le[i]; break;
+            case 2: v = up[j]; break;
+            case 3: v = i > j ? le[i - j - 1] : (i == j ? up[-1] : up[j - i - 1]); break;
+            default: v = (up[i + j + 1] + le[i + j + 1]) >> 1; break;
+            }
+            dst[i * w + j] = (int16_t)v;
+        }
+}
+
+/* xeve_eco_coef for an intra CU (pred_mode == MODE_INTRA branch of xeve_eco_cbf): cbf_cb, cbf_cr, cbf_luma for the planes
+ * named by run_stats, then the run-length coded planes */
+static void cb_coef_intra(cabac_t *c, const int nnz[3], int log2_cuw, const int16_t *coef, int run_stats)
+{
+    const int ny = 1 << (2 * log2_cuw), off[3] = {0, ny, ny + (ny >> 2)};
+    if(run_stats & 2) cb_bin(c, XB200_CM_CBF_CB, nnz[1] != 0);
+    if(run_stats & 4) cb_bin(c, XB200_CM_CBF_CR, nnz[2] != 0);
+    if(run_stats & 1) cb_bin(c, XB200_CM_CBF_LUMA, nnz[0] != 0);
+    for(int k = 0; k < 3; k++)
+        if(nnz[k] && ((run_stats >> k) & 1)) cb_run_length(c, coef + off[k], k ? log2_cuw - 1 : log2_cuw, nnz[k], k);
+}
+
+void xo_analyze_intra(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_intra_item *it, xb200_sbac *states,
+                      const int16_t *side, int16_t *coef_out, int16_t *rec_out)
+{
+    const int l2 = it->log2_cuw, w = 1 << l2, ny = w * w, nc = ny >> 2, wc = w >> 1, bd = sq->bit_depth;
+    const xo_planes *o = &pl[it->cur_pic];
+    const int16_t *org[3] = {o->y + it->y * o->s_l + it->x, o->u + (it->y >> 1) * o->s_c + (it->x >> 1),
+                             o->v + (it->y >> 1) * o->s_c + (it->x >> 1)};
+    /* neighbour samples: per plane left[-1..2n-1] | up[-1..2n-1] */
+    const int16_t *nb = side + it->nb_off, *le[3], *up[3];
+    for(int c = 0; c < 3; c++) {
+        const int n = c ? wc : w;
+        le[c] = nb + 1; up[c] = nb + (2 * n + 1) + 1;
+        nb += 2 * (2 * n + 1);
+    }
+    cabac_t base, run;
+    base.s = states[it->state_in]; base.ipm[0] = it->cm_ipm_in[0]; base.ipm[1] = it->cm_ipm_in[1]; base.bits = 0;
+
+    /* ---- make_ipred_list: every mode predicted once (pred_cache), ranked by SATD + sqrt(lambda) * mode bits ---- */
+    int16_t *pred_cache = malloc(sizeof(int16_t) * 5 * ny);
+    int      list[5];
+    double   cand_cost[5];
+    uint32_t cand_satd[5];
+    for(int i = 0; i < 5; i++) { list[i] = 0; cand_cost[i] = 1.7e+308; cand_satd[i] = UINT32_MAX; }
+    for(int i = 0; i < 5; i++) {
+        ipred_b(le[0], up[0], pred_cache + i * ny, i, w, w);
+        const uint32_t satd = (uint32_t)xo_satd(w, w, org[0], o->s_l, pred_cache + i * ny, w, bd);
+        run = base;
+        cb_unary(&run, it->mpm[i], XO_CM_IPM);
+        double cost = (double)satd;
+        cost += (double)run.bits * it->sqrt_lambda0;
+        int shift = 0;
+        while(shift < 5 && cost < cand_cost[4 - shift]) shift++;
+        if(shift) {
+            for(int j = 1; j < shift; j++) {
+                list[5 - j] = list[4 - j]; cand_cost[5 - j] = cand_cost[4 - j]; cand_satd[5 - j] = cand_satd[4 - j];
+            }
+            list[5 - shift] = i; cand_cost[5 - shift] = cost; cand_satd[5 - shift] = satd;
+        }
+    }
+    int pred_cnt = 5;
+    for(int i = 4; i >= 1; i--) {
+        if(cand_satd[i] > it->inter_satd * (1.2)) pred_cnt--;
+        else break;
+    }
+
+    /* ---- luma RDO over the surviving modes (pintra_residue_rdo, mode 0) ------------------------------------------- */
+    xb200_tq_item tq;
+    memset(&tq, 0, sizeof(tq));
+    tq.log2_cuw = tq.log2_cuh = (uint8_t)l2; tq.slice_type = it->slice_type; tq.is_intra = 1;
+    tq.qp[0] = it->qp[0]; tq.qp[1] = it->qp[1]; tq.qp[2] = it->qp[2]; tq.rate_idx = it->rate_idx;
+    tq.lambda[0] = it->lambda[0]; tq.lambda[1] = it->lambda[1]; tq.lambda[2] = it->lambda[2];
+    int16_t *tmp = calloc((size_t)ny + 2 * nc, sizeof(int16_t)), *rec = calloc((size_t)ny + 2 * nc, sizeof(int16_t));
+    int16_t *pred_c = malloc(sizeof(int16_t) * 2 * nc);
+    double   cost = 1.7e+308;
+    int      best_ipd = -1, nnz[3] = {0, 0, 0}, nnz_best[3] = {0, 0, 0};
+    int32_t  best_dist_y = 0, best_dist_c = 0;
+    run = base;
+    for(int j = 0; j < pred_cnt; j++) {
+        const int      ipm = list[j];
+        const int16_t *pred = pred_cache + ipm * ny;
+        xo_diff(w, w, org[0], o->s_l, pred, w, tmp, w);
+        tq.run_stats = 1;
+        xo_tq(sq, &tq, rates, tmp, nnz);
+        int16_t *cy = malloc(sizeof(int16_t) * ny);
+        memcpy(cy, tmp, sizeof(int16_t) * ny);
+        run = base; run.bits = 0;
+        if(it->slice_type != 2 && it->all_preds) {
+            cb_bin(&run, XB200_CM_SKIP_FLAG + it->ctx_skip, 0);
+            cb_bin(&run, XB200_CM_PRED_MODE + it->ctx_pred_mode, 1);
+        }
+        cb_unary(&run, it->mpm[ipm], XO_CM_IPM);
+        cb_coef_intra(&run, nnz, l2, tmp, 1);
+        xo_itdq(sq, &tq, tmp, nnz);
+        xo_recon(tmp, pred, nnz[0], ny, rec, bd);
+        double cost_t = 0;
+        cost_t += (double)xo_ssd(w, w, rec, w, org[0], o->s_l, bd);
+        const int32_t dist_t = (int32_t)cost_t;
+        cost_t += (double)run.bits * it->lambda[0];
+        if(cost_t < cost) {
+            cost = cost_t; best_dist_y = dist_t; best_ipd = ipm;
+            memcpy(coef_out, cy, sizeof(int16_t) * ny);
+            memcpy(rec_out, rec, sizeof(int16_t) * ny);
+            nnz_best[0] = nnz[0];
+        }
+        free(cy);
+    }
+    if(pred_cnt == 0) { /* cannot happen (the loop above keeps at least one mode) but mirrors :600-602 */
+        it->cost = 1.7e+308;
+        goto done;
+    }
+
+    /* ---- chroma with the winning luma mode (pintra_residue_rdo, mode 1); its bit count does not reach the result ---- */
+    for(int c = 1; c < 3; c++) {
+        ipred_b(le[c], up[c], pred_c + (c - 1) * nc, best_ipd, wc, wc);
+        xo_diff(wc, wc, org[c], o->s_c, pred_c + (c - 1) * nc, wc, tmp + ny + (c - 1) * nc, wc);
+    }
+    tq.run_stats = 6;
+    xo_tq(sq, &tq, rates, tmp, nnz);
+    memcpy(coef_out + ny, tmp + ny, sizeof(int16_t) * 2 * nc);
+    nnz[0] = 0;
+    xo_itdq(sq, &tq, tmp, nnz);
+    {
+        double cc = 0;
+        for(int c = 1; c < 3; c++) {
+            xo_recon(tmp + ny + (c - 1) * nc, pred_c + (c - 1) * nc, nnz[c], nc, rec_out + ny + (c - 1) * nc, bd);
+            cc += it->dist_chroma_weight[c - 1] * (double)xo_ssd(wc, wc, rec_out + ny + (c - 1) * nc, wc, org[c], o->s_c, bd);
+        }
+        best_dist_c = (int32_t)cc;
+    }
+    nnz_best[1] = nnz[1]; nnz_best[2] = nnz[2];
+
+    /* ---- final bit count of the whole CU from the input state (xeve_rdo_bit_cnt_cu_intra) -------------------------- */
+    run = base; run.bits = 0;
+    if(it->slice_type != 2) {
+        cb_bin(&run, XB200_CM_SKIP_FLAG + it->ctx_skip, 0);
+        cb_bin(&run, XB200_CM_PRED_MODE + it->ctx_pred_mode, 1);
+    }
+    cb_unary(&run, it->mpm[best_ipd], XO_CM_IPM);
+    cb_coef_intra(&run, nnz_best, l2, coef_out, 7);
+    cost = (double)run.bits * it->lambda[0];
+    cost += best_dist_y;
+    cost += best_dist_c;
+    it->cost = cost;
+    it->dist_cu = best_dist_y + best_dist_c;
+    it->ipm[0] = it->ipm[1] = (int8_t)best_ipd;
+    it->nnz[0] = nnz_best[0]; it->nnz[1] = nnz_best[1]; it->nnz[2] = nnz_best[2];
+    it->cm_ipm_out[0] = run.ipm[0]; it->cm_ipm_out[1] = run.ipm[1];
+    states[it->state_out] = run.s;
+done:
+    free(pred_cache); free(tmp); free(rec); free(pred_c);
+}
+void xo_analyze_intra_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_intra_item *items, int64_t n,
+                            xb200_sbac *states, const int16_t *side, int16_t *coef, int16_t *rec)
+{
+    for(int64_t i = 0; i < n; i++) xo_analyze_intra(sq, pl, rates, &items[i], states, side, coef + items[i].out_off, rec + items[i].out_off);
+}
+
 
 /* FNV-1a over per-item output slots (the hash the harness records for in-situ results) */
 void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out)

@@ -528,3 +528,36 @@ def test_deblock_matches_oracle_synthetic(w, h, seed):
     with pytest.raises(api.Xb200Error):
         hp.deblock(hb, bad, d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
     hp.close()
+
+
+# ---- intra analysis -----------------------------------------------------------------------------------
+def _gpu_intra(td):
+    hp = api.Hotpath(td.seq)
+    handles = []
+    for i, p in enumerate(td.pics):
+        h = hp.pic_create(padded=int(p["kind"]) == 1)
+        hp.pic_upload_s16(h, *(np.ascontiguousarray(a) for a in td.planes[i]))
+        handles.append(h)
+    items, sz, elems = tracedata.intra_slots(td.intra)
+    dev = items.copy()
+    dev["cur_pic"] = np.array(handles, np.int32)[items["cur_pic"]]
+    got, st, coef, rec = hp.analyze_intra(dev, td.cu_rates, td.cu_sbac, td.side, elems)
+    tracedata.check_intra_results(got, td.intra, coef, rec, sz, st, td.cu_sbac)      # the reference's in-situ results
+    exp, est, ecoef, erec = xo.analyze_intra_batch(td.seq, td.oracle_planes(), td.cu_rates, items, td.cu_sbac, td.side, elems)
+    assert np.array_equal(coef, ecoef) and np.array_equal(rec, erec) and st.tobytes() == est.tobytes()  # and the oracle, byte for byte
+    bad = dev[:4].copy()
+    bad["log2_cuw"][0] = 7
+    with pytest.raises(api.Xb200Error):
+        hp.analyze_intra(bad, td.cu_rates, td.cu_sbac, td.side, elems)
+    hp.close()
+    return got
+
+
+def test_intra_matches_reference_in_situ():
+    """xb200_analyze_intra == pintra_analyze_cu: golden fixture always, live traces (another preset / QP) with oracle/_ref"""
+    _gpu_intra(tracedata.golden_intra())
+    if rh.available():
+        for kw in (dict(pic_hi=3), dict(pic_hi=1, preset="medium", extra="qp=24")):
+            td = tracedata.live_intra(**kw)
+            got = _gpu_intra(td)
+            assert len(got) > 500

@@ -214,3 +214,27 @@ def test_oracle_deblock_matches_reference_live_and_synthetic():
             got = xo.deblock(d["pre"], d["cus"][order], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
             assert all(np.array_equal(g, e) for g, e in zip(got, exp))
             assert not np.array_equal(exp[1], d["pre"][1])
+
+
+# ---- intra analysis -----------------------------------------------------------------------------------
+def _oracle_intra(td):
+    items, sz, elems = tracedata.intra_slots(td.intra)
+    got, st, coef, rec = xo.analyze_intra_batch(td.seq, td.oracle_planes(), td.cu_rates, items, td.cu_sbac, td.side, elems)
+    tracedata.check_intra_results(got, td.intra, coef, rec, sz, st, td.cu_sbac)
+    return got
+
+
+def test_oracle_intra_matches_golden():
+    """xo_analyze_intra == pintra_analyze_cu in situ on the committed fixture: cost (IEEE double), modes, nnz, coefficient /
+    reconstruction hashes, output coder state incl. the intra_dir models; CU sizes 4x4 .. 64x64, I and B slices"""
+    td = tracedata.golden_intra()
+    got = _oracle_intra(td)
+    assert set(np.unique(td.intra["log2_cuw"])) == {2, 3, 4, 5, 6} and len(np.unique(got["ipm"][:, 0])) == 5
+
+
+@needs_ref
+def test_oracle_intra_matches_reference_live():
+    for kw in (dict(pic_hi=3), dict(pic_hi=1, preset="medium", extra="qp=24")):
+        td = tracedata.live_intra(**kw)
+        assert len(td.intra) > 500
+        _oracle_intra(td)

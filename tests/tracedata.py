@@ -110,6 +110,45 @@ def golden_trace() -> TraceData:
     return td
 
 
+INTRA_GOLDEN = os.path.join(ROOT, "tests", "golden", "intra_golden.npz")
+
+
+def intra_slots(items):
+    """(items with out_off assigned, slot sizes, total elements) for the coef / rec outputs of an intra CU list"""
+    items = items.copy()
+    sz = (3 << (2 * items["log2_cuw"].astype(np.int64))) >> 1
+    items["out_off"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+    return items, sz, int(sz.sum())
+
+
+def live_intra(name="cif", frames=20, pic_lo=0, pic_hi=2, preset="fast", extra="", **override) -> TraceData:
+    """ctx->fn_pintra_analyze_cu calls of the traced pictures with the reference's in-situ results (td.intra, td.cu_sbac,
+    td.cu_rates, td.side = neighbour samples addressed by nb_off)"""
+    override = override or QCIF
+    td = live_trace(name, frames, pic_lo, pic_hi, preset, rh.TRACE_INTRA, extra, **override)
+    td.intra = td.live.intra.copy()
+    return td
+
+
+def golden_intra() -> TraceData:
+    z = np.load(INTRA_GOLDEN)
+    pics = z["pics"]
+    planes = [(z[f"p{i}_y"], z[f"p{i}_u"], z[f"p{i}_v"]) for i in range(len(pics))]
+    e = np.empty(0)
+    td = TraceData(z["seq"], pics, planes, e, e, e, z["rates"], z["side"], e, "golden")
+    td.intra, td.cu_sbac, td.cu_rates = z["intra"], z["sbac"], z["rates"]
+    return td
+
+
+def check_intra_results(got, ref, coef, rec, sz, st_got, st_ref):
+    """analyze_intra outputs against the reference's in-situ results"""
+    for f in ("cost", "dist_cu", "ipm", "nnz", "cm_ipm_out"):
+        assert np.array_equal(got[f], ref[f]), f
+    hc, hr = xo.hash_slots(coef, got["out_off"], sz), xo.hash_slots(rec, got["out_off"], sz)
+    assert np.array_equal(hc, ref["coef_hash"]) and np.array_equal(hr, ref["rec_hash"])
+    assert st_got[ref["state_out"]].tobytes() == st_ref[ref["state_out"]].tobytes()
+
+
 DF_GOLDEN = os.path.join(ROOT, "tests", "golden", "df_golden.npz")
 
 

@@ -79,6 +79,15 @@ MVP_ITEM = np.dtype([
 ], align=True)
 MVP_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("poc", "<i4"), ("ref_poc", "<i4", (2,)), ("col_list_poc0", "<i4")], align=True)
 
+INTRA_ITEM = np.dtype([
+    ("poc", "<i4"), ("cur_pic", "<i4"), ("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"),
+    ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("all_preds", "u1"), ("qp", "u1", (3,)), ("mpm", "u1", (5,)), ("pad0_", "u1", (2,)),
+    ("inter_satd", "<u4"), ("rate_idx", "<i4"), ("state_in", "<i4"), ("state_out", "<i4"), ("cm_ipm_in", "<u2", (2,)),
+    ("cm_ipm_out", "<u2", (2,)), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
+    ("nb_off", "<i8"), ("out_off", "<i8"), ("cost", "<f8"), ("dist_cu", "<i4"), ("ipm", "i1", (2,)), ("pad1_", "u1", (2,)),
+    ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"),
+], align=True)
+
 DF_CU = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pad_", "u1", (2,))], align=True)
 DF_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("qp_u_offset", "<i4"), ("qp_v_offset", "<i4"),
                    ("chroma_qp", "<i4", (2, 70))], align=True)
@@ -147,6 +156,7 @@ def load():
         L.xb200_rdo_bits.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]
         L.xb200_rdoq_rates.argtypes = [VP, VP, C.c_int64, VP]
         L.xb200_analyze_cu.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
+        L.xb200_analyze_intra.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
         L.xb200_deblock.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -155,7 +165,7 @@ def load():
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
-           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock"]
+           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra"]
 
 
 def _p(a):
@@ -295,6 +305,18 @@ class Hotpath:
                                   _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_mv, np.int16)),
                                   _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16))), "xb200_mvp")
         return items
+
+    def analyze_intra(self, items, rates, states, side, elems, want_rec=True):
+        """pintra_analyze_cu over a CU list -> (items with results, states with the state_out slots written, coef, rec)"""
+        items = np.ascontiguousarray(items, INTRA_ITEM).copy()
+        rates = np.ascontiguousarray(rates, RATES)
+        states = np.ascontiguousarray(states, SBAC).copy()
+        side = np.ascontiguousarray(side, np.int16)
+        coef = np.zeros(elems, np.int16)
+        rec = np.zeros(elems, np.int16) if want_rec else None
+        self._ck(self.L.xb200_analyze_intra(self.h, _p(items), len(items), _p(rates), len(rates), _p(states), len(states), _p(side),
+                                            len(side), _p(coef), _p(rec), elems), "xb200_analyze_intra")
+        return items, states, coef, rec
 
     def deblock(self, handle, cus, pp, map_scu, map_refi, map_mv, expand=True):
         """xeve_loop_filter (+ xeve_picbuf_expand) on the device picture `handle`, in place"""

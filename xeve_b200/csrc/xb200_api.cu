@@ -204,6 +204,8 @@ int launch_analyze(xb200_ctx *c, xb200_cu_item *d_items, const int32_t *order, i
 
 } // namespace
 
+int xb200_sync_pics(xb200_ctx *c) { return sync_pics(c); }
+
 extern "C" {
 
 const char *xb200_version(void) { return "xeve_b200 0.1 (sm_100a)"; }

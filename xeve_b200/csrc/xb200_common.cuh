@@ -26,13 +26,18 @@ struct SeqDev {
     int32_t tc_dct; // 32/64-point forward DCT on tcgen05 (bit-identical; off by default)
 };
 
-#ifndef XB200_NO_CONSTANTS // the tables are defined once, in the translation unit that uploads them (xb200_api.cu)
-__constant__ int8_t  c_tm64[64 * 64];           // DCT-II matrix, N-point rows at stride 64/N
-__constant__ int16_t c_mc_l[4][8];              // luma taps by quarter-pel phase
-__constant__ int16_t c_mc_c[8][4];              // chroma taps by eighth-pel phase
-__constant__ int32_t c_quant_scale[6];
-__constant__ int32_t c_dequant_scale[6];
-__constant__ int64_t c_err_scale[6][7];         // [qp % 6][log2 size] (host-computed doubles -> s64)
+// The tables live in the translation unit that uploads them: xb200_api.cu defines them with external linkage, xb200_intra.cu
+// keeps its own (static) copies, xb200_frame.cu needs none.
+#ifndef XB200_CONST_LINKAGE
+#define XB200_CONST_LINKAGE
+#endif
+#ifndef XB200_NO_CONSTANTS
+XB200_CONST_LINKAGE __constant__ int8_t  c_tm64[64 * 64];           // DCT-II matrix, N-point rows at stride 64/N
+XB200_CONST_LINKAGE __constant__ int16_t c_mc_l[4][8];              // luma taps by quarter-pel phase
+XB200_CONST_LINKAGE __constant__ int16_t c_mc_c[8][4];              // chroma taps by eighth-pel phase
+XB200_CONST_LINKAGE __constant__ int32_t c_quant_scale[6];
+XB200_CONST_LINKAGE __constant__ int32_t c_dequant_scale[6];
+XB200_CONST_LINKAGE __constant__ int64_t c_err_scale[6][7];         // [qp % 6][log2 size] (host-computed doubles -> s64)
 #endif
 
 #define XB_DEV __device__ __forceinline__

@@ -34,6 +34,8 @@ struct xb200_ctx {
     int             *d_bins = nullptr; // 8 counters + 8 max-range
     DevBuf           b_items, b_side, b_aux0, b_aux1, b_aux2, b_order, b_stage;
     DevBuf           b_df; // deblocking: per-SCU edge flags
+    DevBuf           b_in_items, b_in_rates, b_in_st0, b_in_st1, b_in_side, b_in_coef, b_in_rec, b_in_order; // intra analysis
+    bool             intra_ready = false;
     DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
     DevBuf           b_cu_items, b_cu_rates, b_cu_state, b_cu_me, b_cu_res, b_cu_mc, b_cu_cur, b_cu_off, b_cu_side, b_cu_order,
                      b_cu_coef, b_cu_rec, b_cu_nzr, b_cu_nzl, b_cu_meta; // CU pipeline
@@ -57,6 +59,7 @@ struct xb200_ctx {
 int  xb200_ensure(DevBuf &b, size_t bytes);
 int  xb200_finish(xb200_ctx *c);          // record ev1, synchronise, store the kernel time of [ev0, ev1]
 int  xb200_pad_planes(xb200_ctx *c, Pic &p);
+int  xb200_sync_pics(xb200_ctx *c);       // refresh the device-side picture table (c->d_pics)
 
 inline int  align_up(int v, int a) { return (v + a - 1) / a * a; }
 inline bool pic_ok(const xb200_ctx *c, int h) { return h >= 0 && h < (int)c->pics.size() && c->pics[h].used; }

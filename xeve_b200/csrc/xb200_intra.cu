@@ -1,0 +1,97 @@
+// xb200_intra.cu -- intra analysis operator (third translation unit).  Keeps its own copies of the
+// quantiser tables (static __constant__) so it does not have to be compiled together with the inter operators.
+#define XB200_CONST_LINKAGE static
+#include "xb200_ctx.h"
+#include "xb200_intra.cuh"
+#include <math.h>
+#include <vector>
+
+namespace {
+
+int intra_init(xb200_ctx *c)
+{
+    if(c->intra_ready) return XB200_OK;
+    const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
+    int64_t       es[6][7];
+    for(int q = 0; q < 6; q++)
+        for(int l2 = 0; l2 < 7; l2++) es[q][l2] = xb200_err_scale(q, l2, c->seq.bit_depth);
+    CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
+    CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
+    CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+    CK(cudaFuncSetAttribute(k_intra<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<8>)));
+    CK(cudaFuncSetAttribute(k_intra<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<64>)));
+    c->intra_ready = true;
+    return XB200_OK;
+}
+
+} // namespace
+
+int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates, xb200_sbac *states,
+                        int64_t n_states, const int16_t *side, int64_t side_elems, int16_t *coef, int16_t *rec, int64_t elems)
+{
+    if(!c || n < 0 || n > (1 << 26) || n_rates < 0 || n_states < 0 || side_elems < 0 || elems < 0 ||
+       (n && (!items || !rates || !states || !side || !coef)))
+        return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    int cnt[2] = {0, 0}; // [CUs up to 8x8 | larger CUs]
+    for(int64_t i = 0; i < n; i++) {
+        const xb200_intra_item &it = items[i];
+        if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 2 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
+        const int64_t sz = ((int64_t)3 << (2 * it.log2_cuw)) >> 1;
+        if(!pic_ok(c, it.cur_pic) || it.x < 0 || it.y < 0 || it.x + (1 << it.log2_cuw) > c->seq.w || it.y + (1 << it.log2_cuh) > c->seq.h ||
+           it.slice_type > 2 || it.rate_idx < 0 || it.rate_idx >= n_rates || it.state_in < 0 || it.state_in >= n_states ||
+           it.state_out < 0 || it.state_out >= n_states || it.nb_off < 0 || it.nb_off + 8 * (1 << it.log2_cuw) + 6 > side_elems ||
+           it.out_off < 0 || it.out_off + sz > elems || it.ctx_skip > 1 || it.ctx_pred_mode > 2 || it.mpm[0] > 4 || it.mpm[1] > 4 ||
+           it.mpm[2] > 4 || it.mpm[3] > 4 || it.mpm[4] > 4)
+            return XB200_ERR_INVALID_ARGUMENT;
+        cnt[it.log2_cuw <= 3 ? 0 : 1]++;
+    }
+    std::vector<int32_t> order((size_t)n);
+    {
+        int pos[2] = {0, cnt[0]};
+        for(int64_t i = 0; i < n; i++) order[(size_t)pos[items[i].log2_cuw <= 3 ? 0 : 1]++] = (int32_t)i;
+    }
+    int r;
+    if((r = intra_init(c))) return r;
+    if((r = xb200_sync_pics(c))) return r;
+    xb200_intra_item *d_items;
+    xb200_rates      *d_rates;
+    xb200_sbac       *d_st0, *d_st1;
+    int16_t          *d_side;
+    int32_t          *d_order;
+    if((r = to_dev(c, c->b_in_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_in_rates, rates, (size_t)n_rates, XB200_MEM_HOST, &d_rates))) return r;
+    if((r = to_dev(c, c->b_in_st0, states, (size_t)n_states, XB200_MEM_HOST, &d_st0))) return r;
+    if((r = to_dev(c, c->b_in_st1, states, (size_t)n_states, XB200_MEM_HOST, &d_st1))) return r;
+    if((r = to_dev(c, c->b_in_side, side, (size_t)side_elems, XB200_MEM_HOST, &d_side))) return r;
+    if((r = to_dev(c, c->b_in_order, order.data(), (size_t)n, XB200_MEM_HOST, &d_order))) return r;
+    if((r = xb200_ensure(c->b_in_coef, (size_t)elems * 2 + 64))) return r;
+    if(rec && (r = xb200_ensure(c->b_in_rec, (size_t)elems * 2 + 64))) return r;
+    int16_t *d_coef = static_cast<int16_t *>(c->b_in_coef.p), *d_rec = rec ? static_cast<int16_t *>(c->b_in_rec.p) : nullptr;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(d_coef, 0, (size_t)elems * 2, c->stream));
+    if(cnt[0]) {
+        const int grid = cnt[0] < 148 * 16 ? cnt[0] : 148 * 16;
+        k_intra<3, 32><<<grid, 32, sizeof(IntraSmem<8>), c->stream>>>(c->d_pics, d_items, d_order, cnt[0], d_rates, d_st0, d_st1, d_side, d_coef,
+                                                                        d_rec, c->d_tm64, c->sq);
+        c->launches++;
+    }
+    if(cnt[1]) {
+        const int grid = cnt[1] < 148 * 2 ? cnt[1] : 148 * 2;
+        k_intra<6, 128><<<grid, 128, sizeof(IntraSmem<64>), c->stream>>>(c->d_pics, d_items, d_order + cnt[0], cnt[1], d_rates, d_st0, d_st1,
+                                                                          d_side, d_coef, d_rec, c->d_tm64, c->sq);
+        c->launches++;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, states, d_st1, (size_t)n_states, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, coef, d_coef, (size_t)elems, XB200_MEM_HOST))) return r;
+    if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, XB200_MEM_HOST))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}

@@ -8,66 +8,12 @@
 //   zig-zag order and hand lane 0 only the non-zero ones (ballot + shuffle), which removes the 4096-step serial scan.
 #pragma once
 #include "xb200_common.cuh"
+#include "xb200_cabac.cuh"
 
 __device__ uint16_t g_scan[16 + 64 + 256 + 1024 + 4096];   // zig-zag: scan position -> raster, log2 size 2..6
 __device__ int32_t  g_entropy_bits[1024];                  // xeve_init_bits_est, computed on the host with libm
 __device__ __forceinline__ int scan_base(int l2) { return l2 == 2 ? 0 : l2 == 3 ? 16 : l2 == 4 ? 80 : l2 == 5 ? 336 : 1360; }
 
-struct Cabac {
-    uint32_t  range, bits;
-    uint16_t *m;   // XB200_CM_COUNT models (shared memory)
-};
-__device__ __forceinline__ void cb_bin(Cabac &c, int idx, int bin)
-{
-    const uint32_t model = c.m[idx];
-    uint32_t       mps = model & 1, state = model >> 1;
-    uint32_t       lps = (state * c.range) >> 9;
-    lps = max(lps, 437u);
-    c.range -= lps;
-    if((uint32_t)(bin != 0) != mps) {
-        if(c.range >= lps) c.range = lps;
-        state += (512 - state + 16) >> 5;
-        if(state > 256) { mps ^= 1; state = 512 - state; }
-    }
-    else state -= (state + 16) >> 5;
-    c.m[idx] = (uint16_t)((state << 1) | mps);
-    const int sh = max(0, __clz(c.range) - 18);   // shifts until range >= 8192 (bit 13 set)
-    c.range <<= sh;
-    c.bits += sh;
-}
-__device__ __forceinline__ void cb_ep(Cabac &c, int nbins = 1)   // sbac_encode_bin_ep: range >>= 1, <<= 1 drops the LSB, one shift per bin
-{
-    if(nbins > 0) { c.range &= ~1u; c.bits += nbins; }
-}
-// the engine step on a model held in registers (state / mps unpacked)
-__device__ __forceinline__ void cb_step(uint32_t &range, uint32_t &bits, uint32_t &state, uint32_t &mps, uint32_t bin)
-{
-    uint32_t lps = (state * range) >> 9;
-    lps = max(lps, 437u);
-    range -= lps;
-    if(bin != mps) {
-        if(range >= lps) range = lps;
-        state += (512 - state + 16) >> 5;
-        if(state > 256) { mps ^= 1; state = 512 - state; }
-    }
-    else state -= (state + 16) >> 5;
-    const int sh = max(0, __clz(range) - 18);
-    range <<= sh;
-    bits += sh;
-}
-// sbac_write_unary_sym with two contexts: bin 0 on model idx, the remaining `sym` bins (sym - 1 ones and a zero) on model
-// idx + 1, which stays in registers for the whole run
-__device__ __forceinline__ void cb_unary(Cabac &c, uint32_t sym, int idx)
-{
-    cb_bin(c, idx, sym != 0);
-    if(sym == 0) return;
-    const uint32_t model = c.m[idx + 1];
-    uint32_t       mps = model & 1, state = model >> 1, range = c.range, bits = c.bits;
-    for(; sym > 1; sym--) cb_step(range, bits, state, mps, 1);
-    cb_step(range, bits, state, mps, 0);
-    c.m[idx + 1] = (uint16_t)((state << 1) | mps);
-    c.range = range; c.bits = bits;
-}
 __device__ __forceinline__ void cb_mvp_idx(Cabac &c, int v)
 {
     for(int i = 0; i < 3; i++) {

@@ -18,18 +18,19 @@
 
 #define TQ_THREADS 128
 
-struct TqSmem {
-    int8_t   tm[64 * 64];   // tm[k][n]
-    int8_t   tmT[64 * 64];  // tmT[n][k]
-    int16_t  blk[64 * 64];  // working block (coefficients / residual), stride = N
-    int32_t  T[64 * 64];    // stage buffer; RDOQ scratch aliases it
+template <int MAXN> struct TqSmemT {   // MAXN: largest transform size this instance works on
+    int8_t   tm[64 * 64];       // tm[k][n]
+    int8_t   tmT[64 * 64];      // tmT[n][k]
+    int16_t  blk[MAXN * MAXN];  // working block (coefficients / residual), stride = N
+    int32_t  T[MAXN * MAXN];    // stage buffer; RDOQ scratch aliases it
     int64_t  red64[TQ_THREADS];
     int32_t  red32[TQ_THREADS];
     int64_t  bcast64[4];
     int32_t  bcast32[8];
 };
+using TqSmem = TqSmemT<64>;
 
-XB_DEV void tq_load_tm(TqSmem &S, const int8_t *__restrict__ g_tm64, int tid, int nthr)
+template <class SM> XB_DEV void tq_load_tm(SM &S, const int8_t *__restrict__ g_tm64, int tid, int nthr)
 {
     for(int e = tid; e < 4096; e += nthr) {
         const int8_t v = g_tm64[e];
@@ -40,7 +41,7 @@ XB_DEV void tq_load_tm(TqSmem &S, const int8_t *__restrict__ g_tm64, int tid, in
 }
 
 // forward transform of S.blk (N x N, N = 1 << l2), in place
-XB_DEV void fwd_dct(TqSmem &S, int l2, int bd, int tid, int nthr)
+template <class SM> XB_DEV void fwd_dct(SM &S, int l2, int bd, int tid, int nthr)
 {
     const int N = 1 << l2, K = N == 64 ? 32 : N, ks = 6 - l2;
     const int shift = (l2 - 1 + bd - 8) + (l2 + 6);
@@ -67,7 +68,7 @@ XB_DEV void fwd_dct(TqSmem &S, int l2, int bd, int tid, int nthr)
 }
 
 // inverse transform of S.blk in place (input: dequantised coefficients)
-XB_DEV void inv_dct(TqSmem &S, int l2, int bd, int tid, int nthr)
+template <class SM> XB_DEV void inv_dct(SM &S, int l2, int bd, int tid, int nthr)
 {
     const int N = 1 << l2, ks = 6 - l2, shift = 7 + 12 - (bd - 8);
     // stage 0: T[y][u] = clip32(sum_v tm[v][y] * C[v][u])  (|sum| <= 64*32768*90 fits 32 bits)
@@ -90,7 +91,7 @@ XB_DEV void inv_dct(TqSmem &S, int l2, int bd, int tid, int nthr)
 }
 
 // ---- block reductions (all threads call) ----------------------------------------------------------
-XB_DEV int64_t block_sum_s64(TqSmem &S, int64_t v, int tid, int nthr)
+template <class SM> XB_DEV int64_t block_sum_s64(SM &S, int64_t v, int tid, int nthr)
 {
     S.red64[tid] = v;
     __syncthreads();
@@ -104,7 +105,7 @@ XB_DEV int64_t block_sum_s64(TqSmem &S, int64_t v, int tid, int nthr)
     __syncthreads();
     return r;
 }
-XB_DEV int block_sum_s32(TqSmem &S, int v, int tid, int nthr)
+template <class SM> XB_DEV int block_sum_s32(SM &S, int v, int tid, int nthr)
 {
 #pragma unroll
     for(int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -160,7 +161,7 @@ XB_DEV void rq_quant(int c, int q, int qbits, int64_t &ld, uint32_t &maxl)
 }
 
 // quantise S.blk (N x N transform coefficients) in place; returns nnz (uniform)
-XB_DEV int quant_block(TqSmem &S, int l2, int qp, double d_lambda, int is_intra, int ch, int slice_type,
+template <class SM> XB_DEV int quant_block(SM &S, int l2, int qp, double d_lambda, int is_intra, int ch, int slice_type,
                        const xb200_rates *__restrict__ rt, int bd, int use_rdoq, int tid, int nthr)
 {
     const int N = 1 << l2, n = N * N;
@@ -292,7 +293,7 @@ XB_DEV int quant_block(TqSmem &S, int l2, int qp, double d_lambda, int is_intra,
 }
 
 // dequantise S.blk in place (src_base/xeve_itdq.c:442-452, shift/offset from 454-497)
-XB_DEV void dequant_block(TqSmem &S, int l2, int qp, int bd, int tid, int nthr)
+template <class SM> XB_DEV void dequant_block(SM &S, int l2, int qp, int bd, int tid, int nthr)
 {
     const int     n = 1 << (2 * l2), shift = 20 - 14 - (15 - bd - l2);
     const int64_t scale = (int64_t)c_dequant_scale[qp % 6] << (qp / 6), off = shift ? (int64_t)1 << (shift - 1) : 0;
@@ -303,6 +304,7 @@ XB_DEV void dequant_block(TqSmem &S, int l2, int qp, int bd, int tid, int nthr)
     __syncthreads();
 }
 
+#ifndef XB200_DEVICE_FUNCS_ONLY
 // ---- batched kernels --------------------------------------------------------------------------------------
 // ctx->fn_tq: one CTA per item, planes processed in turn, in place in the global coefficient buffer
 __global__ void __launch_bounds__(TQ_THREADS) k_tq(xb200_tq_item *__restrict__ items, int n, const xb200_rates *__restrict__ rates,
@@ -372,3 +374,4 @@ __global__ void k_recon(const xb200_tq_item *__restrict__ items, int n, const in
         rec[o + e]      = (int16_t)clip3i(0, maxv, t);
     }
 }
+#endif // XB200_DEVICE_FUNCS_ONLY
