@@ -251,6 +251,36 @@ def run_b200(args, rank, world, dist):
                "d2h_bytes": int(cu_items.nbytes + fw.cu_states.nbytes + 4 * fw.cu_elems),
                "best_mode_hist": np.bincount(cu_out["best_idx"], minlength=5).tolist(),
                "note": "whole xeve_pinter_analyze_cu per CU on the device (skip/direct/L0/L1/BI + cbf RDO + CABAC bit counts)"}
+    # ---- intra analysis of every CU of the 32/16/8/4 quad-tree of the same picture (xb200_analyze_intra) --------
+    from xeve_b200.clips import to_internal10
+    from xeve_b200.worklist import synth_intra
+    in_items, in_states, in_rates, in_side, in_elems = synth_intra(W, H, [to_internal10(p, clip.depth) for p in fr[POC]], cur, hp.rdoq_rates,
+                                                                     seed=rank)
+    h_in, h_inst, h_inside = pin(in_items.view(np.uint8)), pin(in_states.view(np.uint8)), pin(in_side)
+    h_in_coef, h_in_rec = pin(np.zeros(in_elems, np.int16)), pin(np.zeros(in_elems, np.int16))
+    in_rates_p = in_rates.ctypes.data_as(C.c_void_p)
+
+    def step_intra():
+        r = L.xb200_analyze_intra(ctx, HP(h_in), len(in_items), in_rates_p, len(in_rates), HP(h_inst), len(in_states), HP(h_inside),
+                                  len(in_side), HP(h_in_coef), HP(h_in_rec), in_elems)
+        if r:
+            raise RuntimeError(f"analyze_intra failed: {r}")
+    step_intra()
+    in_out = np.frombuffer(h_in.numpy().tobytes(), api.INTRA_ITEM)
+    t_in_k, t0 = 0.0, time.perf_counter()
+    in_steps = max(2, args.steps // 4)
+    for _ in range(in_steps):
+        step_intra()
+        t_in_k += hp.last_kernel_ms
+    t_in = (time.perf_counter() - t0) / in_steps
+    intra = {"cus_per_frame": int(len(in_items)), "cu_sizes": {str(1 << k): int(v) for k, v in enumerate(np.bincount(in_items["log2_cuw"])) if v},
+             "kernel_ms_per_frame": round(t_in_k / in_steps, 3), "host_api_ms_per_frame": round(t_in * 1e3, 3),
+             "cus_per_s_kernel": round(len(in_items) / (t_in_k / in_steps * 1e-3), 1),
+             "h2d_bytes": int(in_items.nbytes + in_states.nbytes + in_rates.nbytes + in_side.nbytes),
+             "d2h_bytes": int(in_items.nbytes + in_states.nbytes + 4 * in_elems),
+             "mode_hist": np.bincount(in_out["ipm"][:, 0], minlength=5).tolist(),
+             "note": "whole pintra_analyze_cu per CU on the device (5 predictors, SATD ranking, luma + chroma RDO with RDOQ and CABAC "
+                     "bit counts); frame-parallel mode: reference samples from the original picture"}
     # ---- in-loop deblocking + border expansion of one reconstructed picture (xb200_deblock) ------------
     from xeve_b200.worklist import synth_deblock
     df = synth_deblock(W, H, seed=rank)
@@ -324,6 +354,7 @@ def run_b200(args, rank, world, dist):
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: round(v, 3) for k, v in per_stage.items()},
         "analyze_cu": analyze,
+        "intra": intra,
         "deblock": deblock,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get(dom),
@@ -410,6 +441,25 @@ def reference_cu_rate(frames=3):
             "sample": f"xeve_pinter_analyze_cu inside a real 1-thread encode of {frames} {c.w}x{c.h} pictures (inter pictures only)"}
 
 
+def reference_intra_rate(frames=1):
+    """Reference side of the intra line: a real single-thread encode of the first (intra) picture of the same clip with a
+    stop-watch around the reference's own pintra_analyze_cu (oracle/ref_harness.c, TRACE_INTRA_TIME) -> CUs / s per host core."""
+    from oracle import refharness as rh
+    from xeve_b200.clips import Clip
+    if not rh.available():
+        return {"unavailable": "oracle/_ref not present"}
+    c = Clip(CLIP)
+    dt = np.uint8 if c.depth == 8 else np.dtype("<u2")
+    yuv = np.frombuffer(b"".join(c.frame_bytes(i) for i in range(frames)), dt)
+    rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=PRESET, trace_mask=rh.TRACE_INTRA_TIME, pic_lo=0, pic_hi=1 << 30,
+                   want_bitstream=False)
+    sec, calls = rh.intra_time()
+    rate = calls / sec if sec > 0 else 0.0
+    return {"cus_per_s_per_core": round(rate, 1), "calls": int(calls), "seconds": round(sec, 3), "cores": usable_cores(),
+            "cus_per_s_all_cores_ideal": round(rate * usable_cores(), 1), "kind": "reference",
+            "sample": f"pintra_analyze_cu inside a real 1-thread encode of the intra picture of the {c.w}x{c.h} clip"}
+
+
 def reference_deblock():
     """The reference's own edge filters (xeve_deblock_cu_ver / _hor, one thread -- xeve_loop_filter is single-threaded with one
     tile) over the same synthetic picture as the b200 arm's deblock line."""
@@ -482,6 +532,10 @@ def main():
             ref = run_reference(a)
             out["cpu_baseline"] = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
             out["deblock"]["cpu_reference"] = reference_deblock()
+            iref = reference_intra_rate()
+            out["intra"]["cpu_reference"] = iref
+            if iref.get("cus_per_s_per_core"):
+                out["intra"]["host_cores_equivalent"] = round(out["intra"]["cus_per_s_kernel"] / iref["cus_per_s_per_core"], 1)
             cur = reference_cu_rate()
             out["analyze_cu"]["cpu_reference"] = cur
             if cur.get("cus_per_s_per_core"):

@@ -412,6 +412,10 @@ static double hook_cu(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw
  * intra analysis trace: ctx->fn_pintra_analyze_cu (src_base/xeve_pintra.c:544-698)
  * ---------------------------------------------------------------------------------------- */
 #define RH_T_INTRA 64
+#define RH_T_INTRA_TIME 128 /* no records: only the time spent inside the reference's pintra_analyze_cu and the call count */
+static double  g_intra_secs;
+static int64_t g_intra_calls;
+RH_API double rh_intra_time(int64_t *calls) { if(calls) *calls = g_intra_calls; return g_intra_secs; }
 typedef struct {                /* == xb200_intra_item */
     int32_t  poc, cur_pic;
     int16_t  x, y;
@@ -448,6 +452,13 @@ static int64_t push_nbr(XEVE_CORE *core, int cuw, int cuh)
 static double hook_intra(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_cuw, int log2_cuh, XEVE_MODE *mi,
                          s16 coef[N_C][MAX_CU_DIM], pel *rec[N_C], int s_rec[N_C])
 {
+    if(tracing(RH_T_INTRA_TIME) && !tracing(RH_T_INTRA)) {
+        const double t0 = now_s();
+        const double c = T.org_intra(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
+        g_intra_secs += now_s() - t0;
+        g_intra_calls++;
+        return c;
+    }
     if(!tracing(RH_T_INTRA)) return T.org_intra(ctx, core, x, y, log2_cuw, log2_cuh, mi, coef, rec, s_rec);
     XEVE_PINTRA *pi = &ctx->pintra[core->thread_cnt];
     RH_INTRA_REC r;
@@ -649,7 +660,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     vec_reset(&T.intra, sizeof(RH_INTRA_REC));
     vec_reset(&T.df, sizeof(RH_DF_REC)); vec_reset(&T.df_cu, sizeof(RH_DF_CU)); vec_reset(&T.df_maps, 1); T.df_collect = 0;
     T.have_rates = 0;
-    g_cu_secs = 0; g_cu_calls = 0;
+    g_cu_secs = 0; g_cu_calls = 0; g_intra_secs = 0; g_intra_calls = 0;
     T.ctx = ctx; T.mask = trace_mask; T.pic_lo = pic_lo; T.pic_hi = pic_hi;
     if(trace_mask) {
         T.org_me = ctx->pinter[0].fn_me; T.org_mc = ctx->pinter[0].fn_mc; T.org_tq = ctx->fn_tq;

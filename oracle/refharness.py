@@ -171,7 +171,18 @@ def _p(a):
 
 TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
 TRACE_DF = 32
-TRACE_INTRA = 64
+TRACE_INTRA, TRACE_INTRA_TIME = 64, 128
+
+
+def intra_time():
+    """(seconds inside the reference's pintra_analyze_cu, calls) of the last encode_clip(trace_mask=TRACE_INTRA_TIME)"""
+    L = lib()
+    L.rh_intra_time.restype = C.c_double
+    n = C.c_int64(0)
+    sec = L.rh_intra_time(C.byref(n))
+    return sec, n.value
+
+
 INTRA_REC = np.dtype([
     ("poc", "<i4"), ("cur_pic", "<i4"), ("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("slice_type", "u1"),
     ("ctx_skip", "u1"), ("ctx_pred_mode", "u1"), ("all_preds", "u1"), ("qp", "u1", (3,)), ("mpm", "u1", (5,)), ("pad0_", "u1", (2,)),

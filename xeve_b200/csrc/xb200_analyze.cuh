@@ -71,6 +71,7 @@ template <int T> __device__ __noinline__ uint32_t cu_count(CuHdr &H, const xb200
         c.range = H.rg[ST_RUN]; c.bits = 0; c.m = H.st[ST_RUN];
         cb_count_item(c, it, coef, tt);
         if(tt == 0) { H.bits = c.bits; H.rg[ST_RUN] = c.range; }
+        __syncwarp(); // lane 0 may trail the others through its last bins: reconverge before a block-wide barrier
     }
     team_sync<T>();
     const uint32_t b = H.bits;

@@ -8,6 +8,24 @@
 
 namespace {
 
+template <int L2> constexpr int intra_smem() { return 8192 + IntraCfg<L2>::TEAMS * (int)sizeof(IntraTeam<L2>); }
+
+template <int L2>
+int launch_intra(xb200_ctx *c, xb200_intra_item *d_items, const int32_t *d_order, int cnt, const xb200_rates *d_rates, const xb200_sbac *d_st0,
+                 xb200_sbac *d_st1, const int16_t *d_side, int16_t *d_coef, int16_t *d_rec)
+{
+    if(cnt == 0) return XB200_OK;
+    using Cf = IntraCfg<L2>;
+    const int teams_needed = (cnt + Cf::TEAMS - 1) / Cf::TEAMS;
+    const int resident = L2 <= 4 ? 148 * 8 : (L2 == 5 ? 148 * 4 : 148 * 2);   // persistent CTAs: a few per SM
+    const int grid = teams_needed < resident ? teams_needed : resident;
+    k_intra<L2><<<grid, Cf::CTA, intra_smem<L2>(), c->side[L2 >= 3 ? (L2 - 3 > 3 ? 3 : L2 - 3) : 0]>>>(c->d_pics, d_items, d_order, cnt, d_rates, d_st0,
+                                                                                                     d_st1, d_side, d_coef, d_rec, c->d_tm64, c->sq);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
 int intra_init(xb200_ctx *c)
 {
     if(c->intra_ready) return XB200_OK;
@@ -18,8 +36,8 @@ int intra_init(xb200_ctx *c)
     CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
     CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
     CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
-    CK(cudaFuncSetAttribute(k_intra<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<8>)));
-    CK(cudaFuncSetAttribute(k_intra<6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraSmem<64>)));
+    CK(cudaFuncSetAttribute(k_intra<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<5>()));
+    CK(cudaFuncSetAttribute(k_intra<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<6>()));
     c->intra_ready = true;
     return XB200_OK;
 }
@@ -34,7 +52,7 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
         return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     if(n == 0) return XB200_OK;
-    int cnt[2] = {0, 0}; // [CUs up to 8x8 | larger CUs]
+    int cnt[5] = {0, 0, 0, 0, 0}; // per CU size 4x4 .. 64x64
     for(int64_t i = 0; i < n; i++) {
         const xb200_intra_item &it = items[i];
         if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 2 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
@@ -45,12 +63,14 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
            it.out_off < 0 || it.out_off + sz > elems || it.ctx_skip > 1 || it.ctx_pred_mode > 2 || it.mpm[0] > 4 || it.mpm[1] > 4 ||
            it.mpm[2] > 4 || it.mpm[3] > 4 || it.mpm[4] > 4)
             return XB200_ERR_INVALID_ARGUMENT;
-        cnt[it.log2_cuw <= 3 ? 0 : 1]++;
+        cnt[it.log2_cuw - 2]++;
     }
     std::vector<int32_t> order((size_t)n);
+    int first[5];
     {
-        int pos[2] = {0, cnt[0]};
-        for(int64_t i = 0; i < n; i++) order[(size_t)pos[items[i].log2_cuw <= 3 ? 0 : 1]++] = (int32_t)i;
+        int pos[5], acc = 0;
+        for(int k = 0; k < 5; k++) { first[k] = pos[k] = acc; acc += cnt[k]; }
+        for(int64_t i = 0; i < n; i++) order[(size_t)pos[items[i].log2_cuw - 2]++] = (int32_t)i;
     }
     int r;
     if((r = intra_init(c))) return r;
@@ -71,17 +91,17 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     int16_t *d_coef = static_cast<int16_t *>(c->b_in_coef.p), *d_rec = rec ? static_cast<int16_t *>(c->b_in_rec.p) : nullptr;
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(d_coef, 0, (size_t)elems * 2, c->stream));
-    if(cnt[0]) {
-        const int grid = cnt[0] < 148 * 16 ? cnt[0] : 148 * 16;
-        k_intra<3, 32><<<grid, 32, sizeof(IntraSmem<8>), c->stream>>>(c->d_pics, d_items, d_order, cnt[0], d_rates, d_st0, d_st1, d_side, d_coef,
-                                                                        d_rec, c->d_tm64, c->sq);
-        c->launches++;
-    }
-    if(cnt[1]) {
-        const int grid = cnt[1] < 148 * 2 ? cnt[1] : 148 * 2;
-        k_intra<6, 128><<<grid, 128, sizeof(IntraSmem<64>), c->stream>>>(c->d_pics, d_items, d_order + cnt[0], cnt[1], d_rates, d_st0, d_st1,
-                                                                          d_side, d_coef, d_rec, c->d_tm64, c->sq);
-        c->launches++;
+    // the five size classes run concurrently on the side streams (fork / join around the caller-visible stream)
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for(int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    if((r = launch_intra<2>(c, d_items, d_order + first[0], cnt[0], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    if((r = launch_intra<3>(c, d_items, d_order + first[1], cnt[1], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    if((r = launch_intra<4>(c, d_items, d_order + first[2], cnt[2], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    if((r = launch_intra<5>(c, d_items, d_order + first[3], cnt[3], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    if((r = launch_intra<6>(c, d_items, d_order + first[4], cnt[4], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    for(int i = 0; i < 4; i++) {
+        CK(cudaEventRecord(c->ev_join[i], c->side[i]));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;

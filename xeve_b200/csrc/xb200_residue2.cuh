@@ -200,7 +200,8 @@ template <int LN, int T> XB_DEV void inv_dct_t(int16_t *blk, int32_t *TB, const 
 // ---- RDOQ (see xb200_tq.cuh for the derivation of the two-state scan) -----------------------------------------------
 XB_DEV int compose_map(int first, int second) { return ((second >> (first & 1)) & 1) | (((second >> ((first >> 1) & 1)) & 1) << 1); }
 
-template <int LN, int T>
+// INTRA: the coded-block flag of an intra luma block is cbf_luma, of an inter one cbf_all (src_base/xeve_tq.c:565-577)
+template <int LN, int T, bool INTRA = false>
 XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch, int slice_type, const xb200_rates *__restrict__ rt,
                       int bd, int use_rdoq, int tt, TeamScratch &X)
 {
@@ -257,7 +258,7 @@ XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch
         E.lev[0][0] = rt->level[ctx][0]; E.lev[0][1] = rt->level[ctx][1];
         E.lev[1][0] = rt->level[ctx + 1][0]; E.lev[1][1] = rt->level[ctx + 1][1];
     }
-    const int32_t *cbf = ch == 0 ? rt->cbf_all : (ch == 1 ? rt->cbf_cb : rt->cbf_cr); // inter CU: luma uses cbf_all
+    const int32_t *cbf = ch == 0 ? (INTRA ? rt->cbf_luma : rt->cbf_all) : (ch == 1 ? rt->cbf_cb : rt->cbf_cr);
     const int64_t  best0 = unc_blk + (int64_t)cbf[0] * E.lambda, base0 = unc_blk + (int64_t)cbf[1] * E.lambda;
     const int64_t  last0 = (int64_t)rt->last[ch == 0 ? 0 : 1][0] * E.lambda, last1 = (int64_t)rt->last[ch == 0 ? 0 : 1][1] * E.lambda;
     const int64_t  zero_rate[2] = {(int64_t)E.run[0][1] * E.lambda, (int64_t)E.run[1][1] * E.lambda};
@@ -501,6 +502,7 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
     if constexpr(Cf::TC && USE_TC) tc_teardown<LNMAX>(*TCW, threadIdx.x);
 }
 
+#ifndef XB200_DEVICE_FUNCS_ONLY
 __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,3 +522,4 @@ __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, i
         if(key == k && k < 4) order[(size_t)k * n + base + __popc(m & ((1u << lane) - 1))] = i;
     }
 }
+#endif // XB200_DEVICE_FUNCS_ONLY

@@ -228,3 +228,51 @@ def synth_deblock(w, h, seed, intra_frac=0.1):
     pre = [np.clip(yy, 0, 1023).astype(np.int16), np.clip(yy[::2, ::2] + rng.integers(-9, 10, (h // 2, w // 2)), 0, 1023).astype(np.int16),
            rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16)]
     return dict(pre=pre, cus=cus, pp=pp[0], map_scu=map_scu.reshape(-1), map_refi=map_refi.reshape(-1, 2), map_mv=map_mv.reshape(-1, 2, 2))
+
+
+def synth_intra(w, h, planes10, cur_pic, rates_of_state, qp=29, seed=0, sizes=(5, 4, 3, 2)):
+    """pintra_analyze_cu inputs for every CU of the 32/16/8/4 quad-tree of an intra picture, all at once (frame-parallel
+    mode): the reference samples are taken from the ORIGINAL picture -- what the reference's own
+    look-ahead variant does (pintra_get_nbr_simple, src_base/xeve_pintra.c:463-490) -- with the left column, the upper row
+    and the upper-right extension available inside the picture and the lower-left extension unavailable; fresh coder state.
+    planes10: (Y, U, V) original picture at the internal bit depth.  Returns (items, states, rates, side, elems)."""
+    rng = np.random.default_rng(seed + 5)
+    lam, _ = lambdas(qp)
+    items_all, side_all, pos = [], [], 0
+    half = 512
+    for l2 in sizes:
+        s = 1 << l2
+        gx, gy = np.meshgrid(np.arange(0, w - s + 1, s), np.arange(0, h - s + 1, s))
+        xs, ys = gx.ravel().astype(np.int64), gy.ravel().astype(np.int64)
+        n = len(xs)
+        blocks = []
+        for c, pl in enumerate(planes10):
+            nn = s if c == 0 else s >> 1
+            px, py = (xs, ys) if c == 0 else (xs >> 1, ys >> 1)
+            P = 2 * nn + 2
+            pad = np.pad(pl.astype(np.int16), P, constant_values=half)
+            k = np.arange(-1, 2 * nn)
+            left = pad[py[:, None] + k[None, :] + P, (px - 1)[:, None] + P].copy()
+            left[:, nn + 1:] = half                                    # lower-left extension: not yet coded
+            up = pad[(py - 1)[:, None] + P, px[:, None] + k[None, :] + P].copy()
+            left[:, 0] = up[:, 0]
+            blocks += [left, up]
+        side_all.append(np.concatenate(blocks, axis=1).reshape(-1))
+        it = np.zeros(n, api.INTRA_ITEM)
+        it["cur_pic"], it["x"], it["y"], it["log2_cuw"], it["log2_cuh"] = cur_pic, xs, ys, l2, l2
+        it["nb_off"] = pos + np.arange(n) * (8 * s + 6)
+        pos += n * (8 * s + 6)
+        items_all.append(it)
+    items = np.concatenate(items_all)
+    n = len(items)
+    items["slice_type"], items["all_preds"], items["qp"] = 2, 1, np.array([qp + 12, qp + 10, qp + 10], np.uint8)
+    items["mpm"] = np.array([0, 2, 3, 1, 4], np.uint8)                 # xeve_tbl_mpm[DC][DC]
+    items["inter_satd"] = 0xFFFFFFFF
+    items["lambda"], items["sqrt_lambda0"], items["dist_chroma_weight"] = lam, math.sqrt(lam[0]), 1.0 / 0.63
+    items["cm_ipm_in"] = 512
+    items["rate_idx"], items["state_in"], items["state_out"] = 0, 0, 1 + np.arange(n)
+    sz = (3 << (2 * items["log2_cuw"].astype(np.int64))) >> 1
+    items["out_off"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+    states = np.zeros(n + 1, api.SBAC)
+    states["range"], states["m"] = 16384, 512
+    return items, states, rates_of_state(states[:1]), np.concatenate(side_all), int(sz.sum())
