@@ -509,6 +509,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p fast (default, BASELINE configs[1]) or 2160p 10-bit medium")
     args = ap.parse_args()
+    # exactly ONE line on stdout: everything libraries print (NCCL's version banner, torchrun notices) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
     select_workload(args.workload)
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -516,7 +523,7 @@ def main():
         if rank == 0:
             a = argparse.Namespace(**vars(args))
             a.steps = min(args.steps, 3)
-            print(json.dumps(run_reference(a)))
+            emit(run_reference(a))
         return
     dist = None
     if world > 1:
@@ -542,7 +549,7 @@ def main():
                 gpu_rate = out["analyze_cu"]["cus_per_frame"] * out["analyze_cu"]["frames_per_s_kernel"]
                 out["analyze_cu"]["cus_per_s_kernel"] = round(gpu_rate, 1)
                 out["analyze_cu"]["host_cores_equivalent"] = round(gpu_rate / cur["cus_per_s_per_core"], 1)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
