@@ -33,9 +33,15 @@ int intra_init(xb200_ctx *c)
     int64_t       es[6][7];
     for(int q = 0; q < 6; q++)
         for(int l2 = 0; l2 < 7; l2++) es[q][l2] = xb200_err_scale(q, l2, c->seq.bit_depth);
+    static int8_t tm[64 * 64];
+    xb200_gen_tm64(tm);
+    CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
     CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
     CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
     CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+    CK(cudaFuncSetAttribute(k_intra<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<2>()));
+    CK(cudaFuncSetAttribute(k_intra<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<3>()));
+    CK(cudaFuncSetAttribute(k_intra<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<4>()));
     CK(cudaFuncSetAttribute(k_intra<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<5>()));
     CK(cudaFuncSetAttribute(k_intra<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, intra_smem<6>()));
     c->intra_ready = true;
@@ -94,8 +100,26 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     // the five size classes run concurrently on the side streams (fork / join around the caller-visible stream)
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for(int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
-    if((r = launch_intra<2>(c, d_items, d_order + first[0], cnt[0], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
-    if((r = launch_intra<3>(c, d_items, d_order + first[1], cnt[1], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+    {   // 4x4 and 8x8 CUs: one thread per CU (XB200_INTRA_SMALL=team selects the warp-per-CU kernels instead; identical results)
+        static const char *e = getenv("XB200_INTRA_SMALL");
+        if(e && e[0] == 't') {
+            if((r = launch_intra<2>(c, d_items, d_order + first[0], cnt[0], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+            if((r = launch_intra<3>(c, d_items, d_order + first[1], cnt[1], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
+        }
+        else {
+            if(cnt[0]) {
+                k_intra_thr<2><<<(cnt[0] + I4_THREADS - 1) / I4_THREADS, I4_THREADS, 0, c->side[0]>>>(c->d_pics, d_items, d_order + first[0], cnt[0],
+                                                                                                     d_rates, d_st0, d_st1, d_side, d_coef, d_rec, c->sq);
+                c->launches++;
+            }
+            if(cnt[1]) {
+                k_intra_thr<3><<<(cnt[1] + I4_THREADS - 1) / I4_THREADS, I4_THREADS, 0, c->side[3]>>>(c->d_pics, d_items, d_order + first[1], cnt[1],
+                                                                                                     d_rates, d_st0, d_st1, d_side, d_coef, d_rec, c->sq);
+                c->launches++;
+            }
+            CK(cudaGetLastError());
+        }
+    }
     if((r = launch_intra<4>(c, d_items, d_order + first[2], cnt[2], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
     if((r = launch_intra<5>(c, d_items, d_order + first[3], cnt[3], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
     if((r = launch_intra<6>(c, d_items, d_order + first[4], cnt[4], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;

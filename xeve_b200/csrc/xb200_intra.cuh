@@ -84,6 +84,31 @@ XB_DEV void cb_run_length_sm(Cabac &c, const int16_t *lev, int n, int num_sig, i
 }
 
 
+constexpr int I4_THREADS = 128;
+struct TCabac { // engine of xb200_cabac.cuh with strided models: model idx of this thread / lane at m[idx * CS]
+    uint32_t  range, bits;
+    uint16_t *m;
+};
+template <int CS = I4_THREADS> XB_DEV void tc_bin(TCabac &c, int idx, int bin)
+{
+    const uint32_t model = c.m[idx * CS];
+    uint32_t       mps = model & 1, state = model >> 1;
+    cb_step(c.range, c.bits, state, mps, (uint32_t)(bin != 0));
+    c.m[idx * CS] = (uint16_t)((state << 1) | mps);
+}
+template <int CS = I4_THREADS> XB_DEV void tc_unary(TCabac &c, uint32_t sym, int idx) // sbac_write_unary_sym with two contexts
+{
+    tc_bin<CS>(c, idx, sym != 0);
+    if(sym == 0) return;
+    const uint32_t model = c.m[(idx + 1) * CS];
+    uint32_t       mps = model & 1, state = model >> 1;
+    for(; sym > 1; sym--) cb_step(c.range, c.bits, state, mps, 1);
+    cb_step(c.range, c.bits, state, mps, 0);
+    c.m[(idx + 1) * CS] = (uint16_t)((state << 1) | mps);
+}
+XB_DEV void tc_ep(TCabac &c) { c.range &= ~1u; c.bits++; }
+
+
 // Hadamard SATD tile of (org - predictor) with the predictor evaluated on the fly (src_base/xeve_sad.c:417-607)
 template <int TN, class F> XB_DEV int had_tile_fn(const int16_t *a, int sa, F pred)
 {
@@ -128,8 +153,12 @@ template <int L2> struct IntraTeam {
     int32_t  TB[NY < 32 ? 32 : NY];        // DCT stage buffer / RDOQ scratch
     int16_t  org[NY * 3 / 2];              // Y | U | V original block
     int16_t  blk[NY];                      // transform working block
-    int16_t  levS[NY];                     // current luma levels, zig-zag order
-    int16_t  bestS[NY];                    // best luma candidate, zig-zag order
+    int16_t  candS[5][NY + 2];             // luma levels of every candidate mode, zig-zag order (+2: lanes on different banks)
+    int16_t  candR[5][NY];                 // reconstruction of every candidate mode
+    uint16_t cm_lane[IN_CM_N * 8];         // one model set per candidate lane, [model][lane]
+    int64_t  cand_ssd[5];
+    int32_t  cand_nnz[5];
+    uint32_t cand_bits[5];
     int16_t  chS[NY / 2];                  // chroma levels U | V, zig-zag order
     int16_t  nb[8 * N + 8];                // per plane: left[-1 .. 2n-1], up[-1 .. 2n-1]
     uint16_t cm_base[IN_CM_N + 2], cm_run[IN_CM_N + 2];
@@ -241,9 +270,7 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
         const int pred_cnt = M.pred_cnt;
 
         // ---- luma RDO per surviving mode (pintra_residue_rdo mode 0, src_base/xeve_pintra.c:97-152) ---------------------
-        double   cost = IN_MAX_COST;
-        int      best_ipd = 0, nnz_best0 = 0;
-        int32_t  best_dist_y = 0;
+        // pass 1 (team): transform, RDOQ, reconstruction and SSD of every surviving mode; levels kept in zig-zag order
         int16_t *g_coef = coef + it.out_off, *g_rec = rec ? rec + it.out_off : nullptr;
         for(int j = 0; j < pred_cnt; j++) {
             const int ipm = M.list[j];
@@ -251,28 +278,7 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
             team_sync<T>();
             fwd_dct_t<L2, T>(M.blk, M.TB, tm, tmT, bd, tt);
             const int nnz = quant_team<L2, T, true>(M.blk, M.TB, it.qp[0], lambda0, 0, slice_type, rt, bd, sq.rdoq, tt, M.X);
-            for(int e = tt; e < NY; e += T) M.levS[zz_of(e, L2)] = M.blk[e];
-            for(int k = tt; k < IN_CM_N; k += T) M.cm_run[k] = M.cm_base[k];
-            team_sync<T>();
-            if(tt < 32) { // xeve_rdo_bit_cnt_cu_intra_luma, src_base/xeve_mode.c:81-119
-                Cabac c;
-                c.range = range_base; c.bits = 0; c.m = M.cm_run;
-                if(lane == 0) {
-                    if(slice_type != 2 && all_preds) {
-                        cb_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
-                        cb_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
-                    }
-                    cb_unary(c, mpm[ipm], IN_CM_IPM);
-                    cb_bin(c, XB200_CM_CBF_LUMA, nnz != 0);
-                }
-                if(nnz) cb_run_length_sm(c, M.levS, NY, nnz, 0, lane);
-                if(lane == 0) M.bits = c.bits;
-                __syncwarp(); // lane 0 trails the others through its last bins: reconverge before any block-wide barrier
-            }
-            // candidate levels are still in blk (raster): keep them in registers for the "new best" copy below
-            int16_t keep[(NY + T - 1) / T];
-#pragma unroll
-            for(int k = 0; k < (NY + T - 1) / T; k++) { const int e = tt + k * T; keep[k] = e < NY ? M.blk[e] : (int16_t)0; }
+            for(int e = tt; e < NY; e += T) M.candS[j][zz_of(e, L2)] = M.blk[e];
             if(nnz) {
                 team_sync<T>();
                 dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
@@ -283,27 +289,61 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
                 const int     pr = ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY);
                 const int16_t t = nnz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
                 const int     r = clip3i(0, maxv, t), d = r - M.org[e];
-                M.blk[e] = (int16_t)r;
+                M.candR[j][e] = (int16_t)r;
                 ssd += (int64_t)((d * d) >> sh);
             }
-            team_sync<T>(); // publishes M.bits and the reconstruction in blk
+            team_sync<T>();
             ssd = team_sum_s64<T>(ssd, tt, M.X);
-            double        cost_t = (double)ssd;
-            const int32_t dist_t = (int32_t)cost_t;
-            cost_t = __dadd_rn(cost_t, __dmul_rn((double)M.bits, lambda0));
-            if(cost_t < cost) {
-                cost = cost_t; best_dist_y = dist_t; best_ipd = ipm; nnz_best0 = nnz;
-#pragma unroll
-                for(int k = 0; k < (NY + T - 1) / T; k++) {
-                    const int e = tt + k * T;
-                    if(e < NY) {
-                        g_coef[e] = keep[k];
-                        M.bestS[e] = M.levS[e];
-                        if(g_rec) g_rec[e] = M.blk[e];
-                    }
+            if(tt == 0) { M.cand_ssd[j] = ssd; M.cand_nnz[j] = nnz; }
+        }
+        team_sync<T>();
+        // pass 2 (one lane per mode): xeve_rdo_bit_cnt_cu_intra_luma (src_base/xeve_mode.c:81-119) of all modes at once --
+        // the bins of one mode are serial, the modes are independent, so lane j codes mode j on its own copy of the models
+        if(tt < pred_cnt) {
+            uint16_t *ml = M.cm_lane + tt;
+            for(int k = 0; k < IN_CM_N; k++) ml[k * 8] = M.cm_base[k];
+            TCabac c;
+            c.range = range_base; c.bits = 0; c.m = ml;
+            if(slice_type != 2 && all_preds) {
+                tc_bin<8>(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+                tc_bin<8>(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+            }
+            tc_unary<8>(c, mpm[M.list[tt]], IN_CM_IPM);
+            int num_sig = M.cand_nnz[tt];
+            tc_bin<8>(c, XB200_CM_CBF_LUMA, num_sig != 0);
+            if(num_sig) { // xeve_eco_run_length_cc over the zig-zag ordered levels; ends with the last significant one
+                const int16_t *lv = M.candS[tt];
+                uint32_t       run = 0;
+                for(int sp = 0; sp < NY; sp++) {
+                    const int v = lv[sp];
+                    if(v == 0) { run++; continue; }
+                    tc_unary<8>(c, run, XB200_CM_RUN);
+                    tc_unary<8>(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL);
+                    tc_ep(c);
+                    if(sp == NY - 1) break;
+                    run = 0;
+                    num_sig--;
+                    tc_bin<8>(c, XB200_CM_LAST, num_sig == 0);
+                    if(num_sig == 0) break;
                 }
             }
-            team_sync<T>();
+            M.cand_bits[tt] = c.bits;
+        }
+        __syncwarp();
+        team_sync<T>();
+        double  cost = IN_MAX_COST;
+        int     best_j = 0;
+        int32_t best_dist_y = 0;
+        for(int j = 0; j < pred_cnt; j++) { // first minimum in list order (strict <), every thread alike
+            double        cost_t = (double)M.cand_ssd[j];
+            const int32_t dist_t = (int32_t)cost_t;
+            cost_t = __dadd_rn(cost_t, __dmul_rn((double)M.cand_bits[j], lambda0));
+            if(cost_t < cost) { cost = cost_t; best_dist_y = dist_t; best_j = j; }
+        }
+        const int best_ipd = M.list[best_j], nnz_best0 = M.cand_nnz[best_j];
+        for(int e = tt; e < NY; e += T) {
+            g_coef[e] = M.candS[best_j][zz_of(e, L2)];
+            if(g_rec) g_rec[e] = M.candR[best_j][e];
         }
 
         // ---- chroma with the winning luma mode (pintra_residue_rdo mode 1, :153-270); its own bit count is never used ---
@@ -358,7 +398,7 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
                 cb_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
                 cb_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
             }
-            if(nnz_best0) cb_run_length_sm(c, M.bestS, NY, nnz_best0, 0, lane);
+            if(nnz_best0) cb_run_length_sm(c, M.candS[best_j], NY, nnz_best0, 0, lane);
             if(nnzc[0]) cb_run_length_sm(c, M.chS, NCH, nnzc[0], 1, lane);
             if(nnzc[1]) cb_run_length_sm(c, M.chS + NCH, NCH, nnzc[1], 2, lane);
             if(lane == 0) { M.bits = c.bits; M.range_run = c.range; }
@@ -381,5 +421,418 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
             for(int k = tt; k < XB200_CM_COUNT; k += T) so.m[k] = M.cm_run[k];
         }
         team_sync<T>();
+    }
+}
+
+// =====================================================================================================================
+// 4x4 and 8x8 CUs: one THREAD per CU.  Nine tenths of the CUs of an intra picture are 4x4 or 8x8: a warp per CU leaves most
+// lanes idle through five transform + RDOQ + coder passes (16 k warp-instructions per 4x4 CU).  Here every step is the
+// plain sequential algorithm on arrays private to the thread (registers for 4x4, local memory for 8x8); only the context
+// models live in shared memory, laid out [model][thread] so that the 32 lanes of a warp hit 32 different banks.
+// =====================================================================================================================
+
+// zig-zag scan position -> raster index: closed forms for N = 2 and N = 4, a shared-memory table (built by the kernel from
+// zz_of) for N = 8
+template <int LN> XB_DEV int zz_raster(int sp, const uint8_t *zinv8)
+{
+    if(LN == 1) return sp;
+    if(LN == 2) return (int)((0xFEB7ADC963258410ull >> (4 * sp)) & 15); // 0 1 4 8 5 2 3 6 9 12 13 10 7 11 14 15
+    return zinv8[sp];
+}
+
+// xeve_eco_run_length_cc of one block whose levels are in raster order
+template <int LN> XB_DEV void tc_run_length(TCabac &c, const int16_t *lev, int num_sig, int ch, const uint8_t *zinv8)
+{
+    constexpr int n = 1 << (2 * LN);
+    const int     t0 = ch == 0 ? 0 : 2;
+    uint32_t      run = 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+    for(int sp = 0; sp < n; sp++) {
+        const int v = lev[zz_raster<LN>(sp, zinv8)];
+        if(v == 0) { run++; continue; }
+        tc_unary(c, run, XB200_CM_RUN + t0);
+        tc_unary(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL + t0);
+        tc_ep(c);
+        if(sp == n - 1) break;
+        run = 0;
+        num_sig--;
+        tc_bin(c, XB200_CM_LAST + (ch != 0), num_sig == 0);
+        if(num_sig == 0) break;
+    }
+}
+
+// forward / inverse transform of a private N x N block (src_base/xeve_tq.c:396-404, src_base/xeve_itdq.c:435-440)
+template <int LN> XB_DEV void fwd_dct_thr(int16_t *b, int bd)
+{
+    constexpr int N = 1 << LN;
+    const int     shift = (LN - 1 + bd - 8) + (LN + 6);
+    int           t[N * N];
+#pragma unroll(LN <= 2 ? 4 : 1)
+    for(int y = 0; y < N; y++)
+#pragma unroll
+        for(int u = 0; u < N; u++) {
+            int acc = 0;
+#pragma unroll
+            for(int x = 0; x < N; x++) acc += tmN(LN, u, x) * (int)b[y * N + x];
+            t[y * N + u] = acc;
+        }
+#pragma unroll(LN <= 2 ? 4 : 1)
+    for(int u = 0; u < N; u++)
+#pragma unroll
+        for(int v = 0; v < N; v++) {
+            int64_t acc = 0;
+#pragma unroll
+            for(int y = 0; y < N; y++) acc += (int64_t)tmN(LN, v, y) * (int64_t)t[y * N + u];
+            b[v * N + u] = (int16_t)((acc + ((int64_t)1 << (shift - 1))) >> shift);
+        }
+}
+template <int LN> XB_DEV void inv_dct_thr(int16_t *b, int bd)
+{
+    constexpr int N = 1 << LN;
+    const int     shift = 7 + 12 - (bd - 8);
+    int           t[N * N];
+#pragma unroll(LN <= 2 ? 4 : 1)
+    for(int u = 0; u < N; u++)
+#pragma unroll
+        for(int y = 0; y < N; y++) {
+            int acc = 0; // |sum| <= 8 * 32768 * 90 fits 32 bits
+#pragma unroll
+            for(int v = 0; v < N; v++) acc += tmN(LN, v, y) * (int)b[v * N + u];
+            t[y * N + u] = acc;
+        }
+#pragma unroll(LN <= 2 ? 4 : 1)
+    for(int y = 0; y < N; y++)
+#pragma unroll
+        for(int x = 0; x < N; x++) {
+            int64_t acc = 0;
+#pragma unroll
+            for(int u = 0; u < N; u++) acc += (int64_t)tmN(LN, u, x) * (int64_t)t[y * N + u];
+            acc = (acc + ((int64_t)1 << (shift - 1))) >> shift;
+            b[y * N + x] = (int16_t)max((int64_t)-32768, min((int64_t)32767, acc));
+        }
+}
+
+// xeve_quant_nnz + xeve_rdoq_run_length_cc (src_base/xeve_tq.c:497-730), sequential, intra block; b: coefficients -> levels
+template <int LN>
+XB_DEV int rdoq_thr(int16_t *b, int qp, double d_lambda, int ch, int slice_type, const xb200_rates *__restrict__ rt, int bd, int use_rdoq,
+                    const uint8_t *zinv8)
+{
+    constexpr int n = 1 << (2 * LN);
+    const int     q = c_quant_scale[qp % 6], qbits = 14 + (15 - bd - LN) + qp / 6;
+    if(!use_rdoq) {
+        const int32_t off = (int32_t)(slice_type == 2 ? 171 : 85) << (qbits - 9);
+        int           cnt = 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+        for(int e = 0; e < n; e++) {
+            const int     c = b[e];
+            const int32_t lev = (int16_t)(((int32_t)abs(c) * q + off) >> qbits);
+            b[e] = (int16_t)(c < 0 ? -lev : lev);
+            cnt += lev != 0;
+        }
+        return cnt;
+    }
+    const int64_t thr = ((int64_t)1 << qbits) - ((int64_t)(slice_type == 2 ? 201 : 153) << (qbits - 9));
+    RdoqEnv E;
+    E.lambda = (int64_t)(d_lambda * 32768.0 + 0.5);
+    E.es     = c_err_scale[qp % 6][LN];
+    E.qbits  = qbits;
+    int     coded = 0, any = 0;
+    int64_t unc_blk = 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+    for(int e = 0; e < n; e++) {
+        const int c = b[e];
+        int64_t   ld; uint32_t maxl;
+        rq_quant(c, q, qbits, ld, maxl);
+        const int64_t e0 = (ld * E.es) >> 20;
+        unc_blk += e0 * e0;
+        coded |= ((int64_t)abs(c) * q >= thr);
+        any |= maxl != 0;
+    }
+    if(!coded || !any) {
+#pragma unroll(LN <= 2 ? 16 : 1)
+        for(int e = 0; e < n; e++) b[e] = 0;
+        return 0;
+    }
+    {
+        const int ctx = ch == 0 ? 0 : 2;
+        E.run[0][0] = rt->run[ctx][0]; E.run[0][1] = rt->run[ctx][1];
+        E.run[1][0] = rt->run[ctx + 1][0]; E.run[1][1] = rt->run[ctx + 1][1];
+        E.lev[0][0] = rt->level[ctx][0]; E.lev[0][1] = rt->level[ctx][1];
+        E.lev[1][0] = rt->level[ctx + 1][0]; E.lev[1][1] = rt->level[ctx + 1][1];
+    }
+    const int32_t *cbf = ch == 0 ? rt->cbf_luma : (ch == 1 ? rt->cbf_cb : rt->cbf_cr);
+    int64_t        best = unc_blk + (int64_t)cbf[0] * E.lambda, base = unc_blk + (int64_t)cbf[1] * E.lambda;
+    const int64_t  last0 = (int64_t)rt->last[ch == 0 ? 0 : 1][0] * E.lambda, last1 = (int64_t)rt->last[ch == 0 ? 0 : 1][1] * E.lambda;
+    int            state = 0, best_last = 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+    for(int sp = 0; sp < n; sp++) {
+        const int p = zz_raster<LN>(sp, zinv8), c = b[p];
+        int64_t   ld, dl; uint32_t maxl;
+        rq_quant(c, q, qbits, ld, maxl);
+        const uint32_t lev = rq_level(E, ld, maxl, state, dl);
+        b[p] = (int16_t)(c > 0 ? (int)lev : -(int)lev);
+        base += dl;
+        if(lev) {
+            const int64_t as_last = base + last1;
+            base += last0;
+            if(as_last < best) { best = as_last; best_last = sp + 1; }
+            state = 0;
+        }
+        else state = 1;
+    }
+    int nnz = 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+    for(int sp = 0; sp < n; sp++) {
+        const int p = zz_raster<LN>(sp, zinv8);
+        if(sp < best_last) nnz += b[p] != 0;
+        else b[p] = 0;
+    }
+    return nnz;
+}
+template <int LN> XB_DEV void dequant_thr(int16_t *b, int qp, int bd)
+{
+    constexpr int n = 1 << (2 * LN);
+    const int     shift = 20 - 14 - (15 - bd - LN);
+    const int64_t scale = (int64_t)c_dequant_scale[qp % 6] << (qp / 6), off = shift ? (int64_t)1 << (shift - 1) : 0;
+#pragma unroll(LN <= 2 ? 16 : 1)
+    for(int e = 0; e < n; e++) {
+        const int64_t v = ((int64_t)b[e] * scale + off) >> shift;
+        b[e] = (int16_t)max((int64_t)-32768, min((int64_t)32767, v));
+    }
+}
+
+// the context models a Baseline intra CU can touch: skip_flag[ctx], pred_mode[ctx], intra_dir[0..1], cbf_luma / cb / cr,
+// run[0..3], level[0..3], last[0..1]
+XB_DEV int i4_model(int k, int ctx_skip, int ctx_pm)
+{
+    return k == 0 ? XB200_CM_SKIP_FLAG + ctx_skip : k == 1 ? XB200_CM_PRED_MODE + ctx_pm : k < 4 ? IN_CM_IPM + (k - 2)
+         : k == 4 ? XB200_CM_CBF_LUMA : k == 5 ? XB200_CM_CBF_CB : k == 6 ? XB200_CM_CBF_CR : k < 11 ? XB200_CM_RUN + (k - 7)
+         : k < 15 ? XB200_CM_LEVEL + (k - 11) : XB200_CM_LAST + (k - 15);
+}
+constexpr int I4_MODELS = 17;
+
+template <int L2>
+__global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restrict__ pics, xb200_intra_item *items,
+                                                          const int32_t *__restrict__ order, int cnt, const xb200_rates *__restrict__ rates,
+                                                          const xb200_sbac *__restrict__ st_in, xb200_sbac *__restrict__ st_out,
+                                                          const int16_t *__restrict__ side, int16_t *__restrict__ coef,
+                                                          int16_t *__restrict__ rec, SeqDev sq)
+{
+    constexpr int N = 1 << L2, NY = N * N, NC = N / 2, NCH = NC * NC, LC = L2 - 1;
+    constexpr int NBY = 2 * N + 1, NBC = N + 1;   // samples per reference array (index -1 .. 2n-1)
+    constexpr int UR = L2 == 2 ? 64 : 1;          // arrays of 4x4 CUs stay in registers (every loop over them fully unrolled)
+    __shared__ uint16_t cm_base[IN_CM_N * I4_THREADS], cm_run[IN_CM_N * I4_THREADS];
+    __shared__ uint8_t  zinv8[64];
+    if(threadIdx.x < 64) zinv8[zz_of(threadIdx.x, 3)] = (uint8_t)threadIdx.x;
+    __syncthreads();
+    const int ii = blockIdx.x * I4_THREADS + threadIdx.x;
+    if(ii >= cnt) return;
+    xb200_intra_item &it = items[order[ii]];
+    const int bd = sq.bd, maxv = (1 << bd) - 1, sh = (bd - 8) << 1;
+    const int slice_type = it.slice_type, all_preds = it.all_preds, ctx_skip = it.ctx_skip, ctx_pm = it.ctx_pred_mode;
+    const xb200_rates *rt = &rates[it.rate_idx];
+    const double       lambda0 = it.lambda[0];
+    uint16_t *mb = cm_base + threadIdx.x, *mr = cm_run + threadIdx.x;
+    const xb200_sbac &s0 = st_in[it.state_in];
+    const uint32_t    range_base = s0.range;
+#pragma unroll
+    for(int k = 0; k < I4_MODELS; k++) {
+        const int idx = i4_model(k, ctx_skip, ctx_pm);
+        mb[idx * I4_THREADS] = idx >= IN_CM_IPM ? it.cm_ipm_in[idx - IN_CM_IPM] : s0.m[idx];
+    }
+    uint8_t mpm[5];
+#pragma unroll
+    for(int k = 0; k < 5; k++) mpm[k] = it.mpm[k];
+    // original block and reference samples
+    int16_t org[NY], orgc[2][NCH];
+    {
+        const PicDev   p = pics[it.cur_pic];
+        const int      x0 = it.x, y0 = it.y;
+        const int16_t *gy = p.p[0] + (ptrdiff_t)y0 * p.s[0] + x0;
+#pragma unroll(UR)
+        for(int q = 0; q < NY / 4; q++) { // x0 is a multiple of 4: 8-byte aligned quads
+            const int   r = q / (N / 4), cq = (q % (N / 4)) * 4;
+            const uint2 v = *reinterpret_cast<const uint2 *>(gy + (ptrdiff_t)r * p.s[0] + cq);
+            org[r * N + cq + 0] = (int16_t)(v.x & 0xffff); org[r * N + cq + 1] = (int16_t)(v.x >> 16);
+            org[r * N + cq + 2] = (int16_t)(v.y & 0xffff); org[r * N + cq + 3] = (int16_t)(v.y >> 16);
+        }
+#pragma unroll
+        for(int c = 1; c < 3; c++) {
+            const int16_t *gc = p.p[c] + (ptrdiff_t)(y0 >> 1) * p.s[c] + (x0 >> 1);
+#pragma unroll(UR)
+            for(int q = 0; q < NCH / 2; q++) {
+                const int      r = q / (NC / 2), cq = (q % (NC / 2)) * 2;
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(gc + (ptrdiff_t)r * p.s[c] + cq);
+                orgc[c - 1][r * NC + cq] = (int16_t)(v & 0xffff); orgc[c - 1][r * NC + cq + 1] = (int16_t)(v >> 16);
+            }
+        }
+    }
+    int16_t nbY[2 * NBY], nbC[2][2 * NBC]; // left[-1 .. 2n-1] | up[-1 .. 2n-1]
+    {
+        const int16_t *gn = side + it.nb_off;
+#pragma unroll(UR)
+        for(int k = 0; k < 2 * NBY; k++) nbY[k] = gn[k];
+#pragma unroll
+        for(int c = 0; c < 2; c++)
+#pragma unroll(UR)
+            for(int k = 0; k < 2 * NBC; k++) nbC[c][k] = gn[2 * NBY + c * 2 * NBC + k];
+    }
+    const int16_t *leY = nbY + 1, *upY = nbY + NBY + 1;
+    const int      dcY = ipred_dc(leY, upY, L2);
+
+    // ---- make_ipred_list -------------------------------------------------------------------------------------------------
+    double   cand_cost[5];
+    uint32_t cand_satd[5];
+    int      list[5];
+#pragma unroll
+    for(int k = 0; k < 5; k++) { list[k] = 0; cand_cost[k] = IN_MAX_COST; cand_satd[k] = 0xffffffffu; }
+    TCabac c;
+    c.m = mr;
+#pragma unroll 1
+    for(int ipm = 0; ipm < 5; ipm++) {
+        uint32_t satd;
+        if(L2 == 2) satd = (uint32_t)had_tile_fn<4>(org, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, y, x, dcY); });
+        else satd = (uint32_t)had_tile_fn<8>(org, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, y, x, dcY); });
+        satd >>= (bd - 8);
+        c.range = range_base; c.bits = 0;
+        mr[IN_CM_IPM * I4_THREADS] = mb[IN_CM_IPM * I4_THREADS]; mr[(IN_CM_IPM + 1) * I4_THREADS] = mb[(IN_CM_IPM + 1) * I4_THREADS];
+        tc_unary(c, mpm[ipm], IN_CM_IPM);
+        const double cost = __dadd_rn((double)satd, __dmul_rn((double)c.bits, it.sqrt_lambda0));
+        int shift = 0;
+        while(shift < 5 && cost < cand_cost[4 - shift]) shift++;
+        if(shift) {
+            for(int j = 1; j < shift; j++) { list[5 - j] = list[4 - j]; cand_cost[5 - j] = cand_cost[4 - j]; cand_satd[5 - j] = cand_satd[4 - j]; }
+            list[5 - shift] = ipm; cand_cost[5 - shift] = cost; cand_satd[5 - shift] = satd;
+        }
+    }
+    int pred_cnt = 5;
+    {
+        const double thr = __dmul_rn((double)it.inter_satd, 1.2);
+        for(int i = 4; i >= 1; i--) {
+            if((double)cand_satd[i] > thr) pred_cnt--;
+            else break;
+        }
+    }
+
+    // ---- luma RDO per surviving mode --------------------------------------------------------------------------------------
+    double  cost = IN_MAX_COST;
+    int     best_ipd = 0, nnz_best0 = 0;
+    int32_t best_dist_y = 0;
+    int16_t best_lev[NY], best_rec[NY];
+#pragma unroll 1
+    for(int j = 0; j < pred_cnt; j++) {
+        const int ipm = list[j];
+        int16_t   b[NY], lev[NY];
+#pragma unroll(UR)
+        for(int e = 0; e < NY; e++) b[e] = (int16_t)(org[e] - ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY));
+        fwd_dct_thr<L2>(b, bd);
+        const int nnz = rdoq_thr<L2>(b, it.qp[0], lambda0, 0, slice_type, rt, bd, sq.rdoq, zinv8);
+#pragma unroll(UR)
+        for(int e = 0; e < NY; e++) lev[e] = b[e];
+#pragma unroll
+        for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * I4_THREADS] = mb[idx * I4_THREADS]; }
+        c.range = range_base; c.bits = 0;
+        if(slice_type != 2 && all_preds) {
+            tc_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+            tc_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+        }
+        tc_unary(c, mpm[ipm], IN_CM_IPM);
+        tc_bin(c, XB200_CM_CBF_LUMA, nnz != 0);
+        if(nnz) {
+            tc_run_length<L2>(c, lev, nnz, 0, zinv8);
+            dequant_thr<L2>(b, it.qp[0], bd);
+            inv_dct_thr<L2>(b, bd);
+        }
+        int64_t ssd = 0;
+#pragma unroll(UR)
+        for(int e = 0; e < NY; e++) {
+            const int     pr = ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY);
+            const int16_t t = nnz ? (int16_t)(b[e] + pr) : (int16_t)pr;
+            const int     r = clip3i(0, maxv, t), d = r - org[e];
+            b[e] = (int16_t)r;
+            ssd += (int64_t)((d * d) >> sh);
+        }
+        double        cost_t = (double)ssd;
+        const int32_t dist_t = (int32_t)cost_t;
+        cost_t = __dadd_rn(cost_t, __dmul_rn((double)c.bits, lambda0));
+        if(cost_t < cost) {
+            cost = cost_t; best_dist_y = dist_t; best_ipd = ipm; nnz_best0 = nnz;
+#pragma unroll(UR)
+            for(int e = 0; e < NY; e++) { best_lev[e] = lev[e]; best_rec[e] = b[e]; }
+        }
+    }
+
+    // ---- chroma with the winning luma mode ---------------------------------------------------------------------------------
+    int16_t *g_coef = coef + it.out_off, *g_rec = rec ? rec + it.out_off : nullptr;
+    int      nnzc[2];
+    int64_t  ssdc[2];
+    int16_t  levc[2][NCH];
+#pragma unroll
+    for(int cc = 0; cc < 2; cc++) {
+        const int16_t *le = nbC[cc] + 1, *up = nbC[cc] + NBC + 1;
+        const int      dc = ipred_dc(le, up, LC);
+        int16_t        b[NCH];
+#pragma unroll
+        for(int e = 0; e < NCH; e++) b[e] = (int16_t)(orgc[cc][e] - ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc));
+        fwd_dct_thr<LC>(b, bd);
+        const int nz = rdoq_thr<LC>(b, it.qp[cc + 1], it.lambda[cc + 1], cc + 1, slice_type, rt, bd, sq.rdoq, zinv8);
+        nnzc[cc] = nz;
+#pragma unroll
+        for(int e = 0; e < NCH; e++) { levc[cc][e] = b[e]; g_coef[NY + cc * NCH + e] = b[e]; }
+        if(nz) {
+            dequant_thr<LC>(b, it.qp[cc + 1], bd);
+            inv_dct_thr<LC>(b, bd);
+        }
+        int64_t ssd = 0;
+#pragma unroll
+        for(int e = 0; e < NCH; e++) {
+            const int     pr = ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc);
+            const int16_t t = nz ? (int16_t)(b[e] + pr) : (int16_t)pr;
+            const int     r = clip3i(0, maxv, t), d = r - orgc[cc][e];
+            if(g_rec) g_rec[NY + cc * NCH + e] = (int16_t)r;
+            ssd += (int64_t)((d * d) >> sh);
+        }
+        ssdc[cc] = ssd;
+    }
+    const int32_t best_dist_c = (int32_t)__dadd_rn(__dmul_rn(it.dist_chroma_weight[0], (double)ssdc[0]),
+                                                   __dmul_rn(it.dist_chroma_weight[1], (double)ssdc[1]));
+#pragma unroll(UR)
+    for(int e = 0; e < NY; e++) {
+        g_coef[e] = best_lev[e];
+        if(g_rec) g_rec[e] = best_rec[e];
+    }
+
+    // ---- final bit count from the input state --------------------------------------------------------------------------------
+#pragma unroll
+    for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * I4_THREADS] = mb[idx * I4_THREADS]; }
+    c.range = range_base; c.bits = 0;
+    if(slice_type != 2) {
+        tc_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+        tc_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+    }
+    tc_unary(c, mpm[best_ipd], IN_CM_IPM);
+    tc_bin(c, XB200_CM_CBF_CB, nnzc[0] != 0);
+    tc_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
+    tc_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
+    if(nnz_best0) tc_run_length<L2>(c, best_lev, nnz_best0, 0, zinv8);
+    if(nnzc[0]) tc_run_length<LC>(c, levc[0], nnzc[0], 1, zinv8);
+    if(nnzc[1]) tc_run_length<LC>(c, levc[1], nnzc[1], 2, zinv8);
+
+    double ct = __dmul_rn((double)c.bits, lambda0);
+    ct = __dadd_rn(ct, (double)best_dist_y);
+    ct = __dadd_rn(ct, (double)best_dist_c);
+    it.cost = ct;
+    it.dist_cu = best_dist_y + best_dist_c;
+    it.ipm[0] = it.ipm[1] = (int8_t)best_ipd;
+    it.nnz[0] = nnz_best0; it.nnz[1] = nnzc[0]; it.nnz[2] = nnzc[1];
+    it.cm_ipm_out[0] = mr[IN_CM_IPM * I4_THREADS]; it.cm_ipm_out[1] = mr[(IN_CM_IPM + 1) * I4_THREADS];
+    // output state = input state with the models this CU touched replaced
+    xb200_sbac &so = st_out[it.state_out];
+    so.range = c.range;
+    for(int k = 0; k < XB200_CM_COUNT; k++) so.m[k] = s0.m[k];
+#pragma unroll
+    for(int k = 0; k < I4_MODELS; k++) {
+        const int idx = i4_model(k, ctx_skip, ctx_pm);
+        if(idx < XB200_CM_COUNT) so.m[idx] = mr[idx * I4_THREADS];
     }
 }
