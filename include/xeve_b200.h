@@ -287,6 +287,20 @@ typedef struct {
     uint64_t coef_hash, rec_hash;   /* unused by the library (test bookkeeping) */
 } xb200_intra_item;
 
+/* Inputs of xb200_analyze_intra taken from the picture being reconstructed: xeve_get_avail_intra (src_base/xeve_util.c:717-772),
+ * xeve_get_nbr for Y, U, V (src_base/xeve_ipred.c:33-97) and xeve_get_mpm (:230-252), one tile.  The samples of item i are
+ * written at element offset nb_off of `side` in the layout xb200_intra_item::nb_off expects (8 * cuw + 6 samples). */
+typedef struct {
+    int16_t  x, y;                  /* luma position of the CU */
+    uint8_t  log2_cuw, log2_cuh;
+    /* results */
+    uint8_t  mpm[5];                /* xeve_tbl_mpm[ipm_left][ipm_up][0..4] */
+    uint8_t  pad_;
+    uint16_t avail;                 /* AVAIL_* bit mask of xeve_get_avail_intra (src_base/xeve_def.h:402-425) */
+    uint16_t pad2_;
+    int64_t  nb_off;                /* in: where the reference samples go */
+} xb200_nbr_item;
+
 /* ---- in-loop deblocking of a reconstructed picture --------------------------------------------------
  * One leaf CU of the coding tree, as xeve_deblock_tree hands it to ctx->fn_deblock_unit (src_base/xeve_df.c:575-639). */
 typedef struct {
@@ -377,6 +391,11 @@ XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, 
 XB200_API int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const xb200_rates *rates, int64_t n_rates,
                                   xb200_sbac *states, int64_t n_states, const int16_t *side, int64_t side_elems, int16_t *coef,
                                   int16_t *rec, int64_t elems);
+
+/* pic: device picture holding the reconstruction so far (PIC_MODE).  map_scu: u32[f_scu] (COD bit 31 = already coded, IF bit 15
+ * = intra); map_ipm: s8[f_scu] luma intra modes; constrained_intra_pred: pps.constrained_intra_pred_flag.  Host buffers. */
+XB200_API int xb200_intra_nbr(xb200_ctx *c, int32_t pic, xb200_nbr_item *items, int64_t n, const uint32_t *map_scu, const int8_t *map_ipm,
+                              int w_scu, int h_scu, int constrained_intra_pred, int16_t *side, int64_t side_elems);
 
 /* In-loop deblocking of picture `pic` (a padded picture holding the unfiltered reconstruction), in place: every CU's left
  * edge (x > 0), then every CU's top edge (y > 0), 4-sample segments with the filter strength derived from the two

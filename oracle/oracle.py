@@ -169,3 +169,16 @@ def analyze_intra_batch(seq, planes, rates, items, states, side, elems):
     L.xo_analyze_intra_batch(_p(seq), C.addressof(planes), _p(np.ascontiguousarray(rates)), _p(items), len(items), _p(states),
                              _p(np.ascontiguousarray(side, np.int16)), _p(coef), _p(rec))
     return items, states, coef, rec
+
+
+def intra_nbr(planes, items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems, bit_depth=10):
+    L = lib()
+    L.xo_intra_nbr_batch.restype = None
+    L.xo_intra_nbr_batch.argtypes = [VP, VP, VP, I, I, VP, C.c_int64, VP, VP, I, I, I, I, VP]
+    keep = [np.ascontiguousarray(a, np.int16) for a in planes]
+    items = items.copy()
+    side = np.zeros(side_elems, np.int16)
+    L.xo_intra_nbr_batch(_p(keep[0]), _p(keep[1]), _p(keep[2]), keep[0].shape[1], keep[1].shape[1], _p(items), len(items),
+                         _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_ipm, np.int8)), w_scu, h_scu, int(cip),
+                         bit_depth, _p(side))
+    return items, side

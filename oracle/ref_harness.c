@@ -504,6 +504,37 @@ static double hook_intra(XEVE_CTX *ctx, XEVE_CORE *core, int x, int y, int log2_
     return cost;
 }
 
+/* the reference's xeve_get_avail_intra + xeve_get_nbr (Y, U, V) + xeve_get_mpm on caller-provided planes and maps */
+typedef struct { int16_t x, y; uint8_t log2_cuw, log2_cuh; uint8_t mpm[5]; uint8_t pad_; uint16_t avail; uint16_t pad2_; int64_t nb_off; } RH_NBR_REC;
+RH_API int rh_sizeof_nbr(void) { return sizeof(RH_NBR_REC); }
+RH_API void rh_intra_nbr(const RH_PLANES *pl, RH_NBR_REC *items, int n, u32 *map_scu, s8 *map_ipm, int w_scu, int h_scu, int cip,
+                         int bit_depth, s16 *side)
+{
+    static pel nb[N_C][N_REF][MAX_CU_SIZE * 3];
+    u8 *tidx = calloc((size_t)w_scu * h_scu, 1);
+    for(int i = 0; i < n; i++) {
+        RH_NBR_REC *it = &items[i];
+        const int   x = it->x, y = it->y, cuw = 1 << it->log2_cuw, cuh = 1 << it->log2_cuh, xs = x >> 2, ys = y >> 2, scup = xs + ys * w_scu;
+        u16 av = xeve_get_avail_intra(xs, ys, w_scu, h_scu, scup, it->log2_cuw, it->log2_cuh, map_scu, tidx);
+        it->avail = av;
+        xeve_get_nbr(x, y, cuw, cuh, pl->y + y * pl->s_l + x, pl->s_l, av, nb, scup, map_scu, w_scu, h_scu, Y_C, cip, tidx, bit_depth, 1);
+        xeve_get_nbr(x >> 1, y >> 1, cuw >> 1, cuh >> 1, pl->u + (y >> 1) * pl->s_c + (x >> 1), pl->s_c, av, nb, scup, map_scu, w_scu, h_scu,
+                     U_C, cip, tidx, bit_depth, 1);
+        xeve_get_nbr(x >> 1, y >> 1, cuw >> 1, cuh >> 1, pl->v + (y >> 1) * pl->s_c + (x >> 1), pl->s_c, av, nb, scup, map_scu, w_scu, h_scu,
+                     V_C, cip, tidx, bit_depth, 1);
+        u8 *mpm;
+        xeve_get_mpm(xs, ys, cuw, cuh, map_scu, map_ipm, scup, w_scu, &mpm, tidx);
+        memcpy(it->mpm, mpm, 5);
+        s16 *out = side + it->nb_off;
+        for(int c = 0; c < 3; c++) {
+            int w = c ? cuw >> 1 : cuw, h = c ? cuh >> 1 : cuh, m = w + h + 1;
+            memcpy(out, nb[c][0] + 2 - 1, m * sizeof(s16)); out += m;
+            memcpy(out, nb[c][1] + h - 1, m * sizeof(s16)); out += m;
+        }
+    }
+    free(tidx);
+}
+
 /* ------------------------------------------------------------------------------------------
  * deblocking trace: ctx->fn_loop_filter with the picture before / after, the frame
  * maps it reads and the CU rectangles xeve_deblock_tree enumerates (ctx->fn_deblock_unit)
@@ -865,6 +896,7 @@ RH_API const void *rh_table(int which, int *bytes)
     case 12: *bytes = sizeof(xeve_tbl_mc_c_coeff); return xeve_tbl_mc_c_coeff;
     case 13: *bytes = sizeof(util_ctx()->err_scale); return util_ctx()->err_scale;
     case 14: *bytes = sizeof(xeve_tbl_df_st); return xeve_tbl_df_st;
+    case 15: *bytes = sizeof(xeve_tbl_mpm); return xeve_tbl_mpm;
     }
     *bytes = 0;
     return NULL;

@@ -200,6 +200,27 @@ DF_REC = np.dtype([("poc", "<i4"), ("pre_pic", "<i4"), ("post_pic", "<i4"), ("on
                    ("maps_off", "<i8"), ("pp", DF_PIC)], align=True)
 
 
+NBR_REC = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("mpm", "u1", (5,)), ("pad_", "u1"),
+                    ("avail", "<u2"), ("pad2_", "<u2"), ("nb_off", "<i8")], align=True)
+
+
+def intra_nbr(planes, items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems, bit_depth=10):
+    """The reference's xeve_get_avail_intra / xeve_get_nbr / xeve_get_mpm over a CU list -> (items, side)"""
+    L = lib()
+    assert L.rh_sizeof_nbr() == NBR_REC.itemsize
+    L.rh_intra_nbr.restype = None
+    L.rh_intra_nbr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    pl = PLANES()
+    keep = [np.ascontiguousarray(a, np.int16) for a in planes]
+    pl.y, pl.u, pl.v = (a.ctypes.data for a in keep)
+    pl.s_l, pl.s_c, pl.w_l, pl.h_l = keep[0].shape[1], keep[1].shape[1], keep[0].shape[1], keep[0].shape[0]
+    items = np.ascontiguousarray(items, NBR_REC).copy()
+    side = np.zeros(side_elems, np.int16)
+    L.rh_intra_nbr(C.addressof(pl), _p(items), len(items), _p(np.ascontiguousarray(map_scu, np.uint32)),
+                   _p(np.ascontiguousarray(map_ipm, np.int8)), w_scu, h_scu, int(cip), bit_depth, _p(side))
+    return items, side
+
+
 def df_maps(maps, off, f):
     """(map_scu u32[f], map_refi s8[f,2], map_mv s16[f,2,2]) of one traced picture (copies)."""
     b = maps[off:off + 14 * f]

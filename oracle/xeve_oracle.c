@@ -1466,6 +1466,61 @@ void xo_analyze_intra_batch(const xb200_seq *sq, const xo_planes *pl, const xb20
     for(int64_t i = 0; i < n; i++) xo_analyze_intra(sq, pl, rates, &items[i], states, side, coef + items[i].out_off, rec + items[i].out_off);
 }
 
+/* xeve_get_avail_intra (src_base/xeve_util.c:717-772), xeve_get_nbr (src_base/xeve_ipred.c:33-97) for the three planes and
+ * xeve_get_mpm (:230-252), single tile.  y/u/v: active-area origins of the picture reconstructed so far. */
+void xo_intra_nbr(const int16_t *y, const int16_t *u, const int16_t *v, int s_l, int s_c, xb200_nbr_item *it, const uint32_t *map_scu,
+                  const int8_t *map_ipm, int w_scu, int h_scu, int cip, int bd, int16_t *side)
+{
+    static const uint8_t mpm_tbl[6][6][5] = XB200_MPM_TABLE;
+    const int xs = it->x >> 2, ys = it->y >> 2, scuw = (1 << it->log2_cuw) >> 2, scuh = (1 << it->log2_cuh) >> 2;
+    const int scup = xs + ys * w_scu, half = 1 << (bd - 1);
+#define COD(p) ((map_scu[p] >> 31) & 1)
+#define IFL(p) ((map_scu[p] >> 15) & 1)
+    unsigned av = 0;
+    if(xs > 0 && COD(scup - 1)) {
+        av |= 1u << 1;
+        if(ys + scuh + scuw - 1 < h_scu && COD(scup + w_scu * (scuw + scuh) - w_scu - 1)) av |= 1u << 7;
+    }
+    if(ys > 0) {
+        av |= (1u << 0) | (1u << 9);
+        if(xs > 0 && COD(scup - w_scu - 1)) av |= 1u << 5;
+        if(xs + scuw < w_scu && COD(scup - w_scu + scuw)) av |= 1u << 6;
+    }
+    if(xs + scuw < w_scu && COD(scup + scuw)) {
+        av |= 1u << 3;
+        if(ys + scuh + scuw - 1 < h_scu && COD(scup + w_scu * (scuw + scuh - 1) + scuw)) av |= 1u << 8;
+    }
+    it->avail = (uint16_t)av;
+    int ipm_l = 0, ipm_u = 0;
+    if(xs > 0 && IFL(scup - 1) && COD(scup - 1)) ipm_l = map_ipm[scup - 1] + 1;
+    if(ys > 0 && IFL(scup - w_scu) && COD(scup - w_scu)) ipm_u = map_ipm[scup - w_scu] + 1;
+    memcpy(it->mpm, mpm_tbl[ipm_l][ipm_u], 5);
+    int16_t *out = side + it->nb_off;
+    for(int c = 0; c < 3; c++) {
+        const int      n = c ? (1 << it->log2_cuw) >> 1 : 1 << it->log2_cuw, unit = c ? 2 : 4, s = c ? s_c : s_l;
+        const int16_t *src = (c == 0 ? y : c == 1 ? u : v) + (c ? (it->y >> 1) * s + (it->x >> 1) : it->y * s + it->x);
+        int16_t       *left = out + 1, *up = out + (2 * n + 1) + 1;
+        up[-1] = (int16_t)(((av >> 5) & 1) && (!cip || IFL(scup - w_scu - 1)) ? src[-s - 1] : half);
+        for(int i = 0; i < scuw + scuh; i++) {
+            const int ok = ys > 0 && xs + i < w_scu && COD(scup - w_scu + i) && (!cip || IFL(scup - w_scu + i));
+            for(int k = 0; k < unit; k++) up[i * unit + k] = (int16_t)(ok ? src[-s + i * unit + k] : half);
+        }
+        for(int i = 0; i < scuh + scuw; i++) {
+            const int ok = xs > 0 && ys + i < h_scu && COD(scup - 1 + i * w_scu) && (!cip || IFL(scup - 1 + i * w_scu));
+            for(int k = 0; k < unit; k++) left[i * unit + k] = (int16_t)(ok ? src[(i * unit + k) * s - 1] : half);
+        }
+        left[-1] = up[-1];
+        out += 2 * (2 * n + 1);
+    }
+#undef COD
+#undef IFL
+}
+void xo_intra_nbr_batch(const int16_t *y, const int16_t *u, const int16_t *v, int s_l, int s_c, xb200_nbr_item *items, int64_t n,
+                        const uint32_t *map_scu, const int8_t *map_ipm, int w_scu, int h_scu, int cip, int bd, int16_t *side)
+{
+    for(int64_t i = 0; i < n; i++) xo_intra_nbr(y, u, v, s_l, s_c, &items[i], map_scu, map_ipm, w_scu, h_scu, cip, bd, side);
+}
+
 
 /* FNV-1a over per-item output slots (the hash the harness records for in-situ results) */
 void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out)

@@ -561,3 +561,25 @@ def test_intra_matches_reference_in_situ():
             td = tracedata.live_intra(**kw)
             got = _gpu_intra(td)
             assert len(got) > 500
+
+
+@pytest.mark.parametrize("w,h,seed,cip", [(64, 64, 0, 0), (176, 144, 1, 1), (1920, 1080, 2, 0)])
+def test_intra_neighbours_match_oracle_and_reference(w, h, seed, cip):
+    """xb200_intra_nbr == xeve_get_avail_intra + xeve_get_nbr + xeve_get_mpm: random pictures / COD / IF maps, with and without
+    constrained intra prediction, CUs 4x4 .. 64x64 incl. the picture corners; the samples feed xb200_analyze_intra unchanged"""
+    planes, items, ms, mi, ws, hs, elems = tracedata.synth_nbr(w, h, seed, n=2000)
+    hp = api.Hotpath(api.make_seq(w, h))
+    pic = hp.pic_create(padded=True)
+    hp.pic_upload_s16(pic, *planes)
+    got_it, got_side = hp.intra_nbr(pic, items, ms, mi, ws, hs, cip, elems)
+    exp_it, exp_side = xo.intra_nbr(planes, items, ms, mi, ws, hs, cip, elems)
+    assert np.array_equal(got_side, exp_side)
+    assert np.array_equal(got_it["avail"], exp_it["avail"]) and np.array_equal(got_it["mpm"], exp_it["mpm"])
+    if rh.available():
+        ref_it, ref_side = rh.intra_nbr(planes, items.astype(rh.NBR_REC), ms, mi, ws, hs, cip, elems)
+        assert np.array_equal(got_side, ref_side) and np.array_equal(got_it["mpm"], ref_it["mpm"]) and np.array_equal(got_it["avail"], ref_it["avail"])
+    bad = items[:2].copy()
+    bad["x"][0] = 2
+    with pytest.raises(api.Xb200Error):
+        hp.intra_nbr(pic, bad, ms, mi, ws, hs, cip, elems)
+    hp.close()

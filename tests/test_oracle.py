@@ -238,3 +238,16 @@ def test_oracle_intra_matches_reference_live():
         td = tracedata.live_intra(**kw)
         assert len(td.intra) > 500
         _oracle_intra(td)
+
+
+@needs_ref
+def test_oracle_intra_neighbours_match_reference():
+    """xo_intra_nbr == xeve_get_avail_intra + xeve_get_nbr (Y, U, V) + xeve_get_mpm on random pictures / maps, with and without
+    constrained intra prediction; every availability pattern incl. picture corners"""
+    for seed, (w, h), cip in ((0, (64, 64), 0), (1, (176, 144), 1), (2, (352, 288), 0)):
+        planes, items, ms, mi, ws, hs, elems = tracedata.synth_nbr(w, h, seed)
+        exp_it, exp_side = rh.intra_nbr(planes, items.astype(rh.NBR_REC), ms, mi, ws, hs, cip, elems)
+        got_it, got_side = xo.intra_nbr(planes, items, ms, mi, ws, hs, cip, elems)
+        assert np.array_equal(got_side, exp_side)
+        assert np.array_equal(got_it["avail"], exp_it["avail"]) and np.array_equal(got_it["mpm"], exp_it["mpm"])
+        assert len(np.unique(got_it["avail"])) > 8

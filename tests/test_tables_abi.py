@@ -24,6 +24,9 @@ int main(void){
          sizeof(xb200_mc_item), sizeof(xb200_rates), sizeof(xb200_tq_item), sizeof(xb200_residue_item), sizeof(xb200_blk_item));
   printf("sbac %zu\nbits %zu\ncu %zu\nmvpi %zu\n", sizeof(xb200_sbac), sizeof(xb200_bits_item), sizeof(xb200_cu_item), sizeof(xb200_mvp_item));
   printf("dfcu %zu\ndfpic %zu\n", sizeof(xb200_df_cu), sizeof(xb200_df_pic));
+  printf("intra %zu\nnbr %zu\nintraoff %zu %zu %zu\n", sizeof(xb200_intra_item), sizeof(xb200_nbr_item), offsetof(xb200_intra_item, lambda),
+         offsetof(xb200_intra_item, cost), offsetof(xb200_nbr_item, nb_off));
+  { static const unsigned char m[6][6][5] = XB200_MPM_TABLE; FILE* g = fopen("mpm.bin","wb"); fwrite(m,1,sizeof(m),g); fclose(g); }
   printf("cuoff %zu %zu %zu %zu\n", offsetof(xb200_cu_item, lambda), offsetof(xb200_cu_item, mvp), offsetof(xb200_cu_item, cost), offsetof(xb200_bits_item, coef_off));
   printf("off %zu %zu %zu %zu\n", offsetof(xb200_me_item, lambda_mv), offsetof(xb200_tq_item, lambda),
          offsetof(xb200_residue_item, out_off), offsetof(xb200_residue_item, dist_rec));
@@ -63,6 +66,10 @@ def test_struct_layouts_match_numpy(probe_dir):
     assert int(sizes["sbac"]) == api.SBAC.itemsize and int(sizes["bits"]) == api.BITS_ITEM.itemsize
     assert int(sizes["cu"]) == api.CU_ITEM.itemsize == rh.CU_REC.itemsize and int(sizes["mvpi"]) == api.MVP_ITEM.itemsize
     assert int(sizes["dfcu"]) == api.DF_CU.itemsize == rh.DF_CU.itemsize and int(sizes["dfpic"]) == api.DF_PIC.itemsize == rh.DF_PIC.itemsize
+    assert int(sizes["intra"]) == api.INTRA_ITEM.itemsize == rh.INTRA_REC.itemsize and api.INTRA_ITEM.fields == rh.INTRA_REC.fields
+    assert int(sizes["nbr"]) == api.NBR_ITEM.itemsize == rh.NBR_REC.itemsize
+    ioffs = [int(v) for v in re.search(r"intraoff (\d+) (\d+) (\d+)", out).groups()]
+    assert ioffs == [api.INTRA_ITEM.fields["lambda"][1], api.INTRA_ITEM.fields["cost"][1], api.NBR_ITEM.fields["nb_off"][1]]
     cuoffs = [int(v) for v in re.search(r"cuoff (\d+) (\d+) (\d+) (\d+)", out).groups()]
     assert cuoffs == [api.CU_ITEM.fields["lambda"][1], api.CU_ITEM.fields["mvp"][1], api.CU_ITEM.fields["cost"][1],
                       api.BITS_ITEM.fields["coef_off"][1]]
@@ -94,6 +101,7 @@ def test_generated_tables_match_reference(probe_dir):
     assert np.array_equal(rd("refi.bin", np.uint8).reshape(17, 16), rh.table(7, np.uint8).reshape(17, 16))
     assert np.array_equal(rd("es.bin", np.int64).reshape(6, 7), rh.table(13, np.int64).reshape(6, 7))
     assert np.array_equal(rd("dfst.bin", np.uint8), rh.table(14, np.uint8))
+    assert np.array_equal(rd("mpm.bin", np.uint8), rh.table(15, np.uint8))
     assert list(rh.table(9, np.int32)) == [40, 45, 51, 57, 64, 71]
     assert list(rh.table(10, np.int32)[:6]) == [26214, 23302, 20560, 18396, 16384, 14764]
 

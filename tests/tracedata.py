@@ -149,6 +149,31 @@ def check_intra_results(got, ref, coef, rec, sz, st_got, st_ref):
     assert st_got[ref["state_out"]].tobytes() == st_ref[ref["state_out"]].tobytes()
 
 
+def synth_nbr(w, h, seed, n=600):
+    """Random intra-neighbourhood queries: a picture of random samples, random COD / IF bits and intra modes per SCU, random
+    CUs (4x4 .. 64x64) inside the picture.  Returns (planes, items, map_scu, map_ipm, w_scu, h_scu, side_elems)."""
+    from xeve_b200 import api
+    rng = np.random.default_rng(seed)
+    ws, hs = w // 4, h // 4
+    planes = [rng.integers(0, 1024, (h, w)).astype(np.int16), rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16),
+              rng.integers(0, 1024, (h // 2, w // 2)).astype(np.int16)]
+    map_scu = ((rng.random(ws * hs) < 0.7).astype(np.uint32) << 31) | ((rng.random(ws * hs) < 0.5).astype(np.uint32) << 15)
+    map_ipm = rng.integers(0, 5, ws * hs).astype(np.int8)
+    items = np.zeros(n, api.NBR_ITEM)
+    l2 = rng.integers(2, 7, n)
+    l2 = np.minimum(l2, int(np.log2(min(w, h))))
+    s = 1 << l2
+    items["log2_cuw"] = items["log2_cuh"] = l2
+    items["x"] = (rng.integers(0, 1 << 16, n) % ((w - s) // 4 + 1)) * 4
+    items["y"] = (rng.integers(0, 1 << 16, n) % ((h - s) // 4 + 1)) * 4
+    items["x"][:8] = [0, w - 4, 0, w - 4, 0, 4, w - 8, 0][:8]   # corners and borders
+    items["y"][:8] = [0, 0, h - 4, h - 4, 4, 0, h - 8, h - 8][:8]
+    items["log2_cuw"][:8] = items["log2_cuh"][:8] = [2, 2, 2, 2, 2, 2, 3, 3]
+    sz = 8 * (1 << items["log2_cuw"].astype(np.int64)) + 6
+    items["nb_off"] = np.concatenate([[0], np.cumsum(sz)[:-1]])
+    return planes, items, map_scu, map_ipm, ws, hs, int(sz.sum())
+
+
 DF_GOLDEN = os.path.join(ROOT, "tests", "golden", "df_golden.npz")
 
 

@@ -88,6 +88,9 @@ INTRA_ITEM = np.dtype([
     ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"),
 ], align=True)
 
+NBR_ITEM = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("mpm", "u1", (5,)), ("pad_", "u1"),
+                     ("avail", "<u2"), ("pad2_", "<u2"), ("nb_off", "<i8")], align=True)
+
 DF_CU = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("pad_", "u1", (2,))], align=True)
 DF_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("qp_u_offset", "<i4"), ("qp_v_offset", "<i4"),
                    ("chroma_qp", "<i4", (2, 70))], align=True)
@@ -157,6 +160,7 @@ def load():
         L.xb200_rdoq_rates.argtypes = [VP, VP, C.c_int64, VP]
         L.xb200_analyze_cu.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
         L.xb200_analyze_intra.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
+        L.xb200_intra_nbr.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, C.c_int, C.c_int, C.c_int, VP, C.c_int64]
         L.xb200_deblock.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -165,7 +169,7 @@ def load():
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
-           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra"]
+           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr"]
 
 
 def _p(a):
@@ -317,6 +321,15 @@ class Hotpath:
         self._ck(self.L.xb200_analyze_intra(self.h, _p(items), len(items), _p(rates), len(rates), _p(states), len(states), _p(side),
                                             len(side), _p(coef), _p(rec), elems), "xb200_analyze_intra")
         return items, states, coef, rec
+
+    def intra_nbr(self, handle, items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems):
+        """xeve_get_avail_intra + xeve_get_nbr + xeve_get_mpm of a CU list from device picture `handle` -> (items, side)"""
+        items = np.ascontiguousarray(items, NBR_ITEM).copy()
+        side = np.zeros(side_elems, np.int16)
+        self._ck(self.L.xb200_intra_nbr(self.h, handle, _p(items), len(items), _p(np.ascontiguousarray(map_scu, np.uint32)),
+                                        _p(np.ascontiguousarray(map_ipm, np.int8)), w_scu, h_scu, int(cip), _p(side), side_elems),
+                 "xb200_intra_nbr")
+        return items, side
 
     def deblock(self, handle, cus, pp, map_scu, map_refi, map_mv, expand=True):
         """xeve_loop_filter (+ xeve_picbuf_expand) on the device picture `handle`, in place"""

@@ -36,6 +36,8 @@ int intra_init(xb200_ctx *c)
     static int8_t tm[64 * 64];
     xb200_gen_tm64(tm);
     CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
+    static const uint8_t mpm[6][6][5] = XB200_MPM_TABLE;
+    CK(cudaMemcpyToSymbol(c_mpm_tbl, mpm, sizeof(mpm)));
     CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
     CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
     CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
@@ -132,6 +134,49 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     if((r = to_host(c, states, d_st1, (size_t)n_states, XB200_MEM_HOST))) return r;
     if((r = to_host(c, coef, d_coef, (size_t)elems, XB200_MEM_HOST))) return r;
     if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, XB200_MEM_HOST))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_intra_nbr(xb200_ctx *c, int32_t pic, xb200_nbr_item *items, int64_t n, const uint32_t *map_scu, const int8_t *map_ipm, int w_scu,
+                    int h_scu, int constrained_intra_pred, int16_t *side, int64_t side_elems)
+{
+    if(!c || !pic_ok(c, pic) || n < 0 || n > (1 << 26) || side_elems < 0 || (n && (!items || !map_scu || !map_ipm || !side)))
+        return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    if(n == 0) return XB200_OK;
+    const Pic &p = c->pics[pic];
+    if(w_scu != (p.w[0] + 3) / 4 || h_scu != (p.h[0] + 3) / 4) return XB200_ERR_INVALID_ARGUMENT;
+    for(int64_t i = 0; i < n; i++) {
+        const xb200_nbr_item &it = items[i];
+        if(it.log2_cuw < 2 || it.log2_cuw > 6 || it.log2_cuh != it.log2_cuw) return XB200_ERR_UNSUPPORTED;
+        if(it.x < 0 || it.y < 0 || (it.x & 3) || (it.y & 3) || it.x + (1 << it.log2_cuw) > p.w[0] || it.y + (1 << it.log2_cuh) > p.h[0] ||
+           it.nb_off < 0 || it.nb_off + 8 * (1 << it.log2_cuw) + 6 > side_elems)
+            return XB200_ERR_INVALID_ARGUMENT;
+    }
+    int r;
+    if((r = intra_init(c))) return r;
+    if((r = xb200_sync_pics(c))) return r;
+    const size_t    f = (size_t)w_scu * h_scu;
+    xb200_nbr_item *d_items;
+    uint32_t       *d_scu;
+    int8_t         *d_ipm;
+    if((r = to_dev(c, c->b_in_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
+    if((r = to_dev(c, c->b_in_st0, map_scu, f, XB200_MEM_HOST, &d_scu))) return r;
+    if((r = to_dev(c, c->b_in_st1, map_ipm, f, XB200_MEM_HOST, &d_ipm))) return r;
+    if((r = xb200_ensure(c->b_in_side, (size_t)side_elems * 2 + 64))) return r;
+    int16_t *d_side = static_cast<int16_t *>(c->b_in_side.p);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_intra_nbr<<<(unsigned)((n + 3) / 4), 128, 0, c->stream>>>(c->d_pics, pic, d_items, n, d_scu, d_ipm, w_scu, h_scu, constrained_intra_pred != 0,
+                                                               c->seq.bit_depth, d_side);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
+    if((r = to_host(c, side, d_side, (size_t)side_elems, XB200_MEM_HOST))) return r;
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);

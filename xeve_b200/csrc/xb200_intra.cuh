@@ -836,3 +836,71 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
         if(idx < XB200_CM_COUNT) so.m[idx] = mr[idx * I4_THREADS];
     }
 }
+
+// =====================================================================================================================
+// Reference samples + MPM list of a CU list from the picture reconstructed so far: xeve_get_avail_intra
+// (src_base/xeve_util.c:717-772), xeve_get_nbr for Y, U, V (src_base/xeve_ipred.c:33-97), xeve_get_mpm (:230-252).
+// One warp per CU; lanes stride over the 8N+6 output samples, each deciding the availability of its own 4x4 unit.
+// =====================================================================================================================
+__constant__ uint8_t c_mpm_tbl[6][6][5];
+
+__global__ void k_intra_nbr(const PicDev *__restrict__ pics, int pic, xb200_nbr_item *__restrict__ items, int64_t n,
+                            const uint32_t *__restrict__ map_scu, const int8_t *__restrict__ map_ipm, int w_scu, int h_scu, int cip, int bd,
+                            int16_t *__restrict__ side)
+{
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(i >= n) return;
+    const int       lane = threadIdx.x & 31;
+    xb200_nbr_item &it = items[i];
+    const PicDev    p = pics[pic];
+    const int x = it.x, y = it.y, N = 1 << it.log2_cuw, scuw = N >> 2, scuh = (1 << it.log2_cuh) >> 2, xs = x >> 2, ys = y >> 2;
+    const int scup = xs + ys * w_scu, half = 1 << (bd - 1);
+    auto COD = [&](int q) { return (int)((map_scu[q] >> 31) & 1); };
+    auto IFL = [&](int q) { return (int)((map_scu[q] >> 15) & 1); };
+    unsigned av = 0;
+    if(xs > 0 && COD(scup - 1)) {
+        av |= 1u << 1;
+        if(ys + scuh + scuw - 1 < h_scu && COD(scup + w_scu * (scuw + scuh) - w_scu - 1)) av |= 1u << 7;
+    }
+    if(ys > 0) {
+        av |= (1u << 0) | (1u << 9);
+        if(xs > 0 && COD(scup - w_scu - 1)) av |= 1u << 5;
+        if(xs + scuw < w_scu && COD(scup - w_scu + scuw)) av |= 1u << 6;
+    }
+    if(xs + scuw < w_scu && COD(scup + scuw)) {
+        av |= 1u << 3;
+        if(ys + scuh + scuw - 1 < h_scu && COD(scup + w_scu * (scuw + scuh - 1) + scuw)) av |= 1u << 8;
+    }
+    const bool ul_ok = ((av >> 5) & 1) && (!cip || IFL(scup - w_scu - 1));
+    if(lane == 0) {
+        it.avail = (uint16_t)av;
+        int ipm_l = 0, ipm_u = 0;
+        if(xs > 0 && IFL(scup - 1) && COD(scup - 1)) ipm_l = map_ipm[scup - 1] + 1;
+        if(ys > 0 && IFL(scup - w_scu) && COD(scup - w_scu)) ipm_u = map_ipm[scup - w_scu] + 1;
+        ipm_l = min(max(ipm_l, 0), 5); ipm_u = min(max(ipm_u, 0), 5);
+#pragma unroll
+        for(int k = 0; k < 5; k++) it.mpm[k] = c_mpm_tbl[ipm_l][ipm_u][k];
+    }
+    int16_t *out = side + it.nb_off;
+    for(int e = lane; e < 8 * N + 6; e += 32) {
+        // plane / array / index of output sample e: Y left (2N+1), Y up (2N+1), then U, V with N+1 each
+        int c, r = e;
+        if(r < 2 * (2 * N + 1)) c = 0;
+        else { r -= 2 * (2 * N + 1); c = 1 + r / (2 * (N + 1)); r %= 2 * (N + 1); }
+        const int  nn = c ? N >> 1 : N, per = 2 * nn + 1, unit = c ? 2 : 4;
+        const bool is_up = r >= per;
+        const int  k = (is_up ? r - per : r) - 1; // -1 .. 2nn-1
+        const int16_t *src = p.p[c] + (ptrdiff_t)(c ? y >> 1 : y) * p.s[c] + (c ? x >> 1 : x);
+        const ptrdiff_t s = p.s[c];
+        int v = half;
+        if(k < 0) { if(ul_ok) v = src[-s - 1]; }
+        else {
+            const int u = k / unit;
+            if(is_up) {
+                if(ys > 0 && xs + u < w_scu && COD(scup - w_scu + u) && (!cip || IFL(scup - w_scu + u))) v = src[-s + k];
+            }
+            else if(xs > 0 && ys + u < h_scu && COD(scup - 1 + u * w_scu) && (!cip || IFL(scup - 1 + u * w_scu))) v = src[(ptrdiff_t)k * s - 1];
+        }
+        out[e] = (int16_t)v;
+    }
+}

@@ -115,3 +115,13 @@ XB_HD int xb200_df_strength(int idx, int qp)
     st -= idx;
     return st < 0 ? 0 : st;
 }
+
+// Most-probable-mode symbol table of the Baseline intra mode syntax, [left mode + 1][upper mode + 1][mode] with index 0 = neighbour
+// not intra / not available (EVC Baseline table; src_base/xeve_tbl.c:40-48)
+#define XB200_MPM_TABLE { \
+    { {0,2,3,1,4},{0,2,1,3,4},{0,2,1,3,4},{1,2,0,3,4},{0,2,1,3,4},{0,1,2,3,4} }, \
+    { {1,0,2,3,4},{0,1,2,3,4},{0,1,2,3,4},{1,2,0,3,4},{0,1,3,2,4},{0,2,1,4,3} }, \
+    { {1,0,2,3,4},{1,0,2,3,4},{1,0,2,3,4},{2,0,1,3,4},{1,0,3,2,4},{0,1,2,4,3} }, \
+    { {1,0,2,3,4},{0,2,1,3,4},{1,0,2,3,4},{1,2,0,3,4},{0,1,2,3,4},{0,2,1,4,3} }, \
+    { {0,1,2,3,4},{0,3,2,1,4},{1,0,2,3,4},{1,2,0,3,4},{1,2,3,0,4},{0,2,1,4,3} }, \
+    { {0,1,2,3,4},{0,1,2,4,3},{0,1,2,4,3},{0,2,1,4,3},{0,1,2,3,4},{0,1,2,4,3} } }
