@@ -298,7 +298,11 @@ void xb200_destroy(xb200_ctx *c)
     for(auto &p : c->pics)
         for(int k = 0; k < 3; k++)
             if(p.buf[k]) cudaFree(p.buf[k]);
-    for(DevBuf *b : {&c->b_items, &c->b_side, &c->b_aux0, &c->b_aux1, &c->b_aux2, &c->b_order, &c->b_stage})
+    for(DevBuf *b : {&c->b_items, &c->b_side, &c->b_aux0, &c->b_aux1, &c->b_aux2, &c->b_order, &c->b_stage, &c->b_df, &c->b_in_items,
+                     &c->b_in_rates, &c->b_in_st0, &c->b_in_st1, &c->b_in_side, &c->b_in_coef, &c->b_in_rec, &c->b_in_order, &c->b_scr[0],
+                     &c->b_scr[1], &c->b_scr[2], &c->b_scr[3], &c->b_st0, &c->b_st1, &c->b_cu_items, &c->b_cu_rates, &c->b_cu_state,
+                     &c->b_cu_me, &c->b_cu_res, &c->b_cu_mc, &c->b_cu_cur, &c->b_cu_off, &c->b_cu_side, &c->b_cu_order, &c->b_cu_coef,
+                     &c->b_cu_rec, &c->b_cu_nzr, &c->b_cu_nzl, &c->b_cu_meta})
         if(b->p) cudaFree(b->p);
     if(c->d_pics) cudaFree(c->d_pics);
     if(c->d_tm64) cudaFree(c->d_tm64);
@@ -357,12 +361,17 @@ int xb200_pic_destroy(xb200_ctx *c, int32_t handle)
 extern "C++" int xb200_pad_planes(xb200_ctx *c, Pic &p)
 {
     if(!p.padded) return XB200_OK;
+    PadArgs a;
+    int     total = 0;
     for(int k = 0; k < 3; k++) {
-        int16_t *act = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
-        dim3     grid((p.w[k] + 2 * p.pad[k] + 127) / 128, p.h[k] + 2 * p.pad[k]);
-        k_pad<<<grid, 128, 0, c->stream>>>(act, p.s[k], p.w[k], p.h[k], p.pad[k]);
-        c->launches++;
+        a.act[k] = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k];
+        a.s[k] = p.s[k]; a.w[k] = p.w[k]; a.h[k] = p.h[k]; a.pad[k] = p.pad[k];
+        a.first[k] = total;
+        total += pad_plane_groups(p.w[k], p.h[k], p.pad[k]);
     }
+    a.first[3] = total;
+    k_pad3<<<(total + 255) / 256, 256, 0, c->stream>>>(a);
+    c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
 }

@@ -137,14 +137,25 @@ template <bool HOR> __global__ void __launch_bounds__(256) k_df_pass(const DfArg
     const int     p = ys * a.w_scu + xs;
     if(!(a.flags[p] & bit)) return;
     const int maxv = (1 << a.bd) - 1;
+    // the luma samples of the segment are fetched BEFORE the strength is known: the loads do not depend on the map reads, so
+    // both round trips to memory overlap (a segment whose strength turns out to be 0 costs one wasted read, nothing is written)
+    int16_t        *b = a.pl[0] + (ptrdiff_t)(ys * 4) * a.s[0] + xs * 4;
+    const ptrdiff_t s = a.s[0];
+    uint2           r0, r1, r2, r3; // HOR: rows -2 -1 | 0 1 (4 columns each); VER: rows 0..3 (columns -2 -1 | 0 1)
+    if(HOR) {
+        r0 = *reinterpret_cast<uint2 *>(b - 2 * s); r1 = *reinterpret_cast<uint2 *>(b - s);
+        r2 = *reinterpret_cast<uint2 *>(b); r3 = *reinterpret_cast<uint2 *>(b + s);
+    }
+    else {
+        r0.x = *reinterpret_cast<uint32_t *>(b - 2); r0.y = *reinterpret_cast<uint32_t *>(b);
+        r1.x = *reinterpret_cast<uint32_t *>(b + s - 2); r1.y = *reinterpret_cast<uint32_t *>(b + s);
+        r2.x = *reinterpret_cast<uint32_t *>(b + 2 * s - 2); r2.y = *reinterpret_cast<uint32_t *>(b + 2 * s);
+        r3.x = *reinterpret_cast<uint32_t *>(b + 3 * s - 2); r3.y = *reinterpret_cast<uint32_t *>(b + 3 * s);
+    }
     int       cls = df_class(a.scu, a.refi, a.mv, p, p - nb), qp = DF_MCU_QP(a.scu[p]);
     const int st = xb200_df_strength(cls, qp) << (a.bd - 8);
     if(st) {
-        int16_t        *b = a.pl[0] + (ptrdiff_t)(ys * 4) * a.s[0] + xs * 4;
-        const ptrdiff_t s = a.s[0];
         if(HOR) { // 4 columns; rows -2 -1 | 0 1 (8-byte aligned row segments)
-            uint2 r0 = *reinterpret_cast<uint2 *>(b - 2 * s), r1 = *reinterpret_cast<uint2 *>(b - s);
-            uint2 r2 = *reinterpret_cast<uint2 *>(b), r3 = *reinterpret_cast<uint2 *>(b + s);
             int A[4] = {lo16(r0.x), hi16(r0.x), lo16(r0.y), hi16(r0.y)}, B[4] = {lo16(r1.x), hi16(r1.x), lo16(r1.y), hi16(r1.y)};
             int C[4] = {lo16(r2.x), hi16(r2.x), lo16(r2.y), hi16(r2.y)}, D[4] = {lo16(r3.x), hi16(r3.x), lo16(r3.y), hi16(r3.y)};
 #pragma unroll
@@ -155,11 +166,11 @@ template <bool HOR> __global__ void __launch_bounds__(256) k_df_pass(const DfArg
             *reinterpret_cast<uint2 *>(b + s)     = make_uint2(pack16(D[0], D[1]), pack16(D[2], D[3]));
         }
         else {    // 4 rows; columns -2 -1 | 0 1
+            const uint2 rr[4] = {r0, r1, r2, r3};
 #pragma unroll
             for(int i = 0; i < 4; i++) {
                 int16_t *r = b + i * s;
-                uint32_t ab = *reinterpret_cast<uint32_t *>(r - 2), cd = *reinterpret_cast<uint32_t *>(r);
-                int A = lo16(ab), B = hi16(ab), C = lo16(cd), D = hi16(cd);
+                int A = lo16(rr[i].x), B = hi16(rr[i].x), C = lo16(rr[i].y), D = hi16(rr[i].y);
                 df_taps<true>(A, B, C, D, st, maxv);
                 *reinterpret_cast<uint32_t *>(r - 2) = pack16(A, B);
                 *reinterpret_cast<uint32_t *>(r)     = pack16(C, D);

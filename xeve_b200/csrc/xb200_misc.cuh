@@ -16,14 +16,45 @@ __global__ void k_convert(const T *__restrict__ src, int src_stride_elems, int16
     if(x < w && y < h) dst[(size_t)y * dst_stride + x] = (int16_t)((int)src[(size_t)y * src_stride_elems + x] << shift);
 }
 
-// one thread per sample of the padded plane; interior samples are left alone
-__global__ void k_pad(int16_t *__restrict__ act, int stride, int w, int h, int pad)
+// Border replication of all three planes in ONE launch that only touches the border (xeve_picbuf_expand,
+// src_base/xeve_util.c:190-248).  One thread writes one aligned group of 4 samples (an 8-byte store): groups of the rows above /
+// below the picture copy (or, in the corners, broadcast) from the first / last active row, groups of the left / right strips
+// broadcast the edge sample of their row.  Plane widths and paddings are multiples of 4 samples, strides multiples of 64 and the
+// active origin is 16-byte aligned (xb200_pic_create), so every group is aligned.
+struct PadArgs {
+    int16_t *act[3];
+    int      s[3], w[3], h[3], pad[3];
+    int      first[4]; // first group index of plane 0, 1, 2 and the total
+};
+__host__ __device__ inline int pad_plane_groups(int w, int h, int pad) { return 2 * pad * ((w + 2 * pad) >> 2) + h * 2 * (pad >> 2); }
+__global__ void __launch_bounds__(256) k_pad3(const PadArgs a)
 {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x) - pad, y = (int)blockIdx.y - pad;
-    if(x >= w + pad) return;
-    if(x >= 0 && x < w && y >= 0 && y < h) return;
-    const int sx = min(max(x, 0), w - 1), sy = min(max(y, 0), h - 1);
-    act[(ptrdiff_t)y * stride + x] = act[(ptrdiff_t)sy * stride + sx];
+    int g = blockIdx.x * 256 + threadIdx.x;
+    if(g >= a.first[3]) return;
+    const int k = g >= a.first[2] ? 2 : (g >= a.first[1] ? 1 : 0);
+    g -= a.first[k];
+    const int w = a.w[k], h = a.h[k], pad = a.pad[k], stride = a.s[k], gpr = (w + 2 * pad) >> 2, gps = pad >> 2;
+    int16_t  *act = a.act[k];
+    int       x, y;
+    if(g < 2 * pad * gpr) { // rows above / below the picture
+        const int row = g / gpr;
+        y = row < pad ? row - pad : h + (row - pad);
+        x = (g % gpr) * 4 - pad;
+    }
+    else {                  // left / right strips of an active row
+        g -= 2 * pad * gpr;
+        y = g / (2 * gps);
+        const int c = g % (2 * gps);
+        x = c < gps ? c * 4 - pad : w + (c - gps) * 4;
+    }
+    const int16_t *srow = act + (ptrdiff_t)min(max(y, 0), h - 1) * stride;
+    uint2          v;
+    if(x >= 0 && x < w) v = *reinterpret_cast<const uint2 *>(srow + x); // above / below the active columns: copy
+    else {
+        const uint32_t e = (uint16_t)srow[x < 0 ? 0 : w - 1];
+        v.x = v.y = e | (e << 16);
+    }
+    *reinterpret_cast<uint2 *>(act + (ptrdiff_t)y * stride + x) = v;
 }
 
 // ---- distortion probes: one warp per item, blocks addressed inside device pictures -------------------------
