@@ -583,3 +583,24 @@ def test_intra_neighbours_match_oracle_and_reference(w, h, seed, cip):
     with pytest.raises(api.Xb200Error):
         hp.intra_nbr(pic, bad, ms, mi, ws, hs, cip, elems)
     hp.close()
+
+
+@pytest.mark.skipif(not rh.available(), reason="needs oracle/_ref to trace a live encode")
+@pytest.mark.parametrize("name,preset,frames,extra,override,pic_hi", [
+    ("2160p10", "fast", 6, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2)), 2),   # 10-bit input
+    ("cif", "fast", 8, "rdoq=0;qp=27", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)]), 2),        # plain quantiser, lower QP
+    ("cif", "fast", 8, "bframes=0;inter_slice_type=1", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)]), 3),  # low delay, P slices
+    ("cif", "medium", 8, "qp=40", dict(w=176, h=144, squares=[(32, 20, 30, 3, 2)]), 2),              # high QP: many all-zero blocks
+])
+def test_intra_and_deblock_other_configs(name, preset, frames, extra, override, pic_hi):
+    """intra analysis and the loop filter on other encoder configurations, against the reference's in-situ results"""
+    td = tracedata.live_intra(name, frames, 0, pic_hi, preset, extra, **override)
+    assert len(td.intra) > 100
+    _gpu_intra(td)
+    pics = tracedata.live_df(name, frames, 0, pic_hi, preset, extra, **override)
+    h, w = pics[0]["pre"][0].shape
+    hp = api.Hotpath(api.make_seq(w, h))
+    for d in pics:
+        act, _ = _gpu_deblock(hp, d)
+        assert all(np.array_equal(g, e) for g, e in zip(act, d["post"]))
+    hp.close()

@@ -251,3 +251,23 @@ def test_oracle_intra_neighbours_match_reference():
         assert np.array_equal(got_side, exp_side)
         assert np.array_equal(got_it["avail"], exp_it["avail"]) and np.array_equal(got_it["mpm"], exp_it["mpm"])
         assert len(np.unique(got_it["avail"])) > 8
+
+
+OTHER_CONFIGS = [
+    ("2160p10", "fast", 6, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2)), 2),   # 10-bit input
+    ("cif", "fast", 8, "rdoq=0;qp=27", dict(tracedata.QCIF), 2),                                     # plain quantiser, lower QP
+    ("cif", "fast", 8, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF), 3),                     # low delay, P slices
+    ("cif", "medium", 8, "qp=40", dict(tracedata.QCIF), 2),                                          # high QP: many all-zero blocks
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,preset,frames,extra,override,pic_hi", OTHER_CONFIGS)
+def test_oracle_intra_and_deblock_other_configs(name, preset, frames, extra, override, pic_hi):
+    override = {k: v for k, v in override.items() if k != "n"}
+    td = tracedata.live_intra(name, frames, 0, pic_hi, preset, extra, **override)
+    assert len(td.intra) > 100
+    _oracle_intra(td)
+    for d in tracedata.live_df(name, frames, 0, pic_hi, preset, extra, **override):
+        got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+        assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
