@@ -5,8 +5,8 @@
 // CABAC syntax of src_base/xeve_eco.c:793-905 (cbf), 1104-1121 (intra_dir), run-length coefficients.
 //
 // One kernel instance per CU size (all block dimensions compile-time).  A TEAM owns a CU from the mode ranking to the final
-// bit count: one warp for 4x4 .. 16x16 CUs (four teams per CTA, warp-synchronous, no block barriers), 128 threads for 32x32
-// and 64x64 -- the team transforms / parallel RDOQ of xb200_residue2.cuh.  Everything stays in shared memory: original
+// bit count: one warp for CUs up to 32x32 (four teams per CTA, warp-synchronous, no block barriers: the serial coder sections of
+// one team overlap the transforms of the others), 128 threads for 64x64 -- the team transforms / parallel RDOQ of xb200_residue2.cuh.  Everything stays in shared memory: original
 // block, reference samples, the quantised levels of the current / best candidate in zig-zag order for the coder.
 // Predictions are never stored: a predictor is two or three shared-memory reads, so each use recomputes it.  The SATD of
 // the five modes is evaluated in parallel, one (mode, 8x8 tile) pair per thread.  CTAs are persistent (the DCT matrix is
@@ -141,8 +141,8 @@ template <int TN, class F> XB_DEV int had_tile_fn(const int16_t *a, int sa, F pr
 }
 
 template <int L2> struct IntraCfg {
-    static constexpr int T     = L2 <= 4 ? 32 : 128;   // (a 256-thread team for 64x64 showed a shared-memory hazard under racecheck)
-    static constexpr int TEAMS = L2 <= 4 ? 4 : 1;
+    static constexpr int T     = L2 <= 5 ? 32 : 128;   // (a 256-thread team for 64x64 showed a shared-memory hazard under racecheck)
+    static constexpr int TEAMS = L2 <= 5 ? 4 : 1;
     static constexpr int CTA   = T * TEAMS;
     static constexpr int N     = 1 << L2, NY = N * N, NCH = NY / 4;
     static constexpr int TILES = L2 == 2 ? 1 : (N / 8) * (N / 8);   // SATD tiles per mode (4x4 CU: one 4x4 tile)
@@ -154,7 +154,6 @@ template <int L2> struct IntraTeam {
     int16_t  org[NY * 3 / 2];              // Y | U | V original block
     int16_t  blk[NY];                      // transform working block
     int16_t  candS[5][NY + 2];             // luma levels of every candidate mode, zig-zag order (+2: lanes on different banks)
-    int16_t  candR[5][NY];                 // reconstruction of every candidate mode
     uint16_t cm_lane[IN_CM_N * 8];         // one model set per candidate lane, [model][lane]
     int64_t  cand_ssd[5];
     int32_t  cand_nnz[5];
@@ -289,7 +288,6 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
                 const int     pr = ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY);
                 const int16_t t = nnz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
                 const int     r = clip3i(0, maxv, t), d = r - M.org[e];
-                M.candR[j][e] = (int16_t)r;
                 ssd += (int64_t)((d * d) >> sh);
             }
             team_sync<T>();
@@ -341,10 +339,25 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
             if(cost_t < cost) { cost = cost_t; best_dist_y = dist_t; best_j = j; }
         }
         const int best_ipd = M.list[best_j], nnz_best0 = M.cand_nnz[best_j];
+        // the winner's levels go out in raster order; its reconstruction is rebuilt from them (cheaper than keeping five)
         for(int e = tt; e < NY; e += T) {
-            g_coef[e] = M.candS[best_j][zz_of(e, L2)];
-            if(g_rec) g_rec[e] = M.candR[best_j][e];
+            const int16_t v = M.candS[best_j][zz_of(e, L2)];
+            g_coef[e] = v;
+            M.blk[e] = v;
         }
+        if(g_rec) {
+            team_sync<T>();
+            if(nnz_best0) {
+                dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
+                inv_dct_t<L2, T>(M.blk, M.TB, tm, bd, tt);
+            }
+            for(int e = tt; e < NY; e += T) {
+                const int     pr = ipred_at(leY, upY, best_ipd, e >> L2, e & (N - 1), dcY);
+                const int16_t t = nnz_best0 ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
+                g_rec[e] = (int16_t)clip3i(0, maxv, t);
+            }
+        }
+        team_sync<T>();
 
         // ---- chroma with the winning luma mode (pintra_residue_rdo mode 1, :153-270); its own bit count is never used ---
         int     nnzc[2] = {0, 0};
