@@ -604,3 +604,36 @@ def test_intra_and_deblock_other_configs(name, preset, frames, extra, override, 
         act, _ = _gpu_deblock(hp, d)
         assert all(np.array_equal(g, e) for g, e in zip(act, d["post"]))
     hp.close()
+
+
+def test_intra_full_size_sample_matches_oracle():
+    """1080p: a random sample of the frame-parallel intra work list (reference samples from the original picture, every CU size
+    of the 32/16/8/4 quad-tree, positions all over the picture) -- CUDA path == oracle, byte for byte"""
+    from xeve_b200.clips import Clip, to_internal10
+    from xeve_b200.worklist import synth_intra
+    w, h = 1920, 1080
+    c = Clip("1080p")
+    planes = [to_internal10(p, c.depth) for p in c.frame(8)]
+    hp = api.Hotpath(api.make_seq(w, h))
+    cur = hp.pic_create(padded=False)
+    hp.pic_upload_s16(cur, *planes)
+    items, states, rates, side, _ = synth_intra(w, h, planes, cur, hp.rdoq_rates, seed=3)
+    rng = np.random.default_rng(9)
+    pick = np.concatenate([rng.permutation(np.nonzero(items["log2_cuw"] == l2)[0])[:n] for l2, n in ((2, 1500), (3, 1000), (4, 500), (5, 200))])
+    sel = items[np.sort(pick)].copy()
+    sel["state_out"] = 1 + np.arange(len(sel))
+    sel, sz, elems = tracedata.intra_slots(sel)
+    st = states[:len(sel) + 1]
+    got, gst, gcoef, grec = hp.analyze_intra(sel, rates, st, side, elems)
+    ora = sel.copy()
+    ora["cur_pic"] = 0
+    pl = (xo.PLANES * 1)()
+    keep = [np.ascontiguousarray(p) for p in planes]
+    pl[0].y, pl[0].u, pl[0].v = (k.ctypes.data for k in keep)
+    pl[0].s_l, pl[0].s_c, pl[0].w_l, pl[0].h_l, pl[0].poc = w, w // 2, w, h, 0
+    exp, est, ecoef, erec = xo.analyze_intra_batch(api.make_seq(w, h), pl, rates, ora, st, side, elems)
+    for f in ("cost", "dist_cu", "ipm", "nnz", "cm_ipm_out"):
+        assert np.array_equal(got[f], exp[f]), f
+    assert np.array_equal(gcoef, ecoef) and np.array_equal(grec, erec) and gst.tobytes() == est.tobytes()
+    assert len(np.unique(got["ipm"][:, 0])) == 5 and (got["nnz"] == 0).all(1).any() and (got["nnz"] != 0).all(1).any()
+    hp.close()

@@ -1,4 +1,5 @@
-"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (last analyze_cu pass only)."""
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel: the last analyze_cu pass (default) or,
+with a second argument `all`, every launch of the file."""
 import collections
 import csv
 import sys
@@ -8,7 +9,7 @@ hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 L = [(r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", "")[:36], float(r[vi]) / 1e3) for r in rows[1:]]
 finals = [i for i, (k, t) in enumerate(L) if k.startswith("k_cu_final")]
-seg = L[finals[-2] + 1:finals[-1] + 1] if len(finals) >= 2 else L
+seg = L[finals[-2] + 1:finals[-1] + 1] if len(finals) >= 2 and len(sys.argv) < 3 else L
 agg = collections.OrderedDict()
 for k, t in seg:
     a = agg.setdefault(k, [0, 0.0])

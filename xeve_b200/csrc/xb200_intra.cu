@@ -91,7 +91,9 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     if((r = to_dev(c, c->b_in_items, items, (size_t)n, XB200_MEM_HOST, &d_items))) return r;
     if((r = to_dev(c, c->b_in_rates, rates, (size_t)n_rates, XB200_MEM_HOST, &d_rates))) return r;
     if((r = to_dev(c, c->b_in_st0, states, (size_t)n_states, XB200_MEM_HOST, &d_st0))) return r;
-    if((r = to_dev(c, c->b_in_st1, states, (size_t)n_states, XB200_MEM_HOST, &d_st1))) return r;
+    if((r = xb200_ensure(c->b_in_st1, (size_t)n_states * sizeof(xb200_sbac) + 64))) return r;   // output states start as a copy of the input
+    d_st1 = static_cast<xb200_sbac *>(c->b_in_st1.p);
+    CK(cudaMemcpyAsync(d_st1, d_st0, (size_t)n_states * sizeof(xb200_sbac), cudaMemcpyDeviceToDevice, c->stream));
     if((r = to_dev(c, c->b_in_side, side, (size_t)side_elems, XB200_MEM_HOST, &d_side))) return r;
     if((r = to_dev(c, c->b_in_order, order.data(), (size_t)n, XB200_MEM_HOST, &d_order))) return r;
     if((r = xb200_ensure(c->b_in_coef, (size_t)elems * 2 + 64))) return r;
