@@ -553,9 +553,13 @@ def _gpu_intra(td):
     return got
 
 
-def test_intra_matches_reference_in_situ():
-    """xb200_analyze_intra == pintra_analyze_cu: golden fixture always, live traces (another preset / QP) with oracle/_ref"""
+def test_intra_matches_reference_in_situ(monkeypatch):
+    """xb200_analyze_intra == pintra_analyze_cu: golden fixture always (through the thread-per-CU kernels and, with
+    XB200_INTRA_SMALL=team, through the team kernels for 4x4 / 8x8 as well), live traces (another preset / QP) with oracle/_ref"""
     _gpu_intra(tracedata.golden_intra())
+    monkeypatch.setenv("XB200_INTRA_SMALL", "team")
+    _gpu_intra(tracedata.golden_intra())
+    monkeypatch.delenv("XB200_INTRA_SMALL")
     if rh.available():
         for kw in (dict(pic_hi=3), dict(pic_hi=1, preset="medium", extra="qp=24")):
             td = tracedata.live_intra(**kw)
@@ -636,4 +640,31 @@ def test_intra_full_size_sample_matches_oracle():
         assert np.array_equal(got[f], exp[f]), f
     assert np.array_equal(gcoef, ecoef) and np.array_equal(grec, erec) and gst.tobytes() == est.tobytes()
     assert len(np.unique(got["ipm"][:, 0])) == 5 and (got["nnz"] == 0).all(1).any() and (got["nnz"] != 0).all(1).any()
+    hp.close()
+
+
+def test_new_operators_edge_cases():
+    """empty work lists are accepted and leave everything untouched; a deblock call without CUs still expands the borders;
+    bad handles / sizes are rejected with the reference's status codes"""
+    w, h = 64, 64
+    hp = api.Hotpath(api.make_seq(w, h))
+    d = tracedata.synth_df(w, h, 5)
+    pic = hp.pic_create(padded=True)
+    hp.pic_upload_s16(pic, *(np.ascontiguousarray(a) for a in d["pre"]))
+    hp.deblock(pic, d["cus"][:0], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"], expand=True)
+    full = hp.pic_download(pic, with_padding=True)
+    for k, (g, e) in enumerate(zip(full, d["pre"])):
+        assert np.array_equal(g, np.pad(e, 144 if k == 0 else 72, mode="edge"))
+    z = np.zeros(0, api.INTRA_ITEM)
+    got, st, coef, rec = hp.analyze_intra(z, np.zeros(1, api.RATES), np.zeros(1, api.SBAC), np.zeros(8, np.int16), 0)
+    assert len(got) == 0
+    it, side = hp.intra_nbr(pic, np.zeros(0, api.NBR_ITEM), d["map_scu"], np.zeros(len(d["map_scu"]), np.int8), w // 4, h // 4, 0, 0)
+    assert len(it) == 0
+    with pytest.raises(api.Xb200Error) as e:
+        hp.deblock(99, d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+    assert e.value.code == api.ERR_INVALID_ARGUMENT
+    bad_pp = d["pp"].copy()
+    bad_pp["w_scu"] = 3
+    with pytest.raises(api.Xb200Error):
+        hp.deblock(pic, d["cus"], bad_pp, d["map_scu"], d["map_refi"], d["map_mv"])
     hp.close()

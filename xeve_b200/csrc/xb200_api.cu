@@ -1024,14 +1024,14 @@ template <int L2> int launch_skip(xb200_ctx *c, const xb200_cu_item *d_items, co
 
 extern "C" {
 
-// cbf decisions of all residue slots.  Small CUs (short bin streams, 92 % of the slots): one coder per LANE; large CUs (long
+// cbf decisions of all residue slots.  Small CUs (8x8: short bin streams, three quarters of the slots): one coder per LANE; large CUs (long
 // streams: the serial critical path matters, not throughput): one coder per warp with ballot-parallel coefficient fetch and
 // register-resident unary runs.  The two grids run concurrently.  XB200_DECIDE=warp / lanes forces one kernel for all sizes.
 static int run_decide(xb200_ctx *c, const xb200_cu_item *d_items, int n_slots, int per_cu, const xb200_sbac *d_in, CuState *d_state,
                       const xb200_residue_item *d_res, const int16_t *d_scr, int64_t elems)
 {
     const char *e = getenv("XB200_DECIDE");
-    int         split = (e && e[0] == 'w') ? 0 : ((e && e[0] == 'l') ? 64 : 16);   // widths <= split go to the lane coder
+    int         split = (e && e[0] == 'w') ? 0 : ((e && e[0] == 'l') ? 64 : 8);    // widths <= split go to the lane coder (8: measured best)
     if(e && e[0] >= '0' && e[0] <= '9') split = atoi(e);
     int r;
     if((r = fork_streams(c))) return r;

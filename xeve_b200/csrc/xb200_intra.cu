@@ -105,7 +105,7 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for(int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
     {   // 4x4 and 8x8 CUs: one thread per CU (XB200_INTRA_SMALL=team selects the warp-per-CU kernels instead; identical results)
-        static const char *e = getenv("XB200_INTRA_SMALL");
+        const char *e = getenv("XB200_INTRA_SMALL");
         if(e && e[0] == 't') {
             if((r = launch_intra<2>(c, d_items, d_order + first[0], cnt[0], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
             if((r = launch_intra<3>(c, d_items, d_order + first[1], cnt[1], d_rates, d_st0, d_st1, d_side, d_coef, d_rec))) return r;
