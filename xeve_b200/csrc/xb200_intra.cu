@@ -19,7 +19,7 @@ int launch_intra(xb200_ctx *c, xb200_intra_item *d_items, const int32_t *d_order
     const int teams_needed = (cnt + Cf::TEAMS - 1) / Cf::TEAMS;
     const int resident = L2 <= 4 ? 148 * 8 : (L2 == 5 ? 148 * 2 : 148 * 2);   // persistent CTAs: a few per SM
     const int grid = teams_needed < resident ? teams_needed : resident;
-    k_intra<L2><<<grid, Cf::CTA, intra_smem<L2>(), c->side[L2 >= 3 ? (L2 - 3 > 3 ? 3 : L2 - 3) : 0]>>>(c->d_pics, d_items, d_order, cnt, d_rates, d_st0,
+    k_intra<L2><<<grid, Cf::CTA, intra_smem<L2>(), c->side[L2 <= 3 ? 0 : L2 - 3]>>>(c->d_pics, d_items, d_order, cnt, d_rates, d_st0,
                                                                                                      d_st1, d_side, d_coef, d_rec, c->d_tm64, c->sq);
     c->launches++;
     CK(cudaGetLastError());
