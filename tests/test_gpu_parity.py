@@ -507,7 +507,7 @@ def test_deblock_matches_reference_in_situ():
     hp.close()
 
 
-@pytest.mark.parametrize("w,h,seed", [(64, 64, 0), (200, 136, 1), (1920, 1080, 2)])
+@pytest.mark.parametrize("w,h,seed", [(64, 64, 0), (200, 136, 1), (1920, 1080, 2), (3840, 2160, 3)])
 def test_deblock_matches_oracle_synthetic(w, h, seed):
     """random quad-trees down to 4x4 with 30 % intra CUs (long chroma runs), random strengths, up to full 1080p"""
     d = tracedata.synth_df(w, h, seed, intra_frac=0.3)
@@ -610,13 +610,14 @@ def test_intra_and_deblock_other_configs(name, preset, frames, extra, override, 
     hp.close()
 
 
-def test_intra_full_size_sample_matches_oracle():
-    """1080p: a random sample of the frame-parallel intra work list (reference samples from the original picture, every CU size
-    of the 32/16/8/4 quad-tree, positions all over the picture) -- CUDA path == oracle, byte for byte"""
+@pytest.mark.parametrize("clip,w,h", [("1080p", 1920, 1080), ("2160p10", 3840, 2160)])
+def test_intra_full_size_sample_matches_oracle(clip, w, h):
+    """BASELINE.json sizes (1080p 8-bit, 2160p 10-bit input): a random sample of the frame-parallel intra work list (reference
+    samples from the original picture, every CU size of the 32/16/8/4 quad-tree, positions all over the picture) -- CUDA path ==
+    oracle, byte for byte"""
     from xeve_b200.clips import Clip, to_internal10
     from xeve_b200.worklist import synth_intra
-    w, h = 1920, 1080
-    c = Clip("1080p")
+    c = Clip(clip)
     planes = [to_internal10(p, c.depth) for p in c.frame(8)]
     hp = api.Hotpath(api.make_seq(w, h))
     cur = hp.pic_create(padded=False)
