@@ -320,7 +320,10 @@ def run_b200(args, rank, world, dist):
     frame_bytes = W * H * 3 // 2 * bps
     h2d = frame_bytes + fw.me_uni.nbytes + bi_mc.nbytes + fw.bi_cur.nbytes + fw.side_off.nbytes + me_bi_in.nbytes + 2 * fw.side_elems \
         + res_in.nbytes + fw.rates.nbytes
-    d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + 2 * fw.res_elems
+    # coefficient planes travel compacted (only planes with a non-zero level): count what really crosses the bus
+    wsq = res_out["mc"]["w"].astype(np.int64) ** 2
+    coef_bytes = int(2 * (np.stack([wsq, wsq // 4, wsq // 4], 1) * (res_out["nnz"] != 0)).sum()) + 16 * int((res_out["nnz"] != 0).sum())
+    d2h = fw.me_uni.nbytes + 2 * fw.side_elems + me_bi_in.nbytes + res_in.nbytes + coef_bytes
 
     if world > 1:
         t_dev, t_e2e = xd.max_over_ranks([t_dev, t_e2e], dist, device="cuda")

@@ -382,7 +382,10 @@ XB200_API int xb200_itdq(xb200_ctx *c, const xb200_tq_item *items, int64_t n, in
 XB200_API int xb200_recon(xb200_ctx *c, const xb200_tq_item *items, int64_t n, const int16_t *resi, const int16_t *pred,
                           int16_t *rec, int64_t elems, int mem);
 /* rec may be NULL: the per-candidate reconstruction is then only used for dist_rec and not stored -- the
- * reference itself recomputes the reconstruction of the winning mode (src_base/xeve_pinter.c:2006-2038). */
+ * reference itself recomputes the reconstruction of the winning mode (src_base/xeve_pinter.c:2006-2038).
+ * With XB200_MEM_HOST the coefficient planes are read back compacted: a plane whose nnz[] is 0 is not copied and the caller's
+ * `coef` is left untouched there (the reference never reads the coefficients of such a plane); with XB200_MEM_DEVICE every plane
+ * is written. */
 XB200_API int xb200_residue(xb200_ctx *c, xb200_residue_item *items, int64_t n, const xb200_rates *rates,
                             int64_t n_rates, int16_t *coef, int16_t *rec, int64_t elems, int mem);
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <chrono>
 
 #include "xb200_ctx.h"
 #include "xb200_me.cuh"
@@ -75,7 +76,16 @@ int sync_pics(xb200_ctx *c)
 
 int finish(xb200_ctx *c) { return xb200_finish(c); }
 
-__global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
+// Arguments of the caller's records are checked here, on the device, when `validate` is set (host-buffer calls): a host loop over
+// the records costs more than the search of a small picture (1.3 ms per 20 MB of records).  bins[6] != 0: invalid argument.
+struct BinCheck {
+    const PicDev *pics;
+    int           n_pics, validate, have_side, n_rates;
+    long long     side_elems, elems;
+};
+XB_DEV bool bin_pic_ok(const BinCheck &ck, int h) { return h >= 0 && h < ck.n_pics && ck.pics[h].valid; }
+
+__global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins, BinCheck ck)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     int       key = 5, margin = 0; // key 4 = unsupported shape, 5 = out of range
@@ -83,6 +93,12 @@ __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t
         const xb200_me_item &it = items[i];
         const int            l2 = it.log2_cuw;
         key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : (l2 == 0 ? 5 : 4); // log2 0: slot left empty by the CU pipeline
+        if(ck.validate && l2 != 0) {
+            const bool bad = !bin_pic_ok(ck, it.cur_pic) || !bin_pic_ok(ck, it.ref_pic) || ck.pics[it.ref_pic].pad_l == 0 || it.gop_size <= 0 ||
+                             (it.bi && (it.org_bi_off < 0 || (it.org_bi_off & 3) || !ck.have_side ||
+                                        (long long)it.org_bi_off + (1ll << (it.log2_cuw + it.log2_cuh)) > ck.side_elems));
+            if(bad) { key = 5; atomicOr(&bins[6], 1); }
+        }
         int d = it.poc - it.ref_poc;
         d     = d < 0 ? -d : d;
         int dyn = (it.max_search_range * d + (it.gop_size >> 1)) / max(1, it.gop_size);
@@ -104,6 +120,40 @@ __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t
         }
         base = __shfl_sync(0xffffffffu, base, leader);
         if(key == k && k < 4) order[(size_t)k * n + base + __popc(m & ((1u << lane) - 1))] = i;
+    }
+}
+
+// Coefficient read-back of xb200_residue with host buffers: only the planes that hold a non-zero level travel.  A warp per item
+// reserves room for each non-zero plane in the compact buffer (atomic bump), records {destination in the caller's buffer, place in
+// the compact buffer, size} and copies the plane.
+struct PlaneRef {
+    long long dst;          // element offset in the caller's coefficient buffer
+    unsigned  src, elems;   // element offset in the compact buffer, plane size
+};
+__global__ void k_compact_planes(const xb200_residue_item *__restrict__ items, int n, const int16_t *__restrict__ coef,
+                                 int16_t *__restrict__ compact, PlaneRef *__restrict__ list, unsigned long long *__restrict__ total,
+                                 int *__restrict__ count)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(i >= n) return;
+    const xb200_residue_item &it = items[i];
+    const int ny = it.mc.w * it.mc.h, nc = ny >> 2;
+    if(ny == 0) return; // empty slot
+#pragma unroll
+    for(int c = 0; c < 3; c++) {
+        if(it.nnz[c] == 0) continue;
+        const long long dst = it.out_off + (c == 0 ? 0 : (c == 1 ? ny : ny + nc));
+        const int       sz = c ? nc : ny;
+        unsigned        at = 0;
+        if(lane == 0) {
+            at = (unsigned)atomicAdd(total, (unsigned long long)sz);
+            const int k = atomicAdd(count, 1);
+            list[k].dst = dst; list[k].src = at; list[k].elems = (unsigned)sz;
+        }
+        at = __shfl_sync(0xffffffffu, at, 0);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(coef + dst);   // plane sizes and offsets are even
+        uint32_t       *out = reinterpret_cast<uint32_t *>(compact + at);
+        for(int e = lane; e < (sz >> 1); e += 32) out[e] = src[e];
     }
 }
 
@@ -304,6 +354,9 @@ void xb200_destroy(xb200_ctx *c)
                      &c->b_cu_me, &c->b_cu_res, &c->b_cu_mc, &c->b_cu_cur, &c->b_cu_off, &c->b_cu_side, &c->b_cu_order, &c->b_cu_coef,
                      &c->b_cu_rec, &c->b_cu_nzr, &c->b_cu_nzl, &c->b_cu_meta})
         if(b->p) cudaFree(b->p);
+    for(DevBuf *b : {&c->b_compact, &c->b_coff})
+        if(b->p) cudaFree(b->p);
+    if(c->h_pin) cudaFreeHost(c->h_pin);
     if(c->d_pics) cudaFree(c->d_pics);
     if(c->d_tm64) cudaFree(c->d_tm64);
     if(c->d_err) cudaFree(c->d_err);
@@ -700,15 +753,6 @@ int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side,
 {
     if(!c || n < 0 || (n && !items) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
-    if(mem == XB200_MEM_HOST)
-        for(int64_t i = 0; i < n; i++) {
-            const xb200_me_item &it = items[i];
-            if(!pic_ok(c, it.cur_pic) || !pic_ok(c, it.ref_pic) || !c->pics[it.ref_pic].padded || it.gop_size <= 0 ||
-               (it.bi && (it.org_bi_off < 0 || (it.org_bi_off & 3) || !side ||
-                          it.org_bi_off + (1 << (it.log2_cuw + it.log2_cuh)) > side_elems)))
-                return XB200_ERR_INVALID_ARGUMENT;
-            if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 3 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
-        }
     if(c->sq.me_complexity > 1) return XB200_ERR_UNSUPPORTED; // me_raster (placebo) is not offloaded
     if(n == 0) return XB200_OK;
     int r = sync_pics(c);
@@ -721,11 +765,14 @@ int xb200_me(xb200_ctx *c, xb200_me_item *items, int64_t n, const int16_t *side,
     int32_t *order = static_cast<int32_t *>(c->b_order.p);
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int) * 16, c->stream));
-    k_me_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins);
+    // host-buffer calls: the records are validated by the binning kernel (invalid picture handles, org_bi ranges -> bins[6])
+    const BinCheck ck = {c->d_pics, (int)c->pics.size(), mem == XB200_MEM_HOST, side != nullptr, 0, (long long)side_elems, 0};
+    k_me_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins, ck);
     c->launches++;
     int bins[16];
     CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if(bins[6]) return XB200_ERR_INVALID_ARGUMENT;
     if(bins[4]) return XB200_ERR_UNSUPPORTED;
     // largest blocks first: they are the long poles of the launch sequence
     if((r = fork_streams(c))) return r;
@@ -950,17 +997,11 @@ static int residue_impl(xb200_ctx *c, xb200_residue_item *items, int64_t n, cons
 {
     if(!c || n < 0 || (n && (!items || !coef || !rates)) || n > (1 << 28)) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
-    if(mem == XB200_MEM_HOST)
-        for(int64_t i = 0; i < n; i++) {
-            const xb200_residue_item &it = items[i];
-            int r = check_mc(c, it.mc);
-            if(r) return r;
-            if(it.mc.w != it.mc.h || it.mc.w < 8 || (it.mc.w & (it.mc.w - 1))) return XB200_ERR_UNSUPPORTED;
-            if(!pic_ok(c, it.cur_pic) || it.rate_idx < 0 || it.rate_idx >= n_rates || it.out_off < 0 ||
-               it.out_off + it.mc.w * it.mc.h * 3 / 2 > elems)
-                return XB200_ERR_INVALID_ARGUMENT;
-        }
+    static const bool timing = getenv("XB200_TIMING") != nullptr;   // per-phase wall times of the host-buffer path on stderr
+    auto              now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double            t_ph[8] = {now(), 0, 0, 0, 0, 0, 0, 0};
     if(n == 0) return XB200_OK;
+    t_ph[1] = now();
     int r = sync_pics(c);
     if(r) return r;
     xb200_residue_item *d_items;
@@ -980,12 +1021,15 @@ static int residue_impl(xb200_ctx *c, xb200_residue_item *items, int64_t n, cons
     int32_t *order = static_cast<int32_t *>(c->b_order.p);
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int) * 16, c->stream));
-    k_res_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins);
+    // host-buffer calls: the records are validated by the binning kernel (bins[6]: invalid argument, bins[7] / bins[4]: unsupported)
+    const BinCheck ck = {c->d_pics, (int)c->pics.size(), mem == XB200_MEM_HOST, 0, (int)n_rates, 0, (long long)elems};
+    k_res_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, order, c->d_bins, ck);
     c->launches++;
     int bins[16];
     CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if(bins[4]) return XB200_ERR_UNSUPPORTED;
+    if(bins[6]) return XB200_ERR_INVALID_ARGUMENT;
+    if(bins[4] || bins[7]) return XB200_ERR_UNSUPPORTED;
     if((r = fork_streams(c))) return r;
     if((r = launch_residue2<6>(c, d_items, order + 3 * n, bins[3], d_rates, d_coef, d_rec, pred_dev))) return r;
     if((r = launch_residue2<5>(c, d_items, order + 2 * n, bins[2], d_rates, d_coef, d_rec, pred_dev))) return r;
@@ -994,8 +1038,45 @@ static int residue_impl(xb200_ctx *c, xb200_residue_item *items, int64_t n, cons
     if((r = join_streams(c))) return r;
     CK(cudaEventRecord(c->ev1, c->stream));
     if((r = to_host(c, items, d_items, (size_t)n, mem))) return r;
-    if((r = to_host(c, coef, d_coef, (size_t)elems, mem))) return r;
     if(rec && (r = to_host(c, rec, d_rec, (size_t)elems, mem))) return r;
+    if(mem == XB200_MEM_HOST) {
+        // coefficient read-back, compacted: a plane without a non-zero level (94 % of the bytes at the bench's QP) is not copied and
+        // the caller's buffer is left untouched there -- the reference never reads coefficients of a plane whose nnz is 0.  The
+        // device packs the non-zero planes and lists them; the host only walks that list (no pass over the records).
+        if((r = ensure(c->b_compact, (size_t)elems * 2 + 64))) return r;
+        if((r = ensure(c->b_coff, (size_t)3 * n * sizeof(PlaneRef) + 64))) return r;
+        int16_t  *d_compact = static_cast<int16_t *>(c->b_compact.p);
+        PlaneRef *d_list = static_cast<PlaneRef *>(c->b_coff.p);
+        CK(cudaMemsetAsync(c->d_bins + 12, 0, sizeof(int) * 4, c->stream));
+        k_compact_planes<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(d_items, (int)n, d_coef, d_compact, d_list,
+                                                                        reinterpret_cast<unsigned long long *>(c->d_bins + 12), c->d_bins + 14);
+        c->launches++;
+        struct { unsigned long long total; int cnt, pad; } hdr;
+        CK(cudaMemcpyAsync(&hdr, c->d_bins + 12, sizeof(hdr), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        t_ph[2] = now();
+        if(hdr.cnt) {
+            const size_t need = (size_t)hdr.total * 2 + (size_t)hdr.cnt * sizeof(PlaneRef) + 64;
+            if(c->h_pin_cap < need) {
+                if(c->h_pin) cudaFreeHost(c->h_pin);
+                c->h_pin = nullptr; c->h_pin_cap = 0;
+                const size_t want = need + need / 2 + 4096;
+                CK(cudaHostAlloc(&c->h_pin, want, cudaHostAllocDefault));
+                c->h_pin_cap = want;
+            }
+            PlaneRef *h_list = static_cast<PlaneRef *>(c->h_pin);
+            int16_t  *h_data = reinterpret_cast<int16_t *>(h_list + hdr.cnt);
+            CK(cudaMemcpyAsync(h_list, d_list, (size_t)hdr.cnt * sizeof(PlaneRef), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(h_data, d_compact, (size_t)hdr.total * 2, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            t_ph[3] = now();
+            for(int k = 0; k < hdr.cnt; k++) memcpy(coef + h_list[k].dst, h_data + h_list[k].src, (size_t)h_list[k].elems * 2);
+        }
+        t_ph[4] = now();
+        if(timing)
+            fprintf(stderr, "xb200_residue host path: upload + kernels + records back %.3f | list + compact copy %.3f | scatter of %d planes %.3f ms\n",
+                    t_ph[2] - t_ph[1], t_ph[3] > 0 ? t_ph[3] - t_ph[2] : 0.0, hdr.cnt, t_ph[3] > 0 ? t_ph[4] - t_ph[3] : 0.0);
+    }
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);

@@ -36,6 +36,9 @@ struct xb200_ctx {
     DevBuf           b_df; // deblocking: per-SCU edge flags
     DevBuf           b_in_items, b_in_rates, b_in_st0, b_in_st1, b_in_side, b_in_coef, b_in_rec, b_in_order; // intra analysis
     bool             intra_ready = false;
+    void            *h_pin = nullptr;   // library-owned pinned staging (compacted coefficient read-back)
+    size_t           h_pin_cap = 0;
+    DevBuf           b_compact, b_coff;
     DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
     DevBuf           b_cu_items, b_cu_rates, b_cu_state, b_cu_me, b_cu_res, b_cu_mc, b_cu_cur, b_cu_off, b_cu_side, b_cu_order,
                      b_cu_coef, b_cu_rec, b_cu_nzr, b_cu_nzl, b_cu_meta; // CU pipeline

@@ -503,13 +503,30 @@ __global__ void __launch_bounds__(Res2Cfg<L2>::CTA) k_residue2(const PicDev *__r
 }
 
 #ifndef XB200_DEVICE_FUNCS_ONLY
-__global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins)
+// CK: the argument checks of a host-buffer call, done here instead of in a host loop over the records (see BinCheck, xb200_api.cu):
+// bins[6] invalid argument, bins[7] unsupported shape
+template <class CK>
+__global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins, CK ck)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int       key = 5;
     if(i < n) {
-        const int w = items[i].mc.w;
-        key = (items[i].mc.h == w) ? (w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : w == 64 ? 3 : (w == 0 ? 5 : 4)) : 4; // w 0: empty slot
+        const xb200_residue_item &it = items[i];
+        const int w = it.mc.w;
+        key = (it.mc.h == w) ? (w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : w == 64 ? 3 : (w == 0 ? 5 : 4)) : 4; // w 0: empty slot
+        if(ck.validate && w != 0) {
+            auto pic_ok = [&](int h) { return h >= 0 && h < ck.n_pics && ck.pics[h].valid; };
+            const int h = it.mc.h;
+            bool unsup = w < 4 || h < 4 || w > 64 || h > 64 || (w & 3) || (h & 3) || w != h || w < 8 || (w & (w - 1));
+            bool bad = it.mc.refi[0] < 0 && it.mc.refi[1] < 0;
+#pragma unroll
+            for(int l = 0; l < 2; l++)
+                if(it.mc.refi[l] >= 0 && (!pic_ok(it.mc.ref_pic[l]) || ck.pics[it.mc.ref_pic[l]].pad_l == 0)) bad = true;
+            bad = bad || !pic_ok(it.cur_pic) || it.rate_idx < 0 || it.rate_idx >= ck.n_rates || it.out_off < 0 ||
+                  it.out_off + (long long)w * h * 3 / 2 > ck.elems;
+            if(unsup) { key = 5; atomicOr(&bins[7], 1); }
+            else if(bad) { key = 5; atomicOr(&bins[6], 1); }
+        }
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll
