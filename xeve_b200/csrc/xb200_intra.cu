@@ -8,6 +8,45 @@
 
 namespace {
 
+struct IntraCheck {
+    const PicDev *pics;
+    int           n_pics, w, h, n_rates;
+    long long     n_states, side_elems, elems;
+};
+// size-class binning (order[k * n + ...] = indices of the CUs with log2 size k + 2, warp-aggregated) and argument checks:
+// bins[5] unsupported shape, bins[6] invalid argument
+__global__ void k_intra_bin(const xb200_intra_item *__restrict__ items, int n, int32_t *__restrict__ order, int *__restrict__ bins, IntraCheck ck)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int       key = 7;
+    if(i < n) {
+        const xb200_intra_item &it = items[i];
+        const int l2 = it.log2_cuw;
+        if(l2 != it.log2_cuh || l2 < 2 || l2 > 6) { key = 7; atomicOr(&bins[5], 1); }
+        else {
+            const long long sz = (3ll << (2 * l2)) >> 1;
+            const bool bad = it.cur_pic < 0 || it.cur_pic >= ck.n_pics || !ck.pics[it.cur_pic].valid || it.x < 0 || it.y < 0 ||
+                             it.x + (1 << l2) > ck.w || it.y + (1 << l2) > ck.h || it.slice_type > 2 || it.rate_idx < 0 ||
+                             it.rate_idx >= ck.n_rates || it.state_in < 0 || it.state_in >= ck.n_states || it.state_out < 0 ||
+                             it.state_out >= ck.n_states || it.nb_off < 0 || it.nb_off + 8 * (1 << l2) + 6 > ck.side_elems || it.out_off < 0 ||
+                             it.out_off + sz > ck.elems || it.ctx_skip > 1 || it.ctx_pred_mode > 2 || it.mpm[0] > 4 || it.mpm[1] > 4 ||
+                             it.mpm[2] > 4 || it.mpm[3] > 4 || it.mpm[4] > 4;
+            if(bad) { key = 7; atomicOr(&bins[6], 1); }
+            else key = l2 - 2;
+        }
+    }
+#pragma unroll
+    for(int k = 0; k < 5; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, key == k);
+        if(m == 0) continue;
+        const int leader = __ffs(m) - 1;
+        int       base = 0;
+        if(lane == leader) base = atomicAdd(&bins[k], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if(key == k) order[(size_t)k * n + base + __popc(m & ((1u << lane) - 1))] = i;
+    }
+}
+
 template <int L2> constexpr int intra_smem() { return 8192 + IntraCfg<L2>::TEAMS * (int)sizeof(IntraTeam<L2>); }
 
 template <int L2>
@@ -60,26 +99,6 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
         return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     if(n == 0) return XB200_OK;
-    int cnt[5] = {0, 0, 0, 0, 0}; // per CU size 4x4 .. 64x64
-    for(int64_t i = 0; i < n; i++) {
-        const xb200_intra_item &it = items[i];
-        if(it.log2_cuw != it.log2_cuh || it.log2_cuw < 2 || it.log2_cuw > 6) return XB200_ERR_UNSUPPORTED;
-        const int64_t sz = ((int64_t)3 << (2 * it.log2_cuw)) >> 1;
-        if(!pic_ok(c, it.cur_pic) || it.x < 0 || it.y < 0 || it.x + (1 << it.log2_cuw) > c->seq.w || it.y + (1 << it.log2_cuh) > c->seq.h ||
-           it.slice_type > 2 || it.rate_idx < 0 || it.rate_idx >= n_rates || it.state_in < 0 || it.state_in >= n_states ||
-           it.state_out < 0 || it.state_out >= n_states || it.nb_off < 0 || it.nb_off + 8 * (1 << it.log2_cuw) + 6 > side_elems ||
-           it.out_off < 0 || it.out_off + sz > elems || it.ctx_skip > 1 || it.ctx_pred_mode > 2 || it.mpm[0] > 4 || it.mpm[1] > 4 ||
-           it.mpm[2] > 4 || it.mpm[3] > 4 || it.mpm[4] > 4)
-            return XB200_ERR_INVALID_ARGUMENT;
-        cnt[it.log2_cuw - 2]++;
-    }
-    std::vector<int32_t> order((size_t)n);
-    int first[5];
-    {
-        int pos[5], acc = 0;
-        for(int k = 0; k < 5; k++) { first[k] = pos[k] = acc; acc += cnt[k]; }
-        for(int64_t i = 0; i < n; i++) order[(size_t)pos[items[i].log2_cuw - 2]++] = (int32_t)i;
-    }
     int r;
     if((r = intra_init(c))) return r;
     if((r = xb200_sync_pics(c))) return r;
@@ -95,10 +114,24 @@ int xb200_analyze_intra(xb200_ctx *c, xb200_intra_item *items, int64_t n, const 
     d_st1 = static_cast<xb200_sbac *>(c->b_in_st1.p);
     CK(cudaMemcpyAsync(d_st1, d_st0, (size_t)n_states * sizeof(xb200_sbac), cudaMemcpyDeviceToDevice, c->stream));
     if((r = to_dev(c, c->b_in_side, side, (size_t)side_elems, XB200_MEM_HOST, &d_side))) return r;
-    if((r = to_dev(c, c->b_in_order, order.data(), (size_t)n, XB200_MEM_HOST, &d_order))) return r;
+    if((r = xb200_ensure(c->b_in_order, (size_t)5 * n * sizeof(int32_t) + 64))) return r;
+    d_order = static_cast<int32_t *>(c->b_in_order.p);
     if((r = xb200_ensure(c->b_in_coef, (size_t)elems * 2 + 64))) return r;
     if(rec && (r = xb200_ensure(c->b_in_rec, (size_t)elems * 2 + 64))) return r;
     int16_t *d_coef = static_cast<int16_t *>(c->b_in_coef.p), *d_rec = rec ? static_cast<int16_t *>(c->b_in_rec.p) : nullptr;
+    // the records are checked and binned by CU size on the device (a host pass over 170 k records costs more than the 4x4 kernel)
+    CK(cudaMemsetAsync(c->d_bins, 0, sizeof(int) * 16, c->stream));
+    const IntraCheck ck = {c->d_pics, (int)c->pics.size(), c->seq.w, c->seq.h, (int)n_rates, (long long)n_states, (long long)side_elems,
+                           (long long)elems};
+    k_intra_bin<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_items, (int)n, d_order, c->d_bins, ck);
+    c->launches++;
+    int bins[16];
+    CK(cudaMemcpyAsync(bins, c->d_bins, sizeof(bins), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if(bins[5]) return XB200_ERR_UNSUPPORTED;
+    if(bins[6]) return XB200_ERR_INVALID_ARGUMENT;
+    const int cnt[5] = {bins[0], bins[1], bins[2], bins[3], bins[4]};
+    const int first[5] = {0, (int)n, 2 * (int)n, 3 * (int)n, 4 * (int)n};
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(d_coef, 0, (size_t)elems * 2, c->stream));
     // the five size classes run concurrently on the side streams (fork / join around the caller-visible stream)
