@@ -669,3 +669,31 @@ def test_new_operators_edge_cases():
     with pytest.raises(api.Xb200Error):
         hp.deblock(pic, d["cus"], bad_pp, d["map_scu"], d["map_refi"], d["map_mv"])
     hp.close()
+
+
+@pytest.mark.skipif(not rh.available(), reason="needs oracle/_ref to trace a live encode")
+def test_full_size_1080p_in_situ():
+    """BASELINE.json configs[1] size, straight against the reference: the first two pictures of the 1080p clip encoded by the
+    reference (low delay) -- all 172 k pintra_analyze_cu calls, all 42 k xeve_pinter_analyze_cu calls and both loop-filter passes,
+    recomputed on the device from the traced inputs: costs (IEEE doubles), modes, coder states, coefficient / reconstruction hashes,
+    deblocked pictures"""
+    td = tracedata.live_trace("1080p", frames=2, pic_lo=0, pic_hi=1, preset="fast", mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU,
+                              extra="bframes=0")
+    td.intra = td.live.intra.copy()
+    assert len(td.intra) > 150000 and len(td.cu) > 40000
+    hp = _upload_trace(td)
+    items, sz, elems = tracedata.intra_slots(td.intra)
+    dev = items.copy()
+    dev["cur_pic"] = hp.handles[items["cur_pic"]]
+    got, st, coef, rec = hp.analyze_intra(dev, td.cu_rates, td.cu_sbac, td.side, elems)
+    tracedata.check_intra_results(got, td.intra, coef, rec, sz, st, td.cu_sbac)
+    cu, sz, elems = tracedata.cu_slots(td.cu)
+    dcu = cu.copy()
+    dcu["cur_pic"] = hp.handles[cu["cur_pic"]]
+    dcu["ref_pic"] = np.where(cu["ref_pic"] >= 0, hp.handles[np.clip(cu["ref_pic"], 0, len(hp.handles) - 1)], -1)
+    gcu, gst, gcoef, grec = hp.analyze_cu(dcu, td.cu_rates, td.cu_sbac, elems)
+    tracedata.check_cu_results(gcu, td.cu, gcoef, grec, sz, gst, td.cu_sbac)
+    for d in tracedata.df_from_trace(td.live):
+        act, _ = _gpu_deblock(hp, d)
+        assert all(np.array_equal(g, e) for g, e in zip(act, d["post"]))
+    hp.close()

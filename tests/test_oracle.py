@@ -271,3 +271,22 @@ def test_oracle_intra_and_deblock_other_configs(name, preset, frames, extra, ove
     for d in tracedata.live_df(name, frames, 0, pic_hi, preset, extra, **override):
         got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
         assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
+
+
+@needs_ref
+def test_oracle_full_size_1080p_in_situ():
+    """BASELINE.json configs[1] size: the first two pictures of the 1080p clip encoded by the reference (low delay, so the second is
+    an inter picture) -- every pintra_analyze_cu call (172 k, CU 4x4 .. 64x64), every xeve_pinter_analyze_cu call (42 k) and both
+    loop-filter passes, reproduced by the oracle from the traced inputs: costs as IEEE doubles, coder states, coefficient and
+    reconstruction hashes, deblocked pictures"""
+    td = tracedata.live_trace("1080p", frames=2, pic_lo=0, pic_hi=1, preset="fast", mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU,
+                              extra="bframes=0")
+    td.intra = td.live.intra.copy()
+    assert len(td.intra) > 150000 and len(td.cu) > 40000
+    _oracle_intra(td)
+    cu, sz, elems = tracedata.cu_slots(td.cu)
+    ocu, ost, ocoef, orec = xo.analyze_cu_batch(td.seq, td.oracle_planes(), td.cu_rates, cu, td.cu_sbac, elems)
+    tracedata.check_cu_results(ocu, td.cu, ocoef, orec, sz, ost, td.cu_sbac)
+    for d in tracedata.df_from_trace(td.live):
+        got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
+        assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))

@@ -177,14 +177,9 @@ def synth_nbr(w, h, seed, n=600):
 DF_GOLDEN = os.path.join(ROOT, "tests", "golden", "df_golden.npz")
 
 
-def live_df(name="cif", frames=20, pic_lo=0, pic_hi=2, preset="fast", extra="", **override):
-    """Deblocking inputs / in-situ results of the traced pictures: list of dicts {pre, post: (Y, U, V) active areas,
-    cus, pp, map_scu, map_refi, map_mv}."""
-    override = override or QCIF
-    c, yuv = clip_yuv(name, frames, **override)
-    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_DF, pic_lo=pic_lo,
-                        pic_hi=pic_hi)
-
+def df_from_trace(tr):
+    """Deblocking inputs / in-situ results of a live trace recorded with rh.TRACE_DF: list of dicts {pre, post: (Y, U, V) active
+    areas, cus, pp, map_scu, map_refi, map_mv}."""
     def act(i):
         p, full = tr.pics[i], tr.plane_views(i)
         pl, pc, w, h = int(p["pad_l"]), int(p["pad_c"]), int(p["w_l"]), int(p["h_l"])
@@ -198,6 +193,15 @@ def live_df(name="cif", frames=20, pic_lo=0, pic_hi=2, preset="fast", extra="", 
         out.append(dict(pre=act(int(r["pre_pic"])), post=act(int(r["post_pic"])), pp=r["pp"].copy(), map_scu=ms, map_refi=mr,
                         map_mv=mm, cus=tr.df_cu[int(r["cu_first"]):int(r["cu_first"] + r["cu_cnt"])].copy(), poc=int(r["poc"])))
     return out
+
+
+def live_df(name="cif", frames=20, pic_lo=0, pic_hi=2, preset="fast", extra="", **override):
+    """Deblocking inputs / in-situ results of the traced pictures (see df_from_trace)."""
+    override = override or QCIF
+    c, yuv = clip_yuv(name, frames, **override)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_DF, pic_lo=pic_lo,
+                        pic_hi=pic_hi)
+    return df_from_trace(tr)
 
 
 def golden_df():
