@@ -273,16 +273,24 @@ def test_oracle_intra_and_deblock_other_configs(name, preset, frames, extra, ove
         assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
 
 
+import os  # noqa: E402
+
+FULL_SIZE = [("1080p", "fast", 150000, 40000)]
+if os.environ.get("XB200_SLOW_TESTS"):  # two more minutes of CPU: BASELINE.json configs[2] (688 961 intra calls, 170 196 inter CU decisions)
+    FULL_SIZE.append(("2160p10", "medium", 600000, 160000))
+
+
 @needs_ref
-def test_oracle_full_size_1080p_in_situ():
-    """BASELINE.json configs[1] size: the first two pictures of the 1080p clip encoded by the reference (low delay, so the second is
-    an inter picture) -- every pintra_analyze_cu call (172 k, CU 4x4 .. 64x64), every xeve_pinter_analyze_cu call (42 k) and both
-    loop-filter passes, reproduced by the oracle from the traced inputs: costs as IEEE doubles, coder states, coefficient and
-    reconstruction hashes, deblocked pictures"""
-    td = tracedata.live_trace("1080p", frames=2, pic_lo=0, pic_hi=1, preset="fast", mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU,
+@pytest.mark.parametrize("clip,preset,min_intra,min_cu", FULL_SIZE)
+def test_oracle_full_size_in_situ(clip, preset, min_intra, min_cu):
+    """BASELINE.json configs[1] size (and configs[2] = 2160p 10-bit medium with XB200_SLOW_TESTS=1): the first two pictures of the clip
+    encoded by the reference (low delay, so the second is an inter picture) -- every pintra_analyze_cu call (172 k at 1080p, CU 4x4 ..
+    64x64), every xeve_pinter_analyze_cu call (42 k) and both loop-filter passes, reproduced by the oracle from the traced inputs:
+    costs as IEEE doubles, coder states, coefficient and reconstruction hashes, deblocked pictures"""
+    td = tracedata.live_trace(clip, frames=2, pic_lo=0, pic_hi=1, preset=preset, mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU,
                               extra="bframes=0")
     td.intra = td.live.intra.copy()
-    assert len(td.intra) > 150000 and len(td.cu) > 40000
+    assert len(td.intra) > min_intra and len(td.cu) > min_cu
     _oracle_intra(td)
     cu, sz, elems = tracedata.cu_slots(td.cu)
     ocu, ost, ocoef, orec = xo.analyze_cu_batch(td.seq, td.oracle_planes(), td.cu_rates, cu, td.cu_sbac, elems)
