@@ -182,3 +182,13 @@ def intra_nbr(planes, items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems, bi
                          _p(np.ascontiguousarray(map_scu, np.uint32)), _p(np.ascontiguousarray(map_ipm, np.int8)), w_scu, h_scu, int(cip),
                          bit_depth, _p(side))
     return items, side
+
+
+def mvp_batch(items, pic, map_scu, map_mv, col0, col1):
+    L = lib()
+    L.xo_mvp_batch.restype = None
+    L.xo_mvp_batch.argtypes = [VP, C.c_int64, VP, VP, VP, VP, VP]
+    items = items.copy()
+    L.xo_mvp_batch(_p(items), len(items), _p(np.ascontiguousarray(pic)), _p(np.ascontiguousarray(map_scu, np.uint32)),
+                   _p(np.ascontiguousarray(map_mv, np.int16)), _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16)))
+    return items

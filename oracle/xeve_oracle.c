@@ -1466,6 +1466,65 @@ void xo_analyze_intra_batch(const xb200_seq *sq, const xo_planes *pl, const xb20
     for(int64_t i = 0; i < n; i++) xo_analyze_intra(sq, pl, rates, &items[i], states, side, coef + items[i].out_off, rec + items[i].out_off);
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * MV-predictor inputs of one CU: xeve_get_avail_inter (src_base/xeve_util.c:652-715, one tile),
+ * xeve_get_motion (:526-573: left / up / up-right spatial candidates or (1,1), colocated MV as the fourth, refi always 0) and
+ * the temporal-direct MVs of xeve_get_mv_dir (:619-650: POC-scaled colocated MV of list 1, C integer division).
+ * ------------------------------------------------------------------------------------------- */
+void xo_mvp(xb200_mvp_item *it, const xb200_mvp_pic *pp, const uint32_t *map_scu, const int16_t *map_mv, const int16_t *col_mv0,
+            const int16_t *col_mv1)
+{
+    const int x = it->x_scu, y = it->y_scu, w = pp->w_scu, h = pp->h_scu;
+    const int scuw = (1 << it->log2_cuw) >> 2, scuh = (1 << it->log2_cuh) >> 2, scup = x + y * w, l = it->lidx;
+#define M_COD(p) ((map_scu[p] >> 31) & 1)
+#define M_IF(p)  ((map_scu[p] >> 15) & 1)
+#define M_IBC(p) ((map_scu[p] >> 26) & 1)
+#define M_INTER(p) (!M_IF(p) && !M_IBC(p))
+    unsigned av = 0;
+    if(x > 0 && M_INTER(scup - 1) && M_COD(scup - 1)) {
+        av |= 1u << 1;                                                                       /* AVAIL_LE */
+        if(y + scuh < h && M_COD(scup + scuh * w - 1) && M_INTER(scup + scuh * w - 1)) av |= 1u << 7;  /* LO_LE */
+    }
+    if(y > 0) {
+        if(M_INTER(scup - w)) av |= 1u << 0;                                                 /* AVAIL_UP: no COD test */
+        if(M_INTER(scup - w + scuw - 1)) av |= 1u << 9;                                      /* AVAIL_RI_UP */
+        if(x > 0 && M_INTER(scup - w - 1) && M_COD(scup - w - 1)) av |= 1u << 5;             /* UP_LE */
+        /* MCU_IS_COD_NIF: coded and not intra (the IBC flag is not part of this test) */
+        if(x + scuw < w && M_COD(scup - w + scuw) && !M_IF(scup - w + scuw)) av |= 1u << 6;  /* UP_RI */
+    }
+    if(x + scuw < w && M_INTER(scup + scuw) && M_COD(scup + scuw)) {
+        av |= 1u << 3;                                                                       /* AVAIL_RI */
+        if(y + scuh < h && M_COD(scup + scuh * w + scuw) && M_INTER(scup + scuh * w + scuw)) av |= 1u << 8;  /* LO_RI */
+    }
+    it->avail = (uint16_t)av;
+    const int nb[3] = {scup - 1, scup - w, scup - w + scuw}, need[3] = {1, 0, 6};
+    for(int k = 0; k < 3; k++) {
+        it->refi[k] = 0;
+        if((av >> need[k]) & 1) { it->mvp[k][0] = map_mv[(nb[k] * 2 + l) * 2]; it->mvp[k][1] = map_mv[(nb[k] * 2 + l) * 2 + 1]; }
+        else it->mvp[k][0] = it->mvp[k][1] = 1;
+    }
+    const int16_t *col = l ? col_mv1 : col_mv0;                  /* refp[0][lidx].map_mv[scup][0] */
+    it->refi[3] = 0;
+    it->mvp[3][0] = col[(scup * 2 + 0) * 2]; it->mvp[3][1] = col[(scup * 2 + 0) * 2 + 1];
+    /* temporal direct: colocated MV (list 0 entry) of the list-1 reference at the CU's bottom-right SCU */
+    const int br = scup + (scuw - 1) + (scuh - 1) * w;
+    const int mvc[2] = {col_mv1[(br * 2 + 0) * 2], col_mv1[(br * 2 + 0) * 2 + 1]};
+    const int dpoc_co = pp->ref_poc[1] - pp->col_list_poc0, d0 = pp->poc - pp->ref_poc[0], d1 = pp->ref_poc[1] - pp->poc;
+    for(int k = 0; k < 2; k++) {
+        it->mv_dir[0][k] = (int16_t)(dpoc_co ? d0 * mvc[k] / dpoc_co : 0);
+        it->mv_dir[1][k] = (int16_t)(dpoc_co ? -d1 * mvc[k] / dpoc_co : 0);
+    }
+#undef M_COD
+#undef M_IF
+#undef M_IBC
+#undef M_INTER
+}
+void xo_mvp_batch(xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pp, const uint32_t *map_scu, const int16_t *map_mv,
+                  const int16_t *col_mv0, const int16_t *col_mv1)
+{
+    for(int64_t i = 0; i < n; i++) xo_mvp(&items[i], pp, map_scu, map_mv, col_mv0, col_mv1);
+}
+
 /* xeve_get_avail_intra (src_base/xeve_util.c:717-772), xeve_get_nbr (src_base/xeve_ipred.c:33-97) for the three planes and
  * xeve_get_mpm (:230-252), single tile.  y/u/v: active-area origins of the picture reconstructed so far. */
 void xo_intra_nbr(const int16_t *y, const int16_t *u, const int16_t *v, int s_l, int s_c, xb200_nbr_item *it, const uint32_t *map_scu,

@@ -48,6 +48,10 @@ XO_API void xo_intra_nbr(const int16_t *y, const int16_t *u, const int16_t *v, i
                          const int8_t *map_ipm, int w_scu, int h_scu, int cip, int bd, int16_t *side);
 XO_API void xo_intra_nbr_batch(const int16_t *y, const int16_t *u, const int16_t *v, int s_l, int s_c, xb200_nbr_item *items, int64_t n,
                                const uint32_t *map_scu, const int8_t *map_ipm, int w_scu, int h_scu, int cip, int bd, int16_t *side);
+XO_API void xo_mvp(xb200_mvp_item *it, const xb200_mvp_pic *pp, const uint32_t *map_scu, const int16_t *map_mv, const int16_t *col_mv0,
+                   const int16_t *col_mv1);
+XO_API void xo_mvp_batch(xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pp, const uint32_t *map_scu, const int16_t *map_mv,
+                         const int16_t *col_mv0, const int16_t *col_mv1);
 XO_API void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out);
 XO_API void xo_deblock(int16_t *y, int16_t *u, int16_t *v, int s_l, int s_c, int w, int h, const xb200_df_cu *cus, int64_t n,
                        const xb200_df_pic *pp, const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int bit_depth);

@@ -298,3 +298,37 @@ def test_oracle_full_size_in_situ(clip, preset, min_intra, min_cu):
     for d in tracedata.df_from_trace(td.live):
         got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
         assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
+
+
+@needs_ref
+def test_oracle_mvp_inputs_match_reference():
+    """xo_mvp == xeve_get_avail_inter + xeve_get_motion + xeve_get_mv_dir on random SCU maps (same generator as the GPU test):
+    availability masks, the (1,1) fallback (quirk q7), the unscaled colocated candidate, POC-scaled temporal-direct MVs"""
+    from xeve_b200 import api
+    rng = np.random.default_rng(17)
+    w_scu, h_scu = 88, 72
+    f = w_scu * h_scu
+    map_scu = ((rng.random(f) < 0.8).astype(np.uint32) << 31) | ((rng.random(f) < 0.2).astype(np.uint32) << 15) | \
+        rng.integers(0, 1 << 15, f).astype(np.uint32) | ((rng.random(f) < 0.05).astype(np.uint32) << 26)
+    maps = [rng.integers(-600, 600, (f, 2, 2)).astype(np.int16) for _ in range(3)]
+    n = 4000
+    items = np.zeros(n, api.MVP_ITEM)
+    l2 = rng.integers(3, 7, n)
+    items["log2_cuw"] = items["log2_cuh"] = l2
+    s = (1 << l2) >> 2
+    items["x_scu"] = (rng.integers(0, w_scu, n) // s * s).clip(0, w_scu - s)
+    items["y_scu"] = (rng.integers(0, h_scu, n) // s * s).clip(0, h_scu - s)
+    items["lidx"] = rng.integers(0, 2, n)
+    L = rh.lib()
+    assert L.rh_sizeof_mvp() == api.MVP_ITEM.itemsize
+    L.rh_mvp.restype = None
+    L.rh_mvp.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    for poc, rp, lp0 in ((8, (0, 16), 0), (4, (0, 8), 8), (12, (8, 16), 0), (16, (0, 0), 0)):
+        pic = np.zeros(1, api.MVP_PIC)
+        pic["w_scu"], pic["h_scu"], pic["poc"], pic["ref_poc"], pic["col_list_poc0"] = w_scu, h_scu, poc, rp, lp0
+        exp = items.copy()
+        L.rh_mvp(p(exp), n, p(pic), p(map_scu), p(maps[0]), p(maps[1]), p(maps[2]))
+        got = xo.mvp_batch(items, pic, map_scu, maps[0], maps[1], maps[2])
+        for fld in ("avail", "refi", "mvp", "mv_dir"):
+            assert np.array_equal(got[fld], exp[fld]), (fld, poc)
+    assert len(np.unique(exp["avail"])) > 10 and (exp["mvp"][:, :3] == 1).all(-1).any()
