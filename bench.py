@@ -363,7 +363,8 @@ def run_b200(args, rank, world, dist):
                      "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get(dom),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": int(alg[dom]),
-                     "note": "integer ALU / shared-memory bound, not HBM bound: see DESIGN.md section 5"},
+                     "note": "integer ALU / shared-memory bound, not HBM bound (ncu: issue slots 48-60 % active, DRAM 0.4-0.5 % of peak for k_me<3..6>; "
+                             "profiles/r01_final_ncu_summary.txt): see DESIGN.md section 5"},
         "clocks": sampler.summary(),
     }
     hp.close()
