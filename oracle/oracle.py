@@ -192,3 +192,36 @@ def mvp_batch(items, pic, map_scu, map_mv, col0, col1):
     L.xo_mvp_batch(_p(items), len(items), _p(np.ascontiguousarray(pic)), _p(np.ascontiguousarray(map_scu, np.uint32)),
                    _p(np.ascontiguousarray(map_mv, np.int16)), _p(np.ascontiguousarray(col0, np.int16)), _p(np.ascontiguousarray(col1, np.int16)))
     return items
+
+
+def chain_picture(seq, planes, pp, col0, col1, dtypes, ctu_limit=0):
+    """xo_chain_picture: the CU decision chain of one picture (mode_coding_tree over every CTU).  pp: one CTU record (the
+    harness's LCU_REC layout) carrying the picture-level inputs; dtypes = (LCU_REC, DF_CU, CU_ITEM, INTRA_ITEM).  Returns a
+    dict: ctu (records with state_in / state_out), cost, rec (Y, U, V), map_scu, map_ipm, map_refi, map_mv, cus (leaf CUs in
+    coding order), cu_log / intra_log (every inter / intra analysis in call order)."""
+    lcu_dt, dfcu_dt, cu_dt, intra_dt = dtypes
+    sq = np.ascontiguousarray(seq).reshape(-1)[0]
+    w, h = int(sq["w"]), int(sq["h"])
+    w_scu, h_scu = (w + 3) // 4, (h + 3) // 4
+    f, n_ctu = w_scu * h_scu, ((w + 63) // 64) * ((h + 63) // 64)
+    out = np.zeros(n_ctu, lcu_dt)
+    cost = np.zeros(n_ctu, np.float64)
+    rec = [np.zeros((h, w), np.int16), np.zeros((h // 2, w // 2), np.int16), np.zeros((h // 2, w // 2), np.int16)]
+    map_scu, map_ipm = np.zeros(f, np.uint32), np.zeros(f, np.int8)
+    map_refi, map_mv = np.zeros((f, 2), np.int8), np.zeros((f, 2, 2), np.int16)
+    cap = f * 2
+    cus, cu_log, intra_log = np.zeros(f, dfcu_dt), np.zeros(cap, cu_dt), np.zeros(cap, intra_dt)
+    n_out = np.zeros(3, np.int64)
+    pp = np.ascontiguousarray(pp).reshape(-1)[:1].copy()
+    col0 = None if col0 is None else np.ascontiguousarray(col0, np.int16)
+    col1 = None if col1 is None else np.ascontiguousarray(col1, np.int16)
+    L = lib()
+    assert L.xo_sizeof_chain(0) == lcu_dt.itemsize, (L.xo_sizeof_chain(0), lcu_dt.itemsize)
+    L.xo_chain_picture.restype = None
+    L.xo_chain_picture.argtypes = [VP] * 10 + [I, I] + [VP] * 5 + [C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, I]
+    L.xo_chain_picture(_p(np.ascontiguousarray(seq)), C.addressof(planes), _p(pp), _p(col0), _p(col1), _p(out), _p(cost), _p(rec[0]),
+                       _p(rec[1]), _p(rec[2]), w, w // 2, _p(map_scu), _p(map_ipm), _p(map_refi), _p(map_mv), _p(cus), len(cus),
+                       _p(cu_log), cap, _p(intra_log), cap, _p(n_out), ctu_limit)
+    assert n_out[1] <= cap and n_out[2] <= cap
+    return dict(ctu=out, cost=cost, rec=rec, map_scu=map_scu, map_ipm=map_ipm, map_refi=map_refi, map_mv=map_mv,
+                cus=cus[:int(n_out[0])], cu_log=cu_log[:int(n_out[1])], intra_log=intra_log[:int(n_out[2])])

@@ -176,6 +176,8 @@ static struct {
     double (*org_intra)(XEVE_CTX *, XEVE_CORE *, int, int, int, int, XEVE_MODE *, s16 (*)[MAX_CU_DIM], pel **, int *);
     vec_t    intra;    /* RH_INTRA_REC; coder states go to cu_sbac, neighbour samples to samp */
     vec_t    df, df_cu, df_maps; /* deblocking: one record per picture, CU rectangles, frame maps (bytes) */
+    int (*org_lcu)(XEVE_CTX *, XEVE_CORE *);
+    vec_t    lcu;      /* RH_LCU_REC: one per ctx->fn_mode_analyze_lcu call */
     int      df_collect;
     vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
     /* samp: s16 side buffer (pictures, org_bi, tq inputs) */
@@ -536,6 +538,88 @@ RH_API void rh_intra_nbr(const RH_PLANES *pl, RH_NBR_REC *items, int n, u32 *map
 }
 
 /* ------------------------------------------------------------------------------------------
+ * CTU decision trace: ctx->fn_mode_analyze_lcu (mode_analyze_lcu -> mode_coding_tree, src_base/xeve_mode.c:2007-2374,
+ * 2521-2608).  One record per CTU: the picture-level inputs of the decision pass, the coder state the CTU starts from
+ * (core->s_curr_best[CTU], loaded from the bitstream coder, src_base/xeve_enc.c:139) and the one it leaves
+ * (core->s_next_best[CTU]).  The colocated MV maps of the picture are stored once, with the first CTU.
+ * ---------------------------------------------------------------------------------------- */
+#define RH_T_LCU 256
+typedef struct { RH_SBAC s; uint16_t ipm[2], split, pad_; } RH_STATE;
+typedef struct {
+    int32_t  poc, slice_type, lcu_num, x_pel, y_pel, tile_qp, cur_pic;
+    int32_t  num_refp[2], ref_pic[2][RH_MAXR], ref_poc[2][RH_MAXR], col_list_poc0;
+    int32_t  max_cu_inter, min_cu_inter, max_cu_intra, min_cu_intra, cip;
+    int32_t  qp[3];
+    uint32_t lambda_mv;
+    int32_t  max_search_range, pad_;
+    double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
+    int64_t  col_off[2];            /* s16 offset in samp of refp[0][l].map_mv (f_scu x [2][2]); -1: none */
+    RH_STATE state_in, state_out;
+} RH_LCU_REC;
+static void state_pack(const XEVE_SBAC *d, RH_STATE *s)
+{
+    memset(s, 0, sizeof(*s));
+    sbac_pack(d, &s->s);
+    memcpy(s->ipm, d->ctx.intra_dir, 4);
+    memcpy(&s->split, d->ctx.split_cu_flag, 2);
+}
+static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
+{
+    if(!tracing(RH_T_LCU)) return T.org_lcu(ctx, core);
+    static int64_t col_off[2];
+    XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];
+    XEVE_PINTRA *pa = &ctx->pintra[core->thread_cnt];
+    RH_LCU_REC   r;
+    memset(&r, 0, sizeof(r));
+    const int L = ctx->log2_max_cuwh - 2;
+    r.poc = ctx->poc.poc_val; r.slice_type = ctx->slice_type; r.lcu_num = core->lcu_num;
+    r.x_pel = core->x_pel; r.y_pel = core->y_pel; r.tile_qp = ctx->tile[core->tile_idx].qp;
+    r.cur_pic = find_or_add_pic(pa->pic_o, r.poc, 0);
+    for(int l = 0; l < 2; l++) {
+        r.num_refp[l] = ctx->rpm.num_refp[l];
+        for(int k = 0; k < RH_MAXR; k++) {
+            r.ref_pic[l][k] = -1; r.ref_poc[l][k] = -1;
+            if(ctx->slice_type != SLICE_I && k < r.num_refp[l] && (l == 0 || ctx->slice_type == SLICE_B)) {
+                XEVE_PIC *rp = ctx->refp[k][l].pic;
+                r.ref_pic[l][k] = find_or_add_pic(rp, (int)rp->poc, 1);
+                r.ref_poc[l][k] = (int)ctx->refp[k][l].poc;
+            }
+        }
+    }
+    if(core->lcu_num == 0) {
+        col_off[0] = col_off[1] = -1;
+        if(ctx->slice_type != SLICE_I)
+            for(int l = 0; l < 2; l++) {
+                if(l == 1 && ctx->slice_type != SLICE_B) break;
+                if(!ctx->refp[0][l].map_mv) continue;
+                col_off[l] = (int64_t)T.samp.n;
+                memcpy(vec_push(&T.samp, (size_t)ctx->f_scu * 4), ctx->refp[0][l].map_mv, (size_t)ctx->f_scu * 8);
+            }
+    }
+    r.col_off[0] = col_off[0]; r.col_off[1] = col_off[1];
+    if(ctx->slice_type == SLICE_B && ctx->refp[0][REFP_1].list_poc) r.col_list_poc0 = (int)ctx->refp[0][REFP_1].list_poc[0];
+    r.max_cu_inter = ctx->param.max_cu_inter; r.min_cu_inter = ctx->param.min_cu_inter;
+    r.max_cu_intra = ctx->param.max_cu_intra; r.min_cu_intra = ctx->param.min_cu_intra;
+    r.cip = ctx->pps.constrained_intra_pred_flag;
+    {   /* mode_cu_init, src_base/xeve_mode.c:776-783, with core->qp == tile qp (no delta QP) */
+        const int q = r.tile_qp, bdc = ctx->sps.bit_depth_chroma_minus8;
+        r.qp[0] = GET_LUMA_QP(q, ctx->sps.bit_depth_luma_minus8);
+        r.qp[1] = ctx->qp_chroma_dynamic[0][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_u_offset)] + 6 * bdc;
+        r.qp[2] = ctx->qp_chroma_dynamic[1][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_v_offset)] + 6 * bdc;
+    }
+    r.lambda_mv = pi->lambda_mv; r.max_search_range = pi->max_search_range;
+    for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
+    r.sqrt_lambda0 = core->sqrt_lambda[0];
+    r.dist_chroma_weight[0] = core->dist_chroma_weight[0]; r.dist_chroma_weight[1] = core->dist_chroma_weight[1];
+    state_pack(&core->s_curr_best[L][L], &r.state_in);
+    int ret = T.org_lcu(ctx, core);
+    state_pack(&core->s_next_best[L][L], &r.state_out);
+    *(RH_LCU_REC *)vec_push(&T.lcu, 1) = r;
+    return ret;
+}
+RH_API int rh_sizeof_lcu(void) { return sizeof(RH_LCU_REC); }
+
+/* ------------------------------------------------------------------------------------------
  * deblocking trace: ctx->fn_loop_filter with the picture before / after, the frame
  * maps it reads and the CU rectangles xeve_deblock_tree enumerates (ctx->fn_deblock_unit)
  * ---------------------------------------------------------------------------------------- */
@@ -688,7 +772,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
     vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
-    vec_reset(&T.intra, sizeof(RH_INTRA_REC));
+    vec_reset(&T.intra, sizeof(RH_INTRA_REC)); vec_reset(&T.lcu, sizeof(RH_LCU_REC));
     vec_reset(&T.df, sizeof(RH_DF_REC)); vec_reset(&T.df_cu, sizeof(RH_DF_CU)); vec_reset(&T.df_maps, 1); T.df_collect = 0;
     T.have_rates = 0;
     g_cu_secs = 0; g_cu_calls = 0; g_intra_secs = 0; g_intra_calls = 0;
@@ -702,6 +786,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
         T.org_intra = ctx->fn_pintra_analyze_cu; ctx->fn_pintra_analyze_cu = hook_intra;
         T.org_lf = ctx->fn_loop_filter; T.org_df_unit = ctx->fn_deblock_unit;
         ctx->fn_loop_filter = hook_loop_filter; ctx->fn_deblock_unit = hook_df_unit;
+        T.org_lcu = ctx->fn_mode_analyze_lcu; ctx->fn_mode_analyze_lcu = hook_lcu;
     }
     XEVE_PINTER *pi = &ctx->pinter[0];
     T.cst.w = w; T.cst.h = h; T.cst.bit_depth = ctx->param.codec_bit_depth; T.cst.me_level = pi->me_level;
@@ -769,7 +854,7 @@ RH_API int64_t rh_trace_get(int what, void **ptr)
 {
     vec_t *v = what == 0 ? &T.me : what == 1 ? &T.mc : what == 2 ? &T.tq : what == 3 ? &T.rates
              : what == 4 ? &T.pics : what == 5 ? &T.samp : what == 6 ? &T.sbac : what == 7 ? &T.cu : what == 8 ? &T.cu_sbac
-             : what == 9 ? &T.df : what == 10 ? &T.df_cu : what == 11 ? &T.df_maps : &T.intra;
+             : what == 9 ? &T.df : what == 10 ? &T.df_cu : what == 11 ? &T.df_maps : what == 13 ? &T.lcu : &T.intra;
     *ptr = v->p;
     return (int64_t)v->n;
 }

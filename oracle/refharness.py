@@ -172,6 +172,7 @@ def _p(a):
 TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
 TRACE_DF = 32
 TRACE_INTRA, TRACE_INTRA_TIME = 64, 128
+TRACE_LCU = 256
 
 
 def intra_time():
@@ -198,6 +199,16 @@ DF_PIC = np.dtype([("w_scu", "<i4"), ("h_scu", "<i4"), ("qp_u_offset", "<i4"), (
                    ("chroma_qp", "<i4", (2, 70))], align=True)
 DF_REC = np.dtype([("poc", "<i4"), ("pre_pic", "<i4"), ("post_pic", "<i4"), ("on", "<i4"), ("cu_first", "<i8"), ("cu_cnt", "<i8"),
                    ("maps_off", "<i8"), ("pp", DF_PIC)], align=True)
+
+
+# CTU decision trace (ctx->fn_mode_analyze_lcu): layouts == RH_STATE / RH_LCU_REC of ref_harness.c == xo_state / xo_chain_pic + states
+STATE = np.dtype([("range", "<u4"), ("m", "<u2", (68,)), ("ipm", "<u2", (2,)), ("split", "<u2"), ("pad_", "<u2")], align=True)
+LCU_REC = np.dtype([("poc", "<i4"), ("slice_type", "<i4"), ("lcu_num", "<i4"), ("x_pel", "<i4"), ("y_pel", "<i4"), ("tile_qp", "<i4"),
+                    ("cur_pic", "<i4"), ("num_refp", "<i4", (2,)), ("ref_pic", "<i4", (2, 4)), ("ref_poc", "<i4", (2, 4)),
+                    ("col_list_poc0", "<i4"), ("max_cu_inter", "<i4"), ("min_cu_inter", "<i4"), ("max_cu_intra", "<i4"),
+                    ("min_cu_intra", "<i4"), ("cip", "<i4"), ("qp", "<i4", (3,)), ("lambda_mv", "<u4"), ("max_search_range", "<i4"),
+                    ("pad_", "<i4"), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
+                    ("col_off", "<i8", (2,)), ("state_in", STATE), ("state_out", STATE)], align=True)
 
 
 NBR_REC = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("mpm", "u1", (5,)), ("pad_", "u1"),
@@ -314,6 +325,8 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
     assert L.rh_sizeof_intra() == INTRA_REC.itemsize, (L.rh_sizeof_intra(), INTRA_REC.itemsize)
     tr.intra = grab(12, INTRA_REC)
     tr.df, tr.df_cu, tr.df_maps = grab(9, DF_REC), grab(10, DF_CU), grab(11, np.dtype("u1"))
+    assert L.rh_sizeof_lcu() == LCU_REC.itemsize, (L.rh_sizeof_lcu(), LCU_REC.itemsize)
+    tr.lcu = grab(13, LCU_REC)
     return tr
 
 

@@ -1084,6 +1084,7 @@ static double cu_residue_rdo(const cu_env *e, int pidx, cu_mode *m, const uint8_
     return best;
 }
 
+static int16_t *g_pred_y_sink; /* xo_chain_picture: where the winner's luma prediction (mi->pred_y_best) goes */
 void xo_analyze_cu(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_cu_item *cu, xb200_sbac *states,
                    int16_t *coef_out, int16_t *rec_out)
 {
@@ -1280,6 +1281,7 @@ void xo_analyze_cu(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *
     }
     cu->nnz[0] = m->nnz[0]; cu->nnz[1] = m->nnz[1]; cu->nnz[2] = m->nnz[2];
     if(cu->state_out >= 0) states[cu->state_out] = m->st;
+    if(g_pred_y_sink) memcpy(g_pred_y_sink, m->pred, sizeof(int16_t) * e.ny); /* src_base/xeve_pinter.c:2040 */
     free(buf);
 }
 void xo_analyze_cu_batch(const xb200_seq *sq, const xo_planes *pl, const xb200_rates *rates, xb200_cu_item *items, int64_t n,
@@ -1580,6 +1582,405 @@ void xo_intra_nbr_batch(const int16_t *y, const int16_t *u, const int16_t *v, in
     for(int64_t i = 0; i < n; i++) xo_intra_nbr(y, u, v, s_l, s_c, &items[i], map_scu, map_ipm, w_scu, h_scu, cip, bd, side);
 }
 
+
+/* ---------------------------------------------------------------------------------------------
+ * CU decision chain of one picture (SURVEY 8a' q15 / q16, the caller of rows a1 and f-3): mode_analyze_lcu ->
+ * mode_coding_tree -> mode_coding_unit -> mode_check_inter / mode_check_intra (src_base/xeve_mode.c:1170-1348, 2007-2374,
+ * 2521-2608) with the bookkeeping around them: init_cu_data / copy_cu_data / copy_to_cu_data (:375-632, 868-1034),
+ * update_map_scu / clear_map_scu (:1036-1155), mode_cpy_rec_to_ref (:797-866), the split_cu_flag count of
+ * xeve_eco_split_mode (src_base/xeve_eco.c:1377-1429) and the CTU loop of xeve_ctu_mt_core (src_base/xeve_enc.c:103-175,
+ * one thread, one tile, no delta QP).  Baseline: quad split only, the context-index flags are all 0, and the coder state
+ * a CTU starts from equals the state the previous CTU's decision pass ended with (checked against the reference's own
+ * per-CTU states in tests/test_oracle.py), so a picture needs no input besides its original, its references and the
+ * colocated MV maps.
+ * ------------------------------------------------------------------------------------------- */
+#define XO_MAX_COST 1.7e+308
+enum { XO_MODE_SKIP = 0, XO_MODE_DIR = 1, XO_MODE_INTER = 2, XO_MODE_INTRA = 3 };
+typedef struct {              /* XEVE_CU_DATA of one quad-tree level, SCU-granular, row stride = block width in SCUs */
+    uint8_t  mode[256], log2[256];
+    int8_t   ipm[256], refi[256][2];
+    int16_t  mv[256][2][2];
+    int32_t  nnz[256][3];
+    uint8_t  mvp_idx[256][2];
+    int16_t  mvd[256][2][2];
+    uint32_t scu[256];
+    int16_t *rec[3], *coef[3]; /* reconstruction and quantised coefficients, CU rectangles at their place, stride = block width */
+} cud_t;
+typedef struct {
+    const xb200_seq *sq; const xo_planes *pl; const xo_ctu_rec *pp;
+    const int16_t *col[2];
+    int       w, h, w_scu, h_scu;
+    int16_t  *rec[3]; int s_l, s_c;
+    uint32_t *map_scu; int8_t *map_ipm, *map_refi; int16_t *map_mv;
+    xo_state  curr[5], next[5], before[5];
+    cud_t     best[5], temp[5];
+    int       cu_mode, dist_cu_best;
+    int16_t  *coef, *rec_cu, *pred_y, *side;
+    xb200_cu_item *cu_log; xb200_intra_item *intra_log; int64_t cu_cap, intra_cap, n_cu, n_intra;
+} chain_t;
+
+static void cud_init(cud_t *d, int L)       /* init_cu_data: everything the chain reads later */
+{
+    const int n = 1 << (2 * L);
+    memset(d->mode, 0, n); memset(d->log2, 0, n); memset(d->ipm, 0, n); memset(d->refi, 0, 2 * n);
+    memset(d->mv, 0, 8 * n); memset(d->nnz, 0, 12 * n); memset(d->scu, 0, 4 * n); memset(d->mvp_idx, 0, 2 * n); memset(d->mvd, 0, 8 * n);
+}
+static void cud_copy(cud_t *dst, int Ld, const cud_t *src, int Ls, int xoff, int yoff) /* copy_cu_data */
+{
+    const int ns = 1 << Ls, nd = 1 << Ld, ws = 4 << Ls, wd = 4 << Ld;
+    for(int j = 0; j < ns; j++) {
+        const int d = ((yoff >> 2) + j) * nd + (xoff >> 2), s0 = j * ns;
+        memcpy(dst->mode + d, src->mode + s0, ns); memcpy(dst->log2 + d, src->log2 + s0, ns); memcpy(dst->ipm + d, src->ipm + s0, ns);
+        memcpy(dst->refi + d, src->refi + s0, 2 * ns); memcpy(dst->mv + d, src->mv + s0, 8 * ns);
+        memcpy(dst->nnz + d, src->nnz + s0, 12 * ns); memcpy(dst->scu + d, src->scu + s0, 4 * ns);
+        memcpy(dst->mvp_idx + d, src->mvp_idx + s0, 2 * ns); memcpy(dst->mvd + d, src->mvd + s0, 8 * ns);
+    }
+    for(int j = 0; j < ws; j++) {
+        memcpy(dst->rec[0] + (yoff + j) * wd + xoff, src->rec[0] + j * ws, 2 * ws);
+        memcpy(dst->coef[0] + (yoff + j) * wd + xoff, src->coef[0] + j * ws, 2 * ws);
+    }
+    for(int c = 1; c < 3; c++)
+        for(int j = 0; j < ws / 2; j++) {
+            memcpy(dst->rec[c] + ((yoff >> 1) + j) * (wd / 2) + (xoff >> 1), src->rec[c] + j * (ws / 2), ws);
+            memcpy(dst->coef[c] + ((yoff >> 1) + j) * (wd / 2) + (xoff >> 1), src->coef[c] + j * (ws / 2), ws);
+        }
+}
+static void chain_clear_map(chain_t *k, int x, int y, int cuw)                          /* clear_map_scu */
+{
+    const int w = ((x + cuw > k->w ? k->w - x : cuw) >> 2), h = ((y + cuw > k->h ? k->h - y : cuw) >> 2);
+    for(int j = 0; j < h; j++) memset(k->map_scu + ((y >> 2) + j) * k->w_scu + (x >> 2), 0, 4 * w);
+}
+static void chain_update_map(chain_t *k, int x, int y, int L)                           /* update_map_scu from cu_data_best[L] */
+{
+    const cud_t *b = &k->best[L];
+    const int cuw = 4 << L, n = 1 << L, w = ((x + cuw > k->w ? k->w - x : cuw) >> 2), h = ((y + cuw > k->h ? k->h - y : cuw) >> 2);
+    for(int j = 0; j < h; j++) {
+        const int64_t p = (int64_t)((y >> 2) + j) * k->w_scu + (x >> 2);
+        memcpy(k->map_scu + p, b->scu + j * n, 4 * w); memcpy(k->map_ipm + p, b->ipm + j * n, w);
+        memcpy(k->map_mv + p * 4, b->mv + j * n, 8 * w); memcpy(k->map_refi + p * 2, b->refi + j * n, 2 * w);
+    }
+}
+static void chain_rec_to_pic(chain_t *k, int x, int y, int L)                           /* mode_cpy_rec_to_ref from cu_data_best[L] */
+{
+    const cud_t *b = &k->best[L];
+    const int cuw = 4 << L, w = x + cuw > k->w ? k->w - x : cuw, h = y + cuw > k->h ? k->h - y : cuw;
+    for(int j = 0; j < h; j++) memcpy(k->rec[0] + (int64_t)(y + j) * k->s_l + x, b->rec[0] + j * cuw, 2 * w);
+    for(int c = 1; c < 3; c++)
+        for(int j = 0; j < h / 2; j++) memcpy(k->rec[c] + (int64_t)(y / 2 + j) * k->s_c + x / 2, b->rec[c] + j * (cuw / 2), w);
+}
+/* copy_to_cu_data into cu_data_temp[L] */
+static void chain_store_cu(chain_t *k, int L, int mode, int ipm, const int8_t refi[2], int16_t mv[2][2], const int32_t nnz[3],
+                           const uint8_t mvp_idx[2], int16_t mvd[2][2], const int16_t *coef)
+{
+    cud_t *t = &k->temp[L];
+    const int n = 1 << (2 * L), ny = 16 << (2 * L);
+    const uint32_t word = (uint32_t)(((uint32_t)k->pp->tile_qp << 16) | ((uint32_t)(mode == XO_MODE_INTRA) << 15) | (1u << 31) |
+                                     ((uint32_t)(mode == XO_MODE_SKIP) << 23));
+    for(int i = 0; i < n; i++) {
+        t->mode[i] = (uint8_t)mode; t->log2[i] = (uint8_t)(L + 2); memcpy(t->nnz[i], nnz, 12); t->scu[i] = word;
+        if(mode == XO_MODE_INTRA) { t->ipm[i] = (int8_t)ipm; memset(t->mv[i], 0, 8); t->refi[i][0] = t->refi[i][1] = -1; }
+        else {
+            t->refi[i][0] = refi[0]; t->refi[i][1] = refi[1]; memcpy(t->mv[i], mv, 8);
+            memcpy(t->mvp_idx[i], mvp_idx, 2); memcpy(t->mvd[i], mvd, 8);
+        }
+    }
+    memcpy(t->rec[0], k->rec_cu, 2 * ny); memcpy(t->rec[1], k->rec_cu + ny, ny / 2); memcpy(t->rec[2], k->rec_cu + ny + ny / 4, ny / 2);
+    memcpy(t->coef[0], coef, 2 * ny); memcpy(t->coef[1], coef + ny, ny / 2); memcpy(t->coef[2], coef + ny + ny / 4, ny / 2);
+}
+static uint32_t chain_split_flag(xo_state *st, int cuw, int split)   /* xeve_eco_split_mode in bit-count mode; returns the bits */
+{
+    if(cuw < 8) return 0;
+    cabac_t c;
+    c.s = st->s; c.bits = 0; c.ipm[0] = st->split;       /* borrow the first spare model slot for ctx.split_cu_flag */
+    cb_bin(&c, XO_CM_IPM, split);
+    st->s = c.s; st->split = c.ipm[0];
+    return c.bits;
+}
+static double chain_unit(chain_t *k, int x, int y, int L, int cud)   /* mode_coding_unit */
+{
+    const xo_ctu_rec *pp = k->pp;
+    const int log2 = L + 2, cuw = 1 << log2, ny = cuw * cuw, B = pp->slice_type == 0;
+    xb200_rates rates;
+    xb200_sbac  st[2];
+    double      cost_best = XO_MAX_COST;
+    int         nnz[3] = {0, 0, 0};
+    (void)cud;
+    xo_rdoq_rates(&k->curr[L].s, 1, &rates);                          /* mode_cu_init -> xeve_rdoq_bit_est */
+    k->cu_mode = XO_MODE_INTRA;
+    if(pp->slice_type != 2) {                                         /* mode_check_inter */
+        xb200_cu_item cu;
+        memset(&cu, 0, sizeof(cu));
+        cu.poc = pp->poc; cu.cur_pic = pp->cur_pic; cu.x = (int16_t)x; cu.y = (int16_t)y; cu.log2_cuw = cu.log2_cuh = (uint8_t)log2;
+        cu.slice_type = (uint8_t)pp->slice_type; cu.all_preds = 1;
+        cu.max_search_range = pp->max_search_range; cu.lambda_mv = pp->lambda_mv;
+        for(int l = 0; l < 2; l++) {
+            cu.num_refp[l] = (uint8_t)pp->num_refp[l];
+            for(int r = 0; r < 4; r++) { cu.ref_pic[l][r] = pp->ref_pic[l][r]; cu.ref_poc[l][r] = pp->ref_poc[l][r]; }
+        }
+        for(int i = 0; i < 3; i++) { cu.qp[i] = (uint8_t)pp->qp[i]; cu.lambda[i] = pp->lambda[i]; }
+        cu.dist_chroma_weight[0] = pp->dist_chroma_weight[0]; cu.dist_chroma_weight[1] = pp->dist_chroma_weight[1];
+        xb200_mvp_pic mp = {k->w_scu, k->h_scu, pp->poc, {pp->ref_poc[0][0], pp->ref_poc[1][0]}, pp->col_list_poc0};
+        for(int l = 0; l < (B ? 2 : 1); l++) {
+            xb200_mvp_item mi;
+            memset(&mi, 0, sizeof(mi));
+            mi.x_scu = (int16_t)(x >> 2); mi.y_scu = (int16_t)(y >> 2); mi.log2_cuw = mi.log2_cuh = (uint8_t)log2; mi.lidx = (uint8_t)l;
+            xo_mvp(&mi, &mp, k->map_scu, k->map_mv, k->col[0], k->col[1] ? k->col[1] : k->col[0]);
+            memcpy(cu.mvp[l], mi.mvp, sizeof(mi.mvp)); memcpy(cu.refi_pred[l], mi.refi, 4);
+            if(B) memcpy(cu.mv_dir, mi.mv_dir, sizeof(mi.mv_dir));
+        }
+        cu.rate_idx = 0; cu.state_in = 0; cu.state_out = 1; cu.out_off = 0;
+        st[0] = k->curr[L].s;
+        g_pred_y_sink = k->pred_y;
+        xo_analyze_cu(k->sq, k->pl, &rates, &cu, st, k->coef, k->rec_cu);
+        g_pred_y_sink = NULL;
+        if(k->n_cu < k->cu_cap) k->cu_log[k->n_cu] = cu;
+        k->n_cu++;
+        k->cu_mode = cu.best_idx == 3 ? XO_MODE_SKIP : cu.best_idx == 4 ? XO_MODE_DIR : XO_MODE_INTER;
+        nnz[0] = cu.nnz[0]; nnz[1] = cu.nnz[1]; nnz[2] = cu.nnz[2];
+        k->next[L] = k->curr[L]; k->next[L].s = st[1];                /* SBAC_STORE(s_next_best, s_temp_best), src_base/xeve_pinter.c */
+        if(cu.cost < cost_best) {
+            cost_best = cu.cost;
+            chain_store_cu(k, L, k->cu_mode, 0, cu.refi, cu.mv, cu.nnz, cu.mvp_idx, cu.mvd, k->coef);
+        }
+    }
+    if(pp->slice_type == 2 || nnz[0] || nnz[1] || nnz[2] || cost_best == XO_MAX_COST) {   /* mode_check_intra */
+        const xo_planes *o = &k->pl[pp->cur_pic];
+        xb200_intra_item it;
+        xb200_nbr_item   nb;
+        memset(&it, 0, sizeof(it)); memset(&nb, 0, sizeof(nb));
+        k->dist_cu_best = 0x7fffffff;
+        it.inter_satd = cost_best != XO_MAX_COST
+            ? (uint32_t)xo_satd(cuw, cuw, o->y + (int64_t)y * o->s_l + x, o->s_l, k->pred_y, cuw, k->sq->bit_depth) : 0xffffffffu;
+        nb.x = (int16_t)x; nb.y = (int16_t)y; nb.log2_cuw = nb.log2_cuh = (uint8_t)log2; nb.nb_off = 0;
+        xo_intra_nbr(k->rec[0], k->rec[1], k->rec[2], k->s_l, k->s_c, &nb, k->map_scu, k->map_ipm, k->w_scu, k->h_scu, pp->cip,
+                     k->sq->bit_depth, k->side);
+        it.poc = pp->poc; it.cur_pic = pp->cur_pic; it.x = (int16_t)x; it.y = (int16_t)y; it.log2_cuw = it.log2_cuh = (uint8_t)log2;
+        it.slice_type = (uint8_t)pp->slice_type; it.all_preds = 1;
+        for(int i = 0; i < 3; i++) { it.qp[i] = (uint8_t)pp->qp[i]; it.lambda[i] = pp->lambda[i]; }
+        memcpy(it.mpm, nb.mpm, 5);
+        it.rate_idx = 0; it.state_in = 0; it.state_out = 1;
+        it.cm_ipm_in[0] = k->curr[L].ipm[0]; it.cm_ipm_in[1] = k->curr[L].ipm[1];
+        it.sqrt_lambda0 = pp->sqrt_lambda0;
+        it.dist_chroma_weight[0] = pp->dist_chroma_weight[0]; it.dist_chroma_weight[1] = pp->dist_chroma_weight[1];
+        it.nb_off = 0; it.out_off = 0;
+        st[0] = k->curr[L].s; st[1] = st[0];
+        /* the inter winner's reconstruction already sits in cu_data_temp; the intra trial works in its own buffers */
+        int16_t *coef_i = k->coef + 3 * ny / 2 + 64, *rec_i = k->rec_cu + 3 * ny / 2 + 64;
+        xo_analyze_intra(k->sq, k->pl, &rates, &it, st, k->side, coef_i, rec_i);
+        if(k->n_intra < k->intra_cap) k->intra_log[k->n_intra] = it;
+        k->n_intra++;
+        if(it.cost < cost_best) {
+            cost_best = it.cost;
+            k->cu_mode = XO_MODE_INTRA;
+            k->next[L] = k->curr[L]; k->next[L].s = st[1]; k->next[L].ipm[0] = it.cm_ipm_out[0]; k->next[L].ipm[1] = it.cm_ipm_out[1];
+            k->dist_cu_best = it.dist_cu;
+            memcpy(k->rec_cu, rec_i, sizeof(int16_t) * 3 * ny / 2);
+            int8_t  none[2] = {-1, -1};
+            int16_t zero[2][2] = {{0, 0}, {0, 0}};
+            chain_store_cu(k, L, XO_MODE_INTRA, it.ipm[0], none, zero, it.nnz, NULL, zero, coef_i);
+        }
+    }
+    return cost_best;
+}
+static double chain_tree(chain_t *k, int x0, int y0, int L, int cud, int next_split)     /* mode_coding_tree */
+{
+    const xo_ctu_rec *pp = k->pp;
+    const int    cuw = 4 << L, log2 = L + 2, intra_slice = pp->slice_type == 2;
+    const int    boundary = !(x0 + cuw <= k->w && y0 + cuw <= k->h);
+    const int    check_max = intra_slice ? pp->max_cu_intra : pp->max_cu_inter, check_min = intra_slice ? pp->min_cu_intra : pp->min_cu_inter;
+    const double lambda0 = pp->lambda[0];
+    double       cost_best = XO_MAX_COST, cost_temp;
+    xo_state     s_depth;
+    memset(&s_depth, 0, sizeof(s_depth));
+    k->before[L] = k->curr[L];
+    if(!boundary && cuw <= check_max) {
+        cost_temp = 0.0;
+        if(cuw > 4) {
+            const uint32_t bits = chain_split_flag(&k->curr[L], cuw, 0);
+            cost_temp += (double)bits * lambda0;
+        }
+        cud_init(&k->temp[L], L);
+        chain_clear_map(k, x0, y0, cuw);
+        double cost_dqp = cost_temp;
+        cost_dqp += chain_unit(k, x0, y0, L, cud);
+        int cu_mode_dqp = 0, dist_dqp = 0;
+        if(cost_best > cost_dqp) {
+            cu_mode_dqp = k->cu_mode; dist_dqp = k->dist_cu_best;
+            cud_copy(&k->best[L], L, &k->temp[L], L, 0, 0);
+            cost_best = cost_dqp;
+            s_depth = k->next[L];
+            chain_rec_to_pic(k, x0, y0, L);
+        }
+        k->cu_mode = cu_mode_dqp; k->dist_cu_best = dist_dqp;
+    }
+    if(cost_best != XO_MAX_COST && cud >= ((pp->poc % 2) ? 2 : 4) && k->cu_mode == XO_MODE_SKIP) next_split = 0;   /* ENC_ECU_ADAPTIVE */
+    if(cost_best != XO_MAX_COST && intra_slice) {
+        const int dist_cu = k->dist_cu_best, dist_th = 1 << (2 * log2 + 7);
+        if(dist_cu < dist_th) {
+            const uint8_t inc = (uint8_t)((2 * log2 >= 6 ? 2 : 0) + 8);
+            if(dist_cu < lambda0 * inc) next_split = 0;
+        }
+    }
+    if(cuw > 4 && next_split && cuw > check_min) {
+        cud_init(&k->temp[L], L);
+        chain_clear_map(k, x0, y0, cuw);
+        cost_temp = 0.0;
+        k->curr[L] = k->before[L];
+        cost_temp += (double)chain_split_flag(&k->curr[L], cuw, 1) * lambda0;
+        const int half = cuw >> 1;
+        for(int part = 0; part < 4; part++) {
+            const int xp = x0 + (part & 1) * half, yp = y0 + (part >> 1) * half;
+            if(xp < k->w && yp < k->h) {
+                k->curr[L - 1] = part == 0 ? k->curr[L] : k->next[L - 1];
+                cost_temp += chain_tree(k, xp, yp, L - 1, cud + 2, 1);      /* xeve_split_get_part_structure: a quad split is two levels */
+                cud_copy(&k->temp[L], L, &k->best[L - 1], L - 1, xp - x0, yp - y0);
+                chain_update_map(k, xp, yp, L - 1);
+            }
+        }
+        if(cost_best - 0.0001 > cost_temp) {
+            cud_copy(&k->best[L], L, &k->temp[L], L, 0, 0);
+            cost_best = cost_temp;
+            s_depth = k->next[L - 1];
+        }
+    }
+    chain_rec_to_pic(k, x0, y0, L);
+    k->next[L] = s_depth;
+    return cost_best > XO_MAX_COST ? XO_MAX_COST : cost_best;
+}
+static void chain_leaves(const chain_t *k, int xc, int yc, int x, int y, int L, xb200_df_cu *cus, int64_t cap, int64_t *n)
+{
+    if(x >= k->w || y >= k->h) return;
+    const int idx = ((y - yc) >> 2) * 16 + ((x - xc) >> 2);
+    if(k->best[4].log2[idx] == L + 2 || L == 0) {
+        if(*n < cap) { cus[*n].x = (int16_t)x; cus[*n].y = (int16_t)y; cus[*n].log2_cuw = cus[*n].log2_cuh = (uint8_t)(L + 2); }
+        (*n)++;
+        return;
+    }
+    const int half = 2 << L;
+    for(int part = 0; part < 4; part++) chain_leaves(k, xc, yc, x + (part & 1) * half, y + (part >> 1) * half, L - 1, cus, cap, n);
+}
+/* xeve_eco_tree + xeve_eco_unit (src_base/xeve_enc.c:35-101, src_base/xeve_eco.c:1431-1603) over the decided CTU, models and
+ * range only: the state the next CTU's decision pass is loaded from (src_base/xeve_enc.c:139).  In B and I slices it equals the
+ * decision pass's own end state; in P slices it does not (the RDO counter codes a direct_mode_flag the bitstream lacks). */
+static void chain_eco(const chain_t *k, xo_state *st, int xc, int yc, int x, int y, int L)
+{
+    if(x >= k->w || y >= k->h) return;
+    const cud_t *b = &k->best[4];
+    const int    idx = ((y - yc) >> 2) * 16 + ((x - xc) >> 2), cuw = 4 << L;
+    if(b->log2[idx] != L + 2 && L > 0) {
+        chain_split_flag(st, cuw, 1);
+        for(int part = 0; part < 4; part++) chain_eco(k, st, xc, yc, x + (part & 1) * (cuw >> 1), y + (part >> 1) * (cuw >> 1), L - 1);
+        return;
+    }
+    if(cuw > 4) chain_split_flag(st, cuw, 0);
+    const int slice = k->pp->slice_type, B = slice == 0, mode = b->mode[idx], ny = cuw * cuw;
+    cabac_t c;
+    c.s = st->s; c.bits = 0; c.ipm[0] = st->ipm[0]; c.ipm[1] = st->ipm[1];
+    int16_t *coef = malloc(sizeof(int16_t) * 3 * ny / 2);                            /* coef_rect_to_series */
+    for(int j = 0; j < cuw; j++) memcpy(coef + j * cuw, b->coef[0] + (y - yc + j) * 64 + (x - xc), 2 * cuw);
+    for(int p = 1; p < 3; p++)
+        for(int j = 0; j < cuw / 2; j++)
+            memcpy(coef + ny + (p - 1) * (ny / 4) + j * (cuw / 2), b->coef[p] + ((y - yc) / 2 + j) * 32 + (x - xc) / 2, cuw);
+    if(slice != 2) {
+        cb_bin(&c, XB200_CM_SKIP_FLAG, mode == XO_MODE_SKIP);
+        if(mode == XO_MODE_SKIP) {
+            cb_mvp_idx(&c, b->mvp_idx[idx][0]);
+            if(B) cb_mvp_idx(&c, b->mvp_idx[idx][1]);
+        }
+        else {
+            cb_bin(&c, XB200_CM_PRED_MODE, mode == XO_MODE_INTRA);
+            if(mode != XO_MODE_INTRA) {
+                if(B) cb_bin(&c, XB200_CM_DIRECT, mode == XO_MODE_DIR);
+                if(mode != XO_MODE_DIR) {
+                    const int r0 = b->refi[idx][0], r1 = b->refi[idx][1];
+                    if(B) {                                                            /* xeve_eco_inter_pred_idc */
+                        if(r0 >= 0 && r1 >= 0) cb_bin(&c, XB200_CM_INTER_DIR, 0);
+                        else { cb_bin(&c, XB200_CM_INTER_DIR, 1); cb_bin(&c, XB200_CM_INTER_DIR + 1, r0 >= 0 ? 0 : 1); }
+                    }
+                    if(r0 >= 0) { cb_refi(&c, k->pp->num_refp[0], r0); cb_mvp_idx(&c, b->mvp_idx[idx][0]); cb_mvd(&c, b->mvd[idx][0]); }
+                    if(B && r1 >= 0) { cb_refi(&c, k->pp->num_refp[1], r1); cb_mvp_idx(&c, b->mvp_idx[idx][1]); cb_mvd(&c, b->mvd[idx][1]); }
+                }
+            }
+        }
+    }
+    if(mode == XO_MODE_INTRA) {
+        xb200_nbr_item nb;
+        memset(&nb, 0, sizeof(nb));
+        nb.x = (int16_t)x; nb.y = (int16_t)y; nb.log2_cuw = nb.log2_cuh = (uint8_t)(L + 2);
+        xo_intra_nbr(k->rec[0], k->rec[1], k->rec[2], k->s_l, k->s_c, &nb, k->map_scu, k->map_ipm, k->w_scu, k->h_scu, k->pp->cip,
+                     k->sq->bit_depth, k->side);                                        /* xeve_get_mpm */
+        cb_unary(&c, nb.mpm[b->ipm[idx]], XO_CM_IPM);
+        cb_coef_intra(&c, b->nnz[idx], L + 2, coef, 7);
+    }
+    else if(mode != XO_MODE_SKIP) {
+        xb200_bits_item it;
+        memset(&it, 0, sizeof(it));
+        it.log2_cuw = it.log2_cuh = (uint8_t)(L + 2); memcpy(it.nnz, b->nnz[idx], 12);
+        cb_coef(&c, &it, coef, 7);
+    }
+    free(coef);
+    st->s = c.s; st->ipm[0] = c.ipm[0]; st->ipm[1] = c.ipm[1];
+}
+int xo_sizeof_chain(int what) { return what == 0 ? (int)sizeof(xo_ctu_rec) : (int)sizeof(xo_state); }
+/* One picture.  pp: picture-level inputs (the per-CTU fields are ignored); col_mv0/1: refp[0][REFP_0/1].map_mv; out[]: one record
+ * per CTU with lcu_num / x_pel / y_pel / state_in / state_out filled; rec_*: the reconstruction before deblocking (active area);
+ * maps: frame maps as they stand when the loop filter starts (COD, intra, QP, skip and luma-cbf bits of map_scu); cus: leaf CUs
+ * in coding order; cu_log / intra_log: every inter / intra CU analysis in call order.  n_out: {leaf CUs, inter calls, intra calls}.
+ * ctu_limit > 0 stops after that many CTUs. */
+void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec *pp, const int16_t *col_mv0, const int16_t *col_mv1,
+                      xo_ctu_rec *out, double *ctu_cost, int16_t *rec_y, int16_t *rec_u, int16_t *rec_v, int s_l, int s_c,
+                      uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv, xb200_df_cu *cus, int64_t cus_cap,
+                      xb200_cu_item *cu_log, int64_t cu_cap, xb200_intra_item *intra_log, int64_t intra_cap, int64_t *n_out,
+                      int ctu_limit)
+{
+    chain_t *k = calloc(1, sizeof(chain_t));
+    k->sq = sq; k->pl = pl; k->pp = pp; k->col[0] = col_mv0; k->col[1] = col_mv1;
+    k->w = sq->w; k->h = sq->h; k->w_scu = (sq->w + 3) >> 2; k->h_scu = (sq->h + 3) >> 2;
+    k->rec[0] = rec_y; k->rec[1] = rec_u; k->rec[2] = rec_v; k->s_l = s_l; k->s_c = s_c;
+    k->map_scu = map_scu; k->map_ipm = map_ipm; k->map_refi = map_refi; k->map_mv = map_mv;
+    k->cu_log = cu_log; k->cu_cap = cu_cap; k->intra_log = intra_log; k->intra_cap = intra_cap;
+    for(int L = 0; L < 5; L++) {
+        const int ny = 16 << (2 * L);
+        for(int t = 0; t < 2; t++) {
+            cud_t *d = t ? &k->temp[L] : &k->best[L];
+            d->rec[0] = calloc((size_t)ny * 3, sizeof(int16_t)); d->rec[1] = d->rec[0] + ny; d->rec[2] = d->rec[1] + ny / 4;
+            d->coef[0] = d->rec[2] + ny / 4; d->coef[1] = d->coef[0] + ny; d->coef[2] = d->coef[1] + ny / 4;
+        }
+    }
+    k->coef = calloc(2 * (64 * 64 * 3 / 2 + 64), sizeof(int16_t)); k->rec_cu = calloc(2 * (64 * 64 * 3 / 2 + 64), sizeof(int16_t));
+    k->pred_y = calloc(64 * 64, sizeof(int16_t)); k->side = calloc(8 * 64 + 6 + 16, sizeof(int16_t));
+    const int64_t f = (int64_t)k->w_scu * k->h_scu;
+    memset(map_scu, 0, 4 * f); memset(map_ipm, 0, f); memset(map_refi, 0, 2 * f); memset(map_mv, 0, 8 * f);
+    xo_state st;                                   /* xeve_sbac_reset with cm_init off: every model PROB_INIT, range 16384 */
+    memset(&st, 0, sizeof(st));
+    st.s.range = 16384;
+    for(int i = 0; i < XB200_CM_COUNT; i++) st.s.m[i] = 512;
+    st.ipm[0] = st.ipm[1] = st.split = 512;
+    const int w_lcu = (k->w + 63) >> 6, h_lcu = (k->h + 63) >> 6;
+    int64_t   n_leaf = 0;
+    for(int lcu = 0; lcu < w_lcu * h_lcu && (ctu_limit <= 0 || lcu < ctu_limit); lcu++) {
+        const int x = (lcu % w_lcu) << 6, y = (lcu / w_lcu) << 6;
+        out[lcu] = *pp;
+        out[lcu].lcu_num = lcu; out[lcu].x_pel = x; out[lcu].y_pel = y; out[lcu].state_in = st;
+        cud_init(&k->best[4], 4); cud_init(&k->temp[4], 4);                               /* mode_init_lcu */
+        k->curr[4] = st;
+        const double c = chain_tree(k, x, y, 4, 0, 1);
+        if(ctu_cost) ctu_cost[lcu] = c;
+        out[lcu].state_out = k->next[4];
+        /* mode_analyze_lcu: update_to_ctx_map; then the bitstream pass marks every CU coded and sets the luma cbf bit
+         * (xeve_eco_unit, src_base/xeve_eco.c:1575-1603) */
+        chain_update_map(k, x, y, 4);
+        const int ws = ((x + 64 > k->w ? k->w - x : 64) >> 2), hs = ((y + 64 > k->h ? k->h - y : 64) >> 2);
+        for(int j = 0; j < hs; j++)
+            for(int i = 0; i < ws; i++)
+                if(k->best[4].nnz[j * 16 + i][0] > 0) k->map_scu[(int64_t)((y >> 2) + j) * k->w_scu + (x >> 2) + i] |= 1u << 24;
+        chain_leaves(k, x, y, x, y, 4, cus, cus_cap, &n_leaf);
+        chain_eco(k, &st, x, y, x, y, 4);
+    }
+    n_out[0] = n_leaf; n_out[1] = k->n_cu; n_out[2] = k->n_intra;
+    for(int L = 0; L < 5; L++) { free(k->best[L].rec[0]); free(k->temp[L].rec[0]); }
+    free(k->coef); free(k->rec_cu); free(k->pred_y); free(k->side); free(k);
+}
 
 /* FNV-1a over per-item output slots (the hash the harness records for in-situ results) */
 void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out)

@@ -9,6 +9,20 @@ typedef struct {          /* one picture: pointers to the top-left sample of the
     int32_t  s_l, s_c, w_l, h_l, poc;
 } xo_planes;
 
+/* CU decision chain (xo_chain_picture): full coder state and the per-CTU record == RH_LCU_REC of oracle/ref_harness.c */
+typedef struct { xb200_sbac s; uint16_t ipm[2], split, pad_; } xo_state;
+typedef struct {
+    int32_t  poc, slice_type, lcu_num, x_pel, y_pel, tile_qp, cur_pic;
+    int32_t  num_refp[2], ref_pic[2][4], ref_poc[2][4], col_list_poc0;
+    int32_t  max_cu_inter, min_cu_inter, max_cu_intra, min_cu_intra, cip;
+    int32_t  qp[3];
+    uint32_t lambda_mv;
+    int32_t  max_search_range, pad_;
+    double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
+    int64_t  col_off[2];
+    xo_state state_in, state_out;
+} xo_ctu_rec;
+
 #define XO_API __attribute__((visibility("default")))
 XO_API int     xo_sad(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd);
 XO_API int64_t xo_ssd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, int bd);
@@ -52,6 +66,12 @@ XO_API void xo_mvp(xb200_mvp_item *it, const xb200_mvp_pic *pp, const uint32_t *
                    const int16_t *col_mv1);
 XO_API void xo_mvp_batch(xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pp, const uint32_t *map_scu, const int16_t *map_mv,
                          const int16_t *col_mv0, const int16_t *col_mv1);
+XO_API int  xo_sizeof_chain(int what);
+XO_API void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec *pp, const int16_t *col_mv0, const int16_t *col_mv1,
+                             xo_ctu_rec *out, double *ctu_cost, int16_t *rec_y, int16_t *rec_u, int16_t *rec_v, int s_l, int s_c,
+                             uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv, xb200_df_cu *cus, int64_t cus_cap,
+                             xb200_cu_item *cu_log, int64_t cu_cap, xb200_intra_item *intra_log, int64_t intra_cap, int64_t *n_out,
+                             int ctu_limit);
 XO_API void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out);
 XO_API void xo_deblock(int16_t *y, int16_t *u, int16_t *v, int s_l, int s_c, int w, int h, const xb200_df_cu *cus, int64_t n,
                        const xb200_df_pic *pp, const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int bit_depth);

@@ -287,8 +287,8 @@ def test_oracle_full_size_in_situ(clip, preset, min_intra, min_cu):
     encoded by the reference (low delay, so the second is an inter picture) -- every pintra_analyze_cu call (172 k at 1080p, CU 4x4 ..
     64x64), every xeve_pinter_analyze_cu call (42 k) and both loop-filter passes, reproduced by the oracle from the traced inputs:
     costs as IEEE doubles, coder states, coefficient and reconstruction hashes, deblocked pictures"""
-    td = tracedata.live_trace(clip, frames=2, pic_lo=0, pic_hi=1, preset=preset, mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU,
-                              extra="bframes=0")
+    td = tracedata.live_trace(clip, frames=2, pic_lo=0, pic_hi=1, preset=preset,
+                              mask=rh.TRACE_INTRA | rh.TRACE_DF | rh.TRACE_CU | rh.TRACE_LCU, extra="bframes=0")
     td.intra = td.live.intra.copy()
     assert len(td.intra) > min_intra and len(td.cu) > min_cu
     _oracle_intra(td)
@@ -298,6 +298,9 @@ def test_oracle_full_size_in_situ(clip, preset, min_intra, min_cu):
     for d in tracedata.df_from_trace(td.live):
         got = xo.deblock(d["pre"], d["cus"], d["pp"], d["map_scu"], d["map_refi"], d["map_mv"])
         assert all(np.array_equal(g, e) for g, e in zip(got, d["post"]))
+    # the same two pictures through the decision chain: the oracle picks every CU itself (3 174 + 1 512 leaf CUs at 1080p)
+    out = tracedata.chain_sequence(*tracedata.chain_inputs_from_trace(td.live))
+    assert len(out[0]["intra_log"]) + len(out[1]["intra_log"]) == len(td.intra) and len(out[1]["cu_log"]) == len(td.cu)
 
 
 @needs_ref
@@ -332,3 +335,48 @@ def test_oracle_mvp_inputs_match_reference():
         for fld in ("avail", "refi", "mvp", "mv_dir"):
             assert np.array_equal(got[fld], exp[fld]), (fld, poc)
     assert len(np.unique(exp["avail"])) > 10 and (exp["mvp"][:, :3] == 1).all(-1).any()
+
+
+# ---- CU decision chain: mode_coding_tree over whole pictures (SURVEY 8a' q15 / q16) ---------------------------------------------
+def test_oracle_decision_chain_matches_golden():
+    """three pictures (intra, then two bi-predicted ones referencing the earlier two) encoded by the oracle alone from the original
+    pictures and the picture-level parameters: xo_chain_picture -> xo_deblock -> xo_pad_plane, each result feeding the next picture.
+    Coder state before / after every CTU, frame maps, leaf CUs and the deblocked pictures equal what the reference produced."""
+    seq, pics = tracedata.chain_golden()
+    out = tracedata.chain_sequence(seq, pics)
+    assert [r["slice_type"] for r in out] == [2, 0, 0]
+    assert len(out[0]["intra_log"]) > 500 and len(out[2]["cu_log"]) > 100 and len(out[2]["intra_log"]) > 0
+    modes = np.concatenate([r["cu_log"]["best_idx"] for r in out[1:]])
+    assert len(np.unique(modes)) >= 4                                   # SKIP, DIRECT, uni- and bi-prediction all won somewhere
+    sizes = np.concatenate([r["cus"]["log2_cuw"] for r in out])
+    assert set(np.unique(sizes)) >= {2, 3, 4, 5}                        # leaf CUs from 4x4 to 32x32 (64x64 ones: the live tests)
+
+
+@needs_ref
+def test_oracle_decision_chain_whole_sequence():
+    """all 20 pictures of the default hierarchical-B GOP (intra picture, anchors, four B layers incl. the odd POCs whose early CU
+    termination threshold differs): the oracle's own reconstruction is the only reference data later pictures see, and every
+    picture still equals the reference's -- a whole-sequence statement of rows a1 - a14, f-1, f-2, f-3 and the tree around them."""
+    seq, pics = tracedata.live_chain(frames=20)
+    out = tracedata.chain_sequence(seq, pics)
+    assert len(out) == 20 and sorted(r["poc"] for r in out) == list(range(20))
+    calls = [len(r["cu_log"]) for r in out[1:]]
+    assert min(calls) < max(calls)                                      # early termination skipped sub-trees in some pictures
+
+
+CHAIN_CONFIGS = [
+    ("2160p10", "fast", 6, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),        # 10-bit input
+    ("cif", "fast", 8, "rdoq=0;qp=27", dict(tracedata.QCIF)),                                          # plain quantiser, lower QP
+    ("cif", "fast", 8, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # low delay, P slices
+    ("cif", "medium", 8, "qp=40", dict(tracedata.QCIF)),                                               # high QP: many all-zero blocks
+    ("cif", "medium", 6, "qp=22", {}),                                                                 # CIF 352x288, low QP
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,preset,frames,extra,override", CHAIN_CONFIGS)
+def test_oracle_decision_chain_other_configs(name, preset, frames, extra, override):
+    """P slices need the bitstream-order state walk (chain_eco): their RDO counter codes a direct_mode_flag the bitstream lacks"""
+    seq, pics = tracedata.live_chain(name, frames, preset, extra, **override)
+    out = tracedata.chain_sequence(seq, pics)
+    assert len(out) == frames

@@ -243,3 +243,107 @@ def get_trace() -> TraceData:
     if rh.available():
         return live_trace()
     return golden_trace()
+
+
+# ---- CU decision chain (mode_coding_tree over whole pictures / a whole sequence) --------------------------------------
+CHAIN_GOLDEN = os.path.join(ROOT, "tests", "golden", "chain_golden.npz")
+
+
+def chain_dtypes():
+    from xeve_b200 import api
+    return rh.LCU_REC, rh.DF_CU, api.CU_ITEM, api.INTRA_ITEM
+
+
+def chain_inputs_from_trace(tr):
+    """(seq, pictures in coding order) of a live trace recorded with rh.TRACE_LCU | rh.TRACE_DF from picture 0.  Per picture:
+    pp = the picture-level parameters a rate controller / reference-list manager supplies (LCU_REC of CTU 0: slice type, QP,
+    lambdas, reference POCs, CU size limits), df_pp (DF_PIC), org = the original picture, expect = what the reference produced
+    (per-CTU coder states, frame maps, leaf CUs, the picture before / after deblocking)."""
+    td = from_live(tr)
+    dfs = {d["poc"]: d for d in df_from_trace(tr)}
+    pics = []
+    for idx in np.flatnonzero(tr.lcu["lcu_num"] == 0):
+        pp = tr.lcu[idx].copy()
+        poc, d = int(pp["poc"]), dfs[int(pp["poc"])]
+        recs = tr.lcu[tr.lcu["poc"] == poc]
+        pics.append(dict(pp=pp, df_pp=d["pp"], org=td.planes[int(pp["cur_pic"])],
+                         expect=dict(state_in=recs["state_in"].copy(), state_out=recs["state_out"].copy(), map_scu=d["map_scu"],
+                                     map_refi=np.asarray(d["map_refi"]), map_mv=np.asarray(d["map_mv"]), cus=d["cus"], pre=d["pre"],
+                                     post=d["post"])))
+    return td.seq, pics
+
+
+def chain_golden():
+    z = np.load(CHAIN_GOLDEN)
+    pics = []
+    for i in range(int(z["n"])):
+        g = lambda k: z[f"{k}{i}"]  # noqa: E731
+        pics.append(dict(pp=g("pp")[0], df_pp=g("df_pp")[0], org=[g("org_y"), g("org_u"), g("org_v")],
+                         expect=dict(state_in=g("state_in"), state_out=g("state_out"), map_scu=g("map_scu"), map_refi=g("map_refi"),
+                                     map_mv=g("map_mv"), cus=g("cus"), pre=None, post=[g("post_y"), g("post_u"), g("post_v")])))
+    return z["seq"], pics
+
+
+def chain_sequence(seq, pics, check=True):
+    """Encode the pictures with the oracle alone: per picture xo_chain_picture (every CTU's mode_coding_tree) -> xo_deblock ->
+    xo_pad_plane, the result becoming the reference picture and the colocated MV map of later pictures.  Nothing of the reference's
+    own reconstruction is read; with check=True every picture's coder states, frame maps, leaf CUs and pictures before / after
+    deblocking are asserted equal to `expect`."""
+    bd = int(np.asarray(seq).reshape(-1)[0]["bit_depth"])
+    planes = (xo.PLANES * (2 * len(pics)))()
+    done, keep, out = {}, [], []
+    for i, pc in enumerate(pics):
+        pp = np.array(pc["pp"]).reshape(1).copy()
+        poc = int(pp["poc"][0])
+        org = [np.ascontiguousarray(a) for a in pc["org"]]
+        keep.append(org)
+        h_org = 2 * i
+        planes[h_org].y, planes[h_org].u, planes[h_org].v = [a.ctypes.data for a in org]
+        planes[h_org].s_l, planes[h_org].s_c = org[0].shape[1], org[1].shape[1]
+        planes[h_org].w_l, planes[h_org].h_l, planes[h_org].poc = org[0].shape[1], org[0].shape[0], poc
+        pp["cur_pic"] = h_org
+        col = [None, None]
+        for l in range(2):
+            for k in range(4):
+                if int(pp["ref_pic"][0][l][k]) < 0:
+                    continue
+                rp = done[int(pp["ref_poc"][0][l][k])]     # our own reconstruction of that POC
+                pp["ref_pic"][0][l][k] = rp["handle"]
+                if k == 0:
+                    col[l] = rp["map_mv"]
+        r = xo.chain_picture(seq, planes, pp, col[0], col[1], chain_dtypes())
+        post = xo.deblock(r["rec"], r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], bit_depth=bd)
+        padded = []
+        for a, pad in zip(post, (144, 72, 72)):
+            hh, ww = a.shape
+            buf = np.zeros((hh + 2 * pad, ww + 2 * pad), np.int16)
+            buf[pad:pad + hh, pad:pad + ww] = a
+            xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
+            padded.append(buf)
+        h_rec = 2 * i + 1
+        planes[h_rec].y, planes[h_rec].u, planes[h_rec].v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(padded, (144, 72, 72))]
+        planes[h_rec].s_l, planes[h_rec].s_c = padded[0].shape[1], padded[1].shape[1]
+        planes[h_rec].w_l, planes[h_rec].h_l, planes[h_rec].poc = org[0].shape[1], org[0].shape[0], poc
+        r.update(poc=poc, post=post, padded=padded, slice_type=int(pp["slice_type"][0]), handle=h_rec)
+        done[poc] = r
+        out.append(r)
+        if check:
+            e = pc["expect"]
+            assert len(e["state_in"]) == len(r["ctu"])
+            assert r["ctu"]["state_in"].tobytes() == e["state_in"].tobytes() and r["ctu"]["state_out"].tobytes() == e["state_out"].tobytes(), poc
+            assert np.array_equal(r["map_scu"] & 0x81FF8000, e["map_scu"] & 0x81FF8000), poc   # coded, luma cbf, skip, QP, intra
+            assert np.array_equal(r["map_refi"].reshape(-1), e["map_refi"].reshape(-1)), poc
+            assert np.array_equal(r["map_mv"].reshape(-1), e["map_mv"].reshape(-1)), poc
+            assert len(r["cus"]) == len(e["cus"]) and all(np.array_equal(r["cus"][k], e["cus"][k]) for k in ("x", "y", "log2_cuw", "log2_cuh")), poc
+            assert e["pre"] is None or all(np.array_equal(a, b) for a, b in zip(r["rec"], e["pre"])), poc
+            assert all(np.array_equal(a, b) for a, b in zip(post, e["post"])), poc
+    return out
+
+
+def live_chain(name="cif", frames=20, preset="fast", extra="", **override):
+    override = override or QCIF
+    override = {k: v for k, v in override.items() if k != "n"}
+    c, yuv = clip_yuv(name, frames, **override)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_LCU | rh.TRACE_DF,
+                        pic_lo=0, pic_hi=1 << 20, want_bitstream=False)
+    return chain_inputs_from_trace(tr)
