@@ -194,6 +194,10 @@ def mvp_batch(items, pic, map_scu, map_mv, col0, col1):
     return items
 
 
+SCU_REC = np.dtype([("mode", "u1"), ("log2", "u1"), ("ipm", "i1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("pad_", "u1"),
+                    ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,))], align=True)
+
+
 def chain_picture(seq, planes, pp, col0, col1, dtypes, ctu_limit=0):
     """xo_chain_picture: the CU decision chain of one picture (mode_coding_tree over every CTU).  pp: one CTU record (the
     harness's LCU_REC layout) carrying the picture-level inputs; dtypes = (LCU_REC, DF_CU, CU_ITEM, INTRA_ITEM).  Returns a
@@ -218,10 +222,12 @@ def chain_picture(seq, planes, pp, col0, col1, dtypes, ctu_limit=0):
     L = lib()
     assert L.xo_sizeof_chain(0) == lcu_dt.itemsize, (L.xo_sizeof_chain(0), lcu_dt.itemsize)
     L.xo_chain_picture.restype = None
-    L.xo_chain_picture.argtypes = [VP] * 10 + [I, I] + [VP] * 5 + [C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, I]
+    assert L.xo_sizeof_chain(2) == SCU_REC.itemsize
+    scu, coef = np.zeros((n_ctu, 256), SCU_REC), np.zeros((n_ctu, 6144), np.int16)
+    L.xo_chain_picture.argtypes = [VP] * 10 + [I, I] + [VP] * 5 + [C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, I, VP, VP]
     L.xo_chain_picture(_p(np.ascontiguousarray(seq)), C.addressof(planes), _p(pp), _p(col0), _p(col1), _p(out), _p(cost), _p(rec[0]),
                        _p(rec[1]), _p(rec[2]), w, w // 2, _p(map_scu), _p(map_ipm), _p(map_refi), _p(map_mv), _p(cus), len(cus),
-                       _p(cu_log), cap, _p(intra_log), cap, _p(n_out), ctu_limit)
+                       _p(cu_log), cap, _p(intra_log), cap, _p(n_out), ctu_limit, _p(scu), _p(coef))
     assert n_out[1] <= cap and n_out[2] <= cap
-    return dict(ctu=out, cost=cost, rec=rec, map_scu=map_scu, map_ipm=map_ipm, map_refi=map_refi, map_mv=map_mv,
+    return dict(ctu=out, cost=cost, rec=rec, scu=scu, coef=coef, map_scu=map_scu, map_ipm=map_ipm, map_refi=map_refi, map_mv=map_mv,
                 cus=cus[:int(n_out[0])], cu_log=cu_log[:int(n_out[1])], intra_log=intra_log[:int(n_out[2])])

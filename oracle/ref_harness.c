@@ -563,8 +563,92 @@ static void state_pack(const XEVE_SBAC *d, RH_STATE *s)
     memcpy(s->ipm, d->ctx.intra_dir, 4);
     memcpy(&s->split, d->ctx.split_cu_flag, 2);
 }
+/* Decision injection: ctx->fn_mode_analyze_lcu replaced by "take the CTU's decisions from outside" -- the reference-side binding
+ * of a picture-level decision engine.  The records (oracle/xeve_oracle.h xo_scu_rec, coefficient planes, the
+ * picture before deblocking) are put where mode_analyze_lcu leaves its own results: core->cu_data_best[CTU] ->
+ * mode_cpy_rec_to_ref -> update_to_ctx_map -> ctx->map_cu_data[lcu] (src_base/xeve_mode.c:2521-2608).  The reference's own
+ * entropy coder, loop filter and picture management then run unchanged on them. */
+#define RH_T_INJECT 512
+typedef struct { uint8_t mode, log2; int8_t ipm, refi[2]; uint8_t mvp_idx[2], pad_; int16_t mv[2][2], mvd[2][2]; int32_t nnz[3]; } RH_SCU_REC;
+typedef struct { int32_t poc, s_l, s_c, pad_; const RH_SCU_REC *scu; const int16_t *coef, *rec_y, *rec_u, *rec_v; } RH_INJECT_PIC;
+static const RH_INJECT_PIC *g_inject;
+static int g_inject_n;
+static int64_t g_inject_ctus;
+RH_API void rh_inject(const RH_INJECT_PIC *pics, int n) { g_inject = pics; g_inject_n = n; g_inject_ctus = 0; }
+RH_API int64_t rh_inject_count(void) { return g_inject_ctus; }
+RH_API int rh_sizeof_inject(int what) { return what == 0 ? sizeof(RH_SCU_REC) : sizeof(RH_INJECT_PIC); }
+
+static void inject_split(XEVE_CTX *ctx, XEVE_CU_DATA *cd, const RH_SCU_REC *scu, int x0, int y0, int x, int y, int log2, int cud, int cup)
+{
+    if(x >= ctx->w || y >= ctx->h) return;
+    const int cuw = 1 << log2, leaf = scu[((y - y0) >> 2) * 16 + ((x - x0) >> 2)].log2 == log2 || log2 == 2;
+    xeve_set_split_mode(leaf ? NO_SPLIT : SPLIT_QUAD, cud, cup, cuw, cuw, ctx->max_cuwh, cd->split_mode);
+    if(leaf) return;
+    XEVE_SPLIT_STRUCT ss;
+    xeve_split_get_part_structure(SPLIT_QUAD, x, y, cuw, cuw, cup, cud, ctx->log2_culine, &ss);
+    for(int i = 0; i < ss.part_count; i++)
+        inject_split(ctx, cd, scu, x0, y0, ss.x_pos[i], ss.y_pos[i], ss.log_cuw[i], ss.cud[i], ss.cup[i]);
+}
+static int inject_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
+{
+    const RH_INJECT_PIC *ip = NULL;
+    for(int i = 0; i < g_inject_n; i++) if(g_inject[i].poc == (int)ctx->poc.poc_val) ip = &g_inject[i];
+    if(!ip) return XEVE_ERR;
+    const int L = ctx->log2_max_cuwh - 2, x0 = core->x_pel, y0 = core->y_pel, q = ctx->tile[core->tile_idx].qp;
+    const int bdc = ctx->sps.bit_depth_chroma_minus8;
+    const int qp_y = GET_LUMA_QP(q, ctx->sps.bit_depth_luma_minus8);
+    const int qp_u = ctx->qp_chroma_dynamic[0][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_u_offset)] + 6 * bdc;
+    const int qp_v = ctx->qp_chroma_dynamic[1][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_v_offset)] + 6 * bdc;
+    const RH_SCU_REC *scu = ip->scu + (size_t)core->lcu_num * 256;
+    const int16_t    *coef = ip->coef + (size_t)core->lcu_num * 6144;
+    XEVE_CU_DATA     *cd = &core->cu_data_best[L][L];
+    init_cu_data(cd, ctx->log2_max_cuwh, ctx->log2_max_cuwh, ctx->qp, ctx->qp, ctx->qp);
+    inject_split(ctx, cd, scu, x0, y0, x0, y0, ctx->log2_max_cuwh, 0, 0);
+    static const u8 mode_of[4] = {MODE_SKIP, MODE_DIR, MODE_INTER, MODE_INTRA};
+    for(int i = 0; i < 256; i++) {
+        const RH_SCU_REC *r = &scu[i];
+        if(x0 + (i & 15) * 4 >= ctx->w || y0 + (i >> 4) * 4 >= ctx->h) continue;
+        const int mode = mode_of[r->mode];
+        cd->pred_mode[i] = cd->pred_mode_chroma[i] = mode;
+        cd->skip_flag[i] = mode == MODE_SKIP; cd->mmvd_flag[i] = 0; cd->affine_flag[i] = 0; cd->ibc_flag[i] = 0;
+        for(int c = 0; c < 3; c++) {
+            cd->nnz[c][i] = r->nnz[c];
+            for(int sb = 0; sb < MAX_SUB_TB_NUM; sb++) cd->nnz_sub[c][sb][i] = sb == 0 ? r->nnz[c] : 0;
+        }
+        cd->qp_y[i] = qp_y; cd->qp_u[i] = qp_u; cd->qp_v[i] = qp_v;
+        cd->map_scu[i] = 0;
+        MCU_SET_IF_COD_SN_QP(cd->map_scu[i], mode == MODE_INTRA, ctx->slice_num, q);
+        if(mode == MODE_SKIP) MCU_SET_SF(cd->map_scu[i]);
+        cd->depth[i] = 2 * (ctx->log2_max_cuwh - r->log2);
+        cd->map_cu_mode[i] = 0;
+        MCU_SET_LOGW(cd->map_cu_mode[i], r->log2); MCU_SET_LOGH(cd->map_cu_mode[i], r->log2);
+        cd->ipm[0][i] = cd->ipm[1][i] = mode == MODE_INTRA ? r->ipm : 0;
+        for(int l = 0; l < 2; l++) {
+            cd->refi[i][l] = r->refi[l]; cd->mvp_idx[i][l] = r->mvp_idx[l];
+            cd->mv[i][l][0] = r->mv[l][0]; cd->mv[i][l][1] = r->mv[l][1]; cd->mvd[i][l][0] = r->mvd[l][0]; cd->mvd[i][l][1] = r->mvd[l][1];
+        }
+        cd->mvr_idx[i] = 0; cd->bi_idx[i] = 0; cd->mmvd_idx[i] = 0; cd->dmvr_flag[i] = 0;
+    }
+    memcpy(cd->coef[Y_C], coef, 4096 * 2); memcpy(cd->coef[U_C], coef + 4096, 1024 * 2); memcpy(cd->coef[V_C], coef + 5120, 1024 * 2);
+    for(int j = 0; j < 64 && y0 + j < ctx->h; j++)
+        memcpy(cd->reco[Y_C] + j * 64, ip->rec_y + (size_t)(y0 + j) * ip->s_l + x0, 2 * XEVE_MIN(64, ctx->w - x0));
+    for(int j = 0; j < 32 && y0 / 2 + j < ctx->h / 2; j++) {
+        memcpy(cd->reco[U_C] + j * 32, ip->rec_u + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
+        memcpy(cd->reco[V_C] + j * 32, ip->rec_v + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
+    }
+    mode_cpy_rec_to_ref(core, x0, y0, ctx->max_cuwh, ctx->max_cuwh, PIC_MODE(ctx), xeve_get_default_tree_cons(), ctx->sps.chroma_format_idc);
+    update_to_ctx_map(ctx, core);
+    copy_cu_data(&ctx->map_cu_data[core->lcu_num], cd, 0, 0, ctx->log2_max_cuwh, ctx->log2_max_cuwh, ctx->log2_max_cuwh, 0,
+                 xeve_get_default_tree_cons(), ctx->sps.chroma_format_idc);
+    const int xs = x0 >> 2, ys = y0 >> 2, w = XEVE_MIN(16, ctx->w_scu - xs), h = XEVE_MIN(16, ctx->h_scu - ys);
+    for(int j = 0; j < h; j++)
+        for(int i = 0; i < w; i++) MCU_CLR_COD(ctx->map_scu[(size_t)(ys + j) * ctx->w_scu + xs + i]);
+    g_inject_ctus++;
+    return XEVE_OK;
+}
 static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
 {
+    if((T.mask & RH_T_INJECT) && g_inject) return inject_lcu(ctx, core);
     if(!tracing(RH_T_LCU)) return T.org_lcu(ctx, core);
     static int64_t col_off[2];
     XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];

@@ -173,6 +173,7 @@ TRACE_ME, TRACE_MC, TRACE_TQ = 1, 2, 4
 TRACE_DF = 32
 TRACE_INTRA, TRACE_INTRA_TIME = 64, 128
 TRACE_LCU = 256
+TRACE_INJECT = 512
 
 
 def intra_time():
@@ -328,6 +329,40 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
     assert L.rh_sizeof_lcu() == LCU_REC.itemsize, (L.rh_sizeof_lcu(), LCU_REC.itemsize)
     tr.lcu = grab(13, LCU_REC)
     return tr
+
+
+class INJECT_PIC(C.Structure):
+    _fields_ = [("poc", C.c_int32), ("s_l", C.c_int32), ("s_c", C.c_int32), ("pad_", C.c_int32), ("scu", C.c_void_p), ("coef", C.c_void_p),
+                ("rec_y", C.c_void_p), ("rec_u", C.c_void_p), ("rec_v", C.c_void_p)]
+
+
+def encode_clip_injected(yuv, nframes, w, h, decisions, **kw):
+    """Reference encode whose mode decision (ctx->fn_mode_analyze_lcu) is REPLACED by externally supplied decisions: `decisions` =
+    per picture dict(poc, scu [n_ctu, 256] SCU records, coef [n_ctu, 6144] s16, rec (Y, U, V) before deblocking).  Everything
+    else -- entropy coding, bitstream writing, loop filter, reference picture management -- is the unmodified reference.
+    Returns (trace, CTUs injected, inter analyses run by the reference, intra analyses run by the reference)."""
+    L = lib()
+    assert L.rh_sizeof_inject(1) == C.sizeof(INJECT_PIC)
+    arr = (INJECT_PIC * len(decisions))()
+    keep = []
+    for i, d in enumerate(decisions):
+        scu, coef = np.ascontiguousarray(d["scu"]), np.ascontiguousarray(d["coef"], np.int16)
+        rec = [np.ascontiguousarray(a, np.int16) for a in d["rec"]]
+        assert scu.dtype.itemsize == L.rh_sizeof_inject(0)
+        keep.append((scu, coef, rec))
+        arr[i].poc, arr[i].s_l, arr[i].s_c = int(d["poc"]), rec[0].shape[1], rec[1].shape[1]
+        arr[i].scu, arr[i].coef = scu.ctypes.data, coef.ctypes.data
+        arr[i].rec_y, arr[i].rec_u, arr[i].rec_v = [a.ctypes.data for a in rec]
+    L.rh_inject.restype = None
+    L.rh_inject.argtypes = [C.c_void_p, C.c_int]
+    L.rh_inject_count.restype = C.c_int64
+    L.rh_inject(C.addressof(arr), len(decisions))
+    try:
+        tr = encode_clip(yuv, nframes, w, h, trace_mask=TRACE_INJECT | TRACE_CU_TIME | TRACE_INTRA_TIME, **kw)
+        n = int(L.rh_inject_count())
+    finally:
+        L.rh_inject(None, 0)
+    return tr, n, cu_time()[1], intra_time()[1]
 
 
 def replay_me(tr: Trace, recs: np.ndarray | None = None, nthreads=1):

@@ -1921,17 +1921,18 @@ static void chain_eco(const chain_t *k, xo_state *st, int xc, int yc, int x, int
     free(coef);
     st->s = c.s; st->ipm[0] = c.ipm[0]; st->ipm[1] = c.ipm[1];
 }
-int xo_sizeof_chain(int what) { return what == 0 ? (int)sizeof(xo_ctu_rec) : (int)sizeof(xo_state); }
+int xo_sizeof_chain(int what) { return what == 0 ? (int)sizeof(xo_ctu_rec) : what == 1 ? (int)sizeof(xo_state) : (int)sizeof(xo_scu_rec); }
 /* One picture.  pp: picture-level inputs (the per-CTU fields are ignored); col_mv0/1: refp[0][REFP_0/1].map_mv; out[]: one record
  * per CTU with lcu_num / x_pel / y_pel / state_in / state_out filled; rec_*: the reconstruction before deblocking (active area);
  * maps: frame maps as they stand when the loop filter starts (COD, intra, QP, skip and luma-cbf bits of map_scu); cus: leaf CUs
  * in coding order; cu_log / intra_log: every inter / intra CU analysis in call order.  n_out: {leaf CUs, inter calls, intra calls}.
- * ctu_limit > 0 stops after that many CTUs. */
+ * ctu_limit > 0 stops after that many CTUs.  scu_out / coef_out (optional): per CTU the 256 SCU records and the coefficient planes
+ * (Y 64x64 | U 32x32 | V 32x32, CU rectangles in place) -- the contents of the reference's ctx->map_cu_data[lcu]. */
 void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec *pp, const int16_t *col_mv0, const int16_t *col_mv1,
                       xo_ctu_rec *out, double *ctu_cost, int16_t *rec_y, int16_t *rec_u, int16_t *rec_v, int s_l, int s_c,
                       uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv, xb200_df_cu *cus, int64_t cus_cap,
                       xb200_cu_item *cu_log, int64_t cu_cap, xb200_intra_item *intra_log, int64_t intra_cap, int64_t *n_out,
-                      int ctu_limit)
+                      int ctu_limit, xo_scu_rec *scu_out, int16_t *coef_out)
 {
     chain_t *k = calloc(1, sizeof(chain_t));
     k->sq = sq; k->pl = pl; k->pp = pp; k->col[0] = col_mv0; k->col[1] = col_mv1;
@@ -1976,6 +1977,16 @@ void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec
                 if(k->best[4].nnz[j * 16 + i][0] > 0) k->map_scu[(int64_t)((y >> 2) + j) * k->w_scu + (x >> 2) + i] |= 1u << 24;
         chain_leaves(k, x, y, x, y, 4, cus, cus_cap, &n_leaf);
         chain_eco(k, &st, x, y, x, y, 4);
+        if(scu_out) {                                 /* what crosses the boundary to the host's entropy coder: XEVE_CU_DATA of the CTU */
+            const cud_t *b = &k->best[4];
+            for(int i = 0; i < 256; i++) {
+                xo_scu_rec *o = &scu_out[(int64_t)lcu * 256 + i];
+                memset(o, 0, sizeof(*o));
+                o->mode = b->mode[i]; o->log2 = b->log2[i]; o->ipm = b->ipm[i]; memcpy(o->refi, b->refi[i], 2);
+                memcpy(o->mvp_idx, b->mvp_idx[i], 2); memcpy(o->mv, b->mv[i], 8); memcpy(o->mvd, b->mvd[i], 8); memcpy(o->nnz, b->nnz[i], 12);
+            }
+        }
+        if(coef_out) memcpy(coef_out + (int64_t)lcu * 6144, k->best[4].coef[0], sizeof(int16_t) * 6144);
     }
     n_out[0] = n_leaf; n_out[1] = k->n_cu; n_out[2] = k->n_intra;
     for(int L = 0; L < 5; L++) { free(k->best[L].rec[0]); free(k->temp[L].rec[0]); }

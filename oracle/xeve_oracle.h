@@ -11,6 +11,13 @@ typedef struct {          /* one picture: pointers to the top-left sample of the
 
 /* CU decision chain (xo_chain_picture): full coder state and the per-CTU record == RH_LCU_REC of oracle/ref_harness.c */
 typedef struct { xb200_sbac s; uint16_t ipm[2], split, pad_; } xo_state;
+typedef struct {          /* decision of one 4x4 unit of a CTU (XEVE_CU_DATA fields the entropy coder and the loop filter read) */
+    uint8_t mode, log2;    /* 0 SKIP, 1 DIRECT, 2 INTER, 3 INTRA; log2 size of the leaf CU covering the unit */
+    int8_t  ipm, refi[2];
+    uint8_t mvp_idx[2], pad_;
+    int16_t mv[2][2], mvd[2][2];
+    int32_t nnz[3];
+} xo_scu_rec;
 typedef struct {
     int32_t  poc, slice_type, lcu_num, x_pel, y_pel, tile_qp, cur_pic;
     int32_t  num_refp[2], ref_pic[2][4], ref_poc[2][4], col_list_poc0;
@@ -71,7 +78,7 @@ XO_API void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_
                              xo_ctu_rec *out, double *ctu_cost, int16_t *rec_y, int16_t *rec_u, int16_t *rec_v, int s_l, int s_c,
                              uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv, xb200_df_cu *cus, int64_t cus_cap,
                              xb200_cu_item *cu_log, int64_t cu_cap, xb200_intra_item *intra_log, int64_t intra_cap, int64_t *n_out,
-                             int ctu_limit);
+                             int ctu_limit, xo_scu_rec *scu_out, int16_t *coef_out);
 XO_API void xo_hash_slots(const int16_t *buf, const int64_t *off, const int64_t *elems, int64_t n, uint64_t *out);
 XO_API void xo_deblock(int16_t *y, int16_t *u, int16_t *v, int s_l, int s_c, int w, int h, const xb200_df_cu *cus, int64_t n,
                        const xb200_df_pic *pp, const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int bit_depth);

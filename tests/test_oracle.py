@@ -380,3 +380,23 @@ def test_oracle_decision_chain_other_configs(name, preset, frames, extra, overri
     seq, pics = tracedata.live_chain(name, frames, preset, extra, **override)
     out = tracedata.chain_sequence(seq, pics)
     assert len(out) == frames
+
+
+INJECT_CONFIGS = [
+    ("cif", "fast", 20, "", dict(tracedata.QCIF)),                                                      # default GOP, 20 pictures
+    ("2160p10", "medium", 5, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),        # 10-bit, medium
+    ("cif", "fast", 6, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # P slices
+    ("cif", "fast", 4, "qp=24", {}),                                                                   # CIF 352x288 (BASELINE configs[0] size)
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,preset,frames,extra,override", INJECT_CONFIGS)
+def test_bitstream_is_bit_exact_with_the_decision_pass_replaced(name, preset, frames, extra, override):
+    """the picture-level boundary end to end: the reference encoder with ctx->fn_mode_analyze_lcu replaced by "take the decisions
+    from outside" (per 4x4 unit: mode, CU size, motion, MVP index, MVD, intra mode, nnz; coefficient planes; the picture before
+    deblocking), fed with what the oracle chain decided from the original pictures alone, writes the byte-identical bitstream --
+    its own entropy coder, loop filter and picture management run unchanged and none of its inter / intra analyses run"""
+    ref_bs, got_bs, n_ctu, ref_calls, out = tracedata.chain_inject_roundtrip(name, frames, preset, extra, **override)
+    assert n_ctu == sum(len(r["ctu"]) for r in out) and ref_calls == 0
+    assert len(ref_bs) > 1000 and np.array_equal(ref_bs, got_bs)

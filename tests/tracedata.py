@@ -347,3 +347,17 @@ def live_chain(name="cif", frames=20, preset="fast", extra="", **override):
     tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_LCU | rh.TRACE_DF,
                         pic_lo=0, pic_hi=1 << 20, want_bitstream=False)
     return chain_inputs_from_trace(tr)
+
+
+def chain_inject_roundtrip(name="cif", frames=20, preset="fast", extra="", **override):
+    """(reference bitstream, bitstream of the reference with its mode decision replaced by the oracle chain's decisions, CTUs injected,
+    analyses the reference still ran) -- see rh.encode_clip_injected"""
+    override = override or QCIF
+    override = {k: v for k, v in override.items() if k != "n"}
+    c, yuv = clip_yuv(name, frames, **override)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_LCU | rh.TRACE_DF,
+                        pic_lo=0, pic_hi=1 << 20)
+    out = chain_sequence(*chain_inputs_from_trace(tr))
+    dec = [dict(poc=r["poc"], scu=r["scu"], coef=r["coef"], rec=r["rec"]) for r in out]
+    tr2, n, ncu, nintra = rh.encode_clip_injected(yuv, frames, c.w, c.h, dec, in_depth=c.depth, preset=preset, extra=extra)
+    return tr.bitstream, tr2.bitstream, n, ncu + nintra, out
