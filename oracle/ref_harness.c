@@ -551,7 +551,7 @@ typedef struct {
     int32_t  max_cu_inter, min_cu_inter, max_cu_intra, min_cu_intra, cip;
     int32_t  qp[3];
     uint32_t lambda_mv;
-    int32_t  max_search_range, pad_;
+    int32_t  max_search_range, parallel_rows; /* ctx->parallel_rows: CTU rows y, y + n, ... share one coder-state chain */
     double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
     int64_t  col_off[2];            /* s16 offset in samp of refp[0][l].map_mv (f_scu x [2][2]); -1: none */
     RH_STATE state_in, state_out;
@@ -651,6 +651,8 @@ static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
     if((T.mask & RH_T_INJECT) && g_inject) return inject_lcu(ctx, core);
     if(!tracing(RH_T_LCU)) return T.org_lcu(ctx, core);
     static int64_t col_off[2];
+    static pthread_mutex_t mtx = PTHREAD_MUTEX_INITIALIZER;   /* with threads > 1 the CTU rows run concurrently */
+    pthread_mutex_lock(&mtx);
     XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];
     XEVE_PINTRA *pa = &ctx->pintra[core->thread_cnt];
     RH_LCU_REC   r;
@@ -695,10 +697,14 @@ static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
     for(int i = 0; i < 3; i++) r.lambda[i] = core->lambda[i];
     r.sqrt_lambda0 = core->sqrt_lambda[0];
     r.dist_chroma_weight[0] = core->dist_chroma_weight[0]; r.dist_chroma_weight[1] = core->dist_chroma_weight[1];
+    r.parallel_rows = ctx->parallel_rows;
     state_pack(&core->s_curr_best[L][L], &r.state_in);
+    pthread_mutex_unlock(&mtx);
     int ret = T.org_lcu(ctx, core);
     state_pack(&core->s_next_best[L][L], &r.state_out);
+    pthread_mutex_lock(&mtx);
     *(RH_LCU_REC *)vec_push(&T.lcu, 1) = r;
+    pthread_mutex_unlock(&mtx);
     return ret;
 }
 RH_API int rh_sizeof_lcu(void) { return sizeof(RH_LCU_REC); }

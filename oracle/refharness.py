@@ -208,7 +208,7 @@ LCU_REC = np.dtype([("poc", "<i4"), ("slice_type", "<i4"), ("lcu_num", "<i4"), (
                     ("cur_pic", "<i4"), ("num_refp", "<i4", (2,)), ("ref_pic", "<i4", (2, 4)), ("ref_poc", "<i4", (2, 4)),
                     ("col_list_poc0", "<i4"), ("max_cu_inter", "<i4"), ("min_cu_inter", "<i4"), ("max_cu_intra", "<i4"),
                     ("min_cu_intra", "<i4"), ("cip", "<i4"), ("qp", "<i4", (3,)), ("lambda_mv", "<u4"), ("max_search_range", "<i4"),
-                    ("pad_", "<i4"), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
+                    ("parallel_rows", "<i4"), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
                     ("col_off", "<i8", (2,)), ("state_in", STATE), ("state_out", STATE)], align=True)
 
 

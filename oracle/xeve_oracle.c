@@ -1952,15 +1952,21 @@ void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec
     k->pred_y = calloc(64 * 64, sizeof(int16_t)); k->side = calloc(8 * 64 + 6 + 16, sizeof(int16_t));
     const int64_t f = (int64_t)k->w_scu * k->h_scu;
     memset(map_scu, 0, 4 * f); memset(map_ipm, 0, f); memset(map_refi, 0, 2 * f); memset(map_mv, 0, 8 * f);
-    xo_state st;                                   /* xeve_sbac_reset with cm_init off: every model PROB_INIT, range 16384 */
-    memset(&st, 0, sizeof(st));
-    st.s.range = 16384;
-    for(int i = 0; i < XB200_CM_COUNT; i++) st.s.m[i] = 512;
-    st.ipm[0] = st.ipm[1] = st.split = 512;
+    /* xeve_sbac_reset with cm_init off: every model PROB_INIT, range 16384.  With threads = n the reference runs CTU rows y, y + n,
+     * y + 2n, ... as one chain per thread, each reset at its first row (src_base/xeve_enc.c:103-175, 322-358; a CTU waits for its
+     * upper-right neighbour only), so raster order with one state per chain reproduces it. */
     const int w_lcu = (k->w + 63) >> 6, h_lcu = (k->h + 63) >> 6;
+    const int n_chain = pp->parallel_rows > 1 ? (pp->parallel_rows > h_lcu ? h_lcu : pp->parallel_rows) : 1;
+    xo_state *chain_st = calloc((size_t)n_chain, sizeof(xo_state));
+    for(int t = 0; t < n_chain; t++) {
+        chain_st[t].s.range = 16384;
+        for(int i = 0; i < XB200_CM_COUNT; i++) chain_st[t].s.m[i] = 512;
+        chain_st[t].ipm[0] = chain_st[t].ipm[1] = chain_st[t].split = 512;
+    }
     int64_t   n_leaf = 0;
     for(int lcu = 0; lcu < w_lcu * h_lcu && (ctu_limit <= 0 || lcu < ctu_limit); lcu++) {
         const int x = (lcu % w_lcu) << 6, y = (lcu / w_lcu) << 6;
+        xo_state  st = chain_st[(lcu / w_lcu) % n_chain];
         out[lcu] = *pp;
         out[lcu].lcu_num = lcu; out[lcu].x_pel = x; out[lcu].y_pel = y; out[lcu].state_in = st;
         cud_init(&k->best[4], 4); cud_init(&k->temp[4], 4);                               /* mode_init_lcu */
@@ -1977,6 +1983,7 @@ void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec
                 if(k->best[4].nnz[j * 16 + i][0] > 0) k->map_scu[(int64_t)((y >> 2) + j) * k->w_scu + (x >> 2) + i] |= 1u << 24;
         chain_leaves(k, x, y, x, y, 4, cus, cus_cap, &n_leaf);
         chain_eco(k, &st, x, y, x, y, 4);
+        chain_st[(lcu / w_lcu) % n_chain] = st;
         if(scu_out) {                                 /* what crosses the boundary to the host's entropy coder: XEVE_CU_DATA of the CTU */
             const cud_t *b = &k->best[4];
             for(int i = 0; i < 256; i++) {
@@ -1990,7 +1997,7 @@ void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec
     }
     n_out[0] = n_leaf; n_out[1] = k->n_cu; n_out[2] = k->n_intra;
     for(int L = 0; L < 5; L++) { free(k->best[L].rec[0]); free(k->temp[L].rec[0]); }
-    free(k->coef); free(k->rec_cu); free(k->pred_y); free(k->side); free(k);
+    free(k->coef); free(k->rec_cu); free(k->pred_y); free(k->side); free(k); free(chain_st);
 }
 
 /* FNV-1a over per-item output slots (the hash the harness records for in-situ results) */

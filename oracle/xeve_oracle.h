@@ -24,7 +24,7 @@ typedef struct {
     int32_t  max_cu_inter, min_cu_inter, max_cu_intra, min_cu_intra, cip;
     int32_t  qp[3];
     uint32_t lambda_mv;
-    int32_t  max_search_range, pad_;
+    int32_t  max_search_range, parallel_rows; /* ctx->parallel_rows (threads, at most the CTU rows): CTU rows y, y + n, .. share a state chain */
     double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];
     int64_t  col_off[2];
     xo_state state_in, state_out;

@@ -369,7 +369,7 @@ CHAIN_CONFIGS = [
     ("cif", "fast", 8, "rdoq=0;qp=27", dict(tracedata.QCIF)),                                          # plain quantiser, lower QP
     ("cif", "fast", 8, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # low delay, P slices
     ("cif", "medium", 8, "qp=40", dict(tracedata.QCIF)),                                               # high QP: many all-zero blocks
-    ("cif", "medium", 6, "qp=22", {}),                                                                 # CIF 352x288, low QP
+    ("cif", "medium", 6, "qp=22", dict(w=352, h=288)),   # CIF 352x288, low QP
 ]
 
 
@@ -386,7 +386,7 @@ INJECT_CONFIGS = [
     ("cif", "fast", 20, "", dict(tracedata.QCIF)),                                                      # default GOP, 20 pictures
     ("2160p10", "medium", 5, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),        # 10-bit, medium
     ("cif", "fast", 6, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # P slices
-    ("cif", "fast", 4, "qp=24", {}),                                                                   # CIF 352x288 (BASELINE configs[0] size)
+    ("cif", "fast", 4, "qp=24", dict(w=352, h=288)),     # CIF 352x288 (BASELINE configs[0] size)
 ]
 
 
@@ -400,3 +400,15 @@ def test_bitstream_is_bit_exact_with_the_decision_pass_replaced(name, preset, fr
     ref_bs, got_bs, n_ctu, ref_calls, out = tracedata.chain_inject_roundtrip(name, frames, preset, extra, **override)
     assert n_ctu == sum(len(r["ctu"]) for r in out) and ref_calls == 0
     assert len(ref_bs) > 1000 and np.array_equal(ref_bs, got_bs)
+
+
+@needs_ref
+@pytest.mark.parametrize("threads,override", [(2, dict(tracedata.QCIF)), (4, dict(w=352, h=288))])
+def test_oracle_decision_chain_threaded_reference(threads, override):
+    """the reference with threads = n decides CTU rows y, y + n, ... as one coder-state chain per thread (each reset at its first row,
+    a CTU waiting for its upper-right neighbour only); the oracle reproduces those decisions too -- n independent chains per picture"""
+    seq, pics = tracedata.live_chain("cif", 6, "fast", "", threads=threads, **override)
+    assert int(pics[0]["pp"]["parallel_rows"]) == threads
+    first_of_rows = pics[1]["expect"]["state_in"][::(int(np.asarray(seq).reshape(-1)[0]["w"]) + 63) // 64]
+    assert all(int(s["range"]) == 16384 and (s["m"] == 512).all() for s in first_of_rows[:threads])   # every chain starts from reset
+    tracedata.chain_sequence(seq, pics)

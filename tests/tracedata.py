@@ -266,6 +266,7 @@ def chain_inputs_from_trace(tr):
         pp = tr.lcu[idx].copy()
         poc, d = int(pp["poc"]), dfs[int(pp["poc"])]
         recs = tr.lcu[tr.lcu["poc"] == poc]
+        recs = recs[np.argsort(recs["lcu_num"], kind="stable")]     # threads > 1: CTU rows are recorded as they finish
         pics.append(dict(pp=pp, df_pp=d["pp"], org=td.planes[int(pp["cur_pic"])],
                          expect=dict(state_in=recs["state_in"].copy(), state_out=recs["state_out"].copy(), map_scu=d["map_scu"],
                                      map_refi=np.asarray(d["map_refi"]), map_mv=np.asarray(d["map_mv"]), cus=d["cus"], pre=d["pre"],
@@ -340,12 +341,12 @@ def chain_sequence(seq, pics, check=True):
     return out
 
 
-def live_chain(name="cif", frames=20, preset="fast", extra="", **override):
+def live_chain(name="cif", frames=20, preset="fast", extra="", threads=1, **override):
     override = override or QCIF
     override = {k: v for k, v in override.items() if k != "n"}
     c, yuv = clip_yuv(name, frames, **override)
-    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_LCU | rh.TRACE_DF,
-                        pic_lo=0, pic_hi=1 << 20, want_bitstream=False)
+    tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, threads=threads,
+                        trace_mask=rh.TRACE_LCU | rh.TRACE_DF, pic_lo=0, pic_hi=1 << 20, want_bitstream=False)
     return chain_inputs_from_trace(tr)
 
 
