@@ -275,6 +275,56 @@ void xo_inv_transform(int16_t *blk, int log2w, int log2h, int bd)
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Main profile, first piece: the "IQT" transforms, two 16-bit stages (sps.tool_iqt = 1).
+ * Forward: xeve_trans with iqt_flag (src_main/xevem_tq.c:709-716) over tx_pb2 .. tx_pb64 (:58-334): rows with
+ * shift log2w - 1 + bd - 8, then columns with shift log2h + 6 (src_base/xeve_util.c:1348-1351), each stage rounded and
+ * stored as s16 (plain truncation); the 64-point stage leaves outputs 32..63 zero.  Inverse: xeve_itrans
+ * (src_main/xevem_itdq.c:551-557) over itx_pb2 .. itx_pb64 (:302-549): columns with shift 7, rows with shift 12 - (bd - 8),
+ * each stage clipped to s16.  Blocks may be non-square (binary / ternary splits).  The butterflies are exact integer
+ * arithmetic, so each stage is a matrix product with the transform matrix the Baseline path uses.
+ * ------------------------------------------------------------------------------------------- */
+static void iqt_stage_fwd(const int16_t *src, int16_t *dst, int log2n, int shift, int line)   /* tx_pbN: dst[k * line + j] */
+{
+    const int n = 1 << log2n, kmax = n == 64 ? 32 : n, add = shift == 0 ? 0 : 1 << (shift - 1);
+    for(int j = 0; j < line; j++)
+        for(int k = 0; k < n; k++) {
+            int acc = 0;
+            if(k < kmax) {
+                for(int x = 0; x < n; x++) acc += tm(log2n, k, x) * src[j * n + x];
+                acc = (acc + add) >> shift;
+            }
+            dst[k * line + j] = (int16_t)acc;
+        }
+}
+static void iqt_stage_inv(const int16_t *src, int16_t *dst, int log2n, int shift, int line)   /* itx_pbN: dst[j * n + x] */
+{
+    const int n = 1 << log2n, kmax = n == 64 ? 32 : n, add = shift == 0 ? 0 : 1 << (shift - 1);
+    for(int j = 0; j < line; j++)
+        for(int x = 0; x < n; x++) {
+            int acc = 0;
+            for(int k = 0; k < kmax; k++) acc += tm(log2n, k, x) * src[k * line + j];
+            acc = (acc + add) >> shift;
+            dst[j * n + x] = (int16_t)(acc < -32768 ? -32768 : acc > 32767 ? 32767 : acc);
+        }
+}
+void xo_iqt_fwd(int16_t *blk, int log2w, int log2h, int bd)
+{
+    oracle_init();
+    int16_t *t = malloc(sizeof(int16_t) << (log2w + log2h));
+    iqt_stage_fwd(blk, t, log2w, log2w - 1 + bd - 8, 1 << log2h);
+    iqt_stage_fwd(t, blk, log2h, log2h + 6, 1 << log2w);
+    free(t);
+}
+void xo_iqt_inv(int16_t *blk, int log2w, int log2h, int bd)
+{
+    oracle_init();
+    int16_t *t = malloc(sizeof(int16_t) << (log2w + log2h));
+    iqt_stage_inv(blk, t, log2h, 7, 1 << log2w);
+    iqt_stage_inv(t, blk, log2w, 12 - (bd - 8), 1 << log2h);
+    free(t);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * quantisation with RDOQ (square blocks), src_base/xeve_tq.c:425-730
  * ------------------------------------------------------------------------------------------- */
 typedef struct { const xb200_rates *r; int ctx; int64_t lambda; } rate_env;

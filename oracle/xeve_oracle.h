@@ -42,6 +42,8 @@ XO_API void xo_mc_chroma(const int16_t *ref, int sr, int gx, int gy, int sel_x, 
 XO_API void xo_mc(const xb200_seq *sq, const xo_planes *pl, const xb200_mc_item *it, int16_t *pred);
 XO_API void xo_fwd_transform(int16_t *blk, int log2w, int log2h, int bd);
 XO_API void xo_inv_transform(int16_t *blk, int log2w, int log2h, int bd);
+XO_API void xo_iqt_fwd(int16_t *blk, int log2w, int log2h, int bd);
+XO_API void xo_iqt_inv(int16_t *blk, int log2w, int log2h, int bd);
 XO_API int  xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intra, int ch, int slice_type,
                           const xb200_rates *rt, int bd);
 XO_API int  xo_quant_plain(int16_t *coef, int log2n, int qp, int slice_type, int bd);

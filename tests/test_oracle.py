@@ -412,3 +412,50 @@ def test_oracle_decision_chain_threaded_reference(threads, override):
     first_of_rows = pics[1]["expect"]["state_in"][::(int(np.asarray(seq).reshape(-1)[0]["w"]) + 63) // 64]
     assert all(int(s["range"]) == 16384 and (s["m"] == 512).all() for s in first_of_rows[:threads])   # every chain starts from reset
     tracedata.chain_sequence(seq, pics)
+
+
+# ---- Main profile, first piece: the two-stage 16-bit "IQT" transforms ---------------------------------------------
+MAIN_REF = os.path.join(os.path.dirname(rh._LIB_PATH), "libxeve_main_ref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(MAIN_REF), reason="oracle/_ref/libxeve_main_ref.so (Main-profile reference) not built here")
+def test_oracle_iqt_transforms_match_main_reference():
+    """xo_iqt_fwd / xo_iqt_inv == the Main-profile reference's two-stage transforms (xeve_trans / xeve_itrans with tool_iqt: tx_pbN then
+    tx_pbM with an s16 between the stages) for every block shape the tree can produce (2..64 per side, aspect ratio <= 4), 8- and
+    10-bit: its C table for any s16 input, its AVX2 table (what it runs with) for residuals of the coded bit depth"""
+    M, L = C.CDLL(MAIN_REF), xo.lib()
+    fn_t = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int)
+
+    def aligned(n):
+        raw = np.zeros(n + 64, np.int16)
+        off = (-raw.ctypes.data % 128) // 2
+        return raw[off:off + n]
+    rng = np.random.default_rng(5)
+    big_a, big_t = aligned(4096 + 256), aligned(4096 + 256)
+    for names in (("xeve_tbl_tx", "xeve_tbl_itx"), ("xeve_tbl_tx_avx", "xeve_tbl_itx_avx")):
+        tx = [fn_t(a) for a in (C.c_void_p * 6).in_dll(M, names[0])]
+        itx = [fn_t(a) for a in (C.c_void_p * 6).in_dll(M, names[1])]
+        n = 0
+        for bd in (8, 10):
+            for lw in range(1, 7):
+                for lh in range(max(1, lw - 2), min(6, lw + 2) + 1):
+                    w, h = 1 << lw, 1 << lh
+                    for amp in ((64, (1 << bd) - 1) if "avx" in names[0] else (64, (1 << bd) - 1, 32767)):
+                        blk = rng.integers(-amp, amp + 1, w * h).astype(np.int16)
+                        a, t = big_a[:w * h], big_t[:w * h]
+                        a[:] = blk
+                        tx[lw - 1](p(a), p(t), lw - 1 + bd - 8, h)
+                        tx[lh - 1](p(t), p(a), lh + 6, w)
+                        got = blk.copy()
+                        L.xo_iqt_fwd(p(got), lw, lh, bd)
+                        assert np.array_equal(a, got), ("fwd", names[0], bd, lw, lh, amp)
+                        if w == 64:
+                            assert not got.reshape(h, w)[:, 32:].any()          # the 64-point stage keeps 32 outputs
+                        a[:] = got
+                        itx[lh - 1](p(a), p(t), 7, w)
+                        itx[lw - 1](p(t), p(a), 12 - (bd - 8), h)
+                        back = got.copy()
+                        L.xo_iqt_inv(p(back), lw, lh, bd)
+                        assert np.array_equal(a, back), ("inv", names[1], bd, lw, lh, amp)
+                        n += 1
+        assert n >= 96
