@@ -1669,6 +1669,12 @@ typedef struct {
     xb200_cu_item *cu_log; xb200_intra_item *intra_log; int64_t cu_cap, intra_cap, n_cu, n_intra;
 } chain_t;
 
+/* Optional stand-ins for the two per-CU analyses (tests plug the CUDA library in here, so that the operators under test run inside
+ * the real decision chain): same records as xo_analyze_cu / xo_analyze_intra with one item, states[0] in / states[1] out. */
+static xo_chain_cu_fn    g_chain_cu_fn;
+static xo_chain_intra_fn g_chain_intra_fn;
+void xo_chain_set_callbacks(xo_chain_cu_fn cu_fn, xo_chain_intra_fn intra_fn) { g_chain_cu_fn = cu_fn; g_chain_intra_fn = intra_fn; }
+
 static void cud_init(cud_t *d, int L)       /* init_cu_data: everything the chain reads later */
 {
     const int n = 1 << (2 * L);
@@ -1780,9 +1786,12 @@ static double chain_unit(chain_t *k, int x, int y, int L, int cud)   /* mode_cod
         }
         cu.rate_idx = 0; cu.state_in = 0; cu.state_out = 1; cu.out_off = 0;
         st[0] = k->curr[L].s;
-        g_pred_y_sink = k->pred_y;
-        xo_analyze_cu(k->sq, k->pl, &rates, &cu, st, k->coef, k->rec_cu);
-        g_pred_y_sink = NULL;
+        if(g_chain_cu_fn) g_chain_cu_fn(&cu, st, &rates, k->coef, k->rec_cu, k->pred_y);
+        else {
+            g_pred_y_sink = k->pred_y;
+            xo_analyze_cu(k->sq, k->pl, &rates, &cu, st, k->coef, k->rec_cu);
+            g_pred_y_sink = NULL;
+        }
         if(k->n_cu < k->cu_cap) k->cu_log[k->n_cu] = cu;
         k->n_cu++;
         k->cu_mode = cu.best_idx == 3 ? XO_MODE_SKIP : cu.best_idx == 4 ? XO_MODE_DIR : XO_MODE_INTER;
@@ -1816,7 +1825,8 @@ static double chain_unit(chain_t *k, int x, int y, int L, int cud)   /* mode_cod
         st[0] = k->curr[L].s; st[1] = st[0];
         /* the inter winner's reconstruction already sits in cu_data_temp; the intra trial works in its own buffers */
         int16_t *coef_i = k->coef + 3 * ny / 2 + 64, *rec_i = k->rec_cu + 3 * ny / 2 + 64;
-        xo_analyze_intra(k->sq, k->pl, &rates, &it, st, k->side, coef_i, rec_i);
+        if(g_chain_intra_fn) g_chain_intra_fn(&it, st, &rates, k->side, coef_i, rec_i);
+        else xo_analyze_intra(k->sq, k->pl, &rates, &it, st, k->side, coef_i, rec_i);
         if(k->n_intra < k->intra_cap) k->intra_log[k->n_intra] = it;
         k->n_intra++;
         if(it.cost < cost_best) {

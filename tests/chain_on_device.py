@@ -1,0 +1,114 @@
+"""The CUDA library inside the real decision chain (run by tests/test_zz_gpu_chain.py in a subprocess, or by hand).
+
+Every xeve_pinter_analyze_cu / pintra_analyze_cu of every CU the tree visits, the winner's prediction and the loop filter + border
+expansion of every picture are computed by libxeve_b200.so on the device (xb200_analyze_cu, xb200_analyze_intra, xb200_mc,
+xb200_deblock; reference pictures stay device-resident); the tree bookkeeping around them is the oracle's (test infrastructure as the
+DRIVER, not as the thing under test).  Checked: coder states per CTU, frame maps, leaf CUs and the deblocked pictures equal the
+reference's for the committed three-picture fixture and, where oracle/_ref is present, for a live 6-picture encode whose decisions are
+then injected into the unmodified reference: the bitstream must be byte-identical.
+
+  python tests/chain_on_device.py             # needs a GPU
+  python tests/chain_on_device.py --stand-in  # same plumbing with a CPU stand-in for the device context (no GPU; plumbing check)
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tracedata  # noqa: E402
+from tracedata import rh, xo  # noqa: E402
+
+
+class StandIn:
+    """CPU stand-in with the Hotpath methods the chain uses (oracle functions on host copies of the pictures)."""
+
+    def __init__(self, seq):
+        self.seq, self.pics, self.planes = seq, {}, (xo.PLANES * 4096)()
+
+    def pic_create(self, padded):
+        h = len(self.pics)
+        self.pics[h] = dict(padded=padded)
+        return h
+
+    def _bind(self, h, bufs, pads):
+        self.pics[h]["bufs"] = bufs
+        self.planes[h].y, self.planes[h].u, self.planes[h].v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(bufs, pads)]
+        self.planes[h].s_l, self.planes[h].s_c = bufs[0].shape[1], bufs[1].shape[1]
+
+    def pic_upload_s16(self, h, y, u, v):
+        self.pics[h]["act"] = [np.array(a, np.int16) for a in (y, u, v)]
+        if not self.pics[h]["padded"]:
+            self._bind(h, self.pics[h]["act"], (0, 0, 0))
+
+    def deblock(self, h, cus, pp, map_scu, map_refi, map_mv, expand=True):
+        post = xo.deblock(self.pics[h]["act"], cus, pp, map_scu, map_refi, map_mv, bit_depth=int(np.asarray(self.seq).reshape(-1)[0]["bit_depth"]))
+        bufs = []
+        for a, pad in zip(post, (144, 72, 72)):
+            hh, ww = a.shape
+            buf = np.zeros((hh + 2 * pad, ww + 2 * pad), np.int16)
+            buf[pad:pad + hh, pad:pad + ww] = a
+            xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
+            bufs.append(buf)
+        self.pics[h]["act"] = post
+        self._bind(h, bufs, (144, 72, 72))
+
+    def pic_download(self, h, with_padding):
+        return self.pics[h]["act"]
+
+    def analyze_cu(self, items, rates, states, elems):
+        return xo.analyze_cu_batch(self.seq, self.planes, rates, items, states, elems)
+
+    def mc(self, items, off, total):
+        return xo.mc_batch(self.seq, self.planes, items, off, total)
+
+    def analyze_intra(self, items, rates, states, side, elems):
+        return xo.analyze_intra_batch(self.seq, self.planes, rates, items, states, side, elems)
+
+    def close(self):
+        pass
+
+
+def run(seq, pics, stand_in):
+    if stand_in:
+        hp = StandIn(seq)
+    else:
+        from xeve_b200 import api
+        hp = api.Hotpath(seq)
+    t0 = time.time()
+    with tracedata.chain_with(hp.analyze_cu, hp.mc, hp.analyze_intra) as cw:
+        out = tracedata.chain_sequence(seq, pics, check=True, hp=hp)
+    n_calls = (cw.n_cu, cw.n_intra)
+    assert cw.n_cu == sum(len(r["cu_log"]) for r in out) and cw.n_intra == sum(len(r["intra_log"]) for r in out)
+    launches = 0 if stand_in else hp.launches
+    hp.close()
+    return out, n_calls, launches, time.time() - t0
+
+
+def main():
+    stand_in = "--stand-in" in sys.argv
+    seq, pics = tracedata.chain_golden()
+    out, calls, launches, sec = run(seq, pics, stand_in)
+    print(f"fixture: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel launches, {sec:.1f} s: "
+          "states, maps, leaf CUs and deblocked pictures equal the reference's")
+    if rh.available():
+        override = {k: v for k, v in tracedata.QCIF.items() if k != "n"}
+        c, yuv = tracedata.clip_yuv("cif", 6, **override)
+        tr = rh.encode_clip(yuv, 6, c.w, c.h, in_depth=c.depth, preset="fast", trace_mask=rh.TRACE_LCU | rh.TRACE_DF, pic_lo=0, pic_hi=1 << 20)
+        seq, pics = tracedata.chain_inputs_from_trace(tr)
+        out, calls, launches, sec = run(seq, pics, stand_in)
+        dec = [dict(poc=r["poc"], scu=r["scu"], coef=r["coef"], rec=r["rec"]) for r in out]
+        tr2, n_ctu, ncu, nintra = rh.encode_clip_injected(yuv, 6, c.w, c.h, dec, in_depth=c.depth, preset="fast")
+        assert ncu == 0 and nintra == 0 and n_ctu == sum(len(r["ctu"]) for r in out)
+        assert len(tr.bitstream) > 1000 and np.array_equal(tr.bitstream, tr2.bitstream)
+        print(f"live: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel launches, {sec:.1f} s: "
+              f"injected into the unmodified reference -> byte-identical bitstream ({len(tr.bitstream)} bytes)")
+    print("CHAIN_ON_DEVICE_OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -285,13 +285,16 @@ def chain_golden():
     return z["seq"], pics
 
 
-def chain_sequence(seq, pics, check=True):
+def chain_sequence(seq, pics, check=True, hp=None):
     """Encode the pictures with the oracle alone: per picture xo_chain_picture (every CTU's mode_coding_tree) -> xo_deblock ->
     xo_pad_plane, the result becoming the reference picture and the colocated MV map of later pictures.  Nothing of the reference's
     own reconstruction is read; with check=True every picture's coder states, frame maps, leaf CUs and pictures before / after
-    deblocking are asserted equal to `expect`."""
+    deblocking are asserted equal to `expect`.
+    hp (an xeve_b200.api.Hotpath, used together with chain_with): picture handles are the device's, original pictures are uploaded,
+    and every reconstructed picture is deblocked and border-expanded ON THE DEVICE (xb200_deblock), where it stays as the reference
+    picture of later xb200_analyze_cu / xb200_mc calls; the host copy is only downloaded for the comparison."""
     bd = int(np.asarray(seq).reshape(-1)[0]["bit_depth"])
-    planes = (xo.PLANES * (2 * len(pics)))()
+    planes = (xo.PLANES * (4096 if hp is not None else 2 * len(pics)))()
     done, keep, out = {}, [], []
     for i, pc in enumerate(pics):
         pp = np.array(pc["pp"]).reshape(1).copy()
@@ -299,6 +302,10 @@ def chain_sequence(seq, pics, check=True):
         org = [np.ascontiguousarray(a) for a in pc["org"]]
         keep.append(org)
         h_org = 2 * i
+        if hp is not None:
+            h_org = hp.pic_create(padded=False)
+            hp.pic_upload_s16(h_org, *org)
+            assert 0 <= h_org < 4096
         planes[h_org].y, planes[h_org].u, planes[h_org].v = [a.ctypes.data for a in org]
         planes[h_org].s_l, planes[h_org].s_c = org[0].shape[1], org[1].shape[1]
         planes[h_org].w_l, planes[h_org].h_l, planes[h_org].poc = org[0].shape[1], org[0].shape[0], poc
@@ -313,7 +320,15 @@ def chain_sequence(seq, pics, check=True):
                 if k == 0:
                     col[l] = rp["map_mv"]
         r = xo.chain_picture(seq, planes, pp, col[0], col[1], chain_dtypes())
-        post = xo.deblock(r["rec"], r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], bit_depth=bd)
+        h_rec = 2 * i + 1
+        if hp is not None:
+            h_rec = hp.pic_create(padded=True)
+            hp.pic_upload_s16(h_rec, *r["rec"])
+            hp.deblock(h_rec, r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], expand=True)
+            post = [np.ascontiguousarray(a) for a in hp.pic_download(h_rec, False)]
+            assert 0 <= h_rec < 4096
+        else:
+            post = xo.deblock(r["rec"], r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], bit_depth=bd)
         padded = []
         for a, pad in zip(post, (144, 72, 72)):
             hh, ww = a.shape
@@ -321,7 +336,6 @@ def chain_sequence(seq, pics, check=True):
             buf[pad:pad + hh, pad:pad + ww] = a
             xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
             padded.append(buf)
-        h_rec = 2 * i + 1
         planes[h_rec].y, planes[h_rec].u, planes[h_rec].v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(padded, (144, 72, 72))]
         planes[h_rec].s_l, planes[h_rec].s_c = padded[0].shape[1], padded[1].shape[1]
         planes[h_rec].w_l, planes[h_rec].h_l, planes[h_rec].poc = org[0].shape[1], org[0].shape[0], poc
@@ -362,3 +376,72 @@ def chain_inject_roundtrip(name="cif", frames=20, preset="fast", extra="", **ove
     dec = [dict(poc=r["poc"], scu=r["scu"], coef=r["coef"], rec=r["rec"]) for r in out]
     tr2, n, ncu, nintra = rh.encode_clip_injected(yuv, frames, c.w, c.h, dec, in_depth=c.depth, preset=preset, extra=extra)
     return tr.bitstream, tr2.bitstream, n, ncu + nintra, out
+
+
+# ---- the decision chain with the per-CU analyses done by somebody else (the CUDA library, or the oracle again as a plumbing check)
+_CB6 = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def _view(ptr, dtype, n):
+    dtype = np.dtype(dtype)
+    return np.frombuffer((C.c_char * (dtype.itemsize * n)).from_address(ptr), dtype, n)
+
+
+class chain_with:
+    """Context manager: xo_chain_picture calls analyze_cu(items, rates, states, elems) -> (items, states, coef, rec),
+    mc(items, off, total) -> pred and analyze_intra(items, rates, states, side, elems) -> (items, states, coef, rec) -- the signatures
+    of xeve_b200.api.Hotpath -- for every CU instead of its own restatements.  Errors raised inside a callback are re-raised on exit."""
+
+    def __init__(self, analyze_cu, mc, analyze_intra):
+        from xeve_b200 import api
+        self.err, self.n_cu, self.n_intra = None, 0, 0
+
+        def cu_cb(cu_p, st_p, rates_p, coef_p, rec_p, pred_p):
+            if self.err:
+                return
+            try:
+                cu, st, rates = _view(cu_p, api.CU_ITEM, 1), _view(st_p, api.SBAC, 2), _view(rates_p, api.RATES, 1)
+                n = 1 << (2 * int(cu["log2_cuw"][0]))
+                elems = 3 * n // 2
+                items, states, coef, rec = analyze_cu(cu.copy(), rates.copy(), st.copy(), elems)
+                cu[:], st[:] = items, states
+                _view(coef_p, np.int16, elems)[:], _view(rec_p, np.int16, elems)[:] = coef, rec
+                m = np.zeros(1, api.MC_ITEM)                       # the winner's prediction (mi->pred_y_best): one more pi->fn_mc call
+                m["poc"], m["x"], m["y"], m["w"], m["h"] = cu["poc"], cu["x"], cu["y"], 1 << int(cu["log2_cuw"][0]), 1 << int(cu["log2_cuw"][0])
+                for l in range(2):
+                    r = int(items["refi"][0][l])
+                    m["refi"][0][l], m["mv"][0][l] = r, items["mv"][0][l]
+                    m["ref_pic"][0][l] = int(cu["ref_pic"][0][l][r]) if r >= 0 else -1
+                    m["ref_poc"][0][l] = int(cu["ref_poc"][0][l][r]) if r >= 0 else -1
+                _view(pred_p, np.int16, n)[:] = mc(m, np.zeros(1, np.int64), elems)[:n]
+                self.n_cu += 1
+            except Exception as e:  # noqa: BLE001 -- must not propagate through the C frame
+                self.err = e
+
+        def intra_cb(it_p, st_p, rates_p, side_p, coef_p, rec_p):
+            if self.err:
+                return
+            try:
+                it, st, rates = _view(it_p, api.INTRA_ITEM, 1), _view(st_p, api.SBAC, 2), _view(rates_p, api.RATES, 1)
+                w = 1 << int(it["log2_cuw"][0])
+                elems = 3 * w * w // 2
+                items, states, coef, rec = analyze_intra(it.copy(), rates.copy(), st.copy(), _view(side_p, np.int16, 8 * w + 6).copy(), elems)
+                it[:], st[:] = items, states
+                _view(coef_p, np.int16, elems)[:], _view(rec_p, np.int16, elems)[:] = coef, rec
+                self.n_intra += 1
+            except Exception as e:  # noqa: BLE001
+                self.err = e
+        self.cbs = (_CB6(cu_cb), _CB6(intra_cb))
+
+    def __enter__(self):
+        L = xo.lib()
+        L.xo_chain_set_callbacks.restype = None
+        L.xo_chain_set_callbacks.argtypes = [C.c_void_p, C.c_void_p]
+        L.xo_chain_set_callbacks(*self.cbs)
+        return self
+
+    def __exit__(self, *exc):
+        xo.lib().xo_chain_set_callbacks(None, None)
+        if self.err and exc[0] is None:
+            raise self.err
+        return False
