@@ -25,10 +25,7 @@ def test_cuda_operators_inside_the_decision_chain():
     """every CU analysis of every tree node (xb200_analyze_cu, xb200_analyze_intra), the winner's prediction (xb200_mc) and every
     picture's loop filter + border expansion (xb200_deblock, device-resident references) computed by the library while the oracle's tree
     bookkeeping drives: pictures, maps and coder states equal the reference's and, injected into the unmodified reference, the decisions
-    give the byte-identical bitstream.
-    PROVISIONAL: written after this round's GPU budget was spent, so it has not run on hardware yet; until it has, a failure is
-    reported as xfail with the script's output instead of failing the suite."""
+    give the byte-identical bitstream (first hardware run: profiles/r01s21_chain_on_device.txt)."""
     r = _run()
-    if r.returncode != 0 or "CHAIN_ON_DEVICE_OK" not in r.stdout:
-        pytest.xfail("first hardware run: " + (r.stdout[-1500:] + r.stderr[-1500:]))
+    assert r.returncode == 0 and "CHAIN_ON_DEVICE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     print(r.stdout)
