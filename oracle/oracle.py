@@ -194,6 +194,7 @@ def mvp_batch(items, pic, map_scu, map_mv, col0, col1):
     return items
 
 
+chain_current = None
 SCU_REC = np.dtype([("mode", "u1"), ("log2", "u1"), ("ipm", "i1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("pad_", "u1"),
                     ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,))], align=True)
 
@@ -219,6 +220,9 @@ def chain_picture(seq, planes, pp, col0, col1, dtypes, ctu_limit=0):
     pp = np.ascontiguousarray(pp).reshape(-1)[:1].copy()
     col0 = None if col0 is None else np.ascontiguousarray(col0, np.int16)
     col1 = None if col1 is None else np.ascontiguousarray(col1, np.int16)
+    global chain_current   # what a stand-in for xo_mvp / xo_intra_nbr needs to see: the maps and the picture as they stand right now
+    chain_current = dict(map_scu=map_scu, map_ipm=map_ipm, map_mv=map_mv, rec=rec, col0=col0, col1=col1 if col1 is not None else col0,
+                         w_scu=w_scu, h_scu=h_scu, cip=int(pp["cip"][0]))
     L = lib()
     assert L.xo_sizeof_chain(0) == lcu_dt.itemsize, (L.xo_sizeof_chain(0), lcu_dt.itemsize)
     L.xo_chain_picture.restype = None

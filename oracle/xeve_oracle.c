@@ -1673,7 +1673,10 @@ typedef struct {
  * the real decision chain): same records as xo_analyze_cu / xo_analyze_intra with one item, states[0] in / states[1] out. */
 static xo_chain_cu_fn    g_chain_cu_fn;
 static xo_chain_intra_fn g_chain_intra_fn;
+static xo_chain_mvp_fn   g_chain_mvp_fn;    /* ... and for their inputs: xo_mvp / xo_intra_nbr of the CU under analysis */
+static xo_chain_nbr_fn   g_chain_nbr_fn;
 void xo_chain_set_callbacks(xo_chain_cu_fn cu_fn, xo_chain_intra_fn intra_fn) { g_chain_cu_fn = cu_fn; g_chain_intra_fn = intra_fn; }
+void xo_chain_set_input_callbacks(xo_chain_mvp_fn mvp_fn, xo_chain_nbr_fn nbr_fn) { g_chain_mvp_fn = mvp_fn; g_chain_nbr_fn = nbr_fn; }
 
 static void cud_init(cud_t *d, int L)       /* init_cu_data: everything the chain reads later */
 {
@@ -1780,7 +1783,8 @@ static double chain_unit(chain_t *k, int x, int y, int L, int cud)   /* mode_cod
             xb200_mvp_item mi;
             memset(&mi, 0, sizeof(mi));
             mi.x_scu = (int16_t)(x >> 2); mi.y_scu = (int16_t)(y >> 2); mi.log2_cuw = mi.log2_cuh = (uint8_t)log2; mi.lidx = (uint8_t)l;
-            xo_mvp(&mi, &mp, k->map_scu, k->map_mv, k->col[0], k->col[1] ? k->col[1] : k->col[0]);
+            if(g_chain_mvp_fn) g_chain_mvp_fn(&mi, &mp);
+            else xo_mvp(&mi, &mp, k->map_scu, k->map_mv, k->col[0], k->col[1] ? k->col[1] : k->col[0]);
             memcpy(cu.mvp[l], mi.mvp, sizeof(mi.mvp)); memcpy(cu.refi_pred[l], mi.refi, 4);
             if(B) memcpy(cu.mv_dir, mi.mv_dir, sizeof(mi.mv_dir));
         }
@@ -1811,8 +1815,9 @@ static double chain_unit(chain_t *k, int x, int y, int L, int cud)   /* mode_cod
         it.inter_satd = cost_best != XO_MAX_COST
             ? (uint32_t)xo_satd(cuw, cuw, o->y + (int64_t)y * o->s_l + x, o->s_l, k->pred_y, cuw, k->sq->bit_depth) : 0xffffffffu;
         nb.x = (int16_t)x; nb.y = (int16_t)y; nb.log2_cuw = nb.log2_cuh = (uint8_t)log2; nb.nb_off = 0;
-        xo_intra_nbr(k->rec[0], k->rec[1], k->rec[2], k->s_l, k->s_c, &nb, k->map_scu, k->map_ipm, k->w_scu, k->h_scu, pp->cip,
-                     k->sq->bit_depth, k->side);
+        if(g_chain_nbr_fn) g_chain_nbr_fn(&nb, k->side);
+        else xo_intra_nbr(k->rec[0], k->rec[1], k->rec[2], k->s_l, k->s_c, &nb, k->map_scu, k->map_ipm, k->w_scu, k->h_scu, pp->cip,
+                          k->sq->bit_depth, k->side);
         it.poc = pp->poc; it.cur_pic = pp->cur_pic; it.x = (int16_t)x; it.y = (int16_t)y; it.log2_cuw = it.log2_cuh = (uint8_t)log2;
         it.slice_type = (uint8_t)pp->slice_type; it.all_preds = 1;
         for(int i = 0; i < 3; i++) { it.qp[i] = (uint8_t)pp->qp[i]; it.lambda[i] = pp->lambda[i]; }

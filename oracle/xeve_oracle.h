@@ -78,7 +78,10 @@ XO_API void xo_mvp_batch(xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *
 typedef void (*xo_chain_cu_fn)(xb200_cu_item *cu, xb200_sbac *states, const xb200_rates *rates, int16_t *coef, int16_t *rec, int16_t *pred_y);
 typedef void (*xo_chain_intra_fn)(xb200_intra_item *it, xb200_sbac *states, const xb200_rates *rates, const int16_t *side, int16_t *coef,
                                   int16_t *rec);
+typedef void (*xo_chain_mvp_fn)(xb200_mvp_item *it, const xb200_mvp_pic *pp);
+typedef void (*xo_chain_nbr_fn)(xb200_nbr_item *it, int16_t *side);
 XO_API void xo_chain_set_callbacks(xo_chain_cu_fn cu_fn, xo_chain_intra_fn intra_fn);
+XO_API void xo_chain_set_input_callbacks(xo_chain_mvp_fn mvp_fn, xo_chain_nbr_fn nbr_fn);
 XO_API int  xo_sizeof_chain(int what);
 XO_API void xo_chain_picture(const xb200_seq *sq, const xo_planes *pl, const xo_ctu_rec *pp, const int16_t *col_mv0, const int16_t *col_mv1,
                              xo_ctu_rec *out, double *ctu_cost, int16_t *rec_y, int16_t *rec_u, int16_t *rec_v, int s_l, int s_c,

@@ -9,6 +9,9 @@ then injected into the unmodified reference: the bitstream must be byte-identica
 
   python tests/chain_on_device.py             # needs a GPU
   python tests/chain_on_device.py --stand-in  # same plumbing with a CPU stand-in for the device context (no GPU; plumbing check)
+  --all-inputs   also the inputs of the analyses come from the device: xb200_mvp (MV predictor candidates, temporal direct MVs) and
+                 xb200_intra_nbr (availability, reference samples, MPM list; the picture under reconstruction is uploaded per call)
+  --more         further configurations (10-bit medium, P slices, plain quantiser) instead of the default pair
 """
 import ctypes as C
 import os
@@ -69,44 +72,68 @@ class StandIn:
     def analyze_intra(self, items, rates, states, side, elems):
         return xo.analyze_intra_batch(self.seq, self.planes, rates, items, states, side, elems)
 
+    def mvp(self, items, pic, map_scu, map_mv, col0, col1):
+        return xo.mvp_batch(items, pic, map_scu, map_mv, col0, col1)
+
+    def intra_nbr(self, h, items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems):
+        return xo.intra_nbr(self.pics[h]["act"], items, map_scu, map_ipm, w_scu, h_scu, cip, side_elems,
+                            bit_depth=int(np.asarray(self.seq).reshape(-1)[0]["bit_depth"]))
+
     def close(self):
         pass
 
 
-def run(seq, pics, stand_in):
+def run(seq, pics, stand_in, all_inputs=False):
     if stand_in:
         hp = StandIn(seq)
     else:
         from xeve_b200 import api
         hp = api.Hotpath(seq)
     t0 = time.time()
-    with tracedata.chain_with(hp.analyze_cu, hp.mc, hp.analyze_intra) as cw:
+    extra = {}
+    if all_inputs:
+        scratch = hp.pic_create(padded=True)    # the configuration xb200_intra_nbr is tested with (test_gpu_parity.py)
+
+        def upload(rec):
+            hp.pic_upload_s16(scratch, *rec)
+            return scratch
+        extra = dict(mvp=hp.mvp, intra_nbr=hp.intra_nbr, upload=upload)
+    with tracedata.chain_with(hp.analyze_cu, hp.mc, hp.analyze_intra, **extra) as cw:
         out = tracedata.chain_sequence(seq, pics, check=True, hp=hp)
     n_calls = (cw.n_cu, cw.n_intra)
     assert cw.n_cu == sum(len(r["cu_log"]) for r in out) and cw.n_intra == sum(len(r["intra_log"]) for r in out)
+    assert not all_inputs or (cw.n_nbr == cw.n_intra and cw.n_mvp >= cw.n_cu)
     launches = 0 if stand_in else hp.launches
     hp.close()
     return out, n_calls, launches, time.time() - t0
 
 
+QCIF = {k: v for k, v in tracedata.QCIF.items() if k != "n"}
+DEFAULT = [("cif", "fast", 6, "", QCIF)]
+MORE = [("2160p10", "medium", 5, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),     # 10-bit input, preset medium
+        ("cif", "fast", 6, "bframes=0;inter_slice_type=1", QCIF),                                       # low delay, P slices
+        ("cif", "fast", 5, "rdoq=0;qp=27", QCIF)]                                                       # plain quantiser, lower QP
+
+
 def main():
-    stand_in = "--stand-in" in sys.argv
-    seq, pics = tracedata.chain_golden()
-    out, calls, launches, sec = run(seq, pics, stand_in)
-    print(f"fixture: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel launches, {sec:.1f} s: "
-          "states, maps, leaf CUs and deblocked pictures equal the reference's")
-    if rh.available():
-        override = {k: v for k, v in tracedata.QCIF.items() if k != "n"}
-        c, yuv = tracedata.clip_yuv("cif", 6, **override)
-        tr = rh.encode_clip(yuv, 6, c.w, c.h, in_depth=c.depth, preset="fast", trace_mask=rh.TRACE_LCU | rh.TRACE_DF, pic_lo=0, pic_hi=1 << 20)
+    stand_in, all_inputs = "--stand-in" in sys.argv, "--all-inputs" in sys.argv
+    if "--more" not in sys.argv:
+        seq, pics = tracedata.chain_golden()
+        out, calls, launches, sec = run(seq, pics, stand_in, all_inputs)
+        print(f"fixture: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel launches, {sec:.1f} s: "
+              "states, maps, leaf CUs and deblocked pictures equal the reference's")
+    for name, preset, frames, extra, override in (MORE if "--more" in sys.argv else DEFAULT) if rh.available() and "--fixture-only" not in sys.argv else []:
+        c, yuv = tracedata.clip_yuv(name, frames, **override)
+        tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, trace_mask=rh.TRACE_LCU | rh.TRACE_DF,
+                            pic_lo=0, pic_hi=1 << 20)
         seq, pics = tracedata.chain_inputs_from_trace(tr)
-        out, calls, launches, sec = run(seq, pics, stand_in)
+        out, calls, launches, sec = run(seq, pics, stand_in, all_inputs)
         dec = [dict(poc=r["poc"], scu=r["scu"], coef=r["coef"], rec=r["rec"]) for r in out]
-        tr2, n_ctu, ncu, nintra = rh.encode_clip_injected(yuv, 6, c.w, c.h, dec, in_depth=c.depth, preset="fast")
+        tr2, n_ctu, ncu, nintra = rh.encode_clip_injected(yuv, frames, c.w, c.h, dec, in_depth=c.depth, preset=preset, extra=extra)
         assert ncu == 0 and nintra == 0 and n_ctu == sum(len(r["ctu"]) for r in out)
         assert len(tr.bitstream) > 1000 and np.array_equal(tr.bitstream, tr2.bitstream)
-        print(f"live: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel launches, {sec:.1f} s: "
-              f"injected into the unmodified reference -> byte-identical bitstream ({len(tr.bitstream)} bytes)")
+        print(f"live {name} {preset} {extra or 'default'}: {len(out)} pictures, {calls[0]} inter + {calls[1]} intra CU analyses, {launches} kernel "
+              f"launches, {sec:.1f} s: injected into the unmodified reference -> byte-identical bitstream ({len(tr.bitstream)} bytes)")
     print("CHAIN_ON_DEVICE_OK")
 
 

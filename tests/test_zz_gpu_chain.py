@@ -13,10 +13,11 @@ def _run(*args):
     return subprocess.run([sys.executable, SCRIPT, *args], capture_output=True, text=True, timeout=1200)
 
 
-def test_chain_plumbing_with_a_cpu_stand_in_for_the_device():
-    """same driver, callbacks and picture handling as the GPU test, the device context replaced by oracle calls: pins the plumbing
+@pytest.mark.parametrize("args", [(), ("--all-inputs", "--more")])
+def test_chain_plumbing_with_a_cpu_stand_in_for_the_device(args):
+    """same driver, callbacks and picture handling as the GPU tests, the device context replaced by oracle calls: pins the plumbing
     (and, with oracle/_ref present, ends in a byte-identical bitstream) on machines without a GPU"""
-    r = _run("--stand-in")
+    r = _run("--stand-in", *args)
     assert r.returncode == 0 and "CHAIN_ON_DEVICE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -28,4 +29,19 @@ def test_cuda_operators_inside_the_decision_chain():
     give the byte-identical bitstream (first hardware run: profiles/r01s21_chain_on_device.txt)."""
     r = _run()
     assert r.returncode == 0 and "CHAIN_ON_DEVICE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    print(r.stdout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [("--all-inputs",), ("--all-inputs", "--more")])
+def test_cuda_operators_and_their_inputs_inside_the_decision_chain(args):
+    """as above, with the inputs of the analyses from the device too -- xb200_mvp (MV predictor candidates, temporal direct MVs) and
+    xb200_intra_nbr (availability, reference samples, MPM list) -- so every device row of SURVEY 8 takes part; --more: 10-bit medium,
+    P slices, plain quantiser.
+    PROVISIONAL: on hardware so far only the fixture part of --all-inputs has run (profiles/r01s22_chain_on_device_all_inputs.txt; the
+    round's GPU budget ended there); until the live parts have run once, a failure is reported as xfail with the script's output
+    instead of failing the suite."""
+    r = _run(*args)
+    if r.returncode != 0 or "CHAIN_ON_DEVICE_OK" not in r.stdout:
+        pytest.xfail("first hardware run: " + (r.stdout[-1500:] + r.stderr[-1500:]))
     print(r.stdout)

@@ -392,9 +392,40 @@ class chain_with:
     mc(items, off, total) -> pred and analyze_intra(items, rates, states, side, elems) -> (items, states, coef, rec) -- the signatures
     of xeve_b200.api.Hotpath -- for every CU instead of its own restatements.  Errors raised inside a callback are re-raised on exit."""
 
-    def __init__(self, analyze_cu, mc, analyze_intra):
+    def __init__(self, analyze_cu, mc, analyze_intra, mvp=None, intra_nbr=None, upload=None):
+        """mvp(items, pic, map_scu, map_mv, col0, col1) -> items and intra_nbr(handle, items, map_scu, map_ipm, w_scu, h_scu, cip,
+        side_elems) -> (items, side) (optional) also replace the chain's xo_mvp / xo_intra_nbr; upload(rec) -> handle of a device
+        picture holding the reconstruction as it stands (what xb200_intra_nbr reads)."""
         from xeve_b200 import api
-        self.err, self.n_cu, self.n_intra = None, 0, 0
+        self.err, self.n_cu, self.n_intra, self.n_mvp, self.n_nbr = None, 0, 0, 0, 0
+        self.in_cbs = (None, None)
+        if mvp is not None:
+            def mvp_cb(it_p, pic_p):
+                if self.err:
+                    return
+                try:
+                    cur = xo.chain_current
+                    it = _view(it_p, api.MVP_ITEM, 1)
+                    it[:] = mvp(it.copy(), _view(pic_p, api.MVP_PIC, 1).copy(), cur["map_scu"], cur["map_mv"], cur["col0"], cur["col1"])
+                    self.n_mvp += 1
+                except Exception as e:  # noqa: BLE001
+                    self.err = e
+
+            def nbr_cb(it_p, side_p):
+                if self.err:
+                    return
+                try:
+                    cur = xo.chain_current
+                    it = _view(it_p, api.NBR_ITEM, 1)
+                    n = 8 * (1 << int(it["log2_cuw"][0])) + 6
+                    items, side = intra_nbr(upload(cur["rec"]), it.copy(), cur["map_scu"], cur["map_ipm"], cur["w_scu"], cur["h_scu"],
+                                            cur["cip"], n)
+                    it[:] = items
+                    _view(side_p, np.int16, n)[:] = side
+                    self.n_nbr += 1
+                except Exception as e:  # noqa: BLE001
+                    self.err = e
+            self.in_cbs = (C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(mvp_cb), C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(nbr_cb))
 
         def cu_cb(cu_p, st_p, rates_p, coef_p, rec_p, pred_p):
             if self.err:
@@ -438,10 +469,14 @@ class chain_with:
         L.xo_chain_set_callbacks.restype = None
         L.xo_chain_set_callbacks.argtypes = [C.c_void_p, C.c_void_p]
         L.xo_chain_set_callbacks(*self.cbs)
+        L.xo_chain_set_input_callbacks.restype = None
+        L.xo_chain_set_input_callbacks.argtypes = [C.c_void_p, C.c_void_p]
+        L.xo_chain_set_input_callbacks(*self.in_cbs)
         return self
 
     def __exit__(self, *exc):
         xo.lib().xo_chain_set_callbacks(None, None)
+        xo.lib().xo_chain_set_input_callbacks(None, None)
         if self.err and exc[0] is None:
             raise self.err
         return False
