@@ -370,6 +370,14 @@ CHAIN_CONFIGS = [
     ("cif", "fast", 8, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # low delay, P slices
     ("cif", "medium", 8, "qp=40", dict(tracedata.QCIF)),                                               # high QP: many all-zero blocks
     ("cif", "medium", 6, "qp=22", dict(w=352, h=288)),   # CIF 352x288, low QP
+    ("cif", "fast", 10, "ref=2;me_ref_num=2;qp=24", dict(tracedata.QCIF)),                             # two references per list
+    ("cif", "fast", 8, "me_sub=3;me_sub_pos=8", dict(tracedata.QCIF)),                                 # quarter-pel stage
+    ("cif", "fast", 8, "qp=12", dict(tracedata.QCIF)),                                                 # QP extremes
+    ("cif", "fast", 8, "qp=50", dict(tracedata.QCIF)),
+    ("cif", "fast", 6, "", dict(w=200, h=136, squares=[(32, 20, 30, 3, 2)])),                          # CTUs cut by both picture edges
+    ("cif", "fast", 6, "closed_gop=1;keyint=4", dict(tracedata.QCIF)),                                 # several intra pictures
+    ("cif", "fast", 6, "bframes=0;ref=3;me_ref_num=3", dict(tracedata.QCIF)),                          # low delay, three references
+    ("cif", "medium", 6, "merge_num=4", dict(tracedata.QCIF)),                                         # all four skip candidates
 ]
 
 
