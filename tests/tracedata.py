@@ -285,27 +285,64 @@ def chain_golden():
     return z["seq"], pics
 
 
-def chain_sequence(seq, pics, check=True, hp=None):
-    """Encode the pictures with the oracle alone: per picture xo_chain_picture (every CTU's mode_coding_tree) -> xo_deblock ->
-    xo_pad_plane, the result becoming the reference picture and the colocated MV map of later pictures.  Nothing of the reference's
-    own reconstruction is read; with check=True every picture's coder states, frame maps, leaf CUs and pictures before / after
-    deblocking are asserted equal to `expect`.
+class ChainEncoder:
+    """Picture-by-picture encoder built from the oracle chain: encode(pic) runs xo_chain_picture -> deblock -> pad and keeps the result
+    as a reference picture (+ colocated MV map) for later pictures; adopt() takes a reference picture produced somewhere else (another
+    rank).  Nothing of the reference's own reconstruction is read; with check=True every encoded picture's coder states, frame maps,
+    leaf CUs and pictures before / after deblocking are asserted equal to pic["expect"].
     hp (an xeve_b200.api.Hotpath, used together with chain_with): picture handles are the device's, original pictures are uploaded,
     and every reconstructed picture is deblocked and border-expanded ON THE DEVICE (xb200_deblock), where it stays as the reference
     picture of later xb200_analyze_cu / xb200_mc calls; the host copy is only downloaded for the comparison."""
-    bd = int(np.asarray(seq).reshape(-1)[0]["bit_depth"])
-    planes = (xo.PLANES * (4096 if hp is not None else 2 * len(pics)))()
-    done, keep, out = {}, [], []
-    for i, pc in enumerate(pics):
+
+    def __init__(self, seq, check=True, hp=None):
+        self.seq, self.check, self.hp = seq, check, hp
+        self.bd = int(np.asarray(seq).reshape(-1)[0]["bit_depth"])
+        self.planes = (xo.PLANES * 4096)()
+        self.done, self.keep, self.next_handle = {}, [], 0
+
+    def _handle(self):
+        self.next_handle += 1
+        assert self.next_handle <= 4096
+        return self.next_handle - 1
+
+    def _bind_reference(self, poc, post, map_mv, h_rec, extra=None):
+        padded = []
+        for a, pad in zip(post, (144, 72, 72)):
+            hh, ww = a.shape
+            buf = np.zeros((hh + 2 * pad, ww + 2 * pad), np.int16)
+            buf[pad:pad + hh, pad:pad + ww] = a
+            xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
+            padded.append(buf)
+        pl = self.planes[h_rec]
+        pl.y, pl.u, pl.v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(padded, (144, 72, 72))]
+        pl.s_l, pl.s_c = padded[0].shape[1], padded[1].shape[1]
+        pl.w_l, pl.h_l, pl.poc = post[0].shape[1], post[0].shape[0], poc
+        r = dict(extra or {})
+        r.update(poc=poc, post=post, padded=padded, handle=h_rec, map_mv=np.ascontiguousarray(map_mv, np.int16))
+        self.done[poc] = r
+        return r
+
+    def adopt(self, poc, post, map_mv):
+        post = [np.ascontiguousarray(a, np.int16) for a in post]
+        if self.hp is not None:
+            h_rec = self.hp.pic_create(padded=True)
+            self.hp.pic_upload_s16(h_rec, *post)
+        else:
+            h_rec = self._handle()
+        return self._bind_reference(poc, post, map_mv, h_rec)
+
+    def encode(self, pc):
+        hp, planes = self.hp, self.planes
         pp = np.array(pc["pp"]).reshape(1).copy()
         poc = int(pp["poc"][0])
         org = [np.ascontiguousarray(a) for a in pc["org"]]
-        keep.append(org)
-        h_org = 2 * i
+        self.keep.append(org)
         if hp is not None:
             h_org = hp.pic_create(padded=False)
             hp.pic_upload_s16(h_org, *org)
             assert 0 <= h_org < 4096
+        else:
+            h_org = self._handle()
         planes[h_org].y, planes[h_org].u, planes[h_org].v = [a.ctypes.data for a in org]
         planes[h_org].s_l, planes[h_org].s_c = org[0].shape[1], org[1].shape[1]
         planes[h_org].w_l, planes[h_org].h_l, planes[h_org].poc = org[0].shape[1], org[0].shape[0], poc
@@ -315,12 +352,11 @@ def chain_sequence(seq, pics, check=True, hp=None):
             for k in range(4):
                 if int(pp["ref_pic"][0][l][k]) < 0:
                     continue
-                rp = done[int(pp["ref_poc"][0][l][k])]     # our own reconstruction of that POC
+                rp = self.done[int(pp["ref_poc"][0][l][k])]     # our own (or an adopted) reconstruction of that POC
                 pp["ref_pic"][0][l][k] = rp["handle"]
                 if k == 0:
                     col[l] = rp["map_mv"]
-        r = xo.chain_picture(seq, planes, pp, col[0], col[1], chain_dtypes())
-        h_rec = 2 * i + 1
+        r = xo.chain_picture(self.seq, planes, pp, col[0], col[1], chain_dtypes())
         if hp is not None:
             h_rec = hp.pic_create(padded=True)
             hp.pic_upload_s16(h_rec, *r["rec"])
@@ -328,21 +364,11 @@ def chain_sequence(seq, pics, check=True, hp=None):
             post = [np.ascontiguousarray(a) for a in hp.pic_download(h_rec, False)]
             assert 0 <= h_rec < 4096
         else:
-            post = xo.deblock(r["rec"], r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], bit_depth=bd)
-        padded = []
-        for a, pad in zip(post, (144, 72, 72)):
-            hh, ww = a.shape
-            buf = np.zeros((hh + 2 * pad, ww + 2 * pad), np.int16)
-            buf[pad:pad + hh, pad:pad + ww] = a
-            xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
-            padded.append(buf)
-        planes[h_rec].y, planes[h_rec].u, planes[h_rec].v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(padded, (144, 72, 72))]
-        planes[h_rec].s_l, planes[h_rec].s_c = padded[0].shape[1], padded[1].shape[1]
-        planes[h_rec].w_l, planes[h_rec].h_l, planes[h_rec].poc = org[0].shape[1], org[0].shape[0], poc
-        r.update(poc=poc, post=post, padded=padded, slice_type=int(pp["slice_type"][0]), handle=h_rec)
-        done[poc] = r
-        out.append(r)
-        if check:
+            h_rec = self._handle()
+            post = xo.deblock(r["rec"], r["cus"], pc["df_pp"], r["map_scu"], r["map_refi"], r["map_mv"], bit_depth=self.bd)
+        r["slice_type"] = int(pp["slice_type"][0])
+        r = self._bind_reference(poc, post, r["map_mv"], h_rec, extra=r)
+        if self.check:
             e = pc["expect"]
             assert len(e["state_in"]) == len(r["ctu"])
             assert r["ctu"]["state_in"].tobytes() == e["state_in"].tobytes() and r["ctu"]["state_out"].tobytes() == e["state_out"].tobytes(), poc
@@ -352,7 +378,13 @@ def chain_sequence(seq, pics, check=True, hp=None):
             assert len(r["cus"]) == len(e["cus"]) and all(np.array_equal(r["cus"][k], e["cus"][k]) for k in ("x", "y", "log2_cuw", "log2_cuh")), poc
             assert e["pre"] is None or all(np.array_equal(a, b) for a, b in zip(r["rec"], e["pre"])), poc
             assert all(np.array_equal(a, b) for a, b in zip(post, e["post"])), poc
-    return out
+        return r
+
+
+def chain_sequence(seq, pics, check=True, hp=None):
+    """Encode the pictures in the order given with one ChainEncoder (see there)."""
+    enc = ChainEncoder(seq, check=check, hp=hp)
+    return [enc.encode(pc) for pc in pics]
 
 
 def live_chain(name="cif", frames=20, preset="fast", extra="", threads=1, **override):
