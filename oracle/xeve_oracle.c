@@ -3,10 +3,12 @@
  * inter-search + transform path, used as the checker in tests/, __graft_entry__.smoke() and the
  * cpu_baseline leg of bench.py.  The shipped library never links or calls this file.
  *
- * Parity of this restatement is PINNED: tests/test_oracle_vs_ref.py checks every function here
+ * Parity of this restatement is PINNED: tests/test_oracle.py checks every function here
  * against the compiled reference itself (oracle/_ref, built by oracle/Makefile.ref from the
- * sources under /root/reference) on random blocks and on work lists traced from real encodes,
- * and tests/golden/ holds fixtures generated the same way for machines without /root/reference.
+ * sources under /root/reference) on random blocks, on work lists traced from real encodes, and --
+ * for the decision chain at the end of this file -- on whole sequences up to the bitstream the
+ * unmodified reference writes from the chain's decisions; tests/golden/ holds fixtures generated
+ * the same way for machines without /root/reference.
  * (The reference ships no tests or golden vectors of its own)
  *
  * Each function cites the reference file:line it follows.  The code is written from the
