@@ -326,6 +326,68 @@ void xo_iqt_inv(int16_t *blk, int log2w, int log2h, int bd)
     free(t);
 }
 
+/* ATS, the adaptive transform selection of the Main profile: DST-VII / DCT-VIII, 4..32 points, chosen per direction by
+ * ats_intra_tridx (horizontal = bit 1, vertical = bit 0; 0 -> DST-VII, 1 -> DCT-VIII, src_main/xevem_tbl.c:419).  Forward
+ * xeve_t_MxN_ats_intra (src_main/xevem_tq.c:684-702, stages :336-682), inverse xeve_it_MxN_ats_intra (src_main/xevem_itdq.c:278-300,
+ * stages :63-276): the same two 16-bit stages and shifts as the IQT transforms above.  The 8-bit matrices are the rounded basis
+ * functions scaled by 64 sqrt(N): c(k, n) = round(64 sqrt(N) sqrt(4 / (2N + 1)) f), f = cos(pi (2k+1)(2n+1) / (4N+2)) for DCT-VIII and
+ * sin(pi (2k+1)(n+1) / (2N+1)) for DST-VII (checked against the reference's table in tests/test_oracle.py). */
+static int8_t g_ats[2][4][32 * 32];          /* [0 DCT-VIII | 1 DST-VII][log2n - 2][k * n_ + n] */
+static int    g_ats_init;
+void xo_ats_matrix(int type, int log2n, int8_t *out)
+{
+    const int    n_ = 1 << log2n;
+    const double pi = 3.14159265358979323846, scale = 64.0 * sqrt((double)n_) * sqrt(4.0 / (2 * n_ + 1));
+    for(int k = 0; k < n_; k++)
+        for(int n = 0; n < n_; n++) {
+            const double f = type == 0 ? cos(pi * (2 * k + 1) * (2 * n + 1) / (4 * n_ + 2)) : sin(pi * (2 * k + 1) * (n + 1) / (2 * n_ + 1));
+            out[k * n_ + n] = (int8_t)floor(scale * f + 0.5);
+        }
+}
+static const int8_t *ats_tm(int type, int log2n)
+{
+    if(!g_ats_init) {
+        for(int t = 0; t < 2; t++) for(int l = 2; l <= 5; l++) xo_ats_matrix(t, l, g_ats[t][l - 2]);
+        g_ats_init = 1;
+    }
+    return g_ats[type][log2n - 2];
+}
+static void ats_stage_fwd(const int16_t *src, int16_t *dst, const int8_t *m, int log2n, int shift, int line)
+{
+    const int n = 1 << log2n, add = 1 << (shift - 1);
+    for(int j = 0; j < line; j++)
+        for(int k = 0; k < n; k++) {
+            int acc = 0;
+            for(int x = 0; x < n; x++) acc += m[k * n + x] * src[j * n + x];
+            dst[k * line + j] = (int16_t)((acc + add) >> shift);
+        }
+}
+static void ats_stage_inv(const int16_t *src, int16_t *dst, const int8_t *m, int log2n, int shift, int line)
+{
+    const int n = 1 << log2n, add = 1 << (shift - 1);
+    for(int j = 0; j < line; j++)
+        for(int x = 0; x < n; x++) {
+            int acc = 0;
+            for(int k = 0; k < n; k++) acc += m[k * n + x] * src[k * line + j];
+            acc = (acc + add) >> shift;
+            dst[j * n + x] = (int16_t)(acc < -32768 ? -32768 : acc > 32767 ? 32767 : acc);
+        }
+}
+void xo_ats_fwd(int16_t *blk, int log2w, int log2h, int bd, int tridx)
+{
+    int16_t *t = malloc(sizeof(int16_t) << (log2w + log2h));
+    ats_stage_fwd(blk, t, ats_tm((tridx >> 1) ? 0 : 1, log2w), log2w, log2w - 1 + bd - 8, 1 << log2h);
+    ats_stage_fwd(t, blk, ats_tm((tridx & 1) ? 0 : 1, log2h), log2h, log2h + 6, 1 << log2w);
+    free(t);
+}
+void xo_ats_inv(int16_t *blk, int log2w, int log2h, int bd, int tridx)
+{
+    int16_t *t = malloc(sizeof(int16_t) << (log2w + log2h));
+    ats_stage_inv(blk, t, ats_tm((tridx & 1) ? 0 : 1, log2h), log2h, 7, 1 << log2w);
+    ats_stage_inv(t, blk, ats_tm((tridx >> 1) ? 0 : 1, log2w), log2w, 12 - (bd - 8), 1 << log2h);
+    free(t);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * quantisation with RDOQ (square blocks), src_base/xeve_tq.c:425-730
  * ------------------------------------------------------------------------------------------- */

@@ -44,6 +44,9 @@ XO_API void xo_fwd_transform(int16_t *blk, int log2w, int log2h, int bd);
 XO_API void xo_inv_transform(int16_t *blk, int log2w, int log2h, int bd);
 XO_API void xo_iqt_fwd(int16_t *blk, int log2w, int log2h, int bd);
 XO_API void xo_iqt_inv(int16_t *blk, int log2w, int log2h, int bd);
+XO_API void xo_ats_matrix(int type, int log2n, int8_t *out);
+XO_API void xo_ats_fwd(int16_t *blk, int log2w, int log2h, int bd, int tridx);
+XO_API void xo_ats_inv(int16_t *blk, int log2w, int log2h, int bd, int tridx);
 XO_API int  xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intra, int ch, int slice_type,
                           const xb200_rates *rt, int bd);
 XO_API int  xo_quant_plain(int16_t *coef, int log2n, int qp, int slice_type, int bd);

@@ -467,3 +467,37 @@ def test_oracle_iqt_transforms_match_main_reference():
                         assert np.array_equal(a, back), ("inv", names[1], bd, lw, lh, amp)
                         n += 1
         assert n >= 96
+
+
+@pytest.mark.skipif(not os.path.exists(MAIN_REF), reason="oracle/_ref/libxeve_main_ref.so (Main-profile reference) not built here")
+def test_oracle_ats_transforms_match_main_reference():
+    """xo_ats_fwd / xo_ats_inv == xeve_t_MxN_ats_intra / xeve_it_MxN_ats_intra of the Main-profile reference (DST-VII / DCT-VIII per
+    direction, 4..32 points, aspect ratio <= 4, 8 / 10 bit; C and SSE stage tables), and the generated 8-bit matrices equal its table"""
+    M, L = C.CDLL(MAIN_REF), xo.lib()
+    tbl = np.ctypeslib.as_array((C.c_int8 * (2 * 4 * 1024)).in_dll(M, "xevem_tbl_tr")).reshape(2, 4, 1024)
+    for typ in range(2):                                   # 0 DCT-VIII, 1 DST-VII (src_base/xeve_def.h:557)
+        for l2 in range(2, 6):
+            m = np.zeros(1 << (2 * l2), np.int8)
+            L.xo_ats_matrix(typ, l2, p(m))
+            assert np.array_equal(m, tbl[typ, l2 - 2, :1 << (2 * l2)]), (typ, l2)
+    rng = np.random.default_rng(8)
+    func_itrans = C.c_void_p.in_dll(M, "xeve_func_itrans")
+    n = 0
+    for inv_tbl in ("xeve_itrans_map_tbl", "xeve_itrans_map_tbl_sse"):
+        func_itrans.value = C.addressof((C.c_void_p * 80).in_dll(M, inv_tbl))
+        for bd in (8, 10):
+            for lw in range(2, 6):
+                for lh in range(max(2, lw - 2), min(5, lw + 2) + 1):
+                    for tridx in range(4):
+                        w, h = 1 << lw, 1 << lh
+                        blk = rng.integers(-(1 << bd) + 1, 1 << bd, w * h).astype(np.int16)
+                        a = blk.copy()
+                        M.xeve_t_MxN_ats_intra(p(a), w, h, bd, 1, tridx)
+                        got = blk.copy()
+                        L.xo_ats_fwd(p(got), lw, lh, bd, tridx)
+                        assert np.array_equal(a, got), ("fwd", bd, lw, lh, tridx)
+                        M.xeve_it_MxN_ats_intra(p(a), w, h, bd, 15, tridx, 0, 0)
+                        L.xo_ats_inv(p(got), lw, lh, bd, tridx)
+                        assert np.array_equal(a, got), ("inv", inv_tbl, bd, lw, lh, tridx)
+                        n += 1
+    assert n >= 200
