@@ -410,6 +410,24 @@ XB200_API int xb200_intra_nbr(xb200_ctx *c, int32_t pic, xb200_nbr_item *items, 
 XB200_API int xb200_deblock(xb200_ctx *c, int32_t pic, const xb200_df_cu *cus, int64_t n, const xb200_df_pic *pp,
                             const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int expand, int mem);
 
+/* ---- Main profile, first operator: the two-stage 16-bit transforms -------------------------------------------------
+ * Forward / inverse transform of a list of s16 blocks in place (row-major, w * h samples at element offset `off` of `blocks`):
+ *   ats = 0: the "IQT" DCT-II of sps.tool_iqt -- xeve_trans with iqt_flag (src_main/xevem_tq.c:709-716, stages tx_pb2 .. tx_pb64
+ *            :58-334) and xeve_itrans (src_main/xevem_itdq.c:551-557, stages itx_pb2 .. itx_pb64 :302-549); 2..64 samples per side;
+ *   ats = 1: DST-VII / DCT-VIII chosen per direction by tridx (ats_intra_tridx: bit 1 horizontal, bit 0 vertical; 0 -> DST-VII,
+ *            1 -> DCT-VIII) -- xeve_t_MxN_ats_intra (src_main/xevem_tq.c:684-702) and xeve_it_MxN_ats_intra
+ *            (src_main/xevem_itdq.c:278-300); 4..32 samples per side.
+ * Both stages round, shift and store 16 bits (forward: truncation, inverse: saturation) exactly as the reference's; blocks need not be
+ * square.  The bit depth is the context's (xb200_seq::bit_depth).  `mem` applies to items and blocks. */
+typedef struct {
+    uint8_t log2_w, log2_h;
+    uint8_t inverse;                /* 0 forward (residual -> coefficients), 1 inverse */
+    uint8_t ats, tridx;
+    uint8_t pad_[3];
+    int64_t off;
+} xb200_trm_item;
+XB200_API int xb200_transform_main(xb200_ctx *c, const xb200_trm_item *items, int64_t n, int16_t *blocks, int64_t elems, int mem);
+
 /* ---- timing aid for bench.py: device time (ms) of the kernels of the last call, measured with
  *      CUDA events on the library's own stream ------------------------------------------------- */
 XB200_API double xb200_last_kernel_ms(const xb200_ctx *c);

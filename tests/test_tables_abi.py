@@ -23,7 +23,7 @@ int main(void){
   printf("seq %zu\nme %zu\nmc %zu\nrates %zu\ntq %zu\nres %zu\nblk %zu\n", sizeof(xb200_seq), sizeof(xb200_me_item),
          sizeof(xb200_mc_item), sizeof(xb200_rates), sizeof(xb200_tq_item), sizeof(xb200_residue_item), sizeof(xb200_blk_item));
   printf("sbac %zu\nbits %zu\ncu %zu\nmvpi %zu\n", sizeof(xb200_sbac), sizeof(xb200_bits_item), sizeof(xb200_cu_item), sizeof(xb200_mvp_item));
-  printf("dfcu %zu\ndfpic %zu\n", sizeof(xb200_df_cu), sizeof(xb200_df_pic));
+  printf("dfcu %zu\ndfpic %zu\ntrm %zu\n", sizeof(xb200_df_cu), sizeof(xb200_df_pic), sizeof(xb200_trm_item));
   printf("intra %zu\nnbr %zu\nintraoff %zu %zu %zu\n", sizeof(xb200_intra_item), sizeof(xb200_nbr_item), offsetof(xb200_intra_item, lambda),
          offsetof(xb200_intra_item, cost), offsetof(xb200_nbr_item, nb_off));
   { static const unsigned char m[6][6][5] = XB200_MPM_TABLE; FILE* g = fopen("mpm.bin","wb"); fwrite(m,1,sizeof(m),g); fclose(g); }
@@ -68,6 +68,7 @@ def test_struct_layouts_match_numpy(probe_dir):
     assert int(sizes["dfcu"]) == api.DF_CU.itemsize == rh.DF_CU.itemsize and int(sizes["dfpic"]) == api.DF_PIC.itemsize == rh.DF_PIC.itemsize
     assert int(sizes["intra"]) == api.INTRA_ITEM.itemsize == rh.INTRA_REC.itemsize and api.INTRA_ITEM.fields == rh.INTRA_REC.fields
     assert int(sizes["nbr"]) == api.NBR_ITEM.itemsize == rh.NBR_REC.itemsize
+    assert int(sizes["trm"]) == api.TRM_ITEM.itemsize == 16 and api.TRM_ITEM.fields["off"][1] == 8
     ioffs = [int(v) for v in re.search(r"intraoff (\d+) (\d+) (\d+)", out).groups()]
     assert ioffs == [api.INTRA_ITEM.fields["lambda"][1], api.INTRA_ITEM.fields["cost"][1], api.NBR_ITEM.fields["nb_off"][1]]
     cuoffs = [int(v) for v in re.search(r"cuoff (\d+) (\d+) (\d+) (\d+)", out).groups()]

@@ -88,6 +88,8 @@ INTRA_ITEM = np.dtype([
     ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"),
 ], align=True)
 
+TRM_ITEM = np.dtype([("log2_w", "u1"), ("log2_h", "u1"), ("inverse", "u1"), ("ats", "u1"), ("tridx", "u1"), ("pad_", "u1", (3,)),
+                     ("off", "<i8")], align=True)
 NBR_ITEM = np.dtype([("x", "<i2"), ("y", "<i2"), ("log2_cuw", "u1"), ("log2_cuh", "u1"), ("mpm", "u1", (5,)), ("pad_", "u1"),
                      ("avail", "<u2"), ("pad2_", "<u2"), ("nb_off", "<i8")], align=True)
 
@@ -162,6 +164,7 @@ def load():
         L.xb200_analyze_intra.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64]
         L.xb200_intra_nbr.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, C.c_int, C.c_int, C.c_int, VP, C.c_int64]
         L.xb200_deblock.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int]
+        L.xb200_transform_main.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
         _lib = L
     return _lib
 
@@ -169,7 +172,8 @@ def load():
 EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
-           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr"]
+           "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr",
+           "xb200_transform_main"]
 
 
 def _p(a):
@@ -330,6 +334,13 @@ class Hotpath:
                                         _p(np.ascontiguousarray(map_ipm, np.int8)), w_scu, h_scu, int(cip), _p(side), side_elems),
                  "xb200_intra_nbr")
         return items, side
+
+    def transform_main(self, items, blocks):
+        """Main-profile two-stage 16-bit transforms (IQT DCT-II / ATS), forward or inverse per item, on a copy of `blocks`"""
+        items = np.ascontiguousarray(items, TRM_ITEM)
+        blocks = np.ascontiguousarray(blocks, np.int16).copy()
+        self._ck(self.L.xb200_transform_main(self.h, _p(items), len(items), _p(blocks), len(blocks), MEM_HOST), "xb200_transform_main")
+        return blocks
 
     def deblock(self, handle, cus, pp, map_scu, map_refi, map_mv, expand=True):
         """xeve_loop_filter (+ xeve_picbuf_expand) on the device picture `handle`, in place"""

@@ -354,7 +354,7 @@ void xb200_destroy(xb200_ctx *c)
                      &c->b_cu_me, &c->b_cu_res, &c->b_cu_mc, &c->b_cu_cur, &c->b_cu_off, &c->b_cu_side, &c->b_cu_order, &c->b_cu_coef,
                      &c->b_cu_rec, &c->b_cu_nzr, &c->b_cu_nzl, &c->b_cu_meta})
         if(b->p) cudaFree(b->p);
-    for(DevBuf *b : {&c->b_compact, &c->b_coff})
+    for(DevBuf *b : {&c->b_compact, &c->b_coff, &c->b_ats})
         if(b->p) cudaFree(b->p);
     if(c->h_pin) cudaFreeHost(c->h_pin);
     if(c->d_pics) cudaFree(c->d_pics);

@@ -1,5 +1,5 @@
 // xb200_ctx.h -- host-side context of the library, shared by its translation units (xb200_api.cu: the per-CU operators,
-// xb200_frame.cu: the whole-picture operators).
+// xb200_frame.cu: the whole-picture operators, xb200_intra.cu: intra analysis, xb200_main.cu: Main-profile operators).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,6 +39,7 @@ struct xb200_ctx {
     void            *h_pin = nullptr;   // library-owned pinned staging (compacted coefficient read-back)
     size_t           h_pin_cap = 0;
     DevBuf           b_compact, b_coff;
+    DevBuf           b_ats;             // Main profile: the eight 8-bit ATS matrices (xb200_main.cu)
     DevBuf           b_scr[4], b_st0, b_st1; // analyze_cu: mode scratch per size class, coder states in / out
     DevBuf           b_cu_items, b_cu_rates, b_cu_state, b_cu_me, b_cu_res, b_cu_mc, b_cu_cur, b_cu_off, b_cu_side, b_cu_order,
                      b_cu_coef, b_cu_rec, b_cu_nzr, b_cu_nzl, b_cu_meta; // CU pipeline
