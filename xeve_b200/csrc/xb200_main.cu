@@ -8,7 +8,8 @@
 //
 // One CTA per block, both stages in shared memory (block + intermediate: 16 KB for 64x64); the matrix rows are read through the
 // read-only path (the 64x64 DCT-II matrix is 4 KB, the eight ATS matrices 2.7 KB: L1-resident).  HBM traffic is the block in and out,
-// 4 bytes per sample.
+// 4 bytes per sample.  First version: plain index mapping (lanes walk the lines of the block, so the strided shared-memory reads of a
+// stage conflict); not yet profiled -- it was written after the round's GPU budget was spent.
 #define XB200_NO_CONSTANTS // the __constant__ tables belong to xb200_api.cu
 #include "xb200_ctx.h"
 #include <math.h>
