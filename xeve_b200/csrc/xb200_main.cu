@@ -8,8 +8,8 @@
 //
 // One CTA per block, both stages in shared memory (block + intermediate: 16 KB for 64x64); the matrix rows are read through the
 // read-only path (the 64x64 DCT-II matrix is 4 KB, the eight ATS matrices 2.7 KB: L1-resident).  HBM traffic is the block in and out,
-// 4 bytes per sample.  First version: plain index mapping (lanes walk the lines of the block, so the strided shared-memory reads of a
-// stage conflict); not yet profiled -- it was written after the round's GPU budget was spent.
+// 4 bytes per sample.  The index mapping keeps every shared-memory access of the inner loops either a broadcast or conflict-free (see
+// the stage comments); it has not been profiled yet -- the kernel was written after the round's GPU budget was spent.
 #define XB200_NO_CONSTANTS // the __constant__ tables belong to xb200_api.cu
 #include "xb200_ctx.h"
 #include <math.h>
@@ -23,24 +23,32 @@ struct TrmArgs {
     int                  *err;
 };
 
-// coefficient (k, x) of the n-point matrix of one direction
+// the n-point matrix of one direction, staged in shared memory as int8 rows of n + 4 bytes (the padding makes a warp that walks the
+// rows at a fixed column hit 32 different banks); 64 points: only rows 0..31 exist (outputs 32..63 are zero)
 struct TrmMat {
-    const int8_t *m;
-    int           row_stride, k_step, kmax;
-    __device__ __forceinline__ int at(int k, int x) const { return m[(k * k_step) * row_stride + x]; }
+    const int8_t *src;
+    int           src_stride, k_step, kmax;
 };
 __device__ __forceinline__ TrmMat trm_matrix(const TrmArgs &a, int log2n, int ats, int dct8)
 {
     TrmMat t;
     const int n = 1 << log2n;
-    if(ats) { t.m = a.ats + ((dct8 ? 0 : 1) * 4 + (log2n - 2)) * 1024; t.row_stride = n; t.k_step = 1; t.kmax = n; }
-    else    { t.m = a.tm64; t.row_stride = 64; t.k_step = 64 >> log2n; t.kmax = n == 64 ? 32 : n; } // 64 points: outputs 32..63 are zero
+    if(ats) { t.src = a.ats + ((dct8 ? 0 : 1) * 4 + (log2n - 2)) * 1024; t.src_stride = n; t.k_step = 1; t.kmax = n; }
+    else    { t.src = a.tm64; t.src_stride = 64; t.k_step = 64 >> log2n; t.kmax = n == 64 ? 32 : n; }
     return t;
+}
+__device__ __forceinline__ void trm_stage_matrix(const TrmMat &t, int n, int8_t *dst)
+{
+    for(int e = threadIdx.x; e < t.kmax * n; e += 256) {
+        const int k = e / n, x = e - k * n;
+        dst[k * (n + 4) + x] = t.src[(k * t.k_step) * t.src_stride + x];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_transform_main(TrmArgs a)
 {
     __shared__ int16_t s_a[4096], s_b[4096];
+    __shared__ int8_t  s_mw[64 * 68], s_mh[64 * 68];
     for(int64_t i = blockIdx.x; i < a.n; i += gridDim.x) {
         const xb200_trm_item it = a.items[i];
         const int lw = it.log2_w, lh = it.log2_h;
@@ -50,48 +58,54 @@ __global__ void __launch_bounds__(256) k_transform_main(TrmArgs a)
             if(threadIdx.x == 0) atomicExch(a.err, 1);
             continue;
         }
-        const int w = 1 << lw, h = 1 << lh, n = w * h;
+        const int w = 1 << lw, h = 1 << lh, n = w * h, pw = w + 4, ph = h + 4;
         int16_t  *blk = a.blocks + it.off;
-        __syncthreads(); // the previous block's write-back reads s_a
-        for(int e = threadIdx.x; e < n; e += 256) s_a[e] = blk[e];
-        __syncthreads();
         const TrmMat mw = trm_matrix(a, lw, it.ats, it.tridx >> 1), mh = trm_matrix(a, lh, it.ats, it.tridx & 1);
+        __syncthreads(); // the previous block's write-back reads s_a, its last stage the matrices
+        for(int e = threadIdx.x; e < n; e += 256) s_a[e] = blk[e];
+        trm_stage_matrix(mw, w, s_mw);
+        trm_stage_matrix(mh, h, s_mh);
+        __syncthreads();
         if(!it.inverse) {
             const int sh1 = lw - 1 + a.bd - 8, add1 = sh1 ? 1 << (sh1 - 1) : 0, sh2 = lh + 6, add2 = 1 << (sh2 - 1);
-            for(int e = threadIdx.x; e < n; e += 256) {          // rows: s_b[k * h + j] from row j of the block
-                const int j = e & (h - 1), k = e >> lh;
+            // rows: t[j][k] = sum_x M_w[k][x] * blk[j][x]; lanes walk k: the block sample is a broadcast, the matrix column conflict-free
+            for(int e = threadIdx.x; e < n; e += 256) {
+                const int k = e & (w - 1), j = e >> lw;
                 int       acc = 0;
                 if(k < mw.kmax) {
-                    for(int x = 0; x < w; x++) acc += mw.at(k, x) * s_a[j * w + x];
+                    for(int x = 0; x < w; x++) acc += s_mw[k * pw + x] * s_a[j * w + x];
                     acc = (acc + add1) >> sh1;
                 }
-                s_b[e] = (int16_t)acc;
+                s_b[e] = (int16_t)acc;                              // [j][k], row-major
             }
             __syncthreads();
-            for(int e = threadIdx.x; e < n; e += 256) {          // columns: s_a[k * w + j] from line j of the intermediate
+            // columns: out[k][j] = sum_y M_h[k][y] * t[y][j]; lanes walk j: contiguous reads of t, the matrix entry is a broadcast
+            for(int e = threadIdx.x; e < n; e += 256) {
                 const int j = e & (w - 1), k = e >> lw;
                 int       acc = 0;
                 if(k < mh.kmax) {
-                    for(int y = 0; y < h; y++) acc += mh.at(k, y) * s_b[j * h + y];
+                    for(int y = 0; y < h; y++) acc += s_mh[k * ph + y] * s_b[y * w + j];
                     acc = (acc + add2) >> sh2;
                 }
-                s_a[e] = (int16_t)acc;
+                s_a[e] = (int16_t)acc;                              // [k][j]: vertical frequency major, as the reference stores it
             }
         }
         else {
             const int sh1 = 7, add1 = 64, sh2 = 12 - (a.bd - 8), add2 = 1 << (sh2 - 1);
-            for(int e = threadIdx.x; e < n; e += 256) {          // columns: s_b[j * h + y] from column j of the coefficients
-                const int y = e & (h - 1), j = e >> lh;
+            // columns: t[y][j] = sat16(sum_k M_h[k][y] * coef[k][j]); lanes walk j
+            for(int e = threadIdx.x; e < n; e += 256) {
+                const int j = e & (w - 1), y = e >> lw;
                 int       acc = 0;
-                for(int k = 0; k < mh.kmax; k++) acc += mh.at(k, y) * s_a[k * w + j];
+                for(int k = 0; k < mh.kmax; k++) acc += s_mh[k * ph + y] * s_a[k * w + j];
                 acc = (acc + add1) >> sh1;
-                s_b[e] = (int16_t)max(-32768, min(32767, acc));
+                s_b[e] = (int16_t)max(-32768, min(32767, acc));   // [y][j]
             }
             __syncthreads();
-            for(int e = threadIdx.x; e < n; e += 256) {          // rows: s_a[j * w + x] from line j of the intermediate
-                const int x = e & (w - 1), j = e >> lw;
+            // rows: out[y][x] = sat16(sum_k M_w[k][x] * t[y][k]); lanes walk x: t is a broadcast, the matrix row contiguous
+            for(int e = threadIdx.x; e < n; e += 256) {
+                const int x = e & (w - 1), y = e >> lw;
                 int       acc = 0;
-                for(int k = 0; k < mw.kmax; k++) acc += mw.at(k, x) * s_b[k * h + j];
+                for(int k = 0; k < mw.kmax; k++) acc += s_mw[k * pw + x] * s_b[y * w + k];
                 acc = (acc + add2) >> sh2;
                 s_a[e] = (int16_t)max(-32768, min(32767, acc));
             }
