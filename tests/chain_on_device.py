@@ -98,9 +98,19 @@ def run(seq, pics, stand_in, all_inputs=False):
             hp.pic_upload_s16(scratch, *rec)
             return scratch
         extra = dict(mvp=hp.mvp, intra_nbr=hp.intra_nbr, upload=upload)
-    with tracedata.chain_with(hp.analyze_cu, hp.mc, hp.analyze_intra, **extra) as cw:
+    kernel_ms = [0.0]
+
+    def timed(fn):                      # device time of the operator's kernels (CUDA events on the library's stream), summed over the calls
+        def call(*args, **kw):
+            r = fn(*args, **kw)
+            kernel_ms[0] += float(getattr(hp, "last_kernel_ms", 0.0))
+            return r
+        return call
+    with tracedata.chain_with(timed(hp.analyze_cu), timed(hp.mc), timed(hp.analyze_intra), **extra) as cw:
         out = tracedata.chain_sequence(seq, pics, check=True, hp=hp)
     n_calls = (cw.n_cu, cw.n_intra)
+    if not stand_in:
+        print(f"  device kernel time inside the {cw.n_cu * 2 + cw.n_intra} analysis / prediction calls: {kernel_ms[0] / 1e3:.2f} s")
     assert cw.n_cu == sum(len(r["cu_log"]) for r in out) and cw.n_intra == sum(len(r["intra_log"]) for r in out)
     assert not all_inputs or (cw.n_nbr == cw.n_intra and cw.n_mvp >= cw.n_cu)
     launches = 0 if stand_in else hp.launches
