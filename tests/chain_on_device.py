@@ -12,6 +12,8 @@ then injected into the unmodified reference: the bitstream must be byte-identica
   --all-inputs   also the inputs of the analyses come from the device: xb200_mvp (MV predictor candidates, temporal direct MVs) and
                  xb200_intra_nbr (availability, reference samples, MPM list; the picture under reconstruction is uploaded per call)
   --more         further configurations (10-bit medium, P slices, plain quantiser) instead of the default pair
+  --dag          (under torchrun, one rank per GPU; with --stand-in: gloo on CPU) one stream over several ranks: picture-DAG waves,
+                 reference pictures broadcast after each wave (NCCL), every rank's pictures checked against the reference's
 """
 import ctypes as C
 import os
@@ -43,22 +45,27 @@ class StandIn:
         self.planes[h].y, self.planes[h].u, self.planes[h].v = [b.ctypes.data + 2 * (pd * b.shape[1] + pd) for b, pd in zip(bufs, pads)]
         self.planes[h].s_l, self.planes[h].s_c = bufs[0].shape[1], bufs[1].shape[1]
 
-    def pic_upload_s16(self, h, y, u, v):
-        self.pics[h]["act"] = [np.array(a, np.int16) for a in (y, u, v)]
-        if not self.pics[h]["padded"]:
-            self._bind(h, self.pics[h]["act"], (0, 0, 0))
-
-    def deblock(self, h, cus, pp, map_scu, map_refi, map_mv, expand=True):
-        post = xo.deblock(self.pics[h]["act"], cus, pp, map_scu, map_refi, map_mv, bit_depth=int(np.asarray(self.seq).reshape(-1)[0]["bit_depth"]))
+    def _bind_padded(self, h, planes):      # what the library does for a padded picture: borders replicated on upload / after deblocking
         bufs = []
-        for a, pad in zip(post, (144, 72, 72)):
+        for a, pad in zip(planes, (144, 72, 72)):
             hh, ww = a.shape
             buf = np.zeros((hh + 2 * pad, ww + 2 * pad), np.int16)
             buf[pad:pad + hh, pad:pad + ww] = a
             xo.lib().xo_pad_plane(buf.ctypes.data_as(C.c_void_p), buf.shape[1], ww, hh, pad)
             bufs.append(buf)
-        self.pics[h]["act"] = post
         self._bind(h, bufs, (144, 72, 72))
+
+    def pic_upload_s16(self, h, y, u, v):
+        self.pics[h]["act"] = [np.array(a, np.int16) for a in (y, u, v)]
+        if self.pics[h]["padded"]:
+            self._bind_padded(h, self.pics[h]["act"])
+        else:
+            self._bind(h, self.pics[h]["act"], (0, 0, 0))
+
+    def deblock(self, h, cus, pp, map_scu, map_refi, map_mv, expand=True):
+        post = xo.deblock(self.pics[h]["act"], cus, pp, map_scu, map_refi, map_mv, bit_depth=int(np.asarray(self.seq).reshape(-1)[0]["bit_depth"]))
+        self.pics[h]["act"] = post
+        self._bind_padded(h, post)
 
     def pic_download(self, h, with_padding):
         return self.pics[h]["act"]
@@ -125,7 +132,75 @@ MORE = [("2160p10", "medium", 5, "", dict(w=256, h=192, squares=[(48, 60, 40, 5,
         ("cif", "fast", 5, "rdoq=0;qp=27", QCIF)]                                                       # plain quantiser, lower QP
 
 
+def refs_of(pc):
+    pp = pc["pp"]
+    return sorted({int(pp["ref_poc"][l][k]) for l in range(2) for k in range(4) if int(pp["ref_pic"][l][k]) >= 0})
+
+
+def run_dag(rank, world, dist, stand_in, frames=17, device="cpu"):
+    """One stream over several ranks: the pictures of each wave of the picture DAG round-robin over the ranks
+    (xeve_b200.dist.picture_plan), every reference picture broadcast once after its wave (broadcast_picture); each rank decides its
+    pictures with its own device context (or the CPU stand-in) inside the decision chain and checks them against the reference's.
+    Returns (pictures decided here, pictures received)."""
+    from xeve_b200 import dist as xd
+    seq, pics = tracedata.live_chain(frames=frames)                  # every rank traces the same deterministic reference encode
+    by_poc = {int(pc["pp"]["poc"]): pc for pc in pics}
+    waves, owner, exchanged = xd.picture_plan([(poc, refs_of(pc)) for poc, pc in by_poc.items()], world)
+    if stand_in:
+        hp = StandIn(seq)
+    else:
+        from xeve_b200 import api
+        hp = api.Hotpath(seq, device=int(str(device).split(":")[1]) if ":" in str(device) else 0)
+    enc = tracedata.ChainEncoder(seq, check=True, hp=hp)
+    mine, received = [], []
+    with tracedata.chain_with(hp.analyze_cu, hp.mc, hp.analyze_intra):
+        for wave in waves:
+            for poc in wave:
+                if owner[poc] == rank:
+                    enc.encode(by_poc[poc])
+                    mine.append(poc)
+            for poc in wave:                                          # the exchange step of the wave
+                if poc not in exchanged:
+                    continue
+                shape = [a.shape for a in by_poc[poc]["org"]]
+                f = ((shape[0][1] + 3) // 4) * ((shape[0][0] + 3) // 4)
+                if owner[poc] == rank:
+                    planes, mv = enc.done[poc]["post"], enc.done[poc]["map_mv"]
+                else:
+                    planes, mv = [np.zeros(sh, np.int16) for sh in shape], np.zeros((f, 2, 2), np.int16)
+                planes, mv = xd.broadcast_picture(planes, np.asarray(mv).reshape(f, 2, 2), owner[poc], dist, device=device)
+                if owner[poc] != rank:
+                    enc.adopt(poc, planes, mv)
+                    received.append(poc)
+    hp.close()
+    return mine, received, waves, sorted(exchanged)
+
+
+def dag_main():
+    """torchrun entry: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/chain_on_device.py --dag"""
+    import torch
+    import torch.distributed as dist
+    stand_in = "--stand-in" in sys.argv
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    if stand_in:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        device = "cpu"
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        device = f"cuda:{local}"
+    t0 = time.time()
+    mine, received, waves, exchanged = run_dag(rank, world, dist, stand_in, device=device)
+    dist.barrier()
+    print(f"rank {rank}/{world}: decided {sorted(mine)}, received {sorted(received)}, {time.time() - t0:.1f} s", flush=True)
+    if rank == 0:
+        print(f"waves {waves}; reference pictures that travel: {exchanged}\nCHAIN_DAG_OK", flush=True)
+    dist.destroy_process_group()
+
+
 def main():
+    if "--dag" in sys.argv:
+        return dag_main()
     stand_in, all_inputs = "--stand-in" in sys.argv, "--all-inputs" in sys.argv
     if "--more" not in sys.argv:
         seq, pics = tracedata.chain_golden()

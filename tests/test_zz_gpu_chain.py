@@ -6,6 +6,8 @@ import sys
 
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 SCRIPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chain_on_device.py")
 
 
@@ -45,3 +47,21 @@ def test_cuda_operators_and_their_inputs_inside_the_decision_chain(args):
     if r.returncode != 0 or "CHAIN_ON_DEVICE_OK" not in r.stdout:
         pytest.xfail("first hardware run: " + (r.stdout[-1500:] + r.stderr[-1500:]))
     print(r.stdout)
+
+
+def test_picture_dag_over_two_ranks_with_stand_in_device_contexts():
+    """tests/chain_on_device.py --dag under torchrun (gloo, 2 ranks, the device contexts replaced by the CPU stand-in): the script the
+    GPU box runs with NCCL and one Hotpath per rank -- waves of the picture DAG, reference pictures broadcast after each wave and
+    adopted by the other rank's context, every rank's pictures checked against the reference's"""
+    from oracle import refharness as rh
+    if not rh.available():
+        pytest.skip("oracle/_ref (compiled reference) not built here")
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), SCRIPT, "--dag", "--stand-in"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "CHAIN_DAG_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0/2: decided [0, 1, 2, 4, 5, 8, 9, 10, 13, 16]" in r.stdout and "rank 1/2: decided [3, 6, 7, 11, 12, 14, 15]" in r.stdout
