@@ -395,6 +395,7 @@ INJECT_CONFIGS = [
     ("2160p10", "medium", 5, "", dict(w=256, h=192, squares=[(48, 60, 40, 5, 2)], pan=(6, 2))),        # 10-bit, medium
     ("cif", "fast", 6, "bframes=0;inter_slice_type=1", dict(tracedata.QCIF)),                          # P slices
     ("cif", "fast", 4, "qp=24", dict(w=352, h=288)),     # CIF 352x288 (BASELINE configs[0] size)
+    ("1080p", "fast", 2, "bframes=0", dict(w=1920, h=1080)),                                           # BASELINE configs[1] size: 1 020 CTUs, 387 KB
 ]
 
 
