@@ -398,6 +398,9 @@ INJECT_CONFIGS = [
     ("1080p", "fast", 2, "bframes=0", dict(w=1920, h=1080)),                                           # BASELINE configs[1] size: 1 020 CTUs, 387 KB
 ]
 
+if os.environ.get("XB200_SLOW_TESTS"):  # two more minutes: BASELINE configs[2] size (3840x2160 10-bit medium): 4 080 CTUs, 1.5 MB, byte-identical
+    INJECT_CONFIGS.append(("2160p10", "medium", 2, "bframes=0", dict(w=3840, h=2160)))
+
 
 @needs_ref
 @pytest.mark.parametrize("name,preset,frames,extra,override", INJECT_CONFIGS)
