@@ -410,6 +410,73 @@ XB200_API int xb200_intra_nbr(xb200_ctx *c, int32_t pic, xb200_nbr_item *items, 
 XB200_API int xb200_deblock(xb200_ctx *c, int32_t pic, const xb200_df_cu *cus, int64_t n, const xb200_df_pic *pp,
                             const uint32_t *map_scu, const int8_t *map_refi, const int16_t *map_mv, int expand, int mem);
 
+/* ---- the decision pass of a whole picture on the device (north_star: "the CTU tile loop in xeve_enc is lifted to the device") -----------
+ * xb200_analyze_picture runs, for one picture, everything between the picture-level set-up and the entropy coder:
+ *   the CTU loop of xeve_pic / xeve_ctu_mt_core            (src_base/xeve_enc.c:103-175, 327-404)
+ *   mode_analyze_lcu -> mode_coding_tree -> mode_coding_unit -> mode_check_inter / mode_check_intra
+ *                                                          (src_base/xeve_mode.c:1170-1348, 2007-2374, 2521-2608)
+ *   with init_cu_data / copy_cu_data / copy_to_cu_data, update_map_scu / clear_map_scu, mode_cpy_rec_to_ref, update_to_ctx_map,
+ *   xeve_pinter_analyze_cu and pintra_analyze_cu for every CU the tree visits (the operators above, as device functions),
+ *   then ctx->fn_loop_filter and ctx->fn_picbuf_expand     (src_base/xeve_enc.c:407, 1274)
+ * in ONE persistent kernel of one CTA per coder-state chain plus the loop-filter grids: no host round trip per CU or per CTU.
+ * A chain is what the reference calls a worker thread: with parallel_rows = n (param.threads, at most the CTU rows) CTU rows
+ * y, y + n, .. form one chain, each chain starts from the reset coder state and a CTU waits for its upper-right neighbour
+ * (src_base/xeve_enc.c:128-132) -- bit-exact with the reference run with `threads = n`; n = 1 is the single-thread bitstream.
+ * Pictures whose references are complete run concurrently (the library orders them with events on the reference pictures).
+ *
+ * What returns to the host is what the reference's entropy coder reads (ctx->map_cu_data[lcu]): per CTU 256
+ * xb200_scu_rec (16 x 16 units of 4x4 luma samples, raster inside the CTU) and the coefficient planes (Y 64x64 | U 32x32 | V 32x32,
+ * CU rectangles in place).  The reconstruction stays on the device as picture rec_pic (deblocked, borders replicated: a usable
+ * reference picture) together with its motion maps.  Restrictions: SLICE_B and SLICE_I (a P slice needs the bitstream-order state
+ * walk, src_base/xeve_eco.c:1519), quad-tree CUs 4..64, no delta QP, rdo_dbk_switch = 0 (presets fast / medium). */
+typedef struct {            /* decision of one 4x4 unit of a CTU */
+    uint8_t mode, log2;     /* 0 SKIP, 1 DIRECT, 2 INTER, 3 INTRA; log2 size of the leaf CU covering the unit */
+    int8_t  ipm, refi[2];
+    uint8_t mvp_idx[2], pad_;
+    int16_t mv[2][2], mvd[2][2];
+    int32_t nnz[3];
+} xb200_scu_rec;
+typedef struct { xb200_sbac s; uint16_t ipm[2], split, pad_; } xb200_state;  /* full coder state: + ctx.intra_dir[2], ctx.split_cu_flag[0] */
+typedef struct {
+    int32_t  poc, slice_type;            /* ctx->poc.poc_val; SLICE_B 0, SLICE_P 1, SLICE_I 2 */
+    int32_t  cur_pic, rec_pic;           /* original picture (unpadded) and the padded picture that receives the reconstruction */
+    int32_t  tile_qp;                    /* ctx->tile[0].qp (the QP field of map_scu) */
+    int32_t  num_refp[2], ref_pic[2][XB200_MAX_REFP], ref_poc[2][XB200_MAX_REFP]; /* ctx->rpm.num_refp, ctx->refp[refi][lidx] as [lidx][refi] */
+    int32_t  col_list_poc0;              /* ctx->refp[0][REFP_1].list_poc[0] */
+    int32_t  max_cu_inter, min_cu_inter, max_cu_intra, min_cu_intra, cip; /* param.*; pps.constrained_intra_pred_flag */
+    int32_t  qp[3];                      /* core->qp_y / qp_u / qp_v */
+    uint32_t lambda_mv;                  /* pi->lambda_mv */
+    int32_t  max_search_range;           /* pi->max_search_range */
+    int32_t  parallel_rows;              /* ctx->parallel_rows */
+    int32_t  deblock;                    /* sh->deblocking_filter_on */
+    int32_t  unfiltered_pic;             /* -1, or a padded picture that receives a copy of the reconstruction before the loop filter */
+    double   lambda[3], sqrt_lambda0, dist_chroma_weight[2];   /* core->lambda[], sqrt_lambda[0], dist_chroma_weight[] */
+    xb200_df_pic df;                     /* loop-filter inputs (w_scu / h_scu are filled by the library) */
+} xb200_picture;
+typedef struct {            /* what xb200_picture_fetch reports besides the records */
+    int64_t n_inter, n_intra;            /* CU analyses the decision pass ran */
+    double  chain_ms, filter_ms;         /* device time of the decision kernel and of the loop filter + border expansion */
+} xb200_picture_stat;
+
+/* Enqueues the picture and returns; fails with XB200_ERR_UNSUPPORTED for P slices and out-of-range CU sizes. */
+XB200_API int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp);
+/* Waits for picture rec_pic and copies its records to the caller (host buffers; any pointer may be NULL): scu [n_lcu * 256],
+ * coef [n_lcu * 6144], ctu_states [n_lcu][2] (the coder state each CTU's decision pass started from / ended with), ctu_cost [n_lcu]. */
+XB200_API int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16_t *coef, xb200_state *ctu_states,
+                                  double *ctu_cost, xb200_picture_stat *stat);
+/* Frame maps of a decided picture as the reference holds them when the loop filter starts (host buffers, any may be NULL):
+ * map_scu u32[f_scu], map_ipm s8[f_scu], map_refi s8[f_scu][2], map_mv s16[f_scu][2][2]. */
+XB200_API int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv);
+/* Adopt a reference picture decided elsewhere (another GPU of the picture DAG, a test): its motion map (refp.map_mv, what later
+ * pictures read as colocated MVs) is attached to padded picture `pic`, whose planes the caller uploads as usual. */
+XB200_API int xb200_picture_adopt(xb200_ctx *c, int32_t pic, const int16_t *map_mv);
+/* Debug aid: keep the records of the first cap_cu inter / cap_intra intra CU analyses of every following picture (in call order);
+ * xb200_picture_log copies those of picture rec_pic to the caller and returns their counts through n[2]. */
+XB200_API int xb200_picture_log_enable(xb200_ctx *c, int64_t cap_cu, int64_t cap_intra);
+XB200_API int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_intra_item *intra, int64_t n[2]);
+/* Number of decision chains (CTAs of the persistent kernel) the device can hold at once; pictures beyond it queue on the host. */
+XB200_API int xb200_chain_capacity(xb200_ctx *c);
+
 /* ---- Main profile, first operator: the two-stage 16-bit transforms -------------------------------------------------
  * Forward / inverse transform of a list of s16 blocks in place (row-major, w * h samples at element offset `off` of `blocks`):
  *   ats = 0: the "IQT" DCT-II of sps.tool_iqt -- xeve_trans with iqt_flag (src_main/xevem_tq.c:709-716, stages tx_pb2 .. tx_pb64

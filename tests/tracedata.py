@@ -512,3 +512,115 @@ class chain_with:
         if self.err and exc[0] is None:
             raise self.err
         return False
+
+
+# ---- the whole decision pass ON THE DEVICE (xb200_analyze_picture): the persistent chain kernel decides every CU of the picture ------
+def picture_record(pp, df_pp, cur_pic, rec_pic, ref_handles, unfiltered=-1, deblock=1, threads=None):
+    """xb200_picture from the picture-level fields of an LCU_REC (what the reference's control plane supplies) + the loop-filter inputs"""
+    from xeve_b200 import api
+    pp = np.asarray(pp).reshape(-1)[0]
+    p = np.zeros(1, api.PICTURE)
+    for k in ("poc", "slice_type", "tile_qp", "num_refp", "ref_poc", "col_list_poc0", "max_cu_inter", "min_cu_inter", "max_cu_intra",
+              "min_cu_intra", "cip", "qp", "lambda_mv", "max_search_range", "lambda", "sqrt_lambda0", "dist_chroma_weight"):
+        p[k] = pp[k]
+    p["parallel_rows"] = int(pp["parallel_rows"]) if threads is None else threads
+    p["cur_pic"], p["rec_pic"], p["unfiltered_pic"], p["deblock"] = cur_pic, rec_pic, unfiltered, deblock
+    p["ref_pic"] = -1
+    for l in range(2):
+        for k in range(4):
+            if int(pp["ref_pic"][l][k]) >= 0:
+                p["ref_pic"][0][l][k] = ref_handles[int(pp["ref_poc"][l][k])]
+    p["df"] = np.asarray(df_pp).reshape(-1)[0]
+    return p
+
+
+def leaf_cus_of(scu, w, h):
+    """leaf CUs in coding order (z-scan) from the per-CTU unit records -- what xeve_deblock_tree enumerates"""
+    w_lcu, out = (w + 63) // 64, []
+
+    def walk(lcu, xc, yc, x, y, L):
+        if x >= w or y >= h:
+            return
+        u = scu[lcu][((y - yc) >> 2) * 16 + ((x - xc) >> 2)]
+        if int(u["log2"]) == L + 2 or L == 0:
+            out.append((x, y, L + 2))
+            return
+        half = 2 << L
+        for part in range(4):
+            walk(lcu, xc, yc, x + (part & 1) * half, y + (part >> 1) * half, L - 1)
+    for lcu in range(len(scu)):
+        xc, yc = (lcu % w_lcu) << 6, (lcu // w_lcu) << 6
+        walk(lcu, xc, yc, xc, yc, 4)
+    return np.array(out, np.int64).reshape(-1, 3)
+
+
+class DevicePictureEncoder:
+    """Picture-by-picture encoder on the device: encode(pic) = xb200_analyze_picture (decision pass + loop filter + border expansion in
+    one enqueue); the reconstruction stays on the device as the reference of later pictures.  With check=True everything the reference
+    left behind for the picture (per-CTU coder states, frame maps, leaf CUs, the picture before / after deblocking) is compared.
+    compare_oracle=True additionally runs the oracle chain on the same inputs and compares every CU analysis in call order (debug)."""
+
+    def __init__(self, seq, hp, check=True, compare_oracle=False, threads=None, sync=True):
+        self.seq, self.hp, self.check, self.compare_oracle, self.threads, self.sync = seq, hp, check, compare_oracle, threads, sync
+        self.w, self.h = int(np.asarray(seq).reshape(-1)[0]["w"]), int(np.asarray(seq).reshape(-1)[0]["h"])
+        self.handles, self.pending, self.results = {}, [], []
+        self.oracle = ChainEncoder(seq, check=False, hp=None) if compare_oracle else None
+        if compare_oracle:
+            hp.picture_log_enable(self.hp.f_scu * 2, self.hp.f_scu * 2)
+
+    def enqueue(self, pc):
+        hp = self.hp
+        pp = np.asarray(pc["pp"]).reshape(-1)[0]
+        poc = int(pp["poc"])
+        org = [np.ascontiguousarray(a) for a in pc["org"]]
+        h_org, h_rec, h_pre = hp.pic_create(padded=False), hp.pic_create(padded=True), hp.pic_create(padded=True)
+        hp.pic_upload_s16(h_org, *org)
+        rec = picture_record(pp, pc["df_pp"], h_org, h_rec, self.handles, unfiltered=h_pre, threads=self.threads)
+        hp.analyze_picture(rec)
+        self.handles[poc] = h_rec
+        self.pending.append((pc, poc, h_org, h_rec, h_pre))
+
+    def collect(self):
+        hp = self.hp
+        for pc, poc, h_org, h_rec, h_pre in self.pending:
+            log = hp.picture_log(h_rec) if self.compare_oracle else None
+            r = hp.picture_fetch(h_rec)
+            r.update(hp.picture_maps(h_rec))
+            r["poc"], r["rec"] = poc, [np.ascontiguousarray(a) for a in hp.pic_download(h_pre, False)]
+            r["post"] = [np.ascontiguousarray(a) for a in hp.pic_download(h_rec, False)]
+            r["cus"] = leaf_cus_of(r["scu"], self.w, self.h)
+            hp.pic_destroy(h_pre)
+            hp.pic_destroy(h_org)
+            if self.compare_oracle:
+                o = self.oracle.encode(pc)
+                cu, it = log
+                assert len(cu) == len(o["cu_log"]) and len(it) == len(o["intra_log"]), (poc, len(cu), len(o["cu_log"]), len(it), len(o["intra_log"]))
+                for name, a, b, skip in (("inter", cu, o["cu_log"], ("cur_pic", "ref_pic", "coef_hash", "rec_hash", "me_first", "me_cnt", "pad0_", "pad1_")),
+                                         ("intra", it, o["intra_log"], ("cur_pic", "coef_hash", "rec_hash", "pad0_", "pad1_"))):
+                    for f in a.dtype.names:
+                        if f in skip:
+                            continue
+                        bad = [i for i in range(len(a)) if not np.array_equal(a[f][i], b[f][i])]
+                        assert not bad, f"POC {poc}: {name} CU analysis #{bad[0]} of {len(a)} differs in {f}: device {a[f][bad[0]]} oracle {b[f][bad[0]]} " \
+                                        f"(x {a['x'][bad[0]]} y {a['y'][bad[0]]} log2 {a['log2_cuw'][bad[0]]})"
+            if self.check:
+                e = pc["expect"]
+                st = r["states"].view(rh.STATE) if r["states"].dtype.itemsize == rh.STATE.itemsize else r["states"]
+                assert len(e["state_in"]) == len(st), poc
+                assert st[:, 0].tobytes() == e["state_in"].tobytes(), f"POC {poc}: coder states before the CTUs differ"
+                assert st[:, 1].tobytes() == e["state_out"].tobytes(), f"POC {poc}: coder states after the CTUs differ"
+                assert np.array_equal(r["map_scu"] & 0x81FF8000, e["map_scu"] & 0x81FF8000), poc   # coded, luma cbf, skip, QP, intra
+                assert np.array_equal(r["map_refi"].reshape(-1), np.asarray(e["map_refi"]).reshape(-1)), poc
+                assert np.array_equal(r["map_mv"].reshape(-1), np.asarray(e["map_mv"]).reshape(-1)), poc
+                ec = e["cus"]
+                assert len(r["cus"]) == len(ec) and np.array_equal(r["cus"][:, 0], ec["x"]) and np.array_equal(r["cus"][:, 1], ec["y"]) and \
+                    np.array_equal(r["cus"][:, 2], ec["log2_cuw"]), poc
+                assert e["pre"] is None or all(np.array_equal(a, b) for a, b in zip(r["rec"], e["pre"])), f"POC {poc}: unfiltered picture differs"
+                assert all(np.array_equal(a, b) for a, b in zip(r["post"], e["post"])), f"POC {poc}: deblocked picture differs"
+            self.results.append(r)
+        self.pending = []
+        return self.results
+
+    def encode(self, pc):
+        self.enqueue(pc)
+        return self.collect()[-1]

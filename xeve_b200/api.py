@@ -117,6 +117,20 @@ CU_ITEM = np.dtype([
     ("nnz", "<i4", (3,)), ("coef_hash", "<u8"), ("rec_hash", "<u8"), ("me_first", "<i4"), ("me_cnt", "<i4"),
 ], align=True)
 
+# ---- picture-level decision pass (xb200_analyze_picture) ----
+SCU_REC = np.dtype([("mode", "u1"), ("log2", "u1"), ("ipm", "i1"), ("refi", "i1", (2,)), ("mvp_idx", "u1", (2,)), ("pad_", "u1"),
+                    ("mv", "<i2", (2, 2)), ("mvd", "<i2", (2, 2)), ("nnz", "<i4", (3,))], align=True)
+STATE = np.dtype([("s", SBAC), ("ipm", "<u2", (2,)), ("split", "<u2"), ("pad_", "<u2")], align=True)
+PICTURE = np.dtype([
+    ("poc", "<i4"), ("slice_type", "<i4"), ("cur_pic", "<i4"), ("rec_pic", "<i4"), ("tile_qp", "<i4"),
+    ("num_refp", "<i4", (2,)), ("ref_pic", "<i4", (2, 4)), ("ref_poc", "<i4", (2, 4)), ("col_list_poc0", "<i4"),
+    ("max_cu_inter", "<i4"), ("min_cu_inter", "<i4"), ("max_cu_intra", "<i4"), ("min_cu_intra", "<i4"), ("cip", "<i4"),
+    ("qp", "<i4", (3,)), ("lambda_mv", "<u4"), ("max_search_range", "<i4"), ("parallel_rows", "<i4"), ("deblock", "<i4"),
+    ("unfiltered_pic", "<i4"), ("lambda", "<f8", (3,)), ("sqrt_lambda0", "<f8"), ("dist_chroma_weight", "<f8", (2,)),
+    ("df", DF_PIC),
+], align=True)
+PICTURE_STAT = np.dtype([("n_inter", "<i8"), ("n_intra", "<i8"), ("chain_ms", "<f8"), ("filter_ms", "<f8")], align=True)
+
 VP = C.c_void_p
 _lib = None
 
@@ -165,6 +179,13 @@ def load():
         L.xb200_intra_nbr.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, C.c_int, C.c_int, C.c_int, VP, C.c_int64]
         L.xb200_deblock.argtypes = [VP, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int]
         L.xb200_transform_main.argtypes = [VP, VP, C.c_int64, VP, C.c_int64, C.c_int]
+        L.xb200_analyze_picture.argtypes = [VP, VP]
+        L.xb200_picture_fetch.argtypes = [VP, C.c_int32, VP, VP, VP, VP, VP]
+        L.xb200_picture_maps.argtypes = [VP, C.c_int32, VP, VP, VP, VP]
+        L.xb200_picture_adopt.argtypes = [VP, C.c_int32, VP]
+        L.xb200_picture_log_enable.argtypes = [VP, C.c_int64, C.c_int64]
+        L.xb200_picture_log.argtypes = [VP, C.c_int32, VP, VP, VP]
+        L.xb200_chain_capacity.argtypes = [VP]
         _lib = L
     return _lib
 
@@ -173,7 +194,8 @@ EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
            "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr",
-           "xb200_transform_main"]
+           "xb200_transform_main", "xb200_analyze_picture", "xb200_picture_fetch", "xb200_picture_maps", "xb200_picture_adopt",
+           "xb200_picture_log_enable", "xb200_picture_log", "xb200_chain_capacity"]
 
 
 def _p(a):
@@ -402,3 +424,55 @@ class Hotpath:
         self._ck(self.L.xb200_residue(self.h, _p(items), len(items), _p(rates), len(rates), _p(coef), _p(rec), elems, MEM_HOST),
                  "xb200_residue")
         return items, coef, rec
+
+    # ---- the decision pass of a whole picture (persistent kernel, one CTA per coder-state chain) ----------------------------
+    @property
+    def n_lcu(self):
+        return ((self.w + 63) // 64) * ((self.hgt + 63) // 64)
+
+    @property
+    def f_scu(self):
+        return ((self.w + 3) // 4) * ((self.hgt + 3) // 4)
+
+    def chain_capacity(self):
+        r = self.L.xb200_chain_capacity(self.h)
+        if r < 0:
+            raise Xb200Error(r, "xb200_chain_capacity")
+        return r
+
+    def analyze_picture(self, pic):
+        """Enqueue one picture (PICTURE record); returns at once, xb200 orders it after its reference pictures."""
+        pic = np.ascontiguousarray(pic, PICTURE).reshape(1)
+        self._ck(self.L.xb200_analyze_picture(self.h, _p(pic)), "xb200_analyze_picture")
+
+    def picture_fetch(self, rec_pic, want_states=True):
+        """Wait for picture rec_pic -> dict(scu [n_lcu, 256], coef [n_lcu, 6144], states [n_lcu, 2], cost [n_lcu], stat)"""
+        n = self.n_lcu
+        scu, coef = np.zeros((n, 256), SCU_REC), np.zeros((n, 6144), np.int16)
+        st = np.zeros((n, 2), STATE) if want_states else None
+        cost, stat = np.zeros(n, np.float64), np.zeros(1, PICTURE_STAT)
+        self._ck(self.L.xb200_picture_fetch(self.h, rec_pic, _p(scu), _p(coef), _p(st), _p(cost), _p(stat)), "xb200_picture_fetch")
+        return dict(scu=scu, coef=coef, states=st, cost=cost, stat=stat[0])
+
+    def picture_maps(self, rec_pic):
+        f = self.f_scu
+        m = dict(map_scu=np.zeros(f, np.uint32), map_ipm=np.zeros(f, np.int8), map_refi=np.zeros((f, 2), np.int8),
+                 map_mv=np.zeros((f, 2, 2), np.int16))
+        self._ck(self.L.xb200_picture_maps(self.h, rec_pic, _p(m["map_scu"]), _p(m["map_ipm"]), _p(m["map_refi"]), _p(m["map_mv"])),
+                 "xb200_picture_maps")
+        return m
+
+    def picture_adopt(self, pic, map_mv):
+        map_mv = np.ascontiguousarray(map_mv, np.int16)
+        assert map_mv.size == self.f_scu * 4
+        self._ck(self.L.xb200_picture_adopt(self.h, pic, _p(map_mv)), "xb200_picture_adopt")
+
+    def picture_log_enable(self, cap_cu, cap_intra):
+        self._ck(self.L.xb200_picture_log_enable(self.h, cap_cu, cap_intra), "xb200_picture_log_enable")
+        self._log_caps = (cap_cu, cap_intra)
+
+    def picture_log(self, rec_pic):
+        """(inter CU records, intra CU records) of picture rec_pic in call order -- before picture_fetch releases them"""
+        cu, it, n = np.zeros(self._log_caps[0], CU_ITEM), np.zeros(self._log_caps[1], INTRA_ITEM), np.zeros(2, np.int64)
+        self._ck(self.L.xb200_picture_log(self.h, rec_pic, _p(cu), _p(it), _p(n)), "xb200_picture_log")
+        return cu[:int(n[0])], it[:int(n[1])]

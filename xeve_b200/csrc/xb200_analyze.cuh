@@ -260,6 +260,235 @@ __device__ __noinline__ uint32_t cu_me(const CuTeam<L2> &Tm, const PicDev *__res
     return cost;
 }
 
+// xeve_pinter_analyze_cu of ONE CU by one team (the first T threads of the CTA or one warp): `git` is the CU record (inputs read,
+// results written), st_in / st_out / rates / coef_out / rec_out are the arrays its indices and offsets refer to.  pred_y_out
+// (optional) receives the winner's luma prediction (mi->pred_y_best, the input of core->inter_satd, src_base/xeve_mode.c:1247-1258).
+// `phase` is the parity of the team's search-window mbarrier and persists across calls.
+template <int L2>
+__device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__restrict__ pics, xb200_cu_item *git, const xb200_rates *rates,
+                                            const xb200_sbac *st_in, xb200_sbac *st_out, int16_t *coef_out, int16_t *rec_out,
+                                            int16_t *pred_y_out, const SeqDev &sq, int win_cap, int *err_flag, uint32_t &phase, int tt)
+{
+    using Cf = CuCfg<L2>;
+    constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NCH = Cf::NCH, NP = Cf::NP;
+    CuHdr    &H = *Tm.H;
+    const int sh = (sq.bd - 8) << 1;
+    {   // CU record and input coder state -> shared
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(git);
+        uint32_t       *dst = reinterpret_cast<uint32_t *>(&H.cu);
+        for(int e = tt; e < (int)(sizeof(xb200_cu_item) / 4); e += T) dst[e] = src[e];
+        const xb200_sbac &s = st_in[git->state_in];
+        for(int k = tt; k < XB200_CM_COUNT; k += T) H.st[ST_IN][k] = s.m[k];
+        if(tt == 0) H.rg[ST_IN] = s.range;
+    }
+    team_sync<T>();
+    const xb200_cu_item &cu = H.cu;
+    const xb200_rates   *rt = &rates[cu.rate_idx];
+    const PicDev        &o = pics[cu.cur_pic];
+    Tm.org[0] = o.p[0] + (ptrdiff_t)cu.y * o.s[0] + cu.x;
+    Tm.org[1] = o.p[1] + (ptrdiff_t)(cu.y >> 1) * o.s[1] + (cu.x >> 1);
+    Tm.org[2] = o.p[2] + (ptrdiff_t)(cu.y >> 1) * o.s[2] + (cu.x >> 1);
+    Tm.so[0] = o.s[0]; Tm.so[1] = o.s[1]; Tm.so[2] = o.s[2];
+    const bool   B = cu.slice_type == 0;
+    const double w0 = cu.dist_chroma_weight[0], w1 = cu.dist_chroma_weight[1];
+    double       cost_best = CU_MAX_COST, cost_l0 = CU_MAX_COST, cost_l1 = CU_MAX_COST;
+    int          best_idx = 3;
+
+    // ---- xeve_analyze_skip: merge_num (x merge_num in B) candidate pairs, duplicates pruned ----------------
+    int64_t best_ssd = (int64_t)1 << (2 * L2 + 16);
+    {
+        double sb = CU_MAX_COST;
+        for(int idx0 = 0; idx0 < sq.merge_num; idx0++) {
+            bool dup = false;
+            for(int t = idx0 - 1; t >= 0; t--) dup |= cu.mvp[0][t][0] == cu.mvp[0][idx0][0] && cu.mvp[0][t][1] == cu.mvp[0][idx0][1];
+            if(dup) continue;
+            const int cnt = B ? sq.merge_num : 1;
+            for(int idx1 = 0; idx1 < cnt; idx1++) {
+                dup = false;
+                for(int t = idx1 - 1; t >= 0; t--) dup |= cu.mvp[1][t][0] == cu.mvp[1][idx1][0] && cu.mvp[1][t][1] == cu.mvp[1][idx1][1];
+                if(dup) continue;
+                const int8_t  refi[2] = {cu.refi_pred[0][idx0], (int8_t)(B ? cu.refi_pred[1][idx1] : -1)};
+                const int16_t mv[2][2] = {{cu.mvp[0][idx0][0], cu.mvp[0][idx0][1]}, {cu.mvp[1][idx1][0], cu.mvp[1][idx1][1]}};
+                if(refi[0] < 0 && refi[1] < 0) continue;
+                cu_predict<L2>(pics, cu, sq, refi[0], refi[1], mv[0][0], mv[0][1], mv[1][0], mv[1][1], Tm.pred, Tm.aux,
+                               reinterpret_cast<int16_t *>(Tm.TB), tt);
+                const int64_t cy = ssd_plane_t<L2, T>(Tm.org[0], Tm.so[0], Tm.pred, sh, tt, H.X);
+                const int64_t cb = ssd_plane_t<L2 - 1, T>(Tm.org[1], Tm.so[1], Tm.pred + NY, sh, tt, H.X);
+                const int64_t cr = ssd_plane_t<L2 - 1, T>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, sh, tt, H.X);
+                xb200_bits_item bi = cu_bits_item(cu, 0, 3, 0);
+                bi.mvp_idx[0] = (uint8_t)idx0; bi.mvp_idx[1] = (uint8_t)idx1;
+                const uint32_t bits = cu_count<T>(H, bi, nullptr, ST_IN, tt);
+                double cost = __dadd_rn(__dadd_rn(__ll2double_rn(cy), __dmul_rn(w0, __ll2double_rn(cb))), __dmul_rn(w1, __ll2double_rn(cr)));
+                cost = __dadd_rn(cost, __dmul_rn((double)bits, cu.lambda[0]));
+                if(cost < sb) {
+                    sb = cost;
+                    best_ssd = cy + cb + cr;
+                    if(tt == 0) {
+                        CuMode &M = H.md[3];
+                        M.mvp_idx[0] = (uint8_t)idx0; M.mvp_idx[1] = (uint8_t)idx1;
+                        M.refi[0] = refi[0]; M.refi[1] = refi[1];
+                        M.mv[0][0] = mv[0][0]; M.mv[0][1] = mv[0][1]; M.mv[1][0] = mv[1][0]; M.mv[1][1] = mv[1][1];
+                        M.mvd[0][0] = M.mvd[0][1] = M.mvd[1][0] = M.mvd[1][1] = 0;
+                        M.nnz[0] = M.nnz[1] = M.nnz[2] = 0; M.cbf = 0;
+                    }
+                    cu_st_save<T>(H, ST_MODE, ST_RUN, tt);
+                }
+            }
+        }
+        if(sb < cost_best) { cost_best = sb; best_idx = 3; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
+    }
+    team_sync<T>();
+    double cost_win = cost_best;
+    if(cost_best < CU_MAX_COST && best_ssd > 0) {
+        if(B) { // ---- analyze_t_direct ----
+            if(tt == 0) {
+                CuMode &M = H.md[4];
+                M.refi[0] = M.refi[1] = 0; M.mvp_idx[0] = M.mvp_idx[1] = 0;
+                M.mv[0][0] = cu.mv_dir[0][0]; M.mv[0][1] = cu.mv_dir[0][1]; M.mv[1][0] = cu.mv_dir[1][0]; M.mv[1][1] = cu.mv_dir[1][1];
+                M.mvd[0][0] = M.mvd[0][1] = M.mvd[1][0] = M.mvd[1][1] = 0;
+            }
+            team_sync<T>();
+            const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, 4, 0, 0, tt);
+            if(c < cost_best) { cost_best = c; best_idx = 4; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
+        }
+        // ---- uni-directional search per list, best reference by ME cost, check_best_mvp, residue RDO ----
+        int32_t mot_bits[2] = {0, 0};
+        int16_t mv_scale[2][XB200_MAX_REFP][2];
+        uint8_t mvp_idx[2] = {0, 0};
+        int     num_refp_cur = 0;
+        for(int lidx = 0; lidx <= (B ? 1 : 0); lidx++) {
+            uint32_t best_me = 0xffffffffu;
+            int      refi_t = 0;
+            num_refp_cur = min((int)cu.num_refp[lidx], XB200_MAX_REFP);
+            mvp_idx[lidx] = H.md[3].mvp_idx[lidx];
+            const int16_t(*cand)[2] = cu.mvp[lidx];
+            for(int r = 0; r < num_refp_cur; r++) {
+                int            mx, my;
+                const uint32_t mecost = cu_me<L2>(Tm, pics, sq, win_cap, err_flag, lidx, r, num_refp_cur, 0, cand[mvp_idx[lidx]][0],
+                                                  cand[mvp_idx[lidx]][1], 0, 0, mot_bits, phase, mx, my, tt);
+                mv_scale[lidx][r][0] = (int16_t)mx; mv_scale[lidx][r][1] = (int16_t)my;
+                if(mecost < best_me) { best_me = mecost; refi_t = r; }
+            }
+            const int mvx = mv_scale[lidx][refi_t][0], mvy = mv_scale[lidx][refi_t][1];
+            // check_best_mvp: the loop compares against the cost of the initial index only (quirk q1)
+            {
+                xb200_bits_item bi = cu_bits_item(cu, 2, lidx, 0);
+                bi.refi[lidx] = (int8_t)refi_t;
+                bi.mvp_idx[0] = mvp_idx[lidx];
+                bi.mvd[lidx][0] = (int16_t)(mvx - cand[mvp_idx[lidx]][0]); bi.mvd[lidx][1] = (int16_t)(mvy - cand[mvp_idx[lidx]][1]);
+                const double ref_cost = __dmul_rn((double)cu_count<T>(H, bi, nullptr, ST_IN, tt), cu.lambda[0]);
+                int          best = mvp_idx[lidx];
+                for(int idx = 0; idx < 4; idx++) {
+                    bool dup = false;
+                    for(int t = idx - 1; t >= 0; t--) dup |= cand[idx][0] == cand[t][0] && cand[idx][1] == cand[t][1];
+                    if(dup) continue;
+                    bi.mvp_idx[0] = (uint8_t)idx;
+                    bi.mvd[lidx][0] = (int16_t)(mvx - cand[idx][0]); bi.mvd[lidx][1] = (int16_t)(mvy - cand[idx][1]);
+                    const double c = __dmul_rn((double)cu_count<T>(H, bi, nullptr, ST_IN, tt), cu.lambda[0]);
+                    if(c < ref_cost) best = idx;
+                }
+                mvp_idx[lidx] = (uint8_t)best;
+            }
+            if(tt == 0) {
+                CuMode &M = H.md[lidx];
+                M.refi[lidx] = (int8_t)refi_t; M.refi[1 - lidx] = -1;
+                M.mv[lidx][0] = (int16_t)mvx; M.mv[lidx][1] = (int16_t)mvy; M.mv[1 - lidx][0] = M.mv[1 - lidx][1] = 0;
+                M.mvd[lidx][0] = (int16_t)(mvx - cand[mvp_idx[lidx]][0]); M.mvd[lidx][1] = (int16_t)(mvy - cand[mvp_idx[lidx]][1]);
+                M.mvd[1 - lidx][0] = M.mvd[1 - lidx][1] = 0;
+                M.mvp_idx[lidx] = mvp_idx[lidx]; M.mvp_idx[1 - lidx] = 0;
+            }
+            team_sync<T>();
+            const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, lidx, mvp_idx[0], mvp_idx[1], tt);
+            if(lidx == 0) cost_l0 = c; else cost_l1 = c;
+            if(c < cost_best) { cost_best = c; best_idx = lidx; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
+        }
+        if(B) { // ---- analyze_bi: alternate the refined list, start MVs = the uni results, at most BI_ITER = 4 passes ----
+            int      lidx_ref = cost_l0 <= cost_l1 ? 0 : 1, lidx_cnd = 1 - lidx_ref;
+            int8_t   refi[2] = {-1, -1};
+            int8_t   m_refi[2] = {H.md[0].refi[0], H.md[1].refi[1]};
+            int16_t  m_mv[2][2] = {{H.md[0].mv[0][0], H.md[0].mv[0][1]}, {H.md[1].mv[1][0], H.md[1].mv[1][1]}};
+            const uint8_t m_idx[2] = {H.md[0].mvp_idx[0], H.md[1].mvp_idx[1]};
+            uint32_t best_me = 0xffffffffu;
+            int      refi_best = 0;
+            refi[lidx_ref] = m_refi[lidx_ref];
+            for(int iter = 0; iter < 4; iter++) {
+                cu_predict<L2>(pics, cu, sq, refi[0], refi[1], m_mv[0][0], m_mv[0][1], m_mv[1][0], m_mv[1][1], Tm.pred, Tm.aux,
+                               reinterpret_cast<int16_t *>(Tm.TB), tt);
+                for(int e = tt; e < NY; e += T)   // get_org_bi
+                    Tm.org_bi[e] = (int16_t)(((int)Tm.org[0][(ptrdiff_t)(e >> L2) * Tm.so[0] + (e & (N - 1))] << 1) - (int)Tm.pred[e]);
+                team_sync<T>();
+                { const int8_t t = refi[lidx_ref]; refi[lidx_ref] = refi[lidx_cnd]; refi[lidx_cnd] = t; }
+                { const int t = lidx_ref; lidx_ref = lidx_cnd; lidx_cnd = t; }
+                const int mi = m_idx[lidx_ref];
+                bool      changed = false;
+                for(int r = 0; r < num_refp_cur; r++) {
+                    int            mx, my;
+                    const uint32_t mecost = cu_me<L2>(Tm, pics, sq, win_cap, err_flag, lidx_ref, r, num_refp_cur, 1, cu.mvp[lidx_ref][mi][0],
+                                                      cu.mvp[lidx_ref][mi][1], mv_scale[lidx_ref][r][0], mv_scale[lidx_ref][r][1], mot_bits,
+                                                      phase, mx, my, tt);
+                    mv_scale[lidx_ref][r][0] = (int16_t)mx; mv_scale[lidx_ref][r][1] = (int16_t)my;
+                    if(mecost < best_me) {
+                        refi_best = r; best_me = mecost; changed = true;
+                        m_refi[lidx_ref] = (int8_t)r;
+                        m_mv[lidx_ref][0] = (int16_t)mx; m_mv[lidx_ref][1] = (int16_t)my;
+                    }
+                }
+                refi[lidx_ref] = (int8_t)refi_best; refi[lidx_cnd] = -1;
+                if(!changed) break;
+            }
+            if(tt == 0) {
+                CuMode &M = H.md[2];
+                for(int l = 0; l < 2; l++) {
+                    M.refi[l] = m_refi[l]; M.mvp_idx[l] = m_idx[l];
+                    M.mv[l][0] = m_mv[l][0]; M.mv[l][1] = m_mv[l][1];
+                    M.mvd[l][0] = (int16_t)(m_mv[l][0] - cu.mvp[l][m_idx[l]][0]); M.mvd[l][1] = (int16_t)(m_mv[l][1] - cu.mvp[l][m_idx[l]][1]);
+                }
+            }
+            team_sync<T>();
+            const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, 2, m_idx[0], m_idx[1], tt);
+            if(c < cost_best) { cost_best = c; best_idx = 2; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
+        }
+        cost_win = cost_best;
+    }
+    // ---- winner: coefficients (dropped planes zeroed), reconstruction, XEVE_MODE fields, s_next_best ---------
+    const CuMode &M = H.md[best_idx];
+    int16_t      *gc = coef_out + cu.out_off, *gr = rec_out ? rec_out + cu.out_off : nullptr;
+    if(best_idx == 3) {
+        cu_predict<L2>(pics, cu, sq, M.refi[0], M.refi[1], M.mv[0][0], M.mv[0][1], M.mv[1][0], M.mv[1][1], Tm.pred, Tm.aux,
+                       reinterpret_cast<int16_t *>(Tm.TB), tt);
+        for(int e = tt; e < NP; e += T) {
+            gc[e] = 0;
+            if(gr) gr[e] = Tm.pred[e];
+            if(pred_y_out && e < NY) pred_y_out[e] = Tm.pred[e];
+        }
+    }
+    else {
+        const int16_t *sc = Tm.scratch + (size_t)(3 * best_idx) * NP, *sr = sc + NP, *sp = sr + NP;
+        const int      cbf = M.cbf;
+        for(int e = tt; e < NP; e += T) {
+            const int  c = e < NY ? 0 : (e < NY + NCH ? 1 : 2);
+            const bool on = (cbf >> c) & 1;
+            gc[e] = on ? __ldcg(sc + e) : (int16_t)0;
+            if(gr) gr[e] = on ? __ldcg(sr + e) : __ldcg(sp + e);
+            if(pred_y_out && e < NY) pred_y_out[e] = __ldcg(sp + e);
+        }
+    }
+    if(tt == 0) {
+        git->cost = cost_win; git->best_idx = (uint8_t)best_idx;
+        for(int l = 0; l < 2; l++) {
+            git->refi[l] = M.refi[l]; git->mvp_idx[l] = M.mvp_idx[l];
+            git->mv[l][0] = M.mv[l][0]; git->mv[l][1] = M.mv[l][1]; git->mvd[l][0] = M.mvd[l][0]; git->mvd[l][1] = M.mvd[l][1];
+        }
+        git->nnz[0] = M.nnz[0]; git->nnz[1] = M.nnz[1]; git->nnz[2] = M.nnz[2];
+    }
+    if(cu.state_out >= 0 && tt < 32) {
+        xb200_sbac &so = st_out[cu.state_out];
+        for(int k = tt; k < XB200_CM_COUNT; k += 32) so.m[k] = H.st[ST_BEST][k];
+        if(tt == 0) so.range = H.rg[ST_BEST];
+    }
+    team_sync<T>();
+}
+
 template <int L2, int TEAMS>
 __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicDev *__restrict__ pics, xb200_cu_item *__restrict__ items,
                                                                const int32_t *__restrict__ order, int n, const xb200_rates *__restrict__ rates,
@@ -293,221 +522,7 @@ __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicD
     if(tt == 0) mbar_init(reinterpret_cast<uint64_t *>(Tm.me_area), 1);
     __syncthreads();
     uint32_t phase = 0;
-    const int sh = (sq.bd - 8) << 1;
 
-    for(int i = blockIdx.x * Cf::TEAMS + team; i < n; i += gridDim.x * Cf::TEAMS) {
-        xb200_cu_item *git = &items[order[i]];
-        {   // CU record and input coder state -> shared
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(git);
-            uint32_t       *dst = reinterpret_cast<uint32_t *>(&H.cu);
-            for(int e = tt; e < (int)(sizeof(xb200_cu_item) / 4); e += T) dst[e] = src[e];
-            const xb200_sbac &s = st_in[git->state_in];
-            for(int k = tt; k < XB200_CM_COUNT; k += T) H.st[ST_IN][k] = s.m[k];
-            if(tt == 0) H.rg[ST_IN] = s.range;
-        }
-        team_sync<T>();
-        const xb200_cu_item &cu = H.cu;
-        const xb200_rates   *rt = &rates[cu.rate_idx];
-        const PicDev        &o = pics[cu.cur_pic];
-        Tm.org[0] = o.p[0] + (ptrdiff_t)cu.y * o.s[0] + cu.x;
-        Tm.org[1] = o.p[1] + (ptrdiff_t)(cu.y >> 1) * o.s[1] + (cu.x >> 1);
-        Tm.org[2] = o.p[2] + (ptrdiff_t)(cu.y >> 1) * o.s[2] + (cu.x >> 1);
-        Tm.so[0] = o.s[0]; Tm.so[1] = o.s[1]; Tm.so[2] = o.s[2];
-        const bool   B = cu.slice_type == 0;
-        const double w0 = cu.dist_chroma_weight[0], w1 = cu.dist_chroma_weight[1];
-        double       cost_best = CU_MAX_COST, cost_l0 = CU_MAX_COST, cost_l1 = CU_MAX_COST;
-        int          best_idx = 3;
-
-        // ---- xeve_analyze_skip: merge_num (x merge_num in B) candidate pairs, duplicates pruned ----------------
-        int64_t best_ssd = (int64_t)1 << (2 * L2 + 16);
-        {
-            double sb = CU_MAX_COST;
-            for(int idx0 = 0; idx0 < sq.merge_num; idx0++) {
-                bool dup = false;
-                for(int t = idx0 - 1; t >= 0; t--) dup |= cu.mvp[0][t][0] == cu.mvp[0][idx0][0] && cu.mvp[0][t][1] == cu.mvp[0][idx0][1];
-                if(dup) continue;
-                const int cnt = B ? sq.merge_num : 1;
-                for(int idx1 = 0; idx1 < cnt; idx1++) {
-                    dup = false;
-                    for(int t = idx1 - 1; t >= 0; t--) dup |= cu.mvp[1][t][0] == cu.mvp[1][idx1][0] && cu.mvp[1][t][1] == cu.mvp[1][idx1][1];
-                    if(dup) continue;
-                    const int8_t  refi[2] = {cu.refi_pred[0][idx0], (int8_t)(B ? cu.refi_pred[1][idx1] : -1)};
-                    const int16_t mv[2][2] = {{cu.mvp[0][idx0][0], cu.mvp[0][idx0][1]}, {cu.mvp[1][idx1][0], cu.mvp[1][idx1][1]}};
-                    if(refi[0] < 0 && refi[1] < 0) continue;
-                    cu_predict<L2>(pics, cu, sq, refi[0], refi[1], mv[0][0], mv[0][1], mv[1][0], mv[1][1], Tm.pred, Tm.aux,
-                                   reinterpret_cast<int16_t *>(Tm.TB), tt);
-                    const int64_t cy = ssd_plane_t<L2, T>(Tm.org[0], Tm.so[0], Tm.pred, sh, tt, H.X);
-                    const int64_t cb = ssd_plane_t<L2 - 1, T>(Tm.org[1], Tm.so[1], Tm.pred + NY, sh, tt, H.X);
-                    const int64_t cr = ssd_plane_t<L2 - 1, T>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, sh, tt, H.X);
-                    xb200_bits_item bi = cu_bits_item(cu, 0, 3, 0);
-                    bi.mvp_idx[0] = (uint8_t)idx0; bi.mvp_idx[1] = (uint8_t)idx1;
-                    const uint32_t bits = cu_count<T>(H, bi, nullptr, ST_IN, tt);
-                    double cost = __dadd_rn(__dadd_rn(__ll2double_rn(cy), __dmul_rn(w0, __ll2double_rn(cb))), __dmul_rn(w1, __ll2double_rn(cr)));
-                    cost = __dadd_rn(cost, __dmul_rn((double)bits, cu.lambda[0]));
-                    if(cost < sb) {
-                        sb = cost;
-                        best_ssd = cy + cb + cr;
-                        if(tt == 0) {
-                            CuMode &M = H.md[3];
-                            M.mvp_idx[0] = (uint8_t)idx0; M.mvp_idx[1] = (uint8_t)idx1;
-                            M.refi[0] = refi[0]; M.refi[1] = refi[1];
-                            M.mv[0][0] = mv[0][0]; M.mv[0][1] = mv[0][1]; M.mv[1][0] = mv[1][0]; M.mv[1][1] = mv[1][1];
-                            M.mvd[0][0] = M.mvd[0][1] = M.mvd[1][0] = M.mvd[1][1] = 0;
-                            M.nnz[0] = M.nnz[1] = M.nnz[2] = 0; M.cbf = 0;
-                        }
-                        cu_st_save<T>(H, ST_MODE, ST_RUN, tt);
-                    }
-                }
-            }
-            if(sb < cost_best) { cost_best = sb; best_idx = 3; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
-        }
-        team_sync<T>();
-        double cost_win = cost_best;
-        if(cost_best < CU_MAX_COST && best_ssd > 0) {
-            if(B) { // ---- analyze_t_direct ----
-                if(tt == 0) {
-                    CuMode &M = H.md[4];
-                    M.refi[0] = M.refi[1] = 0; M.mvp_idx[0] = M.mvp_idx[1] = 0;
-                    M.mv[0][0] = cu.mv_dir[0][0]; M.mv[0][1] = cu.mv_dir[0][1]; M.mv[1][0] = cu.mv_dir[1][0]; M.mv[1][1] = cu.mv_dir[1][1];
-                    M.mvd[0][0] = M.mvd[0][1] = M.mvd[1][0] = M.mvd[1][1] = 0;
-                }
-                team_sync<T>();
-                const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, 4, 0, 0, tt);
-                if(c < cost_best) { cost_best = c; best_idx = 4; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
-            }
-            // ---- uni-directional search per list, best reference by ME cost, check_best_mvp, residue RDO ----
-            int32_t mot_bits[2] = {0, 0};
-            int16_t mv_scale[2][XB200_MAX_REFP][2];
-            uint8_t mvp_idx[2] = {0, 0};
-            int     num_refp_cur = 0;
-            for(int lidx = 0; lidx <= (B ? 1 : 0); lidx++) {
-                uint32_t best_me = 0xffffffffu;
-                int      refi_t = 0;
-                num_refp_cur = min((int)cu.num_refp[lidx], XB200_MAX_REFP);
-                mvp_idx[lidx] = H.md[3].mvp_idx[lidx];
-                const int16_t(*cand)[2] = cu.mvp[lidx];
-                for(int r = 0; r < num_refp_cur; r++) {
-                    int            mx, my;
-                    const uint32_t mecost = cu_me<L2>(Tm, pics, sq, win_cap, err_flag, lidx, r, num_refp_cur, 0, cand[mvp_idx[lidx]][0],
-                                                      cand[mvp_idx[lidx]][1], 0, 0, mot_bits, phase, mx, my, tt);
-                    mv_scale[lidx][r][0] = (int16_t)mx; mv_scale[lidx][r][1] = (int16_t)my;
-                    if(mecost < best_me) { best_me = mecost; refi_t = r; }
-                }
-                const int mvx = mv_scale[lidx][refi_t][0], mvy = mv_scale[lidx][refi_t][1];
-                // check_best_mvp: the loop compares against the cost of the initial index only (quirk q1)
-                {
-                    xb200_bits_item bi = cu_bits_item(cu, 2, lidx, 0);
-                    bi.refi[lidx] = (int8_t)refi_t;
-                    bi.mvp_idx[0] = mvp_idx[lidx];
-                    bi.mvd[lidx][0] = (int16_t)(mvx - cand[mvp_idx[lidx]][0]); bi.mvd[lidx][1] = (int16_t)(mvy - cand[mvp_idx[lidx]][1]);
-                    const double ref_cost = __dmul_rn((double)cu_count<T>(H, bi, nullptr, ST_IN, tt), cu.lambda[0]);
-                    int          best = mvp_idx[lidx];
-                    for(int idx = 0; idx < 4; idx++) {
-                        bool dup = false;
-                        for(int t = idx - 1; t >= 0; t--) dup |= cand[idx][0] == cand[t][0] && cand[idx][1] == cand[t][1];
-                        if(dup) continue;
-                        bi.mvp_idx[0] = (uint8_t)idx;
-                        bi.mvd[lidx][0] = (int16_t)(mvx - cand[idx][0]); bi.mvd[lidx][1] = (int16_t)(mvy - cand[idx][1]);
-                        const double c = __dmul_rn((double)cu_count<T>(H, bi, nullptr, ST_IN, tt), cu.lambda[0]);
-                        if(c < ref_cost) best = idx;
-                    }
-                    mvp_idx[lidx] = (uint8_t)best;
-                }
-                if(tt == 0) {
-                    CuMode &M = H.md[lidx];
-                    M.refi[lidx] = (int8_t)refi_t; M.refi[1 - lidx] = -1;
-                    M.mv[lidx][0] = (int16_t)mvx; M.mv[lidx][1] = (int16_t)mvy; M.mv[1 - lidx][0] = M.mv[1 - lidx][1] = 0;
-                    M.mvd[lidx][0] = (int16_t)(mvx - cand[mvp_idx[lidx]][0]); M.mvd[lidx][1] = (int16_t)(mvy - cand[mvp_idx[lidx]][1]);
-                    M.mvd[1 - lidx][0] = M.mvd[1 - lidx][1] = 0;
-                    M.mvp_idx[lidx] = mvp_idx[lidx]; M.mvp_idx[1 - lidx] = 0;
-                }
-                team_sync<T>();
-                const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, lidx, mvp_idx[0], mvp_idx[1], tt);
-                if(lidx == 0) cost_l0 = c; else cost_l1 = c;
-                if(c < cost_best) { cost_best = c; best_idx = lidx; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
-            }
-            if(B) { // ---- analyze_bi: alternate the refined list, start MVs = the uni results, at most BI_ITER = 4 passes ----
-                int      lidx_ref = cost_l0 <= cost_l1 ? 0 : 1, lidx_cnd = 1 - lidx_ref;
-                int8_t   refi[2] = {-1, -1};
-                int8_t   m_refi[2] = {H.md[0].refi[0], H.md[1].refi[1]};
-                int16_t  m_mv[2][2] = {{H.md[0].mv[0][0], H.md[0].mv[0][1]}, {H.md[1].mv[1][0], H.md[1].mv[1][1]}};
-                const uint8_t m_idx[2] = {H.md[0].mvp_idx[0], H.md[1].mvp_idx[1]};
-                uint32_t best_me = 0xffffffffu;
-                int      refi_best = 0;
-                refi[lidx_ref] = m_refi[lidx_ref];
-                for(int iter = 0; iter < 4; iter++) {
-                    cu_predict<L2>(pics, cu, sq, refi[0], refi[1], m_mv[0][0], m_mv[0][1], m_mv[1][0], m_mv[1][1], Tm.pred, Tm.aux,
-                                   reinterpret_cast<int16_t *>(Tm.TB), tt);
-                    for(int e = tt; e < NY; e += T)   // get_org_bi
-                        Tm.org_bi[e] = (int16_t)(((int)Tm.org[0][(ptrdiff_t)(e >> L2) * Tm.so[0] + (e & (N - 1))] << 1) - (int)Tm.pred[e]);
-                    team_sync<T>();
-                    { const int8_t t = refi[lidx_ref]; refi[lidx_ref] = refi[lidx_cnd]; refi[lidx_cnd] = t; }
-                    { const int t = lidx_ref; lidx_ref = lidx_cnd; lidx_cnd = t; }
-                    const int mi = m_idx[lidx_ref];
-                    bool      changed = false;
-                    for(int r = 0; r < num_refp_cur; r++) {
-                        int            mx, my;
-                        const uint32_t mecost = cu_me<L2>(Tm, pics, sq, win_cap, err_flag, lidx_ref, r, num_refp_cur, 1, cu.mvp[lidx_ref][mi][0],
-                                                          cu.mvp[lidx_ref][mi][1], mv_scale[lidx_ref][r][0], mv_scale[lidx_ref][r][1], mot_bits,
-                                                          phase, mx, my, tt);
-                        mv_scale[lidx_ref][r][0] = (int16_t)mx; mv_scale[lidx_ref][r][1] = (int16_t)my;
-                        if(mecost < best_me) {
-                            refi_best = r; best_me = mecost; changed = true;
-                            m_refi[lidx_ref] = (int8_t)r;
-                            m_mv[lidx_ref][0] = (int16_t)mx; m_mv[lidx_ref][1] = (int16_t)my;
-                        }
-                    }
-                    refi[lidx_ref] = (int8_t)refi_best; refi[lidx_cnd] = -1;
-                    if(!changed) break;
-                }
-                if(tt == 0) {
-                    CuMode &M = H.md[2];
-                    for(int l = 0; l < 2; l++) {
-                        M.refi[l] = m_refi[l]; M.mvp_idx[l] = m_idx[l];
-                        M.mv[l][0] = m_mv[l][0]; M.mv[l][1] = m_mv[l][1];
-                        M.mvd[l][0] = (int16_t)(m_mv[l][0] - cu.mvp[l][m_idx[l]][0]); M.mvd[l][1] = (int16_t)(m_mv[l][1] - cu.mvp[l][m_idx[l]][1]);
-                    }
-                }
-                team_sync<T>();
-                const double c = cu_residue_rdo<L2>(Tm, pics, rt, sq, 2, m_idx[0], m_idx[1], tt);
-                if(c < cost_best) { cost_best = c; best_idx = 2; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
-            }
-            cost_win = cost_best;
-        }
-        // ---- winner: coefficients (dropped planes zeroed), reconstruction, XEVE_MODE fields, s_next_best ---------
-        const CuMode &M = H.md[best_idx];
-        int16_t      *gc = coef_out + cu.out_off, *gr = rec_out ? rec_out + cu.out_off : nullptr;
-        if(best_idx == 3) {
-            cu_predict<L2>(pics, cu, sq, M.refi[0], M.refi[1], M.mv[0][0], M.mv[0][1], M.mv[1][0], M.mv[1][1], Tm.pred, Tm.aux,
-                           reinterpret_cast<int16_t *>(Tm.TB), tt);
-            for(int e = tt; e < NP; e += T) {
-                gc[e] = 0;
-                if(gr) gr[e] = Tm.pred[e];
-            }
-        }
-        else {
-            const int16_t *sc = Tm.scratch + (size_t)(3 * best_idx) * NP, *sr = sc + NP, *sp = sr + NP;
-            const int      cbf = M.cbf;
-            for(int e = tt; e < NP; e += T) {
-                const int  c = e < NY ? 0 : (e < NY + NCH ? 1 : 2);
-                const bool on = (cbf >> c) & 1;
-                gc[e] = on ? __ldcg(sc + e) : (int16_t)0;
-                if(gr) gr[e] = on ? __ldcg(sr + e) : __ldcg(sp + e);
-            }
-        }
-        if(tt == 0) {
-            git->cost = cost_win; git->best_idx = (uint8_t)best_idx;
-            for(int l = 0; l < 2; l++) {
-                git->refi[l] = M.refi[l]; git->mvp_idx[l] = M.mvp_idx[l];
-                git->mv[l][0] = M.mv[l][0]; git->mv[l][1] = M.mv[l][1]; git->mvd[l][0] = M.mvd[l][0]; git->mvd[l][1] = M.mvd[l][1];
-            }
-            git->nnz[0] = M.nnz[0]; git->nnz[1] = M.nnz[1]; git->nnz[2] = M.nnz[2];
-        }
-        if(cu.state_out >= 0 && tt < 32) {
-            xb200_sbac &so = st_out[cu.state_out];
-            for(int k = tt; k < XB200_CM_COUNT; k += 32) so.m[k] = H.st[ST_BEST][k];
-            if(tt == 0) so.range = H.rg[ST_BEST];
-        }
-        team_sync<T>();
-    }
+    for(int i = blockIdx.x * Cf::TEAMS + team; i < n; i += gridDim.x * Cf::TEAMS)
+        analyze_cu_one<L2>(Tm, pics, &items[order[i]], rates, st_in, st_out, coef_out, rec_out, nullptr, sq, win_cap, err_flag, phase, tt);
 }

@@ -193,12 +193,12 @@ int launch_residue2_v(xb200_ctx *c, xb200_residue_item *d_items, const int32_t *
                       int16_t *d_coef, int16_t *d_rec, int16_t *d_pred)
 {
     using Cf = Res2Cfg<L2>;
-    static int blocks_per_sm = 0, sms = 0;
     constexpr int smem = USE_TC ? Cf::SMEM : Cf::SMEM_INT;
+    int &blocks_per_sm = c->res2_blocks[L2 - 3][USE_TC ? 1 : 0];   // per context (= per device), not per process
+    const int sms = c->sms;
     if(!blocks_per_sm) {
         CK(cudaFuncSetAttribute(k_residue2<L2, USE_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_residue2<L2, USE_TC>, Cf::CTA, smem));
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         if(blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < sms * blocks_per_sm ? want : sms * blocks_per_sm;
@@ -280,6 +280,7 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
     CK(cudaSetDevice(device));
     xb200_ctx *c = new xb200_ctx();
     c->device = device;
+    c->sms    = prop.multiProcessorCount;
     c->seq    = *seq;
     c->sq.w = seq->w; c->sq.h = seq->h; c->sq.bd = seq->bit_depth;
     c->sq.me_level = seq->me_level; c->sq.hpel_cnt = seq->hpel_cnt; c->sq.qpel_cnt = seq->qpel_cnt;
@@ -308,9 +309,10 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
         const int16_t l[4][8] = XB200_MC_L_TAPS;
         const int16_t ch[8][4] = XB200_MC_C_TAPS;
         const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
-        int64_t       es[6][7];
-        for(int q = 0; q < 6; q++)
-            for(int l2 = 0; l2 < 7; l2++) es[q][l2] = xb200_err_scale(q, l2, seq->bit_depth);
+        static int64_t es[7][6][7];
+        for(int b = 0; b < 7; b++)
+            for(int q = 0; q < 6; q++)
+                for(int l2 = 0; l2 < 7; l2++) es[b][q][l2] = xb200_err_scale(q, l2, b + 8);
         CK(cudaMemcpyToSymbol(c_mc_l, l, sizeof(l)));
         CK(cudaMemcpyToSymbol(c_mc_c, ch, sizeof(ch)));
         CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
@@ -344,6 +346,7 @@ void xb200_destroy(xb200_ctx *c)
 {
     if(!c) return;
     cudaSetDevice(c->device);
+    xb200_chain_free(c);
     cudaStreamSynchronize(c->stream);
     for(auto &p : c->pics)
         for(int k = 0; k < 3; k++)
@@ -411,9 +414,10 @@ int xb200_pic_destroy(xb200_ctx *c, int32_t handle)
     return XB200_OK;
 }
 
-extern "C++" int xb200_pad_planes(xb200_ctx *c, Pic &p)
+extern "C++" int xb200_pad_planes(xb200_ctx *c, Pic &p, cudaStream_t stream)
 {
     if(!p.padded) return XB200_OK;
+    if(!stream) stream = c->stream;
     PadArgs a;
     int     total = 0;
     for(int k = 0; k < 3; k++) {
@@ -423,7 +427,7 @@ extern "C++" int xb200_pad_planes(xb200_ctx *c, Pic &p)
         total += pad_plane_groups(p.w[k], p.h[k], p.pad[k]);
     }
     a.first[3] = total;
-    k_pad3<<<(total + 255) / 256, 256, 0, c->stream>>>(a);
+    k_pad3<<<(total + 255) / 256, 256, 0, stream>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     return XB200_OK;
@@ -723,7 +727,7 @@ int xb200_rdo_bits(xb200_ctx *c, xb200_bits_item *items, int64_t n, xb200_sbac *
     if((r = to_dev(c, c->b_side, coef, (size_t)coef_elems, XB200_MEM_HOST, &d_coef))) return r;
     CK(cudaEventRecord(c->ev0, c->stream));
     const long long blocks = (n + RATE_WARPS - 1) / RATE_WARPS;
-    k_rdo_bits<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), RATE_WARPS * 32, 0, c->stream>>>(d_items, n, d_in, d_out, d_coef);
+    k_rdo_bits<<<(unsigned)(blocks < c->sms * 16 ? blocks : c->sms * 16), RATE_WARPS * 32, 0, c->stream>>>(d_items, n, d_in, d_out, d_coef);
     c->launches++;
     if((r = to_host(c, items, d_items, (size_t)n, XB200_MEM_HOST))) return r;
     if((r = to_host(c, states, d_out, (size_t)n_states, XB200_MEM_HOST))) return r;
@@ -1094,7 +1098,7 @@ template <int L2> int launch_skip(xb200_ctx *c, const xb200_cu_item *d_items, co
     if(cnt == 0) return XB200_OK;
     using Cf = SkipCfg<L2>;
     CK(cudaFuncSetAttribute(k_cu_skip<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM));
-    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < 148 * 8 ? want : 148 * 8;
+    const int want = (cnt + Cf::TEAMS - 1) / Cf::TEAMS, grid = want < c->sms * 8 ? want : c->sms * 8;
     k_cu_skip<L2><<<grid, Cf::CTA, Cf::SMEM, c->side[L2 - 3]>>>(c->d_pics, d_items, order, cnt, d_in, d_state, d_scr, elems, c->sq);
     c->launches++;
     CK(cudaGetLastError());

@@ -1,0 +1,448 @@
+// xb200_chain.cu -- host side of the picture-level decision pass (xb200_analyze_picture and friends, include/xeve_b200.h).
+// Own translation unit with its own (static) copies of the constant tables, like xb200_intra.cu.
+//
+// A call enqueues, on one of the context's picture streams: the persistent decision kernel (k_chain, one CTA per coder-state chain),
+// an optional copy of the unfiltered reconstruction, both loop-filter passes and the border expansion.  Dependencies between
+// pictures are CUDA events on the reference pictures, so the pictures of one wave of the picture DAG run
+// concurrently without the host waiting.  Chains spin on flags of their own picture only; the host admits a picture to the device
+// when all its chains fit next to the ones already there (a CTA that cannot become resident while its siblings spin would dead-lock).
+#define XB200_CONST_LINKAGE static
+#define XB200_CHAIN_TU
+#include "xb200_ctx.h"
+#include "xb200_chain.cuh"
+#include <math.h>
+#include <deque>
+#include <map>
+
+namespace {
+
+constexpr int N_STREAMS = 16;
+
+struct PicMaps {            // frame maps of a decided (or adopted) picture
+    uint32_t *scu = nullptr;
+    int8_t   *ipm = nullptr, *refi = nullptr;
+    int16_t  *mv = nullptr;
+    uint8_t  *flags = nullptr;
+    cudaEvent_t ready = nullptr;   // recorded when the picture is a usable reference
+    bool      has_ready = false;
+};
+struct JobBufs {            // outputs and working set of one picture in flight (recycled)
+    xb200_scu_rec *scu = nullptr;
+    int16_t       *coef = nullptr;
+    ChState       *ctu_state = nullptr;
+    double        *ctu_cost = nullptr;
+    int           *done = nullptr;
+    unsigned long long *counts = nullptr;
+    ChainWs       *ws = nullptr;
+    int            ws_chains = 0;
+    xb200_cu_item    *cu_log = nullptr;
+    xb200_intra_item *intra_log = nullptr;
+    long long      cu_cap = 0, intra_cap = 0;
+    cudaEvent_t    ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+struct Job {
+    JobBufs b;
+    int     rec_pic = -1;
+    double  share = 0.0;    // SM share its chains occupy: n_chain / resident CTAs per SM
+    bool    retired = false;
+};
+struct ChainCtx {
+    cudaStream_t streams[N_STREAMS] = {};
+    cudaStream_t copy = nullptr;
+    int          next_stream = 0;
+    std::vector<PicMaps> maps;
+    std::map<int, Job *> jobs;          // by rec_pic
+    std::deque<Job *>    inflight;      // admission order
+    std::vector<JobBufs> pool;
+    double       load = 0.0;            // sum of the shares of the admitted, unretired pictures
+    int16_t     *zero_mv = nullptr;     // colocated map of a reference picture without one (all zero)
+    long long    log_cu = 0, log_intra = 0;
+    bool         ready = false;
+    int          n_lcu = 0, w_lcu = 0, h_lcu = 0, w_scu = 0, h_scu = 0;
+    size_t       f_scu = 0;
+};
+
+ChainCtx *cc_of(xb200_ctx *c) { return static_cast<ChainCtx *>(c->chain); }
+
+int chain_init(xb200_ctx *c)
+{
+    if(c->chain && cc_of(c)->ready) return XB200_OK;
+    ChainCtx *k = c->chain ? cc_of(c) : new ChainCtx();
+    c->chain = k;
+    k->w_lcu = (c->seq.w + 63) >> 6; k->h_lcu = (c->seq.h + 63) >> 6; k->n_lcu = k->w_lcu * k->h_lcu;
+    k->w_scu = (c->seq.w + 3) >> 2; k->h_scu = (c->seq.h + 3) >> 2; k->f_scu = (size_t)k->w_scu * k->h_scu;
+    for(int i = 0; i < N_STREAMS; i++) CK(cudaStreamCreateWithFlags(&k->streams[i], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&k->copy, cudaStreamNonBlocking));
+    {   // constant tables of this translation unit
+        static int8_t tm[64 * 64];
+        xb200_gen_tm64(tm);
+        const int16_t l[4][8] = XB200_MC_L_TAPS;
+        const int16_t ch[8][4] = XB200_MC_C_TAPS;
+        const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
+        static int64_t es[7][6][7];
+        for(int b = 0; b < 7; b++)
+            for(int q = 0; q < 6; q++)
+                for(int l2 = 0; l2 < 7; l2++) es[b][q][l2] = xb200_err_scale(q, l2, b + 8);
+        static const uint8_t mpm[6][6][5] = XB200_MPM_TABLE;
+        static uint16_t scan[16 + 64 + 256 + 1024 + 4096];
+        static int32_t  eb[1024];
+        int             off = 0;
+        for(int l2 = 2; l2 <= 6; l2++) { xb200_gen_scan(scan + off, l2, l2); off += 1 << (2 * l2); }
+        for(int i = 0; i < 1024; i++) {     // xeve_init_bits_est (src_base/xeve_mode.c:304-313), host libm
+            const double p = (512 * (i + 0.5)) / 1024;
+            eb[i] = (int32_t)(-32768 * (log(p) / log(2.0) - 9));
+        }
+        CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
+        CK(cudaMemcpyToSymbol(c_mc_l, l, sizeof(l)));
+        CK(cudaMemcpyToSymbol(c_mc_c, ch, sizeof(ch)));
+        CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
+        CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
+        CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+        CK(cudaMemcpyToSymbol(c_mpm_tbl, mpm, sizeof(mpm)));
+        CK(cudaMemcpyToSymbol(g_scan, scan, sizeof(scan)));
+        CK(cudaMemcpyToSymbol(g_entropy_bits, eb, sizeof(eb)));
+    }
+    CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
+    CK(cudaMemset(k->zero_mv, 0, k->f_scu * 8));
+    if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
+    CK(cudaDeviceSynchronize());
+    k->ready = true;
+    return XB200_OK;
+}
+
+int maps_of(xb200_ctx *c, int pic, PicMaps **out)
+{
+    ChainCtx *k = cc_of(c);
+    if((int)k->maps.size() <= pic) k->maps.resize(pic + 1);
+    PicMaps &m = k->maps[pic];
+    if(!m.scu) {
+        const size_t f = k->f_scu;
+        CK(cudaMalloc(&m.scu, f * 4)); CK(cudaMalloc(&m.ipm, f)); CK(cudaMalloc(&m.refi, f * 2)); CK(cudaMalloc(&m.mv, f * 8));
+        CK(cudaMalloc(&m.flags, f));
+        CK(cudaEventCreateWithFlags(&m.ready, cudaEventDisableTiming));
+    }
+    *out = &m;
+    return XB200_OK;
+}
+
+int bufs_get(xb200_ctx *c, int n_chain, JobBufs *out)
+{
+    ChainCtx *k = cc_of(c);
+    JobBufs   b;
+    if(!k->pool.empty()) { b = k->pool.back(); k->pool.pop_back(); }
+    const size_t n = (size_t)k->n_lcu;
+    if(!b.scu) {
+        CK(cudaMalloc(&b.scu, n * 256 * sizeof(xb200_scu_rec)));
+        CK(cudaMalloc(&b.coef, n * 6144 * sizeof(int16_t)));
+        CK(cudaMalloc(&b.ctu_state, n * 2 * sizeof(ChState)));
+        CK(cudaMalloc(&b.ctu_cost, n * sizeof(double)));
+        CK(cudaMalloc(&b.done, n * sizeof(int)));
+        CK(cudaMalloc(&b.counts, 2 * sizeof(unsigned long long)));
+        CK(cudaEventCreate(&b.ev0)); CK(cudaEventCreate(&b.ev1)); CK(cudaEventCreate(&b.ev2));
+    }
+    if(b.ws_chains < n_chain) {
+        if(b.ws) cudaFree(b.ws);
+        CK(cudaMalloc(&b.ws, (size_t)n_chain * sizeof(ChainWs)));
+        b.ws_chains = n_chain;
+    }
+    if(b.cu_cap < k->log_cu) {
+        if(b.cu_log) cudaFree(b.cu_log);
+        CK(cudaMalloc(&b.cu_log, (size_t)k->log_cu * sizeof(xb200_cu_item)));
+        b.cu_cap = k->log_cu;
+    }
+    if(b.intra_cap < k->log_intra) {
+        if(b.intra_log) cudaFree(b.intra_log);
+        CK(cudaMalloc(&b.intra_log, (size_t)k->log_intra * sizeof(xb200_intra_item)));
+        b.intra_cap = k->log_intra;
+    }
+    *out = b;
+    return XB200_OK;
+}
+void bufs_free(JobBufs &b)
+{
+    for(void *p : {(void *)b.scu, (void *)b.coef, (void *)b.ctu_state, (void *)b.ctu_cost, (void *)b.done, (void *)b.counts, (void *)b.ws,
+                   (void *)b.cu_log, (void *)b.intra_log})
+        if(p) cudaFree(p);
+    if(b.ev0) { cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev1); cudaEventDestroy(b.ev2); }
+    b = JobBufs();
+}
+
+// retire finished pictures; with `need` > 0 wait (oldest first) until that much SM share is free
+int admit(xb200_ctx *c, double need)
+{
+    ChainCtx *k = cc_of(c);
+    for(;;) {
+        while(!k->inflight.empty()) {
+            Job *j = k->inflight.front();
+            if(!j->retired) {
+                const cudaError_t e = cudaEventQuery(j->b.ev1);
+                if(e == cudaErrorNotReady) break;
+                if(e != cudaSuccess) CK(e);
+                j->retired = true;
+                k->load -= j->share;
+            }
+            k->inflight.pop_front();
+        }
+        if(k->inflight.empty()) k->load = 0.0;
+        if(need <= 0 || k->load + need <= (double)c->sms + 1e-9 || k->inflight.empty()) return XB200_OK;
+        CK(cudaEventSynchronize(k->inflight.front()->b.ev1));
+    }
+}
+
+template <int MB> int launch_chain(xb200_ctx *c, const ChainPic &P, size_t smem, cudaStream_t s)
+{
+    CK(cudaFuncSetAttribute(k_chain<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain<MB><<<P.n_chain, CH_T, smem, s>>>(c->d_pics, P, c->d_tm64, c->sq, c->d_err);
+    c->launches++;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
+} // namespace
+
+void xb200_chain_free(xb200_ctx *c)
+{
+    if(!c || !c->chain) return;
+    ChainCtx *k = cc_of(c);
+    cudaDeviceSynchronize();
+    for(auto &kv : k->jobs) { bufs_free(kv.second->b); delete kv.second; }
+    for(auto &b : k->pool) bufs_free(b);
+    for(auto &m : k->maps) {
+        for(void *p : {(void *)m.scu, (void *)m.ipm, (void *)m.refi, (void *)m.mv, (void *)m.flags})
+            if(p) cudaFree(p);
+        if(m.ready) cudaEventDestroy(m.ready);
+    }
+    if(k->zero_mv) cudaFree(k->zero_mv);
+    for(int i = 0; i < N_STREAMS; i++)
+        if(k->streams[i]) cudaStreamDestroy(k->streams[i]);
+    if(k->copy) cudaStreamDestroy(k->copy);
+    delete k;
+    c->chain = nullptr;
+}
+
+extern "C" {
+
+int xb200_chain_capacity(xb200_ctx *c)
+{
+    if(!c) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    int r = chain_init(c);
+    if(r) return r;
+    int32_t cap[4];
+    for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * 10 + 7; cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
+    const size_t smem = chain_smem_bytes(cap);
+    int bps = 0;
+    CK(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<1>, CH_T, smem));
+    return c->sms * (bps < 1 ? 1 : bps);
+}
+
+int xb200_picture_log_enable(xb200_ctx *c, int64_t cap_cu, int64_t cap_intra)
+{
+    if(!c || cap_cu < 0 || cap_intra < 0 || cap_cu > (1 << 24) || cap_intra > (1 << 24)) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    int r = chain_init(c);
+    if(r) return r;
+    cc_of(c)->log_cu = cap_cu; cc_of(c)->log_intra = cap_intra;
+    return XB200_OK;
+}
+
+int xb200_picture_adopt(xb200_ctx *c, int32_t pic, const int16_t *map_mv)
+{
+    if(!c || !pic_ok(c, pic) || !c->pics[pic].padded || !map_mv) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    int r = chain_init(c);
+    if(r) return r;
+    PicMaps *m;
+    if((r = maps_of(c, pic, &m))) return r;
+    CK(cudaMemcpy(m->mv, map_mv, cc_of(c)->f_scu * 8, cudaMemcpyHostToDevice));
+    m->has_ready = false;   // nothing in flight writes it
+    return XB200_OK;
+}
+
+int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
+{
+    if(!c || !pp) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    int r = chain_init(c);
+    if(r) return r;
+    ChainCtx *k = cc_of(c);
+    // ---- arguments ----
+    if(pp->slice_type == 1) return XB200_ERR_UNSUPPORTED;   // P slices: the next CTU starts from the bitstream coder's state, not the RDO's
+    if(pp->slice_type != 0 && pp->slice_type != 2) return XB200_ERR_INVALID_ARGUMENT;
+    if(!pic_ok(c, pp->cur_pic) || !pic_ok(c, pp->rec_pic) || !c->pics[pp->rec_pic].padded || pp->rec_pic == pp->cur_pic)
+        return XB200_ERR_INVALID_ARGUMENT;
+    if(pp->unfiltered_pic >= 0 && (!pic_ok(c, pp->unfiltered_pic) || !c->pics[pp->unfiltered_pic].padded || pp->unfiltered_pic == pp->rec_pic))
+        return XB200_ERR_INVALID_ARGUMENT;
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if(!pow2(pp->max_cu_inter) || !pow2(pp->min_cu_inter) || !pow2(pp->max_cu_intra) || !pow2(pp->min_cu_intra)) return XB200_ERR_INVALID_ARGUMENT;
+    if(pp->max_cu_inter > 64 || pp->min_cu_inter < 8 || pp->max_cu_intra > 64 || pp->min_cu_intra < 4 || pp->min_cu_inter > pp->max_cu_inter ||
+       pp->min_cu_intra > pp->max_cu_intra)
+        return XB200_ERR_UNSUPPORTED;
+    if(pp->tile_qp < 0 || pp->tile_qp > 63 || pp->parallel_rows < 0 || pp->max_search_range < 1 || pp->max_search_range > 256 ||
+       c->seq.merge_num < 1 || c->seq.merge_num > 4 || c->seq.gop_size < 1 || (c->seq.me_complexity > 1))
+        return c->seq.me_complexity > 1 ? XB200_ERR_UNSUPPORTED : XB200_ERR_INVALID_ARGUMENT;
+    for(int i = 0; i < 3; i++)
+        if(pp->qp[i] < 0 || pp->qp[i] > 100) return XB200_ERR_INVALID_ARGUMENT;
+    int margin = 6;   // bi search: window radius 5, +1 for the integer refinement pass
+    if(pp->slice_type == 0) {
+        for(int l = 0; l < 2; l++) {
+            if(pp->num_refp[l] < 1 || pp->num_refp[l] > XB200_MAX_REFP) return XB200_ERR_UNSUPPORTED;
+            for(int q = 0; q < pp->num_refp[l]; q++) {
+                const int h = pp->ref_pic[l][q];
+                if(!pic_ok(c, h) || !c->pics[h].padded || h == pp->rec_pic) return XB200_ERR_INVALID_ARGUMENT;
+                int d = pp->poc - pp->ref_poc[l][q];
+                d = d < 0 ? -d : d;
+                int dyn = (pp->max_search_range * d + (c->seq.gop_size >> 1)) / c->seq.gop_size;
+                dyn = dyn < (pp->max_search_range >> 2) ? (pp->max_search_range >> 2) : (dyn > pp->max_search_range ? pp->max_search_range : dyn);
+                if(dyn + 2 > margin) margin = dyn + 2;
+            }
+        }
+    }
+    if(k->jobs.count(pp->rec_pic)) return XB200_ERR_INVALID_ARGUMENT;   // fetch the previous result of this handle first
+    if((r = xb200_sync_pics(c))) return r;
+
+    ChainPic P;
+    memset(&P, 0, sizeof(P));
+    P.pp = *pp;
+    P.w = c->seq.w; P.h = c->seq.h; P.w_scu = k->w_scu; P.h_scu = k->h_scu; P.w_lcu = k->w_lcu; P.h_lcu = k->h_lcu;
+    P.pp.df.w_scu = k->w_scu; P.pp.df.h_scu = k->h_scu;
+    P.n_chain = pp->parallel_rows > 1 ? (pp->parallel_rows > k->h_lcu ? k->h_lcu : pp->parallel_rows) : 1;
+    for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * margin + 7; P.win_cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
+    const size_t smem = chain_smem_bytes(P.win_cap);
+    if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
+    {
+        const Pic &p = c->pics[pp->rec_pic];
+        for(int q = 0; q < 3; q++) { P.rec.p[q] = p.buf[q] + (size_t)p.pad[q] * p.s[q] + p.pad[q]; P.rec.s[q] = p.s[q]; }
+        P.rec.w = p.w[0]; P.rec.h = p.h[0]; P.rec.pad_l = p.pad[0]; P.rec.pad_c = p.pad[1]; P.rec.valid = 1;
+    }
+    PicMaps *m;
+    if((r = maps_of(c, pp->rec_pic, &m))) return r;
+    P.map_scu = m->scu; P.map_ipm = m->ipm; P.map_refi = m->refi; P.map_mv = m->mv; P.df_flags = m->flags;
+    P.col0 = P.col1 = k->zero_mv;
+    cudaStream_t s = k->streams[k->next_stream];
+    k->next_stream = (k->next_stream + 1) % N_STREAMS;
+    if(pp->slice_type == 0) {
+        for(int l = 0; l < 2; l++)
+            for(int q = 0; q < pp->num_refp[l]; q++) {
+                const int h = pp->ref_pic[l][q];
+                if(h < (int)k->maps.size() && k->maps[h].mv) {
+                    if(q == 0) (l ? P.col1 : P.col0) = k->maps[h].mv;
+                    if(k->maps[h].has_ready) CK(cudaStreamWaitEvent(s, k->maps[h].ready, 0));
+                }
+                else if(q == 0) return XB200_ERR_INVALID_ARGUMENT;   // a reference picture needs its motion map (decided here or adopted)
+            }
+    }
+    if(m->has_ready) CK(cudaStreamWaitEvent(s, m->ready, 0));   // an earlier life of this handle
+    int bps = 0;
+    CK(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<1>, CH_T, smem));
+    if(bps < 1) return XB200_ERR_UNSUPPORTED;
+    const double share = (double)P.n_chain / bps;
+    if(share > c->sms) return XB200_ERR_UNSUPPORTED;
+    if((r = admit(c, share))) return r;
+
+    Job *j = new Job();
+    if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
+    j->rec_pic = pp->rec_pic; j->share = share;
+    P.scu_out = j->b.scu; P.coef_out = j->b.coef; P.ctu_state = j->b.ctu_state; P.ctu_cost = j->b.ctu_cost; P.done = j->b.done;
+    P.counts = j->b.counts; P.ws = j->b.ws;
+    if(k->log_cu > 0) { P.cu_log = j->b.cu_log; P.cu_cap = k->log_cu; }
+    if(k->log_intra > 0) { P.intra_log = j->b.intra_log; P.intra_cap = k->log_intra; }
+    const size_t f = k->f_scu;
+    CK(cudaMemsetAsync(m->scu, 0, f * 4, s)); CK(cudaMemsetAsync(m->ipm, 0, f, s)); CK(cudaMemsetAsync(m->refi, 0, f * 2, s));
+    CK(cudaMemsetAsync(m->mv, 0, f * 8, s)); CK(cudaMemsetAsync(m->flags, 0, f, s));
+    CK(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
+    CK(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
+    CK(cudaEventRecord(j->b.ev0, s));
+    if((r = launch_chain<1>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
+    CK(cudaEventRecord(j->b.ev1, s));
+    Pic &rp = c->pics[pp->rec_pic];
+    if(pp->unfiltered_pic >= 0) {
+        Pic &up = c->pics[pp->unfiltered_pic];
+        for(int q = 0; q < 3; q++)
+            CK(cudaMemcpy2DAsync(up.buf[q] + (size_t)up.pad[q] * up.s[q] + up.pad[q], (size_t)up.s[q] * 2,
+                                 rp.buf[q] + (size_t)rp.pad[q] * rp.s[q] + rp.pad[q], (size_t)rp.s[q] * 2, (size_t)rp.w[q] * 2, rp.h[q],
+                                 cudaMemcpyDeviceToDevice, s));
+    }
+    if(pp->deblock && (r = xb200_deblock_dev(c, rp, &P.pp.df, m->scu, m->refi, m->mv, m->flags, s))) return r;
+    if((r = xb200_pad_planes(c, rp, s))) return r;
+    CK(cudaEventRecord(j->b.ev2, s));
+    CK(cudaEventRecord(m->ready, s));
+    m->has_ready = true;
+    k->jobs[pp->rec_pic] = j;
+    k->inflight.push_back(j);
+    k->load += share;
+    return XB200_OK;
+}
+
+int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16_t *coef, xb200_state *ctu_states, double *ctu_cost,
+                        xb200_picture_stat *stat)
+{
+    if(!c || !c->chain) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    ChainCtx *k = cc_of(c);
+    auto it = k->jobs.find(rec_pic);
+    if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
+    Job *j = it->second;
+    CK(cudaEventSynchronize(j->b.ev2));
+    const size_t n = (size_t)k->n_lcu;
+    if(scu) CK(cudaMemcpyAsync(scu, j->b.scu, n * 256 * sizeof(xb200_scu_rec), cudaMemcpyDeviceToHost, k->copy));
+    if(coef) CK(cudaMemcpyAsync(coef, j->b.coef, n * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, k->copy));
+    if(ctu_states) CK(cudaMemcpyAsync(ctu_states, j->b.ctu_state, n * 2 * sizeof(ChState), cudaMemcpyDeviceToHost, k->copy));
+    if(ctu_cost) CK(cudaMemcpyAsync(ctu_cost, j->b.ctu_cost, n * sizeof(double), cudaMemcpyDeviceToHost, k->copy));
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(cnt, j->b.counts, sizeof(cnt), cudaMemcpyDeviceToHost, k->copy));
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, k->copy));
+    CK(cudaStreamSynchronize(k->copy));
+    if(stat) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, j->b.ev0, j->b.ev1);
+        cudaEventElapsedTime(&b, j->b.ev1, j->b.ev2);
+        stat->n_inter = (int64_t)cnt[0]; stat->n_intra = (int64_t)cnt[1]; stat->chain_ms = a; stat->filter_ms = b;
+    }
+    if(!j->retired) { j->retired = true; k->load -= j->share; }
+    for(auto q = k->inflight.begin(); q != k->inflight.end(); ++q)
+        if(*q == j) { k->inflight.erase(q); break; }
+    k->pool.push_back(j->b);
+    k->jobs.erase(it);
+    delete j;
+    if(err) { fprintf(stderr, "xeve_b200: search window overflow inside the decision pass\n"); return XB200_ERR_UNEXPECTED; }
+    return XB200_OK;
+}
+
+int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_intra_item *intra, int64_t n[2])
+{
+    if(!c || !c->chain || !n) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    ChainCtx *k = cc_of(c);
+    auto it = k->jobs.find(rec_pic);
+    if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
+    Job *j = it->second;
+    CK(cudaEventSynchronize(j->b.ev2));
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpy(cnt, j->b.counts, sizeof(cnt), cudaMemcpyDeviceToHost));
+    n[0] = (int64_t)cnt[0] < k->log_cu ? (int64_t)cnt[0] : k->log_cu;
+    n[1] = (int64_t)cnt[1] < k->log_intra ? (int64_t)cnt[1] : k->log_intra;
+    if(cu && n[0]) CK(cudaMemcpy(cu, j->b.cu_log, (size_t)n[0] * sizeof(xb200_cu_item), cudaMemcpyDeviceToHost));
+    if(intra && n[1]) CK(cudaMemcpy(intra, j->b.intra_log, (size_t)n[1] * sizeof(xb200_intra_item), cudaMemcpyDeviceToHost));
+    return XB200_OK;
+}
+
+int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv)
+{
+    if(!c || !c->chain || rec_pic < 0 || rec_pic >= (int)cc_of(c)->maps.size() || !cc_of(c)->maps[rec_pic].scu) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    ChainCtx *k = cc_of(c);
+    PicMaps  &m = k->maps[rec_pic];
+    if(m.has_ready) CK(cudaEventSynchronize(m.ready));
+    const size_t f = k->f_scu;
+    if(map_scu) CK(cudaMemcpy(map_scu, m.scu, f * 4, cudaMemcpyDeviceToHost));
+    if(map_ipm) CK(cudaMemcpy(map_ipm, m.ipm, f, cudaMemcpyDeviceToHost));
+    if(map_refi) CK(cudaMemcpy(map_refi, m.refi, f * 2, cudaMemcpyDeviceToHost));
+    if(map_mv) CK(cudaMemcpy(map_mv, m.mv, f * 8, cudaMemcpyDeviceToHost));
+    return XB200_OK;
+}
+
+} // extern "C"

@@ -37,7 +37,8 @@ XB200_CONST_LINKAGE __constant__ int16_t c_mc_l[4][8];              // luma taps
 XB200_CONST_LINKAGE __constant__ int16_t c_mc_c[8][4];              // chroma taps by eighth-pel phase
 XB200_CONST_LINKAGE __constant__ int32_t c_quant_scale[6];
 XB200_CONST_LINKAGE __constant__ int32_t c_dequant_scale[6];
-XB200_CONST_LINKAGE __constant__ int64_t c_err_scale[6][7];         // [qp % 6][log2 size] (host-computed doubles -> s64)
+XB200_CONST_LINKAGE __constant__ int64_t c_err_scale[7][6][7];      // [bit depth - 8][qp % 6][log2 size] (host-computed doubles -> s64): every
+                                                                    // context finds its own depth, whatever other contexts of the process use
 #endif
 
 #define XB_DEV __device__ __forceinline__
@@ -46,6 +47,15 @@ XB_DEV int clip3i(int lo, int hi, int v) { return max(lo, min(hi, v)); }
 #ifndef XB200_NO_CONSTANTS
 XB_DEV int tmN(int log2n, int k, int n) { return c_tm64[(k << (6 - log2n)) * 64 + n]; }
 #endif
+
+// Barrier of a TEAM of T threads (the first T threads of the CTA, or a whole warp): a named barrier, so that a team narrower than its
+// CTA (the decision-chain kernel runs CUs of every size on one CTA) never waits for the idle threads.  With T == blockDim.x it is
+// equivalent to __syncthreads().
+template <int T> XB_DEV void team_bar()
+{
+    if(T == 32) __syncwarp();
+    else asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+}
 
 XB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

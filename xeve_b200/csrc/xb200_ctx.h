@@ -46,6 +46,9 @@ struct xb200_ctx {
     cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
     cudaStream_t     side[4] = {nullptr, nullptr, nullptr, nullptr}; // one per CU size: the four size-binned grids overlap
     cudaEvent_t      ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    int              sms = 148;          // cudaDevAttrMultiProcessorCount of `device`
+    int              res2_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}}; // resident CTAs per SM of k_residue2<L2, TC> on this device
+    void            *chain = nullptr;    // decision-pass state (xb200_chain.cu)
     double           last_ms = 0.0;
     int64_t          launches = 0;
 };
@@ -62,7 +65,11 @@ struct xb200_ctx {
 // defined in xb200_api.cu
 int  xb200_ensure(DevBuf &b, size_t bytes);
 int  xb200_finish(xb200_ctx *c);          // record ev1, synchronise, store the kernel time of [ev0, ev1]
-int  xb200_pad_planes(xb200_ctx *c, Pic &p);
+int  xb200_pad_planes(xb200_ctx *c, Pic &p, cudaStream_t stream = nullptr); // border replication; default: the context's stream
+// both loop-filter passes of picture p on `stream` from device-resident maps and edge flags (xb200_frame.cu)
+int  xb200_deblock_dev(xb200_ctx *c, Pic &p, const xb200_df_pic *pp, const uint32_t *d_scu, const int8_t *d_refi, const int16_t *d_mv,
+                       const uint8_t *d_flags, cudaStream_t stream);
+void xb200_chain_free(xb200_ctx *c);      // releases the decision-pass state of a context (xb200_chain.cu)
 int  xb200_sync_pics(xb200_ctx *c);       // refresh the device-side picture table (c->d_pics)
 
 inline int  align_up(int v, int a) { return (v + a - 1) / a * a; }

@@ -7,6 +7,21 @@
 #define finish xb200_finish
 #define ensure xb200_ensure
 
+int xb200_deblock_dev(xb200_ctx *c, Pic &p, const xb200_df_pic *pp, const uint32_t *d_scu, const int8_t *d_refi, const int16_t *d_mv,
+                      const uint8_t *d_flags, cudaStream_t stream)
+{
+    DfArgs a;
+    for(int k = 0; k < 3; k++) { a.pl[k] = p.buf[k] + (size_t)p.pad[k] * p.s[k] + p.pad[k]; a.s[k] = p.s[k]; }
+    a.w_scu = pp->w_scu; a.h_scu = pp->h_scu; a.bd = c->seq.bit_depth;
+    a.scu = d_scu; a.refi = d_refi; a.mv = d_mv; a.flags = d_flags; a.pp = *pp;
+    const dim3 grid((pp->w_scu + 31) / 32, (pp->h_scu + 7) / 8);
+    k_df_pass<false><<<grid, 256, 0, stream>>>(a);
+    k_df_pass<true><<<grid, 256, 0, stream>>>(a);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return XB200_OK;
+}
+
 // ---- in-loop deblocking --------------------------------------------------------------------------------------
 int xb200_deblock(xb200_ctx *c, int32_t pic, const xb200_df_cu *cus, int64_t n, const xb200_df_pic *pp, const uint32_t *map_scu,
                   const int8_t *map_refi, const int16_t *map_mv, int expand, int mem)

@@ -56,7 +56,7 @@ int launch_intra(xb200_ctx *c, xb200_intra_item *d_items, const int32_t *d_order
     if(cnt == 0) return XB200_OK;
     using Cf = IntraCfg<L2>;
     const int teams_needed = (cnt + Cf::TEAMS - 1) / Cf::TEAMS;
-    const int resident = L2 <= 4 ? 148 * 8 : (L2 == 5 ? 148 * 2 : 148 * 2);   // persistent CTAs: a few per SM
+    const int resident = L2 <= 4 ? c->sms * 8 : c->sms * 2;   // persistent CTAs: a few per SM
     const int grid = teams_needed < resident ? teams_needed : resident;
     k_intra<L2><<<grid, Cf::CTA, intra_smem<L2>(), c->side[L2 <= 3 ? 0 : L2 - 3]>>>(c->d_pics, d_items, d_order, cnt, d_rates, d_st0,
                                                                                                      d_st1, d_side, d_coef, d_rec, c->d_tm64, c->sq);
@@ -69,9 +69,10 @@ int intra_init(xb200_ctx *c)
 {
     if(c->intra_ready) return XB200_OK;
     const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
-    int64_t       es[6][7];
-    for(int q = 0; q < 6; q++)
-        for(int l2 = 0; l2 < 7; l2++) es[q][l2] = xb200_err_scale(q, l2, c->seq.bit_depth);
+    static int64_t es[7][6][7];
+    for(int b = 0; b < 7; b++)
+        for(int q = 0; q < 6; q++)
+            for(int l2 = 0; l2 < 7; l2++) es[b][q][l2] = xb200_err_scale(q, l2, b + 8);
     static int8_t tm[64 * 64];
     xb200_gen_tm64(tm);
     CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));

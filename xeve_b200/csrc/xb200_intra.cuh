@@ -167,6 +167,261 @@ template <int L2> struct IntraTeam {
     TeamScratch X;
 };
 
+// pintra_analyze_cu of ONE CU by one team (one warp up to 32x32, the first 128 threads of the CTA for 64x64)
+template <int L2>
+__device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, const int8_t *tmT, const PicDev *__restrict__ pics,
+                                          xb200_intra_item &it, const xb200_rates *rates, const xb200_sbac *st_in, xb200_sbac *st_out,
+                                          const int16_t *side, int16_t *coef, int16_t *rec, const SeqDev &sq, int tt)
+{
+    using Cf = IntraCfg<L2>;
+    constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NC = N / 2, NCH = Cf::NCH, TILES = Cf::TILES, LC = L2 - 1;
+    const int lane = tt & 31;
+    const int bd = sq.bd, maxv = (1 << bd) - 1, sh = (bd - 8) << 1;
+    const int slice_type = it.slice_type, all_preds = it.all_preds, ctx_skip = it.ctx_skip, ctx_pm = it.ctx_pred_mode;
+    const xb200_rates *rt = &rates[it.rate_idx];
+    const double lambda0 = it.lambda[0];
+    uint32_t range_base;
+    uint8_t  mpm[5];
+    // ---- stage inputs: original block, reference samples, coder state ------------------------------------------
+    {
+        const PicDev   p = pics[it.cur_pic];
+        const int      x0 = it.x, y0 = it.y;
+        const int16_t *gy = p.p[0] + (ptrdiff_t)y0 * p.s[0] + x0;
+        for(int e = tt; e < NY; e += T) M.org[e] = gy[(ptrdiff_t)(e >> L2) * p.s[0] + (e & (N - 1))];
+#pragma unroll
+        for(int c = 1; c < 3; c++) {
+            const int16_t *gc = p.p[c] + (ptrdiff_t)(y0 >> 1) * p.s[c] + (x0 >> 1);
+            for(int e = tt; e < NCH; e += T) M.org[NY + (c - 1) * NCH + e] = gc[(ptrdiff_t)(e >> LC) * p.s[c] + (e & (NC - 1))];
+        }
+        const int16_t *gn = side + it.nb_off;
+        for(int e = tt; e < 8 * N + 6; e += T) M.nb[e] = gn[e];
+        const xb200_sbac &s0 = st_in[it.state_in];
+        for(int k = tt; k < XB200_CM_COUNT; k += T) M.cm_base[k] = s0.m[k];
+        if(tt == 0) { M.cm_base[IN_CM_IPM] = it.cm_ipm_in[0]; M.cm_base[IN_CM_IPM + 1] = it.cm_ipm_in[1]; }
+        range_base = s0.range;
+#pragma unroll
+        for(int k = 0; k < 5; k++) mpm[k] = it.mpm[k];
+    }
+    team_sync<T>();
+    const int16_t *leY = M.nb + 1, *upY = M.nb + (2 * N + 1) + 1;
+    const int16_t *leC[2] = {M.nb + 2 * (2 * N + 1) + 1, M.nb + 2 * (2 * N + 1) + 2 * (N + 1) + 1};
+    const int16_t *upC[2] = {leC[0] + (N + 1), leC[1] + (N + 1)};
+    const int dcY = ipred_dc(leY, upY, L2);
+
+    // ---- make_ipred_list (src_base/xeve_pintra.c:308-374): SATD of the five modes, one (mode, tile) pair per thread ----
+    for(int w = tt; w < 5 * TILES; w += T) {
+        const int ipm = w / TILES, t = w % TILES;
+        if(L2 == 2) M.satd_part[w] = had_tile_fn<4>(M.org, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, y, x, dcY); });
+        else {
+            constexpr int TW = N >= 8 ? N / 8 : 1;
+            const int ty = (t / TW) * 8, tx = (t % TW) * 8;
+            M.satd_part[w] = had_tile_fn<8>(M.org + ty * N + tx, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, ty + y, tx + x, dcY); });
+        }
+    }
+    team_sync<T>();
+    if(tt == 0) {
+        double   cand_cost[5];
+        uint32_t cand_satd[5];
+        int      list[5];
+#pragma unroll
+        for(int k = 0; k < 5; k++) { list[k] = 0; cand_cost[k] = IN_MAX_COST; cand_satd[k] = 0xffffffffu; }
+        for(int ipm = 0; ipm < 5; ipm++) {
+            int sum = 0;
+            for(int t = 0; t < TILES; t++) sum += M.satd_part[ipm * TILES + t];
+            const uint32_t satd = (uint32_t)(sum >> (bd - 8));
+            Cabac c;
+            c.range = range_base; c.bits = 0; c.m = M.cm_run;
+            M.cm_run[IN_CM_IPM] = M.cm_base[IN_CM_IPM]; M.cm_run[IN_CM_IPM + 1] = M.cm_base[IN_CM_IPM + 1];
+            cb_unary(c, mpm[ipm], IN_CM_IPM);
+            const double cost = __dadd_rn((double)satd, __dmul_rn((double)c.bits, it.sqrt_lambda0));
+            int shift = 0;
+            while(shift < 5 && cost < cand_cost[4 - shift]) shift++;
+            if(shift) {
+                for(int j = 1; j < shift; j++) { list[5 - j] = list[4 - j]; cand_cost[5 - j] = cand_cost[4 - j]; cand_satd[5 - j] = cand_satd[4 - j]; }
+                list[5 - shift] = ipm; cand_cost[5 - shift] = cost; cand_satd[5 - shift] = satd;
+            }
+        }
+        int          pc = 5;
+        const double thr = __dmul_rn((double)it.inter_satd, 1.2);
+        for(int i = 4; i >= 1; i--) {
+            if((double)cand_satd[i] > thr) pc--;
+            else break;
+        }
+#pragma unroll
+        for(int k = 0; k < 5; k++) M.list[k] = list[k];
+        M.pred_cnt = pc;
+    }
+    team_sync<T>();
+    const int pred_cnt = M.pred_cnt;
+
+    // ---- luma RDO per surviving mode (pintra_residue_rdo mode 0, src_base/xeve_pintra.c:97-152) ---------------------
+    // pass 1 (team): transform, RDOQ, reconstruction and SSD of every surviving mode; levels kept in zig-zag order
+    int16_t *g_coef = coef + it.out_off, *g_rec = rec ? rec + it.out_off : nullptr;
+    for(int j = 0; j < pred_cnt; j++) {
+        const int ipm = M.list[j];
+        for(int e = tt; e < NY; e += T) M.blk[e] = (int16_t)(M.org[e] - ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY));
+        team_sync<T>();
+        fwd_dct_t<L2, T>(M.blk, M.TB, tm, tmT, bd, tt);
+        const int nnz = quant_team<L2, T, true>(M.blk, M.TB, it.qp[0], lambda0, 0, slice_type, rt, bd, sq.rdoq, tt, M.X);
+        for(int e = tt; e < NY; e += T) M.candS[j][zz_of(e, L2)] = M.blk[e];
+        if(nnz) {
+            team_sync<T>();
+            dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
+            inv_dct_t<L2, T>(M.blk, M.TB, tm, bd, tt);
+        }
+        int64_t ssd = 0;
+        for(int e = tt; e < NY; e += T) {
+            const int     pr = ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY);
+            const int16_t t = nnz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
+            const int     r = clip3i(0, maxv, t), d = r - M.org[e];
+            ssd += (int64_t)((d * d) >> sh);
+        }
+        team_sync<T>();
+        ssd = team_sum_s64<T>(ssd, tt, M.X);
+        if(tt == 0) { M.cand_ssd[j] = ssd; M.cand_nnz[j] = nnz; }
+    }
+    team_sync<T>();
+    // pass 2 (one lane per mode): xeve_rdo_bit_cnt_cu_intra_luma (src_base/xeve_mode.c:81-119) of all modes at once --
+    // the bins of one mode are serial, the modes are independent, so lane j codes mode j on its own copy of the models
+    if(tt < pred_cnt) {
+        uint16_t *ml = M.cm_lane + tt;
+        for(int k = 0; k < IN_CM_N; k++) ml[k * 8] = M.cm_base[k];
+        TCabac c;
+        c.range = range_base; c.bits = 0; c.m = ml;
+        if(slice_type != 2 && all_preds) {
+            tc_bin<8>(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+            tc_bin<8>(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+        }
+        tc_unary<8>(c, mpm[M.list[tt]], IN_CM_IPM);
+        int num_sig = M.cand_nnz[tt];
+        tc_bin<8>(c, XB200_CM_CBF_LUMA, num_sig != 0);
+        if(num_sig) { // xeve_eco_run_length_cc over the zig-zag ordered levels; ends with the last significant one
+            const int16_t *lv = M.candS[tt];
+            uint32_t       run = 0;
+            for(int sp = 0; sp < NY; sp++) {
+                const int v = lv[sp];
+                if(v == 0) { run++; continue; }
+                tc_unary<8>(c, run, XB200_CM_RUN);
+                tc_unary<8>(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL);
+                tc_ep(c);
+                if(sp == NY - 1) break;
+                run = 0;
+                num_sig--;
+                tc_bin<8>(c, XB200_CM_LAST, num_sig == 0);
+                if(num_sig == 0) break;
+            }
+        }
+        M.cand_bits[tt] = c.bits;
+    }
+    __syncwarp();
+    team_sync<T>();
+    double  cost = IN_MAX_COST;
+    int     best_j = 0;
+    int32_t best_dist_y = 0;
+    for(int j = 0; j < pred_cnt; j++) { // first minimum in list order (strict <), every thread alike
+        double        cost_t = (double)M.cand_ssd[j];
+        const int32_t dist_t = (int32_t)cost_t;
+        cost_t = __dadd_rn(cost_t, __dmul_rn((double)M.cand_bits[j], lambda0));
+        if(cost_t < cost) { cost = cost_t; best_dist_y = dist_t; best_j = j; }
+    }
+    const int best_ipd = M.list[best_j], nnz_best0 = M.cand_nnz[best_j];
+    // the winner's levels go out in raster order; its reconstruction is rebuilt from them (cheaper than keeping five)
+    for(int e = tt; e < NY; e += T) {
+        const int16_t v = M.candS[best_j][zz_of(e, L2)];
+        g_coef[e] = v;
+        M.blk[e] = v;
+    }
+    if(g_rec) {
+        team_sync<T>();
+        if(nnz_best0) {
+            dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
+            inv_dct_t<L2, T>(M.blk, M.TB, tm, bd, tt);
+        }
+        for(int e = tt; e < NY; e += T) {
+            const int     pr = ipred_at(leY, upY, best_ipd, e >> L2, e & (N - 1), dcY);
+            const int16_t t = nnz_best0 ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
+            g_rec[e] = (int16_t)clip3i(0, maxv, t);
+        }
+    }
+    team_sync<T>();
+
+    // ---- chroma with the winning luma mode (pintra_residue_rdo mode 1, :153-270); its own bit count is never used ---
+    int     nnzc[2] = {0, 0};
+    int64_t ssdc[2] = {0, 0};
+#pragma unroll
+    for(int c = 1; c < 3; c++) {
+        const int16_t *le = leC[c - 1], *up = upC[c - 1], *og = M.org + NY + (c - 1) * NCH;
+        const int      dc = ipred_dc(le, up, LC);
+        for(int e = tt; e < NCH; e += T) M.blk[e] = (int16_t)(og[e] - ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc));
+        team_sync<T>();
+        fwd_dct_t<LC, T>(M.blk, M.TB, tm, tmT, bd, tt);
+        const int nz = quant_team<LC, T, true>(M.blk, M.TB, it.qp[c], it.lambda[c], c, slice_type, rt, bd, sq.rdoq, tt, M.X);
+        nnzc[c - 1] = nz;
+        for(int e = tt; e < NCH; e += T) {
+            const int16_t v = M.blk[e];
+            g_coef[NY + (c - 1) * NCH + e] = v;
+            M.chS[(c - 1) * NCH + zz_of(e, LC)] = v;
+        }
+        team_sync<T>();
+        if(nz) {
+            dequant_team<LC, T>(M.blk, it.qp[c], bd, tt);
+            inv_dct_t<LC, T>(M.blk, M.TB, tm, bd, tt);
+        }
+        int64_t ssd = 0;
+        for(int e = tt; e < NCH; e += T) {
+            const int     pr = ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc);
+            const int16_t t = nz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
+            const int     r = clip3i(0, maxv, t), d = r - og[e];
+            if(g_rec) g_rec[NY + (c - 1) * NCH + e] = (int16_t)r;
+            ssd += (int64_t)((d * d) >> sh);
+        }
+        team_sync<T>();
+        ssdc[c - 1] = team_sum_s64<T>(ssd, tt, M.X);
+    }
+    const int32_t best_dist_c = (int32_t)__dadd_rn(__dmul_rn(it.dist_chroma_weight[0], (double)ssdc[0]),
+                                                   __dmul_rn(it.dist_chroma_weight[1], (double)ssdc[1]));
+
+    // ---- final bit count of the CU from the input state (xeve_rdo_bit_cnt_cu_intra, src_base/xeve_mode.c:141-171) ----
+    for(int k = tt; k < IN_CM_N; k += T) M.cm_run[k] = M.cm_base[k];
+    team_sync<T>();
+    if(tt < 32) {
+        Cabac c;
+        c.range = range_base; c.bits = 0; c.m = M.cm_run;
+        if(lane == 0) {
+            if(slice_type != 2) {
+                cb_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+                cb_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+            }
+            cb_unary(c, mpm[best_ipd], IN_CM_IPM);
+            cb_bin(c, XB200_CM_CBF_CB, nnzc[0] != 0);
+            cb_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
+            cb_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
+        }
+        if(nnz_best0) cb_run_length_sm(c, M.candS[best_j], NY, nnz_best0, 0, lane);
+        if(nnzc[0]) cb_run_length_sm(c, M.chS, NCH, nnzc[0], 1, lane);
+        if(nnzc[1]) cb_run_length_sm(c, M.chS + NCH, NCH, nnzc[1], 2, lane);
+        if(lane == 0) { M.bits = c.bits; M.range_run = c.range; }
+        __syncwarp();
+    }
+    team_sync<T>();
+    if(tt == 0) {
+        double ct = __dmul_rn((double)M.bits, lambda0);
+        ct = __dadd_rn(ct, (double)best_dist_y);
+        ct = __dadd_rn(ct, (double)best_dist_c);
+        it.cost = ct;
+        it.dist_cu = best_dist_y + best_dist_c;
+        it.ipm[0] = it.ipm[1] = (int8_t)best_ipd;
+        it.nnz[0] = nnz_best0; it.nnz[1] = nnzc[0]; it.nnz[2] = nnzc[1];
+        it.cm_ipm_out[0] = M.cm_run[IN_CM_IPM]; it.cm_ipm_out[1] = M.cm_run[IN_CM_IPM + 1];
+        st_out[it.state_out].range = M.range_run;
+    }
+    {
+        xb200_sbac &so = st_out[it.state_out];
+        for(int k = tt; k < XB200_CM_COUNT; k += T) so.m[k] = M.cm_run[k];
+    }
+    team_sync<T>();
+}
+
 template <int L2>
 __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__restrict__ pics, xb200_intra_item *items,
                                                              const int32_t *__restrict__ order, int cnt,
@@ -176,10 +431,10 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
                                                              const int8_t *__restrict__ g_tm64, SeqDev sq)
 {
     using Cf = IntraCfg<L2>;
-    constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NC = N / 2, NCH = Cf::NCH, TILES = Cf::TILES, LC = L2 - 1;
+    constexpr int T = Cf::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int8_t *tm = reinterpret_cast<int8_t *>(smem_raw), *tmT = tm + 4096;
-    const int team = threadIdx.x / T, tt = threadIdx.x % T, lane = tt & 31;
+    const int team = threadIdx.x / T, tt = threadIdx.x % T;
     IntraTeam<L2> &M = reinterpret_cast<IntraTeam<L2> *>(smem_raw + 8192)[team];
     for(int e = threadIdx.x; e < 4096; e += Cf::CTA) {
         const int8_t v = g_tm64[e];
@@ -187,254 +442,9 @@ __global__ void __launch_bounds__(IntraCfg<L2>::CTA) k_intra(const PicDev *__res
         tmT[(e & 63) * 64 + (e >> 6)] = v;
     }
     __syncthreads();
-    const int bd = sq.bd, maxv = (1 << bd) - 1, sh = (bd - 8) << 1;
 
-    for(int ii = blockIdx.x * Cf::TEAMS + team; ii < cnt; ii += gridDim.x * Cf::TEAMS) {
-        xb200_intra_item &it = items[order[ii]];
-        const int slice_type = it.slice_type, all_preds = it.all_preds, ctx_skip = it.ctx_skip, ctx_pm = it.ctx_pred_mode;
-        const xb200_rates *rt = &rates[it.rate_idx];
-        const double lambda0 = it.lambda[0];
-        uint32_t range_base;
-        uint8_t  mpm[5];
-        // ---- stage inputs: original block, reference samples, coder state ------------------------------------------
-        {
-            const PicDev   p = pics[it.cur_pic];
-            const int      x0 = it.x, y0 = it.y;
-            const int16_t *gy = p.p[0] + (ptrdiff_t)y0 * p.s[0] + x0;
-            for(int e = tt; e < NY; e += T) M.org[e] = gy[(ptrdiff_t)(e >> L2) * p.s[0] + (e & (N - 1))];
-#pragma unroll
-            for(int c = 1; c < 3; c++) {
-                const int16_t *gc = p.p[c] + (ptrdiff_t)(y0 >> 1) * p.s[c] + (x0 >> 1);
-                for(int e = tt; e < NCH; e += T) M.org[NY + (c - 1) * NCH + e] = gc[(ptrdiff_t)(e >> LC) * p.s[c] + (e & (NC - 1))];
-            }
-            const int16_t *gn = side + it.nb_off;
-            for(int e = tt; e < 8 * N + 6; e += T) M.nb[e] = gn[e];
-            const xb200_sbac &s0 = st_in[it.state_in];
-            for(int k = tt; k < XB200_CM_COUNT; k += T) M.cm_base[k] = s0.m[k];
-            if(tt == 0) { M.cm_base[IN_CM_IPM] = it.cm_ipm_in[0]; M.cm_base[IN_CM_IPM + 1] = it.cm_ipm_in[1]; }
-            range_base = s0.range;
-#pragma unroll
-            for(int k = 0; k < 5; k++) mpm[k] = it.mpm[k];
-        }
-        team_sync<T>();
-        const int16_t *leY = M.nb + 1, *upY = M.nb + (2 * N + 1) + 1;
-        const int16_t *leC[2] = {M.nb + 2 * (2 * N + 1) + 1, M.nb + 2 * (2 * N + 1) + 2 * (N + 1) + 1};
-        const int16_t *upC[2] = {leC[0] + (N + 1), leC[1] + (N + 1)};
-        const int dcY = ipred_dc(leY, upY, L2);
-
-        // ---- make_ipred_list (src_base/xeve_pintra.c:308-374): SATD of the five modes, one (mode, tile) pair per thread ----
-        for(int w = tt; w < 5 * TILES; w += T) {
-            const int ipm = w / TILES, t = w % TILES;
-            if(L2 == 2) M.satd_part[w] = had_tile_fn<4>(M.org, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, y, x, dcY); });
-            else {
-                constexpr int TW = N >= 8 ? N / 8 : 1;
-                const int ty = (t / TW) * 8, tx = (t % TW) * 8;
-                M.satd_part[w] = had_tile_fn<8>(M.org + ty * N + tx, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, ty + y, tx + x, dcY); });
-            }
-        }
-        team_sync<T>();
-        if(tt == 0) {
-            double   cand_cost[5];
-            uint32_t cand_satd[5];
-            int      list[5];
-#pragma unroll
-            for(int k = 0; k < 5; k++) { list[k] = 0; cand_cost[k] = IN_MAX_COST; cand_satd[k] = 0xffffffffu; }
-            for(int ipm = 0; ipm < 5; ipm++) {
-                int sum = 0;
-                for(int t = 0; t < TILES; t++) sum += M.satd_part[ipm * TILES + t];
-                const uint32_t satd = (uint32_t)(sum >> (bd - 8));
-                Cabac c;
-                c.range = range_base; c.bits = 0; c.m = M.cm_run;
-                M.cm_run[IN_CM_IPM] = M.cm_base[IN_CM_IPM]; M.cm_run[IN_CM_IPM + 1] = M.cm_base[IN_CM_IPM + 1];
-                cb_unary(c, mpm[ipm], IN_CM_IPM);
-                const double cost = __dadd_rn((double)satd, __dmul_rn((double)c.bits, it.sqrt_lambda0));
-                int shift = 0;
-                while(shift < 5 && cost < cand_cost[4 - shift]) shift++;
-                if(shift) {
-                    for(int j = 1; j < shift; j++) { list[5 - j] = list[4 - j]; cand_cost[5 - j] = cand_cost[4 - j]; cand_satd[5 - j] = cand_satd[4 - j]; }
-                    list[5 - shift] = ipm; cand_cost[5 - shift] = cost; cand_satd[5 - shift] = satd;
-                }
-            }
-            int          pc = 5;
-            const double thr = __dmul_rn((double)it.inter_satd, 1.2);
-            for(int i = 4; i >= 1; i--) {
-                if((double)cand_satd[i] > thr) pc--;
-                else break;
-            }
-#pragma unroll
-            for(int k = 0; k < 5; k++) M.list[k] = list[k];
-            M.pred_cnt = pc;
-        }
-        team_sync<T>();
-        const int pred_cnt = M.pred_cnt;
-
-        // ---- luma RDO per surviving mode (pintra_residue_rdo mode 0, src_base/xeve_pintra.c:97-152) ---------------------
-        // pass 1 (team): transform, RDOQ, reconstruction and SSD of every surviving mode; levels kept in zig-zag order
-        int16_t *g_coef = coef + it.out_off, *g_rec = rec ? rec + it.out_off : nullptr;
-        for(int j = 0; j < pred_cnt; j++) {
-            const int ipm = M.list[j];
-            for(int e = tt; e < NY; e += T) M.blk[e] = (int16_t)(M.org[e] - ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY));
-            team_sync<T>();
-            fwd_dct_t<L2, T>(M.blk, M.TB, tm, tmT, bd, tt);
-            const int nnz = quant_team<L2, T, true>(M.blk, M.TB, it.qp[0], lambda0, 0, slice_type, rt, bd, sq.rdoq, tt, M.X);
-            for(int e = tt; e < NY; e += T) M.candS[j][zz_of(e, L2)] = M.blk[e];
-            if(nnz) {
-                team_sync<T>();
-                dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
-                inv_dct_t<L2, T>(M.blk, M.TB, tm, bd, tt);
-            }
-            int64_t ssd = 0;
-            for(int e = tt; e < NY; e += T) {
-                const int     pr = ipred_at(leY, upY, ipm, e >> L2, e & (N - 1), dcY);
-                const int16_t t = nnz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
-                const int     r = clip3i(0, maxv, t), d = r - M.org[e];
-                ssd += (int64_t)((d * d) >> sh);
-            }
-            team_sync<T>();
-            ssd = team_sum_s64<T>(ssd, tt, M.X);
-            if(tt == 0) { M.cand_ssd[j] = ssd; M.cand_nnz[j] = nnz; }
-        }
-        team_sync<T>();
-        // pass 2 (one lane per mode): xeve_rdo_bit_cnt_cu_intra_luma (src_base/xeve_mode.c:81-119) of all modes at once --
-        // the bins of one mode are serial, the modes are independent, so lane j codes mode j on its own copy of the models
-        if(tt < pred_cnt) {
-            uint16_t *ml = M.cm_lane + tt;
-            for(int k = 0; k < IN_CM_N; k++) ml[k * 8] = M.cm_base[k];
-            TCabac c;
-            c.range = range_base; c.bits = 0; c.m = ml;
-            if(slice_type != 2 && all_preds) {
-                tc_bin<8>(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
-                tc_bin<8>(c, XB200_CM_PRED_MODE + ctx_pm, 1);
-            }
-            tc_unary<8>(c, mpm[M.list[tt]], IN_CM_IPM);
-            int num_sig = M.cand_nnz[tt];
-            tc_bin<8>(c, XB200_CM_CBF_LUMA, num_sig != 0);
-            if(num_sig) { // xeve_eco_run_length_cc over the zig-zag ordered levels; ends with the last significant one
-                const int16_t *lv = M.candS[tt];
-                uint32_t       run = 0;
-                for(int sp = 0; sp < NY; sp++) {
-                    const int v = lv[sp];
-                    if(v == 0) { run++; continue; }
-                    tc_unary<8>(c, run, XB200_CM_RUN);
-                    tc_unary<8>(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL);
-                    tc_ep(c);
-                    if(sp == NY - 1) break;
-                    run = 0;
-                    num_sig--;
-                    tc_bin<8>(c, XB200_CM_LAST, num_sig == 0);
-                    if(num_sig == 0) break;
-                }
-            }
-            M.cand_bits[tt] = c.bits;
-        }
-        __syncwarp();
-        team_sync<T>();
-        double  cost = IN_MAX_COST;
-        int     best_j = 0;
-        int32_t best_dist_y = 0;
-        for(int j = 0; j < pred_cnt; j++) { // first minimum in list order (strict <), every thread alike
-            double        cost_t = (double)M.cand_ssd[j];
-            const int32_t dist_t = (int32_t)cost_t;
-            cost_t = __dadd_rn(cost_t, __dmul_rn((double)M.cand_bits[j], lambda0));
-            if(cost_t < cost) { cost = cost_t; best_dist_y = dist_t; best_j = j; }
-        }
-        const int best_ipd = M.list[best_j], nnz_best0 = M.cand_nnz[best_j];
-        // the winner's levels go out in raster order; its reconstruction is rebuilt from them (cheaper than keeping five)
-        for(int e = tt; e < NY; e += T) {
-            const int16_t v = M.candS[best_j][zz_of(e, L2)];
-            g_coef[e] = v;
-            M.blk[e] = v;
-        }
-        if(g_rec) {
-            team_sync<T>();
-            if(nnz_best0) {
-                dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
-                inv_dct_t<L2, T>(M.blk, M.TB, tm, bd, tt);
-            }
-            for(int e = tt; e < NY; e += T) {
-                const int     pr = ipred_at(leY, upY, best_ipd, e >> L2, e & (N - 1), dcY);
-                const int16_t t = nnz_best0 ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
-                g_rec[e] = (int16_t)clip3i(0, maxv, t);
-            }
-        }
-        team_sync<T>();
-
-        // ---- chroma with the winning luma mode (pintra_residue_rdo mode 1, :153-270); its own bit count is never used ---
-        int     nnzc[2] = {0, 0};
-        int64_t ssdc[2] = {0, 0};
-#pragma unroll
-        for(int c = 1; c < 3; c++) {
-            const int16_t *le = leC[c - 1], *up = upC[c - 1], *og = M.org + NY + (c - 1) * NCH;
-            const int      dc = ipred_dc(le, up, LC);
-            for(int e = tt; e < NCH; e += T) M.blk[e] = (int16_t)(og[e] - ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc));
-            team_sync<T>();
-            fwd_dct_t<LC, T>(M.blk, M.TB, tm, tmT, bd, tt);
-            const int nz = quant_team<LC, T, true>(M.blk, M.TB, it.qp[c], it.lambda[c], c, slice_type, rt, bd, sq.rdoq, tt, M.X);
-            nnzc[c - 1] = nz;
-            for(int e = tt; e < NCH; e += T) {
-                const int16_t v = M.blk[e];
-                g_coef[NY + (c - 1) * NCH + e] = v;
-                M.chS[(c - 1) * NCH + zz_of(e, LC)] = v;
-            }
-            team_sync<T>();
-            if(nz) {
-                dequant_team<LC, T>(M.blk, it.qp[c], bd, tt);
-                inv_dct_t<LC, T>(M.blk, M.TB, tm, bd, tt);
-            }
-            int64_t ssd = 0;
-            for(int e = tt; e < NCH; e += T) {
-                const int     pr = ipred_at(le, up, best_ipd, e >> LC, e & (NC - 1), dc);
-                const int16_t t = nz ? (int16_t)(M.blk[e] + pr) : (int16_t)pr;
-                const int     r = clip3i(0, maxv, t), d = r - og[e];
-                if(g_rec) g_rec[NY + (c - 1) * NCH + e] = (int16_t)r;
-                ssd += (int64_t)((d * d) >> sh);
-            }
-            team_sync<T>();
-            ssdc[c - 1] = team_sum_s64<T>(ssd, tt, M.X);
-        }
-        const int32_t best_dist_c = (int32_t)__dadd_rn(__dmul_rn(it.dist_chroma_weight[0], (double)ssdc[0]),
-                                                       __dmul_rn(it.dist_chroma_weight[1], (double)ssdc[1]));
-
-        // ---- final bit count of the CU from the input state (xeve_rdo_bit_cnt_cu_intra, src_base/xeve_mode.c:141-171) ----
-        for(int k = tt; k < IN_CM_N; k += T) M.cm_run[k] = M.cm_base[k];
-        team_sync<T>();
-        if(tt < 32) {
-            Cabac c;
-            c.range = range_base; c.bits = 0; c.m = M.cm_run;
-            if(lane == 0) {
-                if(slice_type != 2) {
-                    cb_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
-                    cb_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
-                }
-                cb_unary(c, mpm[best_ipd], IN_CM_IPM);
-                cb_bin(c, XB200_CM_CBF_CB, nnzc[0] != 0);
-                cb_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
-                cb_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
-            }
-            if(nnz_best0) cb_run_length_sm(c, M.candS[best_j], NY, nnz_best0, 0, lane);
-            if(nnzc[0]) cb_run_length_sm(c, M.chS, NCH, nnzc[0], 1, lane);
-            if(nnzc[1]) cb_run_length_sm(c, M.chS + NCH, NCH, nnzc[1], 2, lane);
-            if(lane == 0) { M.bits = c.bits; M.range_run = c.range; }
-            __syncwarp();
-        }
-        team_sync<T>();
-        if(tt == 0) {
-            double ct = __dmul_rn((double)M.bits, lambda0);
-            ct = __dadd_rn(ct, (double)best_dist_y);
-            ct = __dadd_rn(ct, (double)best_dist_c);
-            it.cost = ct;
-            it.dist_cu = best_dist_y + best_dist_c;
-            it.ipm[0] = it.ipm[1] = (int8_t)best_ipd;
-            it.nnz[0] = nnz_best0; it.nnz[1] = nnzc[0]; it.nnz[2] = nnzc[1];
-            it.cm_ipm_out[0] = M.cm_run[IN_CM_IPM]; it.cm_ipm_out[1] = M.cm_run[IN_CM_IPM + 1];
-            st_out[it.state_out].range = M.range_run;
-        }
-        {
-            xb200_sbac &so = st_out[it.state_out];
-            for(int k = tt; k < XB200_CM_COUNT; k += T) so.m[k] = M.cm_run[k];
-        }
-        team_sync<T>();
-    }
+    for(int ii = blockIdx.x * Cf::TEAMS + team; ii < cnt; ii += gridDim.x * Cf::TEAMS)
+        intra_cu_one<L2>(M, tm, tmT, pics, items[order[ii]], rates, st_in, st_out, side, coef, rec, sq, tt);
 }
 
 // =====================================================================================================================
@@ -454,7 +464,7 @@ template <int LN> XB_DEV int zz_raster(int sp, const uint8_t *zinv8)
 }
 
 // xeve_eco_run_length_cc of one block whose levels are in raster order
-template <int LN> XB_DEV void tc_run_length(TCabac &c, const int16_t *lev, int num_sig, int ch, const uint8_t *zinv8)
+template <int LN, int CS = I4_THREADS> XB_DEV void tc_run_length(TCabac &c, const int16_t *lev, int num_sig, int ch, const uint8_t *zinv8)
 {
     constexpr int n = 1 << (2 * LN);
     const int     t0 = ch == 0 ? 0 : 2;
@@ -463,13 +473,13 @@ template <int LN> XB_DEV void tc_run_length(TCabac &c, const int16_t *lev, int n
     for(int sp = 0; sp < n; sp++) {
         const int v = lev[zz_raster<LN>(sp, zinv8)];
         if(v == 0) { run++; continue; }
-        tc_unary(c, run, XB200_CM_RUN + t0);
-        tc_unary(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL + t0);
+        tc_unary<CS>(c, run, XB200_CM_RUN + t0);
+        tc_unary<CS>(c, (uint32_t)abs(v) - 1, XB200_CM_LEVEL + t0);
         tc_ep(c);
         if(sp == n - 1) break;
         run = 0;
         num_sig--;
-        tc_bin(c, XB200_CM_LAST + (ch != 0), num_sig == 0);
+        tc_bin<CS>(c, XB200_CM_LAST + (ch != 0), num_sig == 0);
         if(num_sig == 0) break;
     }
 }
@@ -547,7 +557,7 @@ XB_DEV int rdoq_thr(int16_t *b, int qp, double d_lambda, int ch, int slice_type,
     const int64_t thr = ((int64_t)1 << qbits) - ((int64_t)(slice_type == 2 ? 201 : 153) << (qbits - 9));
     RdoqEnv E;
     E.lambda = (int64_t)(d_lambda * 32768.0 + 0.5);
-    E.es     = c_err_scale[qp % 6][LN];
+    E.es     = c_err_scale[bd - 8][qp % 6][LN];
     E.qbits  = qbits;
     int     coded = 0, any = 0;
     int64_t unc_blk = 0;
@@ -624,34 +634,25 @@ XB_DEV int i4_model(int k, int ctx_skip, int ctx_pm)
 }
 constexpr int I4_MODELS = 17;
 
-template <int L2>
-__global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restrict__ pics, xb200_intra_item *items,
-                                                          const int32_t *__restrict__ order, int cnt, const xb200_rates *__restrict__ rates,
-                                                          const xb200_sbac *__restrict__ st_in, xb200_sbac *__restrict__ st_out,
-                                                          const int16_t *__restrict__ side, int16_t *__restrict__ coef,
-                                                          int16_t *__restrict__ rec, SeqDev sq)
+// pintra_analyze_cu of ONE 4x4 / 8x8 CU by ONE thread; mb / mr: the thread's two model sets, model k at [k * CS]
+template <int L2, int CS>
+__device__ __forceinline__ void intra_thr_one(const PicDev *__restrict__ pics, xb200_intra_item &it, const xb200_rates *rates,
+                                              const xb200_sbac *st_in, xb200_sbac *st_out, const int16_t *side, int16_t *coef, int16_t *rec,
+                                              const SeqDev &sq, uint16_t *mb, uint16_t *mr, const uint8_t *zinv8)
 {
     constexpr int N = 1 << L2, NY = N * N, NC = N / 2, NCH = NC * NC, LC = L2 - 1;
     constexpr int NBY = 2 * N + 1, NBC = N + 1;   // samples per reference array (index -1 .. 2n-1)
     constexpr int UR = L2 == 2 ? 64 : 1;          // arrays of 4x4 CUs stay in registers (every loop over them fully unrolled)
-    __shared__ uint16_t cm_base[IN_CM_N * I4_THREADS], cm_run[IN_CM_N * I4_THREADS];
-    __shared__ uint8_t  zinv8[64];
-    if(threadIdx.x < 64) zinv8[zz_of(threadIdx.x, 3)] = (uint8_t)threadIdx.x;
-    __syncthreads();
-    const int ii = blockIdx.x * I4_THREADS + threadIdx.x;
-    if(ii >= cnt) return;
-    xb200_intra_item &it = items[order[ii]];
     const int bd = sq.bd, maxv = (1 << bd) - 1, sh = (bd - 8) << 1;
     const int slice_type = it.slice_type, all_preds = it.all_preds, ctx_skip = it.ctx_skip, ctx_pm = it.ctx_pred_mode;
     const xb200_rates *rt = &rates[it.rate_idx];
     const double       lambda0 = it.lambda[0];
-    uint16_t *mb = cm_base + threadIdx.x, *mr = cm_run + threadIdx.x;
     const xb200_sbac &s0 = st_in[it.state_in];
     const uint32_t    range_base = s0.range;
 #pragma unroll
     for(int k = 0; k < I4_MODELS; k++) {
         const int idx = i4_model(k, ctx_skip, ctx_pm);
-        mb[idx * I4_THREADS] = idx >= IN_CM_IPM ? it.cm_ipm_in[idx - IN_CM_IPM] : s0.m[idx];
+        mb[idx * CS] = idx >= IN_CM_IPM ? it.cm_ipm_in[idx - IN_CM_IPM] : s0.m[idx];
     }
     uint8_t mpm[5];
 #pragma unroll
@@ -708,8 +709,8 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
         else satd = (uint32_t)had_tile_fn<8>(org, N, [&](int y, int x) { return ipred_at(leY, upY, ipm, y, x, dcY); });
         satd >>= (bd - 8);
         c.range = range_base; c.bits = 0;
-        mr[IN_CM_IPM * I4_THREADS] = mb[IN_CM_IPM * I4_THREADS]; mr[(IN_CM_IPM + 1) * I4_THREADS] = mb[(IN_CM_IPM + 1) * I4_THREADS];
-        tc_unary(c, mpm[ipm], IN_CM_IPM);
+        mr[IN_CM_IPM * CS] = mb[IN_CM_IPM * CS]; mr[(IN_CM_IPM + 1) * CS] = mb[(IN_CM_IPM + 1) * CS];
+        tc_unary<CS>(c, mpm[ipm], IN_CM_IPM);
         const double cost = __dadd_rn((double)satd, __dmul_rn((double)c.bits, it.sqrt_lambda0));
         int shift = 0;
         while(shift < 5 && cost < cand_cost[4 - shift]) shift++;
@@ -743,16 +744,16 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
 #pragma unroll(UR)
         for(int e = 0; e < NY; e++) lev[e] = b[e];
 #pragma unroll
-        for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * I4_THREADS] = mb[idx * I4_THREADS]; }
+        for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * CS] = mb[idx * CS]; }
         c.range = range_base; c.bits = 0;
         if(slice_type != 2 && all_preds) {
-            tc_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
-            tc_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+            tc_bin<CS>(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+            tc_bin<CS>(c, XB200_CM_PRED_MODE + ctx_pm, 1);
         }
-        tc_unary(c, mpm[ipm], IN_CM_IPM);
-        tc_bin(c, XB200_CM_CBF_LUMA, nnz != 0);
+        tc_unary<CS>(c, mpm[ipm], IN_CM_IPM);
+        tc_bin<CS>(c, XB200_CM_CBF_LUMA, nnz != 0);
         if(nnz) {
-            tc_run_length<L2>(c, lev, nnz, 0, zinv8);
+            tc_run_length<L2, CS>(c, lev, nnz, 0, zinv8);
             dequant_thr<L2>(b, it.qp[0], bd);
             inv_dct_thr<L2>(b, bd);
         }
@@ -817,19 +818,19 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
 
     // ---- final bit count from the input state --------------------------------------------------------------------------------
 #pragma unroll
-    for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * I4_THREADS] = mb[idx * I4_THREADS]; }
+    for(int k = 0; k < I4_MODELS; k++) { const int idx = i4_model(k, ctx_skip, ctx_pm); mr[idx * CS] = mb[idx * CS]; }
     c.range = range_base; c.bits = 0;
     if(slice_type != 2) {
-        tc_bin(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
-        tc_bin(c, XB200_CM_PRED_MODE + ctx_pm, 1);
+        tc_bin<CS>(c, XB200_CM_SKIP_FLAG + ctx_skip, 0);
+        tc_bin<CS>(c, XB200_CM_PRED_MODE + ctx_pm, 1);
     }
-    tc_unary(c, mpm[best_ipd], IN_CM_IPM);
-    tc_bin(c, XB200_CM_CBF_CB, nnzc[0] != 0);
-    tc_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
-    tc_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
-    if(nnz_best0) tc_run_length<L2>(c, best_lev, nnz_best0, 0, zinv8);
-    if(nnzc[0]) tc_run_length<LC>(c, levc[0], nnzc[0], 1, zinv8);
-    if(nnzc[1]) tc_run_length<LC>(c, levc[1], nnzc[1], 2, zinv8);
+    tc_unary<CS>(c, mpm[best_ipd], IN_CM_IPM);
+    tc_bin<CS>(c, XB200_CM_CBF_CB, nnzc[0] != 0);
+    tc_bin<CS>(c, XB200_CM_CBF_CR, nnzc[1] != 0);
+    tc_bin<CS>(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
+    if(nnz_best0) tc_run_length<L2, CS>(c, best_lev, nnz_best0, 0, zinv8);
+    if(nnzc[0]) tc_run_length<LC, CS>(c, levc[0], nnzc[0], 1, zinv8);
+    if(nnzc[1]) tc_run_length<LC, CS>(c, levc[1], nnzc[1], 2, zinv8);
 
     double ct = __dmul_rn((double)c.bits, lambda0);
     ct = __dadd_rn(ct, (double)best_dist_y);
@@ -838,7 +839,7 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
     it.dist_cu = best_dist_y + best_dist_c;
     it.ipm[0] = it.ipm[1] = (int8_t)best_ipd;
     it.nnz[0] = nnz_best0; it.nnz[1] = nnzc[0]; it.nnz[2] = nnzc[1];
-    it.cm_ipm_out[0] = mr[IN_CM_IPM * I4_THREADS]; it.cm_ipm_out[1] = mr[(IN_CM_IPM + 1) * I4_THREADS];
+    it.cm_ipm_out[0] = mr[IN_CM_IPM * CS]; it.cm_ipm_out[1] = mr[(IN_CM_IPM + 1) * CS];
     // output state = input state with the models this CU touched replaced
     xb200_sbac &so = st_out[it.state_out];
     so.range = c.range;
@@ -846,8 +847,24 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
 #pragma unroll
     for(int k = 0; k < I4_MODELS; k++) {
         const int idx = i4_model(k, ctx_skip, ctx_pm);
-        if(idx < XB200_CM_COUNT) so.m[idx] = mr[idx * I4_THREADS];
+        if(idx < XB200_CM_COUNT) so.m[idx] = mr[idx * CS];
     }
+}
+
+template <int L2>
+__global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restrict__ pics, xb200_intra_item *items,
+                                                          const int32_t *__restrict__ order, int cnt, const xb200_rates *__restrict__ rates,
+                                                          const xb200_sbac *__restrict__ st_in, xb200_sbac *__restrict__ st_out,
+                                                          const int16_t *__restrict__ side, int16_t *__restrict__ coef,
+                                                          int16_t *__restrict__ rec, SeqDev sq)
+{
+    __shared__ uint16_t cm_base[IN_CM_N * I4_THREADS], cm_run[IN_CM_N * I4_THREADS];
+    __shared__ uint8_t  zinv8[64];
+    if(threadIdx.x < 64) zinv8[zz_of(threadIdx.x, 3)] = (uint8_t)threadIdx.x;
+    __syncthreads();
+    const int ii = blockIdx.x * I4_THREADS + threadIdx.x;
+    if(ii >= cnt) return;
+    intra_thr_one<L2, I4_THREADS>(pics, items[order[ii]], rates, st_in, st_out, side, coef, rec, sq, cm_base + threadIdx.x, cm_run + threadIdx.x, zinv8);
 }
 
 // =====================================================================================================================
@@ -855,8 +872,9 @@ __global__ void __launch_bounds__(I4_THREADS) k_intra_thr(const PicDev *__restri
 // (src_base/xeve_util.c:717-772), xeve_get_nbr for Y, U, V (src_base/xeve_ipred.c:33-97), xeve_get_mpm (:230-252).
 // One warp per CU; lanes stride over the 8N+6 output samples, each deciding the availability of its own 4x4 unit.
 // =====================================================================================================================
-__constant__ uint8_t c_mpm_tbl[6][6][5];
+XB200_CONST_LINKAGE __constant__ uint8_t c_mpm_tbl[6][6][5];
 
+#ifndef XB200_CHAIN_TU
 __global__ void k_intra_nbr(const PicDev *__restrict__ pics, int pic, xb200_nbr_item *__restrict__ items, int64_t n,
                             const uint32_t *__restrict__ map_scu, const int8_t *__restrict__ map_ipm, int w_scu, int h_scu, int cip, int bd,
                             int16_t *__restrict__ side)
@@ -917,3 +935,4 @@ __global__ void k_intra_nbr(const PicDev *__restrict__ pics, int pic, xb200_nbr_
         out[e] = (int16_t)v;
     }
 }
+#endif

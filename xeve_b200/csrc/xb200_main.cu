@@ -155,7 +155,7 @@ int xb200_transform_main(xb200_ctx *c, const xb200_trm_item *items, int64_t n, i
     TrmArgs a;
     a.items = d_items; a.n = n; a.elems = elems; a.blocks = d_blocks; a.tm64 = c->d_tm64;
     a.ats = static_cast<const int8_t *>(c->b_ats.p); a.bd = c->seq.bit_depth; a.err = c->d_err;
-    const unsigned grid = (unsigned)(n < 148 * 8 ? n : 148 * 8);
+    const unsigned grid = (unsigned)(n < c->sms * 8 ? n : c->sms * 8);
     k_transform_main<<<grid, 256, 0, c->stream>>>(a);
     c->launches += 1;
     if(mem == XB200_MEM_HOST) CK(cudaMemcpyAsync(blocks, d_blocks, (size_t)elems * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));

@@ -46,11 +46,7 @@ template <int L2> struct MeGeom {
     static constexpr int TEAMS = CTA / T;
     static constexpr int NG    = T / G;                                  // candidates in flight per team
 };
-template <int T> XB_DEV void me_team_sync()
-{
-    if(T == 32) __syncwarp();
-    else __syncthreads();
-}
+template <int T> XB_DEV void me_team_sync() { team_bar<T>(); }
 
 // shared memory of one team: mbarrier, cost table, reduction slots, original block, interpolation
 // scratch, staged window (multiple of 16 bytes)
@@ -443,9 +439,9 @@ XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, 
                 for(int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
                 uint32_t sad = part;
                 if(T > 32) {
-                    __syncthreads(); // red[] free, tmp[] reads done
+                    team_bar<T>(); // red[] free, tmp[] reads done
                     if(lane == 0) red[tid >> 5] = (int32_t)part;
-                    __syncthreads();
+                    team_bar<T>();
                     sad = 0;
 #pragma unroll
                     for(int wi = 0; wi < T / 32; wi++) sad += (uint32_t)red[wi];

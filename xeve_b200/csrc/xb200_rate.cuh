@@ -10,8 +10,8 @@
 #include "xb200_common.cuh"
 #include "xb200_cabac.cuh"
 
-__device__ uint16_t g_scan[16 + 64 + 256 + 1024 + 4096];   // zig-zag: scan position -> raster, log2 size 2..6
-__device__ int32_t  g_entropy_bits[1024];                  // xeve_init_bits_est, computed on the host with libm
+XB200_CONST_LINKAGE __device__ uint16_t g_scan[16 + 64 + 256 + 1024 + 4096];   // zig-zag: scan position -> raster, log2 size 2..6
+XB200_CONST_LINKAGE __device__ int32_t  g_entropy_bits[1024];                  // xeve_init_bits_est, computed on the host with libm
 __device__ __forceinline__ int scan_base(int l2) { return l2 == 2 ? 0 : l2 == 3 ? 16 : l2 == 4 ? 80 : l2 == 5 ? 336 : 1360; }
 
 __device__ __forceinline__ void cb_mvp_idx(Cabac &c, int v)
@@ -134,6 +134,7 @@ __device__ __forceinline__ void cb_count_item(Cabac &c, const xb200_bits_item &i
     else cb_coef(c, it.nnz, it.log2_cuw, it.log2_cuh, coef + it.coef_off, 1 << it.ch, lane);
 }
 
+#ifndef XB200_CHAIN_TU   // non-template kernels: defined once, in the translation unit of the operators
 constexpr int RATE_WARPS = 4;
 __global__ void __launch_bounds__(RATE_WARPS * 32) k_rdo_bits(xb200_bits_item *__restrict__ items, long long n,
                                                                const xb200_sbac *__restrict__ st_in, xb200_sbac *__restrict__ st_out,
@@ -161,12 +162,14 @@ __global__ void __launch_bounds__(RATE_WARPS * 32) k_rdo_bits(xb200_bits_item *_
     }
 }
 
+#endif
 // xeve_rdoq_bit_est: one thread per (state, model, bin)
 __device__ __forceinline__ int32_t rate_of(uint16_t model, int bin)
 {
     const uint32_t mps = model & 1, state = model >> 1;
     return g_entropy_bits[(((uint32_t)bin != mps) ? state : 512 - state) << 1];
 }
+#ifndef XB200_CHAIN_TU
 __global__ void k_rdoq_rates(const xb200_sbac *__restrict__ st, long long n, xb200_rates *__restrict__ out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,3 +191,4 @@ __global__ void k_rdoq_rates(const xb200_sbac *__restrict__ st, long long n, xb2
         }
     }
 }
+#endif

@@ -12,11 +12,7 @@
 #include "xb200_tq.cuh"
 #include "xb200_dct_tc.cuh"
 
-template <int T> XB_DEV void team_sync()
-{
-    if(T == 32) __syncwarp();
-    else __syncthreads();
-}
+template <int T> XB_DEV void team_sync() { team_bar<T>(); }
 
 struct TeamScratch { // cross-warp exchange, only used by teams wider than a warp
     int64_t w64[8];
@@ -29,11 +25,11 @@ template <int T> XB_DEV int64_t team_sum_s64(int64_t v, int tt, TeamScratch &X)
     for(int m = 16; m > 0; m >>= 1) v += (int64_t)shfl_xor_u64((uint64_t)v, m);
     if(T > 32) {
         if((tt & 31) == 0) X.w64[tt >> 5] = v;
-        __syncthreads();
+        team_bar<T>();
         uint64_t s = 0;
 #pragma unroll
         for(int i = 0; i < T / 32; i++) s += (uint64_t)X.w64[i];
-        __syncthreads();
+        team_bar<T>();
         v = (int64_t)s;
     }
     return v;
@@ -44,11 +40,11 @@ template <int T> XB_DEV int team_sum_s32(int v, int tt, TeamScratch &X)
     for(int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     if(T > 32) {
         if((tt & 31) == 0) X.w32[tt >> 5] = v;
-        __syncthreads();
+        team_bar<T>();
         int s = 0;
 #pragma unroll
         for(int i = 0; i < T / 32; i++) s += X.w32[i];
-        __syncthreads();
+        team_bar<T>();
         v = s;
     }
     return v;
@@ -223,7 +219,7 @@ XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch
     // zero-block pre-test + per-coefficient first pass, fused (the sums are only used if the block is coded)
     RdoqEnv E;
     E.lambda = (int64_t)(d_lambda * 32768.0 + 0.5);
-    E.es     = c_err_scale[qp % 6][LN];
+    E.es     = c_err_scale[bd - 8][qp % 6][LN];
     E.qbits  = qbits;
     int16_t  *sc  = reinterpret_cast<int16_t *>(TB);
     uint16_t *pos = reinterpret_cast<uint16_t *>(TB) + n;
@@ -290,9 +286,9 @@ XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch
     int state = 0;
     if(T > 32) {
         if(lane == 31) X.w32[tt >> 5] = incl;
-        __syncthreads();
+        team_bar<T>();
         for(int w = 0; w < (tt >> 5); w++) state = (X.w32[w] >> state) & 1;
-        __syncthreads();
+        team_bar<T>();
     }
     state = (excl >> state) & 1;
     // pass 2: levels, increments, local best "last" candidate
@@ -324,9 +320,9 @@ XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch
     int64_t pre = inc - run_sum;
     if(T > 32) {
         if(lane == 31) X.w64[tt >> 5] = inc;
-        __syncthreads();
+        team_bar<T>();
         for(int w = 0; w < (tt >> 5); w++) pre += X.w64[w];
-        __syncthreads();
+        team_bar<T>();
     }
     // arg-min of (value, scan index): first minimum in scan order
     int64_t bv = (loc_idx >= 0) ? base0 + pre + loc_best : INT64_MAX;
@@ -339,12 +335,12 @@ XB_DEV int quant_team(int16_t *blk, int32_t *TB, int qp, double d_lambda, int ch
     }
     if(T > 32) {
         if(lane == 0) { X.w64[tt >> 5] = bv; X.w32[tt >> 5] = bidx; }
-        __syncthreads();
+        team_bar<T>();
         bv = X.w64[0]; bidx = X.w32[0];
 #pragma unroll
         for(int w = 1; w < T / 32; w++)
             if(X.w64[w] < bv || (X.w64[w] == bv && X.w32[w] < bidx)) { bv = X.w64[w]; bidx = X.w32[w]; }
-        __syncthreads();
+        team_bar<T>();
     }
     const int best_last = (bidx != 0x7fffffff && bv < best0) ? bidx + 1 : 0;
     team_sync<T>(); // sc[] complete

@@ -194,7 +194,7 @@ template <class SM> XB_DEV int quant_block(SM &S, int l2, int qp, double d_lambd
     uint16_t *pos = reinterpret_cast<uint16_t *>(S.T) + n;   // raster position by scan pos
     RdoqEnv   E;
     E.lambda = (int64_t)(d_lambda * 32768.0 + 0.5);
-    E.es     = c_err_scale[qp % 6][l2];
+    E.es     = c_err_scale[bd - 8][qp % 6][l2];
     E.qbits  = qbits;
     {
         const int ctx = ch == 0 ? 0 : 2;
