@@ -177,6 +177,7 @@ static struct {
     vec_t    intra;    /* RH_INTRA_REC; coder states go to cu_sbac, neighbour samples to samp */
     vec_t    df, df_cu, df_maps; /* deblocking: one record per picture, CU rectangles, frame maps (bytes) */
     int (*org_lcu)(XEVE_CTX *, XEVE_CORE *);
+    int (*org_frame)(XEVE_CTX *);
     vec_t    lcu;      /* RH_LCU_REC: one per ctx->fn_mode_analyze_lcu call */
     int      df_collect;
     vec_t    me, mc, tq, rates, pics, samp, sbac; /* sbac[i]: coder state rates[i] was derived from */
@@ -575,6 +576,22 @@ static const RH_INJECT_PIC *g_inject;
 static int g_inject_n;
 static int64_t g_inject_ctus;
 RH_API void rh_inject(const RH_INJECT_PIC *pics, int n) { g_inject = pics; g_inject_n = n; g_inject_ctus = 0; }
+/* Lazy variant: the records of a picture are asked for when the reference starts coding it (ctx->fn_mode_analyze_frame, the
+ * picture-level hook the reference calls before its CTU loop, src_base/xeve_enc.c:322) -- a decision engine that runs ahead of the
+ * entropy coder hands each picture over as soon as it is decided.  rec_* may be NULL (the reconstruction stays with the engine). */
+typedef int (*rh_fetch_fn)(int poc, RH_INJECT_PIC *out);
+static rh_fetch_fn   g_fetch;
+static RH_INJECT_PIC g_fetched;
+static int           g_fetched_ok;
+RH_API void rh_inject_lazy(rh_fetch_fn f) { g_fetch = f; g_fetched_ok = 0; g_inject_ctus = 0; }
+/* Plan mode (RH_T_PLAN): the reference's own control plane run dry -- every CTU gets a trivial decision (8x8 SKIP / 8x8 intra DC
+ * units, no residual), so a sequence is "coded" in milliseconds per picture while slice types, POCs, QPs, lambdas and reference lists
+ * come out exactly as a real encode computes them (constant QP: none of them depends on a decision).  One RH_LCU_REC (CTU 0) and one
+ * RH_DF_REC (parameters only) per picture, in coding order: the picture-level inputs of xb200_analyze_picture for a whole clip. */
+#define RH_T_PLAN 1024
+#define RH_T_NO_LF 2048  /* ctx->fn_loop_filter does nothing: the deblocked picture lives on the device */
+static RH_SCU_REC *g_plan_scu[2];   /* [inter, intra] dummy records of one CTU */
+static int16_t    *g_plan_zero;
 RH_API int64_t rh_inject_count(void) { return g_inject_ctus; }
 RH_API int rh_sizeof_inject(int what) { return what == 0 ? sizeof(RH_SCU_REC) : sizeof(RH_INJECT_PIC); }
 
@@ -592,7 +609,16 @@ static void inject_split(XEVE_CTX *ctx, XEVE_CU_DATA *cd, const RH_SCU_REC *scu,
 static int inject_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
 {
     const RH_INJECT_PIC *ip = NULL;
+    RH_INJECT_PIC        plan;
     for(int i = 0; i < g_inject_n; i++) if(g_inject[i].poc == (int)ctx->poc.poc_val) ip = &g_inject[i];
+    if(!ip && g_fetched_ok && g_fetched.poc == (int)ctx->poc.poc_val) ip = &g_fetched;
+    if(!ip && (T.mask & RH_T_PLAN)) {
+        memset(&plan, 0, sizeof(plan));
+        plan.poc = (int)ctx->poc.poc_val;
+        plan.scu = g_plan_scu[ctx->slice_type == SLICE_I] - (size_t)core->lcu_num * 256;
+        plan.coef = g_plan_zero - (size_t)core->lcu_num * 6144;
+        ip = &plan;
+    }
     if(!ip) return XEVE_ERR;
     const int L = ctx->log2_max_cuwh - 2, x0 = core->x_pel, y0 = core->y_pel, q = ctx->tile[core->tile_idx].qp;
     const int bdc = ctx->sps.bit_depth_chroma_minus8;
@@ -630,13 +656,15 @@ static int inject_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
         cd->mvr_idx[i] = 0; cd->bi_idx[i] = 0; cd->mmvd_idx[i] = 0; cd->dmvr_flag[i] = 0;
     }
     memcpy(cd->coef[Y_C], coef, 4096 * 2); memcpy(cd->coef[U_C], coef + 4096, 1024 * 2); memcpy(cd->coef[V_C], coef + 5120, 1024 * 2);
-    for(int j = 0; j < 64 && y0 + j < ctx->h; j++)
-        memcpy(cd->reco[Y_C] + j * 64, ip->rec_y + (size_t)(y0 + j) * ip->s_l + x0, 2 * XEVE_MIN(64, ctx->w - x0));
-    for(int j = 0; j < 32 && y0 / 2 + j < ctx->h / 2; j++) {
-        memcpy(cd->reco[U_C] + j * 32, ip->rec_u + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
-        memcpy(cd->reco[V_C] + j * 32, ip->rec_v + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
+    if(ip->rec_y) {
+        for(int j = 0; j < 64 && y0 + j < ctx->h; j++)
+            memcpy(cd->reco[Y_C] + j * 64, ip->rec_y + (size_t)(y0 + j) * ip->s_l + x0, 2 * XEVE_MIN(64, ctx->w - x0));
+        for(int j = 0; j < 32 && y0 / 2 + j < ctx->h / 2; j++) {
+            memcpy(cd->reco[U_C] + j * 32, ip->rec_u + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
+            memcpy(cd->reco[V_C] + j * 32, ip->rec_v + (size_t)(y0 / 2 + j) * ip->s_c + x0 / 2, 2 * XEVE_MIN(32, (ctx->w - x0) / 2));
+        }
+        mode_cpy_rec_to_ref(core, x0, y0, ctx->max_cuwh, ctx->max_cuwh, PIC_MODE(ctx), xeve_get_default_tree_cons(), ctx->sps.chroma_format_idc);
     }
-    mode_cpy_rec_to_ref(core, x0, y0, ctx->max_cuwh, ctx->max_cuwh, PIC_MODE(ctx), xeve_get_default_tree_cons(), ctx->sps.chroma_format_idc);
     update_to_ctx_map(ctx, core);
     copy_cu_data(&ctx->map_cu_data[core->lcu_num], cd, 0, 0, ctx->log2_max_cuwh, ctx->log2_max_cuwh, ctx->log2_max_cuwh, 0,
                  xeve_get_default_tree_cons(), ctx->sps.chroma_format_idc);
@@ -646,9 +674,34 @@ static int inject_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
     g_inject_ctus++;
     return XEVE_OK;
 }
+static void lcu_fill_picture_fields(XEVE_CTX *ctx, XEVE_CORE *core, RH_LCU_REC *r);
+static void plan_push_df(XEVE_CTX *ctx);
+static int hook_analyze_frame(XEVE_CTX *ctx)
+{
+    if((T.mask & RH_T_INJECT) && g_fetch) {
+        g_fetched_ok = 0;
+        memset(&g_fetched, 0, sizeof(g_fetched));
+        if(g_fetch((int)ctx->poc.poc_val, &g_fetched) != 0) return XEVE_ERR;
+        g_fetched_ok = 1;
+    }
+    return T.org_frame ? T.org_frame(ctx) : XEVE_OK;
+}
 static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
 {
-    if((T.mask & RH_T_INJECT) && g_inject) return inject_lcu(ctx, core);
+    if(T.mask & RH_T_PLAN) {
+        if(core->lcu_num == 0) {
+            static pthread_mutex_t pm = PTHREAD_MUTEX_INITIALIZER;
+            pthread_mutex_lock(&pm);
+            RH_LCU_REC r;
+            memset(&r, 0, sizeof(r));
+            lcu_fill_picture_fields(ctx, core, &r);
+            *(RH_LCU_REC *)vec_push(&T.lcu, 1) = r;
+            plan_push_df(ctx);
+            pthread_mutex_unlock(&pm);
+        }
+        return inject_lcu(ctx, core);
+    }
+    if((T.mask & RH_T_INJECT) && (g_inject || g_fetch)) return inject_lcu(ctx, core);
     if(!tracing(RH_T_LCU)) return T.org_lcu(ctx, core);
     static int64_t col_off[2];
     static pthread_mutex_t mtx = PTHREAD_MUTEX_INITIALIZER;   /* with threads > 1 the CTU rows run concurrently */
@@ -708,6 +761,41 @@ static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
     return ret;
 }
 RH_API int rh_sizeof_lcu(void) { return sizeof(RH_LCU_REC); }
+/* the picture-level fields of an RH_LCU_REC without touching any picture data (plan mode): reference pictures are named by POC only
+ * (ref_pic = 0 marks a valid entry), no colocated maps, no coder states */
+static void lcu_fill_picture_fields(XEVE_CTX *ctx, XEVE_CORE *core, RH_LCU_REC *r)
+{
+    XEVE_PINTER *pi = &ctx->pinter[core->thread_cnt];
+    r->poc = ctx->poc.poc_val; r->slice_type = ctx->slice_type; r->lcu_num = core->lcu_num;
+    r->x_pel = core->x_pel; r->y_pel = core->y_pel; r->tile_qp = ctx->tile[core->tile_idx].qp;
+    r->cur_pic = -1;
+    for(int l = 0; l < 2; l++) {
+        r->num_refp[l] = ctx->rpm.num_refp[l];
+        for(int k = 0; k < RH_MAXR; k++) {
+            r->ref_pic[l][k] = -1; r->ref_poc[l][k] = -1;
+            if(ctx->slice_type != SLICE_I && k < r->num_refp[l] && (l == 0 || ctx->slice_type == SLICE_B)) {
+                r->ref_pic[l][k] = 0;
+                r->ref_poc[l][k] = (int)ctx->refp[k][l].poc;
+            }
+        }
+    }
+    r->col_off[0] = r->col_off[1] = -1;
+    if(ctx->slice_type == SLICE_B && ctx->refp[0][REFP_1].list_poc) r->col_list_poc0 = (int)ctx->refp[0][REFP_1].list_poc[0];
+    r->max_cu_inter = ctx->param.max_cu_inter; r->min_cu_inter = ctx->param.min_cu_inter;
+    r->max_cu_intra = ctx->param.max_cu_intra; r->min_cu_intra = ctx->param.min_cu_intra;
+    r->cip = ctx->pps.constrained_intra_pred_flag;
+    {
+        const int q = r->tile_qp, bdc = ctx->sps.bit_depth_chroma_minus8;
+        r->qp[0] = GET_LUMA_QP(q, ctx->sps.bit_depth_luma_minus8);
+        r->qp[1] = ctx->qp_chroma_dynamic[0][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_u_offset)] + 6 * bdc;
+        r->qp[2] = ctx->qp_chroma_dynamic[1][XEVE_CLIP3(-6 * bdc, 57, q + ctx->sh->qp_v_offset)] + 6 * bdc;
+    }
+    r->lambda_mv = pi->lambda_mv; r->max_search_range = pi->max_search_range;
+    for(int i = 0; i < 3; i++) r->lambda[i] = core->lambda[i];
+    r->sqrt_lambda0 = core->sqrt_lambda[0];
+    r->dist_chroma_weight[0] = core->dist_chroma_weight[0]; r->dist_chroma_weight[1] = core->dist_chroma_weight[1];
+    r->parallel_rows = ctx->parallel_rows;
+}
 
 /* ------------------------------------------------------------------------------------------
  * deblocking trace: ctx->fn_loop_filter with the picture before / after, the frame
@@ -747,8 +835,20 @@ static void df_fill_pic(XEVE_CTX *ctx, RH_DF_PIC *pp)
         for(int q = -bdo; q <= 57; q++) pp->chroma_qp[c][q + bdo] = ctx->qp_chroma_dynamic[c][q];
 }
 
+static void plan_push_df(XEVE_CTX *ctx)
+{
+    RH_DF_REC r;
+    memset(&r, 0, sizeof(r));
+    r.poc = ctx->poc.poc_val;
+    r.on  = ctx->sh->deblocking_filter_on;
+    r.pre_pic = r.post_pic = -1;
+    r.maps_off = -1;
+    df_fill_pic(ctx, &r.pp);
+    *(RH_DF_REC *)vec_push(&T.df, 1) = r;
+}
 static int hook_loop_filter(XEVE_CTX *ctx, XEVE_CORE *core)
 {
+    if(T.mask & (RH_T_PLAN | RH_T_NO_LF)) return XEVE_OK;
     if(!tracing(RH_T_DF)) return T.org_lf(ctx, core);
     RH_DF_REC r;
     memset(&r, 0, sizeof(r));
@@ -877,6 +977,20 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
         T.org_lf = ctx->fn_loop_filter; T.org_df_unit = ctx->fn_deblock_unit;
         ctx->fn_loop_filter = hook_loop_filter; ctx->fn_deblock_unit = hook_df_unit;
         T.org_lcu = ctx->fn_mode_analyze_lcu; ctx->fn_mode_analyze_lcu = hook_lcu;
+        T.org_frame = ctx->fn_mode_analyze_frame; ctx->fn_mode_analyze_frame = hook_analyze_frame;
+    }
+    if(trace_mask & RH_T_PLAN) {     /* dummy decisions of one CTU: 8x8 units, SKIP with zero motion / intra DC, no residual */
+        for(int k = 0; k < 2; k++) {
+            if(!g_plan_scu[k]) g_plan_scu[k] = calloc(256, sizeof(RH_SCU_REC));
+            for(int i = 0; i < 256; i++) {
+                RH_SCU_REC *u = &g_plan_scu[k][i];
+                memset(u, 0, sizeof(*u));
+                u->log2 = 3;
+                if(k) { u->mode = 3; u->refi[0] = u->refi[1] = -1; }
+                else  { u->mode = 0; u->refi[0] = 0; u->refi[1] = 0; }
+            }
+        }
+        if(!g_plan_zero) g_plan_zero = calloc(6144, sizeof(int16_t));
     }
     XEVE_PINTER *pi = &ctx->pinter[0];
     T.cst.w = w; T.cst.h = h; T.cst.bit_depth = ctx->param.codec_bit_depth; T.cst.me_level = pi->me_level;

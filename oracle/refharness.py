@@ -174,6 +174,8 @@ TRACE_DF = 32
 TRACE_INTRA, TRACE_INTRA_TIME = 64, 128
 TRACE_LCU = 256
 TRACE_INJECT = 512
+TRACE_PLAN = 1024    # the reference's control plane run dry: picture-level parameters of every picture, trivial decisions
+TRACE_NO_LF = 2048   # ctx->fn_loop_filter does nothing (the deblocked picture lives on the device)
 
 
 def intra_time():
@@ -363,6 +365,66 @@ def encode_clip_injected(yuv, nframes, w, h, decisions, **kw):
     finally:
         L.rh_inject(None, 0)
     return tr, n, cu_time()[1], intra_time()[1]
+
+
+def plan_clip(nframes, w, h, in_depth=8, preset="fast", qp=-1, threads=1, bframes=-1, extra=""):
+    """The picture-level plan of a clip from the reference's OWN control plane run dry (RH_T_PLAN): per picture in coding order the
+    LCU_REC of CTU 0 (slice type, POC, QPs, lambdas, reference POCs, CU size limits, search range, parallel rows) and the loop-filter
+    parameters -- the inputs of xb200_analyze_picture.  With constant QP none of them depends on a decision, so the dry run (every CTU
+    gets 8x8 SKIP / intra DC units) yields what a real encode of `nframes` frames computes; takes milliseconds per picture.
+    Returns (seq constants, [dict(pp, df_pp, deblock)])."""
+    bps = 2 if in_depth > 8 else 1
+    yuv = np.zeros(nframes * w * h * 3 // 2 * bps, np.uint8)
+    if in_depth <= 8:
+        yuv[:] = 128
+    tr = encode_clip(yuv, nframes, w, h, in_depth=in_depth, preset=preset, qp=qp, threads=threads, bframes=bframes, extra=extra,
+                     trace_mask=TRACE_PLAN, want_bitstream=False)
+    assert len(tr.lcu) == len(tr.df) == nframes, (len(tr.lcu), len(tr.df), nframes)
+    return tr.const, [dict(pp=tr.lcu[i].copy(), df_pp=tr.df[i]["pp"].copy(), deblock=int(tr.df[i]["on"])) for i in range(nframes)]
+
+
+_FETCH_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(INJECT_PIC))
+
+
+def encode_clip_lazy(yuv, nframes, w, h, fetch, no_loop_filter=True, **kw):
+    """Reference encode whose mode decision is replaced by records handed over picture by picture: fetch(poc) -> dict(scu, coef[, rec])
+    is called when the reference starts coding picture `poc` (ctx->fn_mode_analyze_frame) and may block until that picture is decided.
+    no_loop_filter: the reference's own loop filter is skipped (the reconstruction stays with the decision engine; the bitstream does
+    not depend on it).  Returns (trace with the bitstream, CTUs injected)."""
+    L = lib()
+    keep, err = [], []
+
+    def cb(poc, out):
+        try:
+            d = fetch(int(poc))
+            scu, coef = np.ascontiguousarray(d["scu"]), np.ascontiguousarray(d["coef"], np.int16)
+            assert scu.dtype.itemsize == L.rh_sizeof_inject(0)
+            keep[:] = [(scu, coef, d.get("rec"))]
+            o = out.contents
+            o.poc, o.scu, o.coef = int(poc), scu.ctypes.data, coef.ctypes.data
+            o.rec_y = o.rec_u = o.rec_v = None
+            if d.get("rec") is not None:
+                rec = [np.ascontiguousarray(a, np.int16) for a in d["rec"]]
+                keep.append(rec)
+                o.s_l, o.s_c = rec[0].shape[1], rec[1].shape[1]
+                o.rec_y, o.rec_u, o.rec_v = [a.ctypes.data for a in rec]
+            return 0
+        except Exception as e:  # noqa: BLE001 -- must not propagate through the C frame
+            err.append(e)
+            return -1
+    cfn = _FETCH_CB(cb)
+    L.rh_inject_lazy.restype = None
+    L.rh_inject_lazy.argtypes = [C.c_void_p]
+    L.rh_inject_count.restype = C.c_int64
+    L.rh_inject_lazy(C.cast(cfn, C.c_void_p))
+    try:
+        tr = encode_clip(yuv, nframes, w, h, trace_mask=TRACE_INJECT | (TRACE_NO_LF if no_loop_filter else 0), **kw)
+        n = int(L.rh_inject_count())
+    finally:
+        L.rh_inject_lazy(None)
+    if err:
+        raise err[0]
+    return tr, n
 
 
 def replay_me(tr: Trace, recs: np.ndarray | None = None, nthreads=1):

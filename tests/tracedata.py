@@ -595,8 +595,10 @@ class DevicePictureEncoder:
                 o = self.oracle.encode(pc)
                 cu, it = log
                 assert len(cu) == len(o["cu_log"]) and len(it) == len(o["intra_log"]), (poc, len(cu), len(o["cu_log"]), len(it), len(o["intra_log"]))
-                for name, a, b, skip in (("inter", cu, o["cu_log"], ("cur_pic", "ref_pic", "coef_hash", "rec_hash", "me_first", "me_cnt", "pad0_", "pad1_")),
-                                         ("intra", it, o["intra_log"], ("cur_pic", "coef_hash", "rec_hash", "pad0_", "pad1_"))):
+                for name, a, b, skip in (("inter", cu, o["cu_log"], ("cur_pic", "ref_pic", "coef_hash", "rec_hash", "me_first", "me_cnt", "pad0_", "pad1_",
+                                                                     "state_in", "state_out", "rate_idx", "out_off")),
+                                         ("intra", it, o["intra_log"], ("cur_pic", "coef_hash", "rec_hash", "pad0_", "pad1_", "state_in",
+                                                                        "state_out", "rate_idx", "out_off", "nb_off"))):
                     for f in a.dtype.names:
                         if f in skip:
                             continue

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <deque>
 #include <map>
+#include <mutex>
 
 namespace {
 
@@ -47,6 +48,7 @@ struct Job {
     bool    retired = false;
 };
 struct ChainCtx {
+    std::mutex   mu;                    // host-side bookkeeping: one thread may enqueue pictures while another fetches results
     cudaStream_t streams[N_STREAMS] = {};
     cudaStream_t copy = nullptr;
     int          next_stream = 0;
@@ -167,8 +169,9 @@ void bufs_free(JobBufs &b)
     b = JobBufs();
 }
 
-// retire finished pictures; with `need` > 0 wait (oldest first) until that much SM share is free
-int admit(xb200_ctx *c, double need)
+// retire finished pictures; with `need` > 0 wait (oldest first) until that much SM share is free.  Called with k->mu held; the
+// blocking wait happens with the lock released (only the enqueueing thread creates jobs, so the event stays meaningful).
+int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk)
 {
     ChainCtx *k = cc_of(c);
     for(;;) {
@@ -185,7 +188,11 @@ int admit(xb200_ctx *c, double need)
         }
         if(k->inflight.empty()) k->load = 0.0;
         if(need <= 0 || k->load + need <= (double)c->sms + 1e-9 || k->inflight.empty()) return XB200_OK;
-        CK(cudaEventSynchronize(k->inflight.front()->b.ev1));
+        cudaEvent_t e = k->inflight.front()->b.ev1;
+        lk.unlock();
+        const cudaError_t er = cudaEventSynchronize(e);
+        lk.lock();
+        if(er != cudaSuccess) CK(er);
     }
 }
 
@@ -267,6 +274,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     int r = chain_init(c);
     if(r) return r;
     ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
     // ---- arguments ----
     if(pp->slice_type == 1) return XB200_ERR_UNSUPPORTED;   // P slices: the next CTU starts from the bitstream coder's state, not the RDO's
     if(pp->slice_type != 0 && pp->slice_type != 2) return XB200_ERR_INVALID_ARGUMENT;
@@ -340,7 +348,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     if(bps < 1) return XB200_ERR_UNSUPPORTED;
     const double share = (double)P.n_chain / bps;
     if(share > c->sms) return XB200_ERR_UNSUPPORTED;
-    if((r = admit(c, share))) return r;
+    if((r = admit(c, share, lk))) return r;
 
     Job *j = new Job();
     if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
@@ -382,10 +390,19 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
     if(!c || !c->chain) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
     auto it = k->jobs.find(rec_pic);
     if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
     Job *j = it->second;
-    CK(cudaEventSynchronize(j->b.ev2));
+    {
+        cudaEvent_t e = j->b.ev2;
+        lk.unlock();
+        const cudaError_t er = cudaEventSynchronize(e);
+        lk.lock();
+        if(er != cudaSuccess) CK(er);
+        it = k->jobs.find(rec_pic);
+        if(it == k->jobs.end() || it->second != j) return XB200_ERR_INVALID_ARGUMENT;
+    }
     const size_t n = (size_t)k->n_lcu;
     if(scu) CK(cudaMemcpyAsync(scu, j->b.scu, n * 256 * sizeof(xb200_scu_rec), cudaMemcpyDeviceToHost, k->copy));
     if(coef) CK(cudaMemcpyAsync(coef, j->b.coef, n * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, k->copy));
@@ -417,6 +434,7 @@ int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_in
     if(!c || !c->chain || !n) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
     auto it = k->jobs.find(rec_pic);
     if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
     Job *j = it->second;
@@ -435,6 +453,7 @@ int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t 
     if(!c || !c->chain || rec_pic < 0 || rec_pic >= (int)cc_of(c)->maps.size() || !cc_of(c)->maps[rec_pic].scu) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
     PicMaps  &m = k->maps[rec_pic];
     if(m.has_ready) CK(cudaEventSynchronize(m.ready));
     const size_t f = k->f_scu;
