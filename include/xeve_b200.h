@@ -476,6 +476,12 @@ XB200_API int xb200_picture_log_enable(xb200_ctx *c, int64_t cap_cu, int64_t cap
 XB200_API int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_intra_item *intra, int64_t n[2]);
 /* Number of decision chains (CTAs of the persistent kernel) the device can hold at once; pictures beyond it queue on the host. */
 XB200_API int xb200_chain_capacity(xb200_ctx *c);
+/* Device time (ms, CUDA events) from the first picture enqueued after the last reset to the latest completion among the pictures
+ * fetched since: the span of a batch of pictures that ran concurrently on the library's own streams.  reset != 0 starts a new batch. */
+XB200_API double xb200_chain_span_ms(xb200_ctx *c, int reset);
+/* Profiling builds only (-DXB200_CHAIN_PROF, otherwise XB200_ERR_UNSUPPORTED): SM cycles [0..31] and visit counts [32..63] per phase of
+ * the decision kernel since the previous call (phase numbers: xb200_analyze.cuh / xb200_chain.cuh CU_PROF). */
+XB200_API int xb200_chain_prof(xb200_ctx *c, uint64_t out[64]);
 
 /* ---- Main profile, first operator: the two-stage 16-bit transforms -------------------------------------------------
  * Forward / inverse transform of a list of s16 blocks in place (row-major, w * h samples at element offset `off` of `blocks`):

@@ -162,7 +162,10 @@ static uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
  * ---------------------------------------------------------------------------------------- */
 enum { RH_T_ME = 1, RH_T_MC = 2, RH_T_TQ = 4 };
 
-static struct {
+/* One set of trace state per process (g_T: hooks may run in the reference's worker threads, which have no thread-local state) or,
+ * for encodes started with RH_T_ISOLATED (threads = 1, so every hook runs in the calling thread), one per calling thread: several
+ * such encodes can then run concurrently in one process (one stream per host thread). */
+typedef struct {
     XEVE_CTX *ctx;
     int       mask, pic_lo, pic_hi; /* record while pic_lo <= ctx->pic_cnt <= pic_hi */
     u32 (*org_me)(XEVE_PINTER *, int, int, int, int, s8 *, int, s16 *, s16 *, int, int);
@@ -185,7 +188,11 @@ static struct {
     RH_CONST cst;
     RH_RATES last_rates;
     int      have_rates;
-} T;
+} RH_STATE_T;
+static RH_STATE_T           g_T;
+static __thread RH_STATE_T *tl_T;
+#define T (*(tl_T ? tl_T : &g_T))
+#define RH_T_ISOLATED 4096
 
 static int tracing(int kind)
 {
@@ -580,10 +587,26 @@ RH_API void rh_inject(const RH_INJECT_PIC *pics, int n) { g_inject = pics; g_inj
  * picture-level hook the reference calls before its CTU loop, src_base/xeve_enc.c:322) -- a decision engine that runs ahead of the
  * entropy coder hands each picture over as soon as it is decided.  rec_* may be NULL (the reconstruction stays with the engine). */
 typedef int (*rh_fetch_fn)(int poc, RH_INJECT_PIC *out);
-static rh_fetch_fn   g_fetch;
-static RH_INJECT_PIC g_fetched;
-static int           g_fetched_ok;
-RH_API void rh_inject_lazy(rh_fetch_fn f) { g_fetch = f; g_fetched_ok = 0; g_inject_ctus = 0; }
+static __thread rh_fetch_fn   g_fetch;      /* per calling thread: lazy hand-over needs threads = 1 (hooks run in the caller) */
+static __thread RH_INJECT_PIC g_fetched;
+static __thread int           g_fetched_ok;
+static __thread int64_t       tl_inject_ctus;
+RH_API void rh_inject_lazy(rh_fetch_fn f) { g_fetch = f; g_fetched_ok = 0; tl_inject_ctus = 0; }
+RH_API int64_t rh_inject_lazy_count(void) { return tl_inject_ctus; }
+/* The reference writes its parameters, `threads` among them, into an SEI message of the first access unit (xeve_param2string,
+ * src_base/xeve_enc.c:2533-2537 via xeve_eco_emitsei).  A host pass that runs single-threaded over decisions made as T coder-state
+ * chains labels the stream with T, like the reference run it reproduces: ctx->fn_enc_header sees param.threads = T, nothing else does. */
+static __thread int g_label_threads;
+static __thread int (*g_org_header)(XEVE_CTX *);
+RH_API void rh_label_threads(int t) { g_label_threads = t; }
+static int hook_header(XEVE_CTX *ctx)
+{
+    const int keep = ctx->param.threads;
+    if(g_label_threads > 0) ctx->param.threads = g_label_threads;
+    const int ret = g_org_header(ctx);
+    ctx->param.threads = keep;
+    return ret;
+}
 /* Plan mode (RH_T_PLAN): the reference's own control plane run dry -- every CTU gets a trivial decision (8x8 SKIP / 8x8 intra DC
  * units, no residual), so a sequence is "coded" in milliseconds per picture while slice types, POCs, QPs, lambdas and reference lists
  * come out exactly as a real encode computes them (constant QP: none of them depends on a decision).  One RH_LCU_REC (CTU 0) and one
@@ -671,7 +694,8 @@ static int inject_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
     const int xs = x0 >> 2, ys = y0 >> 2, w = XEVE_MIN(16, ctx->w_scu - xs), h = XEVE_MIN(16, ctx->h_scu - ys);
     for(int j = 0; j < h; j++)
         for(int i = 0; i < w; i++) MCU_CLR_COD(ctx->map_scu[(size_t)(ys + j) * ctx->w_scu + xs + i]);
-    g_inject_ctus++;
+    if(g_fetch) tl_inject_ctus++;
+    else __atomic_fetch_add(&g_inject_ctus, 1, __ATOMIC_RELAXED);
     return XEVE_OK;
 }
 static void lcu_fill_picture_fields(XEVE_CTX *ctx, XEVE_CORE *core, RH_LCU_REC *r);
@@ -959,6 +983,9 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     XEVE id  = make_encoder(w, h, in_depth, preset, qp, threads, bframes, extra, &err);
     if(!id) return -1.0;
     XEVE_CTX *ctx = (XEVE_CTX *)id;
+    RH_STATE_T *own = NULL;
+    if((trace_mask & RH_T_ISOLATED) && threads == 1) { own = calloc(1, sizeof(RH_STATE_T)); tl_T = own; }
+    trace_mask &= ~RH_T_ISOLATED;
 
     vec_reset(&T.me, sizeof(RH_ME_REC)); vec_reset(&T.mc, sizeof(RH_MC_REC)); vec_reset(&T.tq, sizeof(RH_TQ_REC));
     vec_reset(&T.rates, sizeof(RH_RATES)); vec_reset(&T.pics, sizeof(RH_PIC)); vec_reset(&T.samp, sizeof(s16)); vec_reset(&T.sbac, sizeof(RH_SBAC)); vec_reset(&T.cu, sizeof(RH_CU_REC)); vec_reset(&T.cu_sbac, sizeof(RH_SBAC));
@@ -978,6 +1005,7 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
         ctx->fn_loop_filter = hook_loop_filter; ctx->fn_deblock_unit = hook_df_unit;
         T.org_lcu = ctx->fn_mode_analyze_lcu; ctx->fn_mode_analyze_lcu = hook_lcu;
         T.org_frame = ctx->fn_mode_analyze_frame; ctx->fn_mode_analyze_frame = hook_analyze_frame;
+        if(g_label_threads > 0) { g_org_header = ctx->fn_enc_header; ctx->fn_enc_header = hook_header; }
     }
     if(trace_mask & RH_T_PLAN) {     /* dummy decisions of one CTU: 8x8 units, SKIP with zero motion / intra DC, no residual */
         for(int k = 0; k < 2; k++) {
@@ -1051,6 +1079,13 @@ RH_API double rh_encode_clip(const void *yuv, int nframes, int w, int h, int in_
     free(bs);
     T.ctx = NULL;
     xeve_delete(id);
+    if(own) {   /* private state of an isolated encode: nothing to hand back but the bitstream */
+        vec_t *vs[] = {&own->cu, &own->cu_sbac, &own->intra, &own->df, &own->df_cu, &own->df_maps, &own->lcu, &own->me, &own->mc, &own->tq,
+                       &own->rates, &own->pics, &own->samp, &own->sbac};
+        for(size_t i = 0; i < sizeof(vs) / sizeof(vs[0]); i++) free(vs[i]->p);
+        tl_T = NULL;
+        free(own);
+    }
     return t_enc;
 }
 

@@ -176,6 +176,7 @@ TRACE_LCU = 256
 TRACE_INJECT = 512
 TRACE_PLAN = 1024    # the reference's control plane run dry: picture-level parameters of every picture, trivial decisions
 TRACE_NO_LF = 2048   # ctx->fn_loop_filter does nothing (the deblocked picture lives on the device)
+TRACE_ISOLATED = 4096  # threads = 1 only: private harness state for this call, so several encodes can run on several host threads
 
 
 def intra_time():
@@ -306,6 +307,8 @@ def encode_clip(yuv: np.ndarray, nframes, w, h, in_depth=8, preset="fast", qp=-1
                            extra.encode(), trace_mask, pic_lo, pic_hi, _p(bs), cap, C.byref(n))
     if sec < 0:
         raise RuntimeError(f"reference encode failed ({sec})")
+    if trace_mask & TRACE_ISOLATED:      # nothing was recorded in the shared state
+        return Trace(None, None, None, None, None, None, None, sec, bs[: n.value].copy() if want_bitstream else None)
 
     def grab(what, dt):
         ptr = C.c_void_p()
@@ -386,11 +389,13 @@ def plan_clip(nframes, w, h, in_depth=8, preset="fast", qp=-1, threads=1, bframe
 _FETCH_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(INJECT_PIC))
 
 
-def encode_clip_lazy(yuv, nframes, w, h, fetch, no_loop_filter=True, **kw):
+def encode_clip_lazy(yuv, nframes, w, h, fetch, no_loop_filter=True, label_threads=1, **kw):
     """Reference encode whose mode decision is replaced by records handed over picture by picture: fetch(poc) -> dict(scu, coef[, rec])
     is called when the reference starts coding picture `poc` (ctx->fn_mode_analyze_frame) and may block until that picture is decided.
     no_loop_filter: the reference's own loop filter is skipped (the reconstruction stays with the decision engine; the bitstream does
-    not depend on it).  Returns (trace with the bitstream, CTUs injected)."""
+    not depend on it).  label_threads: the `threads` value the decisions were made with -- the reference records it in the parameter SEI of
+    the first access unit, so the single-threaded host pass labels the stream like the reference run it reproduces.
+    Returns (trace with the bitstream, CTUs injected)."""
     L = lib()
     keep, err = [], []
 
@@ -415,13 +420,19 @@ def encode_clip_lazy(yuv, nframes, w, h, fetch, no_loop_filter=True, **kw):
     cfn = _FETCH_CB(cb)
     L.rh_inject_lazy.restype = None
     L.rh_inject_lazy.argtypes = [C.c_void_p]
-    L.rh_inject_count.restype = C.c_int64
+    L.rh_inject_lazy_count.restype = C.c_int64
     L.rh_inject_lazy(C.cast(cfn, C.c_void_p))
+    L.rh_label_threads.restype = None
+    L.rh_label_threads.argtypes = [C.c_int]
+    L.rh_label_threads(int(label_threads))
+    kw = dict(kw)
+    kw["threads"] = 1              # the bitstream is written from the records alone; hooks must run in the calling thread
     try:
-        tr = encode_clip(yuv, nframes, w, h, trace_mask=TRACE_INJECT | (TRACE_NO_LF if no_loop_filter else 0), **kw)
-        n = int(L.rh_inject_count())
+        tr = encode_clip(yuv, nframes, w, h, trace_mask=TRACE_INJECT | TRACE_ISOLATED | (TRACE_NO_LF if no_loop_filter else 0), **kw)
+        n = int(L.rh_inject_lazy_count())
     finally:
         L.rh_inject_lazy(None)
+        L.rh_label_threads(0)
     if err:
         raise err[0]
     return tr, n

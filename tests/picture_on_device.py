@@ -37,6 +37,17 @@ def run(seq, pics, compare_oracle=False, threads=None, overlap=False, check=True
         out = [enc.encode(pc) for pc in pics]
     sec = time.time() - t0
     launches = hp.launches
+    prof = hp.chain_prof()
+    if prof is not None:
+        names = {0: "load", 1: "skip", 3: "ME uni", 4: "mvp check", 6: "bi loop", 7: "pre-final", 8: "final copy-out", 9: "intra (all)",
+                 10: "tree bookkeeping", 12: "RDO: predict", 13: "RDO: transforms", 14: "RDO: cbf coder", 18: "[inter 8x8 total]",
+                 19: "[inter 16x16 total]", 20: "[inter 32x32 total]", 21: "[inter 64x64 total]", 22: "ME: window staging",
+                 23: "ME: first diamond", 24: "ME: refinement runs", 25: "ME: sub-pel"}
+        cyc, cnt = prof
+        tot = sum(int(cyc[k]) for k in names if k < 18 or k > 21) or 1
+        for k, nm in names.items():
+            if cnt[k]:
+                print(f"    prof {nm:22s} {100 * int(cyc[k]) / tot:5.1f}%  {int(cyc[k]) / 1.9e3 / max(int(cnt[k]), 1):9.1f} us/visit  x{int(cnt[k])}")
     hp.close()
     return out, launches, sec
 
@@ -70,7 +81,7 @@ def main():
         tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, threads=threads,
                             trace_mask=rh.TRACE_LCU | rh.TRACE_DF, pic_lo=0, pic_hi=1 << 20)
         seq, pics = tracedata.chain_inputs_from_trace(tr)
-        out, launches, sec = run(seq, pics, compare_oracle=oracle and threads == 1, overlap=True)
+        out, launches, sec = run(seq, pics, compare_oracle=oracle and threads == 1, overlap="XB200_LIB" not in os.environ)
         n_cu, ms = summary(out)
         dec = [dict(poc=r["poc"], scu=r["scu"], coef=r["coef"], rec=r["rec"]) for r in out]
         tr2, n_ctu, ncu, nintra = rh.encode_clip_injected(yuv, frames, c.w, c.h, dec, in_depth=c.depth, preset=preset, extra=extra, threads=threads)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxeve_b200.so")
+LIB_PATH = os.environ.get("XB200_LIB") or os.path.join(_HERE, "libxeve_b200.so")   # XB200_LIB: an alternative build (profiling hooks)
 
 OK, ERR, ERR_INVALID_ARGUMENT, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_UNEXPECTED = 0, -1, -101, -102, -104, -105
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -186,6 +186,9 @@ def load():
         L.xb200_picture_log_enable.argtypes = [VP, C.c_int64, C.c_int64]
         L.xb200_picture_log.argtypes = [VP, C.c_int32, VP, VP, VP]
         L.xb200_chain_capacity.argtypes = [VP]
+        L.xb200_chain_prof.argtypes = [VP, VP]
+        L.xb200_chain_span_ms.argtypes = [VP, C.c_int]
+        L.xb200_chain_span_ms.restype = C.c_double
         _lib = L
     return _lib
 
@@ -195,7 +198,7 @@ EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
            "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr",
            "xb200_transform_main", "xb200_analyze_picture", "xb200_picture_fetch", "xb200_picture_maps", "xb200_picture_adopt",
-           "xb200_picture_log_enable", "xb200_picture_log", "xb200_chain_capacity"]
+           "xb200_picture_log_enable", "xb200_picture_log", "xb200_chain_capacity", "xb200_chain_prof", "xb200_chain_span_ms"]
 
 
 def _p(a):
@@ -440,6 +443,16 @@ class Hotpath:
             raise Xb200Error(r, "xb200_chain_capacity")
         return r
 
+    def chain_span_ms(self, reset=False):
+        """device time from the first enqueue after the last reset to the latest completion among the pictures fetched since"""
+        return float(self.L.xb200_chain_span_ms(self.h, int(reset)))
+
+    def chain_prof(self):
+        """(cycles[32], counts[32]) per phase of the decision kernel -- profiling builds only, else None"""
+        out = np.zeros(64, np.uint64)
+        r = self.L.xb200_chain_prof(self.h, _p(out))
+        return None if r != OK else (out[:32].copy(), out[32:].copy())
+
     def analyze_picture(self, pic):
         """Enqueue one picture (PICTURE record); returns at once, xb200 orders it after its reference pictures."""
         pic = np.ascontiguousarray(pic, PICTURE).reshape(1)
@@ -453,6 +466,12 @@ class Hotpath:
         cost, stat = np.zeros(n, np.float64), np.zeros(1, PICTURE_STAT)
         self._ck(self.L.xb200_picture_fetch(self.h, rec_pic, _p(scu), _p(coef), _p(st), _p(cost), _p(stat)), "xb200_picture_fetch")
         return dict(scu=scu, coef=coef, states=st, cost=cost, stat=stat[0])
+
+    def picture_wait(self, rec_pic):
+        """Wait for picture rec_pic without copying its records (they are released) -> its PICTURE_STAT"""
+        stat = np.zeros(1, PICTURE_STAT)
+        self._ck(self.L.xb200_picture_fetch(self.h, rec_pic, None, None, None, None, _p(stat)), "xb200_picture_fetch")
+        return stat[0]
 
     def picture_maps(self, rec_pic):
         f = self.f_scu

@@ -13,6 +13,15 @@
 // Candidate modes keep {coef, rec, pred} in a per-team global scratch slot (L2 resident); the winner is copied out.
 #pragma once
 #include "xb200_common.cuh"
+// Phase timers of the decision chain (debug builds with -DXB200_CHAIN_PROF): cycles per phase, accumulated by thread 0 of the team.
+#ifdef XB200_CHAIN_PROF
+__device__ unsigned long long g_chain_prof[64];
+__device__ long long g_prof_last;
+#define CU_PROF(k) do { if(tt == 0) { const long long now_ = clock64(); atomicAdd(&g_chain_prof[(k)], (unsigned long long)(now_ - g_prof_last)); atomicAdd(&g_chain_prof[32 + (k)], 1ull); g_prof_last = now_; } } while(0)
+#else
+#define CU_PROF(k) do { } while(0)
+#endif
+
 #include "xb200_me.cuh"
 #include "xb200_rate.cuh"
 #include "xb200_residue2.cuh"
@@ -215,6 +224,7 @@ __device__ __noinline__ double cu_residue_rdo(const CuTeam<L2> &Tm, const PicDev
     cu_predict<L2>(pics, cu, sq, M.refi[0], M.refi[1], M.mv[0][0], M.mv[0][1], M.mv[1][0], M.mv[1][1], Tm.pred, Tm.aux,
                    reinterpret_cast<int16_t *>(Tm.TB), tt);
     for(int e = tt; e < NP; e += T) gpred[e] = Tm.pred[e];
+    CU_PROF(12);
     int     store[3];
     int64_t d0[3], d1[3];
     residue_plane<L2, T, LNMAX, false>(Tm.org[0], Tm.so[0], Tm.pred, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco, grec, 1, cu.qp[0], cu.lambda[0], 0,
@@ -224,8 +234,10 @@ __device__ __noinline__ double cu_residue_rdo(const CuTeam<L2> &Tm, const PicDev
     residue_plane<L2 - 1, T, LNMAX, false>(Tm.org[2], Tm.so[2], Tm.pred + NY + NCH, Tm.blk, Tm.TB, Tm.tm, Tm.tmT, gco + NY + NCH, grec + NY + NCH,
                                            1, cu.qp[2], cu.lambda[2], 2, cu.slice_type, rt, sq, tt, H.X, store[2], d0[2], d1[2], nullptr, nullptr);
     team_sync<T>(); // coefficient planes visible to the coder warp
+    CU_PROF(13);
     int          cbf;
     const double best = cu_cbf_decide<T>(H, pidx, M, mi0, mi1, store, d0, d1, gco, cbf, tt);
+    CU_PROF(14);
     if(tt == 0) {
         M.cbf = cbf;
         M.nnz[0] = (cbf & 1) ? store[0] : 0; M.nnz[1] = (cbf & 2) ? store[1] : 0; M.nnz[2] = (cbf & 4) ? store[2] : 0;
@@ -282,6 +294,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
         if(tt == 0) H.rg[ST_IN] = s.range;
     }
     team_sync<T>();
+    CU_PROF(0);
     const xb200_cu_item &cu = H.cu;
     const xb200_rates   *rt = &rates[cu.rate_idx];
     const PicDev        &o = pics[cu.cur_pic];
@@ -338,6 +351,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
         if(sb < cost_best) { cost_best = sb; best_idx = 3; cu_st_save<T>(H, ST_BEST, ST_MODE, tt); }
     }
     team_sync<T>();
+    CU_PROF(1);
     double cost_win = cost_best;
     if(cost_best < CU_MAX_COST && best_ssd > 0) {
         if(B) { // ---- analyze_t_direct ----
@@ -369,6 +383,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
                 mv_scale[lidx][r][0] = (int16_t)mx; mv_scale[lidx][r][1] = (int16_t)my;
                 if(mecost < best_me) { best_me = mecost; refi_t = r; }
             }
+            CU_PROF(3);
             const int mvx = mv_scale[lidx][refi_t][0], mvy = mv_scale[lidx][refi_t][1];
             // check_best_mvp: the loop compares against the cost of the initial index only (quirk q1)
             {
@@ -389,6 +404,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
                 }
                 mvp_idx[lidx] = (uint8_t)best;
             }
+            CU_PROF(4);
             if(tt == 0) {
                 CuMode &M = H.md[lidx];
                 M.refi[lidx] = (int8_t)refi_t; M.refi[1 - lidx] = -1;
@@ -436,6 +452,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
                 refi[lidx_ref] = (int8_t)refi_best; refi[lidx_cnd] = -1;
                 if(!changed) break;
             }
+            CU_PROF(6);
             if(tt == 0) {
                 CuMode &M = H.md[2];
                 for(int l = 0; l < 2; l++) {
@@ -450,6 +467,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
         }
         cost_win = cost_best;
     }
+    CU_PROF(7);
     // ---- winner: coefficients (dropped planes zeroed), reconstruction, XEVE_MODE fields, s_next_best ---------
     const CuMode &M = H.md[best_idx];
     int16_t      *gc = coef_out + cu.out_off, *gr = rec_out ? rec_out + cu.out_off : nullptr;
@@ -487,6 +505,7 @@ __device__ __noinline__ void analyze_cu_one(CuTeam<L2> &Tm, const PicDev *__rest
         if(tt == 0) so.range = H.rg[ST_BEST];
     }
     team_sync<T>();
+    CU_PROF(8);
 }
 
 template <int L2, int TEAMS>

@@ -59,6 +59,9 @@ struct ChainCtx {
     double       load = 0.0;            // sum of the shares of the admitted, unretired pictures
     int16_t     *zero_mv = nullptr;     // colocated map of a reference picture without one (all zero)
     long long    log_cu = 0, log_intra = 0;
+    cudaEvent_t  ev_span0 = nullptr;    // device time span of a batch of pictures: first enqueue after a reset ...
+    bool         span_on = false;
+    float        span_ms = 0.f;         // ... to the latest completion among the pictures fetched since
     bool         ready = false;
     int          n_lcu = 0, w_lcu = 0, h_lcu = 0, w_scu = 0, h_scu = 0;
     size_t       f_scu = 0;
@@ -75,6 +78,7 @@ int chain_init(xb200_ctx *c)
     k->w_scu = (c->seq.w + 3) >> 2; k->h_scu = (c->seq.h + 3) >> 2; k->f_scu = (size_t)k->w_scu * k->h_scu;
     for(int i = 0; i < N_STREAMS; i++) CK(cudaStreamCreateWithFlags(&k->streams[i], cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&k->copy, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&k->ev_span0));
     {   // constant tables of this translation unit
         static int8_t tm[64 * 64];
         xb200_gen_tm64(tm);
@@ -223,6 +227,7 @@ void xb200_chain_free(xb200_ctx *c)
     for(int i = 0; i < N_STREAMS; i++)
         if(k->streams[i]) cudaStreamDestroy(k->streams[i]);
     if(k->copy) cudaStreamDestroy(k->copy);
+    if(k->ev_span0) cudaEventDestroy(k->ev_span0);
     delete k;
     c->chain = nullptr;
 }
@@ -239,8 +244,8 @@ int xb200_chain_capacity(xb200_ctx *c)
     for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * 10 + 7; cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
     const size_t smem = chain_smem_bytes(cap);
     int bps = 0;
-    CK(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<1>, CH_T, smem));
+    CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<2>, CH_T, smem));
     return c->sms * (bps < 1 ? 1 : bps);
 }
 
@@ -317,6 +322,12 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     P.pp.df.w_scu = k->w_scu; P.pp.df.h_scu = k->h_scu;
     P.n_chain = pp->parallel_rows > 1 ? (pp->parallel_rows > k->h_lcu ? k->h_lcu : pp->parallel_rows) : 1;
     for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * margin + 7; P.win_cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
+    {
+        // 4x4 / 8x8 intra CUs on a warp team: 2.4x shorter latency inside a chain than the thread-per-CU variant the batched operator
+        // uses for throughput (profiles/r02s06_chain_phase_profile.txt); XB200_INTRA_SMALL_TEAM=0 selects the thread variant (same results)
+        const char *e = getenv("XB200_INTRA_SMALL_TEAM");
+        P.small_team = e ? atoi(e) : 3;
+    }
     const size_t smem = chain_smem_bytes(P.win_cap);
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
     {
@@ -342,10 +353,16 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
             }
     }
     if(m->has_ready) CK(cudaStreamWaitEvent(s, m->ready, 0));   // an earlier life of this handle
+    // Register budget by load: one chain per SM with 255 registers while the device has room (fastest chain), two per SM with 128
+    // registers (each ~20 % slower, profiles/r02s06) once the chains in flight would not fit otherwise.
     int bps = 0;
-    CK(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<1>, CH_T, smem));
+    CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<2>, CH_T, smem));
     if(bps < 1) return XB200_ERR_UNSUPPORTED;
+    if((r = admit(c, 0.0, lk))) return r;               // retire what has finished
+    const char *dense_env = getenv("XB200_CHAIN_DENSE"); // 0: always one chain per SM, 1: always two
+    const bool dense = bps >= 2 && (dense_env ? dense_env[0] == '1' : k->load + (double)P.n_chain > (double)c->sms);
+    if(!dense) bps = 1;
     const double share = (double)P.n_chain / bps;
     if(share > c->sms) return XB200_ERR_UNSUPPORTED;
     if((r = admit(c, share, lk))) return r;
@@ -358,12 +375,13 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     if(k->log_cu > 0) { P.cu_log = j->b.cu_log; P.cu_cap = k->log_cu; }
     if(k->log_intra > 0) { P.intra_log = j->b.intra_log; P.intra_cap = k->log_intra; }
     const size_t f = k->f_scu;
+    if(!k->span_on) { CK(cudaEventRecord(k->ev_span0, s)); k->span_on = true; k->span_ms = 0.f; }
     CK(cudaMemsetAsync(m->scu, 0, f * 4, s)); CK(cudaMemsetAsync(m->ipm, 0, f, s)); CK(cudaMemsetAsync(m->refi, 0, f * 2, s));
     CK(cudaMemsetAsync(m->mv, 0, f * 8, s)); CK(cudaMemsetAsync(m->flags, 0, f, s));
     CK(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
     CK(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
     CK(cudaEventRecord(j->b.ev0, s));
-    if((r = launch_chain<1>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
+    if((r = dense ? launch_chain<2>(c, P, smem, s) : launch_chain<1>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
     CK(cudaEventRecord(j->b.ev1, s));
     Pic &rp = c->pics[pp->rec_pic];
     if(pp->unfiltered_pic >= 0) {
@@ -419,6 +437,10 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
         cudaEventElapsedTime(&b, j->b.ev1, j->b.ev2);
         stat->n_inter = (int64_t)cnt[0]; stat->n_intra = (int64_t)cnt[1]; stat->chain_ms = a; stat->filter_ms = b;
     }
+    if(k->span_on) {
+        float sp = 0.f;
+        if(cudaEventElapsedTime(&sp, k->ev_span0, j->b.ev2) == cudaSuccess && sp > k->span_ms) k->span_ms = sp;
+    }
     if(!j->retired) { j->retired = true; k->load -= j->share; }
     for(auto q = k->inflight.begin(); q != k->inflight.end(); ++q)
         if(*q == j) { k->inflight.erase(q); break; }
@@ -446,6 +468,33 @@ int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_in
     if(cu && n[0]) CK(cudaMemcpy(cu, j->b.cu_log, (size_t)n[0] * sizeof(xb200_cu_item), cudaMemcpyDeviceToHost));
     if(intra && n[1]) CK(cudaMemcpy(intra, j->b.intra_log, (size_t)n[1] * sizeof(xb200_intra_item), cudaMemcpyDeviceToHost));
     return XB200_OK;
+}
+
+double xb200_chain_span_ms(xb200_ctx *c, int reset)
+{
+    if(!c || !c->chain) return -1.0;
+    ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
+    const double v = k->span_ms;
+    if(reset) { k->span_on = false; k->span_ms = 0.f; }
+    return v;
+}
+
+/* debug builds (-DXB200_CHAIN_PROF): cycles [0..31] and counts [32..63] per phase of the decision kernel since the last call */
+int xb200_chain_prof(xb200_ctx *c, uint64_t out[64])
+{
+#ifdef XB200_CHAIN_PROF
+    if(!c || !out) return XB200_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    static unsigned long long z[64];
+    CK(cudaMemcpyFromSymbol(out, g_chain_prof, sizeof(z)));
+    CK(cudaMemcpyToSymbol(g_chain_prof, z, sizeof(z)));
+    return XB200_OK;
+#else
+    (void)c; (void)out;
+    return XB200_ERR_UNSUPPORTED;
+#endif
 }
 
 int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv)

@@ -25,6 +25,11 @@
 #include "xb200_had.cuh"
 
 #define CH_T 256
+#ifdef XB200_CHAIN_PROF
+#define CU_PROF_T(k) do { if(t == 0) { const long long now_ = clock64(); atomicAdd(&g_chain_prof[(k)], (unsigned long long)(now_ - g_prof_last)); atomicAdd(&g_chain_prof[32 + (k)], 1ull); g_prof_last = now_; } } while(0)
+#else
+#define CU_PROF_T(k) do { } while(0)
+#endif
 #define CH_MAX_COST (1.7e+308)
 enum { CH_SKIP = 0, CH_DIR = 1, CH_INTER = 2, CH_INTRA = 3 };
 
@@ -56,6 +61,7 @@ struct ChainPic {            // picture-level inputs of the kernel
     xb200_picture pp;
     int32_t  w, h, w_scu, h_scu, w_lcu, h_lcu, n_chain;
     int32_t  win_cap[4];     // search-window capacity (samples) per CU size 8 .. 64
+    int32_t  small_team;     // intra 4x4 (bit 0) / 8x8 (bit 1) CUs on a warp team instead of one thread (same results; tuning switch)
     PicDev   rec;            // the picture under reconstruction (PIC_MODE)
     uint32_t *map_scu;
     int8_t   *map_ipm, *map_refi;
@@ -410,6 +416,10 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
         }
         if(t == 32 || (t == 64 && B)) ch_mvp(P, cu, x, y, log2, t == 64);
         __syncthreads();
+        CU_PROF_T(10);
+#ifdef XB200_CHAIN_PROF
+        const long long prof_start = clock64();   // 18 .. 21: whole inter analysis by CU size (the phases 0 .. 8, 12 .. 14 lie inside)
+#endif
         const int cap = P.win_cap[log2 - 3];
         switch(log2) {
         case 3: ch_inter<3>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
@@ -418,6 +428,9 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
         default: ch_inter<6>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
         }
         __syncthreads();
+#ifdef XB200_CHAIN_PROF
+        if(t == 0) { atomicAdd(&g_chain_prof[15 + log2], (unsigned long long)(clock64() - prof_start)); atomicAdd(&g_chain_prof[32 + 15 + log2], 1ull); }
+#endif
         if(P.cu_log && P.n_chain == 1 && n_inter < P.cu_cap) ch_copy32(&P.cu_log[n_inter], &cu, (int)sizeof(xb200_cu_item) / 4, t);
         n_inter++;
         const int bi = cu.best_idx;
@@ -459,13 +472,20 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
         // the inter winner's reconstruction already sits in cu_data_temp; the intra trial works in its own buffers
         int16_t *coef_i = ws->coef + 3 * ny / 2 + 64, *rec_i = ws->rec_cu + 3 * ny / 2 + 64;
         switch(log2) {
-        case 2: ch_intra_thr<2>(pics, ws, L, coef_i, rec_i, sq, S, t); break;
-        case 3: ch_intra_thr<3>(pics, ws, L, coef_i, rec_i, sq, S, t); break;
+        case 2:
+            if(P.small_team & 1) ch_intra_team<2>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t);
+            else ch_intra_thr<2>(pics, ws, L, coef_i, rec_i, sq, S, t);
+            break;
+        case 3:
+            if(P.small_team & 2) ch_intra_team<3>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t);
+            else ch_intra_thr<3>(pics, ws, L, coef_i, rec_i, sq, S, t);
+            break;
         case 4: ch_intra_team<4>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
         case 5: ch_intra_team<5>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
         default: ch_intra_team<6>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
         }
         __syncthreads();
+        CU_PROF_T(9);
         if(P.intra_log && P.n_chain == 1 && n_intra < P.intra_cap) ch_copy32(&P.intra_log[n_intra], &it, (int)sizeof(xb200_intra_item) / 4, t);
         n_intra++;
         const double c = it.cost;
@@ -502,6 +522,9 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
     }
     if(t < 64) S.zinv8[zz_of(t, 3)] = (uint8_t)t;
     if(t == 0) { mbar_init(reinterpret_cast<uint64_t *>(team + CH_ME_OFF), 1); S.phase = 0; S.bits = 0; S.satd = 0; }
+#ifdef XB200_CHAIN_PROF
+    if(t == 0) g_prof_last = clock64();
+#endif
     // xeve_sbac_reset with cm_init off: every model PROB_INIT, range 16384
     if(t < XB200_CM_COUNT) ws->chain.s.m[t] = 512;
     if(t == XB200_CM_COUNT) { ws->chain.s.range = 16384; ws->chain.ipm[0] = ws->chain.ipm[1] = ws->chain.split = 512; ws->chain.pad_ = 0; }

@@ -26,6 +26,9 @@
 #include "xb200_common.cuh"
 
 #define ME_THREADS 128
+#ifndef CU_PROF
+#define CU_PROF(k) do { } while(0)
+#endif
 #define ME_MAX_CAND 160
 #ifndef ME_ISSUE_SINGLE
 #define ME_ISSUE_SINGLE 0
@@ -214,6 +217,7 @@ XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, 
 #endif
         mbar_wait(bar, phase);
         phase ^= 1;
+        { const int tt = tid; CU_PROF(22); }
         wn.x0 = ax0; wn.y0 = ny0; wn.pitch = pitch; wn.rows = rows; wn.staged = 1; wn.biased = 0;
     };
     auto set_bias = [&](int want) { // see the comment at the original-block load
@@ -361,6 +365,7 @@ XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, 
         best = c; mv_x = (int16_t)((bx - x) << 2); mv_y = (int16_t)((by - y) << 2);
         beststep = (abs(mvp_x - mv_x) < 2 && abs(mvp_y - mv_y) < 2) ? 0 : found;
     }
+    { const int tt = tid; CU_PROF(23); }
     while(bi != 1 && beststep > 0 && sq.me_complexity > 0) {
         set_range(x + (mv_x >> 2), y + (mv_y >> 2), 0);
         beststep = 0;
@@ -374,6 +379,7 @@ XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, 
         }
     }
 
+    { const int tt = tid; CU_PROF(24); }
     if(sq.me_level > 1) {
         // ---- me_spel_pattern: every candidate = 8-tap interpolation of the whole CU + SAD -----------
         int           smv_x = mv_x, smv_y = mv_y, sbits = 0;
@@ -483,6 +489,7 @@ XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, 
         if(rb < best) { best = rb; mv_x = (int16_t)((rx - x) << 2); mv_y = (int16_t)((ry - y) << 2); }
     }
 
+    { const int tt = tid; CU_PROF(25); }
     o_mv_x = mv_x; o_mv_y = mv_y; o_cost = best; o_mot_bits = mot_bits_l;
     me_team_sync<T>(); // the team's shared area is free again
 }

@@ -73,22 +73,37 @@ class ClipEncoder:
             if poc in self.h_org:
                 self.hp.pic_upload_s16(self.h_org[poc], y, u, v)
 
-    def _enqueue_all(self):
+    def reset(self):
+        """before re-encoding the same plan with the same device pictures (every picture of the previous pass must have been fetched)"""
+        self.err = None
+        for ev in self.enqueued.values():
+            ev.clear()
+
+    def enqueue(self, k):
+        """enqueue the k-th picture of the plan (coding order); returns at once unless the device is full"""
         try:
-            for p in self.plan:
-                pp = np.asarray(p["pp"]).reshape(-1)[0]
-                poc = int(pp["poc"])
-                rec = picture_record(pp, p["df_pp"], self.h_org[poc], self.h_rec[poc], self.h_rec, deblock=int(p.get("deblock", 1)),
-                                     threads=self.threads)
-                self.hp.analyze_picture(rec)
-                self.enqueued[poc].set()
-        except Exception as e:  # noqa: BLE001 -- reported by fetch()
+            p = self.plan[k]
+            pp = np.asarray(p["pp"]).reshape(-1)[0]
+            poc = int(pp["poc"])
+            rec = picture_record(pp, p["df_pp"], self.h_org[poc], self.h_rec[poc], self.h_rec, deblock=int(p.get("deblock", 1)),
+                                 threads=self.threads)
+            self.hp.analyze_picture(rec)
+            self.enqueued[poc].set()
+        except Exception as e:  # noqa: BLE001 -- reported by fetch() / wait()
             self.err = e
             for ev in self.enqueued.values():
                 ev.set()
+            raise
+
+    def _enqueue_all(self):
+        try:
+            for k in range(len(self.plan)):
+                self.enqueue(k)
+        except Exception:  # noqa: BLE001 -- already recorded in self.err
+            pass
 
     def start(self, background=True):
-        self.t0 = time.perf_counter()
+        self.reset()
         if background:
             self.t_enqueue = threading.Thread(target=self._enqueue_all, daemon=True)
             self.t_enqueue.start()
@@ -98,10 +113,18 @@ class ClipEncoder:
                 raise self.err
 
     def fetch(self, poc, want_states=False):
+        """blocks until picture `poc` is decided: dict(scu, coef, states, cost, stat)"""
         self.enqueued[poc].wait()
         if self.err:
             raise self.err
         return self.hp.picture_fetch(self.h_rec[poc], want_states=want_states)
+
+    def wait(self, poc):
+        """blocks until picture `poc` is decided, filtered and border-expanded; the records are dropped -> its xb200_picture_stat"""
+        self.enqueued[poc].wait()
+        if self.err:
+            raise self.err
+        return self.hp.picture_wait(self.h_rec[poc])
 
     def reconstruction(self, poc):
         """deblocked picture `poc` (Y, U, V s16 active areas) from the device"""
@@ -110,5 +133,6 @@ class ClipEncoder:
     def close(self):
         if self.t_enqueue is not None:
             self.t_enqueue.join()
+            self.t_enqueue = None
         if self.own:
             self.hp.close()
