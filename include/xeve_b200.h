@@ -479,6 +479,9 @@ XB200_API int xb200_chain_capacity(xb200_ctx *c);
 /* Device time (ms, CUDA events) from the first picture enqueued after the last reset to the latest completion among the pictures
  * fetched since: the span of a batch of pictures that ran concurrently on the library's own streams.  reset != 0 starts a new batch. */
 XB200_API double xb200_chain_span_ms(xb200_ctx *c, int reset);
+/* Debug builds only (-DXB200_CHAIN_DEBUG, otherwise XB200_ERR_UNSUPPORTED): progress words of the decision kernel, kept in host-mapped
+ * memory so that they can be read while a kernel hangs.  Never blocks. */
+XB200_API int xb200_chain_debug(xb200_ctx *c, int32_t out[64]);
 /* Profiling builds only (-DXB200_CHAIN_PROF, otherwise XB200_ERR_UNSUPPORTED): SM cycles [0..31] and visit counts [32..63] per phase of
  * the decision kernel since the previous call (phase numbers: xb200_analyze.cuh / xb200_chain.cuh CU_PROF). */
 XB200_API int xb200_chain_prof(xb200_ctx *c, uint64_t out[64]);

@@ -27,14 +27,26 @@ from tracedata import rh  # noqa: E402
 def run(seq, pics, compare_oracle=False, threads=None, overlap=False, check=True):
     from xeve_b200 import api
     hp = api.Hotpath(seq)
+    if os.environ.get("XB200_WATCHDOG"):       # debug builds: report where the kernel is if it does not finish in time
+        import threading
+
+        def dog():
+            time.sleep(float(os.environ["XB200_WATCHDOG"]))
+            print("WATCHDOG: kernel progress words", hp.chain_debug(), flush=True)
+            os._exit(3)
+        threading.Thread(target=dog, daemon=True).start()
     enc = tracedata.DevicePictureEncoder(seq, hp, check=check, compare_oracle=compare_oracle, threads=threads)
     t0 = time.time()
-    if overlap:                      # enqueue everything, then collect: the library orders the pictures by their references
-        for pc in pics:
-            enc.enqueue(pc)
-        out = enc.collect()
-    else:
-        out = [enc.encode(pc) for pc in pics]
+    try:
+        if overlap:                      # enqueue everything, then collect: the library orders the pictures by their references
+            for pc in pics:
+                enc.enqueue(pc)
+            out = enc.collect()
+        else:
+            out = [enc.encode(pc) for pc in pics]
+    except Exception:
+        print("kernel progress words (debug builds):", hp.chain_debug(), flush=True)
+        raise
     sec = time.time() - t0
     launches = hp.launches
     prof = hp.chain_prof()

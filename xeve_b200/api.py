@@ -187,6 +187,7 @@ def load():
         L.xb200_picture_log.argtypes = [VP, C.c_int32, VP, VP, VP]
         L.xb200_chain_capacity.argtypes = [VP]
         L.xb200_chain_prof.argtypes = [VP, VP]
+        L.xb200_chain_debug.argtypes = [VP, VP]
         L.xb200_chain_span_ms.argtypes = [VP, C.c_int]
         L.xb200_chain_span_ms.restype = C.c_double
         _lib = L
@@ -198,7 +199,7 @@ EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
            "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr",
            "xb200_transform_main", "xb200_analyze_picture", "xb200_picture_fetch", "xb200_picture_maps", "xb200_picture_adopt",
-           "xb200_picture_log_enable", "xb200_picture_log", "xb200_chain_capacity", "xb200_chain_prof", "xb200_chain_span_ms"]
+           "xb200_picture_log_enable", "xb200_picture_log", "xb200_chain_capacity", "xb200_chain_prof", "xb200_chain_span_ms", "xb200_chain_debug"]
 
 
 def _p(a):
@@ -446,6 +447,11 @@ class Hotpath:
     def chain_span_ms(self, reset=False):
         """device time from the first enqueue after the last reset to the latest completion among the pictures fetched since"""
         return float(self.L.xb200_chain_span_ms(self.h, int(reset)))
+
+    def chain_debug(self):
+        """progress words of the decision kernel (debug builds only, else None); never blocks"""
+        out = np.zeros(64, np.int32)
+        return out if self.L.xb200_chain_debug(self.h, _p(out)) == OK else None
 
     def chain_prof(self):
         """(cycles[32], counts[32]) per phase of the decision kernel -- profiling builds only, else None"""

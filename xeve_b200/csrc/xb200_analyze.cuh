@@ -136,7 +136,8 @@ __device__ __noinline__ void cu_predict(const PicDev *__restrict__ pics, const x
 // per-team working set handed to the helpers
 template <int L2> struct CuTeam {
     CuHdr         *H;
-    unsigned char *me_area;        // me_team_bytes(): mbarrier at offset 0
+    unsigned char *me_area;        // me_team_bytes(): 16 reserved bytes, then the search working set
+    uint64_t      *bar;            // mbarrier of the search-window copies (initialised once by the kernel)
     int16_t       *pred, *aux, *blk, *org_bi;
     int32_t       *TB;
     const int8_t  *tm, *tmT;
@@ -267,7 +268,7 @@ __device__ __noinline__ uint32_t cu_me(const CuTeam<L2> &Tm, const PicDev *__res
     team_sync<T>();
     uint32_t cost;
     int      mb;
-    me_search<L2>(Tm.me_area, pics, &H.me, Tm.org_bi, sq, win_cap, err_flag, tt, phase, mv_x, mv_y, cost, mb);
+    me_search<L2>(Tm.me_area, Tm.bar, pics, &H.me, Tm.org_bi, sq, win_cap, err_flag, tt, phase, mv_x, mv_y, cost, mb);
     mot_bits[lidx] = mb;
     return cost;
 }
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(CuCfg<L2, TEAMS>::CTA) k_analyze_cu(const PicD
     Tm.H = reinterpret_cast<CuHdr *>(tb);
     Tm.org_bi = reinterpret_cast<int16_t *>(tb + Cf::HDR);
     Tm.me_area = tb + Cf::HDR + Cf::ORGBI;
+    Tm.bar = reinterpret_cast<uint64_t *>(Tm.me_area);
     Tm.pred = reinterpret_cast<int16_t *>(Tm.me_area + 16);   // the residue working set overlays the search window, not the mbarrier
     Tm.aux = Tm.pred + NP;
     Tm.blk = Tm.aux + NP;

@@ -15,6 +15,10 @@
 #include <map>
 #include <mutex>
 
+#ifdef XB200_CHAIN_DEBUG
+static volatile int *h_dbg_words;   // host view of the kernel's progress words (host-mapped memory)
+#endif
+
 namespace {
 
 constexpr int N_STREAMS = 16;
@@ -108,6 +112,17 @@ int chain_init(xb200_ctx *c)
         CK(cudaMemcpyToSymbol(g_scan, scan, sizeof(scan)));
         CK(cudaMemcpyToSymbol(g_entropy_bits, eb, sizeof(eb)));
     }
+#ifdef XB200_CHAIN_DEBUG
+    if(!h_dbg_words) {
+        int *hp = nullptr, *dp = nullptr;
+        CK(cudaHostAlloc(&hp, 64 * sizeof(int), cudaHostAllocMapped));
+        memset(hp, 0, 64 * sizeof(int));
+        CK(cudaHostGetDevicePointer(&dp, hp, 0));
+        h_dbg_words = hp;
+        volatile int *dv = dp;
+        CK(cudaMemcpyToSymbol(g_dbg, &dv, sizeof(dv)));
+    }
+#endif
     CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
     CK(cudaMemset(k->zero_mv, 0, k->f_scu * 8));
     if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
@@ -330,6 +345,10 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     }
     const size_t smem = chain_smem_bytes(P.win_cap);
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
+    {   // candidate modes of 8x8 / 16x16 CUs on three warps when their working sets fit (XB200_CHAIN_PAR=0: serial analysis, same results)
+        const char *e = getenv("XB200_CHAIN_PAR");
+        P.par_stride = (e && e[0] == '0') ? 0 : chain_par_stride(P.win_cap, smem);
+    }
     {
         const Pic &p = c->pics[pp->rec_pic];
         for(int q = 0; q < 3; q++) { P.rec.p[q] = p.buf[q] + (size_t)p.pad[q] * p.s[q] + p.pad[q]; P.rec.s[q] = p.s[q]; }
@@ -468,6 +487,20 @@ int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_in
     if(cu && n[0]) CK(cudaMemcpy(cu, j->b.cu_log, (size_t)n[0] * sizeof(xb200_cu_item), cudaMemcpyDeviceToHost));
     if(intra && n[1]) CK(cudaMemcpy(intra, j->b.intra_log, (size_t)n[1] * sizeof(xb200_intra_item), cudaMemcpyDeviceToHost));
     return XB200_OK;
+}
+
+/* debug builds (-DXB200_CHAIN_DEBUG): the kernel's progress words (host-mapped memory: readable while a kernel hangs) */
+int xb200_chain_debug(xb200_ctx *c, int32_t out[64])
+{
+#ifdef XB200_CHAIN_DEBUG
+    if(!c || !out) return XB200_ERR_INVALID_ARGUMENT;
+    if(!h_dbg_words) return XB200_ERR;
+    for(int i = 0; i < 64; i++) out[i] = h_dbg_words[i];
+    return XB200_OK;
+#else
+    (void)c; (void)out;
+    return XB200_ERR_UNSUPPORTED;
+#endif
 }
 
 double xb200_chain_span_ms(xb200_ctx *c, int reset)

@@ -21,6 +21,7 @@
 #pragma once
 #define XB200_DEVICE_FUNCS_ONLY
 #include "xb200_analyze.cuh"
+#include "xb200_analyze_par.cuh"
 #include "xb200_intra.cuh"
 #include "xb200_had.cuh"
 
@@ -61,6 +62,7 @@ struct ChainPic {            // picture-level inputs of the kernel
     xb200_picture pp;
     int32_t  w, h, w_scu, h_scu, w_lcu, h_lcu, n_chain;
     int32_t  win_cap[4];     // search-window capacity (samples) per CU size 8 .. 64
+    int32_t  par_stride;     // bytes between the three warps' regions of the parallel 8x8 / 16x16 inter analysis (0: serial analysis)
     int32_t  small_team;     // intra 4x4 (bit 0) / 8x8 (bit 1) CUs on a warp team instead of one thread (same results; tuning switch)
     PicDev   rec;            // the picture under reconstruction (PIC_MODE)
     uint32_t *map_scu;
@@ -81,6 +83,8 @@ struct ChainPic {            // picture-level inputs of the kernel
 };
 
 struct ChShared {            // control block in shared memory
+    uint64_t bar[4];         // search-window mbarriers: [0] serial analysis, [1..3] the three warps of the parallel small-CU analysis;
+    uint32_t bphase[4];      // initialised once per kernel, never overlaid by working sets, parities kept here between CUs
     uint32_t bits, phase;
     int32_t  satd;
     uint8_t  zinv8[64];
@@ -100,6 +104,15 @@ __host__ __device__ inline size_t chain_smem_bytes(const int32_t win_cap[4])
         if(rs > need) need = rs;
     }
     return CH_TEAM_OFF + CH_ME_OFF + ((need + 15) & ~(size_t)15);
+}
+// stride of the three regions of the parallel small-CU analysis if they fit into the team area of `smem` bytes, else 0
+__host__ __device__ inline int chain_par_stride(const int32_t win_cap[4], size_t smem)
+{
+    size_t r = cu_par_region_bytes<3>(win_cap[0]);
+    const size_t r4 = cu_par_region_bytes<4>(win_cap[1]);
+    if(r4 > r) r = r4;
+    r = (r + 127) & ~(size_t)127;
+    return CU_PAR_WARPS * r <= smem - CH_TEAM_OFF ? (int)r : 0;
 }
 
 // ---- small helpers, called by all CH_T threads -------------------------------------------------------------------------------------
@@ -354,17 +367,27 @@ __device__ __noinline__ void ch_inter(unsigned char *team, const int8_t *tm, con
         Tm.H       = reinterpret_cast<CuHdr *>(team);
         Tm.org_bi  = reinterpret_cast<int16_t *>(team + CH_HDR);
         Tm.me_area = team + CH_ME_OFF;
+        Tm.bar     = &S.bar[0];
         Tm.pred    = reinterpret_cast<int16_t *>(Tm.me_area + 16);
         Tm.aux     = Tm.pred + NP;
         Tm.blk     = Tm.aux + NP;
         Tm.TB      = reinterpret_cast<int32_t *>(Tm.blk + NY);
         Tm.tm = tm; Tm.tmT = tmT;
         Tm.scratch = ws->scratch;
-        uint32_t phase = S.phase;
+        uint32_t phase = S.bphase[0];
         analyze_cu_one<L2>(Tm, pics, &ws->cu, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->coef, ws->rec_cu, ws->pred_y, sq, win_cap, err_flag,
                            phase, t);
-        if(t == 0) S.phase = phase;
+        if(t == 0) S.bphase[0] = phase;
     }
+}
+// 8x8 / 16x16: the candidate modes of the CU on three warps (xb200_analyze_par.cuh); the regions overlay the whole team area
+template <int L2>
+__device__ __noinline__ void ch_inter_par(unsigned char *team, const int8_t *tm, const int8_t *tmT, const PicDev *__restrict__ pics, ChainWs *ws,
+                                          int L, const SeqDev &sq, int win_cap, int stride, int *err_flag, ChShared &S, int t)
+{
+    if(t < CU_PAR_WARPS * 32)
+        analyze_cu_par<L2>(team, stride, S.bar + 1, S.bphase + 1, tm, tmT, pics, &ws->cu, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->coef, ws->rec_cu,
+                           ws->pred_y, ws->scratch, sq, win_cap, err_flag, t);
 }
 template <int L2>
 __device__ __noinline__ void ch_intra_team(unsigned char *team, const int8_t *tm, const int8_t *tmT, const PicDev *__restrict__ pics, ChainWs *ws,
@@ -414,6 +437,7 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
                 cu.mv_dir[0][0] = cu.mv_dir[0][1] = cu.mv_dir[1][0] = cu.mv_dir[1][1] = 0;
             }
         }
+        if(t == 0) { CH_DBG(0, x); CH_DBG(1, y); CH_DBG(2, log2); CH_DBG(3, (int)n_inter); }
         if(t == 32 || (t == 64 && B)) ch_mvp(P, cu, x, y, log2, t == 64);
         __syncthreads();
         CU_PROF_T(10);
@@ -422,8 +446,14 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
 #endif
         const int cap = P.win_cap[log2 - 3];
         switch(log2) {
-        case 3: ch_inter<3>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
-        case 4: ch_inter<4>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
+        case 3:
+            if(P.par_stride) ch_inter_par<3>(team, tm, tmT, pics, ws, L, sq, cap, P.par_stride, err_flag, S, t);
+            else ch_inter<3>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t);
+            break;
+        case 4:
+            if(P.par_stride) ch_inter_par<4>(team, tm, tmT, pics, ws, L, sq, cap, P.par_stride, err_flag, S, t);
+            else ch_inter<4>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t);
+            break;
         case 5: ch_inter<5>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
         default: ch_inter<6>(team, tm, tmT, pics, ws, L, sq, cap, err_flag, S, t); break;
         }
@@ -521,7 +551,8 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
         tmT[(e & 63) * 64 + (e >> 6)] = v;
     }
     if(t < 64) S.zinv8[zz_of(t, 3)] = (uint8_t)t;
-    if(t == 0) { mbar_init(reinterpret_cast<uint64_t *>(team + CH_ME_OFF), 1); S.phase = 0; S.bits = 0; S.satd = 0; }
+    if(t < 4) { mbar_init(&S.bar[t], 1); S.bphase[t] = 0; }
+    if(t == 0) { S.phase = 0; S.bits = 0; S.satd = 0; }
 #ifdef XB200_CHAIN_PROF
     if(t == 0) g_prof_last = clock64();
 #endif

@@ -57,6 +57,14 @@ template <int T> XB_DEV void team_bar()
     else asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
 }
 
+// Debug builds (-DXB200_CHAIN_DEBUG): progress words in host-mapped memory, readable by the host while a kernel hangs
+#ifdef XB200_CHAIN_DEBUG
+XB200_CONST_LINKAGE __device__ volatile int *g_dbg;
+#define CH_DBG(slot, val) do { if(g_dbg) g_dbg[(slot)] = (val); } while(0)
+#else
+#define CH_DBG(slot, val) do { } while(0)
+#endif
+
 XB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP) -----------------------------------
@@ -71,6 +79,17 @@ XB_DEV void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 }
 XB_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#ifdef XB200_CHAIN_DEBUG
+    {   // bounded wait: a copy that never completes becomes a trap with the barrier address in the debug words
+        const long long t0 = clock64();
+        uint32_t done = 0;
+        while(!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            if(!done && clock64() - t0 > 4000000000ll) { CH_DBG(60, (int)smem_u32(bar)); CH_DBG(61, (int)parity); CH_DBG(62, (int)threadIdx.x); __threadfence_system(); __trap(); }
+        }
+        return;
+    }
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"

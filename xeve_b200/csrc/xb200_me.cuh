@@ -114,17 +114,17 @@ XB_DEV void me_d16(int c, int &dx, int &dy) // (-4,0) (-3,1) .. (0,4) .. (4,0) .
     dy = c <= 4 ? c : (c <= 12 ? 8 - c : c - 16);
 }
 
-// One pi->fn_me call by one team.  smem_raw: the team's me_team_bytes() area with the mbarrier at offset 0 already
-// initialised (count 1); `phase` is the barrier's parity and persists across calls of the same team.  Results are
-// uniform across the team's threads.
+// One pi->fn_me call by one team.  smem_raw: the team's me_team_bytes() area (its first 16 bytes are reserved: the batched kernels
+// keep the mbarrier there); bar: the mbarrier the window copies complete on, initialised once (count 1) and never re-initialised --
+// re-initialising a live mbarrier object is undefined (PTX mbarrier.init) and hangs the copy engine in practice; `phase` is its
+// parity and persists across calls.  Results are uniform across the team's threads.
 template <int L2>
-XB_DEV void me_search(unsigned char *smem_raw, const PicDev *__restrict__ pics, const xb200_me_item *__restrict__ it,
+XB_DEV void me_search(unsigned char *smem_raw, uint64_t *bar, const PicDev *__restrict__ pics, const xb200_me_item *__restrict__ it,
                       const int16_t *__restrict__ side, const SeqDev &sq, int win_cap_elems, int *__restrict__ err_flag, int tid,
                       uint32_t &phase, int &o_mv_x, int &o_mv_y, uint32_t &o_cost, int &o_mot_bits)
 {
     using Gm = MeGeom<L2>;
     constexpr int W = Gm::W, T = Gm::T, G = Gm::G;
-    uint64_t *bar   = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *costs = reinterpret_cast<uint32_t *>(smem_raw + 16);                       // cost table of the current run
     int32_t  *red   = reinterpret_cast<int32_t *>(smem_raw + 16 + ME_MAX_CAND * 4);      // 8 ints
     int16_t  *org   = reinterpret_cast<int16_t *>(smem_raw + 16 + ME_MAX_CAND * 4 + 32);
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(MeGeom<L2>::CTA) k_me(const PicDev *__restrict
     uint32_t phase = 0, best;
     int      mv_x, mv_y, mot_bits_l;
     const int lidx = it->lidx, other_bits = it->mot_bits_in[lidx ? 0 : 1];
-    me_search<L2>(smem_raw, pics, it, side, sq, win_cap_elems, err_flag, tid, phase, mv_x, mv_y, best, mot_bits_l);
+    me_search<L2>(smem_raw, reinterpret_cast<uint64_t *>(smem_raw), pics, it, side, sq, win_cap_elems, err_flag, tid, phase, mv_x, mv_y, best, mot_bits_l);
     if(tid == 0) {
         it->mv_out[0] = (int16_t)mv_x; it->mv_out[1] = (int16_t)mv_y; it->cost = best;
         it->mot_bits_out[lidx] = mot_bits_l;
