@@ -10,6 +10,7 @@ unmodified reference (its own entropy coder writes the bitstream): the bitstream
   --oracle      also compare EVERY CU analysis (inputs and results, in call order) with the oracle chain: first difference is reported
   --more        further live configurations (10-bit medium, low QP, plain quantiser, CIF)
   --fixture-only
+  --config clip:preset:frames:threads[:extra][,...]   live runs of full-size clips (e.g. 1080p:fast:3:8)
 """
 import os
 import sys
@@ -80,15 +81,22 @@ MORE = [("2160p10", "medium", 5, "", 1, dict(w=256, h=192, squares=[(48, 60, 40,
 
 def main():
     oracle = "--oracle" in sys.argv
-    seq, pics = tracedata.chain_golden()
-    out, launches, sec = run(seq, pics, compare_oracle=oracle)
-    n_cu, ms = summary(out)
-    print(f"fixture: {len(out)} pictures, {n_cu} CU analyses in {launches} kernel launches, chain kernels {ms:.1f} ms "
-          f"({1e3 * ms / max(n_cu, 1):.0f} us per CU decision): states, maps, leaf CUs and pictures equal the reference's", flush=True)
+    if "--config" not in sys.argv:
+        seq, pics = tracedata.chain_golden()
+        out, launches, sec = run(seq, pics, compare_oracle=oracle)
+        n_cu, ms = summary(out)
+        print(f"fixture: {len(out)} pictures, {n_cu} CU analyses in {launches} kernel launches, chain kernels {ms:.1f} ms "
+              f"({1e3 * ms / max(n_cu, 1):.0f} us per CU decision): states, maps, leaf CUs and pictures equal the reference's", flush=True)
     if "--fixture-only" in sys.argv or not rh.available():
         print("PICTURE_ON_DEVICE_OK")
         return
-    for name, preset, frames, extra, threads, override in (MORE if "--more" in sys.argv else DEFAULT):
+    configs = MORE if "--more" in sys.argv else DEFAULT
+    if "--config" in sys.argv:           # --config clip:preset:frames:threads[:extra]  (full-size clips of xeve_b200/clips.py)
+        configs = []
+        for a in sys.argv[sys.argv.index("--config") + 1].split(","):
+            f = a.split(":")
+            configs.append((f[0], f[1], int(f[2]), f[4] if len(f) > 4 else "", int(f[3]), {}))
+    for name, preset, frames, extra, threads, override in configs:
         c, yuv = tracedata.clip_yuv(name, frames, **override)
         tr = rh.encode_clip(yuv, frames, c.w, c.h, in_depth=c.depth, preset=preset, extra=extra, threads=threads,
                             trace_mask=rh.TRACE_LCU | rh.TRACE_DF, pic_lo=0, pic_hi=1 << 20)
