@@ -5,22 +5,23 @@ A "step" = S independent streams x F pictures of the workload's synthetic clip (
 default hierarchical-B GOP, CQP 32), each stream encoded from its original pictures to the MPEG-5 EVC bitstream:
 
   device : xb200_analyze_picture per picture -- ONE persistent kernel runs the CTU loop, the quad-tree mode decision with every inter /
-           intra CU analysis, then the loop filter and the border expansion; pictures of all streams are enqueued at once and ordered by
-           events on their reference pictures (the picture DAG), no host round trip per CU or CTU;
-  host   : the reference's own control plane (picture plan: slice types, QPs, lambdas, reference lists) and its own entropy coder /
-           bitstream writer, reached through the compiled hook harness (oracle/_ref/libref_harness.so: ctx->fn_mode_analyze_frame hands
-           each decided picture over, ctx->fn_mode_analyze_lcu copies the CTU records).  north_star keeps both on the host.  No decision
-           is made there: the harness's counters of reference inter / intra analyses must stay 0.
+           intra CU analysis, then the loop filter and the border expansion; the pictures of all streams that can be coded from the
+           frames pushed so far are in flight together, ordered by events on their reference pictures (the picture DAG);
+  host   : the reference's own control plane, entropy coder and bitstream writer (north_star keeps them on the host), linked with the
+           hook file integration/xeve_b200_dropin.c into the drop-in library oracle/_ref/libxeve_b200_dropin.so.  No decision is made
+           there.
 
 Parity mode: `--threads T` = the reference's `threads` parameter.  Each picture is decided as T coder-state chains (CTU rows y, y + T, ..)
 exactly like the reference's worker threads, so the bitstream equals `xeveb_app -m T` byte for byte; T = 1 is the single-thread
 bitstream.  The md5 of every stream's bitstream is compared with the unmodified reference's inside the run.
 
-  value : pictures/s over all streams with the original pictures already resident in HBM (decision pass + loop filter only)
-  e2e   : the same streams from HOST buffers to the bitstream: H2D of every original picture, D2H of every picture's records, entropy
-          coding by the reference's host code (one host thread per stream), md5 check
-  --impl reference : the unmodified reference (oracle/_ref) on all usable host cores: floor(cores / T) concurrent instances with T
-          threads each, same clip, same frames, "frames / wall time inside xeve_encode" per instance like app/xeve_app.c:1397-1402
+  value : pictures/s over all streams with the original pictures already resident in HBM (decision pass + loop filter only, records
+          stay on the device; driven through the C ABI of libxeve_b200.so)
+  e2e   : the same streams through the PUBLIC API -- xeve_create / xeve_push / xeve_encode of the drop-in library, one host thread per
+          stream in one process (integration/xb200_streams.c, an application-level program): frames from host memory (H2D inside
+          xeve_push), records back (D2H), entropy coding by the reference's host code, bitstream written, md5 checked
+  --impl reference : THE SAME PROGRAM linked against the unmodified reference library (oracle/_ref/xeveb_streams_ref) on the host cores:
+          floor(cores / T) concurrent streams with T threads each -- a bounded sample of the S-stream workload
 """
 from __future__ import annotations
 
@@ -113,54 +114,48 @@ def workload_string(args, c, preset):
             f"(bitstream == reference -m {args.threads})")
 
 
+# ---- the application-level program (integration/xb200_streams.c) against either library ------------------------------------------------
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def run_streams(binary, path, c, preset, frames, streams, threads, passes, out_prefix, env=None):
+    """-> list of per-pass dicts (the program's JSON lines)"""
+    cmd = [os.path.join(REFDIR, binary), "-i", path, "-w", str(c.w), "-h", str(c.h), "-d", str(c.depth), "-z", str(frames), "-n", str(streams),
+           "-m", str(threads), "--preset", preset, "-r", str(passes), "-o", out_prefix]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} failed ({r.returncode}): {r.stdout[-1500:]} {r.stderr[-1500:]}")
+    return [json.loads(line) for line in r.stdout.strip().splitlines() if line.startswith("{")]
+
+
+def stream_md5s(prefix, n):
+    out = []
+    for k in range(n):
+        with open(f"{prefix}.{k}.evc", "rb") as f:
+            out.append(hashlib.md5(f.read()).hexdigest())
+        os.unlink(f"{prefix}.{k}.evc")
+    return out
+
+
 # ---- reference arm: the unmodified reference on the host cores ----------------------------------------------------------------------------
-def _ref_worker(job):
-    path, nframes, w, h, depth, preset, threads = job
-    sys.path.insert(0, ROOT)
-    from oracle import refharness as rh
-    yuv = np.fromfile(path, np.uint8)
-    tr = rh.encode_clip(yuv, nframes, w, h, in_depth=depth, preset=preset, threads=threads)
-    return tr.enc_seconds, hashlib.md5(tr.bitstream.tobytes()).hexdigest(), len(tr.bitstream)
-
-
-def reference_step(path, args, c, preset, n_inst):
-    """n_inst concurrent instances of the unmodified reference, `threads` threads each, one stream each -> (wall s, [(sec, md5, bytes)])"""
-    import multiprocessing as mp
-    jobs = [(path, args.frames, c.w, c.h, c.depth, preset, args.threads)] * n_inst
-    t0 = time.perf_counter()
-    if n_inst == 1:
-        res = [_ref_worker(jobs[0])]
-    else:
-        with mp.get_context("spawn").Pool(n_inst) as pool:
-            res = pool.map(_ref_worker, jobs)
-    return time.perf_counter() - t0, res
-
-
 def run_reference(args, steps, warmup, clip=None, quiet=False):
-    from oracle import refharness as rh
-    if not rh.available():
+    if not os.path.exists(os.path.join(REFDIR, "xeveb_streams_ref")):
         return {"impl": "reference", "unavailable": "oracle/_ref is not built"}
     c, preset, frames, yuv = clip or make_clip(args)
     cores = usable_cores()
-    n_inst = max(1, min(cores // max(args.threads, 1), 16))
-    path = f"/dev/shm/xb200_bench_{os.getpid()}.yuv"
+    n_inst = max(1, min(cores // max(args.threads, 1), args.streams, 16))
+    path = f"/dev/shm/xb200_bench_ref_{os.getpid()}.yuv"
     yuv.tofile(path)
     try:
-        times, md5s = [], set()
-        for it in range(warmup + steps):
-            wall, res = reference_step(path, args, c, preset, n_inst)
-            # each instance's fps is frames / time inside xeve_encode; concurrent instances: the step's throughput is over the slowest
-            enc = max(r[0] for r in res)
-            md5s |= {r[1] for r in res}
-            if it >= warmup:
-                times.append(enc)
+        passes = run_streams("xeveb_streams_ref", path, c, preset, args.frames, n_inst, args.threads, warmup + steps, path)
+        md5s = set(stream_md5s(path, n_inst))
     finally:
         os.unlink(path)
-    sec = float(np.mean(times))
+    sec = float(np.mean([p["wall_s"] for p in passes[warmup:]]))
     value = n_inst * args.frames / sec
-    sample = (f"{n_inst} concurrent instance(s) x {args.threads} threads, {args.frames} pictures each per step (bounded sample of the "
-              f"{args.streams}-stream workload: the reference's streams are independent), {steps} step(s) after {warmup} warm-up; "
-              f"time = inside xeve_encode, slowest instance")
+    sample = (f"{n_inst} concurrent stream(s) x {args.threads} threads of the unmodified reference library, {args.frames} pictures each per step "
+              f"(bounded sample of the {args.streams}-stream workload: the streams are independent), {steps} step(s) after {warmup} warm-up; "
+              f"time = wall time of the whole job (first push to last byte), same program as the device arm")
     cb = {"value": round(value, 3), "unit": "pictures/s", "cores": n_inst * args.threads, "kind": "reference", "sample": sample,
           "usable_cores": cores, "md5": sorted(md5s)[0], "md5_unique": len(md5s) == 1}
     return {"impl": "reference", "metric": "encoded pictures/s", "value": round(value, 3), "unit": "pictures/s", "n_gpus": args.gpus,
@@ -195,7 +190,7 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
     def pin(a):
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     host_frames = {n: tuple(pin(p) for p in frames[n]) for n in range(F)}     # pinned host copies of the original pictures
-    h2d = S * sum(p.nbytes for f in host_frames.values() for p in f)
+    h2d = S * F * (c.w * c.h * 3 // 2) * 2      # xeve_push: the picture as the reference stored it (internal 10-bit, s16) goes to the device
     d2h = S * F * hp.n_lcu * (256 * api.SCU_REC.itemsize + 6144 * 2)
 
     def upload_all():
@@ -220,30 +215,14 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
                 chain_ms.append(float(st["chain_ms"]))
                 n_cu[0] += int(st["n_inter"]); n_cu[1] += int(st["n_intra"])
 
-    bitstreams = [None] * S
+    # e2e: the public API.  One process, one host thread per stream (integration/xb200_streams.c linked against the drop-in library)
+    clip_path = f"/dev/shm/xb200_bench_{os.getpid()}_{rank}.yuv"
+    yuv.tofile(clip_path)
+    env = dict(os.environ, XB200_DEVICE=str(dev), XB200_QUIET="1")
 
-    def step_e2e():
-        """host buffers -> bitstream: H2D of the originals, device decision pass, D2H of the records, host entropy coding"""
-        upload_all()
-        th = threading.Thread(target=enqueue_all, daemon=True)
-        th.start()
-        errs = []
-
-        def entropy(i):
-            try:
-                tr, n = rh.encode_clip_lazy(yuv, F, c.w, c.h, encs[i].fetch, in_depth=c.depth, preset=preset, label_threads=T)
-                assert n == F * hp.n_lcu
-                bitstreams[i] = tr.bitstream
-            except Exception as e:  # noqa: BLE001
-                errs.append(e)
-        ts = [threading.Thread(target=entropy, args=(i,), daemon=True) for i in range(S)]
-        for t_ in ts:
-            t_.start()
-        for t_ in ts:
-            t_.join()
-        th.join()
-        if errs:
-            raise errs[0]
+    def step_e2e(passes):
+        res = run_streams("xb200_streams", clip_path, c, preset, F, S, T, passes, clip_path, env=env)
+        return res, stream_md5s(clip_path, S)
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,18 +246,20 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
     barrier()
     sec = time.perf_counter() - t0
     launches = hp.launches - launches0
-    # e2e: one warm-up, then the timed steps
-    step_e2e()
+    # e2e: one warm-up pass, then the timed passes (each pass = the whole job, encoders created anew; the program times a pass from the
+    # first push to the last bitstream byte).  The Python process keeps its device context but launches nothing meanwhile.
     barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    try:
+        e2e_passes, md5s = step_e2e(1 + args.steps)
+    finally:
+        os.unlink(clip_path)
     barrier()
-    sec_e2e = time.perf_counter() - t1
+    e2e_passes = e2e_passes[1:]
+    sec_e2e = float(np.sum([p["wall_s"] for p in e2e_passes]))
     sampler.stop_flag = True
     sampler.join()
-    md5s = sorted({hashlib.md5(b.tobytes()).hexdigest() for b in bitstreams})
-    ok = ref_md5 is not None and md5s == [ref_md5]
+    md5s = sorted(set(md5s))
+    ok = ref_md5 is not None and md5s == [ref_md5] and all(st["err"] == 0 and st["device_pictures"] == F for p in e2e_passes for st in p["per_stream"])
     if dist is not None:
         tt = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -309,10 +290,14 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         "vs_baseline": None, "dtype": "s16", "data": "synthetic",
         "config": {"workload": workload_string(args, c, preset), "streams_per_gpu": S, "pictures_per_stream": F, "threads": T,
                    "l2": f"inputs larger than L2 ({h2d / 2**20:.0f} MiB of original pictures per step)",
-                   "host_side": "reference control plane + entropy coder through oracle/_ref/libref_harness.so (decisions: 0 on the host)"},
+                   "host_side": "reference control plane + entropy coder (no decision on the host); value: picture plan from the control plane run dry, "
+                                "e2e: the drop-in library's hooks inside the reference's own xeve_encode"},
         "e2e": {"value": round(e2e, 3), "unit": "pictures/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(1e3 * sec_e2e / args.steps, 2), "bitstream_md5": md5s, "reference_md5": ref_md5, "bitstream_matches_reference": ok,
-                "bitstream_bytes_per_stream": int(len(bitstreams[0]))},
+                "bitstream_bytes_per_stream": int(e2e_passes[-1]["per_stream"][0]["bytes"]),
+                "api": "xeve_create / xeve_push / xeve_encode of oracle/_ref/libxeve_b200_dropin.so, one host thread per stream (xb200_streams)",
+                "host_wait_on_device_ms_per_stream": round(float(np.mean([st["wait_ms"] for p in e2e_passes for st in p["per_stream"]])), 1),
+                "push_ms_per_stream": round(1e3 * float(np.mean([st["push_s"] for p in e2e_passes for st in p["per_stream"]])), 1)},
         "gpu_launches": int(launches),
         "device_span_ms_per_step": round(float(np.mean(spans)), 2),
         "chain": {"capacity_chains": capacity, "chains_per_picture": min(T, (c.h + 63) // 64), "kernel_ms_per_picture": round(mean_ms, 2),
@@ -339,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=4, help="independent streams per GPU per step")
+    ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
     ap.add_argument("--frames", type=int, default=17, help="pictures per stream (17 = the intra picture + one GOP of 16)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
     args = ap.parse_args()

@@ -49,8 +49,20 @@ struct Job {
     JobBufs b;
     int     rec_pic = -1;
     double  share = 0.0;    // SM share its chains occupy: n_chain / resident CTAs per SM
-    bool    retired = false;
+    bool    retired = false, dense = false;
 };
+// Chains of ALL contexts of a process share the device: a picture is admitted when its chains fit next to the ones already resident,
+// whoever enqueued them (several encoder instances in one process, integration/xb200_streams.c).  Per device, guarded by its own mutex.
+struct DeviceLoad {
+    std::mutex        mu;
+    std::deque<Job *> inflight;         // admission order, all contexts
+    double            load = 0.0;       // sum of the shares of the admitted, unretired pictures
+    int               n_ctx = 0;        // contexts with a decision pass on this device
+    int               dense_jobs = 0, sparse_jobs = 0;   // unretired pictures launched two / one chain(s) per SM
+    std::vector<cudaEvent_t> graveyard; // events of torn-down contexts: another context may still be waiting on one (never destroyed)
+};
+DeviceLoad g_dev_load[64];
+
 struct ChainCtx {
     std::mutex   mu;                    // host-side bookkeeping: one thread may enqueue pictures while another fetches results
     cudaStream_t streams[N_STREAMS] = {};
@@ -58,9 +70,7 @@ struct ChainCtx {
     int          next_stream = 0;
     std::vector<PicMaps> maps;
     std::map<int, Job *> jobs;          // by rec_pic
-    std::deque<Job *>    inflight;      // admission order
     std::vector<JobBufs> pool;
-    double       load = 0.0;            // sum of the shares of the admitted, unretired pictures
     int16_t     *zero_mv = nullptr;     // colocated map of a reference picture without one (all zero)
     long long    log_cu = 0, log_intra = 0;
     cudaEvent_t  ev_span0 = nullptr;    // device time span of a batch of pictures: first enqueue after a reset ...
@@ -128,6 +138,11 @@ int chain_init(xb200_ctx *c)
     if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
     CK(cudaDeviceSynchronize());
     k->ready = true;
+    {
+        DeviceLoad &D = g_dev_load[c->device & 63];
+        std::lock_guard<std::mutex> dl(D.mu);
+        D.n_ctx++;
+    }
     return XB200_OK;
 }
 
@@ -179,37 +194,46 @@ int bufs_get(xb200_ctx *c, int n_chain, JobBufs *out)
     *out = b;
     return XB200_OK;
 }
-void bufs_free(JobBufs &b)
+void bufs_free(JobBufs &b, DeviceLoad &D)
 {
     for(void *p : {(void *)b.scu, (void *)b.coef, (void *)b.ctu_state, (void *)b.ctu_cost, (void *)b.done, (void *)b.counts, (void *)b.ws,
                    (void *)b.cu_log, (void *)b.intra_log})
         if(p) cudaFree(p);
-    if(b.ev0) { cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev1); cudaEventDestroy(b.ev2); }
+    if(b.ev0) { cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev2); D.graveyard.push_back(b.ev1); }
     b = JobBufs();
 }
 
-// retire finished pictures; with `need` > 0 wait (oldest first) until that much SM share is free.  Called with k->mu held; the
-// blocking wait happens with the lock released (only the enqueueing thread creates jobs, so the event stays meaningful).
-int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk)
+// retire finished pictures (of any context on this device); with `need` > 0 wait (oldest first) until that much SM share is free.
+// Called with k->mu held; the blocking wait happens with both locks released.  A job leaves the device list either here (its kernel
+// has finished) or in xb200_picture_fetch, always under the device mutex, so a listed job's event is alive while the mutex is held;
+// the event waited on outside the lock is a copy of the handle of a pooled (never destroyed before context teardown) event.
+int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk, double *load_out = nullptr, int *mode_out = nullptr)
 {
-    ChainCtx *k = cc_of(c);
+    DeviceLoad &D = g_dev_load[c->device & 63];
     for(;;) {
-        while(!k->inflight.empty()) {
-            Job *j = k->inflight.front();
-            if(!j->retired) {
-                const cudaError_t e = cudaEventQuery(j->b.ev1);
-                if(e == cudaErrorNotReady) break;
-                if(e != cudaSuccess) CK(e);
-                j->retired = true;
-                k->load -= j->share;
+        cudaEvent_t wait_on = nullptr;
+        {
+            std::lock_guard<std::mutex> dl(D.mu);
+            while(!D.inflight.empty()) {
+                Job *j = D.inflight.front();
+                if(!j->retired) {
+                    const cudaError_t e = cudaEventQuery(j->b.ev1);
+                    if(e == cudaErrorNotReady) break;
+                    if(e != cudaSuccess) CK(e);
+                    j->retired = true;
+                    D.load -= j->share;
+                    (j->dense ? D.dense_jobs : D.sparse_jobs)--;
+                }
+                D.inflight.pop_front();
             }
-            k->inflight.pop_front();
+            if(D.inflight.empty()) D.load = 0.0;
+            if(load_out) *load_out = D.load;
+            if(mode_out) *mode_out = D.dense_jobs > 0 ? 2 : (D.sparse_jobs > 0 ? 1 : (D.n_ctx > 1 ? 2 : 0));
+            if(need <= 0 || D.load + need <= (double)c->sms + 1e-9 || D.inflight.empty()) return XB200_OK;
+            wait_on = D.inflight.front()->b.ev1;
         }
-        if(k->inflight.empty()) k->load = 0.0;
-        if(need <= 0 || k->load + need <= (double)c->sms + 1e-9 || k->inflight.empty()) return XB200_OK;
-        cudaEvent_t e = k->inflight.front()->b.ev1;
         lk.unlock();
-        const cudaError_t er = cudaEventSynchronize(e);
+        const cudaError_t er = cudaEventSynchronize(wait_on);
         lk.lock();
         if(er != cudaSuccess) CK(er);
     }
@@ -231,8 +255,20 @@ void xb200_chain_free(xb200_ctx *c)
     if(!c || !c->chain) return;
     ChainCtx *k = cc_of(c);
     cudaDeviceSynchronize();
-    for(auto &kv : k->jobs) { bufs_free(kv.second->b); delete kv.second; }
-    for(auto &b : k->pool) bufs_free(b);
+    DeviceLoad &D = g_dev_load[c->device & 63];
+    {
+        std::lock_guard<std::mutex> dl(D.mu);
+        for(auto &kv : k->jobs) {
+            Job *j = kv.second;
+            if(!j->retired) { D.load -= j->share; (j->dense ? D.dense_jobs : D.sparse_jobs)--; }
+            for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
+                if(*q == j) { D.inflight.erase(q); break; }
+            bufs_free(j->b, D);
+            delete j;
+        }
+        for(auto &b : k->pool) bufs_free(b, D);
+        if(k->ready) D.n_ctx--;
+    }
     for(auto &m : k->maps) {
         for(void *p : {(void *)m.scu, (void *)m.ipm, (void *)m.refi, (void *)m.mv, (void *)m.flags})
             if(p) cudaFree(p);
@@ -343,7 +379,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
         const char *e = getenv("XB200_INTRA_SMALL_TEAM");
         P.small_team = e ? atoi(e) : 3;
     }
-    const size_t smem = chain_smem_bytes(P.win_cap);
+    const size_t smem = chain_smem_bytes(P.win_cap, pp->max_cu_intra, pp->slice_type == 2 ? 8 : pp->max_cu_inter);
     if(smem > 227 * 1024) return XB200_ERR_UNSUPPORTED;
     {   // candidate modes of 8x8 / 16x16 CUs on three warps when their working sets fit (XB200_CHAIN_PAR=0: serial analysis, same results)
         const char *e = getenv("XB200_CHAIN_PAR");
@@ -378,9 +414,14 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<2>, CH_T, smem));
     if(bps < 1) return XB200_ERR_UNSUPPORTED;
-    if((r = admit(c, 0.0, lk))) return r;               // retire what has finished
+    // Two kernels with different footprints must not share the device: a one-per-SM chain needs a whole free SM, which the accounting
+    // by shares cannot promise while two-per-SM chains are spread over the SMs.  So the mode of the pictures in flight is kept; an idle
+    // device picks one chain per SM for a lone context whose chains fit, two per SM otherwise (several contexts: always two).
+    double dev_load = 0.0;
+    int    dev_mode = 0;
+    if((r = admit(c, 0.0, lk, &dev_load, &dev_mode))) return r;     // retire what has finished
     const char *dense_env = getenv("XB200_CHAIN_DENSE"); // 0: always one chain per SM, 1: always two
-    const bool dense = bps >= 2 && (dense_env ? dense_env[0] == '1' : k->load + (double)P.n_chain > (double)c->sms);
+    const bool dense = bps >= 2 && (dense_env ? dense_env[0] == '1' : dev_mode ? dev_mode == 2 : dev_load + (double)P.n_chain > (double)c->sms);
     if(!dense) bps = 1;
     const double share = (double)P.n_chain / bps;
     if(share > c->sms) return XB200_ERR_UNSUPPORTED;
@@ -388,7 +429,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
 
     Job *j = new Job();
     if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
-    j->rec_pic = pp->rec_pic; j->share = share;
+    j->rec_pic = pp->rec_pic; j->share = share; j->dense = dense;
     P.scu_out = j->b.scu; P.coef_out = j->b.coef; P.ctu_state = j->b.ctu_state; P.ctu_cost = j->b.ctu_cost; P.done = j->b.done;
     P.counts = j->b.counts; P.ws = j->b.ws;
     if(k->log_cu > 0) { P.cu_log = j->b.cu_log; P.cu_cap = k->log_cu; }
@@ -416,8 +457,13 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     CK(cudaEventRecord(m->ready, s));
     m->has_ready = true;
     k->jobs[pp->rec_pic] = j;
-    k->inflight.push_back(j);
-    k->load += share;
+    {
+        DeviceLoad &D = g_dev_load[c->device & 63];
+        std::lock_guard<std::mutex> dl(D.mu);
+        D.inflight.push_back(j);
+        D.load += share;
+        (dense ? D.dense_jobs : D.sparse_jobs)++;
+    }
     return XB200_OK;
 }
 
@@ -460,9 +506,13 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
         float sp = 0.f;
         if(cudaEventElapsedTime(&sp, k->ev_span0, j->b.ev2) == cudaSuccess && sp > k->span_ms) k->span_ms = sp;
     }
-    if(!j->retired) { j->retired = true; k->load -= j->share; }
-    for(auto q = k->inflight.begin(); q != k->inflight.end(); ++q)
-        if(*q == j) { k->inflight.erase(q); break; }
+    {
+        DeviceLoad &D = g_dev_load[c->device & 63];
+        std::lock_guard<std::mutex> dl(D.mu);
+        if(!j->retired) { j->retired = true; D.load -= j->share; (j->dense ? D.dense_jobs : D.sparse_jobs)--; }
+        for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
+            if(*q == j) { D.inflight.erase(q); break; }
+    }
     k->pool.push_back(j->b);
     k->jobs.erase(it);
     delete j;

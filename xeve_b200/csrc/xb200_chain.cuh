@@ -94,10 +94,12 @@ constexpr int CH_HDR  = ((int)sizeof(CuHdr) + 15) & ~15;
 constexpr int CH_CTL  = ((int)sizeof(ChShared) + 15) & ~15;
 constexpr int CH_TEAM_OFF = 8192 + CH_CTL;           // tm | tmT | control | team area
 constexpr int CH_ME_OFF   = CH_HDR + 8192;           // team area: CuHdr | org_bi (64x64) | mbarrier + working set
-__host__ __device__ inline size_t chain_smem_bytes(const int32_t win_cap[4])
+// max_cu: largest CU the picture can contain (intra teams are sized by max_cu_intra, the inter working sets by max_cu_inter): presets
+// fast / medium never try a 64x64 intra CU, whose team is the largest working set of all
+__host__ __device__ inline size_t chain_smem_bytes(const int32_t win_cap[4], int max_cu_intra = 64, int max_cu_inter = 64)
 {
-    size_t need = 16 + sizeof(IntraTeam<6>);
-    for(int l2 = 3; l2 <= 6; l2++) {
+    size_t need = 16 + (max_cu_intra >= 64 ? sizeof(IntraTeam<6>) : max_cu_intra >= 32 ? sizeof(IntraTeam<5>) : sizeof(IntraTeam<4>));
+    for(int l2 = 3; l2 <= 6 && (1 << l2) <= max_cu_inter; l2++) {
         const size_t me = me_team_bytes(l2, win_cap[l2 - 3]);
         const size_t rs = 16 + (size_t)(l2 == 3 ? Res2Cfg<3>::TEAM_BYTES : l2 == 4 ? Res2Cfg<4>::TEAM_BYTES : l2 == 5 ? Res2Cfg<5>::TEAM_BYTES : Res2Cfg<6>::TEAM_BYTES);
         if(me > need) need = me;
