@@ -143,7 +143,10 @@ typedef struct {
 
 /* Fused residue work item = the distortion/transform body of pinter_residue_rdo for one
  * candidate mode of one CU.  Outputs are written to per-item slots of size 3/2*cuw*cuh at
- * element offset out_off in each of the coef / rec buffers. */
+ * element offset out_off in each of the coef / rec buffers.
+ * Preconditions (checked on the device for host-buffer calls, XB200_ERR_INVALID_ARGUMENT otherwise): the CU (mc.x, mc.y, mc.w, mc.h)
+ * lies inside the current picture, out_off is even and out_off + 3/2 w h fits the buffers, rate_idx < n_rates, valid picture handles
+ * (reference pictures padded).  xb200_me likewise requires the CU inside the current picture and 1 <= max_search_range <= 256. */
 typedef struct {
     xb200_mc_item mc;              /* prediction to build (x, y, w, h, refi, mv, refs) */
     int32_t  cur_pic;              /* picture handle of the original picture */

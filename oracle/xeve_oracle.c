@@ -17,7 +17,7 @@
  * first strict minimum", RDOQ as a two-pass scan.
  */
 #include "xeve_oracle.h"
-#include "../xeve_b200/csrc/xb200_tables.h"
+#include "xo_tables.h"   /* the oracle's own constants: nothing here includes product code */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,8 +29,8 @@ static int      g_init;
 static void oracle_init(void)
 {
     if(g_init) return;
-    xb200_gen_tm64(g_tm64);
-    for(int l = 1; l <= 6; l++) xb200_gen_scan(g_scan[l], l, l);
+    xo_gen_tm64(g_tm64);
+    for(int l = 1; l <= 6; l++) xo_gen_scan(g_scan[l], l, l);
     g_init = 1;
 }
 static inline int tm(int log2n, int k, int n) { return g_tm64[(k << (6 - log2n)) * 64 + n]; }
@@ -113,8 +113,8 @@ int xo_satd(int w, int h, const int16_t *a, int sa, const int16_t *b, int sb, in
 /* ---------------------------------------------------------------------------------------------
  * motion compensation
  * ------------------------------------------------------------------------------------------- */
-static const int16_t k_luma[4][8]   = XB200_MC_L_TAPS;
-static const int16_t k_chroma[8][4] = XB200_MC_C_TAPS;
+#define k_luma xo_mc_l_taps
+#define k_chroma xo_mc_c_taps
 
 /* Generic separable interpolation, `taps` taps (8 luma / 4 chroma).
  * 1-D cases: sum >> 6 with no rounding offset (src_base/xeve_mc.h:36-48, xeve_mc.c:122-182);
@@ -411,7 +411,7 @@ int xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intr
                   const xb200_rates *rt, int bd)
 {
     oracle_init();
-    static const int qs[6] = XB200_QUANT_SCALE;
+    const int *qs = xo_quant_scale;
     const int        n = 1 << (2 * log2n), q = qs[qp % 6];
     const int        qbits = 14 + (15 - bd - log2n) + qp / 6;
     /* zero-block pre-test, src_base/xeve_tq.c:666-700 (slice_type: 2 == SLICE_I in the reference) */
@@ -422,7 +422,7 @@ int xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intr
         if(!coded) { memset(coef, 0, sizeof(int16_t) * n); return 0; }
     }
     const uint16_t *scan = g_scan[log2n];
-    const int64_t   es = xb200_err_scale(qp % 6, log2n, bd);
+    const int64_t   es = xo_err_scale(qp % 6, log2n, bd);
     rate_env        e  = {rt, ch == 0 ? 0 : 2, (int64_t)(d_lambda * 32768.0 + 0.5)};
     int64_t *ld   = malloc(sizeof(int64_t) * n);
     int32_t *maxl = malloc(sizeof(int32_t) * n);
@@ -480,7 +480,7 @@ int xo_quant_rdoq(int16_t *coef, int log2n, int qp, double d_lambda, int is_intr
 /* plain quantiser (rdoq == 0), src_base/xeve_tq.c:704-727 */
 int xo_quant_plain(int16_t *coef, int log2n, int qp, int slice_type, int bd)
 {
-    static const int qs[6] = XB200_QUANT_SCALE;
+    const int *qs = xo_quant_scale;
     const int n = 1 << (2 * log2n), shift = 14 + (15 - bd - log2n) + qp / 6;
     const int32_t off = (int32_t)(slice_type == 2 ? 171 : 85) << (shift - 9);
     int       nnz = 0;
@@ -513,7 +513,7 @@ void xo_tq(const xb200_seq *sq, const xb200_tq_item *it, const xb200_rates *rate
  * clip s16) then inverse transform, for the planes with nnz != 0 */
 void xo_itdq(const xb200_seq *sq, const xb200_tq_item *it, int16_t *planes, const int nnz[3])
 {
-    static const int dq[6] = XB200_DEQUANT_SCALE;
+    const int *dq = xo_dequant_scale;
     const int ny = 1 << (it->log2_cuw + it->log2_cuh), nc = ny >> 2;
     int16_t  *p[3] = {planes, planes + ny, planes + ny + nc};
     for(int c = 0; c < 3; c++) {
@@ -566,7 +566,7 @@ static void set_window(search_t *s, int cx, int cy, int bi_mode)
 
 static uint32_t mv_cost(const search_t *s, int qx, int qy, int *bits_out)
 {
-    int bits = xb200_mv_bits(qx - s->gmvp[0], qy - s->gmvp[1], s->num_refp, s->refi);
+    int bits = xo_mv_bits(qx - s->gmvp[0], qy - s->gmvp[1], s->num_refp, s->refi);
     if(s->bi) bits += s->other_bits;
     *bits_out = bits;
     return (uint32_t)((s->lambda_mv * (uint32_t)bits + (1u << 15)) >> 16);
@@ -851,7 +851,7 @@ static void df_segment(const df_ctx *d, int x_scu, int y_scu, int64_t p, int64_t
 {
     const int cls = df_class(d->scu, d->refi, d->mv, p, q), qp = XO_MCU_QP(d->scu[p]);
     const int maxv = (1 << d->bd) - 1, bdo = 6 * (d->bd - 8);
-    int st = xb200_df_strength(cls, qp) << (d->bd - 8);
+    int st = xo_df_strength(cls, qp) << (d->bd - 8);
     if(st) {
         int16_t *b = d->pl[0] + (int64_t)(y_scu * 4) * d->s[0] + x_scu * 4;
         for(int i = 0; i < 4; i++) df_line(hor ? b + i : b + (int64_t)i * d->s[0], hor ? d->s[0] : 1, st, 1, maxv);
@@ -859,7 +859,7 @@ static void df_segment(const df_ctx *d, int x_scu, int y_scu, int64_t p, int64_t
     for(int c = 1; c < 3; c++) {
         int qc = qp + (c == 1 ? d->pp->qp_u_offset : d->pp->qp_v_offset);
         qc = qc < -bdo ? -bdo : (qc > 57 ? 57 : qc);
-        st = xb200_df_strength(cls, d->pp->chroma_qp[c - 1][qc + bdo]) << (d->bd - 8);
+        st = xo_df_strength(cls, d->pp->chroma_qp[c - 1][qc + bdo]) << (d->bd - 8);
         if(!st) continue;
         int16_t *b = d->pl[c] + (int64_t)(y_scu * 2) * d->s[c] + x_scu * 2;
         for(int i = 0; i < 2; i++) df_line(hor ? b + i : b + (int64_t)i * d->s[c], hor ? d->s[c] : 1, st, 0, maxv);
@@ -1646,7 +1646,7 @@ void xo_mvp_batch(xb200_mvp_item *items, int64_t n, const xb200_mvp_pic *pp, con
 void xo_intra_nbr(const int16_t *y, const int16_t *u, const int16_t *v, int s_l, int s_c, xb200_nbr_item *it, const uint32_t *map_scu,
                   const int8_t *map_ipm, int w_scu, int h_scu, int cip, int bd, int16_t *side)
 {
-    static const uint8_t mpm_tbl[6][6][5] = XB200_MPM_TABLE;
+    const uint8_t (*mpm_tbl)[6][5] = xo_mpm_tbl;
     const int xs = it->x >> 2, ys = it->y >> 2, scuw = (1 << it->log2_cuw) >> 2, scuh = (1 << it->log2_cuh) >> 2;
     const int scup = xs + ys * w_scu, half = 1 << (bd - 1);
 #define COD(p) ((map_scu[p] >> 31) & 1)

@@ -107,6 +107,61 @@ def test_generated_tables_match_reference(probe_dir):
     assert list(rh.table(10, np.int32)[:6]) == [26214, 23302, 20560, 18396, 16384, 14764]
 
 
+ORACLE_PROBE = r"""
+#include <stdio.h>
+#include "oracle/xo_tables.h"
+int main(void) {
+  static int8_t tm[4096]; xo_gen_tm64(tm);
+  FILE* f = fopen("o_tm64.bin","wb"); fwrite(tm,1,4096,f); fclose(f);
+  static uint16_t sc[4096];
+  f = fopen("o_scan.bin","wb"); for(int l=1;l<=6;l++){ xo_gen_scan(sc,l,l); fwrite(sc,2,1<<(2*l),f);} fclose(f);
+  f = fopen("o_mvbits.bin","wb"); for(int v=-2047; v<=2048; v++){ unsigned char b=(unsigned char)xo_mvd_bits(v); fwrite(&b,1,1,f);} fclose(f);
+  f = fopen("o_refi.bin","wb"); for(int n=0;n<17;n++) for(int r=0;r<16;r++){ unsigned char b = r<n||n==0 ? (unsigned char)xo_refi_bits(n,r):0; fwrite(&b,1,1,f);} fclose(f);
+  f = fopen("o_es.bin","wb"); for(int q=0;q<6;q++) for(int l=1;l<=7;l++){ long long e = xo_err_scale(q,l,10); fwrite(&e,8,1,f);} fclose(f);
+  f = fopen("o_dfst.bin","wb"); fwrite(xo_df_st,1,sizeof(xo_df_st),f); fclose(f);
+  f = fopen("o_mpm.bin","wb"); fwrite(xo_mpm_tbl,1,sizeof(xo_mpm_tbl),f); fclose(f);
+  f = fopen("o_taps.bin","wb"); fwrite(xo_mc_l_taps,1,sizeof(xo_mc_l_taps),f); fwrite(xo_mc_c_taps,1,sizeof(xo_mc_c_taps),f); fclose(f);
+  f = fopen("o_q.bin","wb"); fwrite(xo_quant_scale,1,sizeof(xo_quant_scale),f); fwrite(xo_dequant_scale,1,sizeof(xo_dequant_scale),f); fclose(f);
+  for(int v=-70000; v<=70000; v+=37) if(v > 2048 || v <= -2048) printf("esc %d %d\n", v, xo_mvd_bits(v));
+  return 0; }
+"""
+
+
+@needs_ref
+def test_oracle_tables_match_reference(probe_dir):
+    """the oracle's OWN constants (oracle/xo_tables.h -- no code shared with the library's xb200_tables.h) against the reference's
+    tables (src_base/xeve_tbl.c:40-48, 83-257, 286-517, 625-; src_base/xeve_mc.c:39-93; src_base/xeve_tq.c:37-39, 406-423), and the
+    two generators against each other where the reference has no table (MVD escape lengths beyond +-2048)"""
+    d = tempfile.mkdtemp()
+    open(os.path.join(d, "oprobe.c"), "w").write(ORACLE_PROBE)
+    subprocess.check_call(["gcc", "-O1", "-I", ROOT, "-o", os.path.join(d, "oprobe"), os.path.join(d, "oprobe.c"), "-lm"])
+    out = subprocess.check_output([os.path.join(d, "oprobe")], cwd=d).decode()
+    rd = lambda n, dt: np.fromfile(os.path.join(d, n), dt)
+    assert np.array_equal(rd("o_tm64.bin", np.int8), rh.table(0, np.int8))
+    scan_ref = rh.table(8, np.uint16).reshape(6, 6, 4096)
+    mine, pos = rd("o_scan.bin", np.uint16), 0
+    for l in range(1, 7):
+        n = 1 << (2 * l)
+        assert np.array_equal(mine[pos:pos + n], scan_ref[l - 1, l - 1, :n]), l
+        pos += n
+    assert np.array_equal(rd("o_mvbits.bin", np.uint8), rh.table(6, np.uint8))
+    assert np.array_equal(rd("o_refi.bin", np.uint8).reshape(17, 16), rh.table(7, np.uint8).reshape(17, 16))
+    assert np.array_equal(rd("o_es.bin", np.int64).reshape(6, 7), rh.table(13, np.int64).reshape(6, 7))
+    assert np.array_equal(rd("o_dfst.bin", np.uint8), rh.table(14, np.uint8))
+    assert np.array_equal(rd("o_mpm.bin", np.uint8), rh.table(15, np.uint8))
+    taps = rd("o_taps.bin", np.int16)
+    lref, cref = rh.table(11, np.int16).reshape(-1, 8), rh.table(12, np.int16).reshape(-1, 4)   # 1/16 and 1/32 sample phases
+    assert np.array_equal(taps[:32].reshape(4, 8), lref[:: len(lref) // 4]) and np.array_equal(taps[32:].reshape(8, 4), cref[:: len(cref) // 8])
+    q = rd("o_q.bin", np.int32)
+    assert list(q[:6]) == list(rh.table(10, np.int32)[:6]) and list(q[6:]) == list(rh.table(9, np.int32))
+    # escape branch: against the library's generator (compiled from ITS header)
+    src = os.path.join(d, "esc.c")
+    open(src, "w").write('#include <stdio.h>\n#include "xeve_b200/csrc/xb200_tables.h"\n'
+                         'int main(void){ for(int v=-70000; v<=70000; v+=37) if(v > 2048 || v <= -2048) printf("esc %d %d\\n", v, xb200_mvd_bits(v)); return 0; }\n')
+    subprocess.check_call(["gcc", "-O1", "-I", ROOT, "-o", os.path.join(d, "esc"), src, "-lm"])
+    assert subprocess.check_output([os.path.join(d, "esc")]).decode() == out and out.count("esc") > 3000
+
+
 def test_library_loads_and_exports_every_declared_symbol():
     """the C-ABI .so exists in-tree, dlopens without a GPU and exports what include/xeve_b200.h declares"""
     hdr = open(os.path.join(ROOT, "include", "xeve_b200.h")).read()

@@ -40,12 +40,9 @@ def test_cuda_operators_and_their_inputs_inside_the_decision_chain(args):
     """as above, with the inputs of the analyses from the device too -- xb200_mvp (MV predictor candidates, temporal direct MVs) and
     xb200_intra_nbr (availability, reference samples, MPM list) -- so every device row of SURVEY 8 takes part; --more: 10-bit medium,
     P slices, plain quantiser.
-    PROVISIONAL: on hardware so far only the fixture part of --all-inputs has run (profiles/r01s22_chain_on_device_all_inputs.txt; the
-    round's GPU budget ended there); until the live parts have run once, a failure is reported as xfail with the script's output
-    instead of failing the suite."""
+    First hardware run of the live parts: round 2 (GPUTEST_r01 / profiles/r02s01_gpu_tests.log, 46 passed); a hard assertion since."""
     r = _run(*args)
-    if r.returncode != 0 or "CHAIN_ON_DEVICE_OK" not in r.stdout:
-        pytest.xfail("first hardware run: " + (r.stdout[-1500:] + r.stderr[-1500:]))
+    assert r.returncode == 0 and "CHAIN_ON_DEVICE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     print(r.stdout)
 
 

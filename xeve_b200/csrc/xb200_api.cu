@@ -94,7 +94,10 @@ __global__ void k_me_bin(const xb200_me_item *__restrict__ items, int n, int32_t
         const int            l2 = it.log2_cuw;
         key = (l2 >= 3 && l2 <= 6 && it.log2_cuh == l2) ? l2 - 3 : (l2 == 0 ? 5 : 4); // log2 0: slot left empty by the CU pipeline
         if(ck.validate && l2 != 0) {
+            // the CU must lie inside the (unpadded) current picture; the search range bounds the staged window
             const bool bad = !bin_pic_ok(ck, it.cur_pic) || !bin_pic_ok(ck, it.ref_pic) || ck.pics[it.ref_pic].pad_l == 0 || it.gop_size <= 0 ||
+                             it.max_search_range < 1 || it.max_search_range > 256 || it.x < 0 || it.y < 0 ||
+                             it.x + (1 << l2) > ck.pics[it.cur_pic].w || it.y + (1 << l2) > ck.pics[it.cur_pic].h ||
                              (it.bi && (it.org_bi_off < 0 || (it.org_bi_off & 3) || !ck.have_side ||
                                         (long long)it.org_bi_off + (1ll << (it.log2_cuw + it.log2_cuh)) > ck.side_elems));
             if(bad) { key = 5; atomicOr(&bins[6], 1); }

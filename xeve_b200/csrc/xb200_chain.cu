@@ -8,6 +8,7 @@
 // when all its chains fit next to the ones already there (a CTA that cannot become resident while its siblings spin would dead-lock).
 #define XB200_CONST_LINKAGE static
 #define XB200_CHAIN_TU
+#define XB200_T64 128
 #include "xb200_ctx.h"
 #include "xb200_chain.cuh"
 #include <math.h>
@@ -48,17 +49,18 @@ struct JobBufs {            // outputs and working set of one picture in flight 
 struct Job {
     JobBufs b;
     int     rec_pic = -1;
-    double  share = 0.0;    // SM share its chains occupy: n_chain / resident CTAs per SM
-    bool    retired = false, dense = false;
+    int     n_chain = 0, bps = 1;   // its CTAs, and how many of them an SM can hold (registers / shared memory of its kernel variant)
+    bool    retired = false;
 };
 // Chains of ALL contexts of a process share the device: a picture is admitted when its chains fit next to the ones already resident,
 // whoever enqueued them (several encoder instances in one process, integration/xb200_streams.c).  Per device, guarded by its own mutex.
 struct DeviceLoad {
     std::mutex        mu;
     std::deque<Job *> inflight;         // admission order, all contexts
-    double            load = 0.0;       // sum of the shares of the admitted, unretired pictures
+    int               chains = 0;       // CTAs of the admitted, unretired pictures
+    int               by_bps[33] = {};  // unretired pictures by the number of their CTAs an SM can hold
     int               n_ctx = 0;        // contexts with a decision pass on this device
-    int               dense_jobs = 0, sparse_jobs = 0;   // unretired pictures launched two / one chain(s) per SM
+    int min_bps() const { for(int b = 1; b <= 32; b++) if(by_bps[b]) return b; return 0; }
     std::vector<cudaEvent_t> graveyard; // events of torn-down contexts: another context may still be waiting on one (never destroyed)
 };
 DeviceLoad g_dev_load[64];
@@ -136,6 +138,16 @@ int chain_init(xb200_ctx *c)
     CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
     CK(cudaMemset(k->zero_mv, 0, k->f_scu * 8));
     if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
+    {   // opt-in shared memory of the decision kernel: set ONCE per device to the maximum.  The attribute belongs to the function, not to
+        // a launch: contexts on several host threads setting it to their picture's size would race (launch fails: invalid argument).
+        int optin = 0;
+        cudaFuncAttributes fa;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        CK(cudaFuncGetAttributes(&fa, k_chain<2>));
+        CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        CK(cudaFuncGetAttributes(&fa, k_chain<3>));
+        CK(cudaFuncSetAttribute(k_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    }
     CK(cudaDeviceSynchronize());
     k->ready = true;
     {
@@ -203,11 +215,16 @@ void bufs_free(JobBufs &b, DeviceLoad &D)
     b = JobBufs();
 }
 
-// retire finished pictures (of any context on this device); with `need` > 0 wait (oldest first) until that much SM share is free.
-// Called with k->mu held; the blocking wait happens with both locks released.  A job leaves the device list either here (its kernel
-// has finished) or in xb200_picture_fetch, always under the device mutex, so a listed job's event is alive while the mutex is held;
-// the event waited on outside the lock is a copy of the handle of a pooled (never destroyed before context teardown) event.
-int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk, double *load_out = nullptr, int *mode_out = nullptr)
+// Admission.  CTAs of different pictures have different footprints (kernel variant, shared memory by CU sizes / search range), and a
+// chain that cannot become resident while its siblings spin on its flags would dead-lock, so every CTA of an admitted picture must
+// find an SM.  Rule: with b = the smallest CTAs-per-SM figure among the pictures in flight and the new one, the device holds at most
+// b x SMs CTAs.  Then an SM that cannot take a CTA of the largest footprint (<= 1/b of an SM) already holds >= b CTAs, so as long as
+// fewer than b x SMs CTAs are resident some SM can take it.
+// retire finished pictures (of any context on this device); with `need` > 0 CTAs of a picture that fit `bps` per SM, wait (oldest
+// first) until they are admissible.  Called with k->mu held; the blocking wait happens with both locks released.  A job leaves the
+// device list either here (its kernel has finished) or in xb200_picture_fetch, always under the device mutex; the event waited on
+// outside the lock is never destroyed while the process lives (torn-down contexts leave theirs in the graveyard).
+int admit(xb200_ctx *c, int need, int bps, std::unique_lock<std::mutex> &lk, int *chains_out = nullptr, int *min_bps_out = nullptr)
 {
     DeviceLoad &D = g_dev_load[c->device & 63];
     for(;;) {
@@ -221,15 +238,15 @@ int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk, double *l
                     if(e == cudaErrorNotReady) break;
                     if(e != cudaSuccess) CK(e);
                     j->retired = true;
-                    D.load -= j->share;
-                    (j->dense ? D.dense_jobs : D.sparse_jobs)--;
+                    D.chains -= j->n_chain; D.by_bps[j->bps]--;
                 }
                 D.inflight.pop_front();
             }
-            if(D.inflight.empty()) D.load = 0.0;
-            if(load_out) *load_out = D.load;
-            if(mode_out) *mode_out = D.dense_jobs > 0 ? 2 : (D.sparse_jobs > 0 ? 1 : (D.n_ctx > 1 ? 2 : 0));
-            if(need <= 0 || D.load + need <= (double)c->sms + 1e-9 || D.inflight.empty()) return XB200_OK;
+            if(chains_out) *chains_out = D.chains;
+            if(min_bps_out) *min_bps_out = D.min_bps();
+            if(need <= 0 || D.inflight.empty()) return XB200_OK;
+            const int mb = D.min_bps(), b = mb && mb < bps ? mb : bps;
+            if(D.chains + need <= b * c->sms) return XB200_OK;
             wait_on = D.inflight.front()->b.ev1;
         }
         lk.unlock();
@@ -241,7 +258,6 @@ int admit(xb200_ctx *c, double need, std::unique_lock<std::mutex> &lk, double *l
 
 template <int MB> int launch_chain(xb200_ctx *c, const ChainPic &P, size_t smem, cudaStream_t s)
 {
-    CK(cudaFuncSetAttribute(k_chain<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_chain<MB><<<P.n_chain, CH_T, smem, s>>>(c->d_pics, P, c->d_tm64, c->sq, c->d_err);
     c->launches++;
     CK(cudaGetLastError());
@@ -260,7 +276,7 @@ void xb200_chain_free(xb200_ctx *c)
         std::lock_guard<std::mutex> dl(D.mu);
         for(auto &kv : k->jobs) {
             Job *j = kv.second;
-            if(!j->retired) { D.load -= j->share; (j->dense ? D.dense_jobs : D.sparse_jobs)--; }
+            if(!j->retired) { D.chains -= j->n_chain; D.by_bps[j->bps]--; }
             for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
                 if(*q == j) { D.inflight.erase(q); break; }
             bufs_free(j->b, D);
@@ -295,8 +311,7 @@ int xb200_chain_capacity(xb200_ctx *c)
     for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * 10 + 7; cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
     const size_t smem = chain_smem_bytes(cap);
     int bps = 0;
-    CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<2>, CH_T, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<3>, CH_T, smem));
     return c->sms * (bps < 1 ? 1 : bps);
 }
 
@@ -408,28 +423,30 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
             }
     }
     if(m->has_ready) CK(cudaStreamWaitEvent(s, m->ready, 0));   // an earlier life of this handle
-    // Register budget by load: one chain per SM with 255 registers while the device has room (fastest chain), two per SM with 128
-    // registers (each ~20 % slower, profiles/r02s06) once the chains in flight would not fit otherwise.
-    int bps = 0;
-    CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<2>, CH_T, smem));
-    if(bps < 1) return XB200_ERR_UNSUPPORTED;
-    // Two kernels with different footprints must not share the device: a one-per-SM chain needs a whole free SM, which the accounting
-    // by shares cannot promise while two-per-SM chains are spread over the SMs.  So the mode of the pictures in flight is kept; an idle
-    // device picks one chain per SM for a lone context whose chains fit, two per SM otherwise (several contexts: always two).
-    double dev_load = 0.0;
-    int    dev_mode = 0;
-    if((r = admit(c, 0.0, lk, &dev_load, &dev_mode))) return r;     // retire what has finished
-    const char *dense_env = getenv("XB200_CHAIN_DENSE"); // 0: always one chain per SM, 1: always two
-    const bool dense = bps >= 2 && (dense_env ? dense_env[0] == '1' : dev_mode ? dev_mode == 2 : dev_load + (double)P.n_chain > (double)c->sms);
-    if(!dense) bps = 1;
-    const double share = (double)P.n_chain / bps;
-    if(share > c->sms) return XB200_ERR_UNSUPPORTED;
-    if((r = admit(c, share, lk))) return r;
+    // Kernel variant by load: k_chain<2> (255 registers) is the fastest chain, k_chain<3> (170 registers) lets three chains share an
+    // SM -- as many as the shared memory of a B picture allows (60 - 71 KB per chain: the 64x64 working sets).  A lone context whose chains fit keeps the fast
+    // variant; several contexts (streams sharing the device) or a full device take the dense one.  XB200_CHAIN_DENSE=0 / 1 forces one.
+    int b2 = 0, b4 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_chain<2>, CH_T, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chain<3>, CH_T, smem));
+    if(b2 < 1 || b4 < 1) return XB200_ERR_UNSUPPORTED;
+    int dev_chains = 0, dev_min = 0, n_ctx = 1;
+    if((r = admit(c, 0, 1, lk, &dev_chains, &dev_min))) return r;     // retire what has finished
+    {
+        DeviceLoad &D = g_dev_load[c->device & 63];
+        std::lock_guard<std::mutex> dl(D.mu);
+        n_ctx = D.n_ctx;
+    }
+    const char *dense_env = getenv("XB200_CHAIN_DENSE");
+    const int   b_fast = dev_min && dev_min < b2 ? dev_min : b2;
+    const bool  dense = dense_env ? dense_env[0] == '1' : (n_ctx > 1 || dev_chains + P.n_chain > b_fast * c->sms);
+    const int   bps = dense ? b4 : b2;
+    if(P.n_chain > bps * c->sms) return XB200_ERR_UNSUPPORTED;
+    if((r = admit(c, P.n_chain, bps, lk))) return r;
 
     Job *j = new Job();
     if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
-    j->rec_pic = pp->rec_pic; j->share = share; j->dense = dense;
+    j->rec_pic = pp->rec_pic; j->n_chain = P.n_chain; j->bps = bps;
     P.scu_out = j->b.scu; P.coef_out = j->b.coef; P.ctu_state = j->b.ctu_state; P.ctu_cost = j->b.ctu_cost; P.done = j->b.done;
     P.counts = j->b.counts; P.ws = j->b.ws;
     if(k->log_cu > 0) { P.cu_log = j->b.cu_log; P.cu_cap = k->log_cu; }
@@ -441,7 +458,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     CK(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
     CK(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
     CK(cudaEventRecord(j->b.ev0, s));
-    if((r = dense ? launch_chain<2>(c, P, smem, s) : launch_chain<1>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
+    if((r = dense ? launch_chain<3>(c, P, smem, s) : launch_chain<2>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
     CK(cudaEventRecord(j->b.ev1, s));
     Pic &rp = c->pics[pp->rec_pic];
     if(pp->unfiltered_pic >= 0) {
@@ -461,8 +478,7 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
         DeviceLoad &D = g_dev_load[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
         D.inflight.push_back(j);
-        D.load += share;
-        (dense ? D.dense_jobs : D.sparse_jobs)++;
+        D.chains += j->n_chain; D.by_bps[j->bps]++;
     }
     return XB200_OK;
 }
@@ -509,7 +525,7 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
     {
         DeviceLoad &D = g_dev_load[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
-        if(!j->retired) { j->retired = true; D.load -= j->share; (j->dense ? D.dense_jobs : D.sparse_jobs)--; }
+        if(!j->retired) { j->retired = true; D.chains -= j->n_chain; D.by_bps[j->bps]--; }
         for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
             if(*q == j) { D.inflight.erase(q); break; }
     }

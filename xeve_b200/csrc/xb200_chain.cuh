@@ -12,20 +12,23 @@
 //
 // One CTA per coder-state CHAIN (what the reference calls a worker thread: CTU rows y, y + n, .. with threads = n; one chain per
 // picture with threads = 1).  The CTA walks its CTUs in raster order; inside a CTU it runs the quad-tree recursion as an explicit
-// state machine, uniform over its 256 threads.  Every CU analysis is the SAME device function the work-list operators run
-// (analyze_cu_one of xb200_analyze.cuh, intra_cu_one / intra_thr_one of xb200_intra.cuh) on a team made of the CTA's first 32 / 128 /
-// 256 threads; the bookkeeping between them (CU-data copies, frame maps, the picture under reconstruction) is spread over all 256.
+// state machine, uniform over its 128 threads.  Every CU analysis is the SAME device function the work-list operators run
+// (analyze_cu_one of xb200_analyze.cuh, intra_cu_one / intra_thr_one of xb200_intra.cuh) on a team made of the CTA's first 32 or all
+// 128 threads; the bookkeeping between them (CU-data copies, frame maps, the picture under reconstruction) is spread over all 128.
+// 128 threads, not 256: a chain keeps one to three warps busy most of the time, and the registers of idle warps are what limits the
+// number of chains an SM can hold.
 // A chain waits for the CTU above-right of its next CTU through a flag in global memory (src_base/xeve_enc.c:128-132); data written by
 // other chains (frame maps, reconstructed samples) is read with L2 loads (ld.cg): the L1 of this SM may hold older copies of lines that
 // straddle two CTUs.  Nothing returns to the host until the picture is done.
 #pragma once
 #define XB200_DEVICE_FUNCS_ONLY
+#define XB200_INTRA64_CAND_GLOBAL
 #include "xb200_analyze.cuh"
 #include "xb200_analyze_par.cuh"
 #include "xb200_intra.cuh"
 #include "xb200_had.cuh"
 
-#define CH_T 256
+#define CH_T 128   // threads of a chain: the widest team (32x32 and, with XB200_T64 = 128, 64x64 CUs); three warps for the small CUs
 #ifdef XB200_CHAIN_PROF
 #define CU_PROF_T(k) do { if(t == 0) { const long long now_ = clock64(); atomicAdd(&g_chain_prof[(k)], (unsigned long long)(now_ - g_prof_last)); atomicAdd(&g_chain_prof[32 + (k)], 1ull); g_prof_last = now_; } } while(0)
 #else
@@ -54,6 +57,8 @@ struct alignas(16) ChainWs { // private working set of one chain (global memory,
     alignas(16) int16_t coef[2 * (6144 + 64)];
     alignas(16) int16_t rec_cu[2 * (6144 + 64)];
     alignas(16) int16_t pred_y[4096];
+    alignas(16) int16_t cand64[5 * (4096 + 2)]; // candidate level arrays of a 64x64 intra CU (IN_CAND_SHARED)
+    alignas(16) int16_t org_bi[4096];        // 2 * org - pred of the bi search (written once, copied into the search's own area)
     alignas(16) int16_t side[8 * 64 + 6 + 26];
     alignas(16) int16_t scratch[15 * 6144]; // candidate modes of the inter analysis: {coef, rec, pred} x 5
 };
@@ -93,12 +98,15 @@ struct ChShared {            // control block in shared memory
 constexpr int CH_HDR  = ((int)sizeof(CuHdr) + 15) & ~15;
 constexpr int CH_CTL  = ((int)sizeof(ChShared) + 15) & ~15;
 constexpr int CH_TEAM_OFF = 8192 + CH_CTL;           // tm | tmT | control | team area
-constexpr int CH_ME_OFF   = CH_HDR + 8192;           // team area: CuHdr | org_bi (64x64) | mbarrier + working set
+constexpr int CH_ME_OFF   = CH_HDR;                  // team area: CuHdr | mbarrier + working set
 // max_cu: largest CU the picture can contain (intra teams are sized by max_cu_intra, the inter working sets by max_cu_inter): presets
 // fast / medium never try a 64x64 intra CU, whose team is the largest working set of all
 __host__ __device__ inline size_t chain_smem_bytes(const int32_t win_cap[4], int max_cu_intra = 64, int max_cu_inter = 64)
 {
-    size_t need = 16 + (max_cu_intra >= 64 ? sizeof(IntraTeam<6>) : max_cu_intra >= 32 ? sizeof(IntraTeam<5>) : sizeof(IntraTeam<4>));
+    // in B slices mode_check_intra follows the inter analysis for every CU size, whatever max_cu_intra says (it only bounds the tree of
+    // an I slice): the intra team must cover the largest CU of either kind
+    const int mi = max_cu_intra > max_cu_inter ? max_cu_intra : max_cu_inter;
+    size_t need = 16 + (mi >= 64 ? sizeof(IntraTeam<6>) : mi >= 32 ? sizeof(IntraTeam<5>) : sizeof(IntraTeam<4>));
     for(int l2 = 3; l2 <= 6 && (1 << l2) <= max_cu_inter; l2++) {
         const size_t me = me_team_bytes(l2, win_cap[l2 - 3]);
         const size_t rs = 16 + (size_t)(l2 == 3 ? Res2Cfg<3>::TEAM_BYTES : l2 == 4 ? Res2Cfg<4>::TEAM_BYTES : l2 == 5 ? Res2Cfg<5>::TEAM_BYTES : Res2Cfg<6>::TEAM_BYTES);
@@ -367,7 +375,7 @@ __device__ __noinline__ void ch_inter(unsigned char *team, const int8_t *tm, con
     if(t < T) {
         CuTeam<L2> Tm;
         Tm.H       = reinterpret_cast<CuHdr *>(team);
-        Tm.org_bi  = reinterpret_cast<int16_t *>(team + CH_HDR);
+        Tm.org_bi  = ws->org_bi;
         Tm.me_area = team + CH_ME_OFF;
         Tm.bar     = &S.bar[0];
         Tm.pred    = reinterpret_cast<int16_t *>(Tm.me_area + 16);
@@ -397,7 +405,7 @@ __device__ __noinline__ void ch_intra_team(unsigned char *team, const int8_t *tm
 {
     if(t < IntraCfg<L2>::T) {
         IntraTeam<L2> &M = *reinterpret_cast<IntraTeam<L2> *>(team + CH_ME_OFF + 16);
-        intra_cu_one<L2>(M, tm, tmT, pics, ws->in, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->side, coef, rec, sq, t);
+        intra_cu_one<L2>(M, tm, tmT, pics, ws->in, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->side, coef, rec, sq, t, ws->cand64);
     }
 }
 template <int L2>

@@ -1,5 +1,10 @@
 // xb200_common.cuh -- shared device-side declarations of the B200 hot-path library.
 #pragma once
+// Threads of a 64x64 team: 256 in the batched operators; the decision-chain kernel (xb200_chain.cu) runs 128-thread CTAs so that more
+// chains fit on an SM and defines XB200_T64 = 128 before including the device code.  Every team routine is generic in T.
+#ifndef XB200_T64
+#define XB200_T64 256
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/xeve_b200.h"

@@ -148,12 +148,19 @@ template <int L2> struct IntraCfg {
     static constexpr int TILES = L2 == 2 ? 1 : (N / 8) * (N / 8);   // SATD tiles per mode (4x4 CU: one 4x4 tile)
 };
 
+// XB200_INTRA64_CAND_GLOBAL (decision-chain kernel): the five candidate level arrays of a 64x64 CU (41 KB, the largest item of any
+// working set) live in global memory handed in by the caller instead of shared memory, so that more chains fit on an SM.
+#ifdef XB200_INTRA64_CAND_GLOBAL
+template <int L2> constexpr bool IN_CAND_SHARED = L2 < 6;
+#else
+template <int L2> constexpr bool IN_CAND_SHARED = true;
+#endif
 template <int L2> struct IntraTeam {
     static constexpr int N = 1 << L2, NY = N * N;
     int32_t  TB[NY < 32 ? 32 : NY];        // DCT stage buffer / RDOQ scratch
     int16_t  org[NY * 3 / 2];              // Y | U | V original block
     int16_t  blk[NY];                      // transform working block
-    int16_t  candS[5][NY + 2];             // luma levels of every candidate mode, zig-zag order (+2: lanes on different banks)
+    int16_t  candS[IN_CAND_SHARED<L2> ? 5 : 1][IN_CAND_SHARED<L2> ? NY + 2 : 2]; // luma levels of every candidate mode, zig-zag order (+2: lanes on different banks)
     uint16_t cm_lane[IN_CM_N * 8];         // one model set per candidate lane, [model][lane]
     int64_t  cand_ssd[5];
     int32_t  cand_nnz[5];
@@ -171,10 +178,14 @@ template <int L2> struct IntraTeam {
 template <int L2>
 __device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, const int8_t *tmT, const PicDev *__restrict__ pics,
                                           xb200_intra_item &it, const xb200_rates *rates, const xb200_sbac *st_in, xb200_sbac *st_out,
-                                          const int16_t *side, int16_t *coef, int16_t *rec, const SeqDev &sq, int tt)
+                                          const int16_t *side, int16_t *coef, int16_t *rec, const SeqDev &sq, int tt,
+                                          int16_t *cand_global = nullptr)
 {
     using Cf = IntraCfg<L2>;
     constexpr int T = Cf::T, N = Cf::N, NY = Cf::NY, NC = N / 2, NCH = Cf::NCH, TILES = Cf::TILES, LC = L2 - 1;
+    // candidate level arrays: [5][NY + 2] in the team's shared memory, or in the caller's global buffer (see IN_CAND_SHARED)
+    int16_t (*const candS)[NY + 2] = IN_CAND_SHARED<L2> ? reinterpret_cast<int16_t (*)[NY + 2]>(&M.candS[0][0])
+                                                         : reinterpret_cast<int16_t (*)[NY + 2]>(cand_global);
     const int lane = tt & 31;
     const int bd = sq.bd, maxv = (1 << bd) - 1, sh = (bd - 8) << 1;
     const int slice_type = it.slice_type, all_preds = it.all_preds, ctx_skip = it.ctx_skip, ctx_pm = it.ctx_pred_mode;
@@ -263,7 +274,7 @@ __device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, co
         team_sync<T>();
         fwd_dct_t<L2, T>(M.blk, M.TB, tm, tmT, bd, tt);
         const int nnz = quant_team<L2, T, true>(M.blk, M.TB, it.qp[0], lambda0, 0, slice_type, rt, bd, sq.rdoq, tt, M.X);
-        for(int e = tt; e < NY; e += T) M.candS[j][zz_of(e, L2)] = M.blk[e];
+        for(int e = tt; e < NY; e += T) candS[j][zz_of(e, L2)] = M.blk[e];
         if(nnz) {
             team_sync<T>();
             dequant_team<L2, T>(M.blk, it.qp[0], bd, tt);
@@ -296,7 +307,7 @@ __device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, co
         int num_sig = M.cand_nnz[tt];
         tc_bin<8>(c, XB200_CM_CBF_LUMA, num_sig != 0);
         if(num_sig) { // xeve_eco_run_length_cc over the zig-zag ordered levels; ends with the last significant one
-            const int16_t *lv = M.candS[tt];
+            const int16_t *lv = candS[tt];
             uint32_t       run = 0;
             for(int sp = 0; sp < NY; sp++) {
                 const int v = lv[sp];
@@ -327,7 +338,7 @@ __device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, co
     const int best_ipd = M.list[best_j], nnz_best0 = M.cand_nnz[best_j];
     // the winner's levels go out in raster order; its reconstruction is rebuilt from them (cheaper than keeping five)
     for(int e = tt; e < NY; e += T) {
-        const int16_t v = M.candS[best_j][zz_of(e, L2)];
+        const int16_t v = candS[best_j][zz_of(e, L2)];
         g_coef[e] = v;
         M.blk[e] = v;
     }
@@ -397,7 +408,7 @@ __device__ __noinline__ void intra_cu_one(IntraTeam<L2> &M, const int8_t *tm, co
             cb_bin(c, XB200_CM_CBF_CR, nnzc[1] != 0);
             cb_bin(c, XB200_CM_CBF_LUMA, nnz_best0 != 0);
         }
-        if(nnz_best0) cb_run_length_sm(c, M.candS[best_j], NY, nnz_best0, 0, lane);
+        if(nnz_best0) cb_run_length_sm(c, candS[best_j], NY, nnz_best0, 0, lane);
         if(nnzc[0]) cb_run_length_sm(c, M.chS, NCH, nnzc[0], 1, lane);
         if(nnzc[1]) cb_run_length_sm(c, M.chS + NCH, NCH, nnzc[1], 2, lane);
         if(lane == 0) { M.bits = c.bits; M.range_run = c.range; }

@@ -44,7 +44,7 @@ template <int L2> struct MeGeom {
     static constexpr int LPR   = QPR < G ? QPR : G;                      // lanes along a row
     static constexpr int RG    = G / LPR;                                // row groups inside the lane group
     static constexpr int QPL   = QPR / LPR;                              // quads per lane per row
-    static constexpr int T     = L2 <= 4 ? 32 : (L2 == 5 ? 128 : 256);   // threads per call (team)
+    static constexpr int T     = L2 <= 4 ? 32 : (L2 == 5 ? 128 : XB200_T64);   // threads per call (team)
     static constexpr int CTA   = L2 <= 4 ? ME_THREADS : T;
     static constexpr int TEAMS = CTA / T;
     static constexpr int NG    = T / G;                                  // candidates in flight per team

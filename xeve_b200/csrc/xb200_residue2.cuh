@@ -418,7 +418,7 @@ XB_DEV void residue_plane(const int16_t *__restrict__ org, int so, const int16_t
 }
 
 template <int L2> struct Res2Cfg {
-    static constexpr int T     = L2 <= 4 ? 32 : (L2 == 5 ? 128 : 256);
+    static constexpr int T     = L2 <= 4 ? 32 : (L2 == 5 ? 128 : XB200_T64);
     static constexpr int CTA   = L2 <= 4 ? 128 : T;
     static constexpr int TEAMS = CTA / T;
     static constexpr int N     = 1 << L2;
@@ -518,8 +518,10 @@ __global__ void k_res_bin(const xb200_residue_item *__restrict__ items, int n, i
 #pragma unroll
             for(int l = 0; l < 2; l++)
                 if(it.mc.refi[l] >= 0 && (!pic_ok(it.mc.ref_pic[l]) || ck.pics[it.mc.ref_pic[l]].pad_l == 0)) bad = true;
-            bad = bad || !pic_ok(it.cur_pic) || it.rate_idx < 0 || it.rate_idx >= ck.n_rates || it.out_off < 0 ||
+            // out_off must be even (planes are compacted as 32-bit words); the CU must lie inside the current picture
+            bad = bad || !pic_ok(it.cur_pic) || it.rate_idx < 0 || it.rate_idx >= ck.n_rates || it.out_off < 0 || (it.out_off & 1) ||
                   it.out_off + (long long)w * h * 3 / 2 > ck.elems;
+            if(!bad) bad = it.mc.x < 0 || it.mc.y < 0 || it.mc.x + w > ck.pics[it.cur_pic].w || it.mc.y + h > ck.pics[it.cur_pic].h;
             if(unsup) { key = 5; atomicOr(&bins[7], 1); }
             else if(bad) { key = 5; atomicOr(&bins[6], 1); }
         }
