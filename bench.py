@@ -122,7 +122,19 @@ def run_streams(binary, path, c, preset, frames, streams, threads, passes, out_p
     """-> list of per-pass dicts (the program's JSON lines)"""
     cmd = [os.path.join(REFDIR, binary), "-i", path, "-w", str(c.w), "-h", str(c.h), "-d", str(c.depth), "-z", str(frames), "-n", str(streams),
            "-m", str(threads), "--preset", preset, "-r", str(passes), "-o", out_prefix]
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    # its own process group with a deadline: a hung pass (a kernel that never ends) must not outlive the bench
+    pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        out, err = pr.communicate(timeout=1200)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(pr.pid, signal.SIGKILL)
+        out, err = pr.communicate()
+        raise RuntimeError(f"{binary} did not finish within 1200 s: {out[-800:]} {err[-800:]}")
+
+    class R:
+        returncode, stdout, stderr = pr.returncode, out, err
+    r = R
     if r.returncode != 0:
         raise RuntimeError(f"{binary} failed ({r.returncode}): {r.stdout[-1500:]} {r.stderr[-1500:]}")
     return [json.loads(line) for line in r.stdout.strip().splitlines() if line.startswith("{")]
@@ -282,8 +294,10 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_" + args.workload)
+        issue = traffic.get("issue") if isinstance(traffic, dict) else None
+        traffic = traffic.get("dram_bytes_per_launch") if isinstance(traffic, dict) else traffic
     except (OSError, ValueError):
-        pass
+        issue = None
     out = {
         "metric": "encoded pictures/s", "value": round(value, 3), "unit": "pictures/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * sec / args.steps, 2), "higher_is_better": True, "scaling": "weak",
@@ -306,7 +320,10 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 8),
                      "traffic": traffic, "kernel": "k_chain (decision pass of one picture: ME + MC + TQ + RDO + tree, latency bound)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "algorithmic_bytes_per_launch": int(alg)},
+                     "algorithmic_bytes_per_launch": int(alg),
+                     # the kernel is latency bound (a serial decision chain per CTA): what it uses of the SMs it runs on, from the
+                     # committed ncu capture (smsp__inst_executed / busy SMs' issue slots), next to the HBM figure the contract asks for
+                     "issue_slots": issue},
         "clocks": sampler.summary(),
     }
     if not ok:
@@ -325,7 +342,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
-    ap.add_argument("--frames", type=int, default=17, help="pictures per stream (17 = the intra picture + one GOP of 16)")
+    ap.add_argument("--frames", type=int, default=33, help="pictures per stream (33 = the intra picture + two GOPs of 16)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
     args = ap.parse_args()
     # exactly ONE line on stdout: everything libraries print (NCCL's version banner, torchrun notices) goes to stderr

@@ -467,6 +467,9 @@ XB200_API int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp);
  * coef [n_lcu * 6144], ctu_states [n_lcu][2] (the coder state each CTU's decision pass started from / ended with), ctu_cost [n_lcu]. */
 XB200_API int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16_t *coef, xb200_state *ctu_states,
                                   double *ctu_cost, xb200_picture_stat *stat);
+/* 1 when picture rec_pic is complete (xb200_picture_fetch would not block), 0 while it is queued or running, < 0 for a handle with
+ * no picture in flight.  Lets a caller that must not block (xeve_encode returning XEVE_OK_OUT_NOT_AVAILABLE) poll. */
+XB200_API int xb200_picture_ready(xb200_ctx *c, int32_t rec_pic);
 /* Frame maps of a decided picture as the reference holds them when the loop filter starts (host buffers, any may be NULL):
  * map_scu u32[f_scu], map_ipm s8[f_scu], map_refi s8[f_scu][2], map_mv s16[f_scu][2][2]. */
 XB200_API int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv);

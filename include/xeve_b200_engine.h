@@ -26,6 +26,7 @@ typedef struct xb200_engine {
     int  (*analyze_picture)(xb200_ctx *c, const xb200_picture *pp);                                 /* xb200_analyze_picture */
     int  (*picture_fetch)(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16_t *coef, xb200_state *ctu_states, double *ctu_cost,
                           xb200_picture_stat *stat);                                                /* xb200_picture_fetch */
+    int  (*picture_ready)(xb200_ctx *c, int32_t rec_pic);                                           /* xb200_picture_ready */
 } xb200_engine;
 
 /* Test seam of the drop-in library (see above).  NULL restores the default (CUDA) table.  Affects encoders created afterwards. */
@@ -34,7 +35,7 @@ XB200_API void xeve_b200_set_engine(const xb200_engine *e);
 /* What the drop-in did for an encoder instance (id = the XEVE handle), for tests and benches: pictures decided on the device,
  * pictures whose speculative plan had to be redone at the end of the stream, CU analyses run, summed kernel time. */
 typedef struct {
-    int64_t pictures, replanned, n_inter, n_intra;
+    int64_t pictures, replanned, n_inter, n_intra, deferred;   /* deferred: xeve_encode calls answered XEVE_OK_OUT_NOT_AVAILABLE while the device worked */
     double  chain_ms, filter_ms, wait_ms;   /* wait_ms: host time xeve_encode spent blocked on the device */
     int32_t device_path;                    /* 1: decisions on the device; 0: configuration outside the path, reference host code ran */
     int32_t pad_;

@@ -42,10 +42,12 @@ XEVE xeve_create_host(XEVE_CDSC *cdsc, int *err);   /* the reference's xeve_crea
 
 #define DI_LEAD   16     /* frames the shadow context runs ahead of the pushes (one default GOP) */
 #define DI_MAXPIC 256    /* device pictures per pool */
+#define DI_MAX_LAG 32    /* frames the encoder may fall behind its normal pace while the device works (the reference's input ring holds
+                            XEVE_MAX_INBUF_CNT = 70 frames, its normal delay is bframes + 1 = 16) */
 
 /* ---- engine table ------------------------------------------------------------------------------------------------------------------ */
 static const xb200_engine g_cuda_engine = {xb200_create, xb200_destroy, xb200_pic_create, xb200_pic_destroy, xb200_pic_upload,
-                                           xb200_pic_download, xb200_analyze_picture, xb200_picture_fetch};
+                                           xb200_pic_download, xb200_analyze_picture, xb200_picture_fetch, xb200_picture_ready};
 static const xb200_engine *g_engine = &g_cuda_engine;
 XB200_API void xeve_b200_set_engine(const xb200_engine *e) { g_engine = e ? e : &g_cuda_engine; }
 
@@ -71,7 +73,7 @@ typedef struct DropIn {
     Plan   *plan;
     int     n_plan, cap_plan;
     int     next_enq, next_fetch, pushed, shadow_pushed;
-    int     tail_done, sync_mode, failed, want_recon;
+    int     tail_done, sync_mode, failed, want_recon, lag_ok, catchup;
     int     n_lcu, parallel_rows;
     RecEnt  rec[DI_MAXPIC];
     int     n_rec;
@@ -444,6 +446,32 @@ static int hook_enc(XEVE_CTX *ctx, XEVE_BITB *bitb, XEVE_STAT *stat)
     if(FORCE_OUT(ctx) && !d->tail_done && !d->sync_mode) {
         d->tail_done = 1;
         if(XEVE_FAILED(replan_tail(d, (int)ctx->pic_ticnt + 1))) return XEVE_ERR;
+        /* pictures the encoder would have coded before the end of the input had xeve_encode not answered "not available" while the
+         * device worked: with N frames pushed it codes N - frm_rnum pictures in normal mode, the rest while bumping */
+        d->catchup = (int)ctx->pic_ticnt + 1 - (int)ctx->frm_rnum - d->next_fetch;
+        if(d->catchup < 0) d->catchup = 0;
+    }
+    if(FORCE_OUT(ctx) && d->catchup > 0) {
+        /* The reference derives "pictures coded so far" from the frames pushed (xeve_enc: pic_icnt - frm_rnum, with a pseudo push per
+         * call while bumping, src_base/xeve_enc.c:607-620, 969-972), i.e. it assumes the lock step this encoder left.  Code the
+         * pictures it is behind by exactly as it would have coded them then: the pseudo push undone, force-output off for the call. */
+        ctx->pic_icnt--;
+        ctx->param.force_output = 0;
+        const int ret = d->real_enc(ctx, bitb, stat);
+        ctx->param.force_output = 1;
+        d->catchup--;
+        return ret;
+    }
+    /* Do not block the caller's pushes while the device is still deciding the next picture: xeve_encode may answer
+     * XEVE_OK_OUT_NOT_AVAILABLE (inc/xeve.h:52, the answer it gives while its own delay fills), the application pushes the next frame
+     * and the pictures that frame makes codable are enqueued -- so the next GOPs overlap the current one on the device.  Bounded by
+     * the reference's input ring; at the end of the stream (FORCE_OUT: no more pushes) encode blocks. */
+    if(!FORCE_OUT(ctx) && d->lag_ok && d->next_fetch < d->n_plan && d->plan[d->next_fetch].state == 1) {
+        const int lag = d->pushed - (d->next_fetch + (int)ctx->frm_rnum + 1);
+        if(lag < DI_MAX_LAG && d->E->picture_ready(d->dev, d->plan[d->next_fetch].rec) == 0) {
+            d->stats.deferred++;
+            return XEVE_OK_OUT_NOT_AVAILABLE;
+        }
     }
     return d->real_enc(ctx, bitb, stat);
 }
@@ -601,6 +629,7 @@ static int install(XEVE_CTX *ctx, const XEVE_CDSC *cdsc)
     d->coef = (int16_t *)malloc((size_t)d->n_lcu * 6144 * sizeof(int16_t));
     d->sh_bs = (uint8_t *)malloc(1 << 20);
     d->dummy_buf = calloc(64 * 64, 2);
+    d->lag_ok = !(getenv("XB200_DROPIN_SYNC") && atoi(getenv("XB200_DROPIN_SYNC")));   /* 1: xeve_encode always blocks on the device */
     d->want_recon = ctx->param.use_pic_sign || (getenv("XB200_DROPIN_RECON") && atoi(getenv("XB200_DROPIN_RECON")));
     d->s1 = (Shadow *)calloc(1, sizeof(Shadow));
     if(d->s1) { d->s1->owner = d; d->shadow = shadow_create(d, d->s1); }

@@ -24,6 +24,7 @@ typedef struct {
     xo_scu_rec *scu;        /* results of the last decision into this picture */
     int16_t    *coef;
     int64_t     n_inter, n_intra;
+    int         polls;
 } SiPic;
 struct xb200_ctx {          /* the stand-in's own context behind the opaque handle */
     xb200_seq seq;
@@ -154,7 +155,7 @@ static int si_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     memset(p->map_mv, 0, f * 8);
     xo_chain_picture(&c->seq, c->planes, &r, col[0], col[1] ? col[1] : col[0], out, cost, c->planes[h].y, c->planes[h].u, c->planes[h].v,
                      p->s[0], p->s[1], map_scu, map_ipm, map_refi, p->map_mv, cus, (int64_t)f, NULL, 0, NULL, 0, n_out, 0, p->scu, p->coef);
-    p->n_inter = n_out[1]; p->n_intra = n_out[2];
+    p->n_inter = n_out[1]; p->n_intra = n_out[2]; p->polls = 0;
     if(pp->deblock) {
         xb200_df_pic df = pp->df;
         df.w_scu = (c->seq.w + 3) >> 2; df.h_scu = (c->seq.h + 3) >> 2;
@@ -174,8 +175,18 @@ static int si_picture_fetch(xb200_ctx *c, int32_t h, xb200_scu_rec *scu, int16_t
     if(stat) { memset(stat, 0, sizeof(*stat)); stat->n_inter = c->pic[h].n_inter; stat->n_intra = c->pic[h].n_intra; }
     return XB200_OK;
 }
+/* XO_STANDIN_POLLS=n (test knob): a picture reports "not ready" to its first n polls, so the drop-in's non-blocking xeve_encode path
+ * (XEVE_OK_OUT_NOT_AVAILABLE while the device works) is exercised although this engine decides synchronously */
+static int si_picture_ready(xb200_ctx *c, int32_t h)
+{
+    if(h < 0 || h >= SI_MAXPIC || !c->pic[h].used || !c->pic[h].scu) return XB200_ERR_INVALID_ARGUMENT;
+    const char *e = getenv("XO_STANDIN_POLLS");
+    const int   n = e ? atoi(e) : 0;
+    if(c->pic[h].polls < n) { c->pic[h].polls++; return 0; }
+    return 1;
+}
 static const xb200_engine g_standin = {si_create, si_destroy, si_pic_create, si_pic_destroy, si_pic_upload, si_pic_download, si_analyze_picture,
-                                       si_picture_fetch};
+                                       si_picture_fetch, si_picture_ready};
 XO_API const xb200_engine *xo_engine(void) { return &g_standin; }
 
 /* ---- driver of the public API (inc/xeve.h only): frames in memory -> bitstream, like the reference app's main loop ---------------- */

@@ -34,7 +34,8 @@ needs_dropin = pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists
 
 
 class Stats(C.Structure):
-    _fields_ = [("pictures", C.c_int64), ("replanned", C.c_int64), ("n_inter", C.c_int64), ("n_intra", C.c_int64), ("chain_ms", C.c_double),
+    _fields_ = [("pictures", C.c_int64), ("replanned", C.c_int64), ("n_inter", C.c_int64), ("n_intra", C.c_int64), ("deferred", C.c_int64),
+                ("chain_ms", C.c_double),
                 ("filter_ms", C.c_double), ("wait_ms", C.c_double), ("device_path", C.c_int32), ("pad_", C.c_int32)]
 
 
@@ -81,6 +82,18 @@ def test_dropin_bitstream_equals_reference_with_cpu_engine_table(frames, threads
     got, st = api_encode(yuv, frames, c.w, c.h, c.depth, preset, threads, extra)
     assert st.device_path == 1 and st.pictures == frames and st.n_inter + st.n_intra > 0
     assert len(got) == len(ref) and np.array_equal(got, ref), "bitstream of the drop-in library differs from the reference's"
+
+
+@needs_dropin
+def test_dropin_encode_does_not_block_the_pushes(monkeypatch):
+    """while the device is still deciding the next picture xeve_encode answers XEVE_OK_OUT_NOT_AVAILABLE, the application pushes on and
+    the next GOPs are enqueued (here: the CPU engine reports every picture "not ready" to its first polls): same bitstream"""
+    monkeypatch.setenv("XO_STANDIN_POLLS", "3")
+    c, yuv = tracedata.clip_yuv("cif", 40, **QCIF)
+    ref = rh.encode_clip(yuv, 40, c.w, c.h, in_depth=c.depth, preset="fast", threads=2).bitstream
+    got, st = api_encode(yuv, 40, c.w, c.h, c.depth, "fast", 2)
+    assert st.device_path == 1 and st.pictures == 40 and st.deferred > 20
+    assert np.array_equal(got, ref)
 
 
 @needs_dropin

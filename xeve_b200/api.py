@@ -194,7 +194,7 @@ def load():
     return _lib
 
 
-EXPORTS = ["xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
+EXPORTS = ["xb200_picture_ready", "xb200_create", "xb200_destroy", "xb200_version", "xb200_launch_count", "xb200_pic_create", "xb200_pic_destroy",
            "xb200_pic_upload", "xb200_pic_upload_s16", "xb200_pic_download", "xb200_sad", "xb200_ssd", "xb200_satd",
            "xb200_me", "xb200_mc", "xb200_bi_org", "xb200_fwd_dct_tc", "xb200_mvp", "xb200_tq", "xb200_itdq", "xb200_recon", "xb200_residue", "xb200_last_kernel_ms",
            "xb200_rdo_bits", "xb200_rdoq_rates", "xb200_analyze_cu", "xb200_deblock", "xb200_analyze_intra", "xb200_intra_nbr",

@@ -54,7 +54,7 @@ int sync_pics(xb200_ctx *c)
     const int n = (int)c->pics.size();
     if(n > c->d_pics_cap) {
         if(c->d_pics) cudaFree(c->d_pics);
-        c->d_pics_cap = n + 16;
+        c->d_pics_cap = n + 16 < 4096 ? 4096 : n + 16;   // roomy: growing the table means cudaFree, which waits for every running kernel
         CK(cudaMalloc(&c->d_pics, sizeof(PicDev) * c->d_pics_cap));
     }
     std::vector<PicDev> h(n);

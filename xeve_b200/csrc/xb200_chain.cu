@@ -14,7 +14,11 @@
 #include <math.h>
 #include <deque>
 #include <map>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #ifdef XB200_CHAIN_DEBUG
 static volatile int *h_dbg_words;   // host view of the kernel's progress words (host-mapped memory)
@@ -22,15 +26,16 @@ static volatile int *h_dbg_words;   // host view of the kernel's progress words 
 
 namespace {
 
-constexpr int N_STREAMS = 16;
+constexpr int N_STREAMS = 64;
 
-struct PicMaps {            // frame maps of a decided (or adopted) picture
+struct Job;
+struct PicMaps {            // frame maps of a decided (or adopted) picture; heap-allocated, the address is stable for the context's life
     uint32_t *scu = nullptr;
     int8_t   *ipm = nullptr, *refi = nullptr;
     int16_t  *mv = nullptr;
     uint8_t  *flags = nullptr;
-    cudaEvent_t ready = nullptr;   // recorded when the picture is a usable reference
-    bool      has_ready = false;
+    uint64_t  issued = 0;                 // pictures enqueued into this handle so far (its "lives")
+    std::atomic<uint64_t> ready{0};       // lives that are complete: decided, filtered, border-expanded -- a usable reference picture
 };
 struct JobBufs {            // outputs and working set of one picture in flight (recycled)
     xb200_scu_rec *scu = nullptr;
@@ -46,36 +51,67 @@ struct JobBufs {            // outputs and working set of one picture in flight 
     long long      cu_cap = 0, intra_cap = 0;
     cudaEvent_t    ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
+struct Dep { PicMaps *m; uint64_t life; };   // satisfied when m->ready >= life
+enum { JOB_PENDING = 0, JOB_RUNNING = 1, JOB_CHAIN_DONE = 2, JOB_READY = 3, JOB_FAILED = 4 };
 struct Job {
-    JobBufs b;
-    int     rec_pic = -1;
-    int     n_chain = 0, bps = 1;   // its CTAs, and how many of them an SM can hold (registers / shared memory of its kernel variant)
-    bool    retired = false;
+    JobBufs     b;
+    xb200_ctx  *c = nullptr;
+    int         rec_pic = -1;
+    int         n_chain = 0, bps = 1;   // its CTAs, and how many of them an SM can hold (registers / shared memory of its kernel variant)
+    int         b_fast = 1, b_dense = 1;   // CTAs per SM of k_chain<2> / k_chain<3> with this picture's shared memory
+    bool        dense = false;
+    ChainPic    P;                      // kernel arguments, complete at enqueue
+    size_t      smem = 0;
+    Pic         rp, up;                 // copies of the context's picture descriptors (the table may grow while the job waits)
+    bool        has_up = false, deblock = false;
+    PicMaps    *m = nullptr;
+    uint64_t    life = 0;
+    Dep         deps[2 * XB200_MAX_REFP + 1];
+    int         n_dep = 0;
+    int         stream_no = -1;
+    std::atomic<int> state{JOB_PENDING};
 };
-// Chains of ALL contexts of a process share the device: a picture is admitted when its chains fit next to the ones already resident,
-// whoever enqueued them (several encoder instances in one process, integration/xb200_streams.c).  Per device, guarded by its own mutex.
-struct DeviceLoad {
-    std::mutex        mu;
-    std::deque<Job *> inflight;         // admission order, all contexts
-    int               chains = 0;       // CTAs of the admitted, unretired pictures
-    int               by_bps[33] = {};  // unretired pictures by the number of their CTAs an SM can hold
-    int               n_ctx = 0;        // contexts with a decision pass on this device
+
+// ---- the device scheduler ------------------------------------------------------------------------------------------------------------
+// Pictures are LAUNCHED when their reference pictures are complete, not when they are enqueued: a kernel that sits in a stream behind
+// an event holds no SM, but admission has to count it (a chain that cannot become resident while its siblings spin on its flags
+// dead-locks), so enqueue-time admission filled the device's books with pictures that were not running (12 streams: 62 chains busy of
+// 444).  One scheduler thread per device owns the launches of every context of the process: xb200_analyze_picture only queues the
+// picture; completion callbacks (cudaLaunchHostFunc) wake the thread, which launches every queued picture whose references are ready
+// and whose chains fit.  Capacity rule: CTAs of different pictures have different footprints (kernel variant, shared memory by CU
+// sizes / search range).  With b = the smallest CTAs-per-SM figure among the pictures whose chains are running and the new one, the
+// device holds at most b x SMs CTAs; then an SM that cannot take a CTA of the largest footprint (<= 1/b of an SM) already holds >= b
+// CTAs, so while fewer than b x SMs are resident some SM can take it.
+struct DeviceSched {
+    std::mutex              mu;              // scheduler state below; held by the scheduler thread while it launches
+    std::condition_variable cv_done;         // a picture became complete (waiters: xb200_picture_fetch & co.)
+    // Completion callbacks run on a CUDA-internal thread and must never wait for a thread that is inside a CUDA call: they only append
+    // to `events` under their own small mutex, which no one holds across a CUDA call.
+    std::mutex              cb_mu;
+    std::condition_variable cv_work;
+    std::vector<std::pair<Job *, int>> events;   // {job, 0: decision kernel finished | 1: picture complete}
+    std::deque<Job *>       pending;         // enqueue order, all contexts
+    int                     chains = 0;      // CTAs of the pictures whose decision kernel is running
+    int                     by_bps[33] = {}; // those pictures by their CTAs-per-SM figure
+    int                     n_ctx = 0;       // contexts with a decision pass on this device
+    int                     sms = 0, device = 0;
+    bool                    wake = false, stop = false, started = false;   // wake / stop: guarded by cb_mu
+    std::thread             th;
     int min_bps() const { for(int b = 1; b <= 32; b++) if(by_bps[b]) return b; return 0; }
-    std::vector<cudaEvent_t> graveyard; // events of torn-down contexts: another context may still be waiting on one (never destroyed)
 };
-DeviceLoad g_dev_load[64];
+DeviceSched g_sched[64];
 
 struct ChainCtx {
     std::mutex   mu;                    // host-side bookkeeping: one thread may enqueue pictures while another fetches results
     cudaStream_t streams[N_STREAMS] = {};
+    int          stream_busy[N_STREAMS] = {};   // pictures launched on the stream and not yet complete (guarded by the scheduler mutex)
     cudaStream_t copy = nullptr;
-    int          next_stream = 0;
-    std::vector<PicMaps> maps;
+    std::vector<PicMaps *> maps;
     std::map<int, Job *> jobs;          // by rec_pic
     std::vector<JobBufs> pool;
     int16_t     *zero_mv = nullptr;     // colocated map of a reference picture without one (all zero)
     long long    log_cu = 0, log_intra = 0;
-    cudaEvent_t  ev_span0 = nullptr;    // device time span of a batch of pictures: first enqueue after a reset ...
+    cudaEvent_t  ev_span0 = nullptr;    // device time span of a batch of pictures: first launch after a reset ...
     bool         span_on = false;
     float        span_ms = 0.f;         // ... to the latest completion among the pictures fetched since
     bool         ready = false;
@@ -84,6 +120,7 @@ struct ChainCtx {
 };
 
 ChainCtx *cc_of(xb200_ctx *c) { return static_cast<ChainCtx *>(c->chain); }
+void sched_thread(DeviceSched *D);
 
 int chain_init(xb200_ctx *c)
 {
@@ -151,9 +188,11 @@ int chain_init(xb200_ctx *c)
     CK(cudaDeviceSynchronize());
     k->ready = true;
     {
-        DeviceLoad &D = g_dev_load[c->device & 63];
+        DeviceSched &D = g_sched[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
         D.n_ctx++;
+        D.sms = c->sms; D.device = c->device;
+        if(!D.started) { D.started = true; D.th = std::thread(sched_thread, &D); D.th.detach(); }
     }
     return XB200_OK;
 }
@@ -161,13 +200,13 @@ int chain_init(xb200_ctx *c)
 int maps_of(xb200_ctx *c, int pic, PicMaps **out)
 {
     ChainCtx *k = cc_of(c);
-    if((int)k->maps.size() <= pic) k->maps.resize(pic + 1);
-    PicMaps &m = k->maps[pic];
+    if((int)k->maps.size() <= pic) k->maps.resize(pic + 1, nullptr);
+    if(!k->maps[pic]) k->maps[pic] = new PicMaps();
+    PicMaps &m = *k->maps[pic];
     if(!m.scu) {
         const size_t f = k->f_scu;
         CK(cudaMalloc(&m.scu, f * 4)); CK(cudaMalloc(&m.ipm, f)); CK(cudaMalloc(&m.refi, f * 2)); CK(cudaMalloc(&m.mv, f * 8));
         CK(cudaMalloc(&m.flags, f));
-        CK(cudaEventCreateWithFlags(&m.ready, cudaEventDisableTiming));
     }
     *out = &m;
     return XB200_OK;
@@ -206,62 +245,143 @@ int bufs_get(xb200_ctx *c, int n_chain, JobBufs *out)
     *out = b;
     return XB200_OK;
 }
-void bufs_free(JobBufs &b, DeviceLoad &D)
+void bufs_free(JobBufs &b)
 {
     for(void *p : {(void *)b.scu, (void *)b.coef, (void *)b.ctu_state, (void *)b.ctu_cost, (void *)b.done, (void *)b.counts, (void *)b.ws,
                    (void *)b.cu_log, (void *)b.intra_log})
         if(p) cudaFree(p);
-    if(b.ev0) { cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev2); D.graveyard.push_back(b.ev1); }
+    if(b.ev0) { cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev1); cudaEventDestroy(b.ev2); }
     b = JobBufs();
 }
 
-// Admission.  CTAs of different pictures have different footprints (kernel variant, shared memory by CU sizes / search range), and a
-// chain that cannot become resident while its siblings spin on its flags would dead-lock, so every CTA of an admitted picture must
-// find an SM.  Rule: with b = the smallest CTAs-per-SM figure among the pictures in flight and the new one, the device holds at most
-// b x SMs CTAs.  Then an SM that cannot take a CTA of the largest footprint (<= 1/b of an SM) already holds >= b CTAs, so as long as
-// fewer than b x SMs CTAs are resident some SM can take it.
-// retire finished pictures (of any context on this device); with `need` > 0 CTAs of a picture that fit `bps` per SM, wait (oldest
-// first) until they are admissible.  Called with k->mu held; the blocking wait happens with both locks released.  A job leaves the
-// device list either here (its kernel has finished) or in xb200_picture_fetch, always under the device mutex; the event waited on
-// outside the lock is never destroyed while the process lives (torn-down contexts leave theirs in the graveyard).
-int admit(xb200_ctx *c, int need, int bps, std::unique_lock<std::mutex> &lk, int *chains_out = nullptr, int *min_bps_out = nullptr)
+template <int MB> cudaError_t launch_chain(const Job *j, cudaStream_t s)
 {
-    DeviceLoad &D = g_dev_load[c->device & 63];
+    k_chain<MB><<<j->P.n_chain, CH_T, j->smem, s>>>(j->c->d_pics, j->P, j->c->d_tm64, j->c->sq, j->c->d_err);
+    return cudaGetLastError();
+}
+
+// completion callbacks (run on a CUDA-internal thread: no CUDA calls, no waiting for the scheduler)
+void post_event(Job *j, int kind)
+{
+    DeviceSched &D = g_sched[j->c->device & 63];
+    {
+        std::lock_guard<std::mutex> cl(D.cb_mu);
+        D.events.emplace_back(j, kind);
+        D.wake = true;
+    }
+    D.cv_work.notify_one();
+}
+void CUDART_CB cb_chain_done(void *arg) { post_event(static_cast<Job *>(arg), 0); }
+void CUDART_CB cb_ready(void *arg) { post_event(static_cast<Job *>(arg), 1); }
+void sched_kick(DeviceSched &D)
+{
+    { std::lock_guard<std::mutex> cl(D.cb_mu); D.wake = true; }
+    D.cv_work.notify_one();
+}
+
+// everything of one picture on one stream: clear the maps, the persistent decision kernel, the optional copy of the unfiltered
+// picture, both loop-filter passes, the border expansion.  Called by the scheduler thread with the scheduler mutex held.
+#define CKJ(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { fprintf(stderr, "xeve_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return false; } } while(0)
+bool launch_job(DeviceSched &D, Job *j)
+{
+    xb200_ctx *c = j->c;
+    ChainCtx  *k = cc_of(c);
+    int        sn = 0;
+    for(int i = 1; i < N_STREAMS; i++) if(k->stream_busy[i] < k->stream_busy[sn]) sn = i;
+    cudaStream_t s = k->streams[sn];
+    j->stream_no = sn;
+    PicMaps  *m = j->m;
+    const size_t f = k->f_scu;
+    if(!k->span_on) { CKJ(cudaEventRecord(k->ev_span0, s)); k->span_on = true; k->span_ms = 0.f; }
+    CKJ(cudaMemsetAsync(m->scu, 0, f * 4, s)); CKJ(cudaMemsetAsync(m->ipm, 0, f, s)); CKJ(cudaMemsetAsync(m->refi, 0, f * 2, s));
+    CKJ(cudaMemsetAsync(m->mv, 0, f * 8, s)); CKJ(cudaMemsetAsync(m->flags, 0, f, s));
+    CKJ(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
+    CKJ(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
+    CKJ(cudaEventRecord(j->b.ev0, s));
+    CKJ(j->dense ? launch_chain<3>(j, s) : launch_chain<2>(j, s));
+    c->launches++;
+    CKJ(cudaEventRecord(j->b.ev1, s));
+    k->stream_busy[sn]++;
+    D.chains += j->n_chain; D.by_bps[j->bps]++;
+    j->state.store(JOB_RUNNING);
+    CKJ(cudaLaunchHostFunc(s, cb_chain_done, j));
+    if(j->has_up)
+        for(int q = 0; q < 3; q++)
+            CKJ(cudaMemcpy2DAsync(j->up.buf[q] + (size_t)j->up.pad[q] * j->up.s[q] + j->up.pad[q], (size_t)j->up.s[q] * 2,
+                                  j->rp.buf[q] + (size_t)j->rp.pad[q] * j->rp.s[q] + j->rp.pad[q], (size_t)j->rp.s[q] * 2, (size_t)j->rp.w[q] * 2,
+                                  j->rp.h[q], cudaMemcpyDeviceToDevice, s));
+    if(j->deblock && xb200_deblock_dev(c, j->rp, &j->P.pp.df, m->scu, m->refi, m->mv, m->flags, s)) return false;
+    if(xb200_pad_planes(c, j->rp, s)) return false;
+    CKJ(cudaEventRecord(j->b.ev2, s));
+    CKJ(cudaLaunchHostFunc(s, cb_ready, j));
+    return true;
+}
+
+void sched_thread(DeviceSched *Dp)
+{
+    DeviceSched &D = *Dp;
+    cudaSetDevice(D.device);
+    std::vector<std::pair<Job *, int>> ev;
     for(;;) {
-        cudaEvent_t wait_on = nullptr;
         {
-            std::lock_guard<std::mutex> dl(D.mu);
-            while(!D.inflight.empty()) {
-                Job *j = D.inflight.front();
-                if(!j->retired) {
-                    const cudaError_t e = cudaEventQuery(j->b.ev1);
-                    if(e == cudaErrorNotReady) break;
-                    if(e != cudaSuccess) CK(e);
-                    j->retired = true;
-                    D.chains -= j->n_chain; D.by_bps[j->bps]--;
-                }
-                D.inflight.pop_front();
-            }
-            if(chains_out) *chains_out = D.chains;
-            if(min_bps_out) *min_bps_out = D.min_bps();
-            if(need <= 0 || D.inflight.empty()) return XB200_OK;
-            const int mb = D.min_bps(), b = mb && mb < bps ? mb : bps;
-            if(D.chains + need <= b * c->sms) return XB200_OK;
-            wait_on = D.inflight.front()->b.ev1;
+            std::unique_lock<std::mutex> cl(D.cb_mu);
+            D.cv_work.wait(cl, [&] { return D.wake || D.stop; });
+            if(D.stop) return;
+            D.wake = false;
+            ev.clear();
+            ev.swap(D.events);
         }
-        lk.unlock();
-        const cudaError_t er = cudaEventSynchronize(wait_on);
-        lk.lock();
-        if(er != cudaSuccess) CK(er);
+        std::lock_guard<std::mutex> lk(D.mu);
+        bool any_ready = false;
+        for(auto &e : ev) {
+            Job *j = e.first;
+            if(e.second == 0) {
+                D.chains -= j->n_chain; D.by_bps[j->bps]--;
+                j->state.store(JOB_CHAIN_DONE);
+            }
+            else {
+                j->m->ready.store(j->life);
+                cc_of(j->c)->stream_busy[j->stream_no]--;
+                j->state.store(JOB_READY);
+                any_ready = true;
+            }
+        }
+        // launch, in enqueue order, every queued picture whose references are complete and whose chains fit
+        for(auto it = D.pending.begin(); it != D.pending.end();) {
+            Job *j = *it;
+            bool ok = true;
+            for(int d = 0; d < j->n_dep && ok; d++) ok = j->deps[d].m->ready.load() >= j->deps[d].life;
+            if(ok) {
+                // kernel variant by load: k_chain<2> (255 registers) is the fastest chain, k_chain<3> (170 registers) lets three chains
+                // share an SM -- as many as the shared memory of a B picture allows.  A lone context whose chains fit keeps the fast
+                // variant; several contexts (streams sharing the device) or a full device take the dense one.  XB200_CHAIN_DENSE=0 / 1
+                // forces one.
+                static const char *dense_env = getenv("XB200_CHAIN_DENSE");
+                const int mb = D.min_bps();
+                const int b_fast = mb && mb < j->b_fast ? mb : j->b_fast;
+                j->dense = dense_env ? dense_env[0] == '1' : (D.n_ctx > 1 || D.chains + j->n_chain > b_fast * D.sms);
+                j->bps = j->dense ? j->b_dense : j->b_fast;
+                const int b = mb && mb < j->bps ? mb : j->bps;
+                ok = D.chains + j->n_chain <= b * D.sms;
+            }
+            if(!ok) { ++it; continue; }
+            it = D.pending.erase(it);
+            if(!launch_job(D, j)) {
+                j->state.store(JOB_FAILED);
+                any_ready = true;
+            }
+        }
+        if(any_ready) D.cv_done.notify_all();
     }
 }
 
-template <int MB> int launch_chain(xb200_ctx *c, const ChainPic &P, size_t smem, cudaStream_t s)
+// wait until the job is complete (or failed); called with the CONTEXT mutex released
+int wait_job(Job *j)
 {
-    k_chain<MB><<<P.n_chain, CH_T, smem, s>>>(c->d_pics, P, c->d_tm64, c->sq, c->d_err);
-    c->launches++;
-    CK(cudaGetLastError());
-    return XB200_OK;
+    DeviceSched &D = g_sched[j->c->device & 63];
+    std::unique_lock<std::mutex> lk(D.mu);
+    D.cv_done.wait(lk, [&] { const int st = j->state.load(); return st == JOB_READY || st == JOB_FAILED; });
+    return j->state.load() == JOB_READY ? XB200_OK : XB200_ERR_UNEXPECTED;
 }
 
 } // namespace
@@ -269,26 +389,28 @@ template <int MB> int launch_chain(xb200_ctx *c, const ChainPic &P, size_t smem,
 void xb200_chain_free(xb200_ctx *c)
 {
     if(!c || !c->chain) return;
-    ChainCtx *k = cc_of(c);
-    cudaDeviceSynchronize();
-    DeviceLoad &D = g_dev_load[c->device & 63];
-    {
-        std::lock_guard<std::mutex> dl(D.mu);
-        for(auto &kv : k->jobs) {
-            Job *j = kv.second;
-            if(!j->retired) { D.chains -= j->n_chain; D.by_bps[j->bps]--; }
-            for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
-                if(*q == j) { D.inflight.erase(q); break; }
-            bufs_free(j->b, D);
-            delete j;
-        }
-        for(auto &b : k->pool) bufs_free(b, D);
+    ChainCtx    *k = cc_of(c);
+    DeviceSched &D = g_sched[c->device & 63];
+    {   // pictures of this context that were never launched leave the queue; the launched ones are waited for
+        std::unique_lock<std::mutex> lk(D.mu);
+        for(auto it = D.pending.begin(); it != D.pending.end();)
+            if((*it)->c == c) { (*it)->state.store(JOB_FAILED); it = D.pending.erase(it); }
+            else ++it;
+        D.cv_done.wait(lk, [&] {
+            for(auto &kv : k->jobs) { const int st = kv.second->state.load(); if(st == JOB_RUNNING || st == JOB_CHAIN_DONE) return false; }
+            return true;
+        });
         if(k->ready) D.n_ctx--;
     }
-    for(auto &m : k->maps) {
-        for(void *p : {(void *)m.scu, (void *)m.ipm, (void *)m.refi, (void *)m.mv, (void *)m.flags})
+    for(int i = 0; i < N_STREAMS; i++)
+        if(k->streams[i]) cudaStreamSynchronize(k->streams[i]);
+    for(auto &kv : k->jobs) { bufs_free(kv.second->b); delete kv.second; }
+    for(auto &b : k->pool) bufs_free(b);
+    for(PicMaps *m : k->maps) {
+        if(!m) continue;
+        for(void *p : {(void *)m->scu, (void *)m->ipm, (void *)m->refi, (void *)m->mv, (void *)m->flags})
             if(p) cudaFree(p);
-        if(m.ready) cudaEventDestroy(m.ready);
+        delete m;
     }
     if(k->zero_mv) cudaFree(k->zero_mv);
     for(int i = 0; i < N_STREAMS; i++)
@@ -334,7 +456,7 @@ int xb200_picture_adopt(xb200_ctx *c, int32_t pic, const int16_t *map_mv)
     PicMaps *m;
     if((r = maps_of(c, pic, &m))) return r;
     CK(cudaMemcpy(m->mv, map_mv, cc_of(c)->f_scu * 8, cudaMemcpyHostToDevice));
-    m->has_ready = false;   // nothing in flight writes it
+    m->ready.store(m->issued);   // nothing in flight writes it
     return XB200_OK;
 }
 
@@ -409,77 +531,47 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
     if((r = maps_of(c, pp->rec_pic, &m))) return r;
     P.map_scu = m->scu; P.map_ipm = m->ipm; P.map_refi = m->refi; P.map_mv = m->mv; P.df_flags = m->flags;
     P.col0 = P.col1 = k->zero_mv;
-    cudaStream_t s = k->streams[k->next_stream];
-    k->next_stream = (k->next_stream + 1) % N_STREAMS;
+    Job *j = new Job();
+    j->c = c; j->rec_pic = pp->rec_pic; j->m = m;
+    // what has to be complete before the picture may start: its reference pictures (if something in flight still writes them) and
+    // the previous life of its own handle.  Readers of that previous life are the caller's business, as before: a handle is reused
+    // only after every picture that referenced it has been fetched.
     if(pp->slice_type == 0) {
         for(int l = 0; l < 2; l++)
             for(int q = 0; q < pp->num_refp[l]; q++) {
                 const int h = pp->ref_pic[l][q];
-                if(h < (int)k->maps.size() && k->maps[h].mv) {
-                    if(q == 0) (l ? P.col1 : P.col0) = k->maps[h].mv;
-                    if(k->maps[h].has_ready) CK(cudaStreamWaitEvent(s, k->maps[h].ready, 0));
+                PicMaps  *rm = h < (int)k->maps.size() ? k->maps[h] : nullptr;
+                if(rm && rm->mv) {
+                    if(q == 0) (l ? P.col1 : P.col0) = rm->mv;
+                    if(rm->ready.load() < rm->issued) { j->deps[j->n_dep].m = rm; j->deps[j->n_dep].life = rm->issued; j->n_dep++; }
                 }
-                else if(q == 0) return XB200_ERR_INVALID_ARGUMENT;   // a reference picture needs its motion map (decided here or adopted)
+                else if(q == 0) { delete j; return XB200_ERR_INVALID_ARGUMENT; }   // a reference picture needs its motion map (decided here or adopted)
             }
     }
-    if(m->has_ready) CK(cudaStreamWaitEvent(s, m->ready, 0));   // an earlier life of this handle
-    // Kernel variant by load: k_chain<2> (255 registers) is the fastest chain, k_chain<3> (170 registers) lets three chains share an
-    // SM -- as many as the shared memory of a B picture allows (60 - 71 KB per chain: the 64x64 working sets).  A lone context whose chains fit keeps the fast
-    // variant; several contexts (streams sharing the device) or a full device take the dense one.  XB200_CHAIN_DENSE=0 / 1 forces one.
-    int b2 = 0, b4 = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_chain<2>, CH_T, smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chain<3>, CH_T, smem));
-    if(b2 < 1 || b4 < 1) return XB200_ERR_UNSUPPORTED;
-    int dev_chains = 0, dev_min = 0, n_ctx = 1;
-    if((r = admit(c, 0, 1, lk, &dev_chains, &dev_min))) return r;     // retire what has finished
-    {
-        DeviceLoad &D = g_dev_load[c->device & 63];
-        std::lock_guard<std::mutex> dl(D.mu);
-        n_ctx = D.n_ctx;
-    }
-    const char *dense_env = getenv("XB200_CHAIN_DENSE");
-    const int   b_fast = dev_min && dev_min < b2 ? dev_min : b2;
-    const bool  dense = dense_env ? dense_env[0] == '1' : (n_ctx > 1 || dev_chains + P.n_chain > b_fast * c->sms);
-    const int   bps = dense ? b4 : b2;
-    if(P.n_chain > bps * c->sms) return XB200_ERR_UNSUPPORTED;
-    if((r = admit(c, P.n_chain, bps, lk))) return r;
-
-    Job *j = new Job();
+    if(m->ready.load() < m->issued) { j->deps[j->n_dep].m = m; j->deps[j->n_dep].life = m->issued; j->n_dep++; }
+    // CTAs of this picture an SM can hold, per kernel variant (registers x shared memory of this picture)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j->b_fast, k_chain<2>, CH_T, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j->b_dense, k_chain<3>, CH_T, smem));
+    if(j->b_fast < 1 || j->b_dense < 1 || P.n_chain > j->b_dense * c->sms) { delete j; return XB200_ERR_UNSUPPORTED; }
     if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
-    j->rec_pic = pp->rec_pic; j->n_chain = P.n_chain; j->bps = bps;
+    j->n_chain = P.n_chain;
     P.scu_out = j->b.scu; P.coef_out = j->b.coef; P.ctu_state = j->b.ctu_state; P.ctu_cost = j->b.ctu_cost; P.done = j->b.done;
     P.counts = j->b.counts; P.ws = j->b.ws;
     if(k->log_cu > 0) { P.cu_log = j->b.cu_log; P.cu_cap = k->log_cu; }
     if(k->log_intra > 0) { P.intra_log = j->b.intra_log; P.intra_cap = k->log_intra; }
-    const size_t f = k->f_scu;
-    if(!k->span_on) { CK(cudaEventRecord(k->ev_span0, s)); k->span_on = true; k->span_ms = 0.f; }
-    CK(cudaMemsetAsync(m->scu, 0, f * 4, s)); CK(cudaMemsetAsync(m->ipm, 0, f, s)); CK(cudaMemsetAsync(m->refi, 0, f * 2, s));
-    CK(cudaMemsetAsync(m->mv, 0, f * 8, s)); CK(cudaMemsetAsync(m->flags, 0, f, s));
-    CK(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
-    CK(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
-    CK(cudaEventRecord(j->b.ev0, s));
-    if((r = dense ? launch_chain<3>(c, P, smem, s) : launch_chain<2>(c, P, smem, s))) { k->pool.push_back(j->b); delete j; return r; }
-    CK(cudaEventRecord(j->b.ev1, s));
-    Pic &rp = c->pics[pp->rec_pic];
-    if(pp->unfiltered_pic >= 0) {
-        Pic &up = c->pics[pp->unfiltered_pic];
-        for(int q = 0; q < 3; q++)
-            CK(cudaMemcpy2DAsync(up.buf[q] + (size_t)up.pad[q] * up.s[q] + up.pad[q], (size_t)up.s[q] * 2,
-                                 rp.buf[q] + (size_t)rp.pad[q] * rp.s[q] + rp.pad[q], (size_t)rp.s[q] * 2, (size_t)rp.w[q] * 2, rp.h[q],
-                                 cudaMemcpyDeviceToDevice, s));
-    }
-    if(pp->deblock && (r = xb200_deblock_dev(c, rp, &P.pp.df, m->scu, m->refi, m->mv, m->flags, s))) return r;
-    if((r = xb200_pad_planes(c, rp, s))) return r;
-    CK(cudaEventRecord(j->b.ev2, s));
-    CK(cudaEventRecord(m->ready, s));
-    m->has_ready = true;
+    j->P = P; j->smem = smem;
+    j->rp = c->pics[pp->rec_pic];
+    j->has_up = pp->unfiltered_pic >= 0;
+    if(j->has_up) j->up = c->pics[pp->unfiltered_pic];
+    j->deblock = pp->deblock != 0;
+    j->life = ++m->issued;
     k->jobs[pp->rec_pic] = j;
+    DeviceSched &D = g_sched[c->device & 63];
     {
-        DeviceLoad &D = g_dev_load[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
-        D.inflight.push_back(j);
-        D.chains += j->n_chain; D.by_bps[j->bps]++;
+        D.pending.push_back(j);
     }
+    sched_kick(D);
     return XB200_OK;
 }
 
@@ -494,13 +586,17 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
     if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
     Job *j = it->second;
     {
-        cudaEvent_t e = j->b.ev2;
         lk.unlock();
-        const cudaError_t er = cudaEventSynchronize(e);
+        const int wr = wait_job(j);
         lk.lock();
-        if(er != cudaSuccess) CK(er);
         it = k->jobs.find(rec_pic);
         if(it == k->jobs.end() || it->second != j) return XB200_ERR_INVALID_ARGUMENT;
+        if(wr) {   // the launch failed (reported on stderr by the scheduler): nothing to fetch
+            k->pool.push_back(j->b);
+            k->jobs.erase(it);
+            delete j;
+            return wr;
+        }
     }
     const size_t n = (size_t)k->n_lcu;
     if(scu) CK(cudaMemcpyAsync(scu, j->b.scu, n * 256 * sizeof(xb200_scu_rec), cudaMemcpyDeviceToHost, k->copy));
@@ -518,22 +614,30 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
         cudaEventElapsedTime(&b, j->b.ev1, j->b.ev2);
         stat->n_inter = (int64_t)cnt[0]; stat->n_intra = (int64_t)cnt[1]; stat->chain_ms = a; stat->filter_ms = b;
     }
-    if(k->span_on) {
-        float sp = 0.f;
-        if(cudaEventElapsedTime(&sp, k->ev_span0, j->b.ev2) == cudaSuccess && sp > k->span_ms) k->span_ms = sp;
-    }
     {
-        DeviceLoad &D = g_dev_load[c->device & 63];
+        DeviceSched &D = g_sched[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
-        if(!j->retired) { j->retired = true; D.chains -= j->n_chain; D.by_bps[j->bps]--; }
-        for(auto q = D.inflight.begin(); q != D.inflight.end(); ++q)
-            if(*q == j) { D.inflight.erase(q); break; }
+        if(k->span_on) {
+            float sp = 0.f;
+            if(cudaEventElapsedTime(&sp, k->ev_span0, j->b.ev2) == cudaSuccess && sp > k->span_ms) k->span_ms = sp;
+        }
     }
     k->pool.push_back(j->b);
     k->jobs.erase(it);
     delete j;
     if(err) { fprintf(stderr, "xeve_b200: search window overflow inside the decision pass\n"); return XB200_ERR_UNEXPECTED; }
     return XB200_OK;
+}
+
+int xb200_picture_ready(xb200_ctx *c, int32_t rec_pic)
+{
+    if(!c || !c->chain) return XB200_ERR_INVALID_ARGUMENT;
+    ChainCtx *k = cc_of(c);
+    std::unique_lock<std::mutex> lk(k->mu);
+    auto it = k->jobs.find(rec_pic);
+    if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
+    const int st = it->second->state.load();
+    return st == JOB_READY || st == JOB_FAILED ? 1 : 0;
 }
 
 int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_intra_item *intra, int64_t n[2])
@@ -545,7 +649,10 @@ int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_in
     auto it = k->jobs.find(rec_pic);
     if(it == k->jobs.end()) return XB200_ERR_INVALID_ARGUMENT;
     Job *j = it->second;
-    CK(cudaEventSynchronize(j->b.ev2));
+    lk.unlock();
+    const int wr = wait_job(j);
+    lk.lock();
+    if(wr) return wr;
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpy(cnt, j->b.counts, sizeof(cnt), cudaMemcpyDeviceToHost));
     n[0] = (int64_t)cnt[0] < k->log_cu ? (int64_t)cnt[0] : k->log_cu;
@@ -573,7 +680,7 @@ double xb200_chain_span_ms(xb200_ctx *c, int reset)
 {
     if(!c || !c->chain) return -1.0;
     ChainCtx *k = cc_of(c);
-    std::unique_lock<std::mutex> lk(k->mu);
+    std::lock_guard<std::mutex> dl(g_sched[c->device & 63].mu);
     const double v = k->span_ms;
     if(reset) { k->span_on = false; k->span_ms = 0.f; }
     return v;
@@ -598,12 +705,22 @@ int xb200_chain_prof(xb200_ctx *c, uint64_t out[64])
 
 int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t *map_ipm, int8_t *map_refi, int16_t *map_mv)
 {
-    if(!c || !c->chain || rec_pic < 0 || rec_pic >= (int)cc_of(c)->maps.size() || !cc_of(c)->maps[rec_pic].scu) return XB200_ERR_INVALID_ARGUMENT;
+    if(!c || !c->chain || rec_pic < 0 || rec_pic >= (int)cc_of(c)->maps.size() || !cc_of(c)->maps[rec_pic] || !cc_of(c)->maps[rec_pic]->scu)
+        return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     ChainCtx *k = cc_of(c);
     std::unique_lock<std::mutex> lk(k->mu);
-    PicMaps  &m = k->maps[rec_pic];
-    if(m.has_ready) CK(cudaEventSynchronize(m.ready));
+    PicMaps  &m = *k->maps[rec_pic];
+    {
+        auto it = k->jobs.find(rec_pic);
+        if(it != k->jobs.end()) {   // still in flight: wait for it
+            Job *j = it->second;
+            lk.unlock();
+            const int wr = wait_job(j);
+            lk.lock();
+            if(wr) return wr;
+        }
+    }
     const size_t f = k->f_scu;
     if(map_scu) CK(cudaMemcpy(map_scu, m.scu, f * 4, cudaMemcpyDeviceToHost));
     if(map_ipm) CK(cudaMemcpy(map_ipm, m.ipm, f, cudaMemcpyDeviceToHost));

@@ -50,9 +50,6 @@ struct ChCud {              // XEVE_CU_DATA of one quad-tree level: 4x4 units in
 struct alignas(16) ChainWs { // private working set of one chain (global memory, L2 resident)
     xb200_cu_item    cu;
     xb200_intra_item in;
-    xb200_rates      rates;
-    xb200_sbac       st_out;
-    ChState          curr[5], next[5], before[5], sdepth[5], chain;
     ChCud            best[5], temp[5];
     alignas(16) int16_t coef[2 * (6144 + 64)];
     alignas(16) int16_t rec_cu[2 * (6144 + 64)];
@@ -92,6 +89,11 @@ struct ChShared {            // control block in shared memory
     uint32_t bphase[4];      // initialised once per kernel, never overlaid by working sets, parities kept here between CUs
     uint32_t bits, phase;
     int32_t  satd;
+    // coder states of the tree walk (core->s_curr_best / s_next_best / s_temp_depth per level, src_base/xeve_type.h) and the rate tables
+    // derived from them: copied at every node, so they live here and not in the chain's global working set
+    ChState     curr[5], next[5], before[5], sdepth[5], chain;
+    xb200_sbac  st_out;
+    xb200_rates rates;
     uint8_t  zinv8[64];
     uint16_t thr_mb[IN_CM_N + 2], thr_mr[IN_CM_N + 2];
 };
@@ -385,7 +387,7 @@ __device__ __noinline__ void ch_inter(unsigned char *team, const int8_t *tm, con
         Tm.tm = tm; Tm.tmT = tmT;
         Tm.scratch = ws->scratch;
         uint32_t phase = S.bphase[0];
-        analyze_cu_one<L2>(Tm, pics, &ws->cu, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->coef, ws->rec_cu, ws->pred_y, sq, win_cap, err_flag,
+        analyze_cu_one<L2>(Tm, pics, &ws->cu, &S.rates, &S.curr[L].s, &S.st_out, ws->coef, ws->rec_cu, ws->pred_y, sq, win_cap, err_flag,
                            phase, t);
         if(t == 0) S.bphase[0] = phase;
     }
@@ -396,23 +398,23 @@ __device__ __noinline__ void ch_inter_par(unsigned char *team, const int8_t *tm,
                                           int L, const SeqDev &sq, int win_cap, int stride, int *err_flag, ChShared &S, int t)
 {
     if(t < CU_PAR_WARPS * 32)
-        analyze_cu_par<L2>(team, stride, S.bar + 1, S.bphase + 1, tm, tmT, pics, &ws->cu, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->coef, ws->rec_cu,
+        analyze_cu_par<L2>(team, stride, S.bar + 1, S.bphase + 1, tm, tmT, pics, &ws->cu, &S.rates, &S.curr[L].s, &S.st_out, ws->coef, ws->rec_cu,
                            ws->pred_y, ws->scratch, sq, win_cap, err_flag, t);
 }
 template <int L2>
 __device__ __noinline__ void ch_intra_team(unsigned char *team, const int8_t *tm, const int8_t *tmT, const PicDev *__restrict__ pics, ChainWs *ws,
-                                           int L, int16_t *coef, int16_t *rec, const SeqDev &sq, int t)
+                                           int L, int16_t *coef, int16_t *rec, const SeqDev &sq, ChShared &S, int t)
 {
     if(t < IntraCfg<L2>::T) {
         IntraTeam<L2> &M = *reinterpret_cast<IntraTeam<L2> *>(team + CH_ME_OFF + 16);
-        intra_cu_one<L2>(M, tm, tmT, pics, ws->in, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->side, coef, rec, sq, t, ws->cand64);
+        intra_cu_one<L2>(M, tm, tmT, pics, ws->in, &S.rates, &S.curr[L].s, &S.st_out, ws->side, coef, rec, sq, t, ws->cand64);
     }
 }
 template <int L2>
 __device__ __noinline__ void ch_intra_thr(const PicDev *__restrict__ pics, ChainWs *ws, int L, int16_t *coef, int16_t *rec, const SeqDev &sq,
                                           ChShared &S, int t)
 {
-    if(t == 0) intra_thr_one<L2, 1>(pics, ws->in, &ws->rates, &ws->curr[L].s, &ws->st_out, ws->side, coef, rec, sq, S.thr_mb, S.thr_mr, S.zinv8);
+    if(t == 0) intra_thr_one<L2, 1>(pics, ws->in, &S.rates, &S.curr[L].s, &S.st_out, ws->side, coef, rec, sq, S.thr_mb, S.thr_mr, S.zinv8);
 }
 
 // mode_coding_unit for the CU (x, y, 4 << L): returns the best cost; cu_mode / dist_cu as the reference's core->cu_mode / dist_cu_best;
@@ -425,7 +427,7 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
     const int log2 = L + 2, cuw = 1 << log2, ny = cuw * cuw, B = pp.slice_type == 0;
     double    cost_best = CH_MAX_COST;
     int       nnz0 = 0, nnz1 = 0, nnz2 = 0;
-    ch_rates(ws->curr[L], ws->rates, t);                       // mode_cu_init -> xeve_rdoq_bit_est
+    ch_rates(S.curr[L], S.rates, t);                       // mode_cu_init -> xeve_rdoq_bit_est
     cu_mode = CH_INTRA;
     if(pp.slice_type != 2 && L >= 1) {                         // mode_check_inter
         xb200_cu_item &cu = ws->cu;
@@ -478,9 +480,9 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
         nnz0 = cu.nnz[0]; nnz1 = cu.nnz[1]; nnz2 = cu.nnz[2];
         const double c = cu.cost;
         // SBAC_STORE(s_next_best, s_temp_best): the models of the inter syntax; ctx.intra_dir / split stay those of s_curr_best
-        ch_state_copy(&ws->next[L], &ws->curr[L], t);
+        ch_state_copy(&S.next[L], &S.curr[L], t);
         __syncthreads();
-        ch_copy32(&ws->next[L].s, &ws->st_out, (int)sizeof(xb200_sbac) / 4, t);
+        ch_copy32(&S.next[L].s, &S.st_out, (int)sizeof(xb200_sbac) / 4, t);
         if(c < cost_best) {
             cost_best = c;
             ch_store_cu(ws->temp[L], L, cu_mode, 0, pp.tile_qp, &cu, cu.nnz, ws->coef, ws->rec_cu, t);
@@ -501,7 +503,7 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
             it.pad0_[0] = it.pad0_[1] = 0;
             it.inter_satd = inter_satd;
             it.rate_idx = 0; it.state_in = 0; it.state_out = 0;
-            it.cm_ipm_in[0] = ws->curr[L].ipm[0]; it.cm_ipm_in[1] = ws->curr[L].ipm[1];
+            it.cm_ipm_in[0] = S.curr[L].ipm[0]; it.cm_ipm_in[1] = S.curr[L].ipm[1];
             it.cm_ipm_out[0] = it.cm_ipm_out[1] = 0;
             it.sqrt_lambda0 = pp.sqrt_lambda0;
             it.dist_chroma_weight[0] = pp.dist_chroma_weight[0]; it.dist_chroma_weight[1] = pp.dist_chroma_weight[1];
@@ -513,16 +515,16 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
         int16_t *coef_i = ws->coef + 3 * ny / 2 + 64, *rec_i = ws->rec_cu + 3 * ny / 2 + 64;
         switch(log2) {
         case 2:
-            if(P.small_team & 1) ch_intra_team<2>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t);
+            if(P.small_team & 1) ch_intra_team<2>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, S, t);
             else ch_intra_thr<2>(pics, ws, L, coef_i, rec_i, sq, S, t);
             break;
         case 3:
-            if(P.small_team & 2) ch_intra_team<3>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t);
+            if(P.small_team & 2) ch_intra_team<3>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, S, t);
             else ch_intra_thr<3>(pics, ws, L, coef_i, rec_i, sq, S, t);
             break;
-        case 4: ch_intra_team<4>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
-        case 5: ch_intra_team<5>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
-        default: ch_intra_team<6>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, t); break;
+        case 4: ch_intra_team<4>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, S, t); break;
+        case 5: ch_intra_team<5>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, S, t); break;
+        default: ch_intra_team<6>(team, tm, tmT, pics, ws, L, coef_i, rec_i, sq, S, t); break;
         }
         __syncthreads();
         CU_PROF_T(9);
@@ -533,10 +535,10 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
             cost_best = c;
             cu_mode = CH_INTRA;
             dist_cu_best = it.dist_cu;
-            ch_state_copy(&ws->next[L], &ws->curr[L], t);
+            ch_state_copy(&S.next[L], &S.curr[L], t);
             __syncthreads();
-            ch_copy32(&ws->next[L].s, &ws->st_out, (int)sizeof(xb200_sbac) / 4, t);
-            if(t == CH_T - 1) { ws->next[L].ipm[0] = it.cm_ipm_out[0]; ws->next[L].ipm[1] = it.cm_ipm_out[1]; }
+            ch_copy32(&S.next[L].s, &S.st_out, (int)sizeof(xb200_sbac) / 4, t);
+            if(t == CH_T - 1) { S.next[L].ipm[0] = it.cm_ipm_out[0]; S.next[L].ipm[1] = it.cm_ipm_out[1]; }
             ch_store_cu(ws->temp[L], L, CH_INTRA, it.ipm[0], pp.tile_qp, nullptr, it.nnz, coef_i, rec_i, t);
         }
         __syncthreads();
@@ -567,8 +569,8 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
     if(t == 0) g_prof_last = clock64();
 #endif
     // xeve_sbac_reset with cm_init off: every model PROB_INIT, range 16384
-    if(t < XB200_CM_COUNT) ws->chain.s.m[t] = 512;
-    if(t == XB200_CM_COUNT) { ws->chain.s.range = 16384; ws->chain.ipm[0] = ws->chain.ipm[1] = ws->chain.split = 512; ws->chain.pad_ = 0; }
+    if(t < XB200_CM_COUNT) S.chain.s.m[t] = 512;
+    if(t == XB200_CM_COUNT) { S.chain.s.range = 16384; S.chain.ipm[0] = S.chain.ipm[1] = S.chain.split = 512; S.chain.pad_ = 0; }
     __syncthreads();
 
     const int    intra_slice = pp.slice_type == 2;
@@ -589,8 +591,8 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                 __syncthreads();
             }
             ch_cud_init(ws->best[4], 4, t); ch_cud_init(ws->temp[4], 4, t);  // mode_init_lcu
-            ch_state_copy(&ws->curr[4], &ws->chain, t);
-            if(P.ctu_state) ch_state_copy(&P.ctu_state[2 * lcu], &ws->chain, t);
+            ch_state_copy(&S.curr[4], &S.chain, t);
+            if(P.ctu_state) ch_state_copy(&P.ctu_state[2 * lcu], &S.chain, t);
             __syncthreads();
 
             // ---- mode_coding_tree as a state machine; node state per level ----
@@ -605,12 +607,12 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                     const int boundary = !(x0 + cuw <= P.w && y0 + cuw <= P.h);
                     int       next_split = 1, cu_mode = 0, dist_cu = 0;
                     double    cost_best = CH_MAX_COST;
-                    for(int i = t; i < CH_STATE_WORDS; i += CH_T) reinterpret_cast<uint32_t *>(&ws->sdepth[L])[i] = 0;
-                    ch_state_copy(&ws->before[L], &ws->curr[L], t);
+                    for(int i = t; i < CH_STATE_WORDS; i += CH_T) reinterpret_cast<uint32_t *>(&S.sdepth[L])[i] = 0;
+                    ch_state_copy(&S.before[L], &S.curr[L], t);
                     __syncthreads();
                     if(!boundary && cuw <= check_max) {
                         double cost_temp = 0.0;
-                        if(cuw > 4) cost_temp = __dadd_rn(cost_temp, __dmul_rn((double)ch_split_flag(&ws->curr[L], cuw, 0, S, t), lambda0));
+                        if(cuw > 4) cost_temp = __dadd_rn(cost_temp, __dmul_rn((double)ch_split_flag(&S.curr[L], cuw, 0, S, t), lambda0));
                         ch_cud_init(ws->temp[L], L, t);
                         ch_clear_map(P, x0, y0, cuw, t);
                         __syncthreads();
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                             cu_mode = um; dist_cu = ud;
                             ch_cud_copy(ws->best[L], L, ws->temp[L], L, 0, 0, t);
                             cost_best = cost_dqp;
-                            ch_state_copy(&ws->sdepth[L], &ws->next[L], t);
+                            ch_state_copy(&S.sdepth[L], &S.next[L], t);
                             __syncthreads();
                             ch_rec_to_pic(P, ws->best[L], x0, y0, L, t);
                         }
@@ -639,9 +641,9 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                     if(cuw > 4 && next_split && cuw > check_min) {
                         ch_cud_init(ws->temp[L], L, t);
                         ch_clear_map(P, x0, y0, cuw, t);
-                        ch_state_copy(&ws->curr[L], &ws->before[L], t);
+                        ch_state_copy(&S.curr[L], &S.before[L], t);
                         __syncthreads();
-                        ctemp[L] = __dadd_rn(0.0, __dmul_rn((double)ch_split_flag(&ws->curr[L], cuw, 1, S, t), lambda0));
+                        ctemp[L] = __dadd_rn(0.0, __dmul_rn((double)ch_split_flag(&S.curr[L], cuw, 1, S, t), lambda0));
                         npart[L] = 0;
                         st = NEXT_PART;
                     }
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                     while(npart[L] < 4) {
                         const int part = npart[L], xp = x0 + (part & 1) * half, yp = y0 + (part >> 1) * half;
                         if(xp < P.w && yp < P.h) {
-                            ch_state_copy(&ws->curr[L - 1], part == 0 ? &ws->curr[L] : &ws->next[L - 1], t);
+                            ch_state_copy(&S.curr[L - 1], part == 0 ? &S.curr[L] : &S.next[L - 1], t);
                             __syncthreads();
                             nx[L - 1] = xp; nyy[L - 1] = yp; ncud[L - 1] = ncud[L] + 2;   // a quad split is two levels of the split tree
                             L--;
@@ -666,7 +668,7 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                     if(__dadd_rn(cbest[L], -0.0001) > ctemp[L]) {
                         ch_cud_copy(ws->best[L], L, ws->temp[L], L, 0, 0, t);
                         cbest[L] = ctemp[L];
-                        ch_state_copy(&ws->sdepth[L], &ws->next[L - 1], t);
+                        ch_state_copy(&S.sdepth[L], &S.next[L - 1], t);
                         __syncthreads();
                     }
                     st = FINISH;
@@ -674,7 +676,7 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
                 else { // FINISH
                     __syncthreads();
                     ch_rec_to_pic(P, ws->best[L], nx[L], nyy[L], L, t);
-                    ch_state_copy(&ws->next[L], &ws->sdepth[L], t);
+                    ch_state_copy(&S.next[L], &S.sdepth[L], t);
                     __syncthreads();
                     const double ret = cbest[L] > CH_MAX_COST ? CH_MAX_COST : cbest[L];
                     if(L == 4) { if(P.ctu_cost && t == 0) P.ctu_cost[lcu] = ret; break; }
@@ -692,8 +694,8 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
             // ---- mode_analyze_lcu tail: update_to_ctx_map; the bitstream pass then marks the luma cbf (src_base/xeve_eco.c:1575-1603) ----
             const ChCud &b = ws->best[4];
             ch_update_map(P, b, xc, yc, 4, t);
-            ch_state_copy(&ws->chain, &ws->next[4], t);   // B / I slices: the next CTU starts from the state this decision pass ended with
-            if(P.ctu_state) ch_state_copy(&P.ctu_state[2 * lcu + 1], &ws->next[4], t);
+            ch_state_copy(&S.chain, &S.next[4], t);   // B / I slices: the next CTU starts from the state this decision pass ended with
+            if(P.ctu_state) ch_state_copy(&P.ctu_state[2 * lcu + 1], &S.next[4], t);
             __syncthreads();
             {
                 const int wsu = (xc + 64 > P.w ? P.w - xc : 64) >> 2, hsu = (yc + 64 > P.h ? P.h - yc : 64) >> 2;
