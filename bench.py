@@ -334,6 +334,32 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
     return out
 
 
+def run_secondary(args, name, streams, frames):
+    """A second workload on the same line (north_star's target configuration: 3840x2160 10-bit preset fast): S streams x F pictures
+    through the public API of the drop-in library, one timed pass, next to the same program on the unmodified reference library; the
+    bitstreams are compared.  N = 1, rank 0 only."""
+    import copy
+    a = copy.copy(args)
+    a.workload, a.streams, a.frames = name, streams, frames
+    c, preset, _, yuv = make_clip(a)
+    path = f"/dev/shm/xb200_bench2_{os.getpid()}.yuv"
+    yuv.tofile(path)
+    try:
+        n_inst = max(1, min(usable_cores() // max(a.threads, 1), streams))
+        rp = run_streams("xeveb_streams_ref", path, c, preset, frames, n_inst, a.threads, 1, path + ".ref")
+        ref_md5 = sorted(set(stream_md5s(path + ".ref", n_inst)))
+        env = dict(os.environ, XB200_DEVICE=os.environ.get("LOCAL_RANK", "0"), XB200_QUIET="1")
+        dp = run_streams("xb200_streams", path, c, preset, frames, streams, a.threads, 1, path + ".dev", env=env)
+        dev_md5 = sorted(set(stream_md5s(path + ".dev", streams)))
+    finally:
+        os.unlink(path)
+    return {"workload": workload_string(a, c, preset), "e2e": {"value": round(streams * frames / dp[0]["wall_s"], 3), "unit": "pictures/s"},
+            "reference": {"value": round(n_inst * frames / rp[0]["wall_s"], 3), "unit": "pictures/s", "cores": n_inst * a.threads,
+                          "sample": f"{n_inst} concurrent stream(s) x {a.threads} threads"},
+            "bitstream_matches_reference": dev_md5 == ref_md5 and len(ref_md5) == 1, "passes": 1,
+            "device_ms_per_picture": round(float(np.mean([st["chain_ms"] for st in dp[0]["per_stream"]])) / frames, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,6 +370,7 @@ def main():
     ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
     ap.add_argument("--frames", type=int, default=33, help="pictures per stream (33 = the intra picture + two GOPs of 16)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
+    ap.add_argument("--second", default="2160p10:4:17", help="second workload reported on the same line (name:streams:frames), '' to skip")
     args = ap.parse_args()
     # exactly ONE line on stdout: everything libraries print (NCCL's version banner, torchrun notices) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -375,6 +402,12 @@ def main():
     if rank == 0:
         if ref and "cpu_baseline" in ref:
             out["cpu_baseline"] = ref["cpu_baseline"]
+        if args.second and world == 1:
+            try:
+                nm, st_, fr_ = args.second.split(":")
+                out["second_workload"] = run_secondary(args, nm, int(st_), int(fr_))
+            except Exception as e:  # noqa: BLE001 -- the headline stands on its own
+                out["second_workload"] = {"error": str(e)[:300]}
         emit(out)
     if world > 1:
         dist.barrier()

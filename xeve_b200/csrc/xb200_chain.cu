@@ -99,7 +99,9 @@ struct DeviceSched {
     std::thread             th;
     int min_bps() const { for(int b = 1; b <= 32; b++) if(by_bps[b]) return b; return 0; }
 };
-DeviceSched g_sched[64];
+// Never destroyed: the (detached) scheduler threads wait on these condition variables until the process exits, and destroying a
+// condition variable that has a waiter blocks (glibc) -- a static array's destructor would hang every process at exit.
+DeviceSched *const g_sched = new DeviceSched[64];
 
 struct ChainCtx {
     std::mutex   mu;                    // host-side bookkeeping: one thread may enqueue pictures while another fetches results
