@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
     ap.add_argument("--frames", type=int, default=33, help="pictures per stream (33 = the intra picture + two GOPs of 16)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
-    ap.add_argument("--second", default="2160p10:4:17", help="second workload reported on the same line (name:streams:frames), '' to skip")
+    ap.add_argument("--second", default="2160p10:12:17", help="second workload reported on the same line (name:streams:frames), '' to skip")
     args = ap.parse_args()
     # exactly ONE line on stdout: everything libraries print (NCCL's version banner, torchrun notices) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")

@@ -69,19 +69,18 @@ struct Job {
     Dep         deps[2 * XB200_MAX_REFP + 1];
     int         n_dep = 0;
     int         stream_no = -1;
+    int         slot = -1;              // picture slot of the chain server while its chains run
+    unsigned    seq = 0;
+    unsigned long long t_chain[2] = {0, 0};   // %globaltimer: first chain started, last chain finished
     std::atomic<int> state{JOB_PENDING};
 };
 
 // ---- the device scheduler ------------------------------------------------------------------------------------------------------------
-// Pictures are LAUNCHED when their reference pictures are complete, not when they are enqueued: a kernel that sits in a stream behind
-// an event holds no SM, but admission has to count it (a chain that cannot become resident while its siblings spin on its flags
-// dead-locks), so enqueue-time admission filled the device's books with pictures that were not running (12 streams: 62 chains busy of
-// 444).  One scheduler thread per device owns the launches of every context of the process: xb200_analyze_picture only queues the
-// picture; completion callbacks (cudaLaunchHostFunc) wake the thread, which launches every queued picture whose references are ready
-// and whose chains fit.  Capacity rule: CTAs of different pictures have different footprints (kernel variant, shared memory by CU
-// sizes / search range).  With b = the smallest CTAs-per-SM figure among the pictures whose chains are running and the new one, the
-// device holds at most b x SMs CTAs; then an SM that cannot take a CTA of the largest footprint (<= 1/b of an SM) already holds >= b
-// CTAs, so while fewer than b x SMs are resident some SM can take it.
+// One scheduler thread per device owns the chain server (xb200_chain.cuh) and serves every context of the process:
+// xb200_analyze_picture only queues the picture.  A picture is PUBLISHED to the workers when its reference pictures are complete
+// (host side; a chain that has to wait for a reference would hold a worker) and the workers can take all its chains at once; when
+// its last chain has finished (a word in host-mapped memory, polled) the loop filter and the border expansion are launched on one of
+// the context's streams, and their completion callback makes the picture a usable reference.
 struct DeviceSched {
     std::mutex              mu;              // scheduler state below; held by the scheduler thread while it launches
     std::condition_variable cv_done;         // a picture became complete (waiters: xb200_picture_fetch & co.)
@@ -91,13 +90,27 @@ struct DeviceSched {
     std::condition_variable cv_work;
     std::vector<std::pair<Job *, int>> events;   // {job, 0: decision kernel finished | 1: picture complete}
     std::deque<Job *>       pending;         // enqueue order, all contexts
-    int                     chains = 0;      // CTAs of the pictures whose decision kernel is running
-    int                     by_bps[33] = {}; // those pictures by their CTAs-per-SM figure
+    std::vector<Job *>      running;         // published to the chain server, chains not all finished
+    int                     chains = 0;      // chains published and not finished
     int                     n_ctx = 0;       // contexts with a decision pass on this device
+    // the chain server (xb200_chain.cuh: k_chain_server)
+    ChainQueue             *dq = nullptr;    // device queue
+    volatile unsigned      *h_done = nullptr;// host-mapped completion words, one per picture slot
+    unsigned               *d_done = nullptr;// ... their device address
+    ChainPicTask           *h_slot = nullptr;// pinned staging of the picture records
+    ChainTask              *h_tasks = nullptr;   // pinned mirror of the task ring
+    unsigned               *h_tail = nullptr;    // pinned ring of published tail values (sources of the async copies)
+    int                    *h_flag = nullptr;    // pinned {0, 1}
+    int8_t                 *d_tm64 = nullptr;
+    cudaStream_t            feed = nullptr, srv = nullptr;
+    bool                    server_on = false;
+    size_t                  server_smem = 0;
+    int                     workers = 0;
+    unsigned                tail = 0, seq = 0;
+    std::vector<int>        free_slots;
     int                     sms = 0, device = 0;
     bool                    wake = false, stop = false, started = false;   // wake / stop: guarded by cb_mu
     std::thread             th;
-    int min_bps() const { for(int b = 1; b <= 32; b++) if(by_bps[b]) return b; return 0; }
 };
 // Never destroyed: the (detached) scheduler threads wait on these condition variables until the process exits, and destroying a
 // condition variable that has a waiter blocks (glibc) -- a static array's destructor would hang every process at exit.
@@ -177,15 +190,12 @@ int chain_init(xb200_ctx *c)
     CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
     CK(cudaMemset(k->zero_mv, 0, k->f_scu * 8));
     if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
-    {   // opt-in shared memory of the decision kernel: set ONCE per device to the maximum.  The attribute belongs to the function, not to
-        // a launch: contexts on several host threads setting it to their picture's size would race (launch fails: invalid argument).
+    {   // opt-in shared memory of the worker kernel: set ONCE per device to the maximum (the attribute belongs to the function)
         int optin = 0;
         cudaFuncAttributes fa;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-        CK(cudaFuncGetAttributes(&fa, k_chain<2>));
-        CK(cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-        CK(cudaFuncGetAttributes(&fa, k_chain<3>));
-        CK(cudaFuncSetAttribute(k_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        CK(cudaFuncGetAttributes(&fa, k_chain_server<3>));
+        CK(cudaFuncSetAttribute(k_chain_server<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     }
     CK(cudaDeviceSynchronize());
     k->ready = true;
@@ -256,13 +266,8 @@ void bufs_free(JobBufs &b)
     b = JobBufs();
 }
 
-template <int MB> cudaError_t launch_chain(const Job *j, cudaStream_t s)
-{
-    k_chain<MB><<<j->P.n_chain, CH_T, j->smem, s>>>(j->c->d_pics, j->P, j->c->d_tm64, j->c->sq, j->c->d_err);
-    return cudaGetLastError();
-}
-
-// completion callbacks (run on a CUDA-internal thread: no CUDA calls, no waiting for the scheduler)
+// completion callback of a picture's loop filter + border expansion (runs on a CUDA-internal thread: no CUDA calls, no waiting for
+// the scheduler)
 void post_event(Job *j, int kind)
 {
     DeviceSched &D = g_sched[j->c->device & 63];
@@ -273,7 +278,6 @@ void post_event(Job *j, int kind)
     }
     D.cv_work.notify_one();
 }
-void CUDART_CB cb_chain_done(void *arg) { post_event(static_cast<Job *>(arg), 0); }
 void CUDART_CB cb_ready(void *arg) { post_event(static_cast<Job *>(arg), 1); }
 void sched_kick(DeviceSched &D)
 {
@@ -281,32 +285,118 @@ void sched_kick(DeviceSched &D)
     D.cv_work.notify_one();
 }
 
-// everything of one picture on one stream: clear the maps, the persistent decision kernel, the optional copy of the unfiltered
-// picture, both loop-filter passes, the border expansion.  Called by the scheduler thread with the scheduler mutex held.
 #define CKJ(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { fprintf(stderr, "xeve_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return false; } } while(0)
-bool launch_job(DeviceSched &D, Job *j)
+
+// queue, staging and streams of a device's chain server (once)
+bool server_init(DeviceSched &D, xb200_ctx *c)
+{
+    if(D.dq) return true;
+    CKJ(cudaMalloc(&D.dq, sizeof(ChainQueue)));
+    CKJ(cudaMemset(D.dq, 0, sizeof(ChainQueue)));
+    unsigned *hd = nullptr;
+    CKJ(cudaHostAlloc(&hd, CH_Q_SLOTS * sizeof(unsigned), cudaHostAllocMapped));
+    memset(hd, 0, CH_Q_SLOTS * sizeof(unsigned));
+    D.h_done = hd;
+    CKJ(cudaHostGetDevicePointer(&D.d_done, hd, 0));
+    CKJ(cudaHostAlloc(&D.h_slot, CH_Q_SLOTS * sizeof(ChainPicTask), cudaHostAllocDefault));
+    CKJ(cudaHostAlloc(&D.h_tasks, CH_Q_TASKS * sizeof(ChainTask), cudaHostAllocDefault));
+    CKJ(cudaHostAlloc(&D.h_tail, 4096 * sizeof(unsigned), cudaHostAllocDefault));
+    CKJ(cudaHostAlloc(&D.h_flag, 2 * sizeof(int), cudaHostAllocDefault));
+    D.h_flag[0] = 0; D.h_flag[1] = 1;
+    CKJ(cudaMalloc(&D.d_tm64, 4096));
+    CKJ(cudaMemcpy(D.d_tm64, c->d_tm64, 4096, cudaMemcpyDeviceToDevice));
+    CKJ(cudaStreamCreateWithFlags(&D.feed, cudaStreamNonBlocking));
+    CKJ(cudaStreamCreateWithFlags(&D.srv, cudaStreamNonBlocking));
+    for(int i = CH_Q_SLOTS - 1; i >= 0; i--) D.free_slots.push_back(i);
+    return true;
+}
+// tell the workers to leave and wait until the grid is gone (only called when no chain is in flight)
+bool server_stop(DeviceSched &D)
+{
+    if(!D.server_on) return true;
+    CKJ(cudaMemcpyAsync(&D.dq->stop, &D.h_flag[1], sizeof(int), cudaMemcpyHostToDevice, D.feed));
+    CKJ(cudaStreamSynchronize(D.feed));
+    CKJ(cudaStreamSynchronize(D.srv));
+    D.server_on = false;
+    return true;
+}
+// The worker grid: as many CTAs as fit with `smem` bytes each, minus a reserve -- the workers live as long as there is work, and
+// the short kernels around them (upload conversion, loop filter, border expansion) need SM slots of their own to run at all.
+bool server_start(DeviceSched &D, size_t smem)
+{
+    int bps = 0;
+    CKJ(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain_server<3>, CH_T, smem));
+    if(bps < 1) return false;
+    int reserve = D.sms / 8;
+    if(reserve < 8) reserve = 8;
+    D.workers = bps * D.sms - reserve;
+    if(const char *e = getenv("XB200_CHAIN_WORKERS")) { const int v = atoi(e); if(v > 0 && v < D.workers) D.workers = v; }
+    if(D.workers < 1) D.workers = 1;
+    // head = tail = stop = 0: every ticket of the previous grid is void
+    CKJ(cudaMemsetAsync(D.dq, 0, offsetof(ChainQueue, tasks), D.feed));
+    CKJ(cudaStreamSynchronize(D.feed));
+    D.tail = 0;
+    k_chain_server<3><<<D.workers, CH_T, smem, D.srv>>>(D.dq, D.d_tm64);
+    CKJ(cudaGetLastError());
+    D.server_on = true;
+    D.server_smem = smem;
+    return true;
+}
+
+// hand a picture to the chain server: its record, the cleared maps and n_chain tasks, then the new tail -- all on the feed stream, so
+// the workers see the tail move after everything it announces.  Scheduler thread, scheduler mutex held.
+bool publish_job(DeviceSched &D, Job *j)
 {
     xb200_ctx *c = j->c;
     ChainCtx  *k = cc_of(c);
-    int        sn = 0;
-    for(int i = 1; i < N_STREAMS; i++) if(k->stream_busy[i] < k->stream_busy[sn]) sn = i;
-    cudaStream_t s = k->streams[sn];
-    j->stream_no = sn;
-    PicMaps  *m = j->m;
+    PicMaps   *m = j->m;
     const size_t f = k->f_scu;
+    const int  slot = D.free_slots.back();
+    D.free_slots.pop_back();
+    if(++D.seq == 0) ++D.seq;
+    j->slot = slot; j->seq = D.seq;
+    ChainPicTask &T = D.h_slot[slot];
+    memset(&T, 0, sizeof(T));
+    T.P = j->P; T.pics = c->d_pics; T.sq = c->sq; T.err_flag = c->d_err; T.seq = j->seq; T.finished = 0;
+    T.h_done = D.d_done + slot; T.t_first = ~0ull; T.t_last = 0;
+    D.h_done[slot] = 0;
+    cudaStream_t s = D.feed;
     if(!k->span_on) { CKJ(cudaEventRecord(k->ev_span0, s)); k->span_on = true; k->span_ms = 0.f; }
+    CKJ(cudaMemcpyAsync(&D.dq->slot[slot], &T, sizeof(T), cudaMemcpyHostToDevice, s));
     CKJ(cudaMemsetAsync(m->scu, 0, f * 4, s)); CKJ(cudaMemsetAsync(m->ipm, 0, f, s)); CKJ(cudaMemsetAsync(m->refi, 0, f * 2, s));
     CKJ(cudaMemsetAsync(m->mv, 0, f * 8, s)); CKJ(cudaMemsetAsync(m->flags, 0, f, s));
     CKJ(cudaMemsetAsync(j->b.done, 0, (size_t)k->n_lcu * sizeof(int), s));
     CKJ(cudaMemsetAsync(j->b.counts, 0, 2 * sizeof(unsigned long long), s));
-    CKJ(cudaEventRecord(j->b.ev0, s));
-    CKJ(j->dense ? launch_chain<3>(j, s) : launch_chain<2>(j, s));
+    for(int q = 0; q < j->n_chain; q++) {
+        const unsigned pos = (D.tail + (unsigned)q) % CH_Q_TASKS;
+        D.h_tasks[pos].slot = slot; D.h_tasks[pos].chain = q;
+        CKJ(cudaMemcpyAsync(&D.dq->tasks[pos], &D.h_tasks[pos], sizeof(ChainTask), cudaMemcpyHostToDevice, s));
+    }
+    D.tail += (unsigned)j->n_chain;
+    unsigned *src = &D.h_tail[D.seq % 4096];
+    *src = D.tail;
+    CKJ(cudaMemcpyAsync(&D.dq->tail, src, sizeof(unsigned), cudaMemcpyHostToDevice, s));
     c->launches++;
-    CKJ(cudaEventRecord(j->b.ev1, s));
-    k->stream_busy[sn]++;
-    D.chains += j->n_chain; D.by_bps[j->bps]++;
+    D.chains += j->n_chain;
+    D.running.push_back(j);
     j->state.store(JOB_RUNNING);
-    CKJ(cudaLaunchHostFunc(s, cb_chain_done, j));
+    return true;
+}
+// the chains of a picture have all finished: copy of the unfiltered picture (optional), both loop-filter passes, border expansion on
+// one of the context's streams, then the completion callback
+bool finish_job(DeviceSched &D, Job *j)
+{
+    xb200_ctx *c = j->c;
+    ChainCtx  *k = cc_of(c);
+    PicMaps   *m = j->m;
+    int        sn = 0;
+    for(int i = 1; i < N_STREAMS; i++) if(k->stream_busy[i] < k->stream_busy[sn]) sn = i;
+    cudaStream_t s = k->streams[sn];
+    j->stream_no = sn;
+    k->stream_busy[sn]++;
+    CKJ(cudaMemcpyAsync(j->t_chain, &D.dq->slot[j->slot].t_first, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    D.free_slots.insert(D.free_slots.begin(), j->slot);   // reused last: the copy above reads the slot
+    CKJ(cudaEventRecord(j->b.ev1, s));
     if(j->has_up)
         for(int q = 0; q < 3; q++)
             CKJ(cudaMemcpy2DAsync(j->up.buf[q] + (size_t)j->up.pad[q] * j->up.s[q] + j->up.pad[q], (size_t)j->up.s[q] * 2,
@@ -325,9 +415,16 @@ void sched_thread(DeviceSched *Dp)
     cudaSetDevice(D.device);
     std::vector<std::pair<Job *, int>> ev;
     for(;;) {
+        bool poll;
+        {
+            std::lock_guard<std::mutex> lk(D.mu);
+            poll = !D.running.empty();
+        }
         {
             std::unique_lock<std::mutex> cl(D.cb_mu);
-            D.cv_work.wait(cl, [&] { return D.wake || D.stop; });
+            // while chains run the completion words are polled (the workers write them through host-mapped memory)
+            if(poll) D.cv_work.wait_for(cl, std::chrono::microseconds(200), [&] { return D.wake || D.stop; });
+            else D.cv_work.wait(cl, [&] { return D.wake || D.stop; });
             if(D.stop) return;
             D.wake = false;
             ev.clear();
@@ -335,44 +432,43 @@ void sched_thread(DeviceSched *Dp)
         }
         std::lock_guard<std::mutex> lk(D.mu);
         bool any_ready = false;
-        for(auto &e : ev) {
+        for(auto &e : ev) {   // loop filter + border expansion finished: the picture is a usable reference
             Job *j = e.first;
-            if(e.second == 0) {
-                D.chains -= j->n_chain; D.by_bps[j->bps]--;
-                j->state.store(JOB_CHAIN_DONE);
-            }
-            else {
-                j->m->ready.store(j->life);
-                cc_of(j->c)->stream_busy[j->stream_no]--;
-                j->state.store(JOB_READY);
-                any_ready = true;
-            }
+            j->m->ready.store(j->life);
+            cc_of(j->c)->stream_busy[j->stream_no]--;
+            j->state.store(JOB_READY);
+            any_ready = true;
         }
-        // launch, in enqueue order, every queued picture whose references are complete and whose chains fit
+        for(size_t i = 0; i < D.running.size();) {   // pictures whose last chain has finished
+            Job *j = D.running[i];
+            if(D.h_done[j->slot] != j->seq) { i++; continue; }
+            D.running[i] = D.running.back();
+            D.running.pop_back();
+            D.chains -= j->n_chain;
+            j->state.store(JOB_CHAIN_DONE);
+            if(!finish_job(D, j)) { j->state.store(JOB_FAILED); any_ready = true; }
+        }
+        // publish, in enqueue order, every queued picture whose references are complete, while the workers can take all its chains
+        // at once (a partly started picture would only spin)
         for(auto it = D.pending.begin(); it != D.pending.end();) {
             Job *j = *it;
             bool ok = true;
             for(int d = 0; d < j->n_dep && ok; d++) ok = j->deps[d].m->ready.load() >= j->deps[d].life;
-            if(ok) {
-                // kernel variant by load: k_chain<2> (255 registers) is the fastest chain, k_chain<3> (170 registers) lets three chains
-                // share an SM -- as many as the shared memory of a B picture allows.  A lone context whose chains fit keeps the fast
-                // variant; several contexts (streams sharing the device) or a full device take the dense one.  XB200_CHAIN_DENSE=0 / 1
-                // forces one.
-                static const char *dense_env = getenv("XB200_CHAIN_DENSE");
-                const int mb = D.min_bps();
-                const int b_fast = mb && mb < j->b_fast ? mb : j->b_fast;
-                j->dense = dense_env ? dense_env[0] == '1' : (D.n_ctx > 1 || D.chains + j->n_chain > b_fast * D.sms);
-                j->bps = j->dense ? j->b_dense : j->b_fast;
-                const int b = mb && mb < j->bps ? mb : j->bps;
-                ok = D.chains + j->n_chain <= b * D.sms;
-            }
             if(!ok) { ++it; continue; }
-            it = D.pending.erase(it);
-            if(!launch_job(D, j)) {
-                j->state.store(JOB_FAILED);
-                any_ready = true;
+            if(!server_init(D, j->c)) { it = D.pending.erase(it); j->state.store(JOB_FAILED); any_ready = true; continue; }
+            if(j->smem > D.server_smem || !D.server_on) {
+                // a bigger working set than the grid was launched with (or no grid): start a new one when nothing is in flight
+                if(D.chains > 0) break;
+                const size_t sm = j->smem > D.server_smem ? j->smem : D.server_smem;
+                if(!server_stop(D) || !server_start(D, sm)) { it = D.pending.erase(it); j->state.store(JOB_FAILED); any_ready = true; continue; }
             }
+            if(D.chains + j->n_chain > D.workers && D.chains > 0) { ++it; continue; }
+            if(D.free_slots.empty() || (unsigned)(D.chains + j->n_chain) > (unsigned)CH_Q_TASKS / 2) break;
+            it = D.pending.erase(it);
+            if(!publish_job(D, j)) { j->state.store(JOB_FAILED); any_ready = true; }
         }
+        // nothing left to do: let the grid go, so that cudaFree & co. (device-wide synchronisation) are not held up by idle workers
+        if(D.server_on && D.pending.empty() && D.running.empty() && D.chains == 0) server_stop(D);
         if(any_ready) D.cv_done.notify_all();
     }
 }
@@ -435,8 +531,8 @@ int xb200_chain_capacity(xb200_ctx *c)
     for(int l2 = 3; l2 <= 6; l2++) { const int ext = (1 << l2) + 2 * 10 + 7; cap[l2 - 3] = (align_up(ext, 8) + 8) * ext + 16; }
     const size_t smem = chain_smem_bytes(cap);
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain<3>, CH_T, smem));
-    return c->sms * (bps < 1 ? 1 : bps);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_chain_server<3>, CH_T, smem));
+    return c->sms * (bps < 1 ? 1 : bps) - (c->sms / 8 < 8 ? 8 : c->sms / 8);
 }
 
 int xb200_picture_log_enable(xb200_ctx *c, int64_t cap_cu, int64_t cap_intra)
@@ -551,10 +647,9 @@ int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp)
             }
     }
     if(m->ready.load() < m->issued) { j->deps[j->n_dep].m = m; j->deps[j->n_dep].life = m->issued; j->n_dep++; }
-    // CTAs of this picture an SM can hold, per kernel variant (registers x shared memory of this picture)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j->b_fast, k_chain<2>, CH_T, smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j->b_dense, k_chain<3>, CH_T, smem));
-    if(j->b_fast < 1 || j->b_dense < 1 || P.n_chain > j->b_dense * c->sms) { delete j; return XB200_ERR_UNSUPPORTED; }
+    // workers the device can hold with this picture's shared memory (registers x shared memory)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j->b_dense, k_chain_server<3>, CH_T, smem));
+    if(j->b_dense < 1 || P.n_chain > j->b_dense * c->sms - c->sms / 8 - 8) { delete j; return XB200_ERR_UNSUPPORTED; }
     if((r = bufs_get(c, P.n_chain, &j->b))) { delete j; return r; }
     j->n_chain = P.n_chain;
     P.scu_out = j->b.scu; P.coef_out = j->b.coef; P.ctu_state = j->b.ctu_state; P.ctu_cost = j->b.ctu_cost; P.done = j->b.done;
@@ -612,7 +707,7 @@ int xb200_picture_fetch(xb200_ctx *c, int32_t rec_pic, xb200_scu_rec *scu, int16
     CK(cudaStreamSynchronize(k->copy));
     if(stat) {
         float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, j->b.ev0, j->b.ev1);
+        a = j->t_chain[1] > j->t_chain[0] ? (float)(1e-6 * (double)(j->t_chain[1] - j->t_chain[0])) : 0.f;   // %globaltimer, ns
         cudaEventElapsedTime(&b, j->b.ev1, j->b.ev2);
         stat->n_inter = (int64_t)cnt[0]; stat->n_intra = (int64_t)cnt[1]; stat->chain_ms = a; stat->filter_ms = b;
     }

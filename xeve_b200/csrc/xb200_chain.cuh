@@ -84,6 +84,37 @@ struct ChainPic {            // picture-level inputs of the kernel
     long long cu_cap, intra_cap;
 };
 
+// ---- the chain server: device-side work queue ---------------------------------------------------------------------------------------
+// One long-lived grid of chain workers (as many CTAs as the device holds) serves the chains of EVERY picture in flight: the host
+// publishes a picture as n_chain consecutive tasks, a worker takes the next ticket (FIFO), runs that chain and moves on.  One kernel
+// per picture does not scale: the device runs kernels of different streams through a few hardware queues (8 by default, 32 at most),
+// and a kernel that lives for a second at the head of a queue holds back whatever was launched behind it in that queue -- with a
+// kernel per picture at most 8 pictures ran concurrently (61 of 444 chain slots busy, profiles/r02s12), and the short kernels around
+// them (upload conversion, loop filter, border expansion) waited behind them too.
+// Dead-lock freedom without admission control: chains of a picture spin on each other's flags, so all of them must run eventually --
+// tickets are taken strictly in publication order, hence the earliest unfinished picture always has all its chains on workers (or
+// next in line for the first free worker), completes, and frees its workers for the next one.
+struct ChainTask { int32_t slot, chain; };          // picture slot, chain index
+struct ChainPicTask {                               // one picture in flight
+    ChainPic     P;
+    const PicDev *pics;                             // the owning context's picture table
+    SeqDev       sq;
+    int         *err_flag;
+    unsigned     seq;                               // generation written to *h_done when the last chain has finished
+    unsigned     finished;                          // chains finished so far
+    volatile unsigned *h_done;                      // host-mapped completion word of this slot
+    unsigned long long t_first, t_last;             // %globaltimer when the first chain started / the last one finished
+};
+constexpr int CH_Q_TASKS = 1 << 14, CH_Q_SLOTS = 1024;
+struct ChainQueue {
+    unsigned head;                                  // next ticket (workers: atomicAdd)
+    unsigned tail;                                  // tasks published so far (host writes, stream-ordered after the task records)
+    int      stop;                                  // workers leave when they find no task and this is set
+    int      pad_;
+    ChainTask    tasks[CH_Q_TASKS];
+    ChainPicTask slot[CH_Q_SLOTS];
+};
+
 struct ChShared {            // control block in shared memory
     uint64_t bar[4];         // search-window mbarriers: [0] serial analysis, [1..3] the three warps of the parallel small-CU analysis;
     uint32_t bphase[4];      // initialised once per kernel, never overlaid by working sets, parities kept here between CUs
@@ -94,6 +125,9 @@ struct ChShared {            // control block in shared memory
     ChState     curr[5], next[5], before[5], sdepth[5], chain;
     xb200_sbac  st_out;
     xb200_rates rates;
+    int32_t     task_slot, task_chain;   // the task this worker is on (chain server)
+    SeqDev      sq;                      // ... and copies of its picture's parameters
+    ChainPic    P;
     uint8_t  zinv8[64];
     uint16_t thr_mb[IN_CM_N + 2], thr_mr[IN_CM_N + 2];
 };
@@ -546,25 +580,16 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
     return cost_best;
 }
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__restrict__ pics, const ChainPic P, const int8_t *__restrict__ g_tm64,
-                                                           const SeqDev sq, int *__restrict__ err_flag)
+// the decision pass of one chain of one picture (P, sq: the worker's shared-memory copies)
+__device__ __noinline__ void chain_picture(const PicDev *__restrict__ pics, const ChainPic &P, const SeqDev &sq, int *__restrict__ err_flag,
+                                           int chain, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     int8_t        *tm = reinterpret_cast<int8_t *>(smem_raw), *tmT = tm + 4096;
     ChShared      &S = *reinterpret_cast<ChShared *>(smem_raw + 8192);
     unsigned char *team = smem_raw + CH_TEAM_OFF;
-    const int      t = threadIdx.x, chain = blockIdx.x;
+    const int      t = threadIdx.x;
     ChainWs       *ws = P.ws + chain;
     const xb200_picture &pp = P.pp;
-    for(int e = t; e < 4096; e += CH_T) {
-        const int8_t v = g_tm64[e];
-        tm[e] = v;
-        tmT[(e & 63) * 64 + (e >> 6)] = v;
-    }
-    if(t < 64) S.zinv8[zz_of(t, 3)] = (uint8_t)t;
-    if(t < 4) { mbar_init(&S.bar[t], 1); S.bphase[t] = 0; }
-    if(t == 0) { S.phase = 0; S.bits = 0; S.satd = 0; }
 #ifdef XB200_CHAIN_PROF
     if(t == 0) g_prof_last = clock64();
 #endif
@@ -714,4 +739,76 @@ __global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain(const PicDev *__rest
             if(t == 0) atomicExch(P.done + lcu, 1);
         }
     if(t == 0) { atomicAdd(P.counts, (unsigned long long)n_inter); atomicAdd(P.counts + 1, (unsigned long long)n_intra); }
+}
+
+XB_DEV unsigned long long ch_globaltimer()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+
+// A chain worker: takes tickets until the host tells it to leave.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(CH_T, MIN_BLOCKS) k_chain_server(ChainQueue *__restrict__ q, const int8_t *__restrict__ g_tm64)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int8_t   *tm = reinterpret_cast<int8_t *>(smem_raw), *tmT = tm + 4096;
+    ChShared &S = *reinterpret_cast<ChShared *>(smem_raw + 8192);
+    const int t = threadIdx.x;
+    for(int e = t; e < 4096; e += CH_T) {
+        const int8_t v = g_tm64[e];
+        tm[e] = v;
+        tmT[(e & 63) * 64 + (e >> 6)] = v;
+    }
+    if(t < 64) S.zinv8[zz_of(t, 3)] = (uint8_t)t;
+    if(t < 4) { mbar_init(&S.bar[t], 1); S.bphase[t] = 0; }
+    if(t == 0) { S.phase = 0; S.bits = 0; S.satd = 0; }
+    __syncthreads();
+    for(;;) {
+        if(t == 0) {
+            const unsigned ticket = atomicAdd(&q->head, 1u);
+            volatile unsigned *tail = &q->tail;
+            volatile int      *stop = &q->stop;
+            int slot = -1, chain = 0;
+            for(;;) {
+                if((int)(*tail - ticket) > 0) {
+                    __threadfence();                      // the task records were written before tail moved
+                    const volatile int32_t *tk = reinterpret_cast<const volatile int32_t *>(&q->tasks[ticket % CH_Q_TASKS]);
+                    slot = tk[0]; chain = tk[1];
+                    break;
+                }
+                if(*stop) break;
+                __nanosleep(2000);
+            }
+            S.task_slot = slot; S.task_chain = chain;
+        }
+        __syncthreads();
+        const int slot = S.task_slot, chain = S.task_chain;
+        if(slot < 0) return;
+        ChainPicTask *pt = &q->slot[slot];
+        {   // the picture's parameters -> shared memory (read through L2: the host wrote them while this grid was running)
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&pt->P);
+            uint32_t       *dst = reinterpret_cast<uint32_t *>(&S.P);
+            for(int i = t; i < (int)(sizeof(ChainPic) / 4); i += CH_T) dst[i] = __ldcg(src + i);
+            const uint32_t *s2 = reinterpret_cast<const uint32_t *>(&pt->sq);
+            uint32_t       *d2 = reinterpret_cast<uint32_t *>(&S.sq);
+            for(int i = t; i < (int)(sizeof(SeqDev) / 4); i += CH_T) d2[i] = __ldcg(s2 + i);
+        }
+        if(t == 0) atomicMin(&pt->t_first, ch_globaltimer());
+        __syncthreads();
+        chain_picture(pt->pics, S.P, S.sq, pt->err_flag, chain, smem_raw);
+        __syncthreads();
+        if(t == 0) {
+            __threadfence();
+            const unsigned long long now = ch_globaltimer();
+            atomicMax(&pt->t_last, now);
+            if(atomicAdd(&pt->finished, 1u) == (unsigned)S.P.n_chain - 1) {
+                __threadfence();
+                *pt->h_done = pt->seq;                    // host-mapped memory: the scheduler polls it
+                __threadfence_system();
+            }
+        }
+        __syncthreads();
+    }
 }
