@@ -25,6 +25,12 @@ bitstream.  The md5 of every stream's bitstream is compared with the unmodified 
 """
 from __future__ import annotations
 
+import os as _os
+# before anything initialises CUDA (see xb200_process_env in xeve_b200/csrc/xb200_api.cu): kernels are loaded eagerly and the device
+# gets all 32 hardware work queues
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import hashlib
 import json

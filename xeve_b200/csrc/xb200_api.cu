@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
 #include <chrono>
 
 #include "xb200_ctx.h"
@@ -302,13 +303,19 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
         CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
-    // constant tables
+    // constant tables: device-wide state, uploaded by the first context of a device only -- a later context may be created while the
+    // chain server of another one is alive, and then nothing here may wait for the device (xb200_chain.cu: chain_init)
+    static std::mutex once_mu;
+    static bool       once_done[64] = {};
+    std::lock_guard<std::mutex> once_lock(once_mu);
+    const bool first = !once_done[device & 63];
     {
         static int8_t tm[64 * 64];
         xb200_gen_tm64(tm);
-        CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
+        if(first) CK(cudaMemcpyToSymbol(c_tm64, tm, sizeof(tm)));
         CK(cudaMalloc(&c->d_tm64, sizeof(tm)));
-        CK(cudaMemcpy(c->d_tm64, tm, sizeof(tm), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(c->d_tm64, tm, sizeof(tm), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         const int16_t l[4][8] = XB200_MC_L_TAPS;
         const int16_t ch[8][4] = XB200_MC_C_TAPS;
         const int32_t qs[6] = XB200_QUANT_SCALE, dq[6] = XB200_DEQUANT_SCALE;
@@ -316,13 +323,15 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
         for(int b = 0; b < 7; b++)
             for(int q = 0; q < 6; q++)
                 for(int l2 = 0; l2 < 7; l2++) es[b][q][l2] = xb200_err_scale(q, l2, b + 8);
-        CK(cudaMemcpyToSymbol(c_mc_l, l, sizeof(l)));
-        CK(cudaMemcpyToSymbol(c_mc_c, ch, sizeof(ch)));
-        CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
-        CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
-        CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+        if(first) {
+            CK(cudaMemcpyToSymbol(c_mc_l, l, sizeof(l)));
+            CK(cudaMemcpyToSymbol(c_mc_c, ch, sizeof(ch)));
+            CK(cudaMemcpyToSymbol(c_quant_scale, qs, sizeof(qs)));
+            CK(cudaMemcpyToSymbol(c_dequant_scale, dq, sizeof(dq)));
+            CK(cudaMemcpyToSymbol(c_err_scale, es, sizeof(es)));
+        }
     }
-    {   // rate estimation tables: zig-zag scans (closed form) and xeve_init_bits_est (src_base/xeve_mode.c:304-313, host libm)
+    if(first) {   // rate estimation tables: zig-zag scans (closed form) and xeve_init_bits_est (src_base/xeve_mode.c:304-313, host libm)
         static uint16_t scan[16 + 64 + 256 + 1024 + 4096];
         static int32_t  eb[1024];
         int             off = 0;
@@ -335,12 +344,16 @@ int xb200_create(xb200_ctx **out, int device, const xb200_seq *seq)
         CK(cudaMemcpyToSymbol(g_entropy_bits, eb, sizeof(eb)));
     }
     CK(cudaMalloc(&c->d_err, sizeof(int)));
-    CK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     CK(cudaMalloc(&c->d_bins, sizeof(int) * 16));
-    CK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_bi_org, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
-    CK(cudaFuncSetAttribute(k_itdq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
+    if(first) {
+        CK(cudaFuncSetAttribute(k_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_bi_org, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
+        CK(cudaFuncSetAttribute(k_itdq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TqSmem)));
+    }
+    once_done[device & 63] = true;
     *out = c;
     return XB200_OK;
 }
@@ -349,7 +362,9 @@ void xb200_destroy(xb200_ctx *c)
 {
     if(!c) return;
     cudaSetDevice(c->device);
-    xb200_chain_free(c);
+    const bool had_chain = c->chain != nullptr;
+    const int  device = c->device;
+    xb200_chain_free(c);          // returns with the device's worker grid gone and held off (cudaFree waits for the device)
     cudaStreamSynchronize(c->stream);
     for(auto &p : c->pics)
         for(int k = 0; k < 3; k++)
@@ -373,6 +388,7 @@ void xb200_destroy(xb200_ctx *c)
     for(int i = 0; i < 4; i++) { cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
+    if(had_chain) xb200_chain_drain_end(device);
 }
 
 int64_t xb200_launch_count(const xb200_ctx *c) { return c ? c->launches : 0; }
@@ -414,6 +430,29 @@ int xb200_pic_destroy(xb200_ctx *c, int32_t handle)
     for(int k = 0; k < 3; k++) { cudaFree(p.buf[k]); p.buf[k] = nullptr; }
     p.used = false;
     c->pics_dirty = true;
+    return XB200_OK;
+}
+
+// Process-level CUDA settings this library depends on, applied when it is loaded BEFORE the CUDA runtime initialises (an application
+// linked against it; a host that has already initialised CUDA, like the Python bench, sets them itself):
+//   CUDA_MODULE_LOADING=EAGER       a kernel's first launch must never have to load code while the chain server is alive (see below)
+//   CUDA_DEVICE_MAX_CONNECTIONS=32  hardware work queues: short kernels of many streams next to long-running ones
+// Never overrides what the user has set.
+__attribute__((constructor)) static void xb200_process_env()
+{
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
+// Load (not launch) the short kernels that run NEXT TO the chain server.  With lazy module loading (the CUDA 12 default) the first launch
+// of a kernel loads its code, and that can synchronise the device -- which never happens while the long-lived worker grid waits for
+// work: the first loop filter or upload conversion after the server had started dead-locked.  cudaFuncGetAttributes forces the load.
+extern "C++" int xb200_preload_api_kernels()
+{
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_pad3));
+    CK(cudaFuncGetAttributes(&fa, k_convert<uint8_t>));
+    CK(cudaFuncGetAttributes(&fa, k_convert<uint16_t>));
     return XB200_OK;
 }
 

@@ -15,6 +15,7 @@
 #include <deque>
 #include <map>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -93,6 +94,7 @@ struct DeviceSched {
     std::vector<Job *>      running;         // published to the chain server, chains not all finished
     int                     chains = 0;      // chains published and not finished
     int                     n_ctx = 0;       // contexts with a decision pass on this device
+    int                     drain = 0;       // contexts being torn down: nothing is published, the grid ends when its chains have finished
     // the chain server (xb200_chain.cuh: k_chain_server)
     ChainQueue             *dq = nullptr;    // device queue
     volatile unsigned      *h_done = nullptr;// host-mapped completion words, one per picture slot
@@ -101,6 +103,7 @@ struct DeviceSched {
     ChainTask              *h_tasks = nullptr;   // pinned mirror of the task ring
     unsigned               *h_tail = nullptr;    // pinned ring of published tail values (sources of the async copies)
     int                    *h_flag = nullptr;    // pinned {0, 1}
+    unsigned long long     *h_times = nullptr;   // pinned [slot][2]: device timer when the first chain started / the last one finished
     int8_t                 *d_tm64 = nullptr;
     cudaStream_t            feed = nullptr, srv = nullptr;
     bool                    server_on = false;
@@ -136,6 +139,7 @@ struct ChainCtx {
 
 ChainCtx *cc_of(xb200_ctx *c) { return static_cast<ChainCtx *>(c->chain); }
 void sched_thread(DeviceSched *D);
+void sched_atexit();
 
 int chain_init(xb200_ctx *c)
 {
@@ -147,6 +151,15 @@ int chain_init(xb200_ctx *c)
     for(int i = 0; i < N_STREAMS; i++) CK(cudaStreamCreateWithFlags(&k->streams[i], cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&k->copy, cudaStreamNonBlocking));
     CK(cudaEventCreate(&k->ev_span0));
+    // Device-wide state of this translation unit -- constant tables, the worker kernel's shared-memory attribute -- is set ONCE per
+    // device, by the first context: a later context may be created while the chain server is alive, and nothing it does may wait for
+    // the device (cudaMemcpyToSymbol, cudaMemset and cudaDeviceSynchronize do, one way or another; the worker grid only ends when the
+    // scheduler says so).
+    static std::mutex once_mu;
+    static bool       once_done[64] = {};
+    {
+    std::lock_guard<std::mutex> ol(once_mu);
+    if(!once_done[c->device & 63]) {
     {   // constant tables of this translation unit
         static int8_t tm[64 * 64];
         xb200_gen_tm64(tm);
@@ -187,24 +200,34 @@ int chain_init(xb200_ctx *c)
         CK(cudaMemcpyToSymbol(g_dbg, &dv, sizeof(dv)));
     }
 #endif
-    CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
-    CK(cudaMemset(k->zero_mv, 0, k->f_scu * 8));
-    if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemset(c->d_err, 0, sizeof(int))); }
-    {   // opt-in shared memory of the worker kernel: set ONCE per device to the maximum (the attribute belongs to the function)
+    {   // opt-in shared memory of the worker kernel: the maximum (the attribute belongs to the function, not to a launch)
         int optin = 0;
         cudaFuncAttributes fa;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
         CK(cudaFuncGetAttributes(&fa, k_chain_server<3>));
         CK(cudaFuncSetAttribute(k_chain_server<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     }
-    CK(cudaDeviceSynchronize());
+    CK(cudaDeviceSynchronize());   // first context of the device: no worker grid can be alive yet
+    once_done[c->device & 63] = true;
+    }
+    }
+    CK(cudaMalloc(&k->zero_mv, k->f_scu * 8));
+    CK(cudaMemsetAsync(k->zero_mv, 0, k->f_scu * 8, k->copy));
+    if(!c->d_err) { CK(cudaMalloc(&c->d_err, sizeof(int))); CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), k->copy)); }
+    CK(cudaStreamSynchronize(k->copy));
     k->ready = true;
     {
         DeviceSched &D = g_sched[c->device & 63];
         std::lock_guard<std::mutex> dl(D.mu);
         D.n_ctx++;
         D.sms = c->sms; D.device = c->device;
-        if(!D.started) { D.started = true; D.th = std::thread(sched_thread, &D); D.th.detach(); }
+        if(!D.started) {
+            D.started = true;
+            static std::once_flag once;
+            std::call_once(once, [] { atexit(sched_atexit); });
+            D.th = std::thread(sched_thread, &D);
+            D.th.detach();
+        }
     }
     return XB200_OK;
 }
@@ -285,6 +308,14 @@ void sched_kick(DeviceSched &D)
     D.cv_work.notify_one();
 }
 
+// XB200_SCHED_DEBUG=1: the scheduler's steps on stderr (time in ms since its first line)
+static bool sched_debug() { static const bool on = getenv("XB200_SCHED_DEBUG") && atoi(getenv("XB200_SCHED_DEBUG")); return on; }
+static double sched_ms()
+{
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+#define SDBG(...) do { if(sched_debug()) { fprintf(stderr, "[xb200 sched %9.3f] ", sched_ms()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while(0)
 #define CKJ(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { fprintf(stderr, "xeve_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return false; } } while(0)
 
 // queue, staging and streams of a device's chain server (once)
@@ -302,12 +333,28 @@ bool server_init(DeviceSched &D, xb200_ctx *c)
     CKJ(cudaHostAlloc(&D.h_tasks, CH_Q_TASKS * sizeof(ChainTask), cudaHostAllocDefault));
     CKJ(cudaHostAlloc(&D.h_tail, 4096 * sizeof(unsigned), cudaHostAllocDefault));
     CKJ(cudaHostAlloc(&D.h_flag, 2 * sizeof(int), cudaHostAllocDefault));
+    CKJ(cudaHostAlloc(&D.h_times, CH_Q_SLOTS * 2 * sizeof(unsigned long long), cudaHostAllocDefault));
     D.h_flag[0] = 0; D.h_flag[1] = 1;
     CKJ(cudaMalloc(&D.d_tm64, 4096));
     CKJ(cudaMemcpy(D.d_tm64, c->d_tm64, 4096, cudaMemcpyDeviceToDevice));
     CKJ(cudaStreamCreateWithFlags(&D.feed, cudaStreamNonBlocking));
     CKJ(cudaStreamCreateWithFlags(&D.srv, cudaStreamNonBlocking));
     for(int i = CH_Q_SLOTS - 1; i >= 0; i--) D.free_slots.push_back(i);
+    // Everything that will be launched while the worker grid is alive must be LOADED before it starts: with lazy module loading the
+    // first launch of a kernel loads its code, which can synchronise the device -- and the grid only ends when the host says so.
+    if(xb200_preload_api_kernels() || xb200_preload_frame_kernels()) return false;
+    {   // the driver's own memset / copy kernels: run each kind once (1-, 2- and 4-byte patterns, 2-D copy, small and large)
+        unsigned char *scratch = nullptr;
+        CKJ(cudaMalloc(&scratch, 1 << 20));
+        for(size_t n : {(size_t)4, (size_t)4096, (size_t)1 << 20, (size_t)(1 << 20) - 3}) CKJ(cudaMemsetAsync(scratch, 0, n, D.feed));
+        CKJ(cudaMemset2DAsync(scratch, 2048, 0, 1000, 256, D.feed));
+        CKJ(cudaMemcpy2DAsync(scratch, 2048, scratch + (1 << 19), 2048, 1000, 128, cudaMemcpyDeviceToDevice, D.feed));
+        CKJ(cudaMemcpyAsync(scratch, scratch + (1 << 19), 1 << 18, cudaMemcpyDeviceToDevice, D.feed));
+        CKJ(cudaMemcpyAsync(scratch, D.h_flag, 8, cudaMemcpyHostToDevice, D.feed));
+        CKJ(cudaMemcpyAsync(D.h_times, scratch, 16, cudaMemcpyDeviceToHost, D.feed));
+        CKJ(cudaStreamSynchronize(D.feed));
+        CKJ(cudaFree(scratch));
+    }
     return true;
 }
 // tell the workers to leave and wait until the grid is gone (only called when no chain is in flight)
@@ -316,8 +363,10 @@ bool server_stop(DeviceSched &D)
     if(!D.server_on) return true;
     CKJ(cudaMemcpyAsync(&D.dq->stop, &D.h_flag[1], sizeof(int), cudaMemcpyHostToDevice, D.feed));
     CKJ(cudaStreamSynchronize(D.feed));
+    SDBG("server stop requested");
     CKJ(cudaStreamSynchronize(D.srv));
     D.server_on = false;
+    SDBG("server stopped");
     return true;
 }
 // The worker grid: as many CTAs as fit with `smem` bytes each, minus a reserve -- the workers live as long as there is work, and
@@ -340,6 +389,7 @@ bool server_start(DeviceSched &D, size_t smem)
     CKJ(cudaGetLastError());
     D.server_on = true;
     D.server_smem = smem;
+    SDBG("server started: %d workers x %d threads, %zu bytes of shared memory each (%d per SM)", D.workers, CH_T, smem, bps);
     return true;
 }
 
@@ -380,6 +430,7 @@ bool publish_job(DeviceSched &D, Job *j)
     D.chains += j->n_chain;
     D.running.push_back(j);
     j->state.store(JOB_RUNNING);
+    SDBG("published POC %d (%d chains) in slot %d, seq %u, tail %u; %d chains in flight", j->P.pp.poc, j->n_chain, slot, j->seq, D.tail, D.chains);
     return true;
 }
 // the chains of a picture have all finished: copy of the unfiltered picture (optional), both loop-filter passes, border expansion on
@@ -394,8 +445,7 @@ bool finish_job(DeviceSched &D, Job *j)
     cudaStream_t s = k->streams[sn];
     j->stream_no = sn;
     k->stream_busy[sn]++;
-    CKJ(cudaMemcpyAsync(j->t_chain, &D.dq->slot[j->slot].t_first, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    D.free_slots.insert(D.free_slots.begin(), j->slot);   // reused last: the copy above reads the slot
+    CKJ(cudaMemcpyAsync(&D.h_times[2 * j->slot], &D.dq->slot[j->slot].t_first, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CKJ(cudaEventRecord(j->b.ev1, s));
     if(j->has_up)
         for(int q = 0; q < 3; q++)
@@ -406,7 +456,21 @@ bool finish_job(DeviceSched &D, Job *j)
     if(xb200_pad_planes(c, j->rp, s)) return false;
     CKJ(cudaEventRecord(j->b.ev2, s));
     CKJ(cudaLaunchHostFunc(s, cb_ready, j));
+    SDBG("POC %d: chains finished, loop filter launched", j->P.pp.poc);
     return true;
+}
+
+// process exit with a worker grid still alive (an application that never fetched its pictures, a failed run): tell the workers to
+// leave, or the runtime's teardown waits for them forever
+void sched_atexit()
+{
+    for(int d = 0; d < 64; d++) {
+        DeviceSched &D = g_sched[d];
+        if(!D.dq || !D.server_on) continue;
+        cudaSetDevice(D.device);
+        int one = 1;
+        cudaMemcpy(&D.dq->stop, &one, sizeof(int), cudaMemcpyHostToDevice);
+    }
 }
 
 void sched_thread(DeviceSched *Dp)
@@ -436,8 +500,24 @@ void sched_thread(DeviceSched *Dp)
             Job *j = e.first;
             j->m->ready.store(j->life);
             cc_of(j->c)->stream_busy[j->stream_no]--;
+            j->t_chain[0] = D.h_times[2 * j->slot]; j->t_chain[1] = D.h_times[2 * j->slot + 1];
+            D.free_slots.insert(D.free_slots.begin(), j->slot);   // reused last
             j->state.store(JOB_READY);
             any_ready = true;
+            SDBG("POC %d complete", j->P.pp.poc);
+        }
+        if(D.server_on && !D.running.empty()) {   // a fault inside the worker grid must not look like a picture that takes forever
+            const cudaError_t e = cudaStreamQuery(D.srv);
+            if(e != cudaErrorNotReady) {
+                fprintf(stderr, "xeve_b200: the chain server left the device (%s) with %zu pictures in flight\n",
+                        e == cudaSuccess ? "grid ended" : cudaGetErrorString(e), D.running.size());
+                for(Job *j : D.running) j->state.store(JOB_FAILED);
+                for(Job *j : D.pending) j->state.store(JOB_FAILED);
+                D.running.clear(); D.pending.clear();
+                D.chains = 0; D.server_on = false;
+                D.cv_done.notify_all();
+                continue;
+            }
         }
         for(size_t i = 0; i < D.running.size();) {   // pictures whose last chain has finished
             Job *j = D.running[i];
@@ -450,7 +530,7 @@ void sched_thread(DeviceSched *Dp)
         }
         // publish, in enqueue order, every queued picture whose references are complete, while the workers can take all its chains
         // at once (a partly started picture would only spin)
-        for(auto it = D.pending.begin(); it != D.pending.end();) {
+        for(auto it = D.pending.begin(); it != D.pending.end() && D.drain == 0;) {
             Job *j = *it;
             bool ok = true;
             for(int d = 0; d < j->n_dep && ok; d++) ok = j->deps[d].m->ready.load() >= j->deps[d].life;
@@ -468,7 +548,7 @@ void sched_thread(DeviceSched *Dp)
             if(!publish_job(D, j)) { j->state.store(JOB_FAILED); any_ready = true; }
         }
         // nothing left to do: let the grid go, so that cudaFree & co. (device-wide synchronisation) are not held up by idle workers
-        if(D.server_on && D.pending.empty() && D.running.empty() && D.chains == 0) server_stop(D);
+        if(D.server_on && (D.pending.empty() || D.drain > 0) && D.running.empty() && D.chains == 0) { server_stop(D); any_ready = true; }
         if(any_ready) D.cv_done.notify_all();
     }
 }
@@ -499,6 +579,12 @@ void xb200_chain_free(xb200_ctx *c)
             return true;
         });
         if(k->ready) D.n_ctx--;
+        // cudaFree waits for the device, and the worker grid lives as long as ANY context has work: ask the scheduler to let the grid
+        // end (it publishes nothing meanwhile, so this takes as long as the chains now running), free, then let it go on
+        // (xb200_chain_drain_end, called by xb200_destroy when everything of the context has been freed)
+        D.drain++;
+        sched_kick(D);
+        D.cv_done.wait(lk, [&] { return !D.server_on; });
     }
     for(int i = 0; i < N_STREAMS; i++)
         if(k->streams[i]) cudaStreamSynchronize(k->streams[i]);
@@ -517,6 +603,13 @@ void xb200_chain_free(xb200_ctx *c)
     if(k->ev_span0) cudaEventDestroy(k->ev_span0);
     delete k;
     c->chain = nullptr;
+}
+
+void xb200_chain_drain_end(int device)
+{
+    DeviceSched &D = g_sched[device & 63];
+    { std::lock_guard<std::mutex> dl(D.mu); if(D.drain > 0) D.drain--; }
+    sched_kick(D);
 }
 
 extern "C" {

@@ -581,8 +581,8 @@ __device__ __noinline__ double ch_unit(const ChainPic &P, const PicDev *__restri
 }
 
 // the decision pass of one chain of one picture (P, sq: the worker's shared-memory copies)
-__device__ __noinline__ void chain_picture(const PicDev *__restrict__ pics, const ChainPic &P, const SeqDev &sq, int *__restrict__ err_flag,
-                                           int chain, unsigned char *smem_raw)
+__device__ __forceinline__ void chain_picture(const PicDev *__restrict__ pics, const ChainPic &P, const SeqDev &sq, int *__restrict__ err_flag,
+                                              int chain, unsigned char *smem_raw)
 {
     int8_t        *tm = reinterpret_cast<int8_t *>(smem_raw), *tmT = tm + 4096;
     ChShared      &S = *reinterpret_cast<ChShared *>(smem_raw + 8192);

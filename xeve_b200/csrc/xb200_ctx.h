@@ -69,6 +69,9 @@ int  xb200_pad_planes(xb200_ctx *c, Pic &p, cudaStream_t stream = nullptr); // b
 // both loop-filter passes of picture p on `stream` from device-resident maps and edge flags (xb200_frame.cu)
 int  xb200_deblock_dev(xb200_ctx *c, Pic &p, const xb200_df_pic *pp, const uint32_t *d_scu, const int8_t *d_refi, const int16_t *d_mv,
                        const uint8_t *d_flags, cudaStream_t stream);
+int  xb200_preload_api_kernels();          // force-load the short kernels that run next to the chain server (lazy module loading)
+int  xb200_preload_frame_kernels();
+void xb200_chain_drain_end(int device);    // after xb200_chain_free and the context's cudaFree calls: the scheduler may publish again
 void xb200_chain_free(xb200_ctx *c);      // releases the decision-pass state of a context (xb200_chain.cu)
 int  xb200_sync_pics(xb200_ctx *c);       // refresh the device-side picture table (c->d_pics)
 

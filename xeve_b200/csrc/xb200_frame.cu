@@ -7,6 +7,15 @@
 #define finish xb200_finish
 #define ensure xb200_ensure
 
+int xb200_preload_frame_kernels()   // see xb200_preload_api_kernels
+{
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_df_pass<false>));
+    CK(cudaFuncGetAttributes(&fa, k_df_pass<true>));
+    CK(cudaFuncGetAttributes(&fa, k_df_mark));
+    return XB200_OK;
+}
+
 int xb200_deblock_dev(xb200_ctx *c, Pic &p, const xb200_df_pic *pp, const uint32_t *d_scu, const int8_t *d_refi, const int16_t *d_mv,
                       const uint8_t *d_flags, cudaStream_t stream)
 {
