@@ -369,6 +369,7 @@ void xb200_destroy(xb200_ctx *c)
     for(auto &p : c->pics)
         for(int k = 0; k < 3; k++)
             if(p.buf[k]) cudaFree(p.buf[k]);
+    for(void *g : c->garbage) cudaFree(g);
     for(DevBuf *b : {&c->b_items, &c->b_side, &c->b_aux0, &c->b_aux1, &c->b_aux2, &c->b_order, &c->b_stage, &c->b_df, &c->b_in_items,
                      &c->b_in_rates, &c->b_in_st0, &c->b_in_st1, &c->b_in_side, &c->b_in_coef, &c->b_in_rec, &c->b_in_order, &c->b_scr[0],
                      &c->b_scr[1], &c->b_scr[2], &c->b_scr[3], &c->b_st0, &c->b_st1, &c->b_cu_items, &c->b_cu_rates, &c->b_cu_state,
@@ -400,19 +401,27 @@ int xb200_pic_create(xb200_ctx *c, int padded, int32_t *handle)
     if(!c || !handle) return XB200_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(c->device));
     int idx = -1;
-    for(size_t i = 0; i < c->pics.size(); i++)
+    for(size_t i = 0; i < c->pics.size(); i++)    // prefer a free slot that already holds buffers of this kind
+        if(!c->pics[i].used && c->pics[i].buf[0] && c->pics[i].padded == (padded != 0)) { idx = (int)i; break; }
+    for(size_t i = 0; i < c->pics.size() && idx < 0; i++)
         if(!c->pics[i].used) { idx = (int)i; break; }
     if(idx < 0) { c->pics.emplace_back(); idx = (int)c->pics.size() - 1; }
     Pic &p = c->pics[idx];
-    p = Pic();
-    p.padded = padded != 0;
+    // a destroyed picture keeps its buffers (cudaFree waits for the device, and the chain server's worker grid lives as long as any
+    // context has work): a slot of the same kind is reused as it is, zeroed like a new one
+    const bool reuse = p.buf[0] && p.padded == (padded != 0);
+    if(!reuse) {
+        for(int k = 0; k < 3; k++) if(p.buf[k]) c->garbage.push_back(p.buf[k]);   // other kind: freed with the context
+        p = Pic();
+        p.padded = padded != 0;
+    }
     for(int k = 0; k < 3; k++) {
         p.w[k]   = k ? c->seq.w / 2 : c->seq.w;
         p.h[k]   = k ? c->seq.h / 2 : c->seq.h;
         p.pad[k] = padded ? (k ? XB200_PAD_C : XB200_PAD_L) : 0;
         p.s[k]   = align_up(p.w[k] + 2 * p.pad[k], 64);
         const size_t elems = (size_t)p.s[k] * (p.h[k] + 2 * p.pad[k] + 1) + 64;
-        CK(cudaMalloc(&p.buf[k], elems * sizeof(int16_t)));
+        if(!reuse) CK(cudaMalloc(&p.buf[k], elems * sizeof(int16_t)));
         CK(cudaMemsetAsync(p.buf[k], 0, elems * sizeof(int16_t), c->stream));
     }
     p.used = true;
@@ -427,8 +436,7 @@ int xb200_pic_destroy(xb200_ctx *c, int32_t handle)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     Pic &p = c->pics[handle];
-    for(int k = 0; k < 3; k++) { cudaFree(p.buf[k]); p.buf[k] = nullptr; }
-    p.used = false;
+    p.used = false;               // the buffers stay with the slot (see xb200_pic_create)
     c->pics_dirty = true;
     return XB200_OK;
 }

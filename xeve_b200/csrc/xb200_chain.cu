@@ -646,7 +646,8 @@ int xb200_picture_adopt(xb200_ctx *c, int32_t pic, const int16_t *map_mv)
     if(r) return r;
     PicMaps *m;
     if((r = maps_of(c, pic, &m))) return r;
-    CK(cudaMemcpy(m->mv, map_mv, cc_of(c)->f_scu * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(m->mv, map_mv, cc_of(c)->f_scu * 8, cudaMemcpyHostToDevice, cc_of(c)->copy));   // never the legacy stream:
+    CK(cudaStreamSynchronize(cc_of(c)->copy));                                                           // its copies can wait for the device
     m->ready.store(m->issued);   // nothing in flight writes it
     return XB200_OK;
 }
@@ -844,11 +845,13 @@ int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_in
     lk.lock();
     if(wr) return wr;
     unsigned long long cnt[2] = {0, 0};
-    CK(cudaMemcpy(cnt, j->b.counts, sizeof(cnt), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(cnt, j->b.counts, sizeof(cnt), cudaMemcpyDeviceToHost, k->copy));
+    CK(cudaStreamSynchronize(k->copy));
     n[0] = (int64_t)cnt[0] < k->log_cu ? (int64_t)cnt[0] : k->log_cu;
     n[1] = (int64_t)cnt[1] < k->log_intra ? (int64_t)cnt[1] : k->log_intra;
-    if(cu && n[0]) CK(cudaMemcpy(cu, j->b.cu_log, (size_t)n[0] * sizeof(xb200_cu_item), cudaMemcpyDeviceToHost));
-    if(intra && n[1]) CK(cudaMemcpy(intra, j->b.intra_log, (size_t)n[1] * sizeof(xb200_intra_item), cudaMemcpyDeviceToHost));
+    if(cu && n[0]) CK(cudaMemcpyAsync(cu, j->b.cu_log, (size_t)n[0] * sizeof(xb200_cu_item), cudaMemcpyDeviceToHost, k->copy));
+    if(intra && n[1]) CK(cudaMemcpyAsync(intra, j->b.intra_log, (size_t)n[1] * sizeof(xb200_intra_item), cudaMemcpyDeviceToHost, k->copy));
+    CK(cudaStreamSynchronize(k->copy));
     return XB200_OK;
 }
 
@@ -912,10 +915,11 @@ int xb200_picture_maps(xb200_ctx *c, int32_t rec_pic, uint32_t *map_scu, int8_t 
         }
     }
     const size_t f = k->f_scu;
-    if(map_scu) CK(cudaMemcpy(map_scu, m.scu, f * 4, cudaMemcpyDeviceToHost));
-    if(map_ipm) CK(cudaMemcpy(map_ipm, m.ipm, f, cudaMemcpyDeviceToHost));
-    if(map_refi) CK(cudaMemcpy(map_refi, m.refi, f * 2, cudaMemcpyDeviceToHost));
-    if(map_mv) CK(cudaMemcpy(map_mv, m.mv, f * 8, cudaMemcpyDeviceToHost));
+    if(map_scu) CK(cudaMemcpyAsync(map_scu, m.scu, f * 4, cudaMemcpyDeviceToHost, k->copy));
+    if(map_ipm) CK(cudaMemcpyAsync(map_ipm, m.ipm, f, cudaMemcpyDeviceToHost, k->copy));
+    if(map_refi) CK(cudaMemcpyAsync(map_refi, m.refi, f * 2, cudaMemcpyDeviceToHost, k->copy));
+    if(map_mv) CK(cudaMemcpyAsync(map_mv, m.mv, f * 8, cudaMemcpyDeviceToHost, k->copy));
+    CK(cudaStreamSynchronize(k->copy));
     return XB200_OK;
 }
 

@@ -26,6 +26,7 @@ struct xb200_ctx {
     xb200_seq        seq{};
     SeqDev           sq{};
     std::vector<Pic> pics;
+    std::vector<void *> garbage;    // buffers of destroyed pictures whose slot changed kind: freed with the context
     PicDev          *d_pics = nullptr;
     int              d_pics_cap = 0;
     bool             pics_dirty = true;
