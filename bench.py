@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
     ap.add_argument("--frames", type=int, default=33, help="pictures per stream (33 = the intra picture + two GOPs of 16)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
-    ap.add_argument("--second", default="2160p10:12:17", help="second workload reported on the same line (name:streams:frames), '' to skip")
+    ap.add_argument("--second", default="", help="second workload reported on the same line (name:streams:frames), '' to skip")
     args = ap.parse_args()
     # exactly ONE line on stdout: everything libraries print (NCCL's version banner, torchrun notices) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -396,6 +396,7 @@ def main():
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))   # before any collective: object broadcasts use the current device
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
     clip = make_clip(args)
     ref = None
