@@ -202,7 +202,10 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         seq = t.cpu().numpy().view(api.SEQ).copy()
     hp = api.Hotpath(seq, device=dev)
     capacity = hp.chain_capacity()
-    encs = [ClipEncoder(seq, plan, hp=hp, threads=T) for _ in range(S)]
+    # two sets of S encoder instances: consecutive steps are independent workloads, so step k + 1 is enqueued while the last pictures of
+    # step k are still in flight (the tail of a step -- the deepest layer of the last GOP -- cannot fill the device by itself)
+    sets = [[ClipEncoder(seq, plan, hp=hp, threads=T) for _ in range(S)] for _ in range(2)]
+    encs = sets[0] + sets[1]
     pocs = [int(p["pp"]["poc"]) for p in plan]
 
     def pin(a):
@@ -215,23 +218,33 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         for e in encs:
             e.upload(host_frames, c.depth)
 
-    def enqueue_all():
-        for e in encs:
+    def enqueue_set(es):
+        for e in es:
             e.reset()
         for k in range(F):                         # coding order, the streams interleaved: every stream advances with the others
-            for e in encs:
+            for e in es:
                 e.enqueue(k)
 
     chain_ms, n_cu = [], [0, 0]
 
-    def step_device():
-        """originals resident in HBM -> every picture decided, filtered, border-expanded (records stay on the device)"""
-        enqueue_all()
-        for e in encs:
+    def wait_set(es):
+        for e in es:
             for poc in pocs:
                 st = e.wait(poc)
                 chain_ms.append(float(st["chain_ms"]))
                 n_cu[0] += int(st["n_inter"]); n_cu[1] += int(st["n_intra"])
+
+    def run_steps(n):
+        """n steps, each = S streams x F pictures with the originals resident in HBM -> every picture decided, filtered,
+        border-expanded (records stay on the device).  Starts and ends on an idle device; in between the next step's pictures are
+        already queued when a step's last pictures finish."""
+        if n <= 0:
+            return
+        enqueue_set(sets[0])
+        for i in range(n):
+            if i + 1 < n:
+                enqueue_set(sets[(i + 1) % 2])
+            wait_set(sets[i % 2])
 
     # e2e: the public API.  One process, one host thread per stream (integration/xb200_streams.c linked against the drop-in library)
     clip_path = f"/dev/shm/xb200_bench_{os.getpid()}_{rank}.yuv"
@@ -248,8 +261,7 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
             dist.barrier()
 
     upload_all()
-    for _ in range(args.warmup):
-        step_device()
+    run_steps(args.warmup)
     chain_ms.clear(); n_cu[0] = n_cu[1] = 0
     sampler = ClockSampler(dev)
     sampler.start()
@@ -257,23 +269,22 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
     hp.chain_span_ms(reset=True)
     barrier()
     t0 = time.perf_counter()
-    spans = []
-    for _ in range(args.steps):
-        step_device()
-        spans.append(hp.chain_span_ms(reset=True))
+    run_steps(args.steps)
+    spans = [hp.chain_span_ms(reset=True) / max(args.steps, 1)]
     barrier()
     sec = time.perf_counter() - t0
     launches = hp.launches - launches0
     # e2e: one warm-up pass, then the timed passes (each pass = the whole job, encoders created anew; the program times a pass from the
     # first push to the last bitstream byte).  The Python process keeps its device context but launches nothing meanwhile.
     barrier()
+    e2e_steps = min(args.steps, 3)   # every pass is a whole job of S x F pictures from cold encoders: a bounded number of them
     e2e_error = None
     try:
-        e2e_passes, md5s = step_e2e(1 + args.steps)
+        e2e_passes, md5s = step_e2e(1 + e2e_steps)
     except Exception as e:  # noqa: BLE001 -- the line is still emitted, marked invalid, so that the failure is visible in the record
         e2e_error = str(e)[:400]
         dummy = {"wall_s": float("inf"), "per_stream": [{"err": -1, "device_pictures": 0, "bytes": 0, "wait_ms": 0.0, "push_s": 0.0}]}
-        e2e_passes, md5s = [dummy] * (1 + args.steps), []
+        e2e_passes, md5s = [dummy] * (1 + e2e_steps), []
     finally:
         if os.path.exists(clip_path):
             os.unlink(clip_path)
@@ -292,7 +303,8 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         ok = bool(int(okt[0]))
     pics = world * S * F * args.steps
-    value, e2e = pics / sec, (pics / sec_e2e if sec_e2e > 0 and np.isfinite(sec_e2e) else 0.0)
+    pics_e2e = world * S * F * e2e_steps
+    value, e2e = pics / sec, (pics_e2e / sec_e2e if sec_e2e > 0 and np.isfinite(sec_e2e) else 0.0)
     # roofline of the dominant kernel (k_chain): algorithmic bytes of one picture / mean launch duration measured live with CUDA events
     peaks = {}
     try:
@@ -316,10 +328,13 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         "vs_baseline": None, "dtype": "s16", "data": "synthetic",
         "config": {"workload": workload_string(args, c, preset), "streams_per_gpu": S, "pictures_per_stream": F, "threads": T,
                    "l2": f"inputs larger than L2 ({h2d / 2**20:.0f} MiB of original pictures per step)",
+                   "steps": "independent workloads, pipelined two deep: step k + 1 is enqueued while the last pictures of step k are in flight; "
+                            "the timed region starts and ends on an idle device",
                    "host_side": "reference control plane + entropy coder (no decision on the host); value: picture plan from the control plane run dry, "
                                 "e2e: the drop-in library's hooks inside the reference's own xeve_encode"},
         "e2e": {"value": round(e2e, 3), "unit": "pictures/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": round(1e3 * sec_e2e / args.steps, 2) if np.isfinite(sec_e2e) else None, "bitstream_md5": md5s, "reference_md5": ref_md5, "bitstream_matches_reference": ok,
+                "ms_per_step": round(1e3 * sec_e2e / e2e_steps, 2) if np.isfinite(sec_e2e) else None, "steps": e2e_steps, "warmup": 1,
+                "bitstream_md5": md5s, "reference_md5": ref_md5, "bitstream_matches_reference": ok,
                 "bitstream_bytes_per_stream": int(e2e_passes[-1]["per_stream"][0]["bytes"]),
                 "api": "xeve_create / xeve_push / xeve_encode of oracle/_ref/libxeve_b200_dropin.so, one host thread per stream (xb200_streams)",
                 "host_wait_on_device_ms_per_stream": round(float(np.mean([st["wait_ms"] for p in e2e_passes for st in p["per_stream"]])), 1),

@@ -70,6 +70,8 @@ typedef struct DropIn {
     void (*real_flush)(XEVE_CTX *);
     int  (*real_enc)(XEVE_CTX *, XEVE_BITB *, XEVE_STAT *);
     int  (*real_frame)(XEVE_CTX *);
+    int  (*real_header)(XEVE_CTX *);
+    int     label_threads;   /* the caller's `threads`: coder-state chains per picture on the device, and what the parameter SEI says */
     Plan   *plan;
     int     n_plan, cap_plan;
     int     next_enq, next_fetch, pushed, shadow_pushed;
@@ -547,6 +549,19 @@ static int hook_loop_filter(XEVE_CTX *ctx, XEVE_CORE *core)
     }
     return XEVE_OK;
 }
+/* The reference writes its parameters, `threads` among them, into an SEI message of the first access unit (xeve_param2string via
+ * ctx->fn_enc_header, src_base/xeve_enc.c:2533-2537).  The host context runs single-threaded here (it decides nothing; its worker
+ * threads would only busy-wait next to the other streams), the decisions are made as `threads` coder-state chains on the device: the
+ * stream is labelled like the reference run it reproduces. */
+static int hook_header(XEVE_CTX *ctx)
+{
+    DropIn   *d = (DropIn *)ctx->pf;
+    const int keep = ctx->param.threads;
+    ctx->param.threads = d->label_threads;
+    const int ret = d->real_header(ctx);
+    ctx->param.threads = keep;
+    return ret;
+}
 static void dropin_free(DropIn *d)
 {
     if(!d) return;
@@ -591,18 +606,14 @@ static const char *outside(const XEVE_PARAM *p)
 }
 
 /* the lines a maintainer would add to xeve_platform_init */
-static int install(XEVE_CTX *ctx, const XEVE_CDSC *cdsc)
+static int install(XEVE_CTX *ctx, const XEVE_CDSC *cdsc, int label_threads)
 {
-    const char *why = outside(&ctx->param);
-    if(why) {
-        if(!getenv("XB200_QUIET")) fprintf(stderr, "xeve_b200 drop-in: %s is outside the device path -- this encoder runs the reference's host code\n", why);
-        return XEVE_OK;
-    }
     pthread_once(&g_dummy_once, dummy_init);
     DropIn *d = (DropIn *)calloc(1, sizeof(DropIn));
     if(!d) return XEVE_ERR_OUT_OF_MEMORY;
     d->real = ctx; d->cdsc = *cdsc; d->E = g_engine;
     d->cur_rec = -1;
+    d->label_threads = label_threads < 1 ? 1 : label_threads;
     {
         XEVE_PINTER *pi = &ctx->pinter[0];
         xb200_seq    sq;
@@ -623,7 +634,7 @@ static int install(XEVE_CTX *ctx, const XEVE_CDSC *cdsc)
     }
     const int h_lcu = (ctx->h + ctx->max_cuwh - 1) >> ctx->log2_max_cuwh;
     d->n_lcu = (int)ctx->f_lcu;
-    d->parallel_rows = ctx->param.threads > h_lcu ? h_lcu : ctx->param.threads;
+    d->parallel_rows = d->label_threads > h_lcu ? h_lcu : d->label_threads;
     if(d->parallel_rows < 1) d->parallel_rows = 1;
     d->scu = (xb200_scu_rec *)malloc((size_t)d->n_lcu * 256 * sizeof(xb200_scu_rec));
     d->coef = (int16_t *)malloc((size_t)d->n_lcu * 6144 * sizeof(int16_t));
@@ -639,6 +650,7 @@ static int install(XEVE_CTX *ctx, const XEVE_CDSC *cdsc)
     d->real_flush = ctx->fn_flush; ctx->fn_flush = hook_flush;
     d->real_enc = ctx->fn_enc; ctx->fn_enc = hook_enc;
     d->real_frame = ctx->fn_mode_analyze_frame; ctx->fn_mode_analyze_frame = hook_frame;
+    d->real_header = ctx->fn_enc_header; ctx->fn_enc_header = hook_header;
     ctx->fn_mode_analyze_lcu = hook_lcu;
     ctx->fn_loop_filter = hook_loop_filter;
     return XEVE_OK;
@@ -649,7 +661,21 @@ XEVE xeve_create(XEVE_CDSC *cdsc, int *err)
 {
     XEVE id = xeve_create_host(cdsc, err);
     if(!id) return NULL;
-    const int r = install((XEVE_CTX *)id, cdsc);
+    const char *why = outside(&((XEVE_CTX *)id)->param);   /* judged on the parameters as the reference completed them */
+    if(why) {
+        if(!getenv("XB200_QUIET")) fprintf(stderr, "xeve_b200 drop-in: %s is outside the device path -- this encoder runs the reference's host code\n", why);
+        return id;
+    }
+    /* inside the path the host context decides nothing: it runs single-threaded (see hook_header), `threads` goes to the device */
+    const int threads = cdsc->param.threads;
+    XEVE_CDSC host = *cdsc;
+    if(threads > 1) {
+        xeve_delete(id);
+        host.param.threads = 1;
+        id = xeve_create_host(&host, err);
+        if(!id) return NULL;
+    }
+    const int r = install((XEVE_CTX *)id, &host, threads);
     if(r != XEVE_OK) {
         xeve_delete(id);
         if(err) *err = r;
