@@ -202,10 +202,7 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         seq = t.cpu().numpy().view(api.SEQ).copy()
     hp = api.Hotpath(seq, device=dev)
     capacity = hp.chain_capacity()
-    # two sets of S encoder instances: consecutive steps are independent workloads, so step k + 1 is enqueued while the last pictures of
-    # step k are still in flight (the tail of a step -- the deepest layer of the last GOP -- cannot fill the device by itself)
-    sets = [[ClipEncoder(seq, plan, hp=hp, threads=T) for _ in range(S)] for _ in range(2)]
-    encs = sets[0] + sets[1]
+    encs = [ClipEncoder(seq, plan, hp=hp, threads=T) for _ in range(S)]
     pocs = [int(p["pp"]["poc"]) for p in plan]
 
     def pin(a):
@@ -236,15 +233,12 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
 
     def run_steps(n):
         """n steps, each = S streams x F pictures with the originals resident in HBM -> every picture decided, filtered,
-        border-expanded (records stay on the device).  Starts and ends on an idle device; in between the next step's pictures are
-        already queued when a step's last pictures finish."""
-        if n <= 0:
-            return
-        enqueue_set(sets[0])
-        for i in range(n):
-            if i + 1 < n:
-                enqueue_set(sets[(i + 1) % 2])
-            wait_set(sets[i % 2])
+        border-expanded (records stay on the device).  Every step starts and ends on an idle device.
+        (Enqueuing step k + 1 behind the tail of step k -- two sets of encoders, 1 584 device pictures -- did not finish within its
+        time limit on the GPU box and could not be investigated within the round's GPU budget)"""
+        for _ in range(n):
+            enqueue_set(encs)
+            wait_set(encs)
 
     # e2e: the public API.  One process, one host thread per stream (integration/xb200_streams.c linked against the drop-in library)
     clip_path = f"/dev/shm/xb200_bench_{os.getpid()}_{rank}.yuv"
@@ -328,8 +322,7 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
         "vs_baseline": None, "dtype": "s16", "data": "synthetic",
         "config": {"workload": workload_string(args, c, preset), "streams_per_gpu": S, "pictures_per_stream": F, "threads": T,
                    "l2": f"inputs larger than L2 ({h2d / 2**20:.0f} MiB of original pictures per step)",
-                   "steps": "independent workloads, pipelined two deep: step k + 1 is enqueued while the last pictures of step k are in flight; "
-                            "the timed region starts and ends on an idle device",
+                   "steps": "every step starts and ends on an idle device (S x F pictures enqueued at once, ordered by the picture DAG)",
                    "host_side": "reference control plane + entropy coder (no decision on the host); value: picture plan from the control plane run dry, "
                                 "e2e: the drop-in library's hooks inside the reference's own xeve_encode"},
         "e2e": {"value": round(e2e, 3), "unit": "pictures/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
