@@ -421,7 +421,9 @@ XB200_API int xb200_deblock(xb200_ctx *c, int32_t pic, const xb200_df_cu *cus, i
  *   with init_cu_data / copy_cu_data / copy_to_cu_data, update_map_scu / clear_map_scu, mode_cpy_rec_to_ref, update_to_ctx_map,
  *   xeve_pinter_analyze_cu and pintra_analyze_cu for every CU the tree visits (the operators above, as device functions),
  *   then ctx->fn_loop_filter and ctx->fn_picbuf_expand     (src_base/xeve_enc.c:407, 1274)
- * in ONE persistent kernel of one CTA per coder-state chain plus the loop-filter grids: no host round trip per CU or per CTU.
+ * on the device with no host round trip per CU or per CTU: every coder-state chain of every picture in flight is a task of ONE
+ * long-lived grid of 128-thread chain workers (the "chain server", a device-side FIFO fed by a per-device scheduler thread that all
+ * contexts of the process share), followed by the two loop-filter grids and the border expansion of the picture.
  * A chain is what the reference calls a worker thread: with parallel_rows = n (param.threads, at most the CTU rows) CTU rows
  * y, y + n, .. form one chain, each chain starts from the reset coder state and a CTU waits for its upper-right neighbour
  * (src_base/xeve_enc.c:128-132) -- bit-exact with the reference run with `threads = n`; n = 1 is the single-thread bitstream.
@@ -461,7 +463,9 @@ typedef struct {            /* what xb200_picture_fetch reports besides the reco
     double  chain_ms, filter_ms;         /* device time of the decision kernel and of the loop filter + border expansion */
 } xb200_picture_stat;
 
-/* Enqueues the picture and returns; fails with XB200_ERR_UNSUPPORTED for P slices and out-of-range CU sizes. */
+/* Queues the picture and returns at once; it runs when its reference pictures are complete and the workers can take all its chains.
+ * Fails with XB200_ERR_UNSUPPORTED for P slices and out-of-range CU sizes.  A picture handle (rec_pic, cur_pic, reference pictures)
+ * must not be reused or destroyed while a queued picture reads or writes it: fetch the pictures that reference it first. */
 XB200_API int xb200_analyze_picture(xb200_ctx *c, const xb200_picture *pp);
 /* Waits for picture rec_pic and copies its records to the caller (host buffers; any pointer may be NULL): scu [n_lcu * 256],
  * coef [n_lcu * 6144], ctu_states [n_lcu][2] (the coder state each CTU's decision pass started from / ended with), ctu_cost [n_lcu]. */
@@ -480,7 +484,7 @@ XB200_API int xb200_picture_adopt(xb200_ctx *c, int32_t pic, const int16_t *map_
  * xb200_picture_log copies those of picture rec_pic to the caller and returns their counts through n[2]. */
 XB200_API int xb200_picture_log_enable(xb200_ctx *c, int64_t cap_cu, int64_t cap_intra);
 XB200_API int xb200_picture_log(xb200_ctx *c, int32_t rec_pic, xb200_cu_item *cu, xb200_intra_item *intra, int64_t n[2]);
-/* Number of decision chains (CTAs of the persistent kernel) the device can hold at once; pictures beyond it queue on the host. */
+/* Number of chain workers of the device (CTAs of the chain server for the default working set); pictures beyond it queue on the host. */
 XB200_API int xb200_chain_capacity(xb200_ctx *c);
 /* Device time (ms, CUDA events) from the first picture enqueued after the last reset to the latest completion among the pictures
  * fetched since: the span of a batch of pictures that ran concurrently on the library's own streams.  reset != 0 starts a new batch. */

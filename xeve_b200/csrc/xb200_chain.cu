@@ -1,11 +1,13 @@
 // xb200_chain.cu -- host side of the picture-level decision pass (xb200_analyze_picture and friends, include/xeve_b200.h).
 // Own translation unit with its own (static) copies of the constant tables, like xb200_intra.cu.
 //
-// A call enqueues, on one of the context's picture streams: the persistent decision kernel (k_chain, one CTA per coder-state chain),
-// an optional copy of the unfiltered reconstruction, both loop-filter passes and the border expansion.  Dependencies between
-// pictures are CUDA events on the reference pictures, so the pictures of one wave of the picture DAG run
-// concurrently without the host waiting.  Chains spin on flags of their own picture only; the host admits a picture to the device
-// when all its chains fit next to the ones already there (a CTA that cannot become resident while its siblings spin would dead-lock).
+// xb200_analyze_picture only QUEUES a picture.  One scheduler thread per device (shared by every context of the process) owns the
+// chain server -- a long-lived grid of chain workers with a device-side task queue (xb200_chain.cuh: k_chain_server) -- and publishes
+// a picture to it when its reference pictures are complete and the workers can take all its chains; when the last chain has finished
+// (a word in host-mapped memory) it launches the optional copy of the unfiltered reconstruction, both loop-filter passes and the
+// border expansion on one of the context's streams, whose completion callback makes the picture a usable reference.  The host
+// never waits per CU or CTU; xb200_picture_fetch waits per picture.  Rules that keep a grid that outlives its work from dead-locking
+// are collected in DESIGN.md section 2 and next to server_init / xb200_chain_free below.
 #define XB200_CONST_LINKAGE static
 #define XB200_CHAIN_TU
 #define XB200_T64 128

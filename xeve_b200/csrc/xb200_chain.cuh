@@ -10,16 +10,17 @@
 //              mode_cpy_rec_to_ref                            src_base/xeve_mode.c:797-866
 //              xeve_eco_split_mode (bit-count mode)           src_base/xeve_eco.c:1377-1429
 //
-// One CTA per coder-state CHAIN (what the reference calls a worker thread: CTU rows y, y + n, .. with threads = n; one chain per
-// picture with threads = 1).  The CTA walks its CTUs in raster order; inside a CTU it runs the quad-tree recursion as an explicit
-// state machine, uniform over its 128 threads.  Every CU analysis is the SAME device function the work-list operators run
-// (analyze_cu_one of xb200_analyze.cuh, intra_cu_one / intra_thr_one of xb200_intra.cuh) on a team made of the CTA's first 32 or all
-// 128 threads; the bookkeeping between them (CU-data copies, frame maps, the picture under reconstruction) is spread over all 128.
-// 128 threads, not 256: a chain keeps one to three warps busy most of the time, and the registers of idle warps are what limits the
-// number of chains an SM can hold.
+// One 128-thread CTA runs one coder-state CHAIN at a time (what the reference calls a worker thread: CTU rows y, y + n, .. with
+// threads = n; one chain per picture with threads = 1).  The CTA walks the chain's CTUs in raster order; inside a CTU it runs the
+// quad-tree recursion as an explicit state machine, uniform over its 128 threads.  Every CU analysis is the SAME device function the
+// work-list operators run (analyze_cu_one / analyze_cu_par of xb200_analyze*.cuh, intra_cu_one / intra_thr_one of xb200_intra.cuh) on
+// a team made of the CTA's first 32 or all 128 threads; the bookkeeping between them (CU-data copies, frame maps, the picture under
+// reconstruction) is spread over all 128.  128 threads, not 256: a chain keeps one to three warps busy most of the time, and the
+// registers of idle warps are what limits the number of chains an SM can hold.
 // A chain waits for the CTU above-right of its next CTU through a flag in global memory (src_base/xeve_enc.c:128-132); data written by
 // other chains (frame maps, reconstructed samples) is read with L2 loads (ld.cg): the L1 of this SM may hold older copies of lines that
-// straddle two CTUs.  Nothing returns to the host until the picture is done.
+// straddle two CTUs.  The CTAs are the workers of the chain server at the end of this file: they take chains of whatever picture
+// comes next from a device-side queue; nothing returns to the host until a picture is done.
 #pragma once
 #define XB200_DEVICE_FUNCS_ONLY
 #define XB200_INTRA64_CAND_GLOBAL
