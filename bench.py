@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- pictures ENCODED per second: whole streams through the device decision pass, bitstream checked inside the run.
 
-A "step" = S independent streams x F pictures of the workload's synthetic clip (default: 1080p 8-bit, Baseline profile, preset fast,
-default hierarchical-B GOP, CQP 32), each stream encoded from its original pictures to the MPEG-5 EVC bitstream:
+A "step" = S independent streams x F pictures of the workload's synthetic clip (default: 12 x 17, 1080p 8-bit, Baseline profile, preset
+fast, default hierarchical-B GOP, CQP 32), each stream encoded from its original pictures to the MPEG-5 EVC bitstream.  A step of
+one-GOP streams takes ~11 s (it is bound by the latency of the picture DAG: the I picture, then five temporal layers), so that the
+driver's `--steps 20 --warmup 5` stays well inside its time limit; `--frames 33` (two GOPs per stream, ~18 s per step) amortises the I
+pictures and is what profiles/r02s18 quotes (22.5 pictures/s device-resident, 17.2 through the public API).
 
   device : xb200_analyze_picture per picture -- ONE persistent kernel runs the CTU loop, the quad-tree mode decision with every inter /
            intra CU analysis, then the loop filter and the border expansion; the pictures of all streams that can be coded from the
@@ -392,7 +395,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=12, help="independent streams per GPU per step")
-    ap.add_argument("--frames", type=int, default=33, help="pictures per stream (33 = the intra picture + two GOPs of 16)")
+    ap.add_argument("--frames", type=int, default=17, help="pictures per stream (17 = the intra picture + one GOP of 16; 33 = two GOPs)")
     ap.add_argument("--threads", type=int, default=8, help="parity mode: the reference's `threads` (coder-state chains per picture)")
     ap.add_argument("--second", default="", help="second workload reported on the same line (name:streams:frames), '' to skip")
     args = ap.parse_args()

@@ -1,18 +1,19 @@
 #!/bin/bash
-# First GPU calls of the next round: everything here was written after round 1's GPU budget ran out.
-# Usage: run the blocks one at a time (one gpurun call each); outputs land in gpurun_out/, copy what matters to profiles/.
+# First GPU calls of a next round.  One gpurun call each; outputs land in gpurun_out/, copy what matters to profiles/.
+# Always gate long runs behind tools/gpu_mini.sh (fixture -> three streams -> live pictures -> a small bench, stops at the first failure):
+# a hang costs the whole time limit of the call.
 set -e
 G=/usr/local/graft/bin/gpurun
 
-# 1. the whole GPU suite incl. the provisional tests (xfail output tells what to fix); then promote them to hard assertions
-$G --timeout 600 -- 'python -m pytest tests -q -m gpu -rxX 2>&1 | tee gpurun_out/gpu_suite.log | tail -30'
+# 1. the gate + a small bench with the scheduler's trace
+$G --timeout 700 -- 'BENCH_TIMEOUT=240 tools/gpu_mini.sh gate --streams 4 --frames 17 --steps 1 --warmup 0'
 
-# 2. the first Main-profile kernel: parity, launch time, one full ncu capture
-$G --timeout 600 -- 'python tests/transform_main_on_device.py > gpurun_out/transform_main.log 2>&1; tail -3 gpurun_out/transform_main.log;
-  ncu --set full --clock-control none --import-source on -k k_transform_main -c 2 -o gpurun_out/transform_main python tests/transform_main_on_device.py > /dev/null 2>&1 || true'
+# 2. the open question of round 2: 1 584 device pictures in one context (24 x 33, or two sets of 12 x 33) did not finish.  Start with
+#    the scheduler trace of the device-resident arm only, 24 streams x 17 pictures, and watch launch rates
+$G --timeout 500 -- 'XB200_SCHED_DEBUG=1 timeout 400 python -u bench.py --streams 24 --frames 17 --steps 1 --warmup 0 > gpurun_out/s24.json 2> gpurun_out/s24.err; tail -5 gpurun_out/s24.err'
 
-# 3. the chain on the device with device-side inputs, further configurations, and the kernel-time / wall-time split per call
-$G --timeout 600 -- 'python tests/chain_on_device.py --all-inputs > gpurun_out/chain_all_inputs.log 2>&1; python tests/chain_on_device.py --all-inputs --more > gpurun_out/chain_more.log 2>&1; tail -6 gpurun_out/chain_all_inputs.log gpurun_out/chain_more.log'
+# 3. racecheck of the worker grid on the fixture (the 256-thread RDOQ hazard of round 1 is gone with 128-thread teams, but nothing proves it)
+$G --timeout 600 -- 'XB200_CHAIN_WORKERS=4 timeout 500 compute-sanitizer --tool racecheck python tests/picture_on_device.py --fixture-only > gpurun_out/racecheck.log 2>&1; tail -20 gpurun_out/racecheck.log'
 
-# 4. one stream over two GPUs: picture-DAG waves, reference pictures broadcast over NCCL
-$G --gpus 2 --timeout 600 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/chain_on_device.py --dag > gpurun_out/chain_dag_n2.log 2>&1; tail -6 gpurun_out/chain_dag_n2.log'
+# 4. the whole GPU suite and the default bench, N = 1, 2, 4, 8
+$G --timeout 600 -- 'python -m pytest tests -q -m gpu 2>&1 | tail -5; python bench.py > gpurun_out/bench_n1.json; cat gpurun_out/bench_n1.json'
