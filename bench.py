@@ -335,7 +335,8 @@ def run_b200(args, rank, world, dist, clip, ref_md5):
                 "api": "xeve_create / xeve_push / xeve_encode of oracle/_ref/libxeve_b200_dropin.so, one host thread per stream (xb200_streams)",
                 "host_wait_on_device_ms_per_stream": round(float(np.mean([st["wait_ms"] for p in e2e_passes for st in p["per_stream"]])), 1),
                 "push_ms_per_stream": round(1e3 * float(np.mean([st["push_s"] for p in e2e_passes for st in p["per_stream"]])), 1)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches),   # per picture 2 loop-filter grids + 1 border expansion, + one launch of the worker grid per busy period
+        "gpu_kernels": ["k_chain_server<3>", "k_df_pass<false>", "k_df_pass<true>", "k_pad3"],
         "device_span_ms_per_step": round(float(np.mean(spans)), 2),
         "chain": {"capacity_chains": capacity, "chains_per_picture": min(T, (c.h + 63) // 64), "kernel_ms_per_picture": round(mean_ms, 2),
                   "cu_analyses_per_step": int((n_cu[0] + n_cu[1]) / max(args.steps, 1)),

@@ -428,7 +428,6 @@ bool publish_job(DeviceSched &D, Job *j)
     unsigned *src = &D.h_tail[D.seq % 4096];
     *src = D.tail;
     CKJ(cudaMemcpyAsync(&D.dq->tail, src, sizeof(unsigned), cudaMemcpyHostToDevice, s));
-    c->launches++;
     D.chains += j->n_chain;
     D.running.push_back(j);
     j->state.store(JOB_RUNNING);
@@ -543,6 +542,7 @@ void sched_thread(DeviceSched *Dp)
                 if(D.chains > 0) break;
                 const size_t sm = j->smem > D.server_smem ? j->smem : D.server_smem;
                 if(!server_stop(D) || !server_start(D, sm)) { it = D.pending.erase(it); j->state.store(JOB_FAILED); any_ready = true; continue; }
+                j->c->launches++;   // the worker grid: one launch per busy period, counted for the context whose picture started it
             }
             if(D.chains + j->n_chain > D.workers && D.chains > 0) { ++it; continue; }
             if(D.free_slots.empty() || (unsigned)(D.chains + j->n_chain) > (unsigned)CH_Q_TASKS / 2) break;
