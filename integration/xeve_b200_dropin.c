@@ -86,6 +86,9 @@ typedef struct DropIn {
     int16_t       *coef;
     int            cur_rec; /* its device picture */
     xeve_b200_stats stats;
+    XEVE_MTIME    *ts;      /* presentation time stamps of the frames pushed so far (closed GOPs: the reference's slice-type decision reads them) */
+    int            n_ts, cap_ts;
+    int            need_sync;   /* sync mode: the picture is planned, enqueued and fetched at its first CTU */
     uint8_t       *sh_bs;   /* bitstream buffer of the shadow context */
     void          *dummy_buf;
     struct Shadow *s1;      /* sink of the incremental shadow context */
@@ -276,11 +279,19 @@ static void shadow_delete(XEVE_CTX *sh)
     xeve_delete((XEVE)sh);
 }
 /* one dummy frame into a shadow context, then every picture it can code */
+/* time stamp of input frame idx: the application's for the frames it has pushed, extrapolated for the ones the shadow runs ahead by */
+static XEVE_MTIME ts_of(const DropIn *d, int idx)
+{
+    if(idx < d->n_ts) return d->ts[idx];
+    if(d->n_ts >= 2) return d->ts[d->n_ts - 1] + (XEVE_MTIME)(idx - (d->n_ts - 1)) * (d->ts[d->n_ts - 1] - d->ts[d->n_ts - 2]);
+    return (d->n_ts == 1 ? d->ts[0] : 0) + idx;
+}
+/* push = -1: encode only; otherwise the index of the dummy frame to push first */
 static int shadow_step(DropIn *d, XEVE_CTX *sh, int push)
 {
     XEVE_BITB bitb;
     XEVE_STAT stat;
-    if(push) {
+    if(push >= 0) {
         XEVE_IMGB img;
         const int depth = d->cdsc.param.codec_bit_depth, bps = depth > 8 ? 2 : 1;
         memset(&img, 0, sizeof(img));
@@ -292,6 +303,7 @@ static int shadow_step(DropIn *d, XEVE_CTX *sh, int push)
             img.a[c] = d->dummy_buf;
         }
         img.addref = img_addref; img.getref = img_getref; img.release = img_release; img.refcnt = 1;
+        img.ts[XEVE_TS_PTS] = ts_of(d, push);
         if(XEVE_FAILED(xeve_push((XEVE)sh, &img))) return XEVE_ERR;
     }
     memset(&bitb, 0, sizeof(bitb));
@@ -400,10 +412,15 @@ static int hook_push(XEVE_CTX *ctx, XEVE_IMGB *img)
         }
         d->org[d->n_org].input = (int)ctx->pic_icnt; d->org[d->n_org].handle = h; d->n_org++;
         d->pushed = (int)ctx->pic_icnt + 1;
+        if(d->n_ts == d->cap_ts) {
+            d->cap_ts = d->cap_ts ? 2 * d->cap_ts : 256;
+            d->ts = (XEVE_MTIME *)realloc(d->ts, (size_t)d->cap_ts * sizeof(XEVE_MTIME));
+        }
+        d->ts[d->n_ts++] = img->ts[XEVE_TS_PTS];
     }
     if(!d->tail_done && !d->sync_mode && d->shadow) {   /* the shadow context stays DI_LEAD frames ahead */
         while(d->shadow_pushed < d->pushed + DI_LEAD) {
-            if(XEVE_FAILED(shadow_step(d, d->shadow, 1))) { DI_FAIL(d, "shadow context failed"); return XEVE_ERR; }
+            if(XEVE_FAILED(shadow_step(d, d->shadow, d->shadow_pushed))) { DI_FAIL(d, "shadow context failed"); return XEVE_ERR; }
             d->shadow_pushed++;
         }
     }
@@ -421,9 +438,9 @@ static int replan_tail(DropIn *d, int n_frames)
     s2.owner = d; s2.out = p2; s2.n_out = &n2; s2.cap_out = n_frames + 1;
     XEVE_CTX *sh = shadow_create(d, &s2);
     if(!sh) { free(p2); return XEVE_ERR; }
-    for(int i = 0; i < n_frames && !XEVE_FAILED(ret); i++) ret = shadow_step(d, sh, 1);
+    for(int i = 0; i < n_frames && !XEVE_FAILED(ret); i++) ret = shadow_step(d, sh, i);
     xeve_config((XEVE)sh, XEVE_CFG_SET_FORCE_OUT, &val, &size);
-    while(!XEVE_FAILED(ret) && ret != XEVE_OK_NO_MORE_FRM) ret = shadow_step(d, sh, 0);
+    while(!XEVE_FAILED(ret) && ret != XEVE_OK_NO_MORE_FRM) ret = shadow_step(d, sh, -1);
     shadow_delete(sh);
     if(XEVE_FAILED(ret) || n2 != n_frames) { free(p2); DI_FAIL(d, "tail plan: %d pictures for %d frames (ret %d)", n2, n_frames, ret); return XEVE_ERR; }
     /* the first picture whose guess differs from the exact plan, and everything after it in coding order, is redone: wait for the
@@ -445,9 +462,9 @@ static int hook_enc(XEVE_CTX *ctx, XEVE_BITB *bitb, XEVE_STAT *stat)
 {
     DropIn *d = (DropIn *)ctx->pf;
     if(d->failed) return XEVE_ERR;
-    if(FORCE_OUT(ctx) && !d->tail_done && !d->sync_mode) {
+    if(FORCE_OUT(ctx) && !d->tail_done) {
         d->tail_done = 1;
-        if(XEVE_FAILED(replan_tail(d, (int)ctx->pic_ticnt + 1))) return XEVE_ERR;
+        if(!d->sync_mode && XEVE_FAILED(replan_tail(d, (int)ctx->pic_ticnt + 1))) return XEVE_ERR;
         /* pictures the encoder would have coded before the end of the input had xeve_encode not answered "not available" while the
          * device worked: with N frames pushed it codes N - frm_rnum pictures in normal mode, the rest while bumping */
         d->catchup = (int)ctx->pic_ticnt + 1 - (int)ctx->frm_rnum - d->next_fetch;
@@ -478,29 +495,9 @@ static int hook_enc(XEVE_CTX *ctx, XEVE_BITB *bitb, XEVE_STAT *stat)
     return d->real_enc(ctx, bitb, stat);
 }
 
-/* the picture the reference is about to code: make sure it is (being) decided with the reference's own parameters, wait, fetch */
-static int hook_frame(XEVE_CTX *ctx)
+/* wait for picture idx (enqueued) and take its records */
+static int fetch_picture(DropIn *d, XEVE_CTX *ctx, int idx)
 {
-    DropIn *d = (DropIn *)ctx->pf;
-    d->cur_rec = -1;
-    if(d->failed) return XEVE_ERR;
-    const int idx = d->next_fetch;
-    int ok = idx < d->n_plan;
-    if(ok) {   /* what is known before the CTU loop must agree with the plan; the rest is checked at the first CTU */
-        const xb200_picture *pp = &d->plan[idx].pp;
-        ok = pp->poc == (int)ctx->poc.poc_val && pp->slice_type == ctx->slice_type && pp->tile_qp == ctx->sh->qp &&
-             d->plan[idx].input == (int)ctx->pico->pic_icnt;
-        for(int l = 0; l < 2 && ok; l++) {
-            if(ctx->slice_type == SLICE_I || (l == 1 && ctx->slice_type != SLICE_B)) continue;
-            ok = pp->num_refp[l] == ctx->rpm.num_refp[l];
-            for(int k = 0; k < pp->num_refp[l] && k < XB200_MAX_REFP && ok; k++) ok = pp->ref_poc[l][k] == (int)ctx->refp[k][l].poc;
-        }
-    }
-    if(!ok) {
-        DI_FAIL(d, "picture %d (POC %d): the picture plan does not match the encoder's state (parameters changed while encoding?)", idx,
-                (int)ctx->poc.poc_val);
-        return XEVE_ERR;
-    }
     if(XEVE_FAILED(enqueue_ready(d)) || d->plan[idx].state != 1) {
         if(!d->failed) DI_FAIL(d, "picture %d (POC %d) could not be enqueued", idx, (int)ctx->poc.poc_val);
         return XEVE_ERR;
@@ -520,12 +517,71 @@ static int hook_frame(XEVE_CTX *ctx)
     d->next_fetch++;
     d->stats.pictures++; d->stats.n_inter += st.n_inter; d->stats.n_intra += st.n_intra;
     d->stats.chain_ms += st.chain_ms; d->stats.filter_ms += st.filter_ms;
+    return XEVE_OK;
+}
+/* The plan ran ahead on a guess that the encoder's own state does not confirm (a parameter changed through xeve_config while
+ * encoding, a GOP structure the shadow context could not foresee): everything enqueued from this picture on is thrown away, and from
+ * now on every picture is planned from the real context at its first CTU, enqueued and waited for -- correct, without look-ahead. */
+static void enter_sync_mode(DropIn *d, int idx, const char *why)
+{
+    if(!getenv("XB200_QUIET")) fprintf(stderr, "xeve_b200 drop-in: picture %d: %s -- pictures are planned one at a time from here on\n", idx, why);
+    for(int j = d->n_plan - 1; j >= idx; j--) discard(d, j);
+    d->n_plan = idx;
+    if(d->next_enq > idx) d->next_enq = idx;
+    d->sync_mode = 1;
+}
+/* the picture the reference is about to code: make sure it is (being) decided with the reference's own parameters, wait, fetch */
+static int hook_frame(XEVE_CTX *ctx)
+{
+    DropIn *d = (DropIn *)ctx->pf;
+    d->cur_rec = -1;
+    d->need_sync = 0;
+    if(d->failed) return XEVE_ERR;
+    const int idx = d->next_fetch;
+    if(!d->sync_mode) {
+        int ok = idx < d->n_plan;
+        if(ok) {   /* what is known before the CTU loop must agree with the plan; the rest is checked at the first CTU */
+            const xb200_picture *pp = &d->plan[idx].pp;
+            ok = pp->poc == (int)ctx->poc.poc_val && pp->slice_type == ctx->slice_type && pp->tile_qp == ctx->sh->qp &&
+                 d->plan[idx].input == (int)ctx->pico->pic_icnt;
+            for(int l = 0; l < 2 && ok; l++) {
+                if(ctx->slice_type == SLICE_I || (l == 1 && ctx->slice_type != SLICE_B)) continue;
+                ok = pp->num_refp[l] == ctx->rpm.num_refp[l];
+                for(int k = 0; k < pp->num_refp[l] && k < XB200_MAX_REFP && ok; k++) ok = pp->ref_poc[l][k] == (int)ctx->refp[k][l].poc;
+            }
+        }
+        {   /* test knob: pretend the plan of picture n was wrong */
+            const char *e = getenv("XB200_DROPIN_FORCE_SYNC_AT");
+            if(e && atoi(e) == idx) ok = 0;
+        }
+        if(!ok) enter_sync_mode(d, idx, "the picture plan does not match the encoder's state");
+    }
+    if(d->sync_mode) d->need_sync = 1;   /* planned at the first CTU, where the lambdas exist */
+    else if(XEVE_FAILED(fetch_picture(d, ctx, idx))) return XEVE_ERR;
     return d->real_frame ? d->real_frame(ctx) : XEVE_OK;
 }
 static int hook_lcu(XEVE_CTX *ctx, XEVE_CORE *core)
 {
     DropIn *d = (DropIn *)ctx->pf;
-    if(d->failed || d->cur_rec < 0) return XEVE_ERR;
+    if(d->failed) return XEVE_ERR;
+    if(core->lcu_num == 0 && d->need_sync) {   /* sync mode: plan from the encoder's own state, enqueue, wait */
+        const int idx = d->next_fetch;
+        d->need_sync = 0;
+        if(idx >= d->cap_plan) {
+            d->cap_plan = d->cap_plan ? 2 * d->cap_plan : 64;
+            d->plan = (Plan *)realloc(d->plan, (size_t)d->cap_plan * sizeof(Plan));
+        }
+        Plan *p = &d->plan[idx];
+        memset(p, 0, sizeof(*p));
+        plan_from_ctx(ctx, core, &p->pp);
+        p->pp.parallel_rows = d->parallel_rows;
+        p->input = (int)ctx->pico->pic_icnt;
+        p->rec = p->org = -1;
+        d->n_plan = idx + 1;
+        d->next_enq = idx;
+        if(XEVE_FAILED(fetch_picture(d, ctx, idx))) return XEVE_ERR;
+    }
+    if(d->cur_rec < 0) return XEVE_ERR;
     if(core->lcu_num == 0) {   /* the lambdas exist now: the plan the device used must be the encoder's */
         xb200_picture cur;
         plan_from_ctx(ctx, core, &cur);
@@ -567,7 +623,7 @@ static void dropin_free(DropIn *d)
     if(!d) return;
     if(d->shadow) shadow_delete(d->shadow);
     if(d->dev) d->E->destroy(d->dev);
-    free(d->plan); free(d->scu); free(d->coef); free(d->sh_bs); free(d->dummy_buf); free(d->s1);
+    free(d->plan); free(d->scu); free(d->coef); free(d->sh_bs); free(d->dummy_buf); free(d->s1); free(d->ts);
     free(d);
 }
 static void hook_flush(XEVE_CTX *ctx)

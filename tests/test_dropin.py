@@ -75,6 +75,9 @@ def test_dropin_exports_the_reference_api():
     (17, 3, "fast", ""),          # exactly I + one GOP
     (3, 1, "fast", ""),           # fewer frames than the encoder's delay: everything is planned at the end
     (9, 1, "medium", "qp=27"),    # preset medium, lower QP
+    (30, 1, "fast", "keyint=8;closed_gop=1"),   # closed GOPs: the slice-type decision reads the frames' time stamps (mirrored into the shadow context)
+    (22, 2, "fast", "bframes=3"),               # GOP of 4
+    (12, 1, "fast", "bframes=0"),               # low delay
 ])
 def test_dropin_bitstream_equals_reference_with_cpu_engine_table(frames, threads, preset, extra):
     c, yuv = tracedata.clip_yuv("cif", frames, **QCIF)
@@ -93,6 +96,21 @@ def test_dropin_encode_does_not_block_the_pushes(monkeypatch):
     ref = rh.encode_clip(yuv, 40, c.w, c.h, in_depth=c.depth, preset="fast", threads=2).bitstream
     got, st = api_encode(yuv, 40, c.w, c.h, c.depth, "fast", 2)
     assert st.device_path == 1 and st.pictures == 40 and st.deferred > 10
+    assert np.array_equal(got, ref)
+
+
+@needs_dropin
+@pytest.mark.parametrize("at", [0, 9, 22])
+def test_dropin_falls_back_to_one_picture_at_a_time_when_the_plan_is_wrong(monkeypatch, at):
+    """the picture plan runs ahead on the shadow context's guess; when the encoder's own state does not confirm it (here: forced for
+    picture `at`) everything enqueued from there on is thrown away and the pictures are planned from the real context one at a time:
+    same bitstream"""
+    monkeypatch.setenv("XB200_DROPIN_FORCE_SYNC_AT", str(at))
+    monkeypatch.setenv("XB200_QUIET", "1")
+    c, yuv = tracedata.clip_yuv("cif", 25, **QCIF)
+    ref = rh.encode_clip(yuv, 25, c.w, c.h, in_depth=c.depth, preset="fast", threads=2).bitstream
+    got, st = api_encode(yuv, 25, c.w, c.h, c.depth, "fast", 2)
+    assert st.device_path == 1 and st.pictures == 25
     assert np.array_equal(got, ref)
 
 
